@@ -1,0 +1,231 @@
+"""ctypes bindings for the CPU oracle (TEST INFRASTRUCTURE).
+
+Loaded only by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs — never by the
+product package.  `port` = oracle/liborb_oracle.so (restatement, built from oracle/*.cc);
+`ref` = oracle/_ref/liborb_ref.so (reference ORBextractor.cc compiled verbatim; prebuilt in the
+authoring container, may be absent elsewhere)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4")])
+MP_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"),
+                     ("level", "<i4"), ("track_in_view", "<i4"), ("bad", "<i4")])
+
+
+class Bounds(C.Structure):
+    _fields_ = [("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
+
+
+def build_oracle(quiet: bool = True) -> None:
+    """Compile the restatement (and _ref when /root/reference exists).  Building the checker
+    is not using it."""
+    subprocess.run(["make", "-C", ORACLE_DIR], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class OracleExtractor:
+    """Handle on either oracle library's extractor API (oracle/orb_oracle.h)."""
+
+    def __init__(self, lib, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7, has_stages=True):
+        self.lib, self.nlevels, self.nfeatures, self.has_stages = lib, nlevels, nfeatures, has_stages
+        lib.oo_create.restype = C.c_void_p
+        lib.oo_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        lib.oo_destroy.argtypes = [C.c_void_p]
+        lib.oo_extract.restype = C.c_int
+        lib.oo_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p,
+                                   C.c_void_p, C.c_int, C.c_void_p]
+        lib.oo_pyramid_level.restype = C.c_int
+        lib.oo_pyramid_level.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int),
+                                         C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+        lib.oo_scale_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        self.h = lib.oo_create(nfeatures, scale, nlevels, ini_th, min_th)
+        assert self.h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.oo_destroy(self.h)
+            self.h = None
+
+    def extract(self, img: np.ndarray):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        cap = self.nfeatures + 4 * self.nlevels + 16
+        kps = np.zeros(cap, dtype=KP_DTYPE)
+        desc = np.zeros((cap, 32), dtype=np.uint8)
+        counts = np.zeros(self.nlevels, dtype=np.int32)
+        n = self.lib.oo_extract(self.h, img.ctypes.data, img.shape[0], img.shape[1], img.strides[0],
+                                kps.ctypes.data, desc.ctypes.data, cap, counts.ctypes.data)
+        assert n >= 0
+        return kps[:n].copy(), desc[:n].copy(), counts
+
+    def pyramid_level(self, level: int, border: int = 19) -> np.ndarray:
+        """Bordered level buffer ((h+38) x (w+38)) of the last extract call."""
+        data, w, h, step = C.c_void_p(), C.c_int(), C.c_int(), C.c_size_t()
+        rc = self.lib.oo_pyramid_level(self.h, level, C.byref(data), C.byref(w), C.byref(h), C.byref(step))
+        assert rc == 0
+        base = data.value - border * step.value - border
+        rows = h.value + 2 * border
+        buf = (C.c_uint8 * (rows * step.value)).from_address(base)
+        a = np.frombuffer(buf, dtype=np.uint8).reshape(rows, step.value)[:, : w.value + 2 * border]
+        return a.copy()
+
+    def scale_tables(self):
+        out = [np.zeros(self.nlevels, dtype=np.float32) for _ in range(4)]
+        self.lib.oo_scale_tables(self.h, *[o.ctypes.data for o in out])
+        return out
+
+    def features_per_level(self):
+        out = np.zeros(self.nlevels, dtype=np.int32)
+        self.lib.oo_features_per_level.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib.oo_features_per_level(self.h, out.ctypes.data)
+        return out
+
+    # stage taps (restatement only)
+    def candidates(self, level: int):
+        cap = 1 << 17
+        x, y, s = (np.zeros(cap, dtype=np.int32) for _ in range(3))
+        f = self.lib.oo_stage_candidates
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        n = f(self.h, level, x.ctypes.data, y.ctypes.data, s.ctypes.data, cap)
+        assert n <= cap
+        return x[:n].copy(), y[:n].copy(), s[:n].copy()
+
+    def blurred(self, level: int, w: int, h: int):
+        out = np.zeros((h, w), dtype=np.uint8)
+        f = self.lib.oo_stage_blurred
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        return out if f(self.h, level, out.ctypes.data) else None
+
+    def level_keypoints(self, level: int):
+        cap = self.nfeatures + 64
+        x, y = (np.zeros(cap, dtype=np.int32) for _ in range(2))
+        r, a = (np.zeros(cap, dtype=np.float32) for _ in range(2))
+        f = self.lib.oo_stage_level_keypoints
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int]
+        n = f(self.h, level, x.ctypes.data, y.ctypes.data, r.ctypes.data, a.ctypes.data, cap)
+        return x[:n].copy(), y[:n].copy(), r[:n].copy(), a[:n].copy()
+
+
+_libs = {}
+
+
+def load(kind: str = "port"):
+    """kind: 'port' (restatement) or 'ref' (verbatim reference build; None if absent)."""
+    if kind in _libs:
+        return _libs[kind]
+    path = os.path.join(ORACLE_DIR, "liborb_oracle.so" if kind == "port" else "_ref/liborb_ref.so")
+    if kind == "port" and not os.path.exists(path):
+        build_oracle()
+    lib = C.CDLL(path) if os.path.exists(path) else None
+    _libs[kind] = lib
+    return lib
+
+
+def extractor(kind="port", **kw):
+    lib = load(kind)
+    if lib is None:
+        return None
+    return OracleExtractor(lib, has_stages=(kind == "port"), **kw)
+
+
+# ---- matcher oracle -------------------------------------------------------------------------
+
+def distance(a: np.ndarray, b: np.ndarray) -> int:
+    lib = load("port")
+    lib.om_distance.restype = C.c_int
+    lib.om_distance.argtypes = [C.c_void_p, C.c_void_p]
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    return lib.om_distance(a.ctypes.data, b.ctypes.data)
+
+
+def bruteforce(q: np.ndarray, t: np.ndarray, ratio: float = 0.9, th: int = 50):
+    lib = load("port")
+    q = np.ascontiguousarray(q, dtype=np.uint8)
+    t = np.ascontiguousarray(t, dtype=np.uint8)
+    nq, nt = q.shape[0], t.shape[0]
+    idx, d1, d2 = (np.zeros(nq, dtype=np.int32) for _ in range(3))
+    lib.om_bruteforce.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.om_bruteforce(q.ctypes.data, nq, t.ctypes.data, nt, ratio, th, idx.ctypes.data, d1.ctypes.data,
+                      d2.ctypes.data)
+    return idx, d1, d2
+
+
+def features_in_area(kx, ky, koct, bounds, x, y, r, min_level, max_level):
+    lib = load("port")
+    kx = np.ascontiguousarray(kx, dtype=np.float32)
+    ky = np.ascontiguousarray(ky, dtype=np.float32)
+    koct = np.ascontiguousarray(koct, dtype=np.int32)
+    out = np.zeros(len(kx) + 1, dtype=np.int32)
+    f = lib.om_features_in_area
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, Bounds, C.c_float, C.c_float, C.c_float,
+                  C.c_int, C.c_int, C.c_void_p, C.c_int]
+    n = f(kx.ctypes.data, ky.ctypes.data, koct.ctypes.data, len(kx), Bounds(*bounds), x, y, r, min_level,
+          max_level, out.ctypes.data, len(out))
+    return out[:n].copy()
+
+
+def search_for_initialization(k1, d1, k2, d2, bounds2, prev_xy, window=100, nnratio=0.9, check_ori=True):
+    lib = load("port")
+    k1 = np.ascontiguousarray(k1, dtype=KP_DTYPE)
+    k2 = np.ascontiguousarray(k2, dtype=KP_DTYPE)
+    d1 = np.ascontiguousarray(d1, dtype=np.uint8)
+    d2 = np.ascontiguousarray(d2, dtype=np.uint8)
+    prev = np.ascontiguousarray(prev_xy, dtype=np.float32).copy()
+    m12 = np.zeros(len(k1), dtype=np.int32)
+    f = lib.om_search_for_initialization
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, Bounds, C.c_void_p,
+                  C.c_int, C.c_float, C.c_int, C.c_void_p]
+    n = f(k1.ctypes.data, d1.ctypes.data, len(k1), k2.ctypes.data, d2.ctypes.data, len(k2), Bounds(*bounds2),
+          prev.ctypes.data, window, nnratio, int(check_ori), m12.ctypes.data)
+    return n, m12, prev
+
+
+def search_by_projection_points(k, d, u_right, bounds, scale_factors, mp, mp_desc, mp_obs, th, nnratio,
+                                frame_mp=None, frame_mp_obs=None):
+    lib = load("port")
+    k = np.ascontiguousarray(k, dtype=KP_DTYPE)
+    d = np.ascontiguousarray(d, dtype=np.uint8)
+    n = len(k)
+    u_right = np.ascontiguousarray(u_right, dtype=np.float32)
+    sf = np.ascontiguousarray(scale_factors, dtype=np.float32)
+    mp = np.ascontiguousarray(mp, dtype=MP_DTYPE)
+    mp_desc = np.ascontiguousarray(mp_desc, dtype=np.uint8)
+    mp_obs = np.ascontiguousarray(mp_obs, dtype=np.int32)
+    fmp = np.full(n, -1, dtype=np.int32) if frame_mp is None else np.ascontiguousarray(frame_mp, dtype=np.int32).copy()
+    fobs = np.zeros(n, dtype=np.int32) if frame_mp_obs is None else np.ascontiguousarray(frame_mp_obs, dtype=np.int32)
+    f = lib.om_search_by_projection_points
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, Bounds, C.c_void_p, C.c_int, C.c_void_p,
+                  C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    nm = f(k.ctypes.data, d.ctypes.data, u_right.ctypes.data, n, Bounds(*bounds), sf.ctypes.data, len(sf),
+           mp.ctypes.data, mp_desc.ctypes.data, mp_obs.ctypes.data, len(mp), th, nnratio, fmp.ctypes.data,
+           fobs.ctypes.data)
+    return nm, fmp
+
+
+def three_maxima(counts):
+    lib = load("port")
+    c = np.ascontiguousarray(counts, dtype=np.int32)
+    i1, i2, i3 = C.c_int(), C.c_int(), C.c_int()
+    lib.om_three_maxima.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.om_three_maxima(c.ctypes.data, len(c), C.byref(i1), C.byref(i2), C.byref(i3))
+    return i1.value, i2.value, i3.value
