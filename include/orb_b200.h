@@ -1,0 +1,189 @@
+/* orb_b200.h — C ABI of the B200-native ORB front end (liborb_b200.so).
+ *
+ * Drop-in boundary for the per-frame hot path of AlterPang/Multi_ORB_SLAM: every entry point
+ * names the reference interface it replaces (paths relative to the reference tree).  The
+ * reference has no FFI of its own (single C++ process); include/ORBextractor.h and
+ * include/ORBmatcher.h in this repo are the C++ classes, shaped like the reference's, that a
+ * maintainer would compile in place of src/ORBextractor.cc / the hot members of
+ * src/ORBmatcher.cc.  See INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes; int status return (0 = ok, <0 = error, see ORBX_E_*);
+ * nothing throws across the boundary.  "_host" entry points take host buffers and include the
+ * H2D/D2H copies; "_device" entry points take device pointers valid on the handle's GPU and are
+ * asynchronous on the handle's stream (orbx_sync to wait).  There is no CPU fallback: without a
+ * CUDA device every create call fails with ORBX_E_CUDA.
+ */
+#ifndef ORB_B200_H
+#define ORB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBX_OK 0
+#define ORBX_E_INVALID (-1)  /* bad argument / unsupported geometry */
+#define ORBX_E_CUDA (-2)     /* CUDA runtime error (see orbx_last_error) */
+#define ORBX_E_CAPACITY (-3) /* caller-provided capacity too small */
+#define ORBX_E_STATE (-4)    /* call order (e.g. stage tap before extract) */
+
+#define ORBX_MAX_LEVELS 16
+
+/* cv::KeyPoint without class_id (reference: include/ORBextractor.h:68-70 outputs
+ * std::vector<cv::KeyPoint>; fields written at src/ORBextractor.cc:838-848,1096-1103). */
+typedef struct {
+  float x, y;     /* pt, level-0 pixel coordinates (scaled by mvScaleFactor[octave]) */
+  float size;     /* (int)(31 * mvScaleFactor[octave]) */
+  float angle;    /* IC_Angle, degrees [0,360) */
+  float response; /* FAST score */
+  int32_t octave; /* pyramid level */
+} orbx_keypoint;
+
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+ * (src/ORBextractor.cc:411-471) plus the geometry the device workspace is sized for. */
+typedef struct {
+  int32_t nfeatures;
+  float scale_factor;
+  int32_t nlevels;
+  int32_t ini_th_fast;
+  int32_t min_th_fast;
+  int32_t width, height; /* image size every frame of this handle has */
+  int32_t max_batch;     /* frames processed per launch group (workspace size) */
+  int32_t device;        /* CUDA device ordinal, -1 = current */
+} orbx_config;
+
+typedef struct orbx_extractor orbx_extractor;
+
+/* ---- extractor: replaces class ORBextractor (include/ORBextractor.h:45-112) ---------------- */
+
+int orbx_create(const orbx_config* cfg, orbx_extractor** out);
+void orbx_destroy(orbx_extractor* h);
+/* Last error text of this handle (or of the failed create when h == NULL). */
+const char* orbx_last_error(const orbx_extractor* h);
+
+/* GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares
+ * (include/ORBextractor.h:71-90); each array nlevels floats, NULL to skip. */
+int orbx_get_scale_tables(const orbx_extractor* h, float* scale, float* inv_scale, float* sigma2,
+                          float* inv_sigma2);
+/* mnFeaturesPerLevel (src/ORBextractor.cc:436-447). */
+int orbx_get_features_per_level(const orbx_extractor* h, int32_t* out);
+/* Safe per-frame output capacity: nfeatures + 3*nlevels (the octree may overshoot each level's
+ * quota by up to 3, src/ORBextractor.cc:731-732). */
+int orbx_max_keypoints(const orbx_extractor* h);
+
+/* ORBextractor::operator()(image, mask, keypoints, descriptors) (src/ORBextractor.cc:1044-1107)
+ * for ONE frame in host memory.  image: rows x cols u8, `stride` bytes per row.  kps / desc have
+ * room for `cap` keypoints (desc: cap x 32 bytes).  *n receives the count. */
+int orbx_extract(orbx_extractor* h, const uint8_t* image, int rows, int cols, size_t stride,
+                 orbx_keypoint* kps, uint8_t* desc, int cap, int* n);
+
+/* The same for a batch of frames (one camera stream, or many cameras with identical settings):
+ * frame f starts at images + f*frame_stride.  Outputs are strided by `cap` keypoints per frame;
+ * counts[f] receives frame f's count.  Host buffers; pinned memory makes the copies async. */
+int orbx_extract_batch_host(orbx_extractor* h, const uint8_t* images, int n_frames, size_t frame_stride,
+                            size_t row_stride, orbx_keypoint* kps, uint8_t* desc, int32_t* counts, int cap);
+
+/* Device-resident variant: all pointers are device pointers; asynchronous on the handle's stream.
+ * counts[f] may exceed cap (the count is exact, the arrays are clamped) — check after orbx_sync. */
+int orbx_extract_batch_device(orbx_extractor* h, const uint8_t* d_images, int n_frames, size_t frame_stride,
+                              size_t row_stride, orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_counts,
+                              int cap);
+int orbx_sync(orbx_extractor* h);
+/* cudaStream_t of the handle as an opaque pointer (to order foreign work after it). */
+void* orbx_stream(orbx_extractor* h);
+
+/* mvImagePyramid[level] (public member, include/ORBextractor.h:92) of frame `frame` of the last
+ * batch, copied to host: with_border != 0 returns the (w+38) x (h+38) buffer including the
+ * EDGE_THRESHOLD border, else the w x h interior.  dst may be NULL to query the size. */
+int orbx_get_pyramid_level(orbx_extractor* h, int frame, int level, int with_border, uint8_t* dst,
+                           size_t dst_stride, int* w, int* hgt);
+
+/* Stage taps for parity tests (frame of the last batch): FAST candidates fed to the octree in
+ * vToDistributeKeys order ((x,y) relative to (16,16)); the blurred working image. */
+int orbx_debug_candidates(orbx_extractor* h, int frame, int level, int32_t* x, int32_t* y, int32_t* score,
+                          int cap, int* n);
+int orbx_debug_blurred(orbx_extractor* h, int frame, int level, uint8_t* dst, size_t dst_stride);
+
+/* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
+long long orbx_launch_count(const orbx_extractor* h);
+/* Device time in ms of the most recent *_batch_* call's kernels, by stage (CUDA events on the
+ * handle's stream; valid after orbx_sync).  stages: 0 pyramid, 1 fast, 2 octree, 3 blur,
+ * 4 orientation+descriptor.  Requires orbx_set_profiling(h, 1) before the call. */
+int orbx_set_profiling(orbx_extractor* h, int enable);
+int orbx_stage_times_ms(orbx_extractor* h, float* ms5);
+
+/* ---- matcher: replaces the hot members of class ORBmatcher (include/ORBmatcher.h:37-137) --- */
+
+typedef struct orbm_matcher orbm_matcher;
+
+int orbm_create(int device, orbm_matcher** out);
+void orbm_destroy(orbm_matcher* m);
+const char* orbm_last_error(const orbm_matcher* m);
+int orbm_sync(orbm_matcher* m);
+long long orbm_launch_count(const orbm_matcher* m);
+
+/* ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:3994-4010) for n independent pairs:
+ * out[i] = Hamming(a[i], b[i]) over 32-byte rows.  Host buffers. */
+int orbm_distance_pairs_host(orbm_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* out);
+
+/* Brute-force best / second-best Hamming scan with the ratio test of the Search* functions
+ * (src/ORBmatcher.cc:895-924 without the window): for each query, targets are scanned in
+ * ascending index with strict-< updates; out_idx = best target if best <= th_dist and
+ * (float)best < ratio*(float)second, else -1; out_d1/out_d2 = best / second-best distance
+ * (256 when absent).  _device: device pointers, async. */
+int orbm_bruteforce_device(orbm_matcher* m, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, float ratio,
+                           int th_dist, int32_t* d_idx, int32_t* d_d1, int32_t* d_d2);
+int orbm_bruteforce_host(orbm_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, float ratio,
+                         int th_dist, int32_t* idx, int32_t* d1, int32_t* d2);
+
+/* Frame grid bounds mnMinX/mnMaxX/mnMinY/mnMaxY (src/Frame.cc:262-278). */
+typedef struct {
+  float min_x, max_x, min_y, max_y;
+} orbm_bounds;
+
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)
+ * (src/ORBmatcher.cc:868-983) for a batch of independent frame pairs.  Pair p uses keypoints
+ * k1 + p*cap (n1[p] valid), k2 + p*cap (n2[p] valid), descriptors likewise (cap x 32 bytes per
+ * frame), prev_xy + p*cap*2 (vbPrevMatched, in/out), matches12 + p*cap (out, -1 = none);
+ * nmatches[p] out.  mfNNratio = nnratio, mbCheckOrientation = check_ori.  Device pointers. */
+int orbm_search_for_initialization_device(orbm_matcher* m, int n_pairs, int cap, const orbx_keypoint* d_k1,
+                                          const uint8_t* d_d1, const int32_t* d_n1, const orbx_keypoint* d_k2,
+                                          const uint8_t* d_d2, const int32_t* d_n2, orbm_bounds bounds2,
+                                          float* d_prev_xy, int window, float nnratio, int check_ori,
+                                          int32_t* d_matches12, int32_t* d_nmatches);
+int orbm_search_for_initialization_host(orbm_matcher* m, int n_pairs, int cap, const orbx_keypoint* k1,
+                                        const uint8_t* d1, const int32_t* n1, const orbx_keypoint* k2,
+                                        const uint8_t* d2, const int32_t* n2, orbm_bounds bounds2, float* prev_xy,
+                                        int window, float nnratio, int check_ori, int32_t* matches12,
+                                        int32_t* nmatches);
+
+/* Flattened MapPoint fields read by SearchByProjection(Frame&, const vector<MapPoint*>&, th)
+ * (src/ORBmatcher.cc:62-149): mTrackProjX/Y/XR, mTrackViewCos, mnTrackScaleLevel,
+ * mbTrackInView, isBad(). */
+typedef struct {
+  float proj_x, proj_y, proj_xr;
+  float view_cos;
+  int32_t level;
+  int32_t track_in_view;
+  int32_t bad;
+} orbm_mappoint;
+
+/* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th)
+ * (src/ORBmatcher.cc:62-157).  Frame side: keypoints k[n] (mvKeysUn), descriptors, u_right[n]
+ * (mvuRight, may be NULL = all -1), scale_factors[nlevels] (mvScaleFactors), frame_mp[n] in/out
+ * (index of the map point held by each keypoint, -1 = none; F.mvpMapPoints), frame_mp_obs[n]
+ * (Observations()>0 of the point initially held; may be NULL).  Map-point side: mp[nmp],
+ * mp_desc (nmp x 32), mp_obs[nmp] (Observations()>0; NULL = all 1).  *nmatches out.  Host buffers. */
+int orbm_search_by_projection_points_host(orbm_matcher* m, const orbx_keypoint* k, const uint8_t* desc,
+                                          const float* u_right, int n, orbm_bounds bounds,
+                                          const float* scale_factors, int nlevels, const orbm_mappoint* mp,
+                                          const uint8_t* mp_desc, const int32_t* mp_obs, int nmp, float th,
+                                          float nnratio, int32_t* frame_mp, const int32_t* frame_mp_obs,
+                                          int* nmatches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORB_B200_H */

@@ -1,0 +1,100 @@
+"""ctypes binding of the C-ABI library (include/orb_b200.h).  No CPU fallback: if the CUDA library
+has not been built, importing this module raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liborb_b200.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4")])
+MP_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"),
+                     ("level", "<i4"), ("track_in_view", "<i4"), ("bad", "<i4")])
+
+OK, E_INVALID, E_CUDA, E_CAPACITY, E_STATE = 0, -1, -2, -3, -4
+
+
+class OrbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"orb_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("width", C.c_int32),
+                ("height", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32)]
+
+
+class Bounds(C.Structure):
+    _fields_ = [("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -m multi_orb_slam_b200.build` "
+        "(__graft_entry__.build()).  multi_orb_slam_b200 has no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_SIGS = {
+    "orbx_create": (_i, [C.POINTER(Config), C.POINTER(_vp)]),
+    "orbx_destroy": (None, [_vp]),
+    "orbx_last_error": (C.c_char_p, [_vp]),
+    "orbx_get_scale_tables": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "orbx_get_features_per_level": (_i, [_vp, _vp]),
+    "orbx_max_keypoints": (_i, [_vp]),
+    "orbx_extract": (_i, [_vp, _vp, _i, _i, _sz, _vp, _vp, _i, C.POINTER(_i)]),
+    "orbx_extract_batch_host": (_i, [_vp, _vp, _i, _sz, _sz, _vp, _vp, _vp, _i]),
+    "orbx_extract_batch_device": (_i, [_vp, _vp, _i, _sz, _sz, _vp, _vp, _vp, _i]),
+    "orbx_sync": (_i, [_vp]),
+    "orbx_stream": (_vp, [_vp]),
+    "orbx_get_pyramid_level": (_i, [_vp, _i, _i, _i, _vp, _sz, C.POINTER(_i), C.POINTER(_i)]),
+    "orbx_debug_candidates": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, C.POINTER(_i)]),
+    "orbx_debug_blurred": (_i, [_vp, _i, _i, _vp, _sz]),
+    "orbx_launch_count": (C.c_longlong, [_vp]),
+    "orbx_set_profiling": (_i, [_vp, _i]),
+    "orbx_stage_times_ms": (_i, [_vp, _vp]),
+    "orbm_create": (_i, [_i, C.POINTER(_vp)]),
+    "orbm_destroy": (None, [_vp]),
+    "orbm_last_error": (C.c_char_p, [_vp]),
+    "orbm_sync": (_i, [_vp]),
+    "orbm_launch_count": (C.c_longlong, [_vp]),
+    "orbm_distance_pairs_host": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "orbm_bruteforce_device": (_i, [_vp, _vp, _i, _vp, _i, _f, _i, _vp, _vp, _vp]),
+    "orbm_bruteforce_host": (_i, [_vp, _vp, _i, _vp, _i, _f, _i, _vp, _vp, _vp]),
+    "orbm_search_for_initialization_device": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, Bounds, _vp, _i, _f, _i,
+                                                  _vp, _vp]),
+    "orbm_search_for_initialization_host": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, Bounds, _vp, _i, _f, _i,
+                                                _vp, _vp]),
+    "orbm_search_by_projection_points_host": (_i, [_vp, _vp, _vp, _vp, _i, Bounds, _vp, _i, _vp, _vp, _vp, _i, _f, _f,
+                                                  _vp, _vp, C.POINTER(_i)]),
+}
+EXPORTS = tuple(_SIGS)
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)  # AttributeError here = header/library mismatch
+    _fn.restype, _fn.argtypes = _res, _args
+
+
+def check_x(handle, rc: int) -> None:
+    if rc != OK:
+        raise OrbError(rc, (lib.orbx_last_error(handle) or b"").decode())
+
+
+def check_m(handle, rc: int) -> None:
+    if rc != OK:
+        raise OrbError(rc, (lib.orbm_last_error(handle) or b"").decode())
+
+
+def ptr(a) -> int:
+    """Raw address of a numpy array or torch tensor (device pointers pass through unchanged)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()

@@ -1,0 +1,523 @@
+// C-ABI of the extractor (include/orb_b200.h): handle, geometry, HBM workspace, launches.
+// Replaces class ORBextractor (reference include/ORBextractor.h:45-112, src/ORBextractor.cc).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/orb_b200.h"
+#include "extract_kernels.h"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+inline int cv_round(float v) { return (int)lrintf(v); }  // cvRound: round-half-even
+inline int cv_round(double v) { return (int)lrint(v); }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct orbx_extractor {
+  orbx_config cfg;
+  int device;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long long launches = 0;
+  std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+  std::vector<int> quota;
+  orbk::OrbGeomHost gh;
+  // HBM workspace (max_batch frames)
+  uint8_t* d_pyr = nullptr;
+  uint8_t* d_blur = nullptr;
+  uint32_t* d_cand = nullptr;
+  int* d_cell_count = nullptr;
+  uint32_t* d_keys = nullptr;
+  uint16_t* d_knode = nullptr;
+  uint32_t* d_sel = nullptr;
+  int* d_sel_count = nullptr;
+  // staging for the host entry points
+  uint8_t* d_img = nullptr;
+  orbx_keypoint* d_kps = nullptr;
+  uint8_t* d_desc = nullptr;
+  int* d_counts = nullptr;
+  int stage_cap = 0;
+  int last_batch = 0;  // frames resident in the workspace (for taps)
+  bool profiling = false;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ev_valid = false;
+
+  bool check(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+  }
+};
+
+namespace {
+
+// ORBextractor ctor tables, src/ORBextractor.cc:411-447
+void build_tables(orbx_extractor* h) {
+  const int nl = h->cfg.nlevels;
+  const double sf = (double)h->cfg.scale_factor;  // the reference keeps the float arg in a double member
+  h->scale.assign(nl, 1.f);
+  h->sigma2.assign(nl, 1.f);
+  for (int i = 1; i < nl; ++i) {
+    h->scale[i] = (float)(h->scale[i - 1] * sf);
+    h->sigma2[i] = h->scale[i] * h->scale[i];
+  }
+  h->inv_scale.resize(nl);
+  h->inv_sigma2.resize(nl);
+  for (int i = 0; i < nl; ++i) {
+    h->inv_scale[i] = 1.0f / h->scale[i];
+    h->inv_sigma2[i] = 1.0f / h->sigma2[i];
+  }
+  h->quota.resize(nl);
+  const float factor = (float)(1.0f / sf);
+  float desired = h->cfg.nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nl));
+  int sum = 0;
+  for (int l = 0; l < nl - 1; ++l) {
+    h->quota[l] = cv_round(desired);
+    sum += h->quota[l];
+    desired *= factor;
+  }
+  h->quota[nl - 1] = std::max(h->cfg.nfeatures - sum, 0);
+}
+
+// cv::resize INTER_LINEAR tables (OpenCV imgproc/resize.cpp), level l <- l-1
+void build_resize_tables(int sw, int sh, int dw, int dh, std::vector<OrbXTap>& xt, std::vector<OrbYTap>& yt) {
+  const double scale_x = 1.0 / ((double)dw / sw), scale_y = 1.0 / ((double)dh / sh);
+  for (int dx = 0; dx < dw; ++dx) {
+    float fx = (float)((dx + 0.5) * scale_x - 0.5);
+    int sx = (int)std::floor(fx);
+    fx -= sx;
+    if (sx < 0) { fx = 0; sx = 0; }
+    if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+    OrbXTap t;
+    t.sx = (unsigned short)sx;
+    t.a0 = (unsigned short)cv_round((1.f - fx) * 2048.f);
+    t.a1 = (unsigned short)cv_round(fx * 2048.f);
+    t.pad = 0;
+    xt.push_back(t);
+  }
+  for (int dy = 0; dy < dh; ++dy) {
+    float fy = (float)((dy + 0.5) * scale_y - 0.5);
+    int sy = (int)std::floor(fy);
+    fy -= sy;
+    OrbYTap t;
+    t.sy0 = (unsigned short)std::min(std::max(sy, 0), sh - 1);
+    t.sy1 = (unsigned short)std::min(std::max(sy + 1, 0), sh - 1);
+    t.b0 = (unsigned short)cv_round((1.f - fy) * 2048.f);
+    t.b1 = (unsigned short)cv_round(fy * 2048.f);
+    yt.push_back(t);
+  }
+}
+
+// Level sizes (:1113-1117), FAST cell grid (:774-807), octree roots (:544-564), HBM offsets.
+bool build_geometry(orbx_extractor* h, std::vector<OrbCell>& cells, std::vector<OrbXTap>& xt,
+                    std::vector<OrbYTap>& yt) {
+  OrbGeom& g = h->gh.g;
+  std::memset(&g, 0, sizeof(g));
+  const int nl = h->cfg.nlevels;
+  g.nlevels = nl;
+  g.width = h->cfg.width;
+  g.height = h->cfg.height;
+  g.ini_th = std::min(std::max(h->cfg.ini_th_fast, 0), 255);
+  g.min_th = std::min(std::max(h->cfg.min_th_fast, 0), 255);
+  if (g.min_th > g.ini_th) { h->err = "minThFAST > iniThFAST is not supported"; return false; }
+  size_t pyr_off = 0, blur_off = 0, cand_off = 0, key_off = 0;
+  int sel_off = 0, tile_base = 0, max_cells_level = 0;
+  g.ot_cap = 0;
+  for (int l = 0; l < nl; ++l) {
+    OrbLevelGeom& L = g.lv[l];
+    L.w = cv_round((float)g.width * h->inv_scale[l]);
+    L.h = cv_round((float)g.height * h->inv_scale[l]);
+    if (L.w > 4000 || L.h > 4000) { h->err = "image larger than 4000 px is not supported"; return false; }
+    L.pitch = (int)align_up(L.w + 2 * ORB_EDGE, 16);
+    L.bpitch = (int)align_up(L.w, 16);
+    L.pyr_off = (unsigned)pyr_off;
+    pyr_off += align_up((size_t)L.pitch * (L.h + 2 * ORB_EDGE), 256);
+    L.blur_off = (unsigned)blur_off;
+    blur_off += align_up((size_t)L.bpitch * L.h, 256);
+    L.scale = h->scale[l];
+    L.patch_size = (float)(int)(31 * h->scale[l]);  // PATCH_SIZE*mvScaleFactor[level] -> int (:838)
+    L.quota = h->quota[l];
+    // cell grid
+    const int minB = ORB_MIN_BORDER, maxBX = L.w - ORB_EDGE + 3, maxBY = L.h - ORB_EDGE + 3;
+    const float width = (float)(maxBX - minB), height = (float)(maxBY - minB);
+    L.n_cols = (int)(width / 30.f);
+    L.n_rows = (int)(height / 30.f);
+    if (L.n_cols < 1 || L.n_rows < 1) {
+      h->err = "pyramid level " + std::to_string(l) + " is too small for a 30-px FAST cell";
+      return false;
+    }
+    L.w_cell = (int)std::ceil(width / L.n_cols);
+    L.h_cell = (int)std::ceil(height / L.n_rows);
+    if (L.w_cell + 6 > ORB_CELL_MAX || L.h_cell + 6 > ORB_CELL_MAX) { h->err = "FAST cell too large"; return false; }
+    L.cell_base = (int)cells.size();
+    for (int i = 0; i < L.n_rows; ++i) {
+      const float iniY = (float)(minB + i * L.h_cell);
+      float maxY = iniY + L.h_cell + 6;
+      if (iniY >= maxBY - 3) continue;
+      if (maxY > maxBY) maxY = (float)maxBY;
+      for (int j = 0; j < L.n_cols; ++j) {
+        const float iniX = (float)(minB + j * L.w_cell);
+        float maxX = iniX + L.w_cell + 6;
+        if (iniX >= maxBX - 6) continue;
+        if (maxX > maxBX) maxX = (float)maxBX;
+        OrbCell c;
+        c.level = (short)l;
+        c.ini_x = (short)iniX;
+        c.ini_y = (short)iniY;
+        c.cw = (short)((int)maxX - (int)iniX);
+        c.ch = (short)((int)maxY - (int)iniY);
+        c.off_x = (short)(j * L.w_cell);
+        c.off_y = (short)(i * L.h_cell);
+        c.slot = (short)((int)cells.size() - L.cell_base);
+        cells.push_back(c);
+      }
+    }
+    L.n_cells = (int)cells.size() - L.cell_base;
+    max_cells_level = std::max(max_cells_level, L.n_cells);
+    // NMS keeps no two 8-adjacent pixels: at most ceil(w/2)*ceil(h/2) per tested w_cell x h_cell area
+    L.cand_cap = ((L.w_cell + 1) / 2) * ((L.h_cell + 1) / 2);
+    L.cand_off = (unsigned)cand_off;
+    L.key_off = (unsigned)key_off;
+    L.key_cap = L.n_cells * L.cand_cap;
+    cand_off += (size_t)L.key_cap;
+    key_off += (size_t)L.key_cap;
+    // octree roots
+    const int W = maxBX - minB, H = maxBY - minB;
+    OtRoots& r = L.roots;
+    r.n_ini = (int)std::round((float)W / (float)H);
+    if (r.n_ini < 1 || r.n_ini > OT_MAX_ROOTS) { h->err = "unsupported aspect ratio for the octree roots"; return false; }
+    r.hx = (float)W / r.n_ini;
+    for (int i = 0; i <= r.n_ini; ++i) r.root_x[i] = (int)(r.hx * (float)i);
+    r.height = H;
+    L.sel_cap = std::max(L.quota + 3, 4 * r.n_ini) + 1;
+    L.sel_off = sel_off;
+    sel_off += L.sel_cap;
+    g.ot_cap = std::max(g.ot_cap, L.sel_cap);
+    // blur tiles
+    L.blur_tiles_x = (L.w + ORB_BLUR_TW - 1) / ORB_BLUR_TW;
+    L.blur_tiles_y = (L.h + ORB_BLUR_TH - 1) / ORB_BLUR_TH;
+    L.blur_tile_base = tile_base;
+    tile_base += L.blur_tiles_x * L.blur_tiles_y;
+    // resize tables
+    if (l > 0) {
+      L.xtab_off = (int)xt.size();
+      L.ytab_off = (int)yt.size();
+      build_resize_tables(g.lv[l - 1].w, g.lv[l - 1].h, L.w, L.h, xt, yt);
+    }
+  }
+  if (g.ot_cap > OT_MAX_NODES) { h->err = "nfeatures too large for the octree kernel"; return false; }
+  g.n_cells = (int)cells.size();
+  g.n_blur_tiles = tile_base;
+  g.ot_scan_cap = std::max(g.ot_cap, max_cells_level) + 1;
+  g.kp_cap_frame = sel_off;
+  g.pyr_frame_bytes = pyr_off;
+  g.blur_frame_bytes = blur_off;
+  g.cand_frame_u32 = cand_off;
+  g.key_frame_u32 = key_off;
+  if (xt.empty()) { xt.push_back(OrbXTap{0, 0, 0, 0}); yt.push_back(OrbYTap{0, 0, 0, 0}); }
+  return true;
+}
+
+template <typename T> bool dev_alloc(orbx_extractor* h, T** p, size_t count, const char* what) {
+  return h->check(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)), what);
+}
+
+bool ensure_staging(orbx_extractor* h, int cap) {
+  if (h->d_kps && cap <= h->stage_cap) return true;
+  cudaFree(h->d_kps);
+  cudaFree(h->d_desc);
+  h->d_kps = nullptr;
+  h->d_desc = nullptr;
+  const size_t n = (size_t)h->cfg.max_batch * cap;
+  if (!dev_alloc(h, &h->d_kps, n, "cudaMalloc(kps staging)")) return false;
+  if (!dev_alloc(h, &h->d_desc, n * 32, "cudaMalloc(desc staging)")) return false;
+  h->stage_cap = cap;
+  return true;
+}
+
+// One batch (<= max_batch frames) of the full pipeline on the handle's stream.
+int run_batch(orbx_extractor* h, const uint8_t* d_images, int n_frames, size_t frame_stride, size_t row_stride,
+              orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_counts, int cap) {
+  cudaStream_t st = h->stream;
+  const bool prof = h->profiling;
+  if (prof) cudaEventRecord(h->ev[0], st);
+  orbk::launch_pyramid(h->gh, d_images, frame_stride, row_stride, n_frames, h->d_pyr, st, &h->launches);
+  if (prof) cudaEventRecord(h->ev[1], st);
+  orbk::launch_fast(h->gh, n_frames, h->d_pyr, h->d_cand, h->d_cell_count, st, &h->launches);
+  if (prof) cudaEventRecord(h->ev[2], st);
+  orbk::launch_octree(h->gh, n_frames, h->d_cand, h->d_cell_count, h->d_keys, h->d_knode, h->d_sel, h->d_sel_count, st,
+                      &h->launches);
+  if (prof) cudaEventRecord(h->ev[3], st);
+  orbk::launch_blur(h->gh, n_frames, h->d_pyr, h->d_blur, st, &h->launches);
+  if (prof) cudaEventRecord(h->ev[4], st);
+  orbk::launch_orient_describe(h->gh, n_frames, h->d_pyr, h->d_blur, h->d_sel, h->d_sel_count, d_kps, d_desc, d_counts,
+                               cap, st, &h->launches);
+  if (prof) { cudaEventRecord(h->ev[5], st); h->ev_valid = true; }
+  h->last_batch = n_frames;
+  if (!h->check(cudaGetLastError(), "kernel launch")) return ORBX_E_CUDA;
+  return ORBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int orbx_create(const orbx_config* cfg, orbx_extractor** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return ORBX_E_INVALID; }
+  *out = nullptr;
+  if (cfg->nfeatures < 1 || cfg->nlevels < 1 || cfg->nlevels > ORBX_MAX_LEVELS || !(cfg->scale_factor > 1.0f) ||
+      cfg->width < 1 || cfg->height < 1 || cfg->max_batch < 1) {
+    g_create_error = "invalid configuration";
+    return ORBX_E_INVALID;
+  }
+  orbx_extractor* h = new orbx_extractor();
+  h->cfg = *cfg;
+  auto fail = [&](int code) {
+    g_create_error = h->err;
+    orbx_destroy(h);
+    return code;
+  };
+  build_tables(h);
+  std::vector<OrbCell> cells;
+  std::vector<OrbXTap> xt;
+  std::vector<OrbYTap> yt;
+  if (!build_geometry(h, cells, xt, yt)) return fail(ORBX_E_INVALID);
+  int ndev = 0;
+  if (!h->check(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount") || ndev == 0) {
+    if (h->err.empty()) h->err = "no CUDA device (this library has no CPU fallback)";
+    return fail(ORBX_E_CUDA);
+  }
+  if (cfg->device >= 0) {
+    if (!h->check(cudaSetDevice(cfg->device), "cudaSetDevice")) return fail(ORBX_E_CUDA);
+  }
+  if (!h->check(cudaGetDevice(&h->device), "cudaGetDevice")) return fail(ORBX_E_CUDA);
+  if (!h->check(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail(ORBX_E_CUDA);
+  for (auto& e : h->ev)
+    if (!h->check(cudaEventCreate(&e), "cudaEventCreate")) return fail(ORBX_E_CUDA);
+  const OrbGeom& g = h->gh.g;
+  const size_t B = (size_t)cfg->max_batch;
+  bool ok = dev_alloc(h, &h->gh.d_geom, 1, "cudaMalloc(geom)") &&
+            dev_alloc(h, &h->gh.d_cells, cells.size(), "cudaMalloc(cells)") &&
+            dev_alloc(h, &h->gh.d_xtab, xt.size(), "cudaMalloc(xtab)") &&
+            dev_alloc(h, &h->gh.d_ytab, yt.size(), "cudaMalloc(ytab)") &&
+            dev_alloc(h, &h->d_pyr, B * g.pyr_frame_bytes, "cudaMalloc(pyramid)") &&
+            dev_alloc(h, &h->d_blur, B * g.blur_frame_bytes, "cudaMalloc(blur)") &&
+            dev_alloc(h, &h->d_cand, B * g.cand_frame_u32, "cudaMalloc(candidates)") &&
+            dev_alloc(h, &h->d_cell_count, B * g.n_cells, "cudaMalloc(cell counts)") &&
+            dev_alloc(h, &h->d_keys, B * g.key_frame_u32, "cudaMalloc(keys)") &&
+            dev_alloc(h, &h->d_knode, B * g.key_frame_u32, "cudaMalloc(key nodes)") &&
+            dev_alloc(h, &h->d_sel, B * g.kp_cap_frame, "cudaMalloc(selection)") &&
+            dev_alloc(h, &h->d_sel_count, B * g.nlevels, "cudaMalloc(selection counts)") &&
+            dev_alloc(h, &h->d_img, B * (size_t)cfg->width * cfg->height, "cudaMalloc(image staging)") &&
+            dev_alloc(h, &h->d_counts, B, "cudaMalloc(counts)");
+  if (!ok) return fail(ORBX_E_CUDA);
+  ok = h->check(cudaMemcpy(h->gh.d_geom, &g, sizeof(g), cudaMemcpyHostToDevice), "copy geom") &&
+       h->check(cudaMemcpy(h->gh.d_cells, cells.data(), cells.size() * sizeof(OrbCell), cudaMemcpyHostToDevice), "copy cells") &&
+       h->check(cudaMemcpy(h->gh.d_xtab, xt.data(), xt.size() * sizeof(OrbXTap), cudaMemcpyHostToDevice), "copy xtab") &&
+       h->check(cudaMemcpy(h->gh.d_ytab, yt.data(), yt.size() * sizeof(OrbYTap), cudaMemcpyHostToDevice), "copy ytab") &&
+       h->check(cudaMemset(h->d_pyr, 0, B * g.pyr_frame_bytes), "clear pyramid") &&
+       h->check(orbk::prepare_octree(g), "octree shared-memory opt-in");
+  if (!ok) return fail(ORBX_E_CUDA);
+  *out = h;
+  return ORBX_OK;
+}
+
+void orbx_destroy(orbx_extractor* h) {
+  if (!h) return;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->gh.d_geom); cudaFree(h->gh.d_cells); cudaFree(h->gh.d_xtab); cudaFree(h->gh.d_ytab);
+  cudaFree(h->d_pyr); cudaFree(h->d_blur); cudaFree(h->d_cand); cudaFree(h->d_cell_count);
+  cudaFree(h->d_keys); cudaFree(h->d_knode); cudaFree(h->d_sel); cudaFree(h->d_sel_count);
+  cudaFree(h->d_img); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* orbx_last_error(const orbx_extractor* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int orbx_get_scale_tables(const orbx_extractor* h, float* s, float* is, float* s2, float* is2) {
+  if (!h) return ORBX_E_INVALID;
+  for (int i = 0; i < h->cfg.nlevels; ++i) {
+    if (s) s[i] = h->scale[i];
+    if (is) is[i] = h->inv_scale[i];
+    if (s2) s2[i] = h->sigma2[i];
+    if (is2) is2[i] = h->inv_sigma2[i];
+  }
+  return ORBX_OK;
+}
+
+int orbx_get_features_per_level(const orbx_extractor* h, int32_t* out) {
+  if (!h || !out) return ORBX_E_INVALID;
+  for (int i = 0; i < h->cfg.nlevels; ++i) out[i] = h->quota[i];
+  return ORBX_OK;
+}
+
+int orbx_max_keypoints(const orbx_extractor* h) { return h ? h->cfg.nfeatures + 3 * h->cfg.nlevels : ORBX_E_INVALID; }
+
+int orbx_extract_batch_device(orbx_extractor* h, const uint8_t* d_images, int n_frames, size_t frame_stride,
+                              size_t row_stride, orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_counts, int cap) {
+  if (!h) return ORBX_E_INVALID;
+  if (!d_images || !d_kps || !d_desc || !d_counts || n_frames < 0 || cap < 1 || row_stride < (size_t)h->cfg.width) {
+    h->err = "invalid argument";
+    return ORBX_E_INVALID;
+  }
+  cudaSetDevice(h->device);
+  for (int f0 = 0; f0 < n_frames; f0 += h->cfg.max_batch) {
+    const int nb = std::min(h->cfg.max_batch, n_frames - f0);
+    const int rc = run_batch(h, d_images + (size_t)f0 * frame_stride, nb, frame_stride, row_stride,
+                             d_kps + (size_t)f0 * cap, d_desc + (size_t)f0 * cap * 32, d_counts + f0, cap);
+    if (rc != ORBX_OK) return rc;
+  }
+  return ORBX_OK;
+}
+
+int orbx_extract_batch_host(orbx_extractor* h, const uint8_t* images, int n_frames, size_t frame_stride,
+                            size_t row_stride, orbx_keypoint* kps, uint8_t* desc, int32_t* counts, int cap) {
+  if (!h) return ORBX_E_INVALID;
+  if (!images || !kps || !desc || !counts || n_frames < 0 || cap < 1 || row_stride < (size_t)h->cfg.width) {
+    h->err = "invalid argument";
+    return ORBX_E_INVALID;
+  }
+  cudaSetDevice(h->device);
+  if (!ensure_staging(h, cap)) return ORBX_E_CUDA;
+  const int W = h->cfg.width, H = h->cfg.height;
+  int status = ORBX_OK;
+  for (int f0 = 0; f0 < n_frames; f0 += h->cfg.max_batch) {
+    const int nb = std::min(h->cfg.max_batch, n_frames - f0);
+    const uint8_t* src = images + (size_t)f0 * frame_stride;
+    // H2D: rows packed to width (one 2D copy per batch when frames are contiguous rows)
+    if (frame_stride == row_stride * (size_t)H) {
+      if (!h->check(cudaMemcpy2DAsync(h->d_img, W, src, row_stride, W, (size_t)H * nb, cudaMemcpyHostToDevice, h->stream),
+                    "H2D images"))
+        return ORBX_E_CUDA;
+    } else {
+      for (int f = 0; f < nb; ++f)
+        if (!h->check(cudaMemcpy2DAsync(h->d_img + (size_t)f * W * H, W, src + (size_t)f * frame_stride, row_stride, W, H,
+                                        cudaMemcpyHostToDevice, h->stream), "H2D image"))
+          return ORBX_E_CUDA;
+    }
+    const int rc = run_batch(h, h->d_img, nb, (size_t)W * H, W, h->d_kps, h->d_desc, h->d_counts, cap);
+    if (rc != ORBX_OK) return rc;
+    if (!h->check(cudaMemcpyAsync(counts + f0, h->d_counts, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, h->stream), "D2H counts") ||
+        !h->check(cudaMemcpyAsync(kps + (size_t)f0 * cap, h->d_kps, sizeof(orbx_keypoint) * (size_t)nb * cap, cudaMemcpyDeviceToHost, h->stream), "D2H keypoints") ||
+        !h->check(cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, h->d_desc, (size_t)nb * cap * 32, cudaMemcpyDeviceToHost, h->stream), "D2H descriptors") ||
+        !h->check(cudaStreamSynchronize(h->stream), "extract batch"))
+      return ORBX_E_CUDA;
+    for (int f = 0; f < nb; ++f)
+      if (counts[f0 + f] > cap) {
+        h->err = "keypoint capacity too small: frame " + std::to_string(f0 + f) + " has " + std::to_string(counts[f0 + f]);
+        status = ORBX_E_CAPACITY;
+      }
+  }
+  return status;
+}
+
+int orbx_extract(orbx_extractor* h, const uint8_t* image, int rows, int cols, size_t stride, orbx_keypoint* kps,
+                 uint8_t* desc, int cap, int* n) {
+  if (!h) return ORBX_E_INVALID;
+  if (n) *n = 0;
+  if (!image || rows == 0 || cols == 0) return ORBX_OK;  // empty image: silent return (:1047-1048)
+  if (rows != h->cfg.height || cols != h->cfg.width) {
+    h->err = "image size differs from the size this handle was created for";
+    return ORBX_E_INVALID;
+  }
+  int32_t count = 0;
+  const int rc = orbx_extract_batch_host(h, image, 1, stride * (size_t)rows, stride, kps, desc, &count, cap);
+  if (n) *n = std::min(count, cap);
+  return rc;
+}
+
+int orbx_sync(orbx_extractor* h) {
+  if (!h) return ORBX_E_INVALID;
+  return h->check(cudaStreamSynchronize(h->stream), "stream synchronize") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+void* orbx_stream(orbx_extractor* h) { return h ? (void*)h->stream : nullptr; }
+
+int orbx_get_pyramid_level(orbx_extractor* h, int frame, int level, int with_border, uint8_t* dst, size_t dst_stride,
+                           int* w, int* hgt) {
+  if (!h || level < 0 || level >= h->cfg.nlevels) return ORBX_E_INVALID;
+  const OrbLevelGeom& L = h->gh.g.lv[level];
+  const int ow = L.w + (with_border ? 2 * ORB_EDGE : 0), oh = L.h + (with_border ? 2 * ORB_EDGE : 0);
+  if (w) *w = ow;
+  if (hgt) *hgt = oh;
+  if (!dst) return ORBX_OK;
+  if (frame < 0 || frame >= h->last_batch) { h->err = "no such frame in the last batch"; return ORBX_E_STATE; }
+  if (dst_stride < (size_t)ow) return ORBX_E_INVALID;
+  cudaSetDevice(h->device);
+  const uint8_t* src = h->d_pyr + (size_t)frame * h->gh.g.pyr_frame_bytes + L.pyr_off +
+                       (with_border ? 0 : (size_t)ORB_EDGE * L.pitch + ORB_EDGE);
+  if (!h->check(cudaStreamSynchronize(h->stream), "sync") ||
+      !h->check(cudaMemcpy2D(dst, dst_stride, src, L.pitch, ow, oh, cudaMemcpyDeviceToHost), "D2H pyramid level"))
+    return ORBX_E_CUDA;
+  return ORBX_OK;
+}
+
+int orbx_debug_candidates(orbx_extractor* h, int frame, int level, int32_t* x, int32_t* y, int32_t* score, int cap,
+                          int* n) {
+  if (!h || level < 0 || level >= h->cfg.nlevels || !n) return ORBX_E_INVALID;
+  if (frame < 0 || frame >= h->last_batch) return ORBX_E_STATE;
+  cudaSetDevice(h->device);
+  const OrbGeom& g = h->gh.g;
+  const OrbLevelGeom& L = g.lv[level];
+  std::vector<int> cc(L.n_cells);
+  std::vector<uint32_t> slots((size_t)L.key_cap);
+  if (!h->check(cudaStreamSynchronize(h->stream), "sync") ||
+      !h->check(cudaMemcpy(cc.data(), h->d_cell_count + (size_t)frame * g.n_cells + L.cell_base, sizeof(int) * L.n_cells, cudaMemcpyDeviceToHost), "D2H cell counts") ||
+      !h->check(cudaMemcpy(slots.data(), h->d_cand + (size_t)frame * g.cand_frame_u32 + L.cand_off, sizeof(uint32_t) * slots.size(), cudaMemcpyDeviceToHost), "D2H candidates"))
+    return ORBX_E_CUDA;
+  int k = 0;
+  for (int c = 0; c < L.n_cells; ++c)
+    for (int i = 0; i < cc[c]; ++i, ++k) {
+      if (k < cap) {
+        const uint32_t key = slots[(size_t)c * L.cand_cap + i];
+        x[k] = OT_KEY_X(key); y[k] = OT_KEY_Y(key); score[k] = OT_KEY_SCORE(key);
+      }
+    }
+  *n = k;
+  return k <= cap ? ORBX_OK : ORBX_E_CAPACITY;
+}
+
+int orbx_debug_blurred(orbx_extractor* h, int frame, int level, uint8_t* dst, size_t dst_stride) {
+  if (!h || level < 0 || level >= h->cfg.nlevels || !dst) return ORBX_E_INVALID;
+  if (frame < 0 || frame >= h->last_batch) return ORBX_E_STATE;
+  cudaSetDevice(h->device);
+  const OrbLevelGeom& L = h->gh.g.lv[level];
+  if (!h->check(cudaStreamSynchronize(h->stream), "sync") ||
+      !h->check(cudaMemcpy2D(dst, dst_stride, h->d_blur + (size_t)frame * h->gh.g.blur_frame_bytes + L.blur_off, L.bpitch,
+                             L.w, L.h, cudaMemcpyDeviceToHost), "D2H blurred level"))
+    return ORBX_E_CUDA;
+  return ORBX_OK;
+}
+
+long long orbx_launch_count(const orbx_extractor* h) { return h ? h->launches : 0; }
+
+int orbx_set_profiling(orbx_extractor* h, int enable) {
+  if (!h) return ORBX_E_INVALID;
+  h->profiling = enable != 0;
+  h->ev_valid = false;
+  return ORBX_OK;
+}
+
+int orbx_stage_times_ms(orbx_extractor* h, float* ms5) {
+  if (!h || !ms5) return ORBX_E_INVALID;
+  if (!h->ev_valid) return ORBX_E_STATE;
+  if (!h->check(cudaEventSynchronize(h->ev[5]), "event sync")) return ORBX_E_CUDA;
+  for (int i = 0; i < 5; ++i)
+    if (!h->check(cudaEventElapsedTime(&ms5[i], h->ev[i], h->ev[i + 1]), "event elapsed")) return ORBX_E_CUDA;
+  return ORBX_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,566 @@
+// Hand-written sm_100a kernels of the ORB extractor hot path.  Reference stages (all in
+// /root/reference/src/ORBextractor.cc): ComputePyramid :1109-1134 (cv::resize INTER_LINEAR +
+// copyMakeBorder REFLECT_101), per-cell cv::FAST with ini/min threshold fallback :790-830,
+// DistributeOctTree :540-764, IC_Angle :77-104, GaussianBlur 7x7 s=2 :1087,
+// computeOrbDescriptor :108-147.  All pixel work is integer and bit-exact by construction;
+// the float pieces (fastAtan2, sin/cos, rotation) use explicit round-to-nearest intrinsics so
+// nvcc cannot contract them into FMAs.
+//
+// Batch layout: every kernel covers ALL frames of a batch in one launch (blockIdx.y or .z =
+// frame) so the small per-frame work fills the 148 SMs.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "extract_kernels.h"
+#include "orb_pattern.h"
+
+namespace orbk {
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+  p = p < 0 ? -p : p;
+  return p >= n ? 2 * (n - 1) - p : p;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1/K2 level 0: input frame -> bordered level-0 buffer (copyMakeBorder REFLECT_101, :1129).
+// One thread writes one aligned 32-bit word of the bordered buffer.
+__global__ void __launch_bounds__(256) k_pyr_level0(const uint8_t* __restrict__ src, size_t frame_stride,
+                                                    size_t row_stride, const OrbGeom* __restrict__ g,
+                                                    uint8_t* __restrict__ pyr) {
+  const OrbLevelGeom& L = g->lv[0];
+  const int words = L.pitch >> 2, rows = L.h + 2 * ORB_EDGE;
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= words * rows) return;
+  const int by = id / words, wx = id - by * words;
+  const int iy = reflect101(by - ORB_EDGE, L.h);
+  const uint8_t* s = src + (size_t)blockIdx.y * frame_stride + (size_t)iy * row_stride;
+  uint32_t v = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int bx = wx * 4 + k;
+    if (bx < L.w + 2 * ORB_EDGE) v |= (uint32_t)__ldg(s + reflect101(bx - ORB_EDGE, L.w)) << (8 * k);
+  }
+  uint8_t* d = pyr + (size_t)blockIdx.y * g->pyr_frame_bytes + L.pyr_off + (size_t)by * L.pitch;
+  reinterpret_cast<uint32_t*>(d)[wx] = v;
+}
+
+// K1/K2 level l >= 1: cv::resize(level l-1 -> l, INTER_LINEAR) (:1122) fused with the
+// REFLECT_101 border (:1124): every word of the bordered buffer is computed from the source
+// level's interior; border pixels recompute their mirror pixel.
+__global__ void __launch_bounds__(256) k_pyr_resize(int level, const OrbGeom* __restrict__ g,
+                                                    const OrbXTap* __restrict__ xtab,
+                                                    const OrbYTap* __restrict__ ytab, uint8_t* __restrict__ pyr) {
+  const OrbLevelGeom& D = g->lv[level];
+  const OrbLevelGeom& S = g->lv[level - 1];
+  const int words = D.pitch >> 2, rows = D.h + 2 * ORB_EDGE;
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= words * rows) return;
+  const int by = id / words, wx = id - by * words;
+  uint8_t* frame = pyr + (size_t)blockIdx.y * g->pyr_frame_bytes;
+  const uint8_t* sp = frame + S.pyr_off + (size_t)ORB_EDGE * S.pitch + ORB_EDGE;  // source interior origin
+  const OrbYTap ty = ytab[D.ytab_off + reflect101(by - ORB_EDGE, D.h)];
+  const uint8_t* r0 = sp + (size_t)ty.sy0 * S.pitch;
+  const uint8_t* r1 = sp + (size_t)ty.sy1 * S.pitch;
+  const int b0 = ty.b0, b1 = ty.b1;
+  uint32_t v = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int bx = wx * 4 + k;
+    if (bx < D.w + 2 * ORB_EDGE) {
+      const OrbXTap tx = xtab[D.xtab_off + reflect101(bx - ORB_EDGE, D.w)];
+      // sx+1 may be the first border column when sx == sw-1; its weight a1 is 0 there
+      const int h0 = r0[tx.sx] * tx.a0 + r0[tx.sx + 1] * tx.a1;
+      const int h1 = r1[tx.sx] * tx.a0 + r1[tx.sx + 1] * tx.a1;
+      const int val = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      v |= (uint32_t)val << (8 * k);
+    }
+  }
+  reinterpret_cast<uint32_t*>(frame + D.pyr_off + (size_t)by * D.pitch)[wx] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 per-cell FAST-9/16 with NMS and the iniThFAST -> minThFAST fallback (:790-830).
+// One CTA (4 warps) per (cell, frame).  The arc measure m = max over the 16 cyclic 9-arcs of
+// min(+-diff) is threshold independent: corner iff m > th, score m-1 (OpenCV cornerScore<16>);
+// a corner survives the 3x3 NMS iff its m is strictly greater than its 8 neighbours' m
+// (neighbours outside this cell's tested area count as 0 — NMS is per cell).
+#define FAST_PITCH 80
+
+__device__ __forceinline__ int arc9_maxmin(const int (&v)[16]) {
+  int a1[16], a2[16], a4[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a1[k] = min(v[k], v[(k + 1) & 15]);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a2[k] = min(a1[k], a1[(k + 2) & 15]);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a4[k] = min(a2[k], a2[(k + 4) & 15]);
+  int best = -256;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) best = max(best, min(a4[k], v[(k + 8) & 15]));
+  return best;
+}
+
+__global__ void __launch_bounds__(128) k_fast_cells(const OrbGeom* __restrict__ g, const OrbCell* __restrict__ cells,
+                                                    const uint8_t* __restrict__ pyr, uint32_t* __restrict__ cand,
+                                                    int* __restrict__ cell_count) {
+  __shared__ __align__(16) uint8_t s_img[ORB_CELL_MAX * FAST_PITCH];
+  __shared__ __align__(16) uint8_t s_m[ORB_CELL_MAX * FAST_PITCH];
+  __shared__ uint32_t s_mask[2][ORB_CELL_MAX][3];
+  __shared__ int s_rowoff[ORB_CELL_MAX + 32];
+  __shared__ int s_cnt[2];
+
+  const OrbCell cell = cells[blockIdx.x];
+  const OrbLevelGeom& L = g->lv[cell.level];
+  const int frame = blockIdx.y;
+  const int cw = cell.cw, ch = cell.ch;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint8_t* base = pyr + (size_t)frame * g->pyr_frame_bytes + L.pyr_off +
+                        (size_t)(ORB_EDGE + cell.ini_y) * L.pitch + ORB_EDGE + cell.ini_x;
+  for (int y = warp; y < ch; y += 4)
+    for (int x = lane; x < cw; x += 32) {
+      s_img[y * FAST_PITCH + x] = base[(size_t)y * L.pitch + x];
+      s_m[y * FAST_PITCH + x] = 0;
+    }
+  if (tid < 2) s_cnt[tid] = 0;
+  __syncthreads();
+
+  const int th_lo = g->min_th, th_hi = g->ini_th;
+  // ring offsets (dx,dy), k = 0..15: (0,3),(1,3),(2,2),(3,1),(3,0),(3,-1),(2,-2),(1,-3),(0,-3),...
+  constexpr int RO[16] = {3 * FAST_PITCH,      3 * FAST_PITCH + 1,  2 * FAST_PITCH + 2,  FAST_PITCH + 3,
+                          3,                   -FAST_PITCH + 3,     -2 * FAST_PITCH + 2, -3 * FAST_PITCH + 1,
+                          -3 * FAST_PITCH,     -3 * FAST_PITCH - 1, -2 * FAST_PITCH - 2, -FAST_PITCH - 3,
+                          -3,                  FAST_PITCH - 3,      2 * FAST_PITCH - 2,  3 * FAST_PITCH - 1};
+  for (int y = 3 + warp; y < ch - 3; y += 4) {
+    for (int x = 3 + lane; x < cw - 3; x += 32) {
+      const uint8_t* p = s_img + y * FAST_PITCH + x;
+      const int c = p[0];
+      const int hi = c + th_lo, lo = c - th_lo;
+      // high-speed rejection at the LOWER threshold: each opposite pair (k,k+8) must hold a
+      // ring pixel of the arc's polarity, otherwise m <= min_th and the pixel can never be a corner
+      bool br = true, dk = true;
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        const int a = p[RO[k]], b = p[RO[k + 8]];
+        br = br && (a > hi || b > hi);
+        dk = dk && (a < lo || b < lo);
+      }
+      if (br || dk) {
+        int d[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d[k] = (int)p[RO[k]] - c;
+        int m = -256;
+        if (br) m = arc9_maxmin(d);
+        if (dk) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) d[k] = -d[k];
+          m = max(m, arc9_maxmin(d));
+        }
+        if (m > th_lo) s_m[y * FAST_PITCH + x] = (uint8_t)m;
+      }
+    }
+  }
+  __syncthreads();
+
+  // NMS + both threshold masks, one ballot word per 32 columns
+  int cnt_hi = 0, cnt_lo = 0;
+  for (int y = 3 + warp; y < ch - 3; y += 4) {
+#pragma unroll
+    for (int cchunk = 0; cchunk < 3; ++cchunk) {
+      const int x = 3 + cchunk * 32 + lane;
+      bool k_hi = false, k_lo = false;
+      if (x < cw - 3) {
+        const uint8_t* q = s_m + y * FAST_PITCH + x;
+        const int mv = q[0];
+        if (mv > th_lo) {
+          int nb = max(max((int)q[-1], (int)q[1]), max((int)q[-FAST_PITCH], (int)q[FAST_PITCH]));
+          nb = max(nb, max(max((int)q[-FAST_PITCH - 1], (int)q[-FAST_PITCH + 1]),
+                           max((int)q[FAST_PITCH - 1], (int)q[FAST_PITCH + 1])));
+          k_lo = mv > nb;
+          k_hi = k_lo && mv > th_hi;
+        }
+      }
+      const uint32_t b_hi = __ballot_sync(0xffffffffu, k_hi), b_lo = __ballot_sync(0xffffffffu, k_lo);
+      if (lane == 0) {
+        s_mask[0][y][cchunk] = b_hi;
+        s_mask[1][y][cchunk] = b_lo;
+        cnt_hi += __popc(b_hi);
+        cnt_lo += __popc(b_lo);
+      }
+    }
+  }
+  if (lane == 0) {
+    if (cnt_hi) atomicAdd(&s_cnt[0], cnt_hi);
+    if (cnt_lo) atomicAdd(&s_cnt[1], cnt_lo);
+  }
+  __syncthreads();
+  const int use = s_cnt[0] > 0 ? 0 : 1;  // :813-817 fallback only when the cell found nothing
+  const int total = s_cnt[use];
+  // row offsets: warp 0, each lane owns 3 consecutive rows (ORB_CELL_MAX <= 96)
+  if (warp == 0) {
+    int c3[3], sum = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int y = lane * 3 + r;
+      c3[r] = 0;
+      if (y >= 3 && y < ch - 3) c3[r] = __popc(s_mask[use][y][0]) + __popc(s_mask[use][y][1]) + __popc(s_mask[use][y][2]);
+      sum += c3[r];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int run = incl - sum;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int y = lane * 3 + r;
+      if (y < ORB_CELL_MAX) s_rowoff[y] = run;
+      run += c3[r];
+    }
+  }
+  __syncthreads();
+  uint32_t* out = cand + (size_t)frame * g->cand_frame_u32 + L.cand_off + (size_t)cell.slot * L.cand_cap;
+  for (int y = 3 + warp; y < ch - 3; y += 4) {
+    int off = s_rowoff[y];
+#pragma unroll
+    for (int cchunk = 0; cchunk < 3; ++cchunk) {
+      const uint32_t mask = s_mask[use][y][cchunk];
+      if (mask >> lane & 1u) {
+        const int x = 3 + cchunk * 32 + lane;
+        const int pos = off + __popc(mask & ((1u << lane) - 1u));
+        const uint32_t score = (uint32_t)s_m[y * FAST_PITCH + x] - 1u;
+        if (pos < L.cand_cap)
+          out[pos] = (uint32_t)(x + cell.off_x) | (uint32_t)(y + cell.off_y) << 12 | score << 24;
+      }
+      off += __popc(mask);
+    }
+  }
+  if (tid == 0) cell_count[(size_t)frame * g->n_cells + blockIdx.x] = min(total, L.cand_cap);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4 DistributeOctTree: one CTA per (level, frame); policy core in octree_core.h.
+__global__ void __launch_bounds__(256) k_octree(const OrbGeom* __restrict__ g, const uint32_t* __restrict__ cand,
+                                                const int* __restrict__ cell_count, uint32_t* __restrict__ keys,
+                                                uint16_t* __restrict__ knode, uint32_t* __restrict__ sel,
+                                                int* __restrict__ sel_count) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int level = blockIdx.x, frame = blockIdx.y;
+  const OrbLevelGeom& L = g->lv[level];
+  const int cap = g->ot_cap, scap = g->ot_scan_cap;
+  OtScratch s;
+  unsigned char* p = smem;
+  s.best = reinterpret_cast<unsigned long long*>(p); p += sizeof(unsigned long long) * cap;
+  s.nodes[0] = reinterpret_cast<OtNode*>(p); p += sizeof(OtNode) * cap;
+  s.nodes[1] = reinterpret_cast<OtNode*>(p); p += sizeof(OtNode) * cap;
+  s.cnt4 = reinterpret_cast<int*>(p); p += sizeof(int) * 4 * cap;
+  s.childpos = reinterpret_cast<int*>(p); p += sizeof(int) * 4 * cap;
+  s.P = reinterpret_cast<int*>(p); p += sizeof(int) * cap;
+  s.rankP = reinterpret_cast<int*>(p); p += sizeof(int) * cap;
+  s.newpos = reinterpret_cast<int*>(p); p += sizeof(int) * cap;
+  s.a = reinterpret_cast<int*>(p); p += sizeof(int) * scap;
+  s.b = reinterpret_cast<int*>(p); p += sizeof(int) * scap;
+  s.c = reinterpret_cast<int*>(p); p += sizeof(int) * scap;
+  s.part = reinterpret_cast<int*>(p); p += sizeof(int) * (256 + 1);
+  s.vars = reinterpret_cast<int*>(p);
+
+  // gather this level's candidates in vToDistributeKeys order: cells row-major, in-cell order
+  const int* cc = cell_count + (size_t)frame * g->n_cells + L.cell_base;
+  OT_FOR(i, L.n_cells) s.a[i] = cc[i];
+  OT_SYNC();
+  ot_exclusive_scan(s.a, s.b, L.n_cells, &s.vars[OT_V_TOTAL], s.part);
+  const int M = s.vars[OT_V_TOTAL];
+  const uint32_t* cslots = cand + (size_t)frame * g->cand_frame_u32 + L.cand_off;
+  uint32_t* fkeys = keys + (size_t)frame * g->key_frame_u32 + L.key_off;
+  uint16_t* fknode = knode + (size_t)frame * g->key_frame_u32 + L.key_off;
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int c = warp; c < L.n_cells; c += nwarp) {
+      const int n = s.a[c], off = s.b[c];
+      for (int k = lane; k < n; k += 32) fkeys[off + k] = cslots[(size_t)c * L.cand_cap + k];
+    }
+  }
+  __syncthreads();
+  uint32_t* out = sel + (size_t)frame * g->kp_cap_frame + L.sel_off;
+  const int n = ot_distribute(fkeys, fknode, M, L.roots, L.quota, s, out);
+  if (threadIdx.x == 0) sel_count[frame * g->nlevels + level] = n;
+}
+
+// ------------------------------------------------------------------------------------------
+// K6 GaussianBlur 7x7 sigma 2, OpenCV 4.x fixed-point path: taps {18,34,48,56,48,34,18}/256 per
+// pass, H pass u8 -> 8.8 (16 bit), V pass -> 16.16, (v + 32768) >> 16.  Reads the bordered
+// pyramid level: its REFLECT_101 border supplies exactly the blur's own border pixels.
+// Tile = 128 x 16 outputs per CTA; H pass with dp4a on packed bytes.
+#define BLUR_IN_PITCH 144
+__global__ void __launch_bounds__(256) k_blur(const OrbGeom* __restrict__ g, const uint8_t* __restrict__ pyr,
+                                              uint8_t* __restrict__ blur) {
+  __shared__ __align__(16) uint8_t s_in[(ORB_BLUR_TH + 6) * BLUR_IN_PITCH];
+  __shared__ __align__(16) uint16_t s_h[(ORB_BLUR_TH + 6) * ORB_BLUR_TW];
+  int level = 0;
+  while (level + 1 < g->nlevels && (int)blockIdx.x >= g->lv[level + 1].blur_tile_base) ++level;
+  const OrbLevelGeom& L = g->lv[level];
+  const int t = blockIdx.x - L.blur_tile_base;
+  const int ty = t / L.blur_tiles_x, tx = t - ty * L.blur_tiles_x;
+  const int x0 = tx * ORB_BLUR_TW, y0 = ty * ORB_BLUR_TH;
+  const int frame = blockIdx.y, tid = threadIdx.x;
+  const uint8_t* src = pyr + (size_t)frame * g->pyr_frame_bytes + L.pyr_off;  // bordered origin
+  // stage rows y0-3 .. y0+TH+2, cols x0-4 .. x0+TW+3 (word aligned: bordered col = x + 19)
+  // bordered col of (x0-4) is x0+15; stage from bordered col x0+12 (multiple of 4) for aligned loads
+  const int bx0 = x0 + 12;                       // bordered x of smem col 0  (image x = x0 - 7)
+  const int bwords = L.pitch >> 2;
+  for (int i = tid; i < (ORB_BLUR_TH + 6) * (BLUR_IN_PITCH / 4); i += 256) {
+    const int r = i / (BLUR_IN_PITCH / 4), wq = i - r * (BLUR_IN_PITCH / 4);
+    int by = y0 - 3 + r + ORB_EDGE;
+    by = min(by, L.h + 2 * ORB_EDGE - 1);
+    const int bw = min((bx0 >> 2) + wq, bwords - 1);
+    reinterpret_cast<uint32_t*>(s_in + r * BLUR_IN_PITCH)[wq] =
+        __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)by * L.pitch) + bw);
+  }
+  __syncthreads();
+  // H pass: output x (0..127) of row r needs image cols x0+x-3 .. x0+x+3 = smem cols x+4 .. x+10
+  const uint32_t K0123 = 18u | 34u << 8 | 48u << 16 | 56u << 24, K456 = 48u | 34u << 8 | 18u << 16;
+  for (int i = tid; i < (ORB_BLUR_TH + 6) * (ORB_BLUR_TW / 4); i += 256) {
+    const int r = i / (ORB_BLUR_TW / 4), q = i - r * (ORB_BLUR_TW / 4);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(s_in + r * BLUR_IN_PITCH) + q + 1;  // cols 4q+4..
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    // window for output 4q+j starts at byte j of w0
+    const uint32_t a0 = w0, b0 = w1;
+    const uint32_t a1 = __byte_perm(w0, w1, 0x4321), b1 = __byte_perm(w1, w2, 0x4321);
+    const uint32_t a2 = __byte_perm(w0, w1, 0x5432), b2 = __byte_perm(w1, w2, 0x5432);
+    const uint32_t a3 = __byte_perm(w0, w1, 0x6543), b3 = __byte_perm(w1, w2, 0x6543);
+    const uint32_t h0 = __dp4a(a0, K0123, __dp4a(b0, K456, 0u));
+    const uint32_t h1 = __dp4a(a1, K0123, __dp4a(b1, K456, 0u));
+    const uint32_t h2 = __dp4a(a2, K0123, __dp4a(b2, K456, 0u));
+    const uint32_t h3 = __dp4a(a3, K0123, __dp4a(b3, K456, 0u));
+    reinterpret_cast<uint2*>(s_h + r * ORB_BLUR_TW)[q] = make_uint2(h0 | h1 << 16, h2 | h3 << 16);
+  }
+  __syncthreads();
+  uint8_t* dst = blur + (size_t)frame * g->blur_frame_bytes + L.blur_off;
+  for (int i = tid; i < ORB_BLUR_TH * (ORB_BLUR_TW / 4); i += 256) {
+    const int r = i / (ORB_BLUR_TW / 4), q = i - r * (ORB_BLUR_TW / 4);
+    const int y = y0 + r, x = x0 + 4 * q;
+    if (y >= L.h || x >= L.bpitch) continue;
+    uint32_t acc0 = 32768u, acc1 = 32768u, acc2 = 32768u, acc3 = 32768u;
+    const uint32_t KT[7] = {18u, 34u, 48u, 56u, 48u, 34u, 18u};
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const uint2 hv = reinterpret_cast<const uint2*>(s_h + (r + j) * ORB_BLUR_TW)[q];
+      acc0 += KT[j] * (hv.x & 0xffffu);
+      acc1 += KT[j] * (hv.x >> 16);
+      acc2 += KT[j] * (hv.y & 0xffffu);
+      acc3 += KT[j] * (hv.y >> 16);
+    }
+    reinterpret_cast<uint32_t*>(dst + (size_t)y * L.bpitch)[x >> 2] =
+        (acc0 >> 16) | (acc1 >> 16) << 8 | (acc2 >> 16) << 16 | (acc3 >> 16) << 24;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5 + K7: IC_Angle orientation (:77-104) and rotated-BRIEF descriptor (:108-147), one warp
+// per keypoint.  Also the epilogue of operator() (:1060-1106): level order concatenation,
+// pt *= mvScaleFactor[level], size, octave.
+__constant__ int c_umax[ORB_HALF_PATCH + 1] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+__device__ __align__(16) const signed char d_pattern[ORB_PATTERN_INTS] = ORB_PATTERN_INIT;
+
+// cv::fastAtan2 (OpenCV core, scalar path): float32, evaluated left to right, no FMA.
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+  const float scale = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = __fmul_rn(0.9997878412794807f, scale), p3 = __fmul_rn(-0.3258083974640975f, scale);
+  const float p5 = __fmul_rn(0.1555786518463281f, scale), p7 = __fmul_rn(-0.04432655554792128f, scale);
+  const float eps = 2.2204460492503131e-16f;  // (float)DBL_EPSILON
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+// glibc >= 2.28 sinf/cosf (ARM optimized-routines algorithm): double-precision reduction and
+// polynomial, rounded once to float.  Valid for |y| < 120; the caller's angles lie in [0, 2pi).
+__device__ __forceinline__ double sincos_poly(double x, double x2, bool neg_cos, int n) {
+  const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+  double C0 = 0x1p0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10,
+         C4 = 0x1.99343027bf8c3p-16;
+  if (neg_cos) { C0 = -C0; C1 = -C1; C2 = -C2; C3 = -C3; C4 = -C4; }
+  if ((n & 1) == 0) {
+    const double x3 = __dmul_rn(x, x2);
+    const double s1 = __dadd_rn(S2, __dmul_rn(x2, S3));
+    const double x7 = __dmul_rn(x3, x2);
+    const double s = __dadd_rn(x, __dmul_rn(x3, S1));
+    return __dadd_rn(s, __dmul_rn(x7, s1));
+  } else {
+    const double x4 = __dmul_rn(x2, x2);
+    const double c2 = __dadd_rn(C3, __dmul_rn(x2, C4));
+    const double c1 = __dadd_rn(C1, __dmul_rn(x2, C2));
+    const double x6 = __dmul_rn(x4, x2);
+    const double c = __dadd_rn(C0, __dmul_rn(x2, c1));
+    return __dadd_rn(c, __dmul_rn(x6, c2));
+  }
+}
+
+__device__ __forceinline__ void glibc_sincosf(float y, float* sinp, float* cosp) {
+  const double x = (double)y;
+  const unsigned top = (__float_as_uint(y) >> 20) & 0x7ffu;
+  if (top < ((0x3f490fdbu >> 20) & 0x7ffu)) {  // |y| < pi/4 (top-12-bit compare as in glibc)
+    const double x2 = __dmul_rn(x, x);
+    if (top < ((0x39800000u >> 20) & 0x7ffu)) {  // |y| < 2^-12
+      *sinp = y;
+      *cosp = 1.0f;
+      return;
+    }
+    *sinp = (float)sincos_poly(x, x2, false, 0);
+    *cosp = (float)sincos_poly(x, x2, false, 1);
+    return;
+  }
+  const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
+  const int n = ((int)r + 0x800000) >> 24;
+  const double xr = __dsub_rn(x, __dmul_rn((double)n, 0x1.921FB54442D18p0));
+  const double sgn = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+  const bool neg = (n & 2) != 0;
+  const double xs = __dmul_rn(xr, sgn), x2 = __dmul_rn(xr, xr);
+  *sinp = (float)sincos_poly(xs, x2, neg, n);
+  *cosp = (float)sincos_poly(xs, x2, neg, n ^ 1);
+}
+
+__global__ void __launch_bounds__(256) k_orient_describe(const OrbGeom* __restrict__ g, const uint8_t* __restrict__ pyr,
+                                                         const uint8_t* __restrict__ blur,
+                                                         const uint32_t* __restrict__ sel,
+                                                         const int* __restrict__ sel_count,
+                                                         orbx_keypoint* __restrict__ kps, uint8_t* __restrict__ desc,
+                                                         int* __restrict__ counts, int cap) {
+  const int frame = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int gidx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // keypoint index in the frame
+  const int* sc = sel_count + frame * g->nlevels;
+  int level = -1, first = 0, total = 0;
+  for (int l = 0; l < g->nlevels; ++l) {
+    const int n = sc[l];
+    if (level < 0 && gidx < total + n) { level = l; first = total; }
+    total += n;
+  }
+  if (gidx == 0 && lane == 0) counts[frame] = total;
+  if (level < 0 || gidx >= cap) return;
+  const OrbLevelGeom& L = g->lv[level];
+  const uint32_t key = sel[(size_t)frame * g->kp_cap_frame + L.sel_off + (gidx - first)];
+  const int kx = OT_KEY_X(key) + ORB_MIN_BORDER, ky = OT_KEY_Y(key) + ORB_MIN_BORDER;  // :843-844
+
+  // IC_Angle on the un-blurred level: lane = u + 15
+  const uint8_t* center = pyr + (size_t)frame * g->pyr_frame_bytes + L.pyr_off +
+                          (size_t)(ky + ORB_EDGE) * L.pitch + kx + ORB_EDGE;
+  const int u = lane - ORB_HALF_PATCH;
+  int m10 = 0, m01 = 0;
+  if (lane < 31) {
+    m10 = u * (int)center[u];
+#pragma unroll
+    for (int v = 1; v <= ORB_HALF_PATCH; ++v) {
+      if (abs(u) <= c_umax[v]) {
+        const int plus = center[u + v * L.pitch], minus = center[u - v * L.pitch];
+        m10 += u * (plus + minus);
+        m01 += v * (plus - minus);
+      }
+    }
+  }
+  m10 = __reduce_add_sync(0xffffffffu, m10);
+  m01 = __reduce_add_sync(0xffffffffu, m01);
+  const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+  // rotated BRIEF on the blurred level: lane computes descriptor byte `lane`
+  const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+  float a, b;
+  glibc_sincosf(__fmul_rn(angle, factorPI), &b, &a);
+  const uint8_t* bc = blur + (size_t)frame * g->blur_frame_bytes + L.blur_off + (size_t)ky * L.bpitch + kx;
+  const char4* pat = reinterpret_cast<const char4*>(d_pattern) + lane * 8;
+  int val = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const char4 pp = pat[k];
+    const float x0 = (float)pp.x, y0 = (float)pp.y, x1 = (float)pp.z, y1 = (float)pp.w;
+    const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+    const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+    const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+    const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+    const int t0 = bc[r0 * L.bpitch + c0], t1 = bc[r1 * L.bpitch + c1];
+    val |= (t0 < t1) << k;
+  }
+  const size_t o = (size_t)frame * cap + gidx;
+  desc[o * 32 + lane] = (uint8_t)val;
+  if (lane < 6) {
+    float f;
+    if (lane == 0) f = level ? __fmul_rn((float)kx, L.scale) : (float)kx;
+    else if (lane == 1) f = level ? __fmul_rn((float)ky, L.scale) : (float)ky;
+    else if (lane == 2) f = L.patch_size;
+    else if (lane == 3) f = angle;
+    else if (lane == 4) f = (float)OT_KEY_SCORE(key);
+    else f = __int_as_float(level);
+    reinterpret_cast<float*>(kps + o)[lane] = f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// launch wrappers (host)
+void launch_pyramid(const OrbGeomHost& gh, const uint8_t* d_src, size_t frame_stride, size_t row_stride,
+                    int n_frames, uint8_t* d_pyr, cudaStream_t st, long long* launches) {
+  {
+    const OrbLevelGeom& L = gh.g.lv[0];
+    const int n = (L.pitch >> 2) * (L.h + 2 * ORB_EDGE);
+    k_pyr_level0<<<dim3((n + 255) / 256, n_frames), 256, 0, st>>>(d_src, frame_stride, row_stride, gh.d_geom, d_pyr);
+    ++*launches;
+  }
+  for (int l = 1; l < gh.g.nlevels; ++l) {
+    const OrbLevelGeom& L = gh.g.lv[l];
+    const int n = (L.pitch >> 2) * (L.h + 2 * ORB_EDGE);
+    k_pyr_resize<<<dim3((n + 255) / 256, n_frames), 256, 0, st>>>(l, gh.d_geom, gh.d_xtab, gh.d_ytab, d_pyr);
+    ++*launches;
+  }
+}
+
+void launch_fast(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, uint32_t* d_cand, int* d_cell_count,
+                 cudaStream_t st, long long* launches) {
+  k_fast_cells<<<dim3(gh.g.n_cells, n_frames), 128, 0, st>>>(gh.d_geom, gh.d_cells, d_pyr, d_cand, d_cell_count);
+  ++*launches;
+}
+
+size_t octree_smem_bytes(const OrbGeom& g) {
+  const size_t cap = g.ot_cap, scap = g.ot_scan_cap;
+  return sizeof(unsigned long long) * cap + 2 * sizeof(OtNode) * cap + sizeof(int) * (8 * cap + 3 * cap) +
+         sizeof(int) * 3 * scap + sizeof(int) * 257 + sizeof(int) * 8;
+}
+
+cudaError_t prepare_octree(const OrbGeom& g) {
+  return cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_smem_bytes(g));
+}
+
+void launch_octree(const OrbGeomHost& gh, int n_frames, const uint32_t* d_cand, const int* d_cell_count,
+                   uint32_t* d_keys, uint16_t* d_knode, uint32_t* d_sel, int* d_sel_count, cudaStream_t st,
+                   long long* launches) {
+  k_octree<<<dim3(gh.g.nlevels, n_frames), 256, octree_smem_bytes(gh.g), st>>>(gh.d_geom, d_cand, d_cell_count, d_keys,
+                                                                                d_knode, d_sel, d_sel_count);
+  ++*launches;
+}
+
+void launch_blur(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, uint8_t* d_blur, cudaStream_t st,
+                 long long* launches) {
+  k_blur<<<dim3(gh.g.n_blur_tiles, n_frames), 256, 0, st>>>(gh.d_geom, d_pyr, d_blur);
+  ++*launches;
+}
+
+void launch_orient_describe(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, const uint8_t* d_blur,
+                            const uint32_t* d_sel, const int* d_sel_count, orbx_keypoint* d_kps, uint8_t* d_desc,
+                            int* d_counts, int cap, cudaStream_t st, long long* launches) {
+  const int max_kp = gh.g.kp_cap_frame;  // upper bound of keypoints per frame
+  k_orient_describe<<<dim3((max_kp + 7) / 8, n_frames), 256, 0, st>>>(gh.d_geom, d_pyr, d_blur, d_sel, d_sel_count,
+                                                                        d_kps, d_desc, d_counts, cap);
+  ++*launches;
+}
+
+}  // namespace orbk

@@ -1,0 +1,34 @@
+// Host-side launch interface of the extractor kernels (extract_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/orb_b200.h"
+#include "orb_geom.h"
+
+namespace orbk {
+
+struct OrbGeomHost {
+  OrbGeom g;               // host copy
+  OrbGeom* d_geom;         // device copy
+  OrbCell* d_cells;        // [g.n_cells]
+  OrbXTap* d_xtab;
+  OrbYTap* d_ytab;
+};
+
+void launch_pyramid(const OrbGeomHost& gh, const uint8_t* d_src, size_t frame_stride, size_t row_stride,
+                    int n_frames, uint8_t* d_pyr, cudaStream_t st, long long* launches);
+void launch_fast(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, uint32_t* d_cand, int* d_cell_count,
+                 cudaStream_t st, long long* launches);
+size_t octree_smem_bytes(const OrbGeom& g);
+cudaError_t prepare_octree(const OrbGeom& g);
+void launch_octree(const OrbGeomHost& gh, int n_frames, const uint32_t* d_cand, const int* d_cell_count,
+                   uint32_t* d_keys, uint16_t* d_knode, uint32_t* d_sel, int* d_sel_count, cudaStream_t st,
+                   long long* launches);
+void launch_blur(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, uint8_t* d_blur, cudaStream_t st,
+                 long long* launches);
+void launch_orient_describe(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, const uint8_t* d_blur,
+                            const uint32_t* d_sel, const int* d_sel_count, orbx_keypoint* d_kps, uint8_t* d_desc,
+                            int* d_counts, int cap, cudaStream_t st, long long* launches);
+
+}  // namespace orbk

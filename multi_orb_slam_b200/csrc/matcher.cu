@@ -1,0 +1,786 @@
+// Hand-written sm_100a kernels + C-ABI of the matcher hot path (include/orb_b200.h, orbm_*).
+// Reference: /root/reference/src/ORBmatcher.cc — DescriptorDistance :3994-4010,
+// SearchForInitialization :868-983, SearchByProjection(Frame&, vector<MapPoint*>&, th) :62-157,
+// ComputeThreeMaxima :3948-3989; and the grid index of src/Frame.cc — AssignFeaturesToGrid
+// :348-395, PosInGrid :632-642, GetFeaturesInArea :510-566.
+//
+// Descriptors are 32 bytes = 8 x u32; distance = sum of __popc(a ^ b).  Matching is bound by the
+// integer POPC issue rate (16 lanes/clk/SM), not by HBM: descriptors are tiny and stay on chip.
+// Order-dependent reference loops are split into a parallel phase (grid lookup + distances,
+// candidates kept in the reference's traversal order) and an ordered resolve phase.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/orb_b200.h"
+
+#define GRID_COLS 64  // FRAME_GRID_COLS (include/Frame.h)
+#define GRID_ROWS 48  // FRAME_GRID_ROWS
+#define GRID_CELLS (GRID_COLS * GRID_ROWS)
+#define TH_HIGH 100   // src/ORBmatcher.cc:37-39
+#define TH_LOW 50
+#define HISTO_LENGTH 30
+
+namespace {
+
+__device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+         __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__device__ __forceinline__ int hamming_rows(const uint8_t* a, const uint8_t* b) {
+  const uint4* pa = reinterpret_cast<const uint4*>(a);
+  const uint4* pb = reinterpret_cast<const uint4*>(b);
+  return hamming256(pa[0], pa[1], pb[0], pb[1]);
+}
+
+// ---- DescriptorDistance for n independent pairs ------------------------------------------
+__global__ void k_distance_pairs(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n,
+                                 int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = hamming_rows(a + (size_t)i * 32, b + (size_t)i * 32);
+}
+
+// ---- brute force ---------------------------------------------------------------------------
+// Each thread owns BF_QPT query rows in registers; the CTA streams its chunk of targets through
+// shared memory (every lane reads the same target word: broadcast).  Best / second-best are
+// tracked on packed keys (dist << 16 | local target index): min over keys = lowest distance
+// then lowest index, which is exactly the strict-< ascending scan of the reference; the second
+// smallest key carries the second-best distance.  Target chunks (blockIdx.y) are merged by
+// k_bf_merge in ascending chunk order.
+#define BF_THREADS 128
+#define BF_QPT 2
+#define BF_TILE 256
+
+__global__ void __launch_bounds__(BF_THREADS) k_bruteforce(const uint8_t* __restrict__ q, int nq,
+                                                           const uint8_t* __restrict__ t, int nt, int chunk,
+                                                           uint2* __restrict__ partial) {
+  __shared__ uint4 s_t[BF_TILE * 2];
+  const int tid = threadIdx.x;
+  const int t_begin = blockIdx.y * chunk, t_end = min(nt, t_begin + chunk);
+  uint4 qa[BF_QPT], qb[BF_QPT];
+  uint32_t best[BF_QPT], second[BF_QPT];
+#pragma unroll
+  for (int r = 0; r < BF_QPT; ++r) {
+    const int qi = min((blockIdx.x * BF_QPT + r) * BF_THREADS + tid, nq - 1);
+    const uint4* p = reinterpret_cast<const uint4*>(q + (size_t)qi * 32);
+    qa[r] = __ldg(p);
+    qb[r] = __ldg(p + 1);
+    best[r] = second[r] = 0xFFFFFFFFu;
+  }
+  for (int base = t_begin; base < t_end; base += BF_TILE) {
+    const int nt_tile = min(BF_TILE, t_end - base);
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(t + (size_t)base * 32);
+    for (int i = tid; i < nt_tile * 2; i += BF_THREADS) s_t[i] = __ldg(src + i);
+    __syncthreads();
+    const uint32_t jbase = (uint32_t)(base - t_begin);
+#pragma unroll 4
+    for (int j = 0; j < nt_tile; ++j) {
+      const uint4 ta = s_t[2 * j], tb = s_t[2 * j + 1];
+#pragma unroll
+      for (int r = 0; r < BF_QPT; ++r) {
+        const uint32_t d = (uint32_t)hamming256(qa[r], qb[r], ta, tb);
+        const uint32_t key = (d << 16) + (jbase + (uint32_t)j);
+        second[r] = min(second[r], max(best[r], key));
+        best[r] = min(best[r], key);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < BF_QPT; ++r) {
+    const int qi = (blockIdx.x * BF_QPT + r) * BF_THREADS + tid;
+    if (qi < nq) partial[(size_t)blockIdx.y * nq + qi] = make_uint2(best[r], second[r]);
+  }
+}
+
+__global__ void k_bf_merge(const uint2* __restrict__ partial, int nq, int nsplit, int chunk, float ratio, int th_dist,
+                           int32_t* __restrict__ out_idx, int32_t* __restrict__ out_d1, int32_t* __restrict__ out_d2) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  int best = 256, second = 256, idx = -1;
+  for (int s = 0; s < nsplit; ++s) {
+    const uint2 p = partial[(size_t)s * nq + qi];
+    if (p.x == 0xFFFFFFFFu) continue;
+    const int b = (int)(p.x >> 16), bi = s * chunk + (int)(p.x & 0xFFFFu);
+    const int sc = p.y == 0xFFFFFFFFu ? 256 : (int)(p.y >> 16);
+    if (b < best) {  // chunks ascend in target index: strict < keeps the earliest on ties
+      second = min(best, sc);
+      best = b;
+      idx = bi;
+    } else {
+      second = min(second, b);
+    }
+  }
+  out_d1[qi] = best;
+  out_d2[qi] = second;
+  out_idx[qi] = (idx >= 0 && best <= th_dist && (float)best < __fmul_rn((float)second, ratio)) ? idx : -1;
+}
+
+// ---- frame grid ------------------------------------------------------------------------------
+// Cells are stored column-major (cell = ix * GRID_ROWS + iy) so that the reference's traversal
+// (ix outer, iy inner, insertion order inside a cell) of one grid column is ONE contiguous run
+// of `items`.
+struct GridView {
+  const int* start;        // [GRID_CELLS + 1]
+  const uint16_t* items;   // keypoint indices, cell-major, insertion (= index) order
+  float min_x, min_y, inv_w, inv_h;
+};
+
+__device__ __forceinline__ int grid_cell_of(float x, float y, float min_x, float min_y, float inv_w, float inv_h) {
+  // PosInGrid: round() = half away from zero (src/Frame.cc:634-635)
+  const int px = (int)roundf(__fmul_rn(__fsub_rn(x, min_x), inv_w));
+  const int py = (int)roundf(__fmul_rn(__fsub_rn(y, min_y), inv_h));
+  if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) return -1;
+  return px * GRID_ROWS + py;
+}
+
+// One CTA per frame: counting sort of keypoints into grid cells, stable in keypoint index.
+__global__ void __launch_bounds__(256) k_build_grid(const orbx_keypoint* __restrict__ kps, const int32_t* __restrict__ n_arr,
+                                                    int n_fixed, int cap, orbm_bounds b, int* __restrict__ start_out,
+                                                    uint16_t* __restrict__ items_out) {
+  __shared__ int s_cnt[GRID_CELLS + 1];
+  __shared__ int s_part[257];
+  const int frame = blockIdx.x, tid = threadIdx.x;
+  const int n = n_arr ? min(n_arr[frame], cap) : n_fixed;
+  const orbx_keypoint* k = kps + (size_t)frame * cap;
+  const float inv_w = __fdiv_rn((float)GRID_COLS, __fsub_rn(b.max_x, b.min_x));
+  const float inv_h = __fdiv_rn((float)GRID_ROWS, __fsub_rn(b.max_y, b.min_y));
+  for (int i = tid; i <= GRID_CELLS; i += 256) s_cnt[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += 256) {
+    const int c = grid_cell_of(k[i].x, k[i].y, b.min_x, b.min_y, inv_w, inv_h);
+    if (c >= 0) atomicAdd(&s_cnt[c], 1);
+  }
+  __syncthreads();
+  // exclusive scan of GRID_CELLS counts: 12 per thread
+  {
+    const int lo = tid * 12;
+    int s = 0;
+    for (int i = lo; i < lo + 12; ++i) s += s_cnt[i];
+    s_part[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0;
+      for (int i = 0; i < 256; ++i) { const int v = s_part[i]; s_part[i] = run; run += v; }
+      s_part[256] = run;
+    }
+    __syncthreads();
+    int run = s_part[tid];
+    for (int i = lo; i < lo + 12; ++i) { const int v = s_cnt[i]; s_cnt[i] = run; run += v; }
+    if (tid == 0) s_cnt[GRID_CELLS] = s_part[256];
+  }
+  __syncthreads();
+  int* start = start_out + (size_t)frame * (GRID_CELLS + 1);
+  for (int i = tid; i <= GRID_CELLS; i += 256) start[i] = s_cnt[i];
+  __syncthreads();
+  // stable placement by warp 0: 32 keypoints at a time, in index order; s_cnt becomes the fill cursor
+  if (tid < 32) {
+    uint16_t* items = items_out + (size_t)frame * cap;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + tid;
+      int c = -1;
+      if (i < n) c = grid_cell_of(k[i].x, k[i].y, b.min_x, b.min_y, inv_w, inv_h);
+      const unsigned peers = __match_any_sync(0xffffffffu, c);
+      if (c >= 0) {
+        const int rank = __popc(peers & ((1u << tid) - 1u));
+        items[s_cnt[c] + rank] = (uint16_t)i;
+      }
+      __syncwarp();
+      if (c >= 0 && (peers >> tid) == 1u) s_cnt[c] += __popc(peers);  // highest peer lane updates the cursor
+      __syncwarp();
+    }
+  }
+}
+
+// Frame::GetFeaturesInArea (src/Frame.cc:510-566), warp-cooperative.  Calls emit(idx) for every
+// keypoint that passes the cell window, octave window and |dx|<r, |dy|<r tests, in the
+// reference's traversal order; `emit` receives (lane_has, idx) and must be called by all lanes.
+template <typename Emit>
+__device__ __forceinline__ void grid_query(const GridView& gv, const orbx_keypoint* __restrict__ k, float x, float y,
+                                           float r, int min_level, int max_level, Emit emit) {
+  const int lane = threadIdx.x & 31;
+  const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, gv.min_x), r), gv.inv_w)));
+  if (cx0 >= GRID_COLS) return;
+  const int cx1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, gv.min_x), r), gv.inv_w)));
+  if (cx1 < 0) return;
+  const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, gv.min_y), r), gv.inv_h)));
+  if (cy0 >= GRID_ROWS) return;
+  const int cy1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, gv.min_y), r), gv.inv_h)));
+  if (cy1 < 0) return;
+  const bool check = (min_level > 0) || (max_level >= 0);
+  for (int ix = cx0; ix <= cx1; ++ix) {
+    const int run0 = gv.start[ix * GRID_ROWS + cy0], run1 = gv.start[ix * GRID_ROWS + cy1 + 1];
+    for (int e = run0; e < run1; e += 32) {
+      const int ei = e + lane;
+      bool ok = false;
+      int idx = 0;
+      if (ei < run1) {
+        idx = gv.items[ei];
+        const orbx_keypoint kp = k[idx];
+        ok = true;
+        if (check) {
+          if (kp.octave < min_level) ok = false;
+          if (max_level >= 0 && kp.octave > max_level) ok = false;
+        }
+        ok = ok && fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r;
+      }
+      emit(ok, idx);
+    }
+  }
+}
+
+// Warp-wide lexicographic top-2 over packed keys (smaller = better); all lanes get the result.
+__device__ __forceinline__ void warp_top2(uint32_t& best, uint32_t& second) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o);
+    const uint32_t nb = min(best, ob);
+    second = min(max(best, ob), min(second, os));
+    best = nb;
+  }
+}
+
+// ---- SearchForInitialization ----------------------------------------------------------------
+// One CTA per frame pair.  Phase A (all warps): for each level-0 keypoint i1 of F1, the window
+// query on F2's grid and the Hamming distances, candidates stored in traversal order as
+// (dist << 16 | i2).  Phase B (warp 0, i1 ascending): the best/second scan with the
+// vMatchedDistance filter (:907), acceptance, match stealing (:926-933) and histogram.  Then
+// the three-maxima rotation filter and the vbPrevMatched update, in parallel.
+__global__ void __launch_bounds__(256) k_search_init(int cap, const orbx_keypoint* __restrict__ k1_all,
+                                                     const uint8_t* __restrict__ d1_all, const int32_t* __restrict__ n1_arr,
+                                                     const orbx_keypoint* __restrict__ k2_all,
+                                                     const uint8_t* __restrict__ d2_all, const int32_t* __restrict__ n2_arr,
+                                                     orbm_bounds b2, const int* __restrict__ grid_start,
+                                                     const uint16_t* __restrict__ grid_items, float* __restrict__ prev_all,
+                                                     float window, float nnratio, int check_ori,
+                                                     uint32_t* __restrict__ cand_all, int* __restrict__ cand_cnt_all,
+                                                     int32_t* __restrict__ matches12_all, int32_t* __restrict__ nmatches_out) {
+  extern __shared__ int s_dyn[];  // matchedDist[cap], matches21[cap], bin_of[cap]
+  __shared__ int s_hist[HISTO_LENGTH];
+  __shared__ int s_keep[HISTO_LENGTH];
+  __shared__ int s_nmatch;
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n1 = min(n1_arr[pair], cap), n2 = min(n2_arr[pair], cap);
+  const orbx_keypoint* k1 = k1_all + (size_t)pair * cap;
+  const orbx_keypoint* k2 = k2_all + (size_t)pair * cap;
+  const uint8_t* d1 = d1_all + (size_t)pair * cap * 32;
+  const uint8_t* d2 = d2_all + (size_t)pair * cap * 32;
+  float* prev = prev_all + (size_t)pair * cap * 2;
+  uint32_t* cand = cand_all + (size_t)pair * cap * cap;
+  int* cand_cnt = cand_cnt_all + (size_t)pair * cap;
+  int32_t* matches12 = matches12_all + (size_t)pair * cap;
+  int* s_mdist = s_dyn;
+  int* s_m21 = s_dyn + cap;
+  int* s_bin = s_dyn + 2 * cap;
+  GridView gv;
+  gv.start = grid_start + (size_t)pair * (GRID_CELLS + 1);
+  gv.items = grid_items + (size_t)pair * cap;
+  gv.min_x = b2.min_x;
+  gv.min_y = b2.min_y;
+  gv.inv_w = __fdiv_rn((float)GRID_COLS, __fsub_rn(b2.max_x, b2.min_x));
+  gv.inv_h = __fdiv_rn((float)GRID_ROWS, __fsub_rn(b2.max_y, b2.min_y));
+
+  for (int i = tid; i < cap; i += 256) {
+    s_mdist[i] = 0x7FFFFFFF;
+    s_m21[i] = -1;
+    s_bin[i] = -1;
+    if (i < n1) matches12[i] = -1;
+  }
+  if (tid < HISTO_LENGTH) s_hist[tid] = 0;
+  if (tid == 0) s_nmatch = 0;
+  // phase A
+  for (int i1 = warp; i1 < n1; i1 += 8) {
+    int cnt = 0;
+    if (k1[i1].octave <= 0) {  // level1 > 0 -> continue (:885-887)
+      const uint4* q = reinterpret_cast<const uint4*>(d1 + (size_t)i1 * 32);
+      const uint4 qa = __ldg(q), qb = __ldg(q + 1);
+      uint32_t* row = cand + (size_t)i1 * cap;
+      const int level1 = k1[i1].octave;
+      grid_query(gv, k2, prev[2 * i1], prev[2 * i1 + 1], window, level1, level1, [&](bool ok, int idx) {
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+          const uint4* tp = reinterpret_cast<const uint4*>(d2 + (size_t)idx * 32);
+          const int dist = hamming256(qa, qb, __ldg(tp), __ldg(tp + 1));
+          row[cnt + __popc(m & ((1u << lane) - 1u))] = (uint32_t)dist << 16 | (uint32_t)idx;
+        }
+        cnt += __popc(m);
+      });
+    }
+    if (lane == 0) cand_cnt[i1] = cnt;
+  }
+  __threadfence_block();
+  __syncthreads();
+  // phase B
+  if (warp == 0) {
+    int nmatches = 0;
+    for (int i1 = 0; i1 < n1; ++i1) {
+      const int cnt = cand_cnt[i1];
+      if (cnt == 0) continue;
+      const uint32_t* row = cand + (size_t)i1 * cap;
+      // key = dist << 16 | traversal position: strict-< scan order (:910-919)
+      uint32_t best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
+      for (int c = lane; c < cnt; c += 32) {
+        const uint32_t e = row[c];
+        const int dist = (int)(e >> 16), i2 = (int)(e & 0xFFFFu);
+        if (s_mdist[i2] <= dist) continue;  // :907
+        const uint32_t key = (uint32_t)dist << 16 | (uint32_t)c;
+        second = min(second, max(best, key));
+        best = min(best, key);
+      }
+      warp_top2(best, second);
+      if (best == 0xFFFFFFFFu) continue;
+      const int bestDist = (int)(best >> 16);
+      const int bestIdx2 = (int)(row[best & 0xFFFFu] & 0xFFFFu);
+      // bestDist2 stays INT_MAX when there is no second candidate (:896-897)
+      const float second_f = second == 0xFFFFFFFFu ? (float)0x7FFFFFFF : (float)(int)(second >> 16);
+      if (bestDist <= TH_LOW && (float)bestDist < __fmul_rn(second_f, nnratio)) {
+        if (lane == 0) {
+          const int old = s_m21[bestIdx2];
+          if (old >= 0) { matches12[old] = -1; nmatches--; }
+          matches12[i1] = bestIdx2;
+          s_m21[bestIdx2] = i1;
+          s_mdist[bestIdx2] = bestDist;
+          nmatches++;
+          if (check_ori) {
+            float rot = __fsub_rn(k1[i1].angle, k2[bestIdx2].angle);
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
+            if (bin == HISTO_LENGTH) bin = 0;
+            s_bin[i1] = bin;
+            s_hist[bin]++;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) {
+      s_nmatch = nmatches;
+      if (check_ori) {  // ComputeThreeMaxima (:3948-3989)
+        int max1 = 0, max2 = 0, max3 = 0, i1_ = -1, i2_ = -1, i3_ = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+          const int s = s_hist[i];
+          if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3_ = i2_; i2_ = i1_; i1_ = i; }
+          else if (s > max2) { max3 = max2; max2 = s; i3_ = i2_; i2_ = i; }
+          else if (s > max3) { max3 = s; i3_ = i; }
+        }
+        if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2_ = -1; i3_ = -1; }
+        else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { i3_ = -1; }
+        for (int i = 0; i < HISTO_LENGTH; ++i) s_keep[i] = (i == i1_ || i == i2_ || i == i3_);
+      }
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  if (check_ori) {
+    for (int i1 = tid; i1 < n1; i1 += 256) {
+      const int bin = s_bin[i1];
+      if (bin >= 0 && !s_keep[bin] && matches12[i1] >= 0) {
+        matches12[i1] = -1;
+        atomicSub(&s_nmatch, 1);
+      }
+    }
+    __syncthreads();
+  }
+  for (int i1 = tid; i1 < n1; i1 += 256) {  // :978-980
+    const int m = matches12[i1];
+    if (m >= 0) {
+      prev[2 * i1] = k2[m].x;
+      prev[2 * i1 + 1] = k2[m].y;
+    }
+  }
+  if (tid == 0) nmatches_out[pair] = s_nmatch;
+}
+
+// ---- SearchByProjection(Frame&, vector<MapPoint*>&, th) ------------------------------------
+// Phase A (warp per map point, whole grid): window query at levels [pred-1, pred], stereo gate
+// (:111-116), distances; candidates kept in traversal order as dist<<20 | octave<<16 | idx.
+// `count_only` pass sizes the ragged rows, then a scan gives row offsets.
+__device__ __forceinline__ float radius_by_viewing_cos(float view_cos) { return view_cos > 0.998f ? 2.5f : 4.0f; }
+
+__global__ void __launch_bounds__(256) k_proj_candidates(const orbx_keypoint* __restrict__ k, const uint8_t* __restrict__ desc,
+                                                         const float* __restrict__ u_right, orbm_bounds b,
+                                                         const int* __restrict__ grid_start,
+                                                         const uint16_t* __restrict__ grid_items,
+                                                         const float* __restrict__ scale_factors,
+                                                         const orbm_mappoint* __restrict__ mp,
+                                                         const uint8_t* __restrict__ mp_desc, int nmp, float th,
+                                                         int count_only, int* __restrict__ row_cnt,
+                                                         const int* __restrict__ row_off, uint32_t* __restrict__ rows) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= nmp) return;
+  const orbm_mappoint p = mp[i];
+  int cnt = 0;
+  if (p.track_in_view && !p.bad) {
+    GridView gv;
+    gv.start = grid_start;
+    gv.items = grid_items;
+    gv.min_x = b.min_x;
+    gv.min_y = b.min_y;
+    gv.inv_w = __fdiv_rn((float)GRID_COLS, __fsub_rn(b.max_x, b.min_x));
+    gv.inv_h = __fdiv_rn((float)GRID_ROWS, __fsub_rn(b.max_y, b.min_y));
+    float r = radius_by_viewing_cos(p.view_cos);
+    if (th != 1.0f) r = __fmul_rn(r, th);
+    const float rs = __fmul_rn(r, scale_factors[p.level]);
+    const uint4* q = reinterpret_cast<const uint4*>(mp_desc + (size_t)i * 32);
+    const uint4 qa = __ldg(q), qb = __ldg(q + 1);
+    uint32_t* row = count_only ? nullptr : rows + row_off[i];
+    grid_query(gv, k, p.proj_x, p.proj_y, rs, p.level - 1, p.level, [&](bool ok, int idx) {
+      if (ok && u_right) {
+        const float ur = u_right[idx];
+        if (ur > 0 && fabsf(__fsub_rn(p.proj_xr, ur)) > rs) ok = false;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok && !count_only) {
+        const uint4* tp = reinterpret_cast<const uint4*>(desc + (size_t)idx * 32);
+        const int dist = hamming256(qa, qb, __ldg(tp), __ldg(tp + 1));
+        row[cnt + __popc(m & ((1u << lane) - 1u))] = (uint32_t)dist << 20 | (uint32_t)(k[idx].octave & 15) << 16 | (uint32_t)idx;
+      }
+      cnt += __popc(m);
+    });
+  }
+  if (lane == 0 && count_only) row_cnt[i] = cnt;
+}
+
+// single-CTA exclusive scan (n up to a few hundred thousand)
+__global__ void __launch_bounds__(1024) k_scan_exclusive(const int* __restrict__ in, int* __restrict__ out, int n,
+                                                         int* __restrict__ total) {
+  __shared__ int s_part[1025];
+  const int tid = threadIdx.x;
+  const int chunk = (n + 1023) / 1024;
+  const int lo = tid * chunk, hi = min(n, lo + chunk);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += in[i];
+  s_part[tid] = s;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int i = 0; i < 1024; ++i) { const int v = s_part[i]; s_part[i] = run; run += v; }
+    *total = run;
+  }
+  __syncthreads();
+  int run = s_part[tid];
+  for (int i = lo; i < hi; ++i) { const int v = in[i]; out[i] = run; run += v; }
+}
+
+// Phase B: ordered resolve by one warp, map points ascending: occupancy skip (:107-109),
+// best/second with levels (:122-135), TH_HIGH + same-level ratio (:138-141), assignment (:143).
+__global__ void __launch_bounds__(32) k_proj_resolve(const int* __restrict__ row_cnt, const int* __restrict__ row_off,
+                                                     const uint32_t* __restrict__ rows, const int32_t* __restrict__ mp_obs,
+                                                     int nmp, int n, float nnratio, int32_t* __restrict__ frame_mp,
+                                                     const int32_t* __restrict__ frame_mp_obs, uint8_t* __restrict__ held,
+                                                     int* __restrict__ nmatches_out) {
+  const int lane = threadIdx.x;
+  for (int i = lane; i < n; i += 32) held[i] = (frame_mp[i] >= 0 && frame_mp_obs && frame_mp_obs[i] > 0) ? 1 : 0;
+  __syncwarp();
+  int nmatches = 0;
+  for (int i = 0; i < nmp; ++i) {
+    const int cnt = row_cnt[i];
+    if (cnt == 0) continue;
+    const uint32_t* row = rows + row_off[i];
+    // key = dist << 16 | position; the level rides along in a second register
+    uint32_t best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
+    for (int c = lane; c < cnt; c += 32) {
+      const uint32_t e = row[c];
+      if (held[e & 0xFFFFu]) continue;
+      const uint32_t key = (e >> 20) << 16 | (uint32_t)c;
+      second = min(second, max(best, key));
+      best = min(best, key);
+    }
+    warp_top2(best, second);
+    if (best == 0xFFFFFFFFu) continue;
+    const int bestDist = (int)(best >> 16);
+    if (bestDist <= TH_HIGH) {
+      const uint32_t eb = row[best & 0xFFFFu];
+      const int bestLevel = (int)(eb >> 16 & 15u), bestIdx = (int)(eb & 0xFFFFu);
+      int bestDist2 = 256, bestLevel2 = -1;
+      if (second != 0xFFFFFFFFu) {
+        bestDist2 = (int)(second >> 16);
+        bestLevel2 = (int)(row[second & 0xFFFFu] >> 16 & 15u);
+      }
+      if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) continue;
+      if (lane == 0) {
+        frame_mp[bestIdx] = i;
+        held[bestIdx] = mp_obs ? (mp_obs[i] > 0 ? 1 : 0) : 1;
+      }
+      nmatches++;
+      __syncwarp();
+    }
+  }
+  if (lane == 0) *nmatches_out = nmatches;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+struct orbm_matcher {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long long launches = 0;
+  // growable device scratch
+  void* buf[12] = {nullptr};
+  size_t buf_bytes[12] = {0};
+
+  bool check(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+  }
+  template <typename T> T* scratch(int slot, size_t count) {
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    if (bytes > buf_bytes[slot]) {
+      cudaStreamSynchronize(stream);
+      cudaFree(buf[slot]);
+      buf[slot] = nullptr;
+      buf_bytes[slot] = 0;
+      if (!check(cudaMalloc(&buf[slot], bytes), "cudaMalloc(matcher scratch)")) return nullptr;
+      buf_bytes[slot] = bytes;
+    }
+    return reinterpret_cast<T*>(buf[slot]);
+  }
+};
+
+namespace {
+thread_local std::string g_mcreate_error;
+
+int bf_launch(orbm_matcher* m, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, float ratio, int th_dist,
+              int32_t* d_idx, int32_t* d_d1, int32_t* d_d2) {
+  if (nq == 0) return ORBX_OK;
+  const int qblocks = (nq + BF_THREADS * BF_QPT - 1) / (BF_THREADS * BF_QPT);
+  // enough target chunks to put >= ~4 CTAs on each of the 148 SMs; chunk <= 65536 (16-bit local index)
+  int nsplit = std::max(1, std::min((nt + BF_TILE - 1) / BF_TILE, (148 * 4 + qblocks - 1) / qblocks));
+  nsplit = std::max(nsplit, (nt + 65535) / 65536);
+  int chunk = nt > 0 ? (nt + nsplit - 1) / nsplit : 1;
+  chunk = (chunk + BF_TILE - 1) / BF_TILE * BF_TILE;
+  nsplit = nt > 0 ? (nt + chunk - 1) / chunk : 1;
+  uint2* partial = m->scratch<uint2>(0, (size_t)nsplit * nq);
+  if (!partial) return ORBX_E_CUDA;
+  k_bruteforce<<<dim3(qblocks, nsplit), BF_THREADS, 0, m->stream>>>(d_q, nq, d_t, nt, chunk, partial);
+  k_bf_merge<<<(nq + 255) / 256, 256, 0, m->stream>>>(partial, nq, nsplit, chunk, ratio, th_dist, d_idx, d_d1, d_d2);
+  m->launches += 2;
+  return m->check(cudaGetLastError(), "bruteforce launch") ? ORBX_OK : ORBX_E_CUDA;
+}
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int orbm_create(int device, orbm_matcher** out) {
+  if (!out) return ORBX_E_INVALID;
+  *out = nullptr;
+  orbm_matcher* m = new orbm_matcher();
+  int ndev = 0;
+  if (!m->check(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount") || ndev == 0) {
+    g_mcreate_error = m->err.empty() ? "no CUDA device (this library has no CPU fallback)" : m->err;
+    delete m;
+    return ORBX_E_CUDA;
+  }
+  if (device >= 0 && !m->check(cudaSetDevice(device), "cudaSetDevice")) { g_mcreate_error = m->err; delete m; return ORBX_E_CUDA; }
+  cudaGetDevice(&m->device);
+  if (!m->check(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+    g_mcreate_error = m->err;
+    delete m;
+    return ORBX_E_CUDA;
+  }
+  *out = m;
+  return ORBX_OK;
+}
+
+void orbm_destroy(orbm_matcher* m) {
+  if (!m) return;
+  cudaStreamSynchronize(m->stream);
+  for (auto& b : m->buf) cudaFree(b);
+  cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+const char* orbm_last_error(const orbm_matcher* m) { return m ? m->err.c_str() : g_mcreate_error.c_str(); }
+int orbm_sync(orbm_matcher* m) {
+  if (!m) return ORBX_E_INVALID;
+  return m->check(cudaStreamSynchronize(m->stream), "stream synchronize") ? ORBX_OK : ORBX_E_CUDA;
+}
+long long orbm_launch_count(const orbm_matcher* m) { return m ? m->launches : 0; }
+
+int orbm_distance_pairs_host(orbm_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* out) {
+  if (!m || !a || !b || !out || n < 0) return ORBX_E_INVALID;
+  if (n == 0) return ORBX_OK;
+  cudaSetDevice(m->device);
+  uint8_t* da = m->scratch<uint8_t>(1, (size_t)n * 32);
+  uint8_t* db = m->scratch<uint8_t>(2, (size_t)n * 32);
+  int32_t* dout = m->scratch<int32_t>(3, n);
+  if (!da || !db || !dout) return ORBX_E_CUDA;
+  cudaMemcpyAsync(da, a, (size_t)n * 32, cudaMemcpyHostToDevice, m->stream);
+  cudaMemcpyAsync(db, b, (size_t)n * 32, cudaMemcpyHostToDevice, m->stream);
+  k_distance_pairs<<<(n + 255) / 256, 256, 0, m->stream>>>(da, db, n, dout);
+  m->launches++;
+  cudaMemcpyAsync(out, dout, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, m->stream);
+  return m->check(cudaStreamSynchronize(m->stream), "distance_pairs") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+int orbm_bruteforce_device(orbm_matcher* m, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, float ratio,
+                           int th_dist, int32_t* d_idx, int32_t* d_d1, int32_t* d_d2) {
+  if (!m || nq < 0 || nt < 0 || (nq && (!d_q || !d_idx || !d_d1 || !d_d2)) || (nt && !d_t)) return ORBX_E_INVALID;
+  cudaSetDevice(m->device);
+  return bf_launch(m, d_q, nq, d_t, nt, ratio, th_dist, d_idx, d_d1, d_d2);
+}
+
+int orbm_bruteforce_host(orbm_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, float ratio, int th_dist,
+                         int32_t* idx, int32_t* d1, int32_t* d2) {
+  if (!m || nq < 0 || nt < 0 || (nq && (!q || !idx || !d1 || !d2)) || (nt && !t)) return ORBX_E_INVALID;
+  if (nq == 0) return ORBX_OK;
+  cudaSetDevice(m->device);
+  uint8_t* dq = m->scratch<uint8_t>(1, (size_t)nq * 32);
+  uint8_t* dt = m->scratch<uint8_t>(2, (size_t)nt * 32);
+  int32_t* dres = m->scratch<int32_t>(3, (size_t)nq * 3);
+  if (!dq || !dt || !dres) return ORBX_E_CUDA;
+  cudaMemcpyAsync(dq, q, (size_t)nq * 32, cudaMemcpyHostToDevice, m->stream);
+  if (nt) cudaMemcpyAsync(dt, t, (size_t)nt * 32, cudaMemcpyHostToDevice, m->stream);
+  const int rc = bf_launch(m, dq, nq, dt, nt, ratio, th_dist, dres, dres + nq, dres + 2 * nq);
+  if (rc != ORBX_OK) return rc;
+  cudaMemcpyAsync(idx, dres, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, m->stream);
+  cudaMemcpyAsync(d1, dres + nq, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, m->stream);
+  cudaMemcpyAsync(d2, dres + 2 * nq, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, m->stream);
+  return m->check(cudaStreamSynchronize(m->stream), "bruteforce") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+int orbm_search_for_initialization_device(orbm_matcher* m, int n_pairs, int cap, const orbx_keypoint* d_k1,
+                                          const uint8_t* d_d1, const int32_t* d_n1, const orbx_keypoint* d_k2,
+                                          const uint8_t* d_d2, const int32_t* d_n2, orbm_bounds bounds2,
+                                          float* d_prev_xy, int window, float nnratio, int check_ori,
+                                          int32_t* d_matches12, int32_t* d_nmatches) {
+  if (!m || n_pairs < 0 || cap < 1 || cap > 65535) return ORBX_E_INVALID;
+  if (n_pairs == 0) return ORBX_OK;
+  cudaSetDevice(m->device);
+  const size_t smem = sizeof(int) * 3 * (size_t)cap;
+  if (smem > 200 * 1024) { m->err = "cap too large for SearchForInitialization"; return ORBX_E_INVALID; }
+  // candidate rows are cap x cap per pair: process pairs in groups that keep the scratch <= ~2 GiB
+  const size_t per_pair = (size_t)cap * cap * sizeof(uint32_t);
+  const int group = (int)std::max<size_t>(1, std::min<size_t>(n_pairs, ((size_t)2 << 30) / per_pair));
+  int* gstart = m->scratch<int>(4, (size_t)group * (GRID_CELLS + 1));
+  uint16_t* gitems = m->scratch<uint16_t>(5, (size_t)group * cap);
+  uint32_t* cand = m->scratch<uint32_t>(6, (size_t)group * cap * cap);
+  int* cand_cnt = m->scratch<int>(7, (size_t)group * cap);
+  if (!gstart || !gitems || !cand || !cand_cnt) return ORBX_E_CUDA;
+  if (!m->check(cudaFuncSetAttribute(k_search_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in"))
+    return ORBX_E_CUDA;
+  for (int p0 = 0; p0 < n_pairs; p0 += group) {
+    const int np = std::min(group, n_pairs - p0);
+    const size_t o = (size_t)p0 * cap;
+    k_build_grid<<<np, 256, 0, m->stream>>>(d_k2 + o, d_n2 + p0, 0, cap, bounds2, gstart, gitems);
+    k_search_init<<<np, 256, smem, m->stream>>>(cap, d_k1 + o, d_d1 + o * 32, d_n1 + p0, d_k2 + o, d_d2 + o * 32, d_n2 + p0,
+                                                bounds2, gstart, gitems, d_prev_xy + o * 2, (float)window, nnratio, check_ori,
+                                                cand, cand_cnt, d_matches12 + o, d_nmatches + p0);
+    m->launches += 2;
+  }
+  return m->check(cudaGetLastError(), "search_for_initialization launch") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+int orbm_search_for_initialization_host(orbm_matcher* m, int n_pairs, int cap, const orbx_keypoint* k1, const uint8_t* d1,
+                                        const int32_t* n1, const orbx_keypoint* k2, const uint8_t* d2, const int32_t* n2,
+                                        orbm_bounds bounds2, float* prev_xy, int window, float nnratio, int check_ori,
+                                        int32_t* matches12, int32_t* nmatches) {
+  if (!m || n_pairs < 0 || cap < 1) return ORBX_E_INVALID;
+  if (n_pairs == 0) return ORBX_OK;
+  cudaSetDevice(m->device);
+  const size_t nk = (size_t)n_pairs * cap;
+  orbx_keypoint* dk = m->scratch<orbx_keypoint>(8, 2 * nk);
+  uint8_t* dd = m->scratch<uint8_t>(9, 2 * nk * 32);
+  int32_t* dn = m->scratch<int32_t>(10, 3 * (size_t)n_pairs + nk);
+  float* dprev = m->scratch<float>(11, nk * 2);
+  if (!dk || !dd || !dn || !dprev) return ORBX_E_CUDA;
+  cudaStream_t st = m->stream;
+  cudaMemcpyAsync(dk, k1, nk * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dk + nk, k2, nk * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dd, d1, nk * 32, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dd + nk * 32, d2, nk * 32, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dn, n1, sizeof(int32_t) * n_pairs, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dn + n_pairs, n2, sizeof(int32_t) * n_pairs, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dprev, prev_xy, nk * 2 * sizeof(float), cudaMemcpyHostToDevice, st);
+  int32_t* dnm = dn + 2 * n_pairs;
+  int32_t* dm12 = dn + 3 * n_pairs;
+  const int rc = orbm_search_for_initialization_device(m, n_pairs, cap, dk, dd, dn, dk + nk, dd + nk * 32, dn + n_pairs,
+                                                       bounds2, dprev, window, nnratio, check_ori, dm12, dnm);
+  if (rc != ORBX_OK) return rc;
+  cudaMemcpyAsync(matches12, dm12, nk * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(nmatches, dnm, sizeof(int32_t) * n_pairs, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(prev_xy, dprev, nk * 2 * sizeof(float), cudaMemcpyDeviceToHost, st);
+  return m->check(cudaStreamSynchronize(st), "search_for_initialization") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+int orbm_search_by_projection_points_host(orbm_matcher* m, const orbx_keypoint* k, const uint8_t* desc,
+                                          const float* u_right, int n, orbm_bounds bounds, const float* scale_factors,
+                                          int nlevels, const orbm_mappoint* mp, const uint8_t* mp_desc,
+                                          const int32_t* mp_obs, int nmp, float th, float nnratio, int32_t* frame_mp,
+                                          const int32_t* frame_mp_obs, int* nmatches) {
+  if (!m || !k || !desc || !scale_factors || !frame_mp || !nmatches || n < 0 || n > 65535 || nmp < 0 || nlevels < 1 ||
+      nlevels > ORBX_MAX_LEVELS || (nmp && (!mp || !mp_desc)))
+    return ORBX_E_INVALID;
+  *nmatches = 0;
+  if (n == 0 || nmp == 0) return ORBX_OK;
+  for (int i = 0; i < nmp; ++i)
+    if (mp[i].track_in_view && !mp[i].bad && (mp[i].level < 0 || mp[i].level >= nlevels)) {
+      m->err = "map point level out of range";
+      return ORBX_E_INVALID;
+    }
+  cudaSetDevice(m->device);
+  cudaStream_t st = m->stream;
+  // frame side
+  const size_t frame_bytes = (size_t)n * (sizeof(orbx_keypoint) + 32 + 4 + 4 + 4 + 1) + 64 * 4;
+  uint8_t* fb = m->scratch<uint8_t>(8, frame_bytes + 256);
+  // map-point side
+  const size_t mp_bytes = (size_t)nmp * (sizeof(orbm_mappoint) + 32 + 4 + 4 + 4) + 256;
+  uint8_t* mb = m->scratch<uint8_t>(9, mp_bytes);
+  int* gstart = m->scratch<int>(4, GRID_CELLS + 1);
+  uint16_t* gitems = m->scratch<uint16_t>(5, n);
+  int* misc = m->scratch<int>(10, 8);
+  if (!fb || !mb || !gstart || !gitems || !misc) return ORBX_E_CUDA;
+  uint8_t* dd = fb;  // descriptors first: uint4 loads need 16-byte alignment
+  orbx_keypoint* dk = reinterpret_cast<orbx_keypoint*>(dd + (size_t)n * 32);
+  float* dur = reinterpret_cast<float*>(dk + n);
+  int32_t* dfmp = reinterpret_cast<int32_t*>(dur + n);
+  int32_t* dfobs = dfmp + n;
+  float* dsf = reinterpret_cast<float*>(dfobs + n);
+  uint8_t* dheld = reinterpret_cast<uint8_t*>(dsf + 64);
+  uint8_t* dmd = mb;
+  orbm_mappoint* dmp = reinterpret_cast<orbm_mappoint*>(dmd + (size_t)nmp * 32);
+  int32_t* dmobs = reinterpret_cast<int32_t*>(dmp + nmp);
+  int* drow_cnt = dmobs + nmp;
+  int* drow_off = drow_cnt + nmp;
+  cudaMemcpyAsync(dk, k, sizeof(orbx_keypoint) * n, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dd, desc, (size_t)n * 32, cudaMemcpyHostToDevice, st);
+  if (u_right) cudaMemcpyAsync(dur, u_right, sizeof(float) * n, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dfmp, frame_mp, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
+  if (frame_mp_obs) cudaMemcpyAsync(dfobs, frame_mp_obs, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dsf, scale_factors, sizeof(float) * nlevels, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dmp, mp, sizeof(orbm_mappoint) * nmp, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dmd, mp_desc, (size_t)nmp * 32, cudaMemcpyHostToDevice, st);
+  if (mp_obs) cudaMemcpyAsync(dmobs, mp_obs, sizeof(int32_t) * nmp, cudaMemcpyHostToDevice, st);
+  k_build_grid<<<1, 256, 0, st>>>(dk, nullptr, n, n, bounds, gstart, gitems);
+  const int blocks = (nmp + 7) / 8;
+  k_proj_candidates<<<blocks, 256, 0, st>>>(dk, dd, u_right ? dur : nullptr, bounds, gstart, gitems, dsf, dmp, dmd, nmp, th, 1,
+                                            drow_cnt, nullptr, nullptr);
+  k_scan_exclusive<<<1, 1024, 0, st>>>(drow_cnt, drow_off, nmp, misc);
+  m->launches += 3;
+  int total = 0;
+  cudaMemcpyAsync(&total, misc, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (!m->check(cudaStreamSynchronize(st), "projection candidates (count)")) return ORBX_E_CUDA;
+  uint32_t* rows = m->scratch<uint32_t>(6, (size_t)total);
+  if (!rows) return ORBX_E_CUDA;
+  k_proj_candidates<<<blocks, 256, 0, st>>>(dk, dd, u_right ? dur : nullptr, bounds, gstart, gitems, dsf, dmp, dmd, nmp, th, 0,
+                                            drow_cnt, drow_off, rows);
+  k_proj_resolve<<<1, 32, 0, st>>>(drow_cnt, drow_off, rows, mp_obs ? dmobs : nullptr, nmp, n, nnratio, dfmp,
+                                   frame_mp_obs ? dfobs : nullptr, dheld, misc + 1);
+  m->launches += 2;
+  cudaMemcpyAsync(frame_mp, dfmp, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(nmatches, misc + 1, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (!m->check(cudaStreamSynchronize(st), "search_by_projection")) return ORBX_E_CUDA;
+  return m->check(cudaGetLastError(), "search_by_projection launch") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,173 @@
+"""Host-side mirror of the hot members of the reference's `ORB_SLAM2::ORBmatcher`
+(include/ORBmatcher.h:37-137, src/ORBmatcher.cc) over the C-ABI CUDA library, plus the flat
+`Frame` / `MapPoints` containers that stand in for the reference's object graphs
+(include/Frame.h, include/MapPoint.h): only the fields the matcher reads."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import KP_DTYPE, MP_DTYPE, Bounds, check_m, lib
+
+
+@dataclass
+class Frame:
+    """Fields of ORB_SLAM2::Frame read by the matcher: mvKeysUn, mDescriptors, mvuRight,
+    mvScaleFactors, mnMinX/MaxX/MinY/MaxY (image bounds, src/Frame.cc:262-278), mvpMapPoints
+    (here: index into the MapPoints passed to the search, -1 = none)."""
+    mvKeysUn: np.ndarray
+    mDescriptors: np.ndarray
+    width: float
+    height: float
+    mvScaleFactors: Optional[np.ndarray] = None
+    mvuRight: Optional[np.ndarray] = None
+    mvpMapPoints: Optional[np.ndarray] = None
+    mvpMapPointsObserved: Optional[np.ndarray] = None  # Observations()>0 of the held points
+
+    def __post_init__(self):
+        self.mvKeysUn = np.ascontiguousarray(self.mvKeysUn, dtype=KP_DTYPE)
+        self.mDescriptors = np.ascontiguousarray(self.mDescriptors, dtype=np.uint8).reshape(-1, 32)
+        if self.mvpMapPoints is None:
+            self.mvpMapPoints = np.full(len(self.mvKeysUn), -1, dtype=np.int32)
+
+    @property
+    def N(self) -> int:
+        return len(self.mvKeysUn)
+
+    @property
+    def bounds(self) -> Bounds:
+        return Bounds(0.0, float(self.width), 0.0, float(self.height))
+
+
+@dataclass
+class MapPoints:
+    """Struct-of-arrays view of vector<MapPoint*>: the tracking fields written by
+    Frame::isInFrustum (src/Frame.cc:443-499) and the representative descriptors."""
+    fields: np.ndarray                 # MP_DTYPE
+    descriptors: np.ndarray            # [n, 32] u8   (MapPoint::GetDescriptor)
+    observed: Optional[np.ndarray] = None  # Observations()>0, default all true
+
+    def __post_init__(self):
+        self.fields = np.ascontiguousarray(self.fields, dtype=MP_DTYPE)
+        self.descriptors = np.ascontiguousarray(self.descriptors, dtype=np.uint8).reshape(-1, 32)
+
+
+class ORBmatcher:
+    TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30  # src/ORBmatcher.cc:37-39
+
+    def __init__(self, nnratio: float = 0.6, checkOri: bool = True, *, device: int = -1):
+        self.mfNNratio, self.mbCheckOrientation = float(nnratio), bool(checkOri)
+        h = C.c_void_p()
+        rc = lib.orbm_create(device, C.byref(h))
+        if rc != _lib.OK:
+            raise _lib.OrbError(rc, (lib.orbm_last_error(None) or b"").decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.orbm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return lib.orbm_launch_count(self._h)
+
+    def sync(self):
+        check_m(self._h, lib.orbm_sync(self._h))
+
+    # -- DescriptorDistance (src/ORBmatcher.cc:3994-4010) ---------------------------------------
+    def DescriptorDistance(self, a: np.ndarray, b: np.ndarray) -> int:
+        return int(self.distance_pairs(np.asarray(a).reshape(1, 32), np.asarray(b).reshape(1, 32))[0])
+
+    def distance_pairs(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, dtype=np.uint8).reshape(-1, 32)
+        assert a.shape == b.shape
+        out = np.zeros(len(a), dtype=np.int32)
+        check_m(self._h, lib.orbm_distance_pairs_host(self._h, a.ctypes.data, b.ctypes.data, len(a), out.ctypes.data))
+        return out
+
+    # -- brute force best/second-best with ratio test ---------------------------------------------
+    def bruteforce(self, q: np.ndarray, t: np.ndarray, th_dist: int = TH_LOW, ratio: Optional[float] = None):
+        q = np.ascontiguousarray(q, dtype=np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(t, dtype=np.uint8).reshape(-1, 32)
+        idx, d1, d2 = (np.zeros(len(q), dtype=np.int32) for _ in range(3))
+        check_m(self._h, lib.orbm_bruteforce_host(self._h, q.ctypes.data, len(q), t.ctypes.data, len(t),
+                                                  self.mfNNratio if ratio is None else ratio, th_dist, idx.ctypes.data,
+                                                  d1.ctypes.data, d2.ctypes.data))
+        return idx, d1, d2
+
+    def bruteforce_device(self, q, t, idx, d1, d2, th_dist: int = TH_LOW, ratio: Optional[float] = None):
+        """torch CUDA tensors: q [nq,32] u8, t [nt,32] u8, idx/d1/d2 [nq] i32.  Asynchronous."""
+        check_m(self._h, lib.orbm_bruteforce_device(self._h, q.data_ptr(), q.shape[0], t.data_ptr(), t.shape[0],
+                                                    self.mfNNratio if ratio is None else ratio, th_dist, idx.data_ptr(),
+                                                    d1.data_ptr(), d2.data_ptr()))
+
+    # -- SearchForInitialization (src/ORBmatcher.cc:868-983) --------------------------------------
+    def SearchForInitialization(self, F1: Frame, F2: Frame, vbPrevMatched: np.ndarray, windowSize: int = 10):
+        """Returns (nmatches, vnMatches12); vbPrevMatched ([N1,2] f32) is updated in place."""
+        n, m12, prev = self.search_for_initialization_batch(
+            F1.mvKeysUn[None], F1.mDescriptors[None], np.array([F1.N], dtype=np.int32),
+            F2.mvKeysUn[None], F2.mDescriptors[None], np.array([F2.N], dtype=np.int32), F2.bounds,
+            np.asarray(vbPrevMatched, dtype=np.float32).reshape(1, -1, 2), windowSize)
+        vbPrevMatched[...] = prev[0, : len(vbPrevMatched)]
+        return int(n[0]), m12[0, : F1.N].copy()
+
+    def search_for_initialization_batch(self, k1, d1, n1, k2, d2, n2, bounds2: Bounds, prev_xy, windowSize: int = 10):
+        """Batch of independent frame pairs.  k1/k2 [P, cap] KP_DTYPE, d1/d2 [P, cap, 32], n1/n2 [P],
+        prev_xy [P, cap, 2].  Arrays narrower than the common cap are padded."""
+        P = len(n1)
+        cap = max(k1.shape[1], k2.shape[1], 1)
+
+        def pad(a, shape, dtype):
+            out = np.zeros(shape, dtype=dtype)
+            out[:, : a.shape[1]] = a
+            return out
+        k1p, k2p = pad(k1, (P, cap), KP_DTYPE), pad(k2, (P, cap), KP_DTYPE)
+        d1p, d2p = pad(d1, (P, cap, 32), np.uint8), pad(d2, (P, cap, 32), np.uint8)
+        prev = pad(np.asarray(prev_xy, dtype=np.float32), (P, cap, 2), np.float32)
+        n1 = np.ascontiguousarray(n1, dtype=np.int32)
+        n2 = np.ascontiguousarray(n2, dtype=np.int32)
+        m12 = np.full((P, cap), -1, dtype=np.int32)
+        nm = np.zeros(P, dtype=np.int32)
+        check_m(self._h, lib.orbm_search_for_initialization_host(
+            self._h, P, cap, k1p.ctypes.data, d1p.ctypes.data, n1.ctypes.data, k2p.ctypes.data, d2p.ctypes.data,
+            n2.ctypes.data, bounds2, prev.ctypes.data, int(windowSize), self.mfNNratio, int(self.mbCheckOrientation),
+            m12.ctypes.data, nm.ctypes.data))
+        return nm, m12, prev
+
+    def search_for_initialization_device(self, P, cap, k1, d1, n1, k2, d2, n2, bounds2: Bounds, prev_xy, windowSize,
+                                         matches12, nmatches):
+        """Device-resident batch (torch CUDA tensors laid out as the extractor's batch outputs)."""
+        check_m(self._h, lib.orbm_search_for_initialization_device(
+            self._h, P, cap, k1.data_ptr(), d1.data_ptr(), n1.data_ptr(), k2.data_ptr(), d2.data_ptr(), n2.data_ptr(),
+            bounds2, prev_xy.data_ptr(), int(windowSize), self.mfNNratio, int(self.mbCheckOrientation),
+            matches12.data_ptr(), nmatches.data_ptr()))
+
+    # -- SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:62-157) ------------
+    def SearchByProjection(self, F: Frame, vpMapPoints: MapPoints, th: float = 3.0) -> int:
+        """Assigns map-point indices into F.mvpMapPoints; returns nmatches."""
+        n = F.N
+        sf = np.ascontiguousarray(F.mvScaleFactors, dtype=np.float32)
+        ur = None if F.mvuRight is None else np.ascontiguousarray(F.mvuRight, dtype=np.float32)
+        obs = None if vpMapPoints.observed is None else np.ascontiguousarray(vpMapPoints.observed, dtype=np.int32)
+        fobs = None if F.mvpMapPointsObserved is None else np.ascontiguousarray(F.mvpMapPointsObserved, dtype=np.int32)
+        fmp = np.ascontiguousarray(F.mvpMapPoints, dtype=np.int32)
+        nm = C.c_int(0)
+        check_m(self._h, lib.orbm_search_by_projection_points_host(
+            self._h, F.mvKeysUn.ctypes.data, F.mDescriptors.ctypes.data, None if ur is None else ur.ctypes.data, n,
+            F.bounds, sf.ctypes.data, len(sf), vpMapPoints.fields.ctypes.data, vpMapPoints.descriptors.ctypes.data,
+            None if obs is None else obs.ctypes.data, len(vpMapPoints.fields), float(th), self.mfNNratio,
+            fmp.ctypes.data, None if fobs is None else fobs.ctypes.data, C.byref(nm)))
+        F.mvpMapPoints = fmp
+        return nm.value

@@ -1,0 +1,102 @@
+"""Pins the oracle's OpenCV-primitive restatements (oracle/cvprim.cc) bit-exact against the real
+cv2 4.13 wheel — the only OpenCV available here.  Skipped where cv2 is
+not importable; tests/test_golden.py covers the same primitives from committed fixtures."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+
+from multi_orb_slam_b200.synth import textured
+
+
+@pytest.fixture(scope="module")
+def lib(oracle_port):
+    return oracle_port.load("port")
+
+
+def _images():
+    rng = np.random.default_rng(123)
+    yield "noise", rng.integers(0, 256, size=(480, 640), dtype=np.uint8)
+    yield "textured", textured(640, 480, 3)
+    yield "odd", rng.integers(0, 256, size=(67, 131), dtype=np.uint8)
+    yield "kitti", textured(1241, 376, 5)
+
+
+@pytest.mark.parametrize("name,img", list(_images()))
+def test_resize_chain(lib, name, img):
+    cur = img
+    for _ in range(4):
+        h, w = cur.shape
+        dw, dh = int(np.rint(np.float32(w) / np.float32(1.2))), int(np.rint(np.float32(h) / np.float32(1.2)))
+        want = cv2.resize(cur, (dw, dh), interpolation=cv2.INTER_LINEAR)
+        got = np.zeros((dh, dw), dtype=np.uint8)
+        lib.cvp_resize(C.c_void_p(cur.ctypes.data), C.c_size_t(cur.strides[0]), w, h,
+                       C.c_void_p(got.ctypes.data), C.c_size_t(got.strides[0]), dw, dh)
+        assert np.array_equal(got, want), name
+        cur = want
+
+
+@pytest.mark.parametrize("name,img", list(_images()))
+def test_border(lib, name, img):
+    want = cv2.copyMakeBorder(img, 19, 19, 19, 19, cv2.BORDER_REFLECT_101)
+    got = np.zeros_like(want)
+    got[19:-19, 19:-19] = img
+    lib.cvp_border(C.c_void_p(got.ctypes.data), C.c_size_t(got.strides[0]), img.shape[1], img.shape[0], 19)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name,img", list(_images()))
+def test_gaussian_blur(lib, name, img):
+    want = cv2.GaussianBlur(img, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+    got = np.zeros_like(img)
+    lib.cvp_blur(C.c_void_p(img.ctypes.data), C.c_size_t(img.strides[0]), C.c_void_p(got.ctypes.data),
+                 C.c_size_t(got.strides[0]), img.shape[1], img.shape[0])
+    assert np.array_equal(got, want)
+
+
+def _fast(lib, img, th):
+    cap = img.size
+    out = np.zeros((cap, 3), dtype=np.int32)
+    lib.cvp_fast.restype = C.c_int
+    n = lib.cvp_fast(C.c_void_p(img.ctypes.data), C.c_size_t(img.strides[0]), img.shape[1], img.shape[0], th, 1,
+                     C.c_void_p(out.ctypes.data), cap)
+    return out[:n]
+
+
+@pytest.mark.parametrize("th", [7, 20])
+@pytest.mark.parametrize("name,img", list(_images()))
+def test_fast(lib, name, img, th):
+    det = cv2.FastFeatureDetector_create(threshold=th, nonmaxSuppression=True,
+                                         type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    kps = det.detect(img, None)
+    want = np.array([[int(k.pt[0]), int(k.pt[1]), int(k.response)] for k in kps], dtype=np.int32).reshape(-1, 3)
+    got = _fast(lib, img, th)
+    assert np.array_equal(got, want), (name, th, len(got), len(want))
+
+
+def test_fast_cells(lib):
+    """Per-cell sub-image calls, as the reference makes them (src/ORBextractor.cc:790-830)."""
+    img = textured(640, 480, 9)
+    det = cv2.FastFeatureDetector_create(threshold=20, nonmaxSuppression=True)
+    for (y0, y1, x0, x1) in [(16, 54, 16, 53), (200, 238, 400, 437), (432, 464, 605, 624), (16, 23, 16, 23)]:
+        sub = img[y0:y1, x0:x1]
+        kps = det.detect(np.ascontiguousarray(sub), None)
+        want = np.array([[int(k.pt[0]), int(k.pt[1]), int(k.response)] for k in kps], dtype=np.int32).reshape(-1, 3)
+        got = _fast(lib, sub, 20)  # strided view: exercises step != width
+        assert np.array_equal(got, want)
+
+
+def test_fast_atan2(lib):
+    rng = np.random.default_rng(5)
+    y = rng.integers(-250000, 250000, size=100000).astype(np.float32)
+    x = rng.integers(-250000, 250000, size=100000).astype(np.float32)
+    y[:10] = 0
+    x[5:15] = 0
+    # the scalar cv::fastAtan2 the reference calls (ORBextractor.cc:103); cv2.phase's SIMD path
+    # contracts to FMA and differs by 1 ulp on ~2 % of inputs, so it is NOT the pin
+    want = np.array([cv2.fastAtan2(float(b), float(a)) for a, b in zip(x, y)], dtype=np.float32)
+    got = np.zeros_like(x)
+    lib.cvp_atan2(C.c_void_p(y.ctypes.data), C.c_void_p(x.ctypes.data), C.c_void_p(got.ctypes.data), len(x))
+    assert np.array_equal(got, want)

@@ -1,0 +1,174 @@
+"""GPU parity tests of the matcher kernels (through the C-ABI) against the flat-array CPU
+restatement of src/ORBmatcher.cc (oracle/matcher_oracle.cc).  Everything here is integer /
+index work: bit-exact."""
+import numpy as np
+import pytest
+
+from multi_orb_slam_b200.synth import perturbed_descriptors, random_descriptors, shifted_noisy, textured
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def O(oracle_port):
+    return oracle_port
+
+
+@pytest.fixture(scope="module")
+def M():
+    from multi_orb_slam_b200.matcher import ORBmatcher
+    return ORBmatcher(0.9, True)
+
+
+def test_distance_known_answers(M):
+    z, o = np.zeros(32, np.uint8), np.full(32, 255, np.uint8)
+    assert M.DescriptorDistance(z, o) == 256
+    assert M.DescriptorDistance(o, o) == 0
+    for bit in (0, 7, 100, 255):
+        a = z.copy()
+        a[bit // 8] |= 1 << (bit % 8)
+        assert M.DescriptorDistance(z, a) == 1
+
+
+def test_distance_pairs_vs_oracle(M, O):
+    a, b = random_descriptors(5000, 1), random_descriptors(5000, 2)
+    got = M.distance_pairs(a, b)
+    want = np.array([O.distance(a[i], b[i]) for i in range(0, 5000, 7)])
+    assert np.array_equal(got[::7], want)
+    assert np.array_equal(got, np.unpackbits(a ^ b, axis=1).sum(axis=1))
+
+
+@pytest.mark.parametrize("nq,nt", [(1, 1), (1000, 1000), (777, 3001), (4096, 4096), (3, 70000), (257, 255)])
+def test_bruteforce_vs_oracle(M, O, nq, nt):
+    A = random_descriptors(max(nq, nt), 7)
+    B, _ = perturbed_descriptors(A, 8)
+    q, t = A[:nq], B[:nt]
+    idx, d1, d2 = M.bruteforce(q, t, th_dist=50, ratio=0.9)
+    ridx, rd1, rd2 = O.bruteforce(q, t, 0.9, 50)
+    assert np.array_equal(d1, rd1) and np.array_equal(d2, rd2) and np.array_equal(idx, ridx)
+    if nq >= 777:
+        assert (idx >= 0).sum() > 0
+
+
+def test_bruteforce_ties_take_lowest_index(M, O):
+    t = np.repeat(random_descriptors(4, 3), 300, axis=0)  # many exact duplicates
+    q = t[::150].copy()
+    idx, d1, d2 = M.bruteforce(q, t, th_dist=50, ratio=2.0)
+    ridx, rd1, rd2 = O.bruteforce(q, t, 2.0, 50)
+    assert np.array_equal(idx, ridx) and np.array_equal(d1, rd1) and np.array_equal(d2, rd2)
+    assert (d1 == 0).all() and (d2 == 0).all()
+
+
+def test_bruteforce_empty_targets(M):
+    idx, d1, d2 = M.bruteforce(random_descriptors(5, 1), np.zeros((0, 32), np.uint8))
+    assert (idx == -1).all() and (d1 == 256).all() and (d2 == 256).all()
+
+
+def test_bruteforce_full_size_properties(M):
+    """64k x 64k (BASELINE.json config 3 upper end): size-independent properties instead of the
+    oracle — every row of B is A[perm] with <=80 flips, so best distance equals the flip count
+    and the match recovers the permutation wherever the ratio test accepts."""
+    n = 65536
+    A = random_descriptors(n, 7)
+    B, perm = perturbed_descriptors(A, 8)
+    idx, d1, d2 = M.bruteforce(B, A, th_dist=50, ratio=0.9)
+    flips = np.unpackbits(B ^ A[perm], axis=1).sum(axis=1)
+    assert np.array_equal(d1, np.minimum(d1, flips)) and (d1 <= flips).all()
+    ok = idx >= 0
+    assert ok.sum() > n // 3
+    assert np.array_equal(idx[ok], perm[ok])
+    assert (d1[ok] == flips[ok]).all() and (d1[ok] <= 50).all()
+    assert (d1[ok].astype(np.float32) < np.float32(0.9) * d2[ok].astype(np.float32)).all()
+
+
+def _frame_pair(O, seed):
+    port = O.extractor("port")
+    img1 = textured(640, 480, seed)
+    img2 = shifted_noisy(img1, 1000 + seed)
+    k1, d1, _ = port.extract(img1)
+    k2, d2, _ = port.extract(img2)
+    return k1, d1, k2, d2
+
+
+@pytest.mark.parametrize("window,check_ori", [(100, True), (30, True), (100, False), (1000, True)])
+def test_search_for_initialization_vs_oracle(M, O, window, check_ori):
+    from multi_orb_slam_b200.matcher import Frame, ORBmatcher
+    m = ORBmatcher(0.9, check_ori)
+    for seed in (0, 1):
+        k1, d1, k2, d2 = _frame_pair(O, seed)
+        prev = np.stack([k1["x"], k1["y"]], axis=1).astype(np.float32)
+        rn, rm12, rprev = O.search_for_initialization(k1, d1, k2, d2, (0, 640, 0, 480), prev, window, 0.9, check_ori)
+        F1, F2 = Frame(k1, d1, 640, 480), Frame(k2, d2, 640, 480)
+        gprev = prev.copy()
+        gn, gm12 = m.SearchForInitialization(F1, F2, gprev, window)
+        assert gn == rn and np.array_equal(gm12, rm12) and np.array_equal(gprev, rprev)
+        assert rn > 20
+
+
+def test_search_for_initialization_batch(M, O):
+    pairs = [_frame_pair(O, s) for s in (3, 4, 5)]
+    cap = max(max(len(p[0]), len(p[2])) for p in pairs)
+    from multi_orb_slam_b200._lib import KP_DTYPE, Bounds
+    P = len(pairs)
+    k1 = np.zeros((P, cap), KP_DTYPE); k2 = np.zeros((P, cap), KP_DTYPE)
+    d1 = np.zeros((P, cap, 32), np.uint8); d2 = np.zeros((P, cap, 32), np.uint8)
+    prev = np.zeros((P, cap, 2), np.float32)
+    n1 = np.zeros(P, np.int32); n2 = np.zeros(P, np.int32)
+    for p, (a, da, b, db) in enumerate(pairs):
+        n1[p], n2[p] = len(a), len(b)
+        k1[p, : len(a)], d1[p, : len(a)], k2[p, : len(b)], d2[p, : len(b)] = a, da, b, db
+        prev[p, : len(a), 0], prev[p, : len(a), 1] = a["x"], a["y"]
+    nm, m12, newprev = M.search_for_initialization_batch(k1, d1, n1, k2, d2, n2, Bounds(0, 640, 0, 480), prev, 100)
+    for p, (a, da, b, db) in enumerate(pairs):
+        rn, rm12, rprev = O.search_for_initialization(a, da, b, db, (0, 640, 0, 480), prev[p, : len(a)], 100, 0.9, True)
+        assert nm[p] == rn and np.array_equal(m12[p, : len(a)], rm12) and np.array_equal(newprev[p, : len(a)], rprev)
+
+
+def _projection_case(O, seed, nmp, th_levels=8):
+    from multi_orb_slam_b200._lib import MP_DTYPE
+    port = O.extractor("port", nfeatures=2000)
+    img = textured(1241, 376, seed)
+    k, d, _ = port.extract(img)
+    rng = np.random.default_rng(seed + 50)
+    mp = np.zeros(nmp, MP_DTYPE)
+    src = rng.integers(0, len(k), nmp)
+    # most points project near the keypoint they were derived from, some anywhere
+    near = rng.random(nmp) < 0.8
+    mp["proj_x"] = np.where(near, k["x"][src] + rng.normal(0, 3, nmp), rng.uniform(0, 1241, nmp)).astype(np.float32)
+    mp["proj_y"] = np.where(near, k["y"][src] + rng.normal(0, 3, nmp), rng.uniform(0, 376, nmp)).astype(np.float32)
+    mp["proj_xr"] = mp["proj_x"] - 5
+    mp["view_cos"] = rng.uniform(0.5, 1.0, nmp).astype(np.float32)
+    mp["view_cos"][rng.random(nmp) < 0.1] = 0.9995
+    mp["level"] = np.where(near, np.clip(k["octave"][src] + rng.integers(0, 2, nmp), 0, 7), rng.integers(0, 8, nmp))
+    mp["track_in_view"] = rng.random(nmp) < 0.95
+    mp["bad"] = rng.random(nmp) < 0.03
+    bits = np.unpackbits(d[src], axis=1)
+    flips = rng.integers(0, 61, nmp)
+    bits ^= (np.argsort(np.argsort(rng.random((nmp, 256)), axis=1), axis=1) < flips[:, None]).astype(np.uint8)
+    return k, d, mp, np.packbits(bits, axis=1), rng
+
+
+@pytest.mark.parametrize("nmp,th,with_stereo,with_obs", [(3000, 3.0, False, False), (20000, 3.0, False, False),
+                                                          (5000, 1.0, True, True), (4000, 6.0, True, False)])
+def test_search_by_projection_points_vs_oracle(M, O, nmp, th, with_stereo, with_obs):
+    from multi_orb_slam_b200.matcher import Frame, MapPoints, ORBmatcher
+    k, d, mp, mpd, rng = _projection_case(O, 2, nmp)
+    sf = O.extractor("port").scale_tables()[0]
+    n = len(k)
+    ur = np.full(n, -1, np.float32)
+    if with_stereo:
+        ur = np.where(rng.random(n) < 0.6, k["x"] - rng.uniform(0, 12, n), -1).astype(np.float32)
+    mp_obs = np.ones(nmp, np.int32)
+    fmp0 = np.full(n, -1, np.int32)
+    fobs0 = np.zeros(n, np.int32)
+    if with_obs:
+        mp_obs = (rng.random(nmp) < 0.8).astype(np.int32)
+        held = rng.random(n) < 0.2
+        fmp0[held] = rng.integers(0, nmp, held.sum())
+        fobs0[held] = rng.random(held.sum()) < 0.7
+    m = ORBmatcher(0.8, True)
+    rn, rfmp = O.search_by_projection_points(k, d, ur, (0, 1241, 0, 376), sf, mp, mpd, mp_obs, th, 0.8, fmp0, fobs0)
+    F = Frame(k, d, 1241, 376, mvScaleFactors=sf, mvuRight=ur, mvpMapPoints=fmp0.copy(), mvpMapPointsObserved=fobs0)
+    gn = m.SearchByProjection(F, MapPoints(mp, mpd, mp_obs), th)
+    assert gn == rn and np.array_equal(F.mvpMapPoints, rfmp)
+    assert rn > nmp // 20
