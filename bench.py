@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native ORB front end.
+
+    python bench.py --gpus N --steps K --warmup W          (torchrun launches N>1 ranks)
+    python bench.py --impl reference ...                    (CPU reference arm)
+
+A step = one pass of the hot path over one batch of synthetic input: BASELINE.json configs[1],
+the two-camera 640x480 rig (camera 1: nFeatures 1000, camera 2: 500 — src/Tracking.cc:144-145),
+256 rig-frames per GPU = 512 camera-frames, ORB extraction on every camera-frame plus
+SearchForInitialization (window 100, ORBmatcher(0.9,true), src/Tracking.cc:870-871) between
+consecutive frames of camera 1.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 640, 480
+NF0, NF1 = 1000, 500
+SCALE, NLEVELS, INI_TH, MIN_TH = 1.2, 8, 20, 7
+WINDOW, NNRATIO = 100, 0.9
+METRIC = "ORB camera-frames/sec @640x480 nFeatures=1000 8 lvls; Hamming matches/sec"
+UNIT = "camera-frames/s"
+
+
+def level_sizes(w, h):
+    out, s = [], np.float32(1.0)
+    for l in range(NLEVELS):
+        inv = np.float32(1.0) / s
+        out.append((int(np.rint(np.float32(w) * inv)), int(np.rint(np.float32(h) * inv))))
+        s = np.float32(np.float64(s) * np.float64(np.float32(SCALE)))
+    return out
+
+
+def stage_bytes_per_frame(w, h, k):
+    """Algorithmic HBM bytes per camera-frame by stage."""
+    lv = level_sizes(w, h)
+    px = sum(a * b for a, b in lv)
+    bordered = sum((a + 38) * (b + 38) for a, b in lv)
+    resize_reads = sum(a * b for a, b in lv[:-1])
+    return {
+        "pyramid": w * h + bordered + resize_reads,
+        "fast": px,
+        "octree": 0,  # a few KB of candidate keys: latency-bound policy replay, not a byte mover
+        "blur": 2 * px,
+        "orient_describe": k * (749 + 512 + 28 + 32),
+    }
+
+
+def make_sequences(n_rig, seed0):
+    """Two camera streams of n_rig frames: frame t+1 = frame t shifted by an integer offset plus noise."""
+    from multi_orb_slam_b200.synth import shifted_noisy, textured
+    cams = []
+    for c in range(2):
+        frames = [textured(W, H, seed0 + c)]
+        for t in range(1, n_rig):
+            frames.append(shifted_noisy(frames[-1], 1000 + 7919 * (seed0 + c) + t))
+        cams.append(np.stack(frames))
+    return cams
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle = test infrastructure; only timed here, never on the product path)
+def cpu_reference_run(cams, n_rig, threads):
+    """Times the reference's own CPU implementation of the step on `n_rig` rig-frames: the verbatim
+    ORBextractor.cc build (oracle/_ref) when present, else the restatement; matcher = restatement
+    of SearchForInitialization.  One extractor instance per thread over independent frames."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from concurrent.futures import ThreadPoolExecutor
+    oracle_lib.build_oracle()
+    kind = "reference" if oracle_lib.load("ref") is not None else "port"
+    libkind = "ref" if kind == "reference" else "port"
+    local = threading.local()
+
+    def ex_for(nf):
+        d = local.__dict__.setdefault("ex", {})
+        if nf not in d:
+            d[nf] = oracle_lib.extractor(libkind, nfeatures=nf, scale=SCALE, nlevels=NLEVELS, ini_th=INI_TH, min_th=MIN_TH)
+        return d[nf]
+
+    jobs = [(c, t) for t in range(n_rig) for c in range(2)]
+    results = {}
+
+    def extract(job):
+        c, t = job
+        results[job] = ex_for(NF0 if c == 0 else NF1).extract(cams[c][t])[:2]
+
+    def match(t):
+        k1, d1 = results[(0, t)]
+        k2, d2 = results[(0, t + 1)]
+        prev = np.stack([k1["x"], k1["y"]], axis=1).astype(np.float32)
+        return oracle_lib.search_for_initialization(k1, d1, k2, d2, (0, W, 0, H), prev, WINDOW, NNRATIO, True)[0]
+
+    with ThreadPoolExecutor(threads) as pool:
+        list(pool.map(extract, jobs[: 2 * threads]))  # warm-up: libraries, arenas, page faults
+        t0 = time.perf_counter()
+        list(pool.map(extract, jobs))
+        list(pool.map(match, range(n_rig - 1)))
+        dt = time.perf_counter() - t0
+    return 2 * n_rig / dt, dt, kind
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_rig = args.ref_rig_frames
+    cams = make_sequences(n_rig, 0)
+    vals = []
+    kind = "port"
+    for i in range(args.warmup + args.steps):
+        v, dt, kind = cpu_reference_run(cams, n_rig, threads)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals])) * 1e3
+    sample = f"{n_rig} rig-frames ({2 * n_rig} camera-frames) + {n_rig - 1} SearchForInitialization pairs per step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "configs[1]: two-camera 640x480 rig, extraction + SearchForInitialization",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rig-frames", type=int, default=256, help="rig-frames per GPU per step")
+    ap.add_argument("--ref-rig-frames", type=int, default=64, help="rig-frames per CPU reference step")
+    ap.add_argument("--cpu-rig-frames", type=int, default=96, help="rig-frames of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bf-size", type=int, default=65536, help="N of the N x N brute-force matching leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from multi_orb_slam_b200._lib import Bounds
+    from multi_orb_slam_b200.extractor import ORBextractor
+    from multi_orb_slam_b200.matcher import ORBmatcher
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    F = args.rig_frames
+    cams = make_sequences(F, 2 * rank)  # every rank owns its own rig-frames: independent units, no exchange
+    # pinned host copies (e2e leg) and HBM-resident copies (device leg)
+    h_img = [torch.from_numpy(c).pin_memory() for c in cams]
+    d_img = [t.to(dev) for t in h_img]
+    ex = [ORBextractor(NF0, SCALE, NLEVELS, INI_TH, MIN_TH, image_size=(W, H), max_batch=F, device=local_rank),
+          ORBextractor(NF1, SCALE, NLEVELS, INI_TH, MIN_TH, image_size=(W, H), max_batch=F, device=local_rank)]
+    matcher = ORBmatcher(NNRATIO, True, device=local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    for e in ex:
+        e.set_stream(stream.cuda_stream)
+    matcher.set_stream(stream.cuda_stream)
+    caps = [e.capacity for e in ex]
+    kps = [torch.empty((F, c, 6), dtype=torch.float32, device=dev) for c in caps]
+    desc = [torch.empty((F, c, 32), dtype=torch.uint8, device=dev) for c in caps]
+    counts = [torch.empty((F,), dtype=torch.int32, device=dev) for _ in caps]
+    m12 = torch.empty((F - 1, caps[0]), dtype=torch.int32, device=dev)
+    nmatch = torch.empty((F - 1,), dtype=torch.int32, device=dev)
+    bounds = Bounds(0.0, float(W), 0.0, float(H))
+    # pinned result buffers for the e2e leg
+    h_kps = [torch.empty((F, c, 6), dtype=torch.float32).pin_memory() for c in caps]
+    h_desc = [torch.empty((F, c, 32), dtype=torch.uint8).pin_memory() for c in caps]
+    h_counts = [torch.empty((F,), dtype=torch.int32).pin_memory() for _ in caps]
+    h_m12 = torch.empty((F - 1, caps[0]), dtype=torch.int32).pin_memory()
+    h_nmatch = torch.empty((F - 1,), dtype=torch.int32).pin_memory()
+    e2e_img = [torch.empty_like(t) for t in d_img]
+
+    def device_step(images):
+        for c in range(2):
+            ex[c].extract_batch_device(images[c], kps[c], desc[c], counts[c])
+        # pairs (t, t+1) of camera 1's stream: F2 arrays are the same buffers shifted by one frame
+        matcher.search_for_initialization_device(F - 1, caps[0], kps[0], desc[0], counts[0], kps[0][1:], desc[0][1:],
+                                                 counts[0][1:], bounds, None, WINDOW, m12, nmatch)
+
+    def e2e_step():
+        with torch.cuda.stream(stream):
+            for c in range(2):
+                e2e_img[c].copy_(h_img[c], non_blocking=True)
+            device_step(e2e_img)
+            for c in range(2):
+                h_kps[c].copy_(kps[c], non_blocking=True)
+                h_desc[c].copy_(desc[c], non_blocking=True)
+                h_counts[c].copy_(counts[c], non_blocking=True)
+            h_m12.copy_(m12, non_blocking=True)
+            h_nmatch.copy_(nmatch, non_blocking=True)
+        stream.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def launches():
+        return sum(e.launch_count for e in ex) + matcher.launch_count
+
+    def timed(fn, steps, sync_each):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+        stream.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident leg -------------------------------------------------------------------
+    for _ in range(args.warmup):
+        device_step(d_img)
+    stream.synchronize()
+    for e in ex:
+        e.set_profiling(True)
+    m_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    step_i = [0]
+
+    def profiled_step():
+        for c in range(2):
+            ex[c].extract_batch_device(d_img[c], kps[c], desc[c], counts[c])
+        a, b = m_ev[step_i[0]]
+        a.record(stream)
+        matcher.search_for_initialization_device(F - 1, caps[0], kps[0], desc[0], counts[0], kps[0][1:], desc[0][1:],
+                                                 counts[0][1:], bounds, None, WINDOW, m12, nmatch)
+        b.record(stream)
+        step_i[0] += 1
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = launches()
+    ms_step = timed(profiled_step, args.steps, False)
+    gpu_launches = launches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    stage_ms = np.zeros(5)
+    for e in ex:
+        s, n = e.stage_times_ms()
+        stage_ms += s / args.steps
+        e.set_profiling(False)
+    match_ms = float(np.mean([a.elapsed_time(b) for a, b in m_ev]))
+    total_matches = int(nmatch.sum().item())
+    n_kp = [int(c.sum().item()) for c in counts]
+
+    # ---- end-to-end leg (pinned host -> device -> pinned host every step) -----------------------
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_ms_dev = timed(e2e_step, args.steps, True)
+    e2e_wall = (time.perf_counter() - t0) / args.steps * 1e3
+    h2d = sum(t.numel() for t in h_img)
+    d2h = sum(t.numel() * t.element_size() for t in h_kps + h_desc + h_counts + [h_m12, h_nmatch])
+
+    # ---- Hamming matches/s: brute-force leg (BASELINE.json configs[2] upper end) ----------------
+    from multi_orb_slam_b200.synth import perturbed_descriptors, random_descriptors
+    nbf = args.bf_size
+    A = random_descriptors(nbf, 7)
+    Bq, _ = perturbed_descriptors(A, 8)
+    dA, dB = torch.from_numpy(A).to(dev), torch.from_numpy(Bq).to(dev)
+    bf_idx, bf_d1, bf_d2 = (torch.empty((nbf,), dtype=torch.int32, device=dev) for _ in range(3))
+
+    def bf_step():
+        matcher.bruteforce_device(dB, dA, bf_idx, bf_d1, bf_d2, th_dist=50, ratio=0.9)
+
+    for _ in range(3):
+        bf_step()
+    bf_ms = timed(bf_step, max(3, args.steps), False)
+    bf_pairs = float(nbf) * nbf * world / (bf_ms * 1e-3)
+    bf_accepted = int((bf_idx >= 0).sum().item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    frames_per_step = 2 * F * world
+    value = frames_per_step / (ms_step * 1e-3)
+    e2e_value = frames_per_step / (e2e_ms_dev * 1e-3)
+    peak, peak_src = load_peaks()
+    sb = stage_bytes_per_frame(W, H, NF0)
+    names = ["pyramid", "fast", "octree", "blur", "orient_describe"]
+    stages = {}
+    for i, nme in enumerate(names):
+        by = sb[nme] * 2 * F  # both cameras go through the same geometry
+        if nme == "orient_describe":
+            by = (749 + 512 + 28 + 32) * (n_kp[0] + n_kp[1])
+        gbs = by / (stage_ms[i] * 1e-3) / 1e9 if stage_ms[i] > 0 else 0.0
+        stages[nme] = {"ms": round(float(stage_ms[i]), 4), "algorithmic_gb": round(by / 1e9, 4),
+                       "gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)}
+    stages["search_for_initialization"] = {"ms": round(match_ms, 4)}
+    dom = max(names, key=lambda n: stages[n]["ms"])
+    total_alg = sum(sb[n] for n in names) * 2 * F
+    pipe_gbs = total_alg / (ms_step * 1e-3) / 1e9
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: two-camera 640x480 rig (cam1 nFeatures 1000, cam2 500, scale 1.2, 8 levels, "
+                               "FAST 20/7): ORB extraction of every camera-frame + SearchForInitialization(window 100, "
+                               "ratio 0.9) between consecutive camera-1 frames",
+                   "rig_frames_per_gpu": F, "camera_frames_per_step": frames_per_step,
+                   "l2_policy": "inputs (157 MB of frames per GPU per step) and workspace exceed the 126 MB L2",
+                   "parallelism": f"rig-frames sharded over {world} GPU(s), no data-path collective",
+                   "keypoints_per_step_rank0": n_kp, "init_matches_per_step_rank0": total_matches},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_ms_dev, "wall_ms_per_step": e2e_wall},
+        "gpu_launches": int(gpu_launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                     "frac": stages[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                     "pipeline": {"algorithmic_bytes_per_frame": int(sum(sb[n] for n in names)),
+                                  "achieved": round(pipe_gbs, 1), "frac": round(pipe_gbs / (peak * 1.0), 4)}},
+        "stages": stages,
+    }
+    sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
+    popc_peak = 148 * 16 * sm_max * 1e6 / 8  # pairs/s: 16 POPC32 lanes/clk/SM, 8 POPC per 256-bit pair
+    out["matching"] = {"workload": f"brute force {nbf} x {nbf} 256-bit descriptors, ratio 0.9, TH_LOW 50 (configs[2])",
+                       "value": bf_pairs, "unit": "Hamming pairs/s", "ms_per_step": bf_ms, "accepted": bf_accepted,
+                       "roofline": {"bound": "popc", "achieved": bf_pairs, "peak": popc_peak * world,
+                                    "unit": "pairs/s", "frac": bf_pairs / (popc_peak * world),
+                                    "peak_source": f"148 SM x 16 POPC/clk x {sm_max:.0f} MHz / 8 words"}}
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_rig = min(args.cpu_rig_frames, F)
+        v, dt, kind = cpu_reference_run([c[:n_rig] for c in cams], n_rig, threads)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+                               "sample": f"{n_rig} rig-frames ({2 * n_rig} camera-frames) + {n_rig - 1} "
+                                         f"SearchForInitialization pairs of the same workload, {dt:.2f} s wall"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -93,6 +93,9 @@ int orbx_extract_batch_device(orbx_extractor* h, const uint8_t* d_images, int n_
 int orbx_sync(orbx_extractor* h);
 /* cudaStream_t of the handle as an opaque pointer (to order foreign work after it). */
 void* orbx_stream(orbx_extractor* h);
+/* Run this handle's work on a caller-owned cudaStream_t (NULL restores the handle's own stream),
+ * e.g. to chain extractor -> matcher without host synchronisation. */
+int orbx_set_stream(orbx_extractor* h, void* cuda_stream);
 
 /* mvImagePyramid[level] (public member, include/ORBextractor.h:92) of frame `frame` of the last
  * batch, copied to host: with_border != 0 returns the (w+38) x (h+38) buffer including the
@@ -108,11 +111,13 @@ int orbx_debug_blurred(orbx_extractor* h, int frame, int level, uint8_t* dst, si
 
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 long long orbx_launch_count(const orbx_extractor* h);
-/* Device time in ms of the most recent *_batch_* call's kernels, by stage (CUDA events on the
- * handle's stream; valid after orbx_sync).  stages: 0 pyramid, 1 fast, 2 octree, 3 blur,
- * 4 orientation+descriptor.  Requires orbx_set_profiling(h, 1) before the call. */
+/* Per-stage device time (CUDA events recorded on the handle's stream around each stage's
+ * launches).  orbx_set_profiling(h, 1) clears the sums and starts recording on every launch
+ * group; orbx_stage_times_ms returns the summed ms per stage since then and the number of launch
+ * groups (batches of <= max_batch frames) they cover.  stages: 0 pyramid, 1 fast, 2 octree,
+ * 3 blur, 4 orientation+descriptor. */
 int orbx_set_profiling(orbx_extractor* h, int enable);
-int orbx_stage_times_ms(orbx_extractor* h, float* ms5);
+int orbx_stage_times_ms(orbx_extractor* h, double* sum_ms5, long long* n_calls);
 
 /* ---- matcher: replaces the hot members of class ORBmatcher (include/ORBmatcher.h:37-137) --- */
 
@@ -122,6 +127,7 @@ int orbm_create(int device, orbm_matcher** out);
 void orbm_destroy(orbm_matcher* m);
 const char* orbm_last_error(const orbm_matcher* m);
 int orbm_sync(orbm_matcher* m);
+int orbm_set_stream(orbm_matcher* m, void* cuda_stream);
 long long orbm_launch_count(const orbm_matcher* m);
 
 /* ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:3994-4010) for n independent pairs:
@@ -147,7 +153,9 @@ typedef struct {
  * (src/ORBmatcher.cc:868-983) for a batch of independent frame pairs.  Pair p uses keypoints
  * k1 + p*cap (n1[p] valid), k2 + p*cap (n2[p] valid), descriptors likewise (cap x 32 bytes per
  * frame), prev_xy + p*cap*2 (vbPrevMatched, in/out), matches12 + p*cap (out, -1 = none);
- * nmatches[p] out.  mfNNratio = nnratio, mbCheckOrientation = check_ori.  Device pointers. */
+ * nmatches[p] out.  mfNNratio = nnratio, mbCheckOrientation = check_ori.  Device pointers.
+ * d_prev_xy == NULL means vbPrevMatched[i] = F1 keypoint i's position (how Tracking initialises it,
+ * src/Tracking.cc:844-846) and nothing is written back. */
 int orbm_search_for_initialization_device(orbm_matcher* m, int n_pairs, int cap, const orbx_keypoint* d_k1,
                                           const uint8_t* d_d1, const int32_t* d_n1, const orbx_keypoint* d_k2,
                                           const uint8_t* d_d2, const int32_t* d_n2, orbm_bounds bounds2,

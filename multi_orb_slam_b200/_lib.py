@@ -54,16 +54,18 @@ _SIGS = {
     "orbx_extract_batch_device": (_i, [_vp, _vp, _i, _sz, _sz, _vp, _vp, _vp, _i]),
     "orbx_sync": (_i, [_vp]),
     "orbx_stream": (_vp, [_vp]),
+    "orbx_set_stream": (_i, [_vp, _vp]),
     "orbx_get_pyramid_level": (_i, [_vp, _i, _i, _i, _vp, _sz, C.POINTER(_i), C.POINTER(_i)]),
     "orbx_debug_candidates": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, C.POINTER(_i)]),
     "orbx_debug_blurred": (_i, [_vp, _i, _i, _vp, _sz]),
     "orbx_launch_count": (C.c_longlong, [_vp]),
     "orbx_set_profiling": (_i, [_vp, _i]),
-    "orbx_stage_times_ms": (_i, [_vp, _vp]),
+    "orbx_stage_times_ms": (_i, [_vp, _vp, C.POINTER(C.c_longlong)]),
     "orbm_create": (_i, [_i, C.POINTER(_vp)]),
     "orbm_destroy": (None, [_vp]),
     "orbm_last_error": (C.c_char_p, [_vp]),
     "orbm_sync": (_i, [_vp]),
+    "orbm_set_stream": (_i, [_vp, _vp]),
     "orbm_launch_count": (C.c_longlong, [_vp]),
     "orbm_distance_pairs_host": (_i, [_vp, _vp, _vp, _i, _vp]),
     "orbm_bruteforce_device": (_i, [_vp, _vp, _i, _vp, _i, _f, _i, _vp, _vp, _vp]),

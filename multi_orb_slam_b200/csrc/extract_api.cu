@@ -25,7 +25,8 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct orbx_extractor {
   orbx_config cfg;
   int device;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // stream in use
+  cudaStream_t own_stream = nullptr;  // created by the handle
   std::string err;
   long long launches = 0;
   std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
@@ -47,9 +48,27 @@ struct orbx_extractor {
   int* d_counts = nullptr;
   int stage_cap = 0;
   int last_batch = 0;  // frames resident in the workspace (for taps)
+  // per-stage device timing: a ring of event sets, harvested into running sums
+  static const int kRing = 32;
   bool profiling = false;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  bool ev_valid = false;
+  cudaEvent_t ev[kRing][6] = {};
+  bool ev_pending[kRing] = {};
+  int ev_next = 0;
+  double stage_sum_ms[5] = {0, 0, 0, 0, 0};
+  long long stage_calls = 0;
+
+  bool harvest(int slot) {
+    if (!ev_pending[slot]) return true;
+    if (!check(cudaEventSynchronize(ev[slot][5]), "event sync")) return false;
+    for (int i = 0; i < 5; ++i) {
+      float ms = 0;
+      if (!check(cudaEventElapsedTime(&ms, ev[slot][i], ev[slot][i + 1]), "event elapsed")) return false;
+      stage_sum_ms[i] += ms;
+    }
+    ++stage_calls;
+    ev_pending[slot] = false;
+    return true;
+  }
 
   bool check(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return true;
@@ -249,19 +268,27 @@ int run_batch(orbx_extractor* h, const uint8_t* d_images, int n_frames, size_t f
               orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_counts, int cap) {
   cudaStream_t st = h->stream;
   const bool prof = h->profiling;
-  if (prof) cudaEventRecord(h->ev[0], st);
+  cudaEvent_t* ev = h->ev[h->ev_next];
+  if (prof) {
+    if (!h->harvest(h->ev_next)) return ORBX_E_CUDA;
+    cudaEventRecord(ev[0], st);
+  }
   orbk::launch_pyramid(h->gh, d_images, frame_stride, row_stride, n_frames, h->d_pyr, st, &h->launches);
-  if (prof) cudaEventRecord(h->ev[1], st);
+  if (prof) cudaEventRecord(ev[1], st);
   orbk::launch_fast(h->gh, n_frames, h->d_pyr, h->d_cand, h->d_cell_count, st, &h->launches);
-  if (prof) cudaEventRecord(h->ev[2], st);
+  if (prof) cudaEventRecord(ev[2], st);
   orbk::launch_octree(h->gh, n_frames, h->d_cand, h->d_cell_count, h->d_keys, h->d_knode, h->d_sel, h->d_sel_count, st,
                       &h->launches);
-  if (prof) cudaEventRecord(h->ev[3], st);
+  if (prof) cudaEventRecord(ev[3], st);
   orbk::launch_blur(h->gh, n_frames, h->d_pyr, h->d_blur, st, &h->launches);
-  if (prof) cudaEventRecord(h->ev[4], st);
+  if (prof) cudaEventRecord(ev[4], st);
   orbk::launch_orient_describe(h->gh, n_frames, h->d_pyr, h->d_blur, h->d_sel, h->d_sel_count, d_kps, d_desc, d_counts,
                                cap, st, &h->launches);
-  if (prof) { cudaEventRecord(h->ev[5], st); h->ev_valid = true; }
+  if (prof) {
+    cudaEventRecord(ev[5], st);
+    h->ev_pending[h->ev_next] = true;
+    h->ev_next = (h->ev_next + 1) % orbx_extractor::kRing;
+  }
   h->last_batch = n_frames;
   if (!h->check(cudaGetLastError(), "kernel launch")) return ORBX_E_CUDA;
   return ORBX_OK;
@@ -301,9 +328,11 @@ int orbx_create(const orbx_config* cfg, orbx_extractor** out) {
     if (!h->check(cudaSetDevice(cfg->device), "cudaSetDevice")) return fail(ORBX_E_CUDA);
   }
   if (!h->check(cudaGetDevice(&h->device), "cudaGetDevice")) return fail(ORBX_E_CUDA);
-  if (!h->check(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail(ORBX_E_CUDA);
-  for (auto& e : h->ev)
-    if (!h->check(cudaEventCreate(&e), "cudaEventCreate")) return fail(ORBX_E_CUDA);
+  if (!h->check(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail(ORBX_E_CUDA);
+  h->stream = h->own_stream;
+  for (auto& set : h->ev)
+    for (auto& e : set)
+      if (!h->check(cudaEventCreate(&e), "cudaEventCreate")) return fail(ORBX_E_CUDA);
   const OrbGeom& g = h->gh.g;
   const size_t B = (size_t)cfg->max_batch;
   bool ok = dev_alloc(h, &h->gh.d_geom, 1, "cudaMalloc(geom)") &&
@@ -339,8 +368,10 @@ void orbx_destroy(orbx_extractor* h) {
   cudaFree(h->d_pyr); cudaFree(h->d_blur); cudaFree(h->d_cand); cudaFree(h->d_cell_count);
   cudaFree(h->d_keys); cudaFree(h->d_knode); cudaFree(h->d_sel); cudaFree(h->d_sel_count);
   cudaFree(h->d_img); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts);
-  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  for (auto& set : h->ev)
+    for (auto& e : set)
+      if (e) cudaEventDestroy(e);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
 
@@ -445,6 +476,13 @@ int orbx_sync(orbx_extractor* h) {
 
 void* orbx_stream(orbx_extractor* h) { return h ? (void*)h->stream : nullptr; }
 
+int orbx_set_stream(orbx_extractor* h, void* cuda_stream) {
+  if (!h) return ORBX_E_INVALID;
+  if (!h->check(cudaStreamSynchronize(h->stream), "stream synchronize")) return ORBX_E_CUDA;
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return ORBX_OK;
+}
+
 int orbx_get_pyramid_level(orbx_extractor* h, int frame, int level, int with_border, uint8_t* dst, size_t dst_stride,
                            int* w, int* hgt) {
   if (!h || level < 0 || level >= h->cfg.nlevels) return ORBX_E_INVALID;
@@ -505,17 +543,20 @@ long long orbx_launch_count(const orbx_extractor* h) { return h ? h->launches : 
 
 int orbx_set_profiling(orbx_extractor* h, int enable) {
   if (!h) return ORBX_E_INVALID;
+  if (!h->check(cudaStreamSynchronize(h->stream), "stream synchronize")) return ORBX_E_CUDA;
   h->profiling = enable != 0;
-  h->ev_valid = false;
+  for (int i = 0; i < orbx_extractor::kRing; ++i) h->ev_pending[i] = false;
+  for (double& v : h->stage_sum_ms) v = 0;
+  h->stage_calls = 0;
   return ORBX_OK;
 }
 
-int orbx_stage_times_ms(orbx_extractor* h, float* ms5) {
-  if (!h || !ms5) return ORBX_E_INVALID;
-  if (!h->ev_valid) return ORBX_E_STATE;
-  if (!h->check(cudaEventSynchronize(h->ev[5]), "event sync")) return ORBX_E_CUDA;
-  for (int i = 0; i < 5; ++i)
-    if (!h->check(cudaEventElapsedTime(&ms5[i], h->ev[i], h->ev[i + 1]), "event elapsed")) return ORBX_E_CUDA;
+int orbx_stage_times_ms(orbx_extractor* h, double* sum_ms5, long long* n_calls) {
+  if (!h || !sum_ms5 || !n_calls) return ORBX_E_INVALID;
+  for (int i = 0; i < orbx_extractor::kRing; ++i)
+    if (!h->harvest(i)) return ORBX_E_CUDA;
+  for (int i = 0; i < 5; ++i) sum_ms5[i] = h->stage_sum_ms[i];
+  *n_calls = h->stage_calls;
   return ORBX_OK;
 }
 

@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256) k_search_init(int cap, const orbx_keypoin
   const orbx_keypoint* k2 = k2_all + (size_t)pair * cap;
   const uint8_t* d1 = d1_all + (size_t)pair * cap * 32;
   const uint8_t* d2 = d2_all + (size_t)pair * cap * 32;
-  float* prev = prev_all + (size_t)pair * cap * 2;
+  float* prev = prev_all ? prev_all + (size_t)pair * cap * 2 : nullptr;
   uint32_t* cand = cand_all + (size_t)pair * cap * cap;
   int* cand_cnt = cand_cnt_all + (size_t)pair * cap;
   int32_t* matches12 = matches12_all + (size_t)pair * cap;
@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(256) k_search_init(int cap, const orbx_keypoin
       const uint4 qa = __ldg(q), qb = __ldg(q + 1);
       uint32_t* row = cand + (size_t)i1 * cap;
       const int level1 = k1[i1].octave;
-      grid_query(gv, k2, prev[2 * i1], prev[2 * i1 + 1], window, level1, level1, [&](bool ok, int idx) {
+      const float px = prev ? prev[2 * i1] : k1[i1].x, py = prev ? prev[2 * i1 + 1] : k1[i1].y;
+      grid_query(gv, k2, px, py, window, level1, level1, [&](bool ok, int idx) {
         const unsigned m = __ballot_sync(0xffffffffu, ok);
         if (ok) {
           const uint4* tp = reinterpret_cast<const uint4*>(d2 + (size_t)idx * 32);
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(256) k_search_init(int cap, const orbx_keypoin
     }
     __syncthreads();
   }
-  for (int i1 = tid; i1 < n1; i1 += 256) {  // :978-980
+  for (int i1 = tid; prev && i1 < n1; i1 += 256) {  // :978-980
     const int m = matches12[i1];
     if (m >= 0) {
       prev[2 * i1] = k2[m].x;
@@ -520,6 +521,7 @@ __global__ void __launch_bounds__(32) k_proj_resolve(const int* __restrict__ row
 struct orbm_matcher {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
   std::string err;
   long long launches = 0;
   // growable device scratch
@@ -582,11 +584,12 @@ int orbm_create(int device, orbm_matcher** out) {
   }
   if (device >= 0 && !m->check(cudaSetDevice(device), "cudaSetDevice")) { g_mcreate_error = m->err; delete m; return ORBX_E_CUDA; }
   cudaGetDevice(&m->device);
-  if (!m->check(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+  if (!m->check(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
     g_mcreate_error = m->err;
     delete m;
     return ORBX_E_CUDA;
   }
+  m->stream = m->own_stream;
   *out = m;
   return ORBX_OK;
 }
@@ -595,7 +598,7 @@ void orbm_destroy(orbm_matcher* m) {
   if (!m) return;
   cudaStreamSynchronize(m->stream);
   for (auto& b : m->buf) cudaFree(b);
-  cudaStreamDestroy(m->stream);
+  cudaStreamDestroy(m->own_stream);
   delete m;
 }
 
@@ -605,6 +608,12 @@ int orbm_sync(orbm_matcher* m) {
   return m->check(cudaStreamSynchronize(m->stream), "stream synchronize") ? ORBX_OK : ORBX_E_CUDA;
 }
 long long orbm_launch_count(const orbm_matcher* m) { return m ? m->launches : 0; }
+int orbm_set_stream(orbm_matcher* m, void* cuda_stream) {
+  if (!m) return ORBX_E_INVALID;
+  if (!m->check(cudaStreamSynchronize(m->stream), "stream synchronize")) return ORBX_E_CUDA;
+  m->stream = cuda_stream ? (cudaStream_t)cuda_stream : m->own_stream;
+  return ORBX_OK;
+}
 
 int orbm_distance_pairs_host(orbm_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* out) {
   if (!m || !a || !b || !out || n < 0) return ORBX_E_INVALID;
@@ -673,7 +682,7 @@ int orbm_search_for_initialization_device(orbm_matcher* m, int n_pairs, int cap,
     const size_t o = (size_t)p0 * cap;
     k_build_grid<<<np, 256, 0, m->stream>>>(d_k2 + o, d_n2 + p0, 0, cap, bounds2, gstart, gitems);
     k_search_init<<<np, 256, smem, m->stream>>>(cap, d_k1 + o, d_d1 + o * 32, d_n1 + p0, d_k2 + o, d_d2 + o * 32, d_n2 + p0,
-                                                bounds2, gstart, gitems, d_prev_xy + o * 2, (float)window, nnratio, check_ori,
+                                                bounds2, gstart, gitems, d_prev_xy ? d_prev_xy + o * 2 : nullptr, (float)window, nnratio, check_ori,
                                                 cand, cand_cnt, d_matches12 + o, d_nmatches + p0);
     m->launches += 2;
   }

@@ -167,6 +167,10 @@ class ORBextractor:
         """cudaStream_t of the handle (wrap with torch.cuda.ExternalStream to record events on it)."""
         return lib.orbx_stream(self._h)
 
+    def set_stream(self, cuda_stream: int) -> None:
+        """Run on a caller-owned cudaStream_t (e.g. torch.cuda.Stream().cuda_stream); 0/None restores."""
+        check_x(self._h, lib.orbx_set_stream(self._h, cuda_stream or None))
+
     @property
     def launch_count(self) -> int:
         return lib.orbx_launch_count(self._h) if self._h else 0
@@ -174,10 +178,14 @@ class ORBextractor:
     def set_profiling(self, on: bool) -> None:
         check_x(self._h, lib.orbx_set_profiling(self._h, int(on)))
 
-    def stage_times_ms(self) -> np.ndarray:
-        out = np.zeros(5, dtype=np.float32)
-        check_x(self._h, lib.orbx_stage_times_ms(self._h, out.ctypes.data))
-        return out
+    STAGES = ("pyramid", "fast", "octree", "blur", "orient_describe")
+
+    def stage_times_ms(self):
+        """(summed ms per stage since set_profiling(True), number of launch groups)."""
+        out = np.zeros(5, dtype=np.float64)
+        n = C.c_longlong(0)
+        check_x(self._h, lib.orbx_stage_times_ms(self._h, out.ctypes.data, C.byref(n)))
+        return out, n.value
 
     # -- stage taps (parity tests) ----------------------------------------------------------------
     def debug_candidates(self, level: int, frame: int = 0):

@@ -85,6 +85,9 @@ class ORBmatcher:
     def sync(self):
         check_m(self._h, lib.orbm_sync(self._h))
 
+    def set_stream(self, cuda_stream: int) -> None:
+        check_m(self._h, lib.orbm_set_stream(self._h, cuda_stream or None))
+
     # -- DescriptorDistance (src/ORBmatcher.cc:3994-4010) ---------------------------------------
     def DescriptorDistance(self, a: np.ndarray, b: np.ndarray) -> int:
         return int(self.distance_pairs(np.asarray(a).reshape(1, 32), np.asarray(b).reshape(1, 32))[0])
@@ -151,7 +154,7 @@ class ORBmatcher:
         """Device-resident batch (torch CUDA tensors laid out as the extractor's batch outputs)."""
         check_m(self._h, lib.orbm_search_for_initialization_device(
             self._h, P, cap, k1.data_ptr(), d1.data_ptr(), n1.data_ptr(), k2.data_ptr(), d2.data_ptr(), n2.data_ptr(),
-            bounds2, prev_xy.data_ptr(), int(windowSize), self.mfNNratio, int(self.mbCheckOrientation),
+            bounds2, None if prev_xy is None else prev_xy.data_ptr(), int(windowSize), self.mfNNratio, int(self.mbCheckOrientation),
             matches12.data_ptr(), nmatches.data_ptr()))
 
     # -- SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:62-157) ------------
