@@ -84,156 +84,203 @@ __global__ void __launch_bounds__(256) k_pyr_resize(int level, const OrbGeom* __
 // min(+-diff) is threshold independent: corner iff m > th, score m-1 (OpenCV cornerScore<16>);
 // a corner survives the 3x3 NMS iff its m is strictly greater than its 8 neighbours' m
 // (neighbours outside this cell's tested area count as 0 — NMS is per cell).
+//
+// Work is split the way the arithmetic cost falls (measured on the synthetic frames: at th=20
+// only ~13 % of pixels survive the 4-pair high-speed test and ~6 % are corners):
+//   phase A  every tested pixel: opposite-pair rejection test (dense lanes, ~30 instr/px),
+//            survivors appended to a shared-memory queue;
+//   phase B  queued pixels only: full arc measure with 3-input min/max (VIMNMX3), dense again;
+//   NMS      ballots over the linearised tested area, ordered compaction = reference order.
+// The pass runs at iniThFAST; only a cell that kept nothing reruns at minThFAST (:813-817).
 #define FAST_PITCH 80
 
-__device__ __forceinline__ int arc9_maxmin(const int (&v)[16]) {
-  int a1[16], a2[16], a4[16];
+struct FastSmem {
+  uint8_t* img;        // [rows][FAST_PITCH], same word alignment as the global rows
+  uint8_t* m;          // arc measure map, 0 = not a corner at the pass threshold
+  uint16_t* queue;     // phase-A survivors (byte offsets into img / m)
+  uint32_t* bal;       // NMS ballots, linear order
+  int* misc;           // [0] queue length, [1] kept count, [8..] per-word offsets
+};
+
+__device__ __forceinline__ int fast_arc_measure(const uint8_t* p) {
+  constexpr int RO[16] = {3 * FAST_PITCH,      3 * FAST_PITCH + 1,  2 * FAST_PITCH + 2,  FAST_PITCH + 3,
+                          3,                   -FAST_PITCH + 3,     -2 * FAST_PITCH + 2, -3 * FAST_PITCH + 1,
+                          -3 * FAST_PITCH,     -3 * FAST_PITCH - 1, -2 * FAST_PITCH - 2, -FAST_PITCH - 3,
+                          -3,                  FAST_PITCH - 3,      2 * FAST_PITCH - 2,  3 * FAST_PITCH - 1};
+  const int c = p[0];
+  int d[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) a1[k] = min(v[k], v[(k + 1) & 15]);
+  for (int k = 0; k < 16; ++k) d[k] = (int)p[RO[k]] - c;
+  int lo3[16], hi3[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) a2[k] = min(a1[k], a1[(k + 2) & 15]);
+  for (int k = 0; k < 16; ++k) {
+    lo3[k] = __vimin3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+    hi3[k] = __vimax3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+  }
+  int mb = -256, md = 256;  // max over arcs of min(d) (bright ring), min over arcs of max(d) (dark ring)
 #pragma unroll
-  for (int k = 0; k < 16; ++k) a4[k] = min(a2[k], a2[(k + 4) & 15]);
-  int best = -256;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) best = max(best, min(a4[k], v[(k + 8) & 15]));
-  return best;
+  for (int k = 0; k < 16; k += 2) {
+    const int a0 = __vimin3_s32(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+    const int a1 = __vimin3_s32(lo3[k + 1], lo3[(k + 4) & 15], lo3[(k + 7) & 15]);
+    mb = __vimax3_s32(mb, a0, a1);
+    const int b0 = __vimax3_s32(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
+    const int b1 = __vimax3_s32(hi3[k + 1], hi3[(k + 4) & 15], hi3[(k + 7) & 15]);
+    md = __vimin3_s32(md, b0, b1);
+  }
+  return max(mb, -md);
+}
+
+// One threshold pass over the tested area [3,cw-3) x [3,ch-3) (tw x thh pixels, linear index
+// idx = ty*tw + tx).  Returns the number of NMS survivors; their ballots are left in sm.bal.
+__device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int T, int a0, bool skip_done) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int q128 = 128 / tw, r128 = 128 - q128 * tw;
+  if (tid == 0) { sm.misc[0] = 0; sm.misc[1] = 0; }
+  __syncthreads();
+  // phase A: high-speed rejection.  A 9-arc contains one pixel of every opposite pair (k, k+8),
+  // so a bright (dark) arc needs min over pairs of max(a,b) > c+th  (max over pairs of min < c-th).
+  {
+    int ty = tid / tw, tx = tid - ty * tw;
+    for (int idx = tid; idx < ((T + 31) & ~31); idx += 128) {
+      bool pass = false;
+      int off = 0;
+      if (idx < T) {
+        off = (ty + 3) * FAST_PITCH + a0 + tx + 3;
+        const uint8_t* p = sm.img + off;
+        if (!(skip_done && sm.m[off] != 0)) {
+          const int c = p[0];
+          const int r0 = p[3 * FAST_PITCH], r8 = p[-3 * FAST_PITCH], r4 = p[3], r12 = p[-3];
+          const int r2 = p[2 * FAST_PITCH + 2], r10 = p[-2 * FAST_PITCH - 2], r6 = p[-2 * FAST_PITCH + 2],
+                    r14 = p[2 * FAST_PITCH - 2];
+          const int mn = __vimin3_s32(max(r0, r8), max(r4, r12), min(max(r2, r10), max(r6, r14)));
+          const int mx = __vimax3_s32(min(r0, r8), min(r4, r12), max(min(r2, r10), min(r6, r14)));
+          pass = (mn > c + th) || (mx < c - th);
+        }
+      }
+      const unsigned bm = __ballot_sync(0xffffffffu, pass);
+      if (bm) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&sm.misc[0], __popc(bm));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (pass) sm.queue[base + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)off;
+      }
+      tx += r128;
+      ty += q128;
+      if (tx >= tw) { tx -= tw; ++ty; }
+    }
+  }
+  __syncthreads();
+  // phase B: full measure for the survivors
+  {
+    const int nq = sm.misc[0];
+    for (int q = tid; q < nq; q += 128) {
+      const int off = sm.queue[q];
+      const int m = fast_arc_measure(sm.img + off);
+      if (m > th) sm.m[off] = (uint8_t)m;
+    }
+  }
+  __syncthreads();
+  // NMS ballots in linear (row-major) order
+  {
+    int ty = tid / tw, tx = tid - ty * tw, kept = 0;
+    for (int idx = tid; idx < ((T + 31) & ~31); idx += 128) {
+      bool keep = false;
+      if (idx < T) {
+        const uint8_t* q = sm.m + (ty + 3) * FAST_PITCH + a0 + tx + 3;
+        const int mv = q[0];
+        if (mv > th) {
+          // neighbours beyond the tested area hold 0; a corner found by an earlier (higher) pass
+          // stays > th, so comparing raw m values equals comparing thresholded scores
+          const int n1 = __vimax3_s32((int)q[-1], (int)q[1], (int)q[-FAST_PITCH]);
+          const int n2 = __vimax3_s32((int)q[FAST_PITCH], (int)q[-FAST_PITCH - 1], (int)q[-FAST_PITCH + 1]);
+          const int n3 = __vimax3_s32((int)q[FAST_PITCH - 1], (int)q[FAST_PITCH + 1], n1);
+          keep = mv > max(n2, n3);
+        }
+      }
+      const unsigned bm = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) { sm.bal[idx >> 5] = bm; kept += __popc(bm); }
+      tx += r128;
+      ty += q128;
+      if (tx >= tw) { tx -= tw; ++ty; }
+    }
+    if (lane == 0 && kept) atomicAdd(&sm.misc[1], kept);
+  }
+  __syncthreads();
+  return sm.misc[1];
 }
 
 __global__ void __launch_bounds__(128) k_fast_cells(const OrbGeom* __restrict__ g, const OrbCell* __restrict__ cells,
                                                     const uint8_t* __restrict__ pyr, uint32_t* __restrict__ cand,
-                                                    int* __restrict__ cell_count) {
-  __shared__ __align__(16) uint8_t s_img[ORB_CELL_MAX * FAST_PITCH];
-  __shared__ __align__(16) uint8_t s_m[ORB_CELL_MAX * FAST_PITCH];
-  __shared__ uint32_t s_mask[2][ORB_CELL_MAX][3];
-  __shared__ int s_rowoff[ORB_CELL_MAX + 32];
-  __shared__ int s_cnt[2];
+                                                    int* __restrict__ cell_count, int rows_max, int t_max) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  FastSmem sm;
+  sm.img = fsm;
+  sm.m = sm.img + rows_max * FAST_PITCH;
+  sm.queue = reinterpret_cast<uint16_t*>(sm.m + rows_max * FAST_PITCH);
+  const int nwords = (t_max + 31) >> 5;
+  sm.bal = reinterpret_cast<uint32_t*>(sm.queue + ((t_max + 1) & ~1));
+  sm.misc = reinterpret_cast<int*>(sm.bal + nwords);
 
   const OrbCell cell = cells[blockIdx.x];
   const OrbLevelGeom& L = g->lv[cell.level];
   const int frame = blockIdx.y;
   const int cw = cell.cw, ch = cell.ch;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // aligned word copy of the sub-image rows; a0 = misalignment of the cell's first column
+  const int bx = ORB_EDGE + cell.ini_x, a0 = bx & 3;
   const uint8_t* base = pyr + (size_t)frame * g->pyr_frame_bytes + L.pyr_off +
-                        (size_t)(ORB_EDGE + cell.ini_y) * L.pitch + ORB_EDGE + cell.ini_x;
-  for (int y = warp; y < ch; y += 4)
-    for (int x = lane; x < cw; x += 32) {
-      s_img[y * FAST_PITCH + x] = base[(size_t)y * L.pitch + x];
-      s_m[y * FAST_PITCH + x] = 0;
+                        (size_t)(ORB_EDGE + cell.ini_y) * L.pitch + (bx - a0);
+  const int nw = (a0 + cw + 3) >> 2;
+  for (int i = tid; i < ch * nw; i += 128) {
+    const int y = i / nw, wq = i - y * nw;
+    reinterpret_cast<uint32_t*>(sm.img + y * FAST_PITCH)[wq] =
+        __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)y * L.pitch) + wq);
+  }
+  for (int i = tid; i < ch * (FAST_PITCH / 4); i += 128) reinterpret_cast<uint32_t*>(sm.m)[i] = 0u;
+  const int tw = cw - 6, thh = ch - 6;
+  const int T = (tw > 0 && thh > 0) ? tw * thh : 0;
+  int total = 0, th = g->ini_th;
+  if (T > 0) {
+    total = fast_pass(sm, th, tw, T, a0, false);
+    if (total == 0 && g->min_th < th) {
+      th = g->min_th;
+      total = fast_pass(sm, th, tw, T, a0, true);
     }
-  if (tid < 2) s_cnt[tid] = 0;
-  __syncthreads();
-
-  const int th_lo = g->min_th, th_hi = g->ini_th;
-  // ring offsets (dx,dy), k = 0..15: (0,3),(1,3),(2,2),(3,1),(3,0),(3,-1),(2,-2),(1,-3),(0,-3),...
-  constexpr int RO[16] = {3 * FAST_PITCH,      3 * FAST_PITCH + 1,  2 * FAST_PITCH + 2,  FAST_PITCH + 3,
-                          3,                   -FAST_PITCH + 3,     -2 * FAST_PITCH + 2, -3 * FAST_PITCH + 1,
-                          -3 * FAST_PITCH,     -3 * FAST_PITCH - 1, -2 * FAST_PITCH - 2, -FAST_PITCH - 3,
-                          -3,                  FAST_PITCH - 3,      2 * FAST_PITCH - 2,  3 * FAST_PITCH - 1};
-  for (int y = 3 + warp; y < ch - 3; y += 4) {
-    for (int x = 3 + lane; x < cw - 3; x += 32) {
-      const uint8_t* p = s_img + y * FAST_PITCH + x;
-      const int c = p[0];
-      const int hi = c + th_lo, lo = c - th_lo;
-      // high-speed rejection at the LOWER threshold: each opposite pair (k,k+8) must hold a
-      // ring pixel of the arc's polarity, otherwise m <= min_th and the pixel can never be a corner
-      bool br = true, dk = true;
+  }
+  if (total > 0) {
+    // exclusive offsets of the ballot words (warp 0), then ordered write-out
+    const int nword = (T + 31) >> 5;
+    int* woff = sm.misc + 8;
+    if (tid < 32) {
+      int run = 0;
+      for (int w0 = 0; w0 < nword; w0 += 32) {
+        const int w = w0 + lane;
+        const int c = w < nword ? __popc(sm.bal[w]) : 0;
+        int incl = c;
 #pragma unroll
-      for (int k = 0; k < 8; k += 2) {
-        const int a = p[RO[k]], b = p[RO[k + 8]];
-        br = br && (a > hi || b > hi);
-        dk = dk && (a < lo || b < lo);
-      }
-      if (br || dk) {
-        int d[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) d[k] = (int)p[RO[k]] - c;
-        int m = -256;
-        if (br) m = arc9_maxmin(d);
-        if (dk) {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) d[k] = -d[k];
-          m = max(m, arc9_maxmin(d));
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
         }
-        if (m > th_lo) s_m[y * FAST_PITCH + x] = (uint8_t)m;
+        if (w < nword) woff[w] = run + incl - c;
+        run += __shfl_sync(0xffffffffu, incl, 31);
       }
     }
-  }
-  __syncthreads();
-
-  // NMS + both threshold masks, one ballot word per 32 columns
-  int cnt_hi = 0, cnt_lo = 0;
-  for (int y = 3 + warp; y < ch - 3; y += 4) {
-#pragma unroll
-    for (int cchunk = 0; cchunk < 3; ++cchunk) {
-      const int x = 3 + cchunk * 32 + lane;
-      bool k_hi = false, k_lo = false;
-      if (x < cw - 3) {
-        const uint8_t* q = s_m + y * FAST_PITCH + x;
-        const int mv = q[0];
-        if (mv > th_lo) {
-          int nb = max(max((int)q[-1], (int)q[1]), max((int)q[-FAST_PITCH], (int)q[FAST_PITCH]));
-          nb = max(nb, max(max((int)q[-FAST_PITCH - 1], (int)q[-FAST_PITCH + 1]),
-                           max((int)q[FAST_PITCH - 1], (int)q[FAST_PITCH + 1])));
-          k_lo = mv > nb;
-          k_hi = k_lo && mv > th_hi;
-        }
-      }
-      const uint32_t b_hi = __ballot_sync(0xffffffffu, k_hi), b_lo = __ballot_sync(0xffffffffu, k_lo);
-      if (lane == 0) {
-        s_mask[0][y][cchunk] = b_hi;
-        s_mask[1][y][cchunk] = b_lo;
-        cnt_hi += __popc(b_hi);
-        cnt_lo += __popc(b_lo);
-      }
-    }
-  }
-  if (lane == 0) {
-    if (cnt_hi) atomicAdd(&s_cnt[0], cnt_hi);
-    if (cnt_lo) atomicAdd(&s_cnt[1], cnt_lo);
-  }
-  __syncthreads();
-  const int use = s_cnt[0] > 0 ? 0 : 1;  // :813-817 fallback only when the cell found nothing
-  const int total = s_cnt[use];
-  // row offsets: warp 0, each lane owns 3 consecutive rows (ORB_CELL_MAX <= 96)
-  if (warp == 0) {
-    int c3[3], sum = 0;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int y = lane * 3 + r;
-      c3[r] = 0;
-      if (y >= 3 && y < ch - 3) c3[r] = __popc(s_mask[use][y][0]) + __popc(s_mask[use][y][1]) + __popc(s_mask[use][y][2]);
-      sum += c3[r];
-    }
-    int incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    int run = incl - sum;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int y = lane * 3 + r;
-      if (y < ORB_CELL_MAX) s_rowoff[y] = run;
-      run += c3[r];
-    }
-  }
-  __syncthreads();
-  uint32_t* out = cand + (size_t)frame * g->cand_frame_u32 + L.cand_off + (size_t)cell.slot * L.cand_cap;
-  for (int y = 3 + warp; y < ch - 3; y += 4) {
-    int off = s_rowoff[y];
-#pragma unroll
-    for (int cchunk = 0; cchunk < 3; ++cchunk) {
-      const uint32_t mask = s_mask[use][y][cchunk];
-      if (mask >> lane & 1u) {
-        const int x = 3 + cchunk * 32 + lane;
-        const int pos = off + __popc(mask & ((1u << lane) - 1u));
-        const uint32_t score = (uint32_t)s_m[y * FAST_PITCH + x] - 1u;
+    __syncthreads();
+    uint32_t* out = cand + (size_t)frame * g->cand_frame_u32 + L.cand_off + (size_t)cell.slot * L.cand_cap;
+    const int q128 = 128 / tw, r128 = 128 - q128 * tw;
+    int ty = tid / tw, tx = tid - ty * tw;
+    for (int idx = tid; idx < T; idx += 128) {
+      const uint32_t bm = sm.bal[idx >> 5];
+      if (bm >> lane & 1u) {
+        const int pos = woff[idx >> 5] + __popc(bm & ((1u << lane) - 1u));
+        const uint32_t score = (uint32_t)sm.m[(ty + 3) * FAST_PITCH + a0 + tx + 3] - 1u;
         if (pos < L.cand_cap)
-          out[pos] = (uint32_t)(x + cell.off_x) | (uint32_t)(y + cell.off_y) << 12 | score << 24;
+          out[pos] = (uint32_t)(tx + 3 + cell.off_x) | (uint32_t)(ty + 3 + cell.off_y) << 12 | score << 24;
       }
-      off += __popc(mask);
+      tx += r128;
+      ty += q128;
+      if (tx >= tw) { tx -= tw; ++ty; }
     }
   }
   if (tid == 0) cell_count[(size_t)frame * g->n_cells + blockIdx.x] = min(total, L.cand_cap);
@@ -526,7 +573,17 @@ void launch_pyramid(const OrbGeomHost& gh, const uint8_t* d_src, size_t frame_st
 
 void launch_fast(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, uint32_t* d_cand, int* d_cell_count,
                  cudaStream_t st, long long* launches) {
-  k_fast_cells<<<dim3(gh.g.n_cells, n_frames), 128, 0, st>>>(gh.d_geom, gh.d_cells, d_pyr, d_cand, d_cell_count);
+  // shared memory sized for this geometry's largest cell (rows x FAST_PITCH image + measure map,
+  // survivor queue, ballots): ~10 KB at 640x480, so 16 CTAs stay resident per SM
+  int rows_max = 0, t_max = 1;
+  for (int l = 0; l < gh.g.nlevels; ++l) {
+    rows_max = max(rows_max, gh.g.lv[l].h_cell + 6);
+    t_max = max(t_max, gh.g.lv[l].w_cell * gh.g.lv[l].h_cell);
+  }
+  const size_t smem = (size_t)2 * rows_max * FAST_PITCH + 2 * (size_t)((t_max + 1) & ~1) + 4 * (size_t)((t_max + 31) >> 5) +
+                      4 * (size_t)(8 + ((t_max + 31) >> 5)) + 16;
+  k_fast_cells<<<dim3(gh.g.n_cells, n_frames), 128, smem, st>>>(gh.d_geom, gh.d_cells, d_pyr, d_cand, d_cell_count,
+                                                                  rows_max, t_max);
   ++*launches;
 }
 
@@ -536,8 +593,18 @@ size_t octree_smem_bytes(const OrbGeom& g) {
          sizeof(int) * 3 * scap + sizeof(int) * 257 + sizeof(int) * 8;
 }
 
+// The opt-in limit is a property of the FUNCTION (per device), shared by every handle: only ever
+// raise it, so a handle with a smaller nfeatures cannot shrink it under another handle's feet.
 cudaError_t prepare_octree(const OrbGeom& g) {
-  return cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_smem_bytes(g));
+  static int raised[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const int need = (int)octree_smem_bytes(g);
+  if (dev < 64 && need <= raised[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+  if (e == cudaSuccess && dev < 64) raised[dev] = need;
+  return e;
 }
 
 void launch_octree(const OrbGeomHost& gh, int n_frames, const uint32_t* d_cand, const int* d_cell_count,

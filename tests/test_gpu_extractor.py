@@ -145,3 +145,13 @@ def test_idempotent_and_deterministic():
     k1, d1 = ex(img)
     k2, d2 = ex(img)
     assert np.array_equal(k1, k2) and np.array_equal(d1, d2)
+
+
+def test_two_handles_with_different_nfeatures(O):
+    """Regression: the octree kernel's shared-memory opt-in is per function, not per handle."""
+    img = textured(640, 480, 8)
+    big, small = _gpu(1000), _gpu(500)
+    for ex, nf in ((big, 1000), (small, 500), (big, 1000)):
+        k_ref, d_ref, _ = O.extractor("port", nfeatures=nf).extract(img)
+        k, d = ex(img)
+        _assert_same_features(k, d, k_ref, d_ref, f"nf={nf}")
