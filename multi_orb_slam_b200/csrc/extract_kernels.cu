@@ -98,8 +98,8 @@ struct FastSmem {
   uint8_t* img;        // [rows][FAST_PITCH], same word alignment as the global rows
   uint8_t* m;          // arc measure map, 0 = not a corner at the pass threshold
   uint16_t* queue;     // phase-A survivors (byte offsets into img / m)
-  uint32_t* bal;       // NMS ballots, linear order
-  int* misc;           // [0] queue length, [1] kept count, [8..] per-word offsets
+  uint16_t* kept;      // NMS survivors (byte offsets), unordered
+  int* misc;           // [0] queue length, [1] kept count
 };
 
 __device__ __forceinline__ int fast_arc_measure(const uint8_t* p) {
@@ -130,80 +130,73 @@ __device__ __forceinline__ int fast_arc_measure(const uint8_t* p) {
   return max(mb, -md);
 }
 
-// One threshold pass over the tested area [3,cw-3) x [3,ch-3) (tw x thh pixels, linear index
-// idx = ty*tw + tx).  Returns the number of NMS survivors; their ballots are left in sm.bal.
-__device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int T, int a0, bool skip_done) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int q128 = 128 / tw, r128 = 128 - q128 * tw;
+// Warp-aggregated append to a shared-memory list.
+__device__ __forceinline__ void fast_push(bool pred, uint16_t value, uint16_t* list, int* counter) {
+  const unsigned bm = __ballot_sync(0xffffffffu, pred);
+  if (bm) {
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counter, __popc(bm));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (pred) list[base + __popc(bm & ((1u << lane) - 1u))] = value;
+  }
+}
+
+// One threshold pass over the tested area (tw x thh pixels starting at sub-image (3,3)).
+// Returns the number of NMS survivors, left (unordered) in sm.kept.
+__device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int thh, int a0, bool second_pass) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) { sm.misc[0] = 0; sm.misc[1] = 0; }
   __syncthreads();
   // phase A: high-speed rejection.  A 9-arc contains one pixel of every opposite pair (k, k+8),
   // so a bright (dark) arc needs min over pairs of max(a,b) > c+th  (max over pairs of min < c-th).
-  {
-    int ty = tid / tw, tx = tid - ty * tw;
-    for (int idx = tid; idx < ((T + 31) & ~31); idx += 128) {
+  for (int ty = warp; ty < thh; ty += 4) {
+    for (int tx0 = 0; tx0 < tw; tx0 += 32) {
+      const int tx = tx0 + lane;
+      const int off = (ty + 3) * FAST_PITCH + a0 + 3 + tx;
       bool pass = false;
-      int off = 0;
-      if (idx < T) {
-        off = (ty + 3) * FAST_PITCH + a0 + tx + 3;
+      if (tx < tw) {
         const uint8_t* p = sm.img + off;
-        if (!(skip_done && sm.m[off] != 0)) {
-          const int c = p[0];
-          const int r0 = p[3 * FAST_PITCH], r8 = p[-3 * FAST_PITCH], r4 = p[3], r12 = p[-3];
-          const int r2 = p[2 * FAST_PITCH + 2], r10 = p[-2 * FAST_PITCH - 2], r6 = p[-2 * FAST_PITCH + 2],
-                    r14 = p[2 * FAST_PITCH - 2];
-          const int mn = __vimin3_s32(max(r0, r8), max(r4, r12), min(max(r2, r10), max(r6, r14)));
-          const int mx = __vimax3_s32(min(r0, r8), min(r4, r12), max(min(r2, r10), min(r6, r14)));
-          pass = (mn > c + th) || (mx < c - th);
-        }
+        const int c = p[0];
+        const int r0 = p[3 * FAST_PITCH], r8 = p[-3 * FAST_PITCH], r4 = p[3], r12 = p[-3];
+        const int r2 = p[2 * FAST_PITCH + 2], r10 = p[-2 * FAST_PITCH - 2], r6 = p[-2 * FAST_PITCH + 2],
+                  r14 = p[2 * FAST_PITCH - 2];
+        const int mn = __vimin3_s32(max(r0, r8), max(r4, r12), min(max(r2, r10), max(r6, r14)));
+        const int mx = __vimax3_s32(min(r0, r8), min(r4, r12), max(min(r2, r10), min(r6, r14)));
+        pass = (mn > c + th) || (mx < c - th);
+        // corners already measured by the first pass stay in play for the second pass's NMS
+        if (second_pass && sm.m[off] != 0) pass = true;
       }
-      const unsigned bm = __ballot_sync(0xffffffffu, pass);
-      if (bm) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&sm.misc[0], __popc(bm));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (pass) sm.queue[base + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)off;
-      }
-      tx += r128;
-      ty += q128;
-      if (tx >= tw) { tx -= tw; ++ty; }
+      fast_push(pass, (uint16_t)off, sm.queue, &sm.misc[0]);
     }
   }
   __syncthreads();
-  // phase B: full measure for the survivors
-  {
-    const int nq = sm.misc[0];
-    for (int q = tid; q < nq; q += 128) {
-      const int off = sm.queue[q];
-      const int m = fast_arc_measure(sm.img + off);
-      if (m > th) sm.m[off] = (uint8_t)m;
-    }
+  // phase B: full measure for the survivors (dense lanes)
+  const int nq = sm.misc[0];
+  for (int q = tid; q < nq; q += 128) {
+    const int off = sm.queue[q];
+    const int m = fast_arc_measure(sm.img + off);
+    if (m > th) sm.m[off] = (uint8_t)m;
   }
   __syncthreads();
-  // NMS ballots in linear (row-major) order
-  {
-    int ty = tid / tw, tx = tid - ty * tw, kept = 0;
-    for (int idx = tid; idx < ((T + 31) & ~31); idx += 128) {
-      bool keep = false;
-      if (idx < T) {
-        const uint8_t* q = sm.m + (ty + 3) * FAST_PITCH + a0 + tx + 3;
-        const int mv = q[0];
-        if (mv > th) {
-          // neighbours beyond the tested area hold 0; a corner found by an earlier (higher) pass
-          // stays > th, so comparing raw m values equals comparing thresholded scores
-          const int n1 = __vimax3_s32((int)q[-1], (int)q[1], (int)q[-FAST_PITCH]);
-          const int n2 = __vimax3_s32((int)q[FAST_PITCH], (int)q[-FAST_PITCH - 1], (int)q[-FAST_PITCH + 1]);
-          const int n3 = __vimax3_s32((int)q[FAST_PITCH - 1], (int)q[FAST_PITCH + 1], n1);
-          keep = mv > max(n2, n3);
-        }
+  // phase C: 3x3 NMS of the corners.  Neighbours outside the tested area hold 0; comparing raw m
+  // values equals comparing thresholded scores because every stored m exceeds the pass threshold.
+  for (int q0 = 0; q0 < nq; q0 += 128) {
+    const int q = q0 + tid;
+    bool keep = false;
+    int off = 0;
+    if (q < nq) {
+      off = sm.queue[q];
+      const uint8_t* c = sm.m + off;
+      const int mv = c[0];
+      if (mv > th) {
+        const int n1 = __vimax3_s32((int)c[-1], (int)c[1], (int)c[-FAST_PITCH]);
+        const int n2 = __vimax3_s32((int)c[FAST_PITCH], (int)c[-FAST_PITCH - 1], (int)c[-FAST_PITCH + 1]);
+        const int n3 = __vimax3_s32((int)c[FAST_PITCH - 1], (int)c[FAST_PITCH + 1], n1);
+        keep = mv > max(n2, n3);
       }
-      const unsigned bm = __ballot_sync(0xffffffffu, keep);
-      if (lane == 0) { sm.bal[idx >> 5] = bm; kept += __popc(bm); }
-      tx += r128;
-      ty += q128;
-      if (tx >= tw) { tx -= tw; ++ty; }
     }
-    if (lane == 0 && kept) atomicAdd(&sm.misc[1], kept);
+    fast_push(keep, (uint16_t)off, sm.kept, &sm.misc[1]);
   }
   __syncthreads();
   return sm.misc[1];
@@ -217,73 +210,45 @@ __global__ void __launch_bounds__(128) k_fast_cells(const OrbGeom* __restrict__ 
   sm.img = fsm;
   sm.m = sm.img + rows_max * FAST_PITCH;
   sm.queue = reinterpret_cast<uint16_t*>(sm.m + rows_max * FAST_PITCH);
-  const int nwords = (t_max + 31) >> 5;
-  sm.bal = reinterpret_cast<uint32_t*>(sm.queue + ((t_max + 1) & ~1));
-  sm.misc = reinterpret_cast<int*>(sm.bal + nwords);
+  sm.kept = sm.queue + ((t_max + 7) & ~7);
+  sm.misc = reinterpret_cast<int*>(sm.kept + ((t_max / 2 + 8) & ~7));
 
   const OrbCell cell = cells[blockIdx.x];
   const OrbLevelGeom& L = g->lv[cell.level];
   const int frame = blockIdx.y;
   const int cw = cell.cw, ch = cell.ch;
-  const int tid = threadIdx.x, lane = tid & 31;
-  // aligned word copy of the sub-image rows; a0 = misalignment of the cell's first column
+  const int tid = threadIdx.x;
+  // aligned word copy of the sub-image rows (16 lanes per row); a0 = misalignment of the first column
   const int bx = ORB_EDGE + cell.ini_x, a0 = bx & 3;
   const uint8_t* base = pyr + (size_t)frame * g->pyr_frame_bytes + L.pyr_off +
                         (size_t)(ORB_EDGE + cell.ini_y) * L.pitch + (bx - a0);
   const int nw = (a0 + cw + 3) >> 2;
-  for (int i = tid; i < ch * nw; i += 128) {
-    const int y = i / nw, wq = i - y * nw;
-    reinterpret_cast<uint32_t*>(sm.img + y * FAST_PITCH)[wq] =
-        __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)y * L.pitch) + wq);
-  }
-  for (int i = tid; i < ch * (FAST_PITCH / 4); i += 128) reinterpret_cast<uint32_t*>(sm.m)[i] = 0u;
+  for (int wq = tid & 15; wq < nw; wq += 16)
+    for (int y = tid >> 4; y < ch; y += 8)
+      reinterpret_cast<uint32_t*>(sm.img + y * FAST_PITCH)[wq] =
+          __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)y * L.pitch) + wq);
+  for (int i = tid; i < ch * (FAST_PITCH / 16); i += 128) reinterpret_cast<uint4*>(sm.m)[i] = make_uint4(0, 0, 0, 0);
   const int tw = cw - 6, thh = ch - 6;
-  const int T = (tw > 0 && thh > 0) ? tw * thh : 0;
   int total = 0, th = g->ini_th;
-  if (T > 0) {
-    total = fast_pass(sm, th, tw, T, a0, false);
+  if (tw > 0 && thh > 0) {
+    total = fast_pass(sm, th, tw, thh, a0, false);
     if (total == 0 && g->min_th < th) {
       th = g->min_th;
-      total = fast_pass(sm, th, tw, T, a0, true);
+      total = fast_pass(sm, th, tw, thh, a0, true);
     }
   }
-  if (total > 0) {
-    // exclusive offsets of the ballot words (warp 0), then ordered write-out
-    const int nword = (T + 31) >> 5;
-    int* woff = sm.misc + 8;
-    if (tid < 32) {
-      int run = 0;
-      for (int w0 = 0; w0 < nword; w0 += 32) {
-        const int w = w0 + lane;
-        const int c = w < nword ? __popc(sm.bal[w]) : 0;
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        if (w < nword) woff[w] = run + incl - c;
-        run += __shfl_sync(0xffffffffu, incl, 31);
-      }
-    }
-    __syncthreads();
-    uint32_t* out = cand + (size_t)frame * g->cand_frame_u32 + L.cand_off + (size_t)cell.slot * L.cand_cap;
-    const int q128 = 128 / tw, r128 = 128 - q128 * tw;
-    int ty = tid / tw, tx = tid - ty * tw;
-    for (int idx = tid; idx < T; idx += 128) {
-      const uint32_t bm = sm.bal[idx >> 5];
-      if (bm >> lane & 1u) {
-        const int pos = woff[idx >> 5] + __popc(bm & ((1u << lane) - 1u));
-        const uint32_t score = (uint32_t)sm.m[(ty + 3) * FAST_PITCH + a0 + tx + 3] - 1u;
-        if (pos < L.cand_cap)
-          out[pos] = (uint32_t)(tx + 3 + cell.off_x) | (uint32_t)(ty + 3 + cell.off_y) << 12 | score << 24;
-      }
-      tx += r128;
-      ty += q128;
-      if (tx >= tw) { tx -= tw; ++ty; }
-    }
+  // ordered write-out: rank of each survivor = number of survivors before it in row-major order
+  // (byte offsets into the pitched map are monotone in (y, x)) = cv::FAST's output order
+  total = min(total, L.cand_cap);
+  uint32_t* out = cand + (size_t)frame * g->cand_frame_u32 + L.cand_off + (size_t)cell.slot * L.cand_cap;
+  for (int i = tid; i < total; i += 128) {
+    const int off = sm.kept[i];
+    int rank = 0;
+    for (int j = 0; j < total; ++j) rank += sm.kept[j] < off;
+    const int y = off / FAST_PITCH, x = off - y * FAST_PITCH - a0;
+    out[rank] = (uint32_t)(x + cell.off_x) | (uint32_t)(y + cell.off_y) << 12 | ((uint32_t)sm.m[off] - 1u) << 24;
   }
-  if (tid == 0) cell_count[(size_t)frame * g->n_cells + blockIdx.x] = min(total, L.cand_cap);
+  if (tid == 0) cell_count[(size_t)frame * g->n_cells + blockIdx.x] = total;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -580,8 +545,8 @@ void launch_fast(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, uint
     rows_max = max(rows_max, gh.g.lv[l].h_cell + 6);
     t_max = max(t_max, gh.g.lv[l].w_cell * gh.g.lv[l].h_cell);
   }
-  const size_t smem = (size_t)2 * rows_max * FAST_PITCH + 2 * (size_t)((t_max + 1) & ~1) + 4 * (size_t)((t_max + 31) >> 5) +
-                      4 * (size_t)(8 + ((t_max + 31) >> 5)) + 16;
+  const size_t smem = (size_t)2 * rows_max * FAST_PITCH + 2 * (size_t)((t_max + 7) & ~7) +
+                      2 * (size_t)((t_max / 2 + 8) & ~7) + 32;
   k_fast_cells<<<dim3(gh.g.n_cells, n_frames), 128, smem, st>>>(gh.d_geom, gh.d_cells, d_pyr, d_cand, d_cell_count,
                                                                   rows_max, t_max);
   ++*launches;

@@ -85,26 +85,45 @@ struct OtScratch {
 enum { OT_V_S = 0, OT_V_NP, OT_V_JSTOP, OT_V_TOTAL, OT_V_TOTAL2, OT_V_SEQ };
 
 // Block-wide exclusive scan: out[i] = sum(in[0..i)), *total = sum(in[0..n)).  in != out.
+// Each thread owns `chunk` consecutive elements.  Device: warp-shuffle scan of the per-thread
+// sums + one shared-memory hop across warps (2 barriers).  Host emulation: the same data flow
+// with the cross-thread step done serially.
 OT_DEV void ot_exclusive_scan(const int* in, int* out, int n, int* total, int* part) {
   const int T = OT_NTHREADS;
   const int chunk = (n + T - 1) / T;
-  OT_FOR_TID(t, T) {
+#ifdef __CUDACC__
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = T >> 5;
+  const int lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += in[i];
+  int incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) part[warp] = incl;
+  __syncthreads();
+  int run = incl - s;
+  for (int w = 0; w < warp; ++w) run += part[w];
+  if (t == T - 1) *total = run + s;
+  for (int i = lo; i < hi; ++i) { const int v = in[i]; out[i] = run; run += v; }
+  (void)nwarp;
+  __syncthreads();
+#else
+  for (int t = 0; t < T; ++t) {
     int lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n, s = 0;
     for (int i = lo; i < hi; ++i) s += in[i];
     part[t] = s;
   }
-  OT_SYNC();
-  OT_SINGLE {
-    int run = 0;
-    for (int t = 0; t < T; ++t) { int v = part[t]; part[t] = run; run += v; }
-    *total = run;
+  int run = 0;
+  for (int t = 0; t < T; ++t) { int v = part[t]; part[t] = run; run += v; }
+  *total = run;
+  for (int t = 0; t < T; ++t) {
+    int lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n, r = part[t];
+    for (int i = lo; i < hi; ++i) { int v = in[i]; out[i] = r; r += v; }
   }
-  OT_SYNC();
-  OT_FOR_TID(t, T) {
-    int lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n, run = part[t];
-    for (int i = lo; i < hi; ++i) { int v = in[i]; out[i] = run; run += v; }
-  }
-  OT_SYNC();
+#endif
 }
 
 // One split round over the nodes flagged in rankP/P (np entries).  early_break_n < 0 disables
