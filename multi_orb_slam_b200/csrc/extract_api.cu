@@ -148,6 +148,7 @@ bool build_geometry(orbx_extractor* h, std::vector<OrbCell>& cells, std::vector<
   g.ini_th = std::min(std::max(h->cfg.ini_th_fast, 0), 255);
   g.min_th = std::min(std::max(h->cfg.min_th_fast, 0), 255);
   if (g.min_th > g.ini_th) { h->err = "minThFAST > iniThFAST is not supported"; return false; }
+  if (h->cfg.scale_factor > 2.5f) { h->err = "scaleFactor > 2.5 is not supported by the pyramid kernel"; return false; }
   size_t pyr_off = 0, blur_off = 0, cand_off = 0, key_off = 0;
   int sel_off = 0, tile_base = 0, max_cells_level = 0;
   g.ot_cap = 0;
@@ -355,7 +356,8 @@ int orbx_create(const orbx_config* cfg, orbx_extractor** out) {
        h->check(cudaMemcpy(h->gh.d_xtab, xt.data(), xt.size() * sizeof(OrbXTap), cudaMemcpyHostToDevice), "copy xtab") &&
        h->check(cudaMemcpy(h->gh.d_ytab, yt.data(), yt.size() * sizeof(OrbYTap), cudaMemcpyHostToDevice), "copy ytab") &&
        h->check(cudaMemset(h->d_pyr, 0, B * g.pyr_frame_bytes), "clear pyramid") &&
-       h->check(orbk::prepare_octree(g), "octree shared-memory opt-in");
+       h->check(orbk::prepare_octree(g), "octree shared-memory opt-in") &&
+       h->check(orbk::prepare_pyramid(g), "pyramid shared-memory opt-in");
   if (!ok) return fail(ORBX_E_CUDA);
   *out = h;
   return ORBX_OK;

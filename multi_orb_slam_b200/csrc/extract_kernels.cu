@@ -45,37 +45,93 @@ __global__ void __launch_bounds__(256) k_pyr_level0(const uint8_t* __restrict__ 
 }
 
 // K1/K2 level l >= 1: cv::resize(level l-1 -> l, INTER_LINEAR) (:1122) fused with the
-// REFLECT_101 border (:1124): every word of the bordered buffer is computed from the source
-// level's interior; border pixels recompute their mirror pixel.
+// REFLECT_101 border (:1124).  One CTA produces a strip of PYR_R consecutive rows of the
+// BORDERED destination buffer:
+//   1. the (<= PYR_NSRC) source rows the strip needs are staged in shared memory with 128-bit
+//      coalesced loads (border rows map to their mirror row, so the range stays contiguous);
+//   2. each thread owns fixed destination columns (taps in registers) and walks the strip's rows;
+//      the horizontal pass of a source row is reused when the next output row shares it;
+//   3. the left/right border is mirrored inside shared memory and the rows leave as 128-bit stores.
+#define PYR_R 8
+#define PYR_NSRC 24
+
 __global__ void __launch_bounds__(256) k_pyr_resize(int level, const OrbGeom* __restrict__ g,
                                                     const OrbXTap* __restrict__ xtab,
                                                     const OrbYTap* __restrict__ ytab, uint8_t* __restrict__ pyr) {
+  extern __shared__ __align__(16) unsigned char psm[];
   const OrbLevelGeom& D = g->lv[level];
   const OrbLevelGeom& S = g->lv[level - 1];
-  const int words = D.pitch >> 2, rows = D.h + 2 * ORB_EDGE;
-  const int id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= words * rows) return;
-  const int by = id / words, wx = id - by * words;
+  uint8_t* s_src = psm;                              // [PYR_NSRC][S.pitch] bordered source rows
+  uint8_t* s_out = psm + (size_t)PYR_NSRC * S.pitch;  // [PYR_R][D.pitch] bordered destination rows
+  __shared__ OrbYTap s_ty[PYR_R];
+  __shared__ int s_range[2];
+  const int tid = threadIdx.x;
+  const int by0 = blockIdx.x * PYR_R, rows_total = D.h + 2 * ORB_EDGE;
+  const int nrows = min(PYR_R, rows_total - by0);
   uint8_t* frame = pyr + (size_t)blockIdx.y * g->pyr_frame_bytes;
-  const uint8_t* sp = frame + S.pyr_off + (size_t)ORB_EDGE * S.pitch + ORB_EDGE;  // source interior origin
-  const OrbYTap ty = ytab[D.ytab_off + reflect101(by - ORB_EDGE, D.h)];
-  const uint8_t* r0 = sp + (size_t)ty.sy0 * S.pitch;
-  const uint8_t* r1 = sp + (size_t)ty.sy1 * S.pitch;
-  const int b0 = ty.b0, b1 = ty.b1;
-  uint32_t v = 0;
+  if (tid < 32) {
+    OrbYTap ty = {0, 0, 0, 0};
+    int lo = 1 << 30, hi = -1;
+    if (tid < nrows) {
+      ty = ytab[D.ytab_off + reflect101(by0 + tid - ORB_EDGE, D.h)];
+      s_ty[tid] = ty;
+      lo = min(ty.sy0, ty.sy1);
+      hi = max(ty.sy0, ty.sy1);
+    }
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int bx = wx * 4 + k;
-    if (bx < D.w + 2 * ORB_EDGE) {
-      const OrbXTap tx = xtab[D.xtab_off + reflect101(bx - ORB_EDGE, D.w)];
-      // sx+1 may be the first border column when sx == sw-1; its weight a1 is 0 there
-      const int h0 = r0[tx.sx] * tx.a0 + r0[tx.sx + 1] * tx.a1;
-      const int h1 = r1[tx.sx] * tx.a0 + r1[tx.sx + 1] * tx.a1;
-      const int val = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-      v |= (uint32_t)val << (8 * k);
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (tid == 0) { s_range[0] = lo; s_range[1] = hi; }
+  }
+  __syncthreads();
+  const int smin = s_range[0], nsrc = min(s_range[1] - smin + 1, PYR_NSRC);
+  // 1. stage bordered source rows (interior row sy = bordered row sy + 19)
+  {
+    const int q_per_row = S.pitch >> 4;
+    const uint8_t* src = frame + S.pyr_off + (size_t)(smin + ORB_EDGE) * S.pitch;
+    for (int i = tid; i < nsrc * q_per_row; i += 256)
+      reinterpret_cast<uint4*>(s_src)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+  }
+  __syncthreads();
+  // 2. bilinear taps; thread-owned columns
+  for (int x = tid; x < D.w; x += 256) {
+    const OrbXTap tx = xtab[D.xtab_off + x];
+    const int c0 = ORB_EDGE + tx.sx;  // bordered column of the left tap; c0+1 is a border column when sx==sw-1 (a1==0)
+    const int a0 = tx.a0, a1 = tx.a1;
+    int prev_row = -1, prev_h = 0;
+    for (int r = 0; r < nrows; ++r) {
+      const OrbYTap ty = s_ty[r];
+      const uint8_t* r0 = s_src + (ty.sy0 - smin) * S.pitch + c0;
+      const uint8_t* r1 = s_src + (ty.sy1 - smin) * S.pitch + c0;
+      const int h0 = (ty.sy0 == prev_row) ? prev_h : r0[0] * a0 + r0[1] * a1;
+      const int h1 = r1[0] * a0 + r1[1] * a1;
+      prev_row = ty.sy1;
+      prev_h = h1;
+      const int val = ((((int)ty.b0 * (h0 >> 4)) >> 16) + (((int)ty.b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      s_out[r * D.pitch + ORB_EDGE + x] = (uint8_t)val;
     }
   }
-  reinterpret_cast<uint32_t*>(frame + D.pyr_off + (size_t)by * D.pitch)[wx] = v;
+  __syncthreads();
+  // 3. mirror the left/right border, zero the pitch padding
+  for (int i = tid; i < nrows * 2 * ORB_EDGE; i += 256) {
+    const int r = i / (2 * ORB_EDGE), k = i - r * (2 * ORB_EDGE);
+    uint8_t* row = s_out + r * D.pitch + ORB_EDGE;
+    if (k < ORB_EDGE) row[-1 - k] = row[1 + k];
+    else row[D.w + (k - ORB_EDGE)] = row[D.w - 2 - (k - ORB_EDGE)];
+  }
+  const int pad = D.pitch - (D.w + 2 * ORB_EDGE);
+  for (int i = tid; i < nrows * pad; i += 256) {
+    const int r = i / pad, k = i - r * pad;
+    s_out[r * D.pitch + D.w + 2 * ORB_EDGE + k] = 0;
+  }
+  __syncthreads();
+  {
+    const int q = nrows * (D.pitch >> 4);
+    uint4* dst = reinterpret_cast<uint4*>(frame + D.pyr_off + (size_t)by0 * D.pitch);
+    for (int i = tid; i < q; i += 256) dst[i] = reinterpret_cast<const uint4*>(s_out)[i];
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -99,7 +155,7 @@ struct FastSmem {
   uint8_t* m;          // arc measure map, 0 = not a corner at the pass threshold
   uint16_t* queue;     // phase-A survivors (byte offsets into img / m)
   uint16_t* kept;      // NMS survivors (byte offsets), unordered
-  int* misc;           // [0] queue length, [1] kept count
+  int* misc;           // [1] kept count, [4..7] per-warp queue lengths
 };
 
 __device__ __forceinline__ int fast_arc_measure(const uint8_t* p) {
@@ -146,35 +202,44 @@ __device__ __forceinline__ void fast_push(bool pred, uint16_t value, uint16_t* l
 // Returns the number of NMS survivors, left (unordered) in sm.kept.
 __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int thh, int a0, bool second_pass) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { sm.misc[0] = 0; sm.misc[1] = 0; }
-  __syncthreads();
+  const unsigned lt = (1u << lane) - 1u;
   // phase A: high-speed rejection.  A 9-arc contains one pixel of every opposite pair (k, k+8),
   // so a bright (dark) arc needs min over pairs of max(a,b) > c+th  (max over pairs of min < c-th).
+  // Each warp appends its survivors to its own queue segment (running count in a register: no
+  // atomics, no shuffles).  Loads are unconditional (lanes beyond tw stay inside the pitched row).
+  const int qseg = ((thh + 3) >> 2) * tw;
+  uint16_t* myq = sm.queue + warp * qseg;
+  int wcount = 0;
   for (int ty = warp; ty < thh; ty += 4) {
+    const uint8_t* prow = sm.img + (ty + 3) * FAST_PITCH + a0 + 3 + lane;
     for (int tx0 = 0; tx0 < tw; tx0 += 32) {
-      const int tx = tx0 + lane;
-      const int off = (ty + 3) * FAST_PITCH + a0 + 3 + tx;
-      bool pass = false;
-      if (tx < tw) {
-        const uint8_t* p = sm.img + off;
-        const int c = p[0];
-        const int r0 = p[3 * FAST_PITCH], r8 = p[-3 * FAST_PITCH], r4 = p[3], r12 = p[-3];
-        const int r2 = p[2 * FAST_PITCH + 2], r10 = p[-2 * FAST_PITCH - 2], r6 = p[-2 * FAST_PITCH + 2],
-                  r14 = p[2 * FAST_PITCH - 2];
-        const int mn = __vimin3_s32(max(r0, r8), max(r4, r12), min(max(r2, r10), max(r6, r14)));
-        const int mx = __vimax3_s32(min(r0, r8), min(r4, r12), max(min(r2, r10), min(r6, r14)));
-        pass = (mn > c + th) || (mx < c - th);
-        // corners already measured by the first pass stay in play for the second pass's NMS
-        if (second_pass && sm.m[off] != 0) pass = true;
-      }
-      fast_push(pass, (uint16_t)off, sm.queue, &sm.misc[0]);
+      const uint8_t* p = prow + tx0;
+      const int c = p[0];
+      const int r0 = p[3 * FAST_PITCH], r8 = p[-3 * FAST_PITCH], r4 = p[3], r12 = p[-3];
+      const int r2 = p[2 * FAST_PITCH + 2], r10 = p[-2 * FAST_PITCH - 2], r6 = p[-2 * FAST_PITCH + 2],
+                r14 = p[2 * FAST_PITCH - 2];
+      const int mn = __vimin3_s32(max(r0, r8), max(r4, r12), min(max(r2, r10), max(r6, r14)));
+      const int mx = __vimax3_s32(min(r0, r8), min(r4, r12), max(min(r2, r10), min(r6, r14)));
+      bool pass = ((mn > c + th) | (mx < c - th)) & (tx0 + lane < tw);
+      // corners already measured by the first pass stay in play for the second pass's NMS
+      if (second_pass) pass = pass | ((sm.m[p - sm.img] != 0) & (tx0 + lane < tw));
+      const unsigned bm = __ballot_sync(0xffffffffu, pass);
+      if (pass) myq[wcount + __popc(bm & lt)] = (uint16_t)(p - sm.img);
+      wcount += __popc(bm);
     }
   }
+  if (lane == 0) sm.misc[4 + warp] = wcount;
+  if (tid == 0) sm.misc[1] = 0;
   __syncthreads();
-  // phase B: full measure for the survivors (dense lanes)
-  const int nq = sm.misc[0];
+  // phase B: full measure for the survivors (dense lanes over the four segments)
+  const int n0 = sm.misc[4], n1 = n0 + sm.misc[5], n2 = n1 + sm.misc[6], nq = n2 + sm.misc[7];
+  auto entry = [&](int q) -> int {
+    const int seg = (q >= n0) + (q >= n1) + (q >= n2);
+    const int base = seg == 0 ? 0 : (seg == 1 ? n0 : (seg == 2 ? n1 : n2));
+    return sm.queue[seg * qseg + (q - base)];
+  };
   for (int q = tid; q < nq; q += 128) {
-    const int off = sm.queue[q];
+    const int off = entry(q);
     const int m = fast_arc_measure(sm.img + off);
     if (m > th) sm.m[off] = (uint8_t)m;
   }
@@ -186,14 +251,14 @@ __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int
     bool keep = false;
     int off = 0;
     if (q < nq) {
-      off = sm.queue[q];
+      off = entry(q);
       const uint8_t* c = sm.m + off;
       const int mv = c[0];
       if (mv > th) {
-        const int n1 = __vimax3_s32((int)c[-1], (int)c[1], (int)c[-FAST_PITCH]);
-        const int n2 = __vimax3_s32((int)c[FAST_PITCH], (int)c[-FAST_PITCH - 1], (int)c[-FAST_PITCH + 1]);
-        const int n3 = __vimax3_s32((int)c[FAST_PITCH - 1], (int)c[FAST_PITCH + 1], n1);
-        keep = mv > max(n2, n3);
+        const int n1_ = __vimax3_s32((int)c[-1], (int)c[1], (int)c[-FAST_PITCH]);
+        const int n2_ = __vimax3_s32((int)c[FAST_PITCH], (int)c[-FAST_PITCH - 1], (int)c[-FAST_PITCH + 1]);
+        const int n3_ = __vimax3_s32((int)c[FAST_PITCH - 1], (int)c[FAST_PITCH + 1], n1_);
+        keep = mv > max(n2_, n3_);
       }
     }
     fast_push(keep, (uint16_t)off, sm.kept, &sm.misc[1]);
@@ -210,7 +275,7 @@ __global__ void __launch_bounds__(128) k_fast_cells(const OrbGeom* __restrict__ 
   sm.img = fsm;
   sm.m = sm.img + rows_max * FAST_PITCH;
   sm.queue = reinterpret_cast<uint16_t*>(sm.m + rows_max * FAST_PITCH);
-  sm.kept = sm.queue + ((t_max + 7) & ~7);
+  sm.kept = sm.queue + ((t_max + 4 * ORB_CELL_MAX + 7) & ~7);
   sm.misc = reinterpret_cast<int*>(sm.kept + ((t_max / 2 + 8) & ~7));
 
   const OrbCell cell = cells[blockIdx.x];
@@ -230,6 +295,7 @@ __global__ void __launch_bounds__(128) k_fast_cells(const OrbGeom* __restrict__ 
   for (int i = tid; i < ch * (FAST_PITCH / 16); i += 128) reinterpret_cast<uint4*>(sm.m)[i] = make_uint4(0, 0, 0, 0);
   const int tw = cw - 6, thh = ch - 6;
   int total = 0, th = g->ini_th;
+  __syncthreads();
   if (tw > 0 && thh > 0) {
     total = fast_pass(sm, th, tw, thh, a0, false);
     if (total == 0 && g->min_th < th) {
@@ -256,7 +322,7 @@ __global__ void __launch_bounds__(128) k_fast_cells(const OrbGeom* __restrict__ 
 __global__ void __launch_bounds__(256) k_octree(const OrbGeom* __restrict__ g, const uint32_t* __restrict__ cand,
                                                 const int* __restrict__ cell_count, uint32_t* __restrict__ keys,
                                                 uint16_t* __restrict__ knode, uint32_t* __restrict__ sel,
-                                                int* __restrict__ sel_count) {
+                                                int* __restrict__ sel_count, int smem_keys) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int level = blockIdx.x, frame = blockIdx.y;
   const OrbLevelGeom& L = g->lv[level];
@@ -264,18 +330,21 @@ __global__ void __launch_bounds__(256) k_octree(const OrbGeom* __restrict__ g, c
   OtScratch s;
   unsigned char* p = smem;
   s.best = reinterpret_cast<unsigned long long*>(p); p += sizeof(unsigned long long) * cap;
-  s.nodes[0] = reinterpret_cast<OtNode*>(p); p += sizeof(OtNode) * cap;
-  s.nodes[1] = reinterpret_cast<OtNode*>(p); p += sizeof(OtNode) * cap;
-  s.cnt4 = reinterpret_cast<int*>(p); p += sizeof(int) * 4 * cap;
-  s.childpos = reinterpret_cast<int*>(p); p += sizeof(int) * 4 * cap;
+  s.nodes = reinterpret_cast<OtNode*>(p); p += sizeof(OtNode) * cap;
+  for (int i = 0; i < 2; ++i) { s.cnt4[i] = reinterpret_cast<int*>(p); p += sizeof(int) * 4 * cap; }
+  for (int i = 0; i < 2; ++i) { s.child[i] = reinterpret_cast<int*>(p); p += sizeof(int) * 4 * cap; }
+  for (int i = 0; i < 2; ++i) { s.order[i] = reinterpret_cast<int*>(p); p += sizeof(int) * cap; }
+  for (int i = 0; i < 2; ++i) { s.split[i] = reinterpret_cast<int*>(p); p += sizeof(int) * cap; }
   s.P = reinterpret_cast<int*>(p); p += sizeof(int) * cap;
-  s.rankP = reinterpret_cast<int*>(p); p += sizeof(int) * cap;
-  s.newpos = reinterpret_cast<int*>(p); p += sizeof(int) * cap;
   s.a = reinterpret_cast<int*>(p); p += sizeof(int) * scap;
   s.b = reinterpret_cast<int*>(p); p += sizeof(int) * scap;
   s.c = reinterpret_cast<int*>(p); p += sizeof(int) * scap;
+  s.d = reinterpret_cast<int*>(p); p += sizeof(int) * scap;
   s.part = reinterpret_cast<int*>(p); p += sizeof(int) * (256 + 1);
-  s.vars = reinterpret_cast<int*>(p);
+  s.vars = reinterpret_cast<int*>(p); p += sizeof(int) * 8;
+  p += (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
+  uint32_t* skeys = reinterpret_cast<uint32_t*>(p);
+  uint16_t* sknode = reinterpret_cast<uint16_t*>(skeys + smem_keys);
 
   // gather this level's candidates in vToDistributeKeys order: cells row-major, in-cell order
   const int* cc = cell_count + (size_t)frame * g->n_cells + L.cell_base;
@@ -284,8 +353,11 @@ __global__ void __launch_bounds__(256) k_octree(const OrbGeom* __restrict__ g, c
   ot_exclusive_scan(s.a, s.b, L.n_cells, &s.vars[OT_V_TOTAL], s.part);
   const int M = s.vars[OT_V_TOTAL];
   const uint32_t* cslots = cand + (size_t)frame * g->cand_frame_u32 + L.cand_off;
-  uint32_t* fkeys = keys + (size_t)frame * g->key_frame_u32 + L.key_off;
-  uint16_t* fknode = knode + (size_t)frame * g->key_frame_u32 + L.key_off;
+  // the policy replay re-labels every key once per round: keep keys and labels in shared memory
+  // whenever the level's candidates fit (they do for camera-like frames), else in the HBM workspace
+  const bool in_smem = M <= smem_keys;
+  uint32_t* fkeys = in_smem ? skeys : keys + (size_t)frame * g->key_frame_u32 + L.key_off;
+  uint16_t* fknode = in_smem ? sknode : knode + (size_t)frame * g->key_frame_u32 + L.key_off;
   {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     for (int c = warp; c < L.n_cells; c += nwarp) {
@@ -530,8 +602,9 @@ void launch_pyramid(const OrbGeomHost& gh, const uint8_t* d_src, size_t frame_st
   }
   for (int l = 1; l < gh.g.nlevels; ++l) {
     const OrbLevelGeom& L = gh.g.lv[l];
-    const int n = (L.pitch >> 2) * (L.h + 2 * ORB_EDGE);
-    k_pyr_resize<<<dim3((n + 255) / 256, n_frames), 256, 0, st>>>(l, gh.d_geom, gh.d_xtab, gh.d_ytab, d_pyr);
+    const int strips = (L.h + 2 * ORB_EDGE + PYR_R - 1) / PYR_R;
+    const size_t smem = (size_t)PYR_NSRC * gh.g.lv[l - 1].pitch + (size_t)PYR_R * L.pitch;
+    k_pyr_resize<<<dim3(strips, n_frames), 256, smem, st>>>(l, gh.d_geom, gh.d_xtab, gh.d_ytab, d_pyr);
     ++*launches;
   }
 }
@@ -545,21 +618,39 @@ void launch_fast(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, uint
     rows_max = max(rows_max, gh.g.lv[l].h_cell + 6);
     t_max = max(t_max, gh.g.lv[l].w_cell * gh.g.lv[l].h_cell);
   }
-  const size_t smem = (size_t)2 * rows_max * FAST_PITCH + 2 * (size_t)((t_max + 7) & ~7) +
+  const size_t smem = (size_t)2 * rows_max * FAST_PITCH + 2 * (size_t)((t_max + 4 * ORB_CELL_MAX + 7) & ~7) +
                       2 * (size_t)((t_max / 2 + 8) & ~7) + 32;
   k_fast_cells<<<dim3(gh.g.n_cells, n_frames), 128, smem, st>>>(gh.d_geom, gh.d_cells, d_pyr, d_cand, d_cell_count,
                                                                   rows_max, t_max);
   ++*launches;
 }
 
+int octree_smem_keys(const OrbGeom& g) {
+  int m = 0;
+  for (int l = 0; l < g.nlevels; ++l) m = max(m, g.lv[l].key_cap);
+  return min(m, 6144);  // 36 KB of keys + labels keeps ~3 CTAs resident per SM
+}
+
 size_t octree_smem_bytes(const OrbGeom& g) {
   const size_t cap = g.ot_cap, scap = g.ot_scan_cap;
-  return sizeof(unsigned long long) * cap + 2 * sizeof(OtNode) * cap + sizeof(int) * (8 * cap + 3 * cap) +
-         sizeof(int) * 3 * scap + sizeof(int) * 257 + sizeof(int) * 8;
+  return sizeof(unsigned long long) * cap + sizeof(OtNode) * cap + sizeof(int) * (16 * cap + 5 * cap) +
+         sizeof(int) * 4 * scap + sizeof(int) * 257 + sizeof(int) * 8 + 16 + (size_t)octree_smem_keys(g) * 6;
 }
 
 // The opt-in limit is a property of the FUNCTION (per device), shared by every handle: only ever
 // raise it, so a handle with a smaller nfeatures cannot shrink it under another handle's feet.
+cudaError_t prepare_pyramid(const OrbGeom& g) {
+  static int raised[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const int need = g.nlevels > 1 ? (int)((size_t)PYR_NSRC * g.lv[0].pitch + (size_t)PYR_R * g.lv[1].pitch) : 0;
+  if (need <= 48 * 1024 || (dev < 64 && need <= raised[dev])) return cudaSuccess;
+  e = cudaFuncSetAttribute(k_pyr_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+  if (e == cudaSuccess && dev < 64) raised[dev] = need;
+  return e;
+}
+
 cudaError_t prepare_octree(const OrbGeom& g) {
   static int raised[64] = {0};
   int dev = 0;
@@ -576,7 +667,7 @@ void launch_octree(const OrbGeomHost& gh, int n_frames, const uint32_t* d_cand, 
                    uint32_t* d_keys, uint16_t* d_knode, uint32_t* d_sel, int* d_sel_count, cudaStream_t st,
                    long long* launches) {
   k_octree<<<dim3(gh.g.nlevels, n_frames), 256, octree_smem_bytes(gh.g), st>>>(gh.d_geom, d_cand, d_cell_count, d_keys,
-                                                                                d_knode, d_sel, d_sel_count);
+                                                                                d_knode, d_sel, d_sel_count, octree_smem_keys(gh.g));
   ++*launches;
 }
 

@@ -22,6 +22,7 @@ void launch_fast(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, uint
                  cudaStream_t st, long long* launches);
 size_t octree_smem_bytes(const OrbGeom& g);
 cudaError_t prepare_octree(const OrbGeom& g);
+cudaError_t prepare_pyramid(const OrbGeom& g);
 void launch_octree(const OrbGeomHost& gh, int n_frames, const uint32_t* d_cand, const int* d_cell_count,
                    uint32_t* d_keys, uint16_t* d_knode, uint32_t* d_sel, int* d_sel_count, cudaStream_t st,
                    long long* launches);

@@ -245,87 +245,126 @@ __device__ __forceinline__ void warp_top2(uint32_t& best, uint32_t& second) {
 }
 
 // ---- SearchForInitialization ----------------------------------------------------------------
-// One CTA per frame pair.  Phase A (all warps): for each level-0 keypoint i1 of F1, the window
-// query on F2's grid and the Hamming distances, candidates stored in traversal order as
-// (dist << 16 | i2).  Phase B (warp 0, i1 ascending): the best/second scan with the
-// vMatchedDistance filter (:907), acceptance, match stealing (:926-933) and histogram.  Then
+// Phase A (k_init_candidates, one warp per (pair, i1), whole GPU): for each level-0 keypoint i1
+// of F1, the window query on F2's grid and the Hamming distances; candidates are stored in the
+// reference's traversal order as (dist << 16 | i2).
+// Phase B (k_init_resolve, one CTA per pair; warp 0 walks i1 ascending): the best/second scan with
+// the vMatchedDistance filter (:907), acceptance, match stealing (:926-933) and histogram; then
 // the three-maxima rotation filter and the vbPrevMatched update, in parallel.
-__global__ void __launch_bounds__(256) k_search_init(int cap, const orbx_keypoint* __restrict__ k1_all,
-                                                     const uint8_t* __restrict__ d1_all, const int32_t* __restrict__ n1_arr,
-                                                     const orbx_keypoint* __restrict__ k2_all,
-                                                     const uint8_t* __restrict__ d2_all, const int32_t* __restrict__ n2_arr,
-                                                     orbm_bounds b2, const int* __restrict__ grid_start,
-                                                     const uint16_t* __restrict__ grid_items, float* __restrict__ prev_all,
-                                                     float window, float nnratio, int check_ori,
-                                                     uint32_t* __restrict__ cand_all, int* __restrict__ cand_cnt_all,
-                                                     int32_t* __restrict__ matches12_all, int32_t* __restrict__ nmatches_out) {
-  extern __shared__ int s_dyn[];  // matchedDist[cap], matches21[cap], bin_of[cap]
+__global__ void __launch_bounds__(256) k_init_candidates(int cap, const orbx_keypoint* __restrict__ k1_all,
+                                                         const uint8_t* __restrict__ d1_all,
+                                                         const int32_t* __restrict__ n1_arr,
+                                                         const orbx_keypoint* __restrict__ k2_all,
+                                                         const uint8_t* __restrict__ d2_all, orbm_bounds b2,
+                                                         const int* __restrict__ grid_start,
+                                                         const uint16_t* __restrict__ grid_items,
+                                                         const float* __restrict__ prev_all, float window,
+                                                         uint32_t* __restrict__ cand_all, int* __restrict__ cand_cnt_all) {
+  const int pair = blockIdx.y, lane = threadIdx.x & 31;
+  const int i1 = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int n1 = min(n1_arr[pair], cap);
+  if (i1 >= n1) return;
+  const orbx_keypoint* k1 = k1_all + (size_t)pair * cap;
+  const orbx_keypoint* k2 = k2_all + (size_t)pair * cap;
+  const uint8_t* d2 = d2_all + (size_t)pair * cap * 32;
+  const orbx_keypoint kp1 = k1[i1];
+  int cnt = 0;
+  if (kp1.octave <= 0) {  // level1 > 0 -> continue (:885-887)
+    GridView gv;
+    gv.start = grid_start + (size_t)pair * (GRID_CELLS + 1);
+    gv.items = grid_items + (size_t)pair * cap;
+    gv.min_x = b2.min_x;
+    gv.min_y = b2.min_y;
+    gv.inv_w = __fdiv_rn((float)GRID_COLS, __fsub_rn(b2.max_x, b2.min_x));
+    gv.inv_h = __fdiv_rn((float)GRID_ROWS, __fsub_rn(b2.max_y, b2.min_y));
+    const uint4* q = reinterpret_cast<const uint4*>(d1_all + ((size_t)pair * cap + i1) * 32);
+    const uint4 qa = __ldg(q), qb = __ldg(q + 1);
+    uint32_t* row = cand_all + ((size_t)pair * cap + i1) * cap;
+    const float* prev = prev_all ? prev_all + ((size_t)pair * cap + i1) * 2 : nullptr;
+    const float px = prev ? prev[0] : kp1.x, py = prev ? prev[1] : kp1.y;
+    grid_query(gv, k2, px, py, window, kp1.octave, kp1.octave, [&](bool ok, int idx) {
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const uint4* tp = reinterpret_cast<const uint4*>(d2 + (size_t)idx * 32);
+        const int dist = hamming256(qa, qb, __ldg(tp), __ldg(tp + 1));
+        row[cnt + __popc(m & ((1u << lane) - 1u))] = (uint32_t)dist << 16 | (uint32_t)idx;
+      }
+      cnt += __popc(m);
+    });
+  }
+  if (lane == 0) cand_cnt_all[(size_t)pair * cap + i1] = cnt;
+}
+
+__global__ void __launch_bounds__(128) k_init_resolve(int cap, const orbx_keypoint* __restrict__ k1_all,
+                                                      const int32_t* __restrict__ n1_arr,
+                                                      const orbx_keypoint* __restrict__ k2_all, float* __restrict__ prev_all,
+                                                      float nnratio, int check_ori, const uint32_t* __restrict__ cand_all,
+                                                      const int* __restrict__ cand_cnt_all,
+                                                      int32_t* __restrict__ matches12_all, int32_t* __restrict__ nmatches_out) {
+  extern __shared__ int s_dyn[];  // matchedDist, matches21, bin_of, cand count, query list: [cap] each
   __shared__ int s_hist[HISTO_LENGTH];
   __shared__ int s_keep[HISTO_LENGTH];
   __shared__ int s_nmatch;
   const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n1 = min(n1_arr[pair], cap), n2 = min(n2_arr[pair], cap);
+  const int n1 = min(n1_arr[pair], cap);
   const orbx_keypoint* k1 = k1_all + (size_t)pair * cap;
   const orbx_keypoint* k2 = k2_all + (size_t)pair * cap;
-  const uint8_t* d1 = d1_all + (size_t)pair * cap * 32;
-  const uint8_t* d2 = d2_all + (size_t)pair * cap * 32;
   float* prev = prev_all ? prev_all + (size_t)pair * cap * 2 : nullptr;
-  uint32_t* cand = cand_all + (size_t)pair * cap * cap;
-  int* cand_cnt = cand_cnt_all + (size_t)pair * cap;
+  const uint32_t* cand = cand_all + (size_t)pair * cap * cap;
+  const int* cand_cnt = cand_cnt_all + (size_t)pair * cap;
   int32_t* matches12 = matches12_all + (size_t)pair * cap;
   int* s_mdist = s_dyn;
   int* s_m21 = s_dyn + cap;
   int* s_bin = s_dyn + 2 * cap;
-  GridView gv;
-  gv.start = grid_start + (size_t)pair * (GRID_CELLS + 1);
-  gv.items = grid_items + (size_t)pair * cap;
-  gv.min_x = b2.min_x;
-  gv.min_y = b2.min_y;
-  gv.inv_w = __fdiv_rn((float)GRID_COLS, __fsub_rn(b2.max_x, b2.min_x));
-  gv.inv_h = __fdiv_rn((float)GRID_ROWS, __fsub_rn(b2.max_y, b2.min_y));
-
-  for (int i = tid; i < cap; i += 256) {
+  int* s_cnt = s_dyn + 3 * cap;   // candidates per i1
+  int* s_list = s_dyn + 4 * cap;  // i1 with at least one candidate, ascending
+  __shared__ int s_nlist;
+  for (int i = tid; i < cap; i += 128) {
     s_mdist[i] = 0x7FFFFFFF;
     s_m21[i] = -1;
     s_bin[i] = -1;
+    s_cnt[i] = i < n1 ? cand_cnt[i] : 0;
     if (i < n1) matches12[i] = -1;
   }
   if (tid < HISTO_LENGTH) s_hist[tid] = 0;
   if (tid == 0) s_nmatch = 0;
-  // phase A
-  for (int i1 = warp; i1 < n1; i1 += 8) {
-    int cnt = 0;
-    if (k1[i1].octave <= 0) {  // level1 > 0 -> continue (:885-887)
-      const uint4* q = reinterpret_cast<const uint4*>(d1 + (size_t)i1 * 32);
-      const uint4 qa = __ldg(q), qb = __ldg(q + 1);
-      uint32_t* row = cand + (size_t)i1 * cap;
-      const int level1 = k1[i1].octave;
-      const float px = prev ? prev[2 * i1] : k1[i1].x, py = prev ? prev[2 * i1 + 1] : k1[i1].y;
-      grid_query(gv, k2, px, py, window, level1, level1, [&](bool ok, int idx) {
-        const unsigned m = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-          const uint4* tp = reinterpret_cast<const uint4*>(d2 + (size_t)idx * 32);
-          const int dist = hamming256(qa, qb, __ldg(tp), __ldg(tp + 1));
-          row[cnt + __popc(m & ((1u << lane) - 1u))] = (uint32_t)dist << 16 | (uint32_t)idx;
-        }
-        cnt += __popc(m);
-      });
-    }
-    if (lane == 0) cand_cnt[i1] = cnt;
-  }
   __threadfence_block();
   __syncthreads();
-  // phase B
   if (warp == 0) {
+    // ordered compaction of the queries that have candidates (most keypoints are not level 0)
+    int nlist = 0;
+    for (int base = 0; base < n1; base += 32) {
+      const int i = base + lane;
+      const bool has = i < n1 && s_cnt[i] > 0;
+      const unsigned bm = __ballot_sync(0xffffffffu, has);
+      if (has) s_list[nlist + __popc(bm & ((1u << lane) - 1u))] = i;
+      nlist += __popc(bm);
+    }
+    __syncwarp();
     int nmatches = 0;
-    for (int i1 = 0; i1 < n1; ++i1) {
-      const int cnt = cand_cnt[i1];
-      if (cnt == 0) continue;
+    // software prefetch: the next query's first 64 candidates are loaded while this one resolves
+    uint32_t pf0 = 0, pf1 = 0;
+    if (nlist > 0) {
+      const uint32_t* r0 = cand + (size_t)s_list[0] * cap;
+      const int c0 = s_cnt[s_list[0]];
+      if (lane < c0) pf0 = r0[lane];
+      if (lane + 32 < c0) pf1 = r0[lane + 32];
+    }
+    for (int j = 0; j < nlist; ++j) {
+      const int i1 = s_list[j];
+      const int cnt = s_cnt[i1];
       const uint32_t* row = cand + (size_t)i1 * cap;
+      const uint32_t e0 = pf0, e1 = pf1;
+      if (j + 1 < nlist) {
+        const uint32_t* rn = cand + (size_t)s_list[j + 1] * cap;
+        const int cn = s_cnt[s_list[j + 1]];
+        if (lane < cn) pf0 = rn[lane];
+        if (lane + 32 < cn) pf1 = rn[lane + 32];
+      }
       // key = dist << 16 | traversal position: strict-< scan order (:910-919)
       uint32_t best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
       for (int c = lane; c < cnt; c += 32) {
-        const uint32_t e = row[c];
+        const uint32_t e = c < 32 ? e0 : (c < 64 ? e1 : row[c]);
         const int dist = (int)(e >> 16), i2 = (int)(e & 0xFFFFu);
         if (s_mdist[i2] <= dist) continue;  // :907
         const uint32_t key = (uint32_t)dist << 16 | (uint32_t)c;
@@ -377,7 +416,7 @@ __global__ void __launch_bounds__(256) k_search_init(int cap, const orbx_keypoin
   __threadfence_block();
   __syncthreads();
   if (check_ori) {
-    for (int i1 = tid; i1 < n1; i1 += 256) {
+    for (int i1 = tid; i1 < n1; i1 += 128) {
       const int bin = s_bin[i1];
       if (bin >= 0 && !s_keep[bin] && matches12[i1] >= 0) {
         matches12[i1] = -1;
@@ -386,7 +425,7 @@ __global__ void __launch_bounds__(256) k_search_init(int cap, const orbx_keypoin
     }
     __syncthreads();
   }
-  for (int i1 = tid; prev && i1 < n1; i1 += 256) {  // :978-980
+  for (int i1 = tid; prev && i1 < n1; i1 += 128) {  // :978-980
     const int m = matches12[i1];
     if (m >= 0) {
       prev[2 * i1] = k2[m].x;
@@ -665,7 +704,7 @@ int orbm_search_for_initialization_device(orbm_matcher* m, int n_pairs, int cap,
   if (!m || n_pairs < 0 || cap < 1 || cap > 65535) return ORBX_E_INVALID;
   if (n_pairs == 0) return ORBX_OK;
   cudaSetDevice(m->device);
-  const size_t smem = sizeof(int) * 3 * (size_t)cap;
+  const size_t smem = sizeof(int) * 5 * (size_t)cap;
   if (smem > 200 * 1024) { m->err = "cap too large for SearchForInitialization"; return ORBX_E_INVALID; }
   // candidate rows are cap x cap per pair: process pairs in groups that keep the scratch <= ~2 GiB
   const size_t per_pair = (size_t)cap * cap * sizeof(uint32_t);
@@ -675,16 +714,20 @@ int orbm_search_for_initialization_device(orbm_matcher* m, int n_pairs, int cap,
   uint32_t* cand = m->scratch<uint32_t>(6, (size_t)group * cap * cap);
   int* cand_cnt = m->scratch<int>(7, (size_t)group * cap);
   if (!gstart || !gitems || !cand || !cand_cnt) return ORBX_E_CUDA;
-  if (!m->check(cudaFuncSetAttribute(k_search_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in"))
+  if (smem > 48 * 1024 &&
+      !m->check(cudaFuncSetAttribute(k_init_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in"))
     return ORBX_E_CUDA;
   for (int p0 = 0; p0 < n_pairs; p0 += group) {
     const int np = std::min(group, n_pairs - p0);
     const size_t o = (size_t)p0 * cap;
     k_build_grid<<<np, 256, 0, m->stream>>>(d_k2 + o, d_n2 + p0, 0, cap, bounds2, gstart, gitems);
-    k_search_init<<<np, 256, smem, m->stream>>>(cap, d_k1 + o, d_d1 + o * 32, d_n1 + p0, d_k2 + o, d_d2 + o * 32, d_n2 + p0,
-                                                bounds2, gstart, gitems, d_prev_xy ? d_prev_xy + o * 2 : nullptr, (float)window, nnratio, check_ori,
-                                                cand, cand_cnt, d_matches12 + o, d_nmatches + p0);
-    m->launches += 2;
+    float* prev = d_prev_xy ? d_prev_xy + o * 2 : nullptr;
+    k_init_candidates<<<dim3((cap + 7) / 8, np), 256, 0, m->stream>>>(cap, d_k1 + o, d_d1 + o * 32, d_n1 + p0, d_k2 + o,
+                                                                        d_d2 + o * 32, bounds2, gstart, gitems, prev,
+                                                                        (float)window, cand, cand_cnt);
+    k_init_resolve<<<np, 128, smem, m->stream>>>(cap, d_k1 + o, d_n1 + p0, d_k2 + o, prev, nnratio, check_ori, cand,
+                                                 cand_cnt, d_matches12 + o, d_nmatches + p0);
+    m->launches += 3;
   }
   return m->check(cudaGetLastError(), "search_for_initialization launch") ? ORBX_OK : ORBX_E_CUDA;
 }

@@ -8,21 +8,23 @@
 //   1. P = nodes with >1 key, in list order (phase 1) or sorted by (count desc, creation seq
 //      desc) (phase 2: std::sort ascending on (size, node address) walked from the back; the
 //      address is pinned to creation order);
-//   2. every key of a P node finds its quadrant -> per-child counts (shared-memory atomics);
+//   2. ONE pass over the keys per round: a key first picks up the child it fell into when its
+//      node was split in the previous round, then — if its (new) node is in P — finds its
+//      quadrant and bumps that child's counter (shared-memory atomics);
 //   3. prefix sums over P give the list size after each split, hence the early-break index
 //      (:731-732), the children's creation sequence and the new list order (children are
-//      push_front'ed, so they appear reversed in front; untouched nodes keep their order);
-//   4. keys are re-labelled with their node's new list position.
-// One CTA handles one (frame, level).  The same source compiles for the host with the OT_*
-// macros expanding to a sequential thread emulation (tests/native/octree_host.cc), which is
-// how the logic is validated against the oracle without a GPU.
+//      push_front'ed, so they appear reversed in front; untouched nodes keep their order).
+// Nodes live in stable slots (the first non-empty child reuses its parent's slot), the list is
+// an array of slots.  One CTA handles one (frame, level).  The same source compiles for the
+// host with the OT_* macros expanding to a sequential thread emulation
+// (tests/native/octree_host.cc), which is how the logic is validated against the oracle
+// without a GPU.
 #pragma once
 #include <stdint.h>
 
 #ifdef __CUDACC__
 #define OT_DEV __device__ __forceinline__
 #define OT_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
-#define OT_FOR_TID(t, T) for (int t = threadIdx.x, _once = 1; _once; _once = 0)
 #define OT_NTHREADS ((int)blockDim.x)
 #define OT_SYNC() __syncthreads()
 #define OT_SINGLE if (threadIdx.x == 0)
@@ -33,7 +35,6 @@
 #else
 #define OT_DEV static inline
 #define OT_FOR(i, n) for (int i = 0; i < (n); ++i)
-#define OT_FOR_TID(t, T) for (int t = 0; t < (T); ++t)
 #define OT_NTHREADS 256
 #define OT_SYNC() ((void)0)
 #define OT_SINGLE
@@ -67,17 +68,20 @@ struct OtRoots {
   int height;                      // maxY - minY
 };
 
-// Scratch (shared memory on the device).  cap = node capacity >= max(N + 3, 4 * n_ini) + 1.
+// Scratch (shared memory on the device).  cap = node capacity >= max(N + 3, 4 * n_ini) + 1;
+// the scan arrays a..d hold max(cap, cells of the level) + 1 entries (the caller's gather
+// reuses a/b).
 struct OtScratch {
-  OtNode* nodes[2];   // [cap] x2   current / next list, index = list position (0 = front)
-  int* P;             // [cap]      processing order -> list position
-  int* rankP;         // [cap]      list position -> index in P, or -1
-  int* cnt4;          // [4*cap]    per P entry, keys per child n1..n4
-  int* a;             // [cap + 1]  scan input / scratch
-  int* b;             // [cap + 1]  scan output
-  int* c;             // [cap + 1]  second scan output
-  int* newpos;        // [cap]      old list position -> new list position (untouched nodes)
-  int* childpos;      // [4*cap]    P entry, child -> new list position
+  OtNode* nodes;      // [cap]      stable slots
+  int* order[2];      // [cap] x2   list position -> slot (current / next)
+  int* P;             // [cap]      processing order -> slot
+  int* split[2];      // [cap] x2   slot -> index in P (this round / previous round), -1 = not split
+  int* cnt4[2];       // [4*cap] x2 per P entry, keys per child n1..n4 (this / previous round)
+  int* child[2];      // [4*cap] x2 per P entry, child -> slot (this / previous round)
+  int* a;             // scan scratch
+  int* b;
+  int* c;
+  int* d;
   int* part;          // [OT_NTHREADS + 1] scan partials
   unsigned long long* best;  // [cap] arg-max accumulator of the final stage
   int* vars;          // [8]
@@ -92,7 +96,7 @@ OT_DEV void ot_exclusive_scan(const int* in, int* out, int n, int* total, int* p
   const int T = OT_NTHREADS;
   const int chunk = (n + T - 1) / T;
 #ifdef __CUDACC__
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = T >> 5;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
   int s = 0;
   for (int i = lo; i < hi; ++i) s += in[i];
@@ -108,7 +112,6 @@ OT_DEV void ot_exclusive_scan(const int* in, int* out, int n, int* total, int* p
   for (int w = 0; w < warp; ++w) run += part[w];
   if (t == T - 1) *total = run + s;
   for (int i = lo; i < hi; ++i) { const int v = in[i]; out[i] = run; run += v; }
-  (void)nwarp;
   __syncthreads();
 #else
   for (int t = 0; t < T; ++t) {
@@ -126,33 +129,89 @@ OT_DEV void ot_exclusive_scan(const int* in, int* out, int n, int* total, int* p
 #endif
 }
 
-// One split round over the nodes flagged in rankP/P (np entries).  early_break_n < 0 disables
-// the early break (phase 1).  Returns the new list size; flips *cur.
-OT_DEV int ot_round(const uint32_t* keys, uint16_t* knode, int M, OtScratch& s, int* cur, int S, int np,
-                    int early_break_n) {
-  const OtNode* L = s.nodes[*cur];
-  OtNode* Lnew = s.nodes[*cur ^ 1];
-  OT_FOR(i, 4 * np) s.cnt4[i] = 0;
-  OT_SYNC();
-  // 2. quadrant of every key that lives in a node being split (DivideNode :521-535)
-  OT_FOR(k, M) {
-    const unsigned pos = knode[k] & OT_POS_MASK;
-    const int j = s.rankP[pos];
-    if (j >= 0) {
-      const OtNode nd = L[pos];
-      const int mx = nd.ulx + ((nd.brx - nd.ulx + 1) >> 1);  // UL.x + ceil(w/2)
-      const int my = nd.uly + ((nd.bry - nd.uly + 1) >> 1);
-      const uint32_t key = keys[k];
-      const int q = (OT_KEY_X(key) < mx ? 0 : 1) + (OT_KEY_Y(key) < my ? 0 : 2);
-      OT_ATOMIC_ADD(&s.cnt4[4 * j + q], 1);
-      knode[k] = (uint16_t)(pos | (unsigned)q << 14);
+// Build P = nodes with count > 1 and split[cur][slot] = index in P (or -1) over the current
+// list.  sorted == 0: list order (phase-1 pass, :607-666).  sorted == 1: (count desc, seq desc),
+// i.e. the reference's ascending sort on (size, address) walked from the back (:685-686).
+// Also zeroes the child counters of the round.  Returns np.
+OT_DEV int ot_build_P(OtScratch& s, int cur, int lst, int S, int sorted) {
+  const int* L = s.order[lst];
+  int* split = s.split[cur];
+  if (!sorted) {
+    OT_FOR(p, S) s.a[p] = s.nodes[L[p]].count > 1;
+    OT_SYNC();
+    ot_exclusive_scan(s.a, s.b, S, &s.vars[OT_V_NP], s.part);
+    OT_FOR(p, S) {
+      const int slot = L[p];
+      if (s.a[p]) { split[slot] = s.b[p]; s.P[s.b[p]] = slot; }
+      else split[slot] = -1;
+    }
+  } else {
+    OT_SINGLE s.vars[OT_V_NP] = 0;
+    OT_SYNC();
+    OT_FOR(p, S) {
+      const int slot = L[p];
+      const int cp = s.nodes[slot].count, sp = s.nodes[slot].seq;
+      if (cp > 1) {
+        int r = 0;
+        for (int o = 0; o < S; ++o) {
+          const OtNode& other = s.nodes[L[o]];
+          r += (other.count > 1) && (other.count > cp || (other.count == cp && other.seq > sp));
+        }
+        split[slot] = r;
+        s.P[r] = slot;
+        OT_ATOMIC_ADD(&s.vars[OT_V_NP], 1);
+      } else {
+        split[slot] = -1;
+      }
     }
   }
   OT_SYNC();
-  // 3. non-empty children per split; prefix sums in processing order
+  const int np = s.vars[OT_V_NP];
+  OT_FOR(i, 4 * np) s.cnt4[cur][i] = 0;
+  OT_SYNC();
+  return np;
+}
+
+// The per-round key pass.  prev >= 0: first move every key of a node split in the previous
+// round (P index <= jstop_prev) into the child it fell into.  cur >= 0: then, if the key's node
+// is about to be split, find its quadrant (DivideNode :521-535) and count it.
+OT_DEV void ot_key_pass(const uint32_t* keys, uint16_t* knode, int M, OtScratch& s, int prev, int jstop_prev, int cur) {
+  OT_FOR(k, M) {
+    unsigned v = knode[k];
+    int slot = (int)(v & OT_POS_MASK);
+    if (prev >= 0) {
+      const int jp = s.split[prev][slot];
+      if (jp >= 0 && jp <= jstop_prev) slot = s.child[prev][4 * jp + (int)(v >> 14)];
+      v = (unsigned)slot;
+    }
+    if (cur >= 0) {
+      const int j = s.split[cur][slot];
+      if (j >= 0) {
+        const OtNode nd = s.nodes[slot];
+        const int mx = nd.ulx + ((nd.brx - nd.ulx + 1) >> 1);  // UL.x + ceil(w/2)
+        const int my = nd.uly + ((nd.bry - nd.uly + 1) >> 1);
+        const uint32_t key = keys[k];
+        const int q = (OT_KEY_X(key) < mx ? 0 : 1) + (OT_KEY_Y(key) < my ? 0 : 2);
+        OT_ATOMIC_ADD(&s.cnt4[cur][4 * j + q], 1);
+        v = (unsigned)slot | (unsigned)q << 14;
+      }
+    }
+    knode[k] = (uint16_t)v;
+  }
+  OT_SYNC();
+}
+
+// Commit one round: given P (np entries), its child counters and the early-break limit
+// (early_break_n < 0: none), create the children, rebuild the list.  Returns the new list size;
+// *jstop_out = last processed P index.
+OT_DEV int ot_commit_round(OtScratch& s, int cur, int lst, int S, int np, int early_break_n, int* jstop_out) {
+  const int* L = s.order[lst];
+  int* Lnew = s.order[lst ^ 1];
+  const int* cnt4 = s.cnt4[cur];
+  // non-empty children per split; prefix sums in processing order
   OT_FOR(j, np) {
     int nne = 0;
-    for (int q = 0; q < 4; ++q) nne += s.cnt4[4 * j + q] > 0;
+    for (int q = 0; q < 4; ++q) nne += cnt4[4 * j + q] > 0;
     s.a[j] = nne;
   }
   OT_SINGLE s.vars[OT_V_JSTOP] = np - 1;
@@ -168,28 +227,28 @@ OT_DEV int ot_round(const uint32_t* keys, uint16_t* knode, int M, OtScratch& s, 
   const int jstop = s.vars[OT_V_JSTOP];
   const int C = np > 0 ? s.b[jstop] + s.a[jstop] : 0;  // children pushed this round
   const int seq_base = s.vars[OT_V_SEQ];
-  // 4a. untouched nodes keep their relative order behind the new children
+  // untouched nodes keep their relative order behind the new children
   OT_FOR(p, S) {
-    const int j = s.rankP[p];
+    const int j = s.split[cur][L[p]];
     s.c[p] = !(j >= 0 && j <= jstop);
   }
   OT_SYNC();
-  ot_exclusive_scan(s.c, s.newpos, S, &s.vars[OT_V_TOTAL2], s.part);
+  ot_exclusive_scan(s.c, s.d, S, &s.vars[OT_V_TOTAL2], s.part);
   OT_FOR(p, S) {
-    if (s.c[p]) {
-      const int np_ = C + s.newpos[p];
-      s.newpos[p] = np_;
-      Lnew[np_] = L[p];
-    }
+    if (s.c[p]) Lnew[C + s.d[p]] = L[p];
   }
-  // 4b. children: creation order (j asc, n1..n4), pushed to the front => reversed positions
+  // children: creation order (j asc, n1..n4), pushed to the front => reversed positions.  The
+  // first non-empty child reuses the parent's slot, the others take fresh slots from S upward.
   OT_FOR(j, jstop + 1) {
-    const OtNode nd = L[s.P[j]];
+    const int pslot = s.P[j];
+    const OtNode nd = s.nodes[pslot];
     const int mx = nd.ulx + ((nd.brx - nd.ulx + 1) >> 1);
     const int my = nd.uly + ((nd.bry - nd.uly + 1) >> 1);
     int cr = s.b[j];
+    int fresh = S + s.b[j] - j;  // slots handed out to earlier splits: sum(nne - 1)
+    bool first = true;
     for (int q = 0; q < 4; ++q) {
-      const int cnt = s.cnt4[4 * j + q];
+      const int cnt = cnt4[4 * j + q];
       if (cnt == 0) continue;
       OtNode ch;
       ch.ulx = (short)((q & 1) ? mx : nd.ulx);
@@ -198,67 +257,23 @@ OT_DEV int ot_round(const uint32_t* keys, uint16_t* knode, int M, OtScratch& s, 
       ch.bry = (short)((q & 2) ? nd.bry : my);
       ch.count = cnt;
       ch.seq = seq_base + cr;
-      const int pos = C - 1 - cr;
-      Lnew[pos] = ch;
-      s.childpos[4 * j + q] = pos;
+      const int slot = first ? pslot : fresh++;
+      first = false;
+      s.nodes[slot] = ch;
+      s.child[cur][4 * j + q] = slot;
+      Lnew[C - 1 - cr] = slot;
       ++cr;
     }
   }
   OT_SYNC();
-  // 5. re-label keys with their node's new list position
-  OT_FOR(k, M) {
-    const unsigned v = knode[k];
-    const unsigned pos = v & OT_POS_MASK;
-    const int j = s.rankP[pos];
-    knode[k] = (uint16_t)((j >= 0 && j <= jstop) ? s.childpos[4 * j + (v >> 14)] : s.newpos[pos]);
-  }
-  OT_SYNC();
-  const int S_new = S + C - (np > 0 ? jstop + 1 : 0);
   OT_SINGLE s.vars[OT_V_SEQ] = seq_base + C;
-  *cur ^= 1;
+  *jstop_out = jstop;
   OT_SYNC();
-  return S_new;
-}
-
-// Build P = nodes with count > 1.  sorted == 0: list order (phase-1 pass, :607-666).
-// sorted == 1: (count desc, seq desc), i.e. the reference's ascending sort on
-// (size, address) walked from the back (:685-686).  Returns np.
-OT_DEV int ot_build_P(OtScratch& s, int cur, int S, int sorted) {
-  const OtNode* L = s.nodes[cur];
-  if (!sorted) {
-    OT_FOR(p, S) s.a[p] = L[p].count > 1;
-    OT_SYNC();
-    ot_exclusive_scan(s.a, s.b, S, &s.vars[OT_V_NP], s.part);
-    OT_FOR(p, S) {
-      if (s.a[p]) { s.rankP[p] = s.b[p]; s.P[s.b[p]] = p; }
-      else s.rankP[p] = -1;
-    }
-    OT_SYNC();
-  } else {
-    OT_SINGLE s.vars[OT_V_NP] = 0;
-    OT_SYNC();
-    OT_FOR(p, S) {
-      const int cp = L[p].count, sp = L[p].seq;
-      if (cp > 1) {
-        int r = 0;
-        for (int o = 0; o < S; ++o) {
-          const int co = L[o].count;
-          r += (co > 1) && (co > cp || (co == cp && L[o].seq > sp));
-        }
-        s.rankP[p] = r;
-        s.P[r] = p;
-        OT_ATOMIC_ADD(&s.vars[OT_V_NP], 1);
-      } else {
-        s.rankP[p] = -1;
-      }
-    }
-    OT_SYNC();
-  }
-  return s.vars[OT_V_NP];
+  return S + C - (np > 0 ? jstop + 1 : 0);
 }
 
 // Full culling of one (frame, level).  keys[M] in vToDistributeKeys order; knode[M] scratch.
-// Writes selected keys to out[] in final list order; returns their count (<= cap).
+// Writes selected keys to out[] in final list order; returns their count.
 OT_DEV int ot_distribute(const uint32_t* keys, uint16_t* knode, int M, const OtRoots& roots, int N,
                          OtScratch& s, uint32_t* out) {
   // roots (:546-586): key -> root by float division, empty roots dropped
@@ -274,9 +289,12 @@ OT_DEV int ot_distribute(const uint32_t* keys, uint16_t* knode, int M, const OtR
   OT_SYNC();
   OT_FOR(i, nIni) s.c[i] = s.a[i] > 0;
   OT_SYNC();
-  ot_exclusive_scan(s.c, s.newpos, nIni, &s.vars[OT_V_S], s.part);
-  int cur = 0;
+  ot_exclusive_scan(s.c, s.d, nIni, &s.vars[OT_V_S], s.part);
+  int lst = 0, cur = 0;
+  // Non-empty root i gets slot == list position d[i].  The keys still carry the root index; they
+  // are re-labelled by the first key pass through a pseudo round "-1" stored in split[1]/child[1].
   OT_FOR(i, nIni) {
+    s.split[1][i] = s.c[i] ? i : -1;
     if (s.c[i]) {
       OtNode nd;
       nd.ulx = (short)roots.root_x[i];
@@ -285,40 +303,45 @@ OT_DEV int ot_distribute(const uint32_t* keys, uint16_t* knode, int M, const OtR
       nd.bry = (short)roots.height;
       nd.count = s.a[i];
       nd.seq = i;
-      s.nodes[0][s.newpos[i]] = nd;
+      s.nodes[s.d[i]] = nd;
+      s.order[0][s.d[i]] = s.d[i];
+      s.child[1][4 * i] = s.d[i];
     }
   }
-  OT_SYNC();
-  OT_FOR(k, M) knode[k] = (uint16_t)s.newpos[knode[k]];
   OT_SYNC();
   int S = s.vars[OT_V_S];
 
   // policy replay (:598-741)
+  int prev = 1, jstop_prev = nIni;
+  int phase2 = 0;
   bool finish = false;
   while (!finish) {
-    const int prev = S;
-    int np = ot_build_P(s, cur, S, 0);
-    S = ot_round(keys, knode, M, s, &cur, S, np, -1);
-    // nToExpand = children with >1 key = all nodes with >1 key after a full pass
-    OT_FOR(p, S) s.a[p] = s.nodes[cur][p].count > 1;
-    OT_SYNC();
-    ot_exclusive_scan(s.a, s.b, S, &s.vars[OT_V_TOTAL], s.part);
-    const int nToExpand = s.vars[OT_V_TOTAL];
-    OT_SYNC();
-    if (S >= N || S == prev) {
+    const int before = S;
+    const int np = ot_build_P(s, cur, lst, S, phase2);
+    ot_key_pass(keys, knode, M, s, prev, jstop_prev, cur);
+    int jstop = -1;
+    S = ot_commit_round(s, cur, lst, S, np, phase2 ? N : -1, &jstop);
+    lst ^= 1;
+    prev = cur;
+    jstop_prev = jstop;
+    cur ^= 1;
+    if (S >= N || S == before) {
       finish = true;
-    } else if (S + nToExpand * 3 > N) {
-      while (!finish) {
-        const int prev2 = S;
-        np = ot_build_P(s, cur, S, 1);
-        S = ot_round(keys, knode, M, s, &cur, S, np, N);
-        if (S >= N || S == prev2) finish = true;
-      }
+    } else if (!phase2) {
+      // nToExpand = children with >1 key = all nodes with >1 key after a full pass (:670-676)
+      OT_FOR(p, S) s.a[p] = s.nodes[s.order[lst][p]].count > 1;
+      OT_SYNC();
+      ot_exclusive_scan(s.a, s.b, S, &s.vars[OT_V_TOTAL], s.part);
+      const int nToExpand = s.vars[OT_V_TOTAL];
+      OT_SYNC();
+      if (S + nToExpand * 3 > N) phase2 = 1;
     }
   }
+  // move the keys of the last round's split nodes into their children
+  ot_key_pass(keys, knode, M, s, prev, jstop_prev, -1);
 
   // retain the best key per node (:745-761): max response, earliest key on ties
-  OT_FOR(p, S) s.best[p] = 0ull;
+  OT_FOR(p, S) s.best[s.order[lst][p]] = 0ull;
   OT_SYNC();
   OT_FOR(k, M) {
     const unsigned long long v =
@@ -326,7 +349,7 @@ OT_DEV int ot_distribute(const uint32_t* keys, uint16_t* knode, int M, const OtR
     OT_ATOMIC_MAX64(&s.best[knode[k] & OT_POS_MASK], v);
   }
   OT_SYNC();
-  OT_FOR(p, S) out[p] = keys[0xFFFFFFFFu - (uint32_t)(s.best[p] & 0xFFFFFFFFull)];
+  OT_FOR(p, S) out[p] = keys[0xFFFFFFFFu - (uint32_t)(s.best[s.order[lst][p]] & 0xFFFFFFFFull)];
   OT_SYNC();
   return S;
 }

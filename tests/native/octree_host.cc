@@ -17,14 +17,18 @@ extern "C" int octree_host_distribute(const int* x, const int* y, const int* sco
   for (int i = 0; i <= roots.n_ini; ++i) roots.root_x[i] = (int)(roots.hx * (float)i);
   roots.height = H;
   int cap = (N + 3 > 4 * roots.n_ini ? N + 3 : 4 * roots.n_ini) + 1;
-  std::vector<OtNode> n0(cap), n1(cap);
-  std::vector<int> P(cap), rankP(cap), cnt4(4 * cap), a(cap + 1), b(cap + 1), c(cap + 1), newpos(cap),
-      childpos(4 * cap), part(OT_NTHREADS + 1), vars(8);
+  std::vector<OtNode> nodes(cap);
+  std::vector<int> o0(cap), o1(cap), P(cap), sp0(cap), sp1(cap), c40(4 * cap), c41(4 * cap), ch0(4 * cap), ch1(4 * cap),
+      a(cap + 1), b(cap + 1), c(cap + 1), d(cap + 1), part(OT_NTHREADS + 1), vars(8);
   std::vector<unsigned long long> best(cap);
   OtScratch s;
-  s.nodes[0] = n0.data(); s.nodes[1] = n1.data();
-  s.P = P.data(); s.rankP = rankP.data(); s.cnt4 = cnt4.data();
-  s.a = a.data(); s.b = b.data(); s.c = c.data(); s.newpos = newpos.data(); s.childpos = childpos.data();
+  s.nodes = nodes.data();
+  s.order[0] = o0.data(); s.order[1] = o1.data();
+  s.P = P.data();
+  s.split[0] = sp0.data(); s.split[1] = sp1.data();
+  s.cnt4[0] = c40.data(); s.cnt4[1] = c41.data();
+  s.child[0] = ch0.data(); s.child[1] = ch1.data();
+  s.a = a.data(); s.b = b.data(); s.c = c.data(); s.d = d.data();
   s.part = part.data(); s.best = best.data(); s.vars = vars.data();
   std::vector<uint32_t> keys(M), out(cap);
   std::vector<uint16_t> knode(M);
