@@ -323,51 +323,45 @@ __global__ void __launch_bounds__(256) k_octree(const OrbGeom* __restrict__ g, c
                                                 const int* __restrict__ cell_count, uint32_t* __restrict__ keys,
                                                 uint16_t* __restrict__ knode, uint32_t* __restrict__ sel,
                                                 int* __restrict__ sel_count, int smem_keys) {
-  extern __shared__ __align__(16) unsigned char smem[];
   const int level = blockIdx.x, frame = blockIdx.y;
   const OrbLevelGeom& L = g->lv[level];
-  const int cap = g->ot_cap, scap = g->ot_scan_cap;
   OtScratch s;
-  unsigned char* p = smem;
-  s.best = reinterpret_cast<unsigned long long*>(p); p += sizeof(unsigned long long) * cap;
-  s.nodes = reinterpret_cast<OtNode*>(p); p += sizeof(OtNode) * cap;
-  for (int i = 0; i < 2; ++i) { s.cnt4[i] = reinterpret_cast<int*>(p); p += sizeof(int) * 4 * cap; }
-  for (int i = 0; i < 2; ++i) { s.child[i] = reinterpret_cast<int*>(p); p += sizeof(int) * 4 * cap; }
-  for (int i = 0; i < 2; ++i) { s.order[i] = reinterpret_cast<int*>(p); p += sizeof(int) * cap; }
-  for (int i = 0; i < 2; ++i) { s.split[i] = reinterpret_cast<int*>(p); p += sizeof(int) * cap; }
-  s.P = reinterpret_cast<int*>(p); p += sizeof(int) * cap;
-  s.a = reinterpret_cast<int*>(p); p += sizeof(int) * scap;
-  s.b = reinterpret_cast<int*>(p); p += sizeof(int) * scap;
-  s.c = reinterpret_cast<int*>(p); p += sizeof(int) * scap;
-  s.d = reinterpret_cast<int*>(p); p += sizeof(int) * scap;
-  s.part = reinterpret_cast<int*>(p); p += sizeof(int) * (256 + 1);
-  s.vars = reinterpret_cast<int*>(p); p += sizeof(int) * 8;
-  p += (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
-  uint32_t* skeys = reinterpret_cast<uint32_t*>(p);
-  uint16_t* sknode = reinterpret_cast<uint16_t*>(skeys + smem_keys);
+  const int scratch_bytes = ot_layout(s, g->ot_cap, g->ot_scan_cap, 256);
+  int* sa = OT_INTS(s, s.a);
+  int* sb = OT_INTS(s, s.b);
+  int* vars = OT_INTS(s, s.vars);
 
   // gather this level's candidates in vToDistributeKeys order: cells row-major, in-cell order
   const int* cc = cell_count + (size_t)frame * g->n_cells + L.cell_base;
-  OT_FOR(i, L.n_cells) s.a[i] = cc[i];
+  OT_FOR(i, L.n_cells) sa[i] = cc[i];
   OT_SYNC();
-  ot_exclusive_scan(s.a, s.b, L.n_cells, &s.vars[OT_V_TOTAL], s.part);
-  const int M = s.vars[OT_V_TOTAL];
+  ot_exclusive_scan(sa, sb, L.n_cells, &vars[OT_V_TOTAL], OT_INTS(s, s.part));
+  const int M = vars[OT_V_TOTAL];
   const uint32_t* cslots = cand + (size_t)frame * g->cand_frame_u32 + L.cand_off;
-  // the policy replay re-labels every key once per round: keep keys and labels in shared memory
-  // whenever the level's candidates fit (they do for camera-like frames), else in the HBM workspace
-  const bool in_smem = M <= smem_keys;
-  uint32_t* fkeys = in_smem ? skeys : keys + (size_t)frame * g->key_frame_u32 + L.key_off;
-  uint16_t* fknode = in_smem ? sknode : knode + (size_t)frame * g->key_frame_u32 + L.key_off;
-  {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (int c = warp; c < L.n_cells; c += nwarp) {
-      const int n = s.a[c], off = s.b[c];
-      for (int k = lane; k < n; k += 32) fkeys[off + k] = cslots[(size_t)c * L.cand_cap + k];
-    }
-  }
-  __syncthreads();
   uint32_t* out = sel + (size_t)frame * g->kp_cap_frame + L.sel_off;
-  const int n = ot_distribute(fkeys, fknode, M, L.roots, L.quota, s, out);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int n;
+  // The policy replay re-labels every key once per round: keys and labels stay in shared memory
+  // whenever the level's candidates fit (camera-like frames), else in the HBM workspace.
+  if (M <= smem_keys) {
+    uint32_t* skeys = reinterpret_cast<uint32_t*>(ot_smem + scratch_bytes);
+    uint16_t* sknode = reinterpret_cast<uint16_t*>(ot_smem + scratch_bytes + 4 * smem_keys);
+    for (int c = warp; c < L.n_cells; c += 8) {
+      const int cn = sa[c], off = sb[c];
+      for (int k = lane; k < cn; k += 32) skeys[off + k] = cslots[(size_t)c * L.cand_cap + k];
+    }
+    __syncthreads();
+    n = ot_distribute(skeys, sknode, M, L.roots, L.quota, s, out);
+  } else {
+    uint32_t* fkeys = keys + (size_t)frame * g->key_frame_u32 + L.key_off;
+    uint16_t* fknode = knode + (size_t)frame * g->key_frame_u32 + L.key_off;
+    for (int c = warp; c < L.n_cells; c += 8) {
+      const int cn = sa[c], off = sb[c];
+      for (int k = lane; k < cn; k += 32) fkeys[off + k] = cslots[(size_t)c * L.cand_cap + k];
+    }
+    __syncthreads();
+    n = ot_distribute(fkeys, fknode, M, L.roots, L.quota, s, out);
+  }
   if (threadIdx.x == 0) sel_count[frame * g->nlevels + level] = n;
 }
 
@@ -632,9 +626,8 @@ int octree_smem_keys(const OrbGeom& g) {
 }
 
 size_t octree_smem_bytes(const OrbGeom& g) {
-  const size_t cap = g.ot_cap, scap = g.ot_scan_cap;
-  return sizeof(unsigned long long) * cap + sizeof(OtNode) * cap + sizeof(int) * (16 * cap + 5 * cap) +
-         sizeof(int) * 4 * scap + sizeof(int) * 257 + sizeof(int) * 8 + 16 + (size_t)octree_smem_keys(g) * 6;
+  OtScratch s;
+  return (size_t)ot_layout(s, g.ot_cap, g.ot_scan_cap, 256) + (size_t)octree_smem_keys(g) * 6;
 }
 
 // The opt-in limit is a property of the FUNCTION (per device), shared by every handle: only ever

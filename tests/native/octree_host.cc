@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <vector>
+struct int4 { int x, y, z, w; };
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 
 #include "../../multi_orb_slam_b200/csrc/octree_core.h"
 
@@ -17,19 +19,10 @@ extern "C" int octree_host_distribute(const int* x, const int* y, const int* sco
   for (int i = 0; i <= roots.n_ini; ++i) roots.root_x[i] = (int)(roots.hx * (float)i);
   roots.height = H;
   int cap = (N + 3 > 4 * roots.n_ini ? N + 3 : 4 * roots.n_ini) + 1;
-  std::vector<OtNode> nodes(cap);
-  std::vector<int> o0(cap), o1(cap), P(cap), sp0(cap), sp1(cap), c40(4 * cap), c41(4 * cap), ch0(4 * cap), ch1(4 * cap),
-      a(cap + 1), b(cap + 1), c(cap + 1), d(cap + 1), part(OT_NTHREADS + 1), vars(8);
-  std::vector<unsigned long long> best(cap);
   OtScratch s;
-  s.nodes = nodes.data();
-  s.order[0] = o0.data(); s.order[1] = o1.data();
-  s.P = P.data();
-  s.split[0] = sp0.data(); s.split[1] = sp1.data();
-  s.cnt4[0] = c40.data(); s.cnt4[1] = c41.data();
-  s.child[0] = ch0.data(); s.child[1] = ch1.data();
-  s.a = a.data(); s.b = b.data(); s.c = c.data(); s.d = d.data();
-  s.part = part.data(); s.best = best.data(); s.vars = vars.data();
+  const int bytes = ot_layout(s, cap, cap + 1, OT_NTHREADS);
+  std::vector<unsigned long long> arena(bytes / 8 + 2);
+  s.host_base = reinterpret_cast<unsigned char*>(arena.data());
   std::vector<uint32_t> keys(M), out(cap);
   std::vector<uint16_t> knode(M);
   for (int i = 0; i < M; ++i) keys[i] = (uint32_t)x[i] | (uint32_t)y[i] << 12 | (uint32_t)score[i] << 24;
