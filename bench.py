@@ -58,15 +58,9 @@ def stage_bytes_per_frame(w, h, k):
 
 
 def make_sequences(n_rig, seed0):
-    """Two camera streams of n_rig frames: frame t+1 = frame t shifted by an integer offset plus noise."""
-    from multi_orb_slam_b200.synth import shifted_noisy, textured
-    cams = []
-    for c in range(2):
-        frames = [textured(W, H, seed0 + c)]
-        for t in range(1, n_rig):
-            frames.append(shifted_noisy(frames[-1], 1000 + 7919 * (seed0 + c) + t))
-        cams.append(np.stack(frames))
-    return cams
+    """Two camera streams of n_rig frames each (moving clean scene + fresh sensor noise per frame)."""
+    from multi_orb_slam_b200.synth import camera_sequence
+    return [camera_sequence(W, H, n_rig, seed0 + c) for c in range(2)]
 
 
 class ClockSampler:

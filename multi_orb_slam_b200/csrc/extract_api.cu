@@ -12,6 +12,10 @@
 #include "../../include/orb_b200.h"
 #include "extract_kernels.h"
 
+#ifdef ORB_OT_TIMING
+namespace orbk { void dump_octree_marks(); }
+#endif
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -365,6 +369,9 @@ int orbx_create(const orbx_config* cfg, orbx_extractor** out) {
 
 void orbx_destroy(orbx_extractor* h) {
   if (!h) return;
+#ifdef ORB_OT_TIMING
+  orbk::dump_octree_marks();
+#endif
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->gh.d_geom); cudaFree(h->gh.d_cells); cudaFree(h->gh.d_xtab); cudaFree(h->gh.d_ytab);
   cudaFree(h->d_pyr); cudaFree(h->d_blur); cudaFree(h->d_cand); cudaFree(h->d_cell_count);

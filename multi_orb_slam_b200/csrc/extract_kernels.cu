@@ -10,7 +10,13 @@
 // frame) so the small per-frame work fills the 148 SMs.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
+#ifdef ORB_OT_TIMING  // dev-only: clock64 marks inside the octree kernel (block 0), dumped by orbk::dump_octree_marks
+__device__ long long g_ot_marks[2 * 4096];
+__device__ int g_ot_nmarks;
+#define OT_MARK(id) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && g_ot_nmarks < 4096) { g_ot_marks[2 * g_ot_nmarks] = (id); g_ot_marks[2 * g_ot_nmarks + 1] = clock64(); ++g_ot_nmarks; } } while (0)
+#endif
 #include "extract_kernels.h"
 #include "orb_pattern.h"
 
@@ -319,6 +325,24 @@ __global__ void __launch_bounds__(128) k_fast_cells(const OrbGeom* __restrict__ 
 
 // ------------------------------------------------------------------------------------------
 // K4 DistributeOctTree: one CTA per (level, frame); policy core in octree_core.h.
+// Gather of the per-cell candidate slots into one key array: a thread per cell, eight loads in
+// flight per thread (the slots sit in HBM: a load -> store loop would serialise the latency).
+__device__ __forceinline__ void gather_cells(const uint32_t* __restrict__ cslots, int cand_cap, int n_cells,
+                                             const int* cnt, const int* off, uint32_t* dst) {
+  for (int c = threadIdx.x; c < n_cells; c += blockDim.x) {
+    const int cn = cnt[c], o = off[c];
+    const uint32_t* src = cslots + (size_t)c * cand_cap;
+    for (int k = 0; k < cn; k += 8) {
+      uint32_t r[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) r[u] = (k + u < cn) ? __ldg(src + k + u) : 0u;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (k + u < cn) dst[o + k + u] = r[u];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) k_octree(const OrbGeom* __restrict__ g, const uint32_t* __restrict__ cand,
                                                 const int* __restrict__ cell_count, uint32_t* __restrict__ keys,
                                                 uint16_t* __restrict__ knode, uint32_t* __restrict__ sel,
@@ -330,6 +354,7 @@ __global__ void __launch_bounds__(256) k_octree(const OrbGeom* __restrict__ g, c
   int* sa = OT_INTS(s, s.a);
   int* sb = OT_INTS(s, s.b);
   int* vars = OT_INTS(s, s.vars);
+  OT_MARK(20);
 
   // gather this level's candidates in vToDistributeKeys order: cells row-major, in-cell order
   const int* cc = cell_count + (size_t)frame * g->n_cells + L.cell_base;
@@ -337,32 +362,28 @@ __global__ void __launch_bounds__(256) k_octree(const OrbGeom* __restrict__ g, c
   OT_SYNC();
   ot_exclusive_scan(sa, sb, L.n_cells, &vars[OT_V_TOTAL], OT_INTS(s, s.part));
   const int M = vars[OT_V_TOTAL];
+  OT_MARK(21);
   const uint32_t* cslots = cand + (size_t)frame * g->cand_frame_u32 + L.cand_off;
   uint32_t* out = sel + (size_t)frame * g->kp_cap_frame + L.sel_off;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int n;
   // The policy replay re-labels every key once per round: keys and labels stay in shared memory
   // whenever the level's candidates fit (camera-like frames), else in the HBM workspace.
   if (M <= smem_keys) {
     uint32_t* skeys = reinterpret_cast<uint32_t*>(ot_smem + scratch_bytes);
     uint16_t* sknode = reinterpret_cast<uint16_t*>(ot_smem + scratch_bytes + 4 * smem_keys);
-    for (int c = warp; c < L.n_cells; c += 8) {
-      const int cn = sa[c], off = sb[c];
-      for (int k = lane; k < cn; k += 32) skeys[off + k] = cslots[(size_t)c * L.cand_cap + k];
-    }
+    gather_cells(cslots, L.cand_cap, L.n_cells, sa, sb, skeys);
     __syncthreads();
+    OT_MARK(22);
     n = ot_distribute(skeys, sknode, M, L.roots, L.quota, s, out);
   } else {
     uint32_t* fkeys = keys + (size_t)frame * g->key_frame_u32 + L.key_off;
     uint16_t* fknode = knode + (size_t)frame * g->key_frame_u32 + L.key_off;
-    for (int c = warp; c < L.n_cells; c += 8) {
-      const int cn = sa[c], off = sb[c];
-      for (int k = lane; k < cn; k += 32) fkeys[off + k] = cslots[(size_t)c * L.cand_cap + k];
-    }
+    gather_cells(cslots, L.cand_cap, L.n_cells, sa, sb, fkeys);
     __syncthreads();
     n = ot_distribute(fkeys, fknode, M, L.roots, L.quota, s, out);
   }
   if (threadIdx.x == 0) sel_count[frame * g->nlevels + level] = n;
+  OT_MARK(23);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -663,6 +684,29 @@ void launch_octree(const OrbGeomHost& gh, int n_frames, const uint32_t* d_cand, 
                                                                                 d_knode, d_sel, d_sel_count, octree_smem_keys(gh.g));
   ++*launches;
 }
+
+#ifdef ORB_OT_TIMING
+void dump_octree_marks() {
+  int nm = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&nm, g_ot_nmarks, 4);
+  static long long marks[2 * 4096];
+  cudaMemcpyFromSymbol(marks, g_ot_marks, sizeof(long long) * 2 * nm);
+  long long agg[128] = {0};
+  int cnt[128] = {0};
+  for (int i = 1; i < nm; ++i) {
+    const int id = (int)marks[2 * i];
+    if (id == 20) continue;  // new launch
+    agg[id] += marks[2 * i + 1] - marks[2 * i - 1];
+    cnt[id]++;
+  }
+  printf("octree marks: %d\n", nm);
+  for (int id = 0; id < 128; ++id)
+    if (cnt[id]) printf("  phase ending at mark %3d: %4d times, %9lld cycles total, %7lld avg\n", id, cnt[id], agg[id], agg[id] / cnt[id]);
+  const int zero = 0;
+  cudaMemcpyToSymbol(g_ot_nmarks, &zero, 4);
+}
+#endif
 
 void launch_blur(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, uint8_t* d_blur, cudaStream_t st,
                  long long* launches) {

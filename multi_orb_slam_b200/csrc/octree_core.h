@@ -36,6 +36,7 @@
 #define OT_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define OT_ATOMIC_MIN(p, v) atomicMin((p), (v))
 #define OT_ATOMIC_MAX64(p, v) atomicMax((p), (v))
+#define OT_ATOMIC_MAX32(p, v) atomicMax((p), (v))
 #define OT_FDIV(a, b) __fdiv_rn((a), (b))
 extern __shared__ __align__(16) unsigned char ot_smem[];  // aliases the kernel's dynamic shared memory
 #define OT_BASE(s) ot_smem
@@ -49,10 +50,14 @@ extern __shared__ __align__(16) unsigned char ot_smem[];  // aliases the kernel'
 #define OT_ATOMIC_ADD(p, v) (*(p) += (v))
 #define OT_ATOMIC_MIN(p, v) (*(p) = (*(p) < (v) ? *(p) : (v)))
 #define OT_ATOMIC_MAX64(p, v) (*(p) = (*(p) > (v) ? *(p) : (v)))
+#define OT_ATOMIC_MAX32(p, v) (*(p) = (*(p) > (v) ? *(p) : (v)))
 #define OT_FDIV(a, b) ((a) / (b))
 #define OT_BASE(s) ((s).host_base)
 #endif
 #define OT_INTS(s, off) (reinterpret_cast<int*>(OT_BASE(s) + (off)))
+#ifndef OT_MARK
+#define OT_MARK(id) ((void)0)  /* dev timing hook, see tools/dev/octree_bench.cu */
+#endif
 
 #define OT_MAX_ROOTS 16
 #define OT_POS_MASK 0x3FFFu
@@ -216,22 +221,42 @@ OT_DEV void ot_key_pass(const uint32_t* keys, uint16_t* knode, int M, const OtSc
   const OtNode* nodes = reinterpret_cast<const OtNode*>(OT_BASE(s) + s.nodes);
   const int* mv = OT_INTS(s, s.mv);
   int* cnt4 = OT_INTS(s, s.cnt4);
-  OT_FOR(k, M) {
-    const unsigned v = knode[k];
-    const int slot = mv[4 * (int)(v & OT_POS_MASK) + (int)(v >> 14)];
-    unsigned nv = (unsigned)slot;
+  // four keys per thread and iteration: the dependent chain label -> mv -> node is issued for all
+  // four before the first atomic, so the shared-memory latencies overlap
+  const int T = OT_NTHREADS;
+#ifdef __CUDACC__
+  for (int k0 = threadIdx.x; k0 < M; k0 += 4 * T) {
+#else
+  for (int k0 = 0; k0 < M; k0 = (k0 % T == T - 1) ? k0 + 3 * T + 1 : k0 + 1) {
+#endif
+    unsigned v[4];
+    int slot[4];
+    OtNode nd[4];
+    uint32_t key[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = (k0 + u * T < M) ? knode[k0 + u * T] : 0u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) slot[u] = mv[4 * (int)(v[u] & OT_POS_MASK) + (int)(v[u] >> 14)];
     if (count_next) {
-      const OtNode nd = nodes[slot];
-      if (nd.count > 1) {
-        const int mx = nd.ulx + ((nd.brx - nd.ulx + 1) >> 1);  // UL.x + ceil(w/2)
-        const int my = nd.uly + ((nd.bry - nd.uly + 1) >> 1);
-        const uint32_t key = keys[k];
-        const int q = (OT_KEY_X(key) < mx ? 0 : 1) + (OT_KEY_Y(key) < my ? 0 : 2);
-        OT_ATOMIC_ADD(&cnt4[4 * slot + q], 1);
-        nv |= (unsigned)q << 14;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        nd[u] = nodes[slot[u]];
+        key[u] = (k0 + u * T < M) ? keys[k0 + u * T] : 0u;
       }
     }
-    knode[k] = (uint16_t)nv;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (k0 + u * T >= M) continue;
+      unsigned nv = (unsigned)slot[u];
+      if (count_next && nd[u].count > 1) {
+        const int mx = nd[u].ulx + ((nd[u].brx - nd[u].ulx + 1) >> 1);  // UL.x + ceil(w/2)
+        const int my = nd[u].uly + ((nd[u].bry - nd[u].uly + 1) >> 1);
+        const int q = (OT_KEY_X(key[u]) < mx ? 0 : 1) + (OT_KEY_Y(key[u]) < my ? 0 : 2);
+        OT_ATOMIC_ADD(&cnt4[4 * slot[u] + q], 1);
+        nv |= (unsigned)q << 14;
+      }
+      knode[k0 + u * T] = (uint16_t)nv;
+    }
   }
   OT_SYNC();
 }
@@ -366,6 +391,7 @@ OT_DEV int ot_distribute(const uint32_t* keys, uint16_t* knode, int M, const OtR
   }
   OT_SYNC();
   int S = vars[OT_V_S];
+  OT_MARK(10);
 
   // policy replay (:598-741)
   int lst = 0, phase2 = 0;
@@ -374,9 +400,13 @@ OT_DEV int ot_distribute(const uint32_t* keys, uint16_t* knode, int M, const OtR
     const int before = S;
     int* L = lst ? order1 : order0;
     int* Lnew = lst ? order0 : order1;
+    OT_MARK(1);
     const int np = ot_build_P(s, L, S, phase2);
+    OT_MARK(phase2 ? 3 : 2);
     ot_key_pass(keys, knode, M, s, 1);
+    OT_MARK(4);
     S = ot_commit_round(s, L, Lnew, S, np, phase2 ? N : -1);
+    OT_MARK(5);
     lst ^= 1;
     if (S >= N || S == before) {
       finish = true;
@@ -391,19 +421,36 @@ OT_DEV int ot_distribute(const uint32_t* keys, uint16_t* knode, int M, const OtR
     }
   }
   const int* Lf = lst ? order1 : order0;
+  OT_MARK(6);
   // move the keys of the last round's split nodes into their children
   ot_key_pass(keys, knode, M, s, 0);
+  OT_MARK(7);
 
-  // retain the best key per node (:745-761): max response, earliest key on ties
-  OT_FOR(p, S) best[Lf[p]] = 0ull;
-  OT_SYNC();
-  OT_FOR(k, M) {
-    const unsigned long long v =
-        ((unsigned long long)(OT_KEY_SCORE(keys[k]) + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)k);
-    OT_ATOMIC_MAX64(&best[knode[k] & OT_POS_MASK], v);
+  // retain the best key per node (:745-761): max response, earliest key on ties.  Packed
+  // (score+1, ~index) arg-max: one native 32-bit shared atomic when the index fits 16 bits.
+  if (M <= 0xFFFF) {
+    unsigned* best32 = reinterpret_cast<unsigned*>(best);
+    OT_FOR(p, S) best32[Lf[p]] = 0u;
+    OT_SYNC();
+    OT_FOR(k, M) {
+      const unsigned v = ((unsigned)(OT_KEY_SCORE(keys[k]) + 1) << 16) | (0xFFFFu - (unsigned)k);
+      OT_ATOMIC_MAX32(&best32[knode[k] & OT_POS_MASK], v);
+    }
+    OT_SYNC();
+    OT_MARK(8);
+    OT_FOR(p, S) out[p] = keys[0xFFFFu - (best32[Lf[p]] & 0xFFFFu)];
+  } else {
+    OT_FOR(p, S) best[Lf[p]] = 0ull;
+    OT_SYNC();
+    OT_FOR(k, M) {
+      const unsigned long long v =
+          ((unsigned long long)(OT_KEY_SCORE(keys[k]) + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)k);
+      OT_ATOMIC_MAX64(&best[knode[k] & OT_POS_MASK], v);
+    }
+    OT_SYNC();
+    OT_MARK(8);
+    OT_FOR(p, S) out[p] = keys[0xFFFFFFFFu - (uint32_t)(best[Lf[p]] & 0xFFFFFFFFull)];
   }
-  OT_SYNC();
-  OT_FOR(p, S) out[p] = keys[0xFFFFFFFFu - (uint32_t)(best[Lf[p]] & 0xFFFFFFFFull)];
   OT_SYNC();
   return S;
 }

@@ -66,6 +66,22 @@ def shifted_noisy(img: np.ndarray, seed: int, max_shift: int = 8, sigma: float =
     return np.clip(np.rint(out), 0, 255).astype(np.uint8)
 
 
+def camera_sequence(width: int, height: int, n_frames: int, seed: int, max_shift: int = 8, sigma: float = 2.0):
+    """n_frames of one synthetic camera stream (config 2): the clean scene moves by an integer
+    offset in [-max_shift, max_shift]^2 per frame (wrapping around, so the texture statistics
+    stay stationary over long sequences) and every frame carries FRESH N(0, sigma) sensor noise
+    (noise does not accumulate from frame to frame)."""
+    rng = np.random.default_rng(100003 * seed + 17)
+    clean = textured(width, height, seed)
+    frames = []
+    for _ in range(n_frames):
+        noisy = clean.astype(np.float32) + rng.normal(0.0, sigma, size=clean.shape).astype(np.float32)
+        frames.append(np.clip(np.rint(noisy), 0, 255).astype(np.uint8))
+        dx, dy = (int(v) for v in rng.integers(-max_shift, max_shift + 1, size=2))
+        clean = np.roll(clean, (dy, dx), axis=(0, 1))
+    return np.stack(frames)
+
+
 def random_descriptors(n: int, seed: int) -> np.ndarray:
     """n x 32 bytes of i.i.d. bits (config 3, set A)."""
     return np.random.default_rng(seed).integers(0, 256, size=(n, 32), dtype=np.uint8)
