@@ -390,68 +390,60 @@ __global__ void __launch_bounds__(256) k_octree(const OrbGeom* __restrict__ g, c
 // K6 GaussianBlur 7x7 sigma 2, OpenCV 4.x fixed-point path: taps {18,34,48,56,48,34,18}/256 per
 // pass, H pass u8 -> 8.8 (16 bit), V pass -> 16.16, (v + 32768) >> 16.  Reads the bordered
 // pyramid level: its REFLECT_101 border supplies exactly the blur's own border pixels.
-// Tile = 128 x 16 outputs per CTA; H pass with dp4a on packed bytes.
-#define BLUR_IN_PITCH 144
-__global__ void __launch_bounds__(256) k_blur(const OrbGeom* __restrict__ g, const uint8_t* __restrict__ pyr,
+// One WARP per 128 x 32 output tile, no shared memory, no barriers: a lane owns four adjacent
+// columns and walks down the rows; the H pass of each new row (dp4a on packed bytes) enters a
+// 7-row register window from which the V pass is taken.  Rows are fully unrolled so the window
+// rotation is register renaming.
+__global__ void __launch_bounds__(128) k_blur(const OrbGeom* __restrict__ g, const uint8_t* __restrict__ pyr,
                                               uint8_t* __restrict__ blur) {
-  __shared__ __align__(16) uint8_t s_in[(ORB_BLUR_TH + 6) * BLUR_IN_PITCH];
-  __shared__ __align__(16) uint16_t s_h[(ORB_BLUR_TH + 6) * ORB_BLUR_TW];
+  const int tile = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (tile >= g->n_blur_tiles) return;
+  const int lane = threadIdx.x & 31;
   int level = 0;
-  while (level + 1 < g->nlevels && (int)blockIdx.x >= g->lv[level + 1].blur_tile_base) ++level;
+  while (level + 1 < g->nlevels && tile >= g->lv[level + 1].blur_tile_base) ++level;
   const OrbLevelGeom& L = g->lv[level];
-  const int t = blockIdx.x - L.blur_tile_base;
+  const int t = tile - L.blur_tile_base;
   const int ty = t / L.blur_tiles_x, tx = t - ty * L.blur_tiles_x;
-  const int x0 = tx * ORB_BLUR_TW, y0 = ty * ORB_BLUR_TH;
-  const int frame = blockIdx.y, tid = threadIdx.x;
-  const uint8_t* src = pyr + (size_t)frame * g->pyr_frame_bytes + L.pyr_off;  // bordered origin
-  // stage rows y0-3 .. y0+TH+2, cols x0-4 .. x0+TW+3 (word aligned: bordered col = x + 19)
-  // bordered col of (x0-4) is x0+15; stage from bordered col x0+12 (multiple of 4) for aligned loads
-  const int bx0 = x0 + 12;                       // bordered x of smem col 0  (image x = x0 - 7)
-  const int bwords = L.pitch >> 2;
-  for (int i = tid; i < (ORB_BLUR_TH + 6) * (BLUR_IN_PITCH / 4); i += 256) {
-    const int r = i / (BLUR_IN_PITCH / 4), wq = i - r * (BLUR_IN_PITCH / 4);
-    int by = y0 - 3 + r + ORB_EDGE;
-    by = min(by, L.h + 2 * ORB_EDGE - 1);
-    const int bw = min((bx0 >> 2) + wq, bwords - 1);
-    reinterpret_cast<uint32_t*>(s_in + r * BLUR_IN_PITCH)[wq] =
-        __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)by * L.pitch) + bw);
-  }
-  __syncthreads();
-  // H pass: output x (0..127) of row r needs image cols x0+x-3 .. x0+x+3 = smem cols x+4 .. x+10
-  const uint32_t K0123 = 18u | 34u << 8 | 48u << 16 | 56u << 24, K456 = 48u | 34u << 8 | 18u << 16;
-  for (int i = tid; i < (ORB_BLUR_TH + 6) * (ORB_BLUR_TW / 4); i += 256) {
-    const int r = i / (ORB_BLUR_TW / 4), q = i - r * (ORB_BLUR_TW / 4);
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(s_in + r * BLUR_IN_PITCH) + q + 1;  // cols 4q+4..
-    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-    // window for output 4q+j starts at byte j of w0
-    const uint32_t a0 = w0, b0 = w1;
-    const uint32_t a1 = __byte_perm(w0, w1, 0x4321), b1 = __byte_perm(w1, w2, 0x4321);
-    const uint32_t a2 = __byte_perm(w0, w1, 0x5432), b2 = __byte_perm(w1, w2, 0x5432);
-    const uint32_t a3 = __byte_perm(w0, w1, 0x6543), b3 = __byte_perm(w1, w2, 0x6543);
-    const uint32_t h0 = __dp4a(a0, K0123, __dp4a(b0, K456, 0u));
-    const uint32_t h1 = __dp4a(a1, K0123, __dp4a(b1, K456, 0u));
-    const uint32_t h2 = __dp4a(a2, K0123, __dp4a(b2, K456, 0u));
-    const uint32_t h3 = __dp4a(a3, K0123, __dp4a(b3, K456, 0u));
-    reinterpret_cast<uint2*>(s_h + r * ORB_BLUR_TW)[q] = make_uint2(h0 | h1 << 16, h2 | h3 << 16);
-  }
-  __syncthreads();
+  const int x = tx * ORB_BLUR_TW + 4 * lane, y0 = ty * ORB_BLUR_TH;
+  const int frame = blockIdx.y;
+  const int pitch_w = L.pitch >> 2;
+  // image columns x-3 .. x+6 are bordered columns x+16 .. x+25: three aligned words from word (x+16)/4
+  const int w0 = min((x + 16) >> 2, pitch_w - 3);
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(pyr + (size_t)frame * g->pyr_frame_bytes + L.pyr_off) + w0;
   uint8_t* dst = blur + (size_t)frame * g->blur_frame_bytes + L.blur_off;
-  for (int i = tid; i < ORB_BLUR_TH * (ORB_BLUR_TW / 4); i += 256) {
-    const int r = i / (ORB_BLUR_TW / 4), q = i - r * (ORB_BLUR_TW / 4);
-    const int y = y0 + r, x = x0 + 4 * q;
-    if (y >= L.h || x >= L.bpitch) continue;
-    uint32_t acc0 = 32768u, acc1 = 32768u, acc2 = 32768u, acc3 = 32768u;
-    const uint32_t KT[7] = {18u, 34u, 48u, 56u, 48u, 34u, 18u};
+  const bool col_ok = x < L.bpitch;
+  const int last_row = L.h + 2 * ORB_EDGE - 1;
+  const uint32_t K0123 = 18u | 34u << 8 | 48u << 16 | 56u << 24, K456 = 48u | 34u << 8 | 18u << 16;
+  uint32_t win[7][4];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) {
-      const uint2 hv = reinterpret_cast<const uint2*>(s_h + (r + j) * ORB_BLUR_TW)[q];
-      acc0 += KT[j] * (hv.x & 0xffffu);
-      acc1 += KT[j] * (hv.x >> 16);
-      acc2 += KT[j] * (hv.y & 0xffffu);
-      acc3 += KT[j] * (hv.y >> 16);
+  for (int r = 0; r < ORB_BLUR_TH + 6; ++r) {
+    // H pass of image row y0 - 3 + r (bordered row + 19)
+    const int by = min(y0 - 3 + r + ORB_EDGE, last_row);
+    const uint32_t* row = src + (size_t)by * pitch_w;
+    const uint32_t a = __ldg(row), b = __ldg(row + 1), c = __ldg(row + 2);
+    uint32_t h[4];
+    h[0] = __dp4a(a, K0123, __dp4a(b, K456, 0u));
+    h[1] = __dp4a(__byte_perm(a, b, 0x4321), K0123, __dp4a(__byte_perm(b, c, 0x4321), K456, 0u));
+    h[2] = __dp4a(__byte_perm(a, b, 0x5432), K0123, __dp4a(__byte_perm(b, c, 0x5432), K456, 0u));
+    h[3] = __dp4a(__byte_perm(a, b, 0x6543), K0123, __dp4a(__byte_perm(b, c, 0x6543), K456, 0u));
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) win[j][i] = win[j + 1][i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) win[6][i] = h[i];
+    if (r >= 6) {
+      const int y = y0 + r - 6;
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t v = 18u * (win[0][i] + win[6][i]) + 34u * (win[1][i] + win[5][i]) +
+                           48u * (win[2][i] + win[4][i]) + 56u * win[3][i] + 32768u;
+        o[i] = v >> 16;
+      }
+      if (col_ok && y < L.h)
+        reinterpret_cast<uint32_t*>(dst + (size_t)y * L.bpitch)[x >> 2] = o[0] | o[1] << 8 | o[2] << 16 | o[3] << 24;
     }
-    reinterpret_cast<uint32_t*>(dst + (size_t)y * L.bpitch)[x >> 2] =
-        (acc0 >> 16) | (acc1 >> 16) << 8 | (acc2 >> 16) << 16 | (acc3 >> 16) << 24;
   }
 }
 
@@ -710,7 +702,7 @@ void dump_octree_marks() {
 
 void launch_blur(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, uint8_t* d_blur, cudaStream_t st,
                  long long* launches) {
-  k_blur<<<dim3(gh.g.n_blur_tiles, n_frames), 256, 0, st>>>(gh.d_geom, d_pyr, d_blur);
+  k_blur<<<dim3((gh.g.n_blur_tiles + 3) / 4, n_frames), 128, 0, st>>>(gh.d_geom, d_pyr, d_blur);
   ++*launches;
 }
 
