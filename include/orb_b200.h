@@ -144,6 +144,15 @@ int orbm_bruteforce_device(orbm_matcher* m, const uint8_t* d_q, int nq, const ui
 int orbm_bruteforce_host(orbm_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, float ratio,
                          int th_dist, int32_t* idx, int32_t* d1, int32_t* d2);
 
+/* The same scan for a batch of small independent pairs — cross-camera matching of a rig, the
+ * per-camera loops the reference runs over mDescriptors_total (src/ORBmatcher.cc:628,2030,2269).
+ * Pair p: query rows at d_q + p*q_stride bytes (d_nq[p] valid, <= cap), target rows at
+ * d_t + p*t_stride (d_nt[p] valid); results at [p*cap + i].  Strides are multiples of 16 bytes.
+ * Device pointers, asynchronous. */
+int orbm_bruteforce_batch_device(orbm_matcher* m, int n_pairs, int cap, const uint8_t* d_q, const int32_t* d_nq,
+                                 size_t q_stride, const uint8_t* d_t, const int32_t* d_nt, size_t t_stride, float ratio,
+                                 int th_dist, int32_t* d_idx, int32_t* d_d1, int32_t* d_d2);
+
 /* Frame grid bounds mnMinX/mnMaxX/mnMinY/mnMaxY (src/Frame.cc:262-278). */
 typedef struct {
   float min_x, max_x, min_y, max_y;

@@ -70,6 +70,7 @@ _SIGS = {
     "orbm_distance_pairs_host": (_i, [_vp, _vp, _vp, _i, _vp]),
     "orbm_bruteforce_device": (_i, [_vp, _vp, _i, _vp, _i, _f, _i, _vp, _vp, _vp]),
     "orbm_bruteforce_host": (_i, [_vp, _vp, _i, _vp, _i, _f, _i, _vp, _vp, _vp]),
+    "orbm_bruteforce_batch_device": (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp, _vp, _sz, _f, _i, _vp, _vp, _vp]),
     "orbm_search_for_initialization_device": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, Bounds, _vp, _i, _f, _i,
                                                   _vp, _vp]),
     "orbm_search_for_initialization_host": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, Bounds, _vp, _i, _f, _i,

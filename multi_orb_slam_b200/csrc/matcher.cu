@@ -120,6 +120,64 @@ __global__ void k_bf_merge(const uint2* __restrict__ partial, int nq, int nsplit
   out_idx[qi] = (idx >= 0 && best <= th_dist && (float)best < __fmul_rn((float)second, ratio)) ? idx : -1;
 }
 
+// Batched variant for many small independent pairs (cross-camera matching of a rig: one pair =
+// (camera c, camera c') of one rig-frame).  Pair p matches rows q + p*q_stride (nq[p] valid)
+// against rows t + p*t_stride (nt[p] valid); results are strided by `cap`.  One CTA per
+// (256-query tile, pair); all targets of the pair stream through shared memory, so no merge pass.
+__global__ void __launch_bounds__(BF_THREADS) k_bruteforce_batch(const uint8_t* __restrict__ q, const int32_t* __restrict__ nq_arr,
+                                                                 size_t q_stride, const uint8_t* __restrict__ t,
+                                                                 const int32_t* __restrict__ nt_arr, size_t t_stride, int cap,
+                                                                 float ratio, int th_dist, int32_t* __restrict__ out_idx,
+                                                                 int32_t* __restrict__ out_d1, int32_t* __restrict__ out_d2) {
+  __shared__ uint4 s_t[BF_TILE * 2];
+  const int pair = blockIdx.y, tid = threadIdx.x;
+  const int nq = min(nq_arr[pair], cap), nt = min(nt_arr[pair], cap);
+  if ((int)(blockIdx.x * BF_QPT * BF_THREADS) >= nq) return;
+  const uint8_t* qp = q + (size_t)pair * q_stride;
+  const uint8_t* tp = t + (size_t)pair * t_stride;
+  uint4 qa[BF_QPT], qb[BF_QPT];
+  uint32_t best[BF_QPT], second[BF_QPT];
+#pragma unroll
+  for (int r = 0; r < BF_QPT; ++r) {
+    const int qi = min((blockIdx.x * BF_QPT + r) * BF_THREADS + tid, nq - 1);
+    const uint4* p = reinterpret_cast<const uint4*>(qp + (size_t)qi * 32);
+    qa[r] = __ldg(p);
+    qb[r] = __ldg(p + 1);
+    best[r] = second[r] = 0xFFFFFFFFu;
+  }
+  for (int base = 0; base < nt; base += BF_TILE) {
+    const int nt_tile = min(BF_TILE, nt - base);
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(tp + (size_t)base * 32);
+    for (int i = tid; i < nt_tile * 2; i += BF_THREADS) s_t[i] = __ldg(src + i);
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < nt_tile; ++j) {
+      const uint4 ta = s_t[2 * j], tb = s_t[2 * j + 1];
+#pragma unroll
+      for (int r = 0; r < BF_QPT; ++r) {
+        const uint32_t d = (uint32_t)hamming256(qa[r], qb[r], ta, tb);
+        const uint32_t key = (d << 16) + (uint32_t)(base + j);
+        second[r] = min(second[r], max(best[r], key));
+        best[r] = min(best[r], key);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < BF_QPT; ++r) {
+    const int qi = (blockIdx.x * BF_QPT + r) * BF_THREADS + tid;
+    if (qi < nq) {
+      const int b = best[r] == 0xFFFFFFFFu ? 256 : (int)(best[r] >> 16);
+      const int sc = second[r] == 0xFFFFFFFFu ? 256 : (int)(second[r] >> 16);
+      const int bi = best[r] == 0xFFFFFFFFu ? -1 : (int)(best[r] & 0xFFFFu);
+      const size_t o = (size_t)pair * cap + qi;
+      out_d1[o] = b;
+      out_d2[o] = sc;
+      out_idx[o] = (bi >= 0 && b <= th_dist && (float)b < __fmul_rn((float)sc, ratio)) ? bi : -1;
+    }
+  }
+}
+
 // ---- frame grid ------------------------------------------------------------------------------
 // Cells are stored column-major (cell = ix * GRID_ROWS + iy) so that the reference's traversal
 // (ix outer, iy inner, insertion order inside a cell) of one grid column is ONE contiguous run
@@ -694,6 +752,25 @@ int orbm_bruteforce_host(orbm_matcher* m, const uint8_t* q, int nq, const uint8_
   cudaMemcpyAsync(d1, dres + nq, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, m->stream);
   cudaMemcpyAsync(d2, dres + 2 * nq, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, m->stream);
   return m->check(cudaStreamSynchronize(m->stream), "bruteforce") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+int orbm_bruteforce_batch_device(orbm_matcher* m, int n_pairs, int cap, const uint8_t* d_q, const int32_t* d_nq,
+                                 size_t q_stride, const uint8_t* d_t, const int32_t* d_nt, size_t t_stride, float ratio,
+                                 int th_dist, int32_t* d_idx, int32_t* d_d1, int32_t* d_d2) {
+  if (!m || n_pairs < 0 || cap < 1 || cap > 65535 || (n_pairs && (!d_q || !d_t || !d_nq || !d_nt || !d_idx || !d_d1 || !d_d2)) ||
+      (q_stride & 15) || (t_stride & 15))
+    return ORBX_E_INVALID;
+  if (n_pairs == 0) return ORBX_OK;
+  cudaSetDevice(m->device);
+  const int qblocks = (cap + BF_THREADS * BF_QPT - 1) / (BF_THREADS * BF_QPT);
+  for (int p0 = 0; p0 < n_pairs; p0 += 65535) {
+    const int np = std::min(65535, n_pairs - p0);
+    k_bruteforce_batch<<<dim3(qblocks, np), BF_THREADS, 0, m->stream>>>(
+        d_q + (size_t)p0 * q_stride, d_nq + p0, q_stride, d_t + (size_t)p0 * t_stride, d_nt + p0, t_stride, cap, ratio,
+        th_dist, d_idx + (size_t)p0 * cap, d_d1 + (size_t)p0 * cap, d_d2 + (size_t)p0 * cap);
+    m->launches++;
+  }
+  return m->check(cudaGetLastError(), "bruteforce batch launch") ? ORBX_OK : ORBX_E_CUDA;
 }
 
 int orbm_search_for_initialization_device(orbm_matcher* m, int n_pairs, int cap, const orbx_keypoint* d_k1,

@@ -116,6 +116,15 @@ class ORBmatcher:
                                                     self.mfNNratio if ratio is None else ratio, th_dist, idx.data_ptr(),
                                                     d1.data_ptr(), d2.data_ptr()))
 
+    def bruteforce_batch_device(self, q, nq, t, nt, idx, d1, d2, th_dist: int = TH_LOW, ratio: Optional[float] = None):
+        """Many small pairs at once (torch CUDA tensors): q/t [P, cap, 32] u8 (may be strided views along
+        dim 0), nq/nt [P] i32, idx/d1/d2 [P, cap] i32.  Asynchronous."""
+        P, cap = q.shape[0], q.shape[1]
+        assert t.shape[1] == cap and q.stride(1) == 32 and t.stride(1) == 32
+        check_m(self._h, lib.orbm_bruteforce_batch_device(
+            self._h, P, cap, q.data_ptr(), nq.data_ptr(), q.stride(0), t.data_ptr(), nt.data_ptr(), t.stride(0),
+            self.mfNNratio if ratio is None else ratio, th_dist, idx.data_ptr(), d1.data_ptr(), d2.data_ptr()))
+
     # -- SearchForInitialization (src/ORBmatcher.cc:868-983) --------------------------------------
     def SearchForInitialization(self, F1: Frame, F2: Frame, vbPrevMatched: np.ndarray, windowSize: int = 10):
         """Returns (nmatches, vnMatches12); vbPrevMatched ([N1,2] f32) is updated in place."""

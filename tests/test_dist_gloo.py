@@ -1,0 +1,69 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic: sharding arithmetic and the
+all-gather of per-camera descriptor blocks."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from multi_orb_slam_b200.dist import (allgather_camera_blocks, camera_owner, cameras_of, cross_camera_pairs,
+                                       shard_range)
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 256, 4096, 4099):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_camera_dealing():
+    assert [camera_owner(c, 8) for c in range(8)] == list(range(8))
+    assert cameras_of(1, 8, 2) == [1, 3, 5, 7]
+    assert cross_camera_pairs(3) == [(0, 1), (1, 2), (2, 0)]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_cams, F, cap, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cams = cameras_of(rank, n_cams, world)
+        g = torch.Generator().manual_seed(0)
+        full_desc = torch.randint(0, 256, (n_cams, F, cap, 32), dtype=torch.uint8, generator=g)
+        full_kps = torch.rand((n_cams, F, cap, 6), generator=g)
+        full_counts = torch.randint(0, cap + 1, (n_cams, F), dtype=torch.int32, generator=g)
+        counts, kps, desc = allgather_camera_blocks(full_counts[cams], full_kps[cams], full_desc[cams], n_cams)
+        ok = torch.equal(counts, full_counts) and torch.equal(kps, full_kps) and torch.equal(desc, full_desc)
+        lo, hi = shard_range(F, rank, world)
+        ret[rank] = (bool(ok), lo, hi)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allgather_camera_blocks_world2():
+    world, n_cams, F, cap = 2, 4, 3, 5
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        ret = mgr.dict()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, n_cams, F, cap, ret)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+        assert ret[0][0] and ret[1][0]
+        assert (ret[0][1], ret[0][2], ret[1][1], ret[1][2]) == (0, 2, 2, 3)

@@ -155,3 +155,27 @@ def test_two_handles_with_different_nfeatures(O):
         k_ref, d_ref, _ = O.extractor("port", nfeatures=nf).extract(img)
         k, d = ex(img)
         _assert_same_features(k, d, k_ref, d_ref, f"nf={nf}")
+
+
+def test_cpp_dropin_classes_run(O, tmp_path):
+    """The reference-shaped C++ classes over the C-ABI: same keypoints/descriptors as the oracle."""
+    import struct
+    import subprocess
+    from test_abi import _build_dropin
+    from multi_orb_slam_b200._lib import KP_DTYPE
+    exe = _build_dropin()
+    img = textured(640, 480, 6)
+    src, dst = tmp_path / "img.bin", tmp_path / "out.bin"
+    src.write_bytes(struct.pack("<2i", 640, 480) + img.tobytes())
+    subprocess.run([exe, str(src), str(dst)], check=True)
+    raw = dst.read_bytes()
+    n = struct.unpack_from("<i", raw, 0)[0]
+    k = np.frombuffer(raw, dtype=KP_DTYPE, count=n, offset=4)
+    d = np.frombuffer(raw, dtype=np.uint8, count=n * 32, offset=4 + 24 * n).reshape(n, 32)
+    nm, d01, self_m, pw, ph = struct.unpack_from("<5i", raw, 4 + 56 * n)
+    k_ref, d_ref, _ = O.extractor("port").extract(img)
+    _assert_same_features(k, d, k_ref, d_ref, "C++ drop-in")
+    prev = np.stack([k_ref["x"], k_ref["y"]], axis=1).astype(np.float32)
+    rn, rm12, _ = O.search_for_initialization(k_ref, d_ref, k_ref, d_ref, (0, 640, 0, 480), prev, 100, 0.9, True)
+    assert nm == rn and self_m == int((rm12 == np.arange(len(rm12))).sum())
+    assert d01 == O.distance(d_ref[0], d_ref[1]) and (pw, ph) == (370, 278)

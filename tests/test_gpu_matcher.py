@@ -172,3 +172,27 @@ def test_search_by_projection_points_vs_oracle(M, O, nmp, th, with_stereo, with_
     gn = m.SearchByProjection(F, MapPoints(mp, mpd, mp_obs), th)
     assert gn == rn and np.array_equal(F.mvpMapPoints, rfmp)
     assert rn > nmp // 20
+
+
+def test_bruteforce_batch_vs_oracle(O):
+    import torch
+    from multi_orb_slam_b200.matcher import ORBmatcher
+    m = ORBmatcher(0.9, True)
+    P, cap = 7, 1100
+    rng = np.random.default_rng(12)
+    A = random_descriptors(P * cap, 21).reshape(P, cap, 32)
+    B = np.stack([perturbed_descriptors(A[p], 30 + p)[0] for p in range(P)])
+    nq = rng.integers(0, cap + 1, P).astype(np.int32)
+    nt = rng.integers(1, cap + 1, P).astype(np.int32)
+    nq[0], nt[1] = cap, cap
+    q, t = torch.from_numpy(B).cuda(), torch.from_numpy(A).cuda()
+    idx, d1, d2 = (torch.full((P, cap), -7, dtype=torch.int32, device="cuda") for _ in range(3))
+    m.bruteforce_batch_device(q, torch.from_numpy(nq).cuda(), t, torch.from_numpy(nt).cuda(), idx, d1, d2)
+    m.sync()
+    idx, d1, d2 = idx.cpu().numpy(), d1.cpu().numpy(), d2.cpu().numpy()
+    for p in range(P):
+        if nq[p] == 0:
+            continue
+        ridx, rd1, rd2 = O.bruteforce(B[p, : nq[p]], A[p, : nt[p]], 0.9, 50)
+        assert np.array_equal(idx[p, : nq[p]], ridx) and np.array_equal(d1[p, : nq[p]], rd1) and np.array_equal(d2[p, : nq[p]], rd2)
+        assert (idx[p, nq[p]:] == -7).all()

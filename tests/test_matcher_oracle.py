@@ -1,0 +1,186 @@
+"""Known-answer tests for the matcher restatement (oracle/matcher_oracle.cc).  The reference ships
+no tests or vectors for these functions ("parity unpinned"), so the pins are
+(1) hand-checkable cases and (2) an independent pure-Python transliteration of
+src/ORBmatcher.cc:868-983 / src/Frame.cc:510-566,632-642 written from the reference text, run on
+small random cases."""
+import math
+
+import numpy as np
+import pytest
+
+from multi_orb_slam_b200.synth import random_descriptors
+
+
+@pytest.fixture(scope="module")
+def O(oracle_port):
+    return oracle_port
+
+
+def test_distance_known_answers(O):
+    z, o = np.zeros(32, np.uint8), np.full(32, 255, np.uint8)
+    assert O.distance(z, o) == 256 and O.distance(o, o) == 0 and O.distance(z, z) == 0
+    for bit in (0, 9, 128, 255):
+        a = z.copy()
+        a[bit // 8] ^= 1 << (bit % 8)
+        assert O.distance(z, a) == 1
+    a, b = random_descriptors(50, 1), random_descriptors(50, 2)
+    for i in range(50):
+        assert O.distance(a[i], b[i]) == int(np.unpackbits(a[i] ^ b[i]).sum())
+
+
+def test_three_maxima(O):
+    assert O.three_maxima([0] * 30) == (-1, -1, -1)
+    c = [0] * 30
+    c[3], c[7], c[9] = 10, 5, 2
+    assert O.three_maxima(c) == (3, 7, 9)
+    c[9] = 0            # max3 (0) < 0.1*max1 -> third dropped
+    assert O.three_maxima(c) == (3, 7, -1)
+    c[7] = 0            # max2 < 0.1*max1 -> second and third dropped
+    assert O.three_maxima(c) == (3, -1, -1)
+    c = [0] * 30
+    c[2] = c[5] = c[8] = 4  # ties: first bin wins (strict >)
+    assert O.three_maxima(c) == (2, 5, 8)
+
+
+def test_bruteforce_known_answers(O):
+    t = random_descriptors(64, 3)
+    q = t[[5, 9]].copy()
+    q[1, 0] ^= 0b111  # three flips
+    idx, d1, d2 = O.bruteforce(q, t, 0.9, 50)
+    assert list(idx) == [5, 9] and list(d1) == [0, 3] and (d2 > 60).all()
+    dup = np.concatenate([t, t[5:6]])  # exact duplicate of target 5 later in the list: ratio test fails, best = first
+    idx, d1, d2 = O.bruteforce(q[:1], dup, 0.9, 50)
+    assert idx[0] == -1 and d1[0] == 0 and d2[0] == 0
+
+
+def _py_grid(kx, ky, bounds):
+    minx, maxx, miny, maxy = bounds
+    inv_w = np.float32(64) / np.float32(maxx - minx)
+    inv_h = np.float32(48) / np.float32(maxy - miny)
+    cells = {}
+    for i, (x, y) in enumerate(zip(kx, ky)):
+        fx = np.float32(np.float32(x - np.float32(minx)) * inv_w)
+        fy = np.float32(np.float32(y - np.float32(miny)) * inv_h)
+        px = int(math.floor(abs(fx) + 0.5) * (1 if fx >= 0 else -1))  # C round(): half away from zero
+        py = int(math.floor(abs(fy) + 0.5) * (1 if fy >= 0 else -1))
+        if 0 <= px < 64 and 0 <= py < 48:
+            cells.setdefault((px, py), []).append(i)
+    return cells, inv_w, inv_h
+
+
+def _py_area(cells, inv_w, inv_h, kx, ky, koct, bounds, x, y, r, lo, hi):
+    minx, _, miny, _ = bounds
+    f = np.float32
+    cx0 = max(0, int(math.floor(f(f(f(x) - f(minx)) - f(r)) * inv_w)))
+    cx1 = min(63, int(math.ceil(f(f(f(x) - f(minx)) + f(r)) * inv_w)))
+    cy0 = max(0, int(math.floor(f(f(f(y) - f(miny)) - f(r)) * inv_h)))
+    cy1 = min(47, int(math.ceil(f(f(f(y) - f(miny)) + f(r)) * inv_h)))
+    if cx0 >= 64 or cx1 < 0 or cy0 >= 48 or cy1 < 0:
+        return []
+    check = lo > 0 or hi >= 0
+    out = []
+    for ix in range(cx0, cx1 + 1):
+        for iy in range(cy0, cy1 + 1):
+            for i in cells.get((ix, iy), []):
+                if check and (koct[i] < lo or (hi >= 0 and koct[i] > hi)):
+                    continue
+                if abs(f(kx[i]) - f(x)) < r and abs(f(ky[i]) - f(y)) < r:
+                    out.append(i)
+    return out
+
+
+def test_features_in_area_vs_python(O):
+    rng = np.random.default_rng(4)
+    n = 400
+    kx = rng.uniform(-5, 645, n).astype(np.float32)
+    ky = rng.uniform(-5, 485, n).astype(np.float32)
+    koct = rng.integers(0, 8, n).astype(np.int32)
+    bounds = (0.0, 640.0, 0.0, 480.0)
+    cells, iw, ih = _py_grid(kx, ky, bounds)
+    for _ in range(60):
+        x, y = float(rng.uniform(-50, 700)), float(rng.uniform(-50, 530))
+        r = float(rng.choice([3.0, 15.5, 100.0]))
+        lo, hi = [(-1, -1), (0, 0), (2, 3), (1, -1)][int(rng.integers(0, 4))]
+        got = O.features_in_area(kx, ky, koct, bounds, x, y, r, lo, hi)
+        want = _py_area(cells, iw, ih, kx, ky, koct, bounds, np.float32(x), np.float32(y), np.float32(r), lo, hi)
+        assert list(got) == want
+
+
+def _py_search_init(k1, d1, k2, d2, bounds, prev, window, ratio, check_ori):
+    n1, n2 = len(k1), len(k2)
+    m12 = [-1] * n1
+    m21 = [-1] * n2
+    md = [2**31 - 1] * n2
+    hist = [[] for _ in range(30)]
+    cells, iw, ih = _py_grid(k2["x"], k2["y"], bounds)
+    nm = 0
+    dist = lambda a, b: int(np.unpackbits(a ^ b).sum())
+    for i1 in range(n1):
+        if k1["octave"][i1] > 0:
+            continue
+        cand = _py_area(cells, iw, ih, k2["x"], k2["y"], k2["octave"], bounds, prev[i1, 0], prev[i1, 1], np.float32(window), 0, 0)
+        if not cand:
+            continue
+        best, best2, bi = 2**31 - 1, 2**31 - 1, -1
+        for i2 in cand:
+            dd = dist(d1[i1], d2[i2])
+            if md[i2] <= dd:
+                continue
+            if dd < best:
+                best2, best, bi = best, dd, i2
+            elif dd < best2:
+                best2 = dd
+        if best <= 50 and np.float32(best) < np.float32(best2) * np.float32(ratio):
+            if m21[bi] >= 0:
+                m12[m21[bi]] = -1
+                nm -= 1
+            m12[i1], m21[bi], md[bi] = bi, i1, best
+            nm += 1
+            if check_ori:
+                rot = np.float32(k1["angle"][i1]) - np.float32(k2["angle"][bi])
+                if rot < 0:
+                    rot = np.float32(rot + np.float32(360.0))
+                v = np.float32(rot * np.float32(1.0 / 30))
+                b = int(math.floor(v + 0.5))
+                hist[0 if b == 30 else b].append(i1)
+    if check_ori:
+        import oracle_lib
+        keep = set(oracle_lib.three_maxima([len(h) for h in hist]))
+        for b in range(30):
+            if b in keep:
+                continue
+            for i1 in hist[b]:
+                if m12[i1] >= 0:
+                    m12[i1] = -1
+                    nm -= 1
+    return nm, m12
+
+
+@pytest.mark.parametrize("seed,window,check_ori", [(0, 40, True), (1, 100, True), (2, 15, False), (3, 1000, True)])
+def test_search_for_initialization_vs_python(O, seed, window, check_ori):
+    from oracle_lib import KP_DTYPE
+    rng = np.random.default_rng(seed)
+    n1, n2 = 120, 140
+    k1 = np.zeros(n1, KP_DTYPE)
+    k1["x"], k1["y"] = rng.uniform(0, 640, n1), rng.uniform(0, 480, n1)
+    k1["octave"] = rng.integers(0, 3, n1)
+    k1["angle"] = rng.uniform(0, 360, n1)
+    d1 = random_descriptors(n1, seed + 10)
+    src = rng.integers(0, n1, n2)
+    k2 = np.zeros(n2, KP_DTYPE)
+    k2["x"] = k1["x"][src] + rng.normal(0, 6, n2)
+    k2["y"] = k1["y"][src] + rng.normal(0, 6, n2)
+    k2["octave"] = np.where(rng.random(n2) < 0.8, 0, 1)
+    k2["angle"] = (k1["angle"][src] + rng.normal(0, 20, n2)) % 360
+    bits = np.unpackbits(d1[src], axis=1)
+    flips = rng.integers(0, 70, n2)
+    bits ^= (np.argsort(np.argsort(rng.random((n2, 256)), axis=1), axis=1) < flips[:, None]).astype(np.uint8)
+    d2 = np.packbits(bits, axis=1)
+    prev = np.stack([k1["x"], k1["y"]], axis=1).astype(np.float32)
+    bounds = (0.0, 640.0, 0.0, 480.0)
+    rn, rm12, rprev = O.search_for_initialization(k1, d1, k2, d2, bounds, prev, window, 0.9, check_ori)
+    pn, pm12 = _py_search_init(k1, d1, k2, d2, bounds, prev, window, 0.9, check_ori)
+    assert rn == pn and list(rm12) == pm12
+    assert rn == int((rm12 >= 0).sum())
+    for i1 in np.nonzero(rm12 >= 0)[0]:
+        assert rprev[i1, 0] == k2["x"][rm12[i1]] and rprev[i1, 1] == k2["y"][rm12[i1]]
