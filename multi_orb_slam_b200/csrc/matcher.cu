@@ -353,18 +353,24 @@ __global__ void __launch_bounds__(256) k_init_candidates(int cap, const orbx_key
   if (lane == 0) cand_cnt_all[(size_t)pair * cap + i1] = cnt;
 }
 
+#define INIT_SMEM_CAND 12288  // candidate entries staged in shared memory per pair (48 KB)
+
 __global__ void __launch_bounds__(128) k_init_resolve(int cap, const orbx_keypoint* __restrict__ k1_all,
                                                       const int32_t* __restrict__ n1_arr,
-                                                      const orbx_keypoint* __restrict__ k2_all, float* __restrict__ prev_all,
+                                                      const orbx_keypoint* __restrict__ k2_all,
+                                                      const int32_t* __restrict__ n2_arr, float* __restrict__ prev_all,
                                                       float nnratio, int check_ori, const uint32_t* __restrict__ cand_all,
                                                       const int* __restrict__ cand_cnt_all,
                                                       int32_t* __restrict__ matches12_all, int32_t* __restrict__ nmatches_out) {
-  extern __shared__ int s_dyn[];  // matchedDist, matches21, bin_of, cand count, query list: [cap] each
+  // matchedDist, matches21, bin_of, cand count, cand offset, query list, matches12: [cap] ints each;
+  // angle1, angle2: [cap] floats; then INIT_SMEM_CAND staged candidate entries
+  extern __shared__ int s_dyn[];
   __shared__ int s_hist[HISTO_LENGTH];
   __shared__ int s_keep[HISTO_LENGTH];
-  __shared__ int s_nmatch;
+  __shared__ int s_nmatch, s_total;
+  __shared__ int s_wsum[4];
   const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n1 = min(n1_arr[pair], cap);
+  const int n1 = min(n1_arr[pair], cap), n2 = min(n2_arr[pair], cap);
   const orbx_keypoint* k1 = k1_all + (size_t)pair * cap;
   const orbx_keypoint* k2 = k2_all + (size_t)pair * cap;
   float* prev = prev_all ? prev_all + (size_t)pair * cap * 2 : nullptr;
@@ -374,19 +380,52 @@ __global__ void __launch_bounds__(128) k_init_resolve(int cap, const orbx_keypoi
   int* s_mdist = s_dyn;
   int* s_m21 = s_dyn + cap;
   int* s_bin = s_dyn + 2 * cap;
-  int* s_cnt = s_dyn + 3 * cap;   // candidates per i1
-  int* s_list = s_dyn + 4 * cap;  // i1 with at least one candidate, ascending
-  __shared__ int s_nlist;
+  int* s_cnt = s_dyn + 3 * cap;
+  int* s_off = s_dyn + 4 * cap;
+  int* s_list = s_dyn + 5 * cap;
+  int* s_m12 = s_dyn + 6 * cap;
+  float* s_ang1 = reinterpret_cast<float*>(s_dyn + 7 * cap);
+  float* s_ang2 = reinterpret_cast<float*>(s_dyn + 8 * cap);
+  uint32_t* s_cand = reinterpret_cast<uint32_t*>(s_dyn + 9 * cap);
   for (int i = tid; i < cap; i += 128) {
     s_mdist[i] = 0x7FFFFFFF;
     s_m21[i] = -1;
     s_bin[i] = -1;
+    s_m12[i] = -1;
     s_cnt[i] = i < n1 ? cand_cnt[i] : 0;
-    if (i < n1) matches12[i] = -1;
+    s_ang1[i] = i < n1 ? k1[i].angle : 0.f;
+    s_ang2[i] = i < n2 ? k2[i].angle : 0.f;
   }
   if (tid < HISTO_LENGTH) s_hist[tid] = 0;
   if (tid == 0) s_nmatch = 0;
-  __threadfence_block();
+  __syncthreads();
+  // exclusive scan of the candidate counts (each thread owns a contiguous chunk of queries)
+  {
+    const int chunk = (cap + 127) / 128, lo = tid * chunk, hi = min(cap, lo + chunk);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += s_cnt[i];
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    int run = incl - s;
+    for (int w = 0; w < warp; ++w) run += s_wsum[w];
+    if (tid == 127) s_total = run + s;
+    for (int i = lo; i < hi; ++i) { s_off[i] = run; run += s_cnt[i]; }
+  }
+  __syncthreads();
+  const bool staged = s_total <= INIT_SMEM_CAND;
+  if (staged) {  // all candidate rows of the pair into shared memory, a warp per row
+    for (int i1 = warp; i1 < n1; i1 += 4) {
+      const int cnt = s_cnt[i1], off = s_off[i1];
+      const uint32_t* row = cand + (size_t)i1 * cap;
+      for (int c = lane; c < cnt; c += 32) s_cand[off + c] = row[c];
+    }
+  }
   __syncthreads();
   if (warp == 0) {
     // ordered compaction of the queries that have candidates (most keypoints are not level 0)
@@ -400,51 +439,40 @@ __global__ void __launch_bounds__(128) k_init_resolve(int cap, const orbx_keypoi
     }
     __syncwarp();
     int nmatches = 0;
-    // software prefetch: the next query's first 64 candidates are loaded while this one resolves
-    uint32_t pf0 = 0, pf1 = 0;
-    if (nlist > 0) {
-      const uint32_t* r0 = cand + (size_t)s_list[0] * cap;
-      const int c0 = s_cnt[s_list[0]];
-      if (lane < c0) pf0 = r0[lane];
-      if (lane + 32 < c0) pf1 = r0[lane + 32];
-    }
     for (int j = 0; j < nlist; ++j) {
       const int i1 = s_list[j];
       const int cnt = s_cnt[i1];
-      const uint32_t* row = cand + (size_t)i1 * cap;
-      const uint32_t e0 = pf0, e1 = pf1;
-      if (j + 1 < nlist) {
-        const uint32_t* rn = cand + (size_t)s_list[j + 1] * cap;
-        const int cn = s_cnt[s_list[j + 1]];
-        if (lane < cn) pf0 = rn[lane];
-        if (lane + 32 < cn) pf1 = rn[lane + 32];
-      }
-      // key = dist << 16 | traversal position: strict-< scan order (:910-919)
+      const uint32_t* row = staged ? s_cand + s_off[i1] : cand + (size_t)i1 * cap;
+      // key = dist << 16 | traversal position: strict-< scan order (:910-919); the lane that
+      // owns the best key also remembers its i2
       uint32_t best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
+      int my_i2 = -1;
       for (int c = lane; c < cnt; c += 32) {
-        const uint32_t e = c < 32 ? e0 : (c < 64 ? e1 : row[c]);
+        const uint32_t e = row[c];
         const int dist = (int)(e >> 16), i2 = (int)(e & 0xFFFFu);
         if (s_mdist[i2] <= dist) continue;  // :907
         const uint32_t key = (uint32_t)dist << 16 | (uint32_t)c;
         second = min(second, max(best, key));
-        best = min(best, key);
+        if (key < best) { best = key; my_i2 = i2; }
       }
+      const uint32_t mine = best;
       warp_top2(best, second);
       if (best == 0xFFFFFFFFu) continue;
       const int bestDist = (int)(best >> 16);
-      const int bestIdx2 = (int)(row[best & 0xFFFFu] & 0xFFFFu);
+      const unsigned owner = __ballot_sync(0xffffffffu, mine == best);
+      const int bestIdx2 = __shfl_sync(0xffffffffu, my_i2, __ffs(owner) - 1);
       // bestDist2 stays INT_MAX when there is no second candidate (:896-897)
       const float second_f = second == 0xFFFFFFFFu ? (float)0x7FFFFFFF : (float)(int)(second >> 16);
       if (bestDist <= TH_LOW && (float)bestDist < __fmul_rn(second_f, nnratio)) {
         if (lane == 0) {
           const int old = s_m21[bestIdx2];
-          if (old >= 0) { matches12[old] = -1; nmatches--; }
-          matches12[i1] = bestIdx2;
+          if (old >= 0) { s_m12[old] = -1; nmatches--; }
+          s_m12[i1] = bestIdx2;
           s_m21[bestIdx2] = i1;
           s_mdist[bestIdx2] = bestDist;
           nmatches++;
           if (check_ori) {
-            float rot = __fsub_rn(k1[i1].angle, k2[bestIdx2].angle);
+            float rot = __fsub_rn(s_ang1[i1], s_ang2[bestIdx2]);
             if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
             int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
             if (bin == HISTO_LENGTH) bin = 0;
@@ -471,25 +499,23 @@ __global__ void __launch_bounds__(128) k_init_resolve(int cap, const orbx_keypoi
       }
     }
   }
-  __threadfence_block();
   __syncthreads();
-  if (check_ori) {
-    for (int i1 = tid; i1 < n1; i1 += 128) {
+  for (int i1 = tid; i1 < n1; i1 += 128) {
+    int m = s_m12[i1];
+    if (check_ori) {
       const int bin = s_bin[i1];
-      if (bin >= 0 && !s_keep[bin] && matches12[i1] >= 0) {
-        matches12[i1] = -1;
+      if (bin >= 0 && !s_keep[bin] && m >= 0) {
+        m = -1;
         atomicSub(&s_nmatch, 1);
       }
     }
-    __syncthreads();
-  }
-  for (int i1 = tid; prev && i1 < n1; i1 += 128) {  // :978-980
-    const int m = matches12[i1];
-    if (m >= 0) {
+    matches12[i1] = m;
+    if (prev && m >= 0) {  // :978-980
       prev[2 * i1] = k2[m].x;
       prev[2 * i1 + 1] = k2[m].y;
     }
   }
+  __syncthreads();
   if (tid == 0) nmatches_out[pair] = s_nmatch;
 }
 
@@ -781,7 +807,7 @@ int orbm_search_for_initialization_device(orbm_matcher* m, int n_pairs, int cap,
   if (!m || n_pairs < 0 || cap < 1 || cap > 65535) return ORBX_E_INVALID;
   if (n_pairs == 0) return ORBX_OK;
   cudaSetDevice(m->device);
-  const size_t smem = sizeof(int) * 5 * (size_t)cap;
+  const size_t smem = sizeof(int) * 9 * (size_t)cap + sizeof(uint32_t) * INIT_SMEM_CAND;
   if (smem > 200 * 1024) { m->err = "cap too large for SearchForInitialization"; return ORBX_E_INVALID; }
   // candidate rows are cap x cap per pair: process pairs in groups that keep the scratch <= ~2 GiB
   const size_t per_pair = (size_t)cap * cap * sizeof(uint32_t);
@@ -802,8 +828,8 @@ int orbm_search_for_initialization_device(orbm_matcher* m, int n_pairs, int cap,
     k_init_candidates<<<dim3((cap + 7) / 8, np), 256, 0, m->stream>>>(cap, d_k1 + o, d_d1 + o * 32, d_n1 + p0, d_k2 + o,
                                                                         d_d2 + o * 32, bounds2, gstart, gitems, prev,
                                                                         (float)window, cand, cand_cnt);
-    k_init_resolve<<<np, 128, smem, m->stream>>>(cap, d_k1 + o, d_n1 + p0, d_k2 + o, prev, nnratio, check_ori, cand,
-                                                 cand_cnt, d_matches12 + o, d_nmatches + p0);
+    k_init_resolve<<<np, 128, smem, m->stream>>>(cap, d_k1 + o, d_n1 + p0, d_k2 + o, d_n2 + p0, prev, nnratio, check_ori,
+                                                 cand, cand_cnt, d_matches12 + o, d_nmatches + p0);
     m->launches += 3;
   }
   return m->check(cudaGetLastError(), "search_for_initialization launch") ? ORBX_OK : ORBX_E_CUDA;
