@@ -270,24 +270,56 @@ __device__ __forceinline__ void grid_query(const GridView& gv, const orbx_keypoi
   const int cy1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, gv.min_y), r), gv.inv_h)));
   if (cy1 < 0) return;
   const bool check = (min_level > 0) || (max_level >= 0);
-  for (int ix = cx0; ix <= cx1; ++ix) {
-    const int run0 = gv.start[ix * GRID_ROWS + cy0], run1 = gv.start[ix * GRID_ROWS + cy1 + 1];
-    for (int e = run0; e < run1; e += 32) {
-      const int ei = e + lane;
-      bool ok = false;
-      int idx = 0;
-      if (ei < run1) {
-        idx = gv.items[ei];
-        const orbx_keypoint kp = k[idx];
-        ok = true;
-        if (check) {
-          if (kp.octave < min_level) ok = false;
-          if (max_level >= 0 && kp.octave > max_level) ok = false;
-        }
-        ok = ok && fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r;
-      }
-      emit(ok, idx);
+  // One contiguous run of `items` per grid column (cells are stored column-major).  The runs of
+  // all (<= 64) columns are flattened: lanes fetch the run bounds of two columns each, a warp
+  // prefix sum gives every column's offset in the flattened order, and the entries are visited 32
+  // at a time in exactly the reference's (ix, iy, insertion) order; a lane finds the column of its
+  // entry by a shuffle binary search over the (sorted) offsets.
+  const int ncol = cx1 - cx0 + 1;
+  int r0a = 0, len_a = 0, r0b = 0, len_b = 0;
+  if (lane < ncol) {
+    r0a = gv.start[(cx0 + lane) * GRID_ROWS + cy0];
+    len_a = gv.start[(cx0 + lane) * GRID_ROWS + cy1 + 1] - r0a;
+  }
+  if (lane + 32 < ncol) {
+    r0b = gv.start[(cx0 + lane + 32) * GRID_ROWS + cy0];
+    len_b = gv.start[(cx0 + lane + 32) * GRID_ROWS + cy1 + 1] - r0b;
+  }
+  int incl_a = len_a, incl_b = len_b;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int va = __shfl_up_sync(0xffffffffu, incl_a, o), vb = __shfl_up_sync(0xffffffffu, incl_b, o);
+    if (lane >= o) { incl_a += va; incl_b += vb; }
+  }
+  const int total_a = __shfl_sync(0xffffffffu, incl_a, 31);
+  const int total = total_a + __shfl_sync(0xffffffffu, incl_b, 31);
+  const int excl_a = incl_a - len_a, excl_b = incl_b - len_b;
+  for (int e = 0; e < total; e += 32) {
+    const int ei = e + lane;
+    const bool second_half = ei >= total_a;
+    const int key = second_half ? ei - total_a : ei;
+    int ca = 0, cb = 0;  // largest column whose exclusive offset is <= key (empty columns precede it)
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int va = __shfl_sync(0xffffffffu, excl_a, (ca + step) & 31), vb = __shfl_sync(0xffffffffu, excl_b, (cb + step) & 31);
+      if (ca + step < 32 && va <= key) ca += step;
+      if (cb + step < 32 && vb <= key) cb += step;
     }
+    const int ra = __shfl_sync(0xffffffffu, r0a, ca), xa = __shfl_sync(0xffffffffu, excl_a, ca);
+    const int rb = __shfl_sync(0xffffffffu, r0b, cb), xb = __shfl_sync(0xffffffffu, excl_b, cb);
+    bool ok = false;
+    int idx = 0;
+    if (ei < total) {
+      idx = gv.items[second_half ? rb + (key - xb) : ra + (key - xa)];
+      const orbx_keypoint kp = k[idx];
+      ok = true;
+      if (check) {
+        if (kp.octave < min_level) ok = false;
+        if (max_level >= 0 && kp.octave > max_level) ok = false;
+      }
+      ok = ok && fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r;
+    }
+    emit(ok, idx);
   }
 }
 
