@@ -202,6 +202,7 @@ bool build_geometry(orbx_extractor* h, std::vector<OrbCell>& cells, std::vector<
         c.off_x = (short)(j * L.w_cell);
         c.off_y = (short)(i * L.h_cell);
         c.slot = (short)((int)cells.size() - L.cell_base);
+        c.pad = 0;
         cells.push_back(c);
       }
     }
@@ -212,6 +213,15 @@ bool build_geometry(orbx_extractor* h, std::vector<OrbCell>& cells, std::vector<
     L.cand_off = (unsigned)cand_off;
     L.key_off = (unsigned)key_off;
     L.key_cap = L.n_cells * L.cand_cap;
+    for (int ci = L.cell_base; ci < (int)cells.size(); ++ci) {
+      OrbCell& c = cells[ci];
+      const int bx = ORB_EDGE + c.ini_x;
+      c.a0 = (short)(bx & 3);
+      c.tile_off = L.pyr_off + (unsigned)(ORB_EDGE + c.ini_y) * (unsigned)L.pitch + (unsigned)(bx - c.a0);
+      c.pitch = (unsigned short)L.pitch;
+      c.cand_cap = (unsigned short)L.cand_cap;
+      c.cand_slot_off = (unsigned)cand_off + (unsigned)c.slot * (unsigned)L.cand_cap;
+    }
     cand_off += (size_t)L.key_cap;
     key_off += (size_t)L.key_cap;
     // octree roots

@@ -273,9 +273,10 @@ __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int
   return sm.misc[1];
 }
 
-__global__ void __launch_bounds__(128) k_fast_cells(const OrbGeom* __restrict__ g, const OrbCell* __restrict__ cells,
-                                                    const uint8_t* __restrict__ pyr, uint32_t* __restrict__ cand,
-                                                    int* __restrict__ cell_count, int rows_max, int t_max) {
+__global__ void __launch_bounds__(128) k_fast_cells(const OrbCell* __restrict__ cells, const uint8_t* __restrict__ pyr,
+                                                    uint32_t* __restrict__ cand, int* __restrict__ cell_count,
+                                                    size_t pyr_frame_bytes, size_t cand_frame_u32, int n_cells,
+                                                    int ini_th, int min_th, int rows_max, int t_max) {
   extern __shared__ __align__(16) unsigned char fsm[];
   FastSmem sm;
   sm.img = fsm;
@@ -284,35 +285,37 @@ __global__ void __launch_bounds__(128) k_fast_cells(const OrbGeom* __restrict__ 
   sm.kept = sm.queue + ((t_max + 4 * ORB_CELL_MAX + 7) & ~7);
   sm.misc = reinterpret_cast<int*>(sm.kept + ((t_max / 2 + 8) & ~7));
 
-  const OrbCell cell = cells[blockIdx.x];
-  const OrbLevelGeom& L = g->lv[cell.level];
+  // one 32-byte record tells the CTA everything about its cell
+  const uint4* crec = reinterpret_cast<const uint4*>(cells + blockIdx.x);
+  const uint4 c0 = __ldg(crec), c1 = __ldg(crec + 1);
+  OrbCell cell;
+  reinterpret_cast<uint4*>(&cell)[0] = c0;
+  reinterpret_cast<uint4*>(&cell)[1] = c1;
   const int frame = blockIdx.y;
-  const int cw = cell.cw, ch = cell.ch;
+  const int cw = cell.cw, ch = cell.ch, a0 = cell.a0, pitch = cell.pitch;
   const int tid = threadIdx.x;
-  // aligned word copy of the sub-image rows (16 lanes per row); a0 = misalignment of the first column
-  const int bx = ORB_EDGE + cell.ini_x, a0 = bx & 3;
-  const uint8_t* base = pyr + (size_t)frame * g->pyr_frame_bytes + L.pyr_off +
-                        (size_t)(ORB_EDGE + cell.ini_y) * L.pitch + (bx - a0);
+  // aligned word copy of the sub-image rows (16 lanes per row)
+  const uint8_t* base = pyr + (size_t)frame * pyr_frame_bytes + cell.tile_off;
   const int nw = (a0 + cw + 3) >> 2;
   for (int wq = tid & 15; wq < nw; wq += 16)
     for (int y = tid >> 4; y < ch; y += 8)
       reinterpret_cast<uint32_t*>(sm.img + y * FAST_PITCH)[wq] =
-          __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)y * L.pitch) + wq);
+          __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)y * pitch) + wq);
   for (int i = tid; i < ch * (FAST_PITCH / 16); i += 128) reinterpret_cast<uint4*>(sm.m)[i] = make_uint4(0, 0, 0, 0);
   const int tw = cw - 6, thh = ch - 6;
-  int total = 0, th = g->ini_th;
+  int total = 0, th = ini_th;
   __syncthreads();
   if (tw > 0 && thh > 0) {
     total = fast_pass(sm, th, tw, thh, a0, false);
-    if (total == 0 && g->min_th < th) {
-      th = g->min_th;
+    if (total == 0 && min_th < th) {
+      th = min_th;
       total = fast_pass(sm, th, tw, thh, a0, true);
     }
   }
   // ordered write-out: rank of each survivor = number of survivors before it in row-major order
   // (byte offsets into the pitched map are monotone in (y, x)) = cv::FAST's output order
-  total = min(total, L.cand_cap);
-  uint32_t* out = cand + (size_t)frame * g->cand_frame_u32 + L.cand_off + (size_t)cell.slot * L.cand_cap;
+  total = min(total, (int)cell.cand_cap);
+  uint32_t* out = cand + (size_t)frame * cand_frame_u32 + cell.cand_slot_off;
   for (int i = tid; i < total; i += 128) {
     const int off = sm.kept[i];
     int rank = 0;
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(128) k_fast_cells(const OrbGeom* __restrict__ 
     const int y = off / FAST_PITCH, x = off - y * FAST_PITCH - a0;
     out[rank] = (uint32_t)(x + cell.off_x) | (uint32_t)(y + cell.off_y) << 12 | ((uint32_t)sm.m[off] - 1u) << 24;
   }
-  if (tid == 0) cell_count[(size_t)frame * g->n_cells + blockIdx.x] = total;
+  if (tid == 0) cell_count[(size_t)frame * n_cells + blockIdx.x] = total;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -627,8 +630,9 @@ void launch_fast(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, uint
   }
   const size_t smem = (size_t)2 * rows_max * FAST_PITCH + 2 * (size_t)((t_max + 4 * ORB_CELL_MAX + 7) & ~7) +
                       2 * (size_t)((t_max / 2 + 8) & ~7) + 32;
-  k_fast_cells<<<dim3(gh.g.n_cells, n_frames), 128, smem, st>>>(gh.d_geom, gh.d_cells, d_pyr, d_cand, d_cell_count,
-                                                                  rows_max, t_max);
+  k_fast_cells<<<dim3(gh.g.n_cells, n_frames), 128, smem, st>>>(gh.d_cells, d_pyr, d_cand, d_cell_count,
+                                                                  gh.g.pyr_frame_bytes, gh.g.cand_frame_u32, gh.g.n_cells,
+                                                                  gh.g.ini_th, gh.g.min_th, rows_max, t_max);
   ++*launches;
 }
 

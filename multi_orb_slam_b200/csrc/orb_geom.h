@@ -37,12 +37,19 @@ struct OrbLevelGeom {
   OtRoots roots;
 };
 
-struct OrbCell {            // one live FAST cell (:790-830)
-  short level;
-  short ini_x, ini_y;       // top-left of the sub-image in level coordinates
+struct __align__(16) OrbCell {  // one live FAST cell (:790-830); self-contained so the cell kernel
+                                // needs ONE 32-byte load before it can fetch its tile
+  unsigned tile_off;        // byte offset, inside a frame's pyramid block, of the word-aligned tile origin
+  unsigned cand_slot_off;   // u32 offset, inside a frame's candidate block, of this cell's slots
+  unsigned short pitch;     // bytes per row of the level's bordered buffer
+  unsigned short cand_cap;  // candidate slots of this cell
   short cw, ch;             // sub-image size (cell + 6, clipped)
   short off_x, off_y;       // j*wCell, i*hCell added to cell-local coordinates (:823-824)
-  short slot;               // cell index within its level (candidate slot block)
+  short a0;                 // misalignment of the sub-image's first column inside its first word
+  short level;
+  short ini_x, ini_y;       // top-left of the sub-image in level coordinates
+  short slot;               // cell index within its level
+  short pad;
 };
 
 struct OrbGeom {
