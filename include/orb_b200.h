@@ -200,6 +200,44 @@ int orbm_search_by_projection_points_host(orbm_matcher* m, const orbx_keypoint* 
                                           float nnratio, int32_t* frame_mp, const int32_t* frame_mp_obs,
                                           int* nmatches);
 
+/* Camera intrinsics / stereo fields of Frame read by the pose-based overloads (fx, fy, cx, cy,
+ * mb = baseline, mbf). */
+typedef struct {
+  float fx, fy, cx, cy, mb, mbf;
+} orbm_camera;
+
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono, CalibMatrix)
+ * (src/ORBmatcher.cc:3448-3641) — the tracking matcher of the two-camera rig
+ * (Tracking::TrackWithMotionModel, src/Tracking.cc:1267).  Current frame: keypoints of all cameras
+ * concatenated (mvKeysUn_total), one descriptor row per global index, cur_uright (mvuRight_total,
+ * may be NULL), cur_cam (keypoint_to_cam, may be NULL = all camera 0), Tcw_cur (mTcw, 4x4
+ * row-major); cur_mp (n_cur, in/out: index into the last-frame arrays or -1 = mvpMapPoints),
+ * cur_mp_obs (Observations()>0 of points held on entry, may be NULL).  Last frame: Tcw_last,
+ * last_k (octave + angle), last_cam, last_valid[i] = mvpMapPoints[i] && !mvbOutlier[i], last_xyz
+ * (GetWorldPos, n_last x 3), last_desc (GetDescriptor), last_obs (Observations()>0, may be NULL).
+ * calib: the 4x3 CalibMatrix row-major (rows 0-2 R_cam12, row 3 t_cam12).  The projection runs on
+ * the host in the reference's float evaluation order; search and resolve run on the GPU. */
+int orbm_search_by_projection_frame_host(orbm_matcher* m, const orbx_keypoint* cur_k, const uint8_t* cur_desc,
+                                         const float* cur_uright, const int32_t* cur_cam, int n_cur, orbm_bounds b,
+                                         const float* scale_factors, int nlevels, orbm_camera cam, const float* Tcw_cur,
+                                         const float* Tcw_last, const orbx_keypoint* last_k, const int32_t* last_cam,
+                                         const int32_t* last_valid, const float* last_xyz, const uint8_t* last_desc,
+                                         const int32_t* last_obs, int n_last, const float* calib, float th, int mono,
+                                         int check_ori, int32_t* cur_mp, const int32_t* cur_mp_obs, int* nmatches);
+
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, sAlreadyFound, th, ORBdist)
+ * (src/ORBmatcher.cc:3809-3937) — relocalisation refinement (src/Tracking.cc:2099,2116).
+ * kf_valid[i] = map point exists, !isBad(), not in sAlreadyFound; kf_max_dist / kf_min_dist =
+ * Get{Max,Min}DistanceInvariance(); kf_max_d = mfMaxDistance (PredictScale, src/MapPoint.cc:602-617);
+ * kf_angle = pKF->mvKeysUn[i].angle; log_scale_factor = Frame::mfLogScaleFactor.  cur_mp (n_cur,
+ * in/out): any value >= 0 means the keypoint already holds a point. */
+int orbm_search_by_projection_keyframe_host(orbm_matcher* m, const orbx_keypoint* cur_k, const uint8_t* cur_desc, int n_cur,
+                                            orbm_bounds b, const float* scale_factors, int nlevels, float log_scale_factor,
+                                            orbm_camera cam, const float* Tcw_cur, const int32_t* kf_valid,
+                                            const float* kf_xyz, const float* kf_max_dist, const float* kf_min_dist,
+                                            const float* kf_max_d, const float* kf_angle, const uint8_t* kf_desc, int n_kf,
+                                            float th, int orb_dist, int check_ori, int32_t* cur_mp, int* nmatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,11 @@ class Config(C.Structure):
                 ("height", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32)]
 
 
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("mb", C.c_float),
+                ("mbf", C.c_float)]
+
+
 class Bounds(C.Structure):
     _fields_ = [("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
 
@@ -77,6 +82,10 @@ _SIGS = {
                                                 _vp, _vp]),
     "orbm_search_by_projection_points_host": (_i, [_vp, _vp, _vp, _vp, _i, Bounds, _vp, _i, _vp, _vp, _vp, _i, _f, _f,
                                                   _vp, _vp, C.POINTER(_i)]),
+    "orbm_search_by_projection_frame_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, Bounds, _vp, _i, Camera, _vp, _vp, _vp, _vp,
+                                                 _vp, _vp, _vp, _vp, _i, _vp, _f, _i, _i, _vp, _vp, C.POINTER(_i)]),
+    "orbm_search_by_projection_keyframe_host": (_i, [_vp, _vp, _vp, _i, Bounds, _vp, _i, _f, Camera, _vp, _vp, _vp, _vp, _vp,
+                                                    _vp, _vp, _vp, _i, _f, _i, _i, _vp, C.POINTER(_i)]),
 }
 EXPORTS = tuple(_SIGS)
 for _name, (_res, _args) in _SIGS.items():

@@ -12,6 +12,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -199,7 +200,8 @@ __device__ __forceinline__ int grid_cell_of(float x, float y, float min_x, float
 // One CTA per frame: counting sort of keypoints into grid cells, stable in keypoint index.
 __global__ void __launch_bounds__(256) k_build_grid(const orbx_keypoint* __restrict__ kps, const int32_t* __restrict__ n_arr,
                                                     int n_fixed, int cap, orbm_bounds b, int* __restrict__ start_out,
-                                                    uint16_t* __restrict__ items_out) {
+                                                    uint16_t* __restrict__ items_out,
+                                                    const int32_t* __restrict__ cam_of = nullptr, int cam = 0) {
   __shared__ int s_cnt[GRID_CELLS + 1];
   __shared__ int s_part[257];
   const int frame = blockIdx.x, tid = threadIdx.x;
@@ -210,7 +212,8 @@ __global__ void __launch_bounds__(256) k_build_grid(const orbx_keypoint* __restr
   for (int i = tid; i <= GRID_CELLS; i += 256) s_cnt[i] = 0;
   __syncthreads();
   for (int i = tid; i < n; i += 256) {
-    const int c = grid_cell_of(k[i].x, k[i].y, b.min_x, b.min_y, inv_w, inv_h);
+    int c = grid_cell_of(k[i].x, k[i].y, b.min_x, b.min_y, inv_w, inv_h);
+    if (cam_of && cam_of[i] != cam) c = -1;  // mGrids[cam] holds that camera's keypoints only (src/Frame.cc:384-393)
     if (c >= 0) atomicAdd(&s_cnt[c], 1);
   }
   __syncthreads();
@@ -242,6 +245,7 @@ __global__ void __launch_bounds__(256) k_build_grid(const orbx_keypoint* __restr
       const int i = base + tid;
       int c = -1;
       if (i < n) c = grid_cell_of(k[i].x, k[i].y, b.min_x, b.min_y, inv_w, inv_h);
+      if (i < n && cam_of && cam_of[i] != cam) c = -1;
       const unsigned peers = __match_any_sync(0xffffffffu, c);
       if (c >= 0) {
         const int rank = __popc(peers & ((1u << tid) - 1u));
@@ -670,6 +674,138 @@ __global__ void __launch_bounds__(32) k_proj_resolve(const int* __restrict__ row
   if (lane == 0) *nmatches_out = nmatches;
 }
 
+// ---- pose-based SearchByProjection overloads: generic projected queries ----------------------
+// The host projects the source points with the reference's own float arithmetic (it is a few
+// thousand flops and must match OpenCV's evaluation order); the device does what costs: window
+// query on the per-camera grid, stereo gate, Hamming distances, ordered resolve with occupancy,
+// rotation histogram.  One query = one projected source point.
+struct ProjQuery {
+  float u, v, radius;   // projection and search radius
+  float ur;             // predicted right coordinate (u - mbf*invz); used when use_ur != 0
+  float angle;          // source keypoint angle (rotation histogram)
+  int32_t min_level, max_level;
+  int32_t cam;          // which per-camera grid
+  int32_t src;          // index written into frame_mp on acceptance
+  int32_t obs;          // Observations()>0 of the source map point
+  int32_t use_ur;
+};
+
+__global__ void __launch_bounds__(256) k_query_candidates(const orbx_keypoint* __restrict__ k, const uint8_t* __restrict__ desc,
+                                                          const float* __restrict__ u_right, orbm_bounds b,
+                                                          const int* __restrict__ grid_start,
+                                                          const uint16_t* __restrict__ grid_items, int n_frame_kps,
+                                                          const ProjQuery* __restrict__ q, const uint8_t* __restrict__ q_desc,
+                                                          int nq, int count_only, int* __restrict__ row_cnt,
+                                                          const int* __restrict__ row_off, uint32_t* __restrict__ rows) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= nq) return;
+  const ProjQuery p = q[i];
+  GridView gv;
+  gv.start = grid_start + (size_t)p.cam * (GRID_CELLS + 1);
+  gv.items = grid_items + (size_t)p.cam * n_frame_kps;
+  gv.min_x = b.min_x;
+  gv.min_y = b.min_y;
+  gv.inv_w = __fdiv_rn((float)GRID_COLS, __fsub_rn(b.max_x, b.min_x));
+  gv.inv_h = __fdiv_rn((float)GRID_ROWS, __fsub_rn(b.max_y, b.min_y));
+  const uint4* qd = reinterpret_cast<const uint4*>(q_desc + (size_t)p.src * 32);
+  const uint4 qa = __ldg(qd), qb = __ldg(qd + 1);
+  uint32_t* row = count_only ? nullptr : rows + row_off[i];
+  int cnt = 0;
+  grid_query(gv, k, p.u, p.v, p.radius, p.min_level, p.max_level, [&](bool ok, int idx) {
+    if (ok && p.use_ur && u_right) {
+      const float ur = u_right[idx];
+      if (ur > 0 && fabsf(__fsub_rn(p.ur, ur)) > p.radius) ok = false;  // :3571-3577
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (ok && !count_only) {
+      const uint4* tp = reinterpret_cast<const uint4*>(desc + (size_t)idx * 32);
+      const int dist = hamming256(qa, qb, __ldg(tp), __ldg(tp + 1));
+      row[cnt + __popc(m & ((1u << lane) - 1u))] = (uint32_t)dist << 16 | (uint32_t)idx;
+    }
+    cnt += __popc(m);
+  });
+  if (lane == 0 && count_only) row_cnt[i] = cnt;
+}
+
+// Ordered resolve, best match only (:3558-3637, :3886-3934): queries ascending; candidates that
+// already hold a point are skipped (any_point_blocks: a15 blocks on any held point, a14 only on
+// points with Observations()>0); accept best <= th_dist; rotation histogram + three maxima.
+__global__ void __launch_bounds__(32) k_query_resolve_best(const ProjQuery* __restrict__ q, const int* __restrict__ row_cnt,
+                                                           const int* __restrict__ row_off, const uint32_t* __restrict__ rows,
+                                                           int nq, int n, const orbx_keypoint* __restrict__ k, int th_dist,
+                                                           int check_ori, int any_point_blocks, int32_t* __restrict__ frame_mp,
+                                                           const int32_t* __restrict__ frame_mp_obs, uint8_t* __restrict__ held,
+                                                           int32_t* __restrict__ acc_idx, int32_t* __restrict__ acc_bin,
+                                                           int* __restrict__ nmatches_out) {
+  __shared__ int s_hist[HISTO_LENGTH];
+  const int lane = threadIdx.x;
+  for (int i = lane; i < n; i += 32)
+    held[i] = frame_mp[i] >= 0 && (any_point_blocks || (frame_mp_obs && frame_mp_obs[i] > 0)) ? 1 : 0;
+  if (lane < HISTO_LENGTH) s_hist[lane] = 0;
+  __syncwarp();
+  int nmatches = 0, nacc = 0;
+  for (int i = 0; i < nq; ++i) {
+    const int cnt = row_cnt[i];
+    if (cnt == 0) continue;
+    const uint32_t* row = rows + row_off[i];
+    uint32_t best = 0xFFFFFFFFu;
+    int my_idx = -1;
+    for (int c = lane; c < cnt; c += 32) {
+      const uint32_t e = row[c];
+      if (held[e & 0xFFFFu]) continue;
+      const uint32_t key = (e >> 16) << 16 | (uint32_t)c;  // dist, then traversal position (strict <)
+      if (key < best) { best = key; my_idx = (int)(e & 0xFFFFu); }
+    }
+    const uint32_t mine = best;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (best == 0xFFFFFFFFu) continue;
+    const int bestDist = (int)(best >> 16);
+    if (bestDist > th_dist) continue;
+    const unsigned owner = __ballot_sync(0xffffffffu, mine == best);
+    const int bestIdx = __shfl_sync(0xffffffffu, my_idx, __ffs(owner) - 1);
+    if (lane == 0) {
+      const ProjQuery p = q[i];
+      frame_mp[bestIdx] = p.src;
+      held[bestIdx] = any_point_blocks ? 1 : (p.obs ? 1 : 0);
+      if (check_ori) {
+        float rot = __fsub_rn(p.angle, k[bestIdx].angle);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
+        if (bin == HISTO_LENGTH) bin = 0;
+        acc_idx[nacc] = bestIdx;
+        acc_bin[nacc] = bin;
+        s_hist[bin]++;
+      }
+    }
+    ++nacc;
+    ++nmatches;
+    __syncwarp();
+  }
+  if (check_ori) {
+    __syncwarp();
+    int max1 = 0, max2 = 0, max3 = 0, i1_ = -1, i2_ = -1, i3_ = -1;  // every lane computes the same maxima
+    for (int i = 0; i < HISTO_LENGTH; ++i) {
+      const int sv = s_hist[i];
+      if (sv > max1) { max3 = max2; max2 = max1; max1 = sv; i3_ = i2_; i2_ = i1_; i1_ = i; }
+      else if (sv > max2) { max3 = max2; max2 = sv; i3_ = i2_; i2_ = i; }
+      else if (sv > max3) { max3 = sv; i3_ = i; }
+    }
+    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2_ = -1; i3_ = -1; }
+    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { i3_ = -1; }
+    int removed = 0;
+    for (int e = lane; e < nacc; e += 32) {
+      const int bin = acc_bin[e];
+      if (bin != i1_ && bin != i2_ && bin != i3_) { frame_mp[acc_idx[e]] = -1; ++removed; }  // :3627-3633
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+    nmatches -= removed;
+  }
+  if (lane == 0) *nmatches_out = nmatches;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -967,6 +1103,204 @@ int orbm_search_by_projection_points_host(orbm_matcher* m, const orbx_keypoint* 
   cudaMemcpyAsync(nmatches, misc + 1, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (!m->check(cudaStreamSynchronize(st), "search_by_projection")) return ORBX_E_CUDA;
   return m->check(cudaGetLastError(), "search_by_projection launch") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+// ---- pose-based SearchByProjection overloads ------------------------------------------------
+}  // extern "C" (helpers below are internal)
+#pragma GCC visibility pop
+namespace {
+
+// cv::Mat float algebra as OpenCV evaluates it for these tiny matrices (probed against cv2.gemm):
+// a product row is accumulated in float32 left to right from 0, then the addend is added.
+inline void mat3_mul_vec_add(const float* R, int rs, const float* x, const float* t, float alpha, float* out) {
+  for (int i = 0; i < 3; ++i) {
+    float s = 0.f;
+    for (int k = 0; k < 3; ++k) s += R[i * rs + k] * x[k];
+    s *= alpha;
+    out[i] = t ? s + t[i] : s;
+  }
+}
+inline void mat3t_mul_vec(const float* R, int rs, const float* x, float alpha, float* out) {
+  for (int i = 0; i < 3; ++i) {
+    float s = 0.f;
+    for (int k = 0; k < 3; ++k) s += R[k * rs + i] * x[k];
+    out[i] = s * alpha;
+  }
+}
+
+// Device side shared by the overloads: per-camera grids, candidates, ordered resolve.
+int run_projected(orbm_matcher* m, const orbx_keypoint* k, const uint8_t* desc, const float* u_right, const int32_t* cam_of,
+                  int n_cams, int n, orbm_bounds bounds, const std::vector<ProjQuery>& q, const uint8_t* src_desc, int n_src,
+                  int th_dist, int check_ori, int any_point_blocks, int32_t* frame_mp, const int32_t* frame_mp_obs,
+                  int* nmatches) {
+  *nmatches = 0;
+  const int nq = (int)q.size();
+  if (n == 0 || nq == 0) return ORBX_OK;
+  cudaSetDevice(m->device);
+  cudaStream_t st = m->stream;
+  const size_t frame_bytes = (size_t)n * (32 + sizeof(orbx_keypoint) + 4 + 4 + 4 + 4 + 1) + 256;
+  uint8_t* fb = m->scratch<uint8_t>(8, frame_bytes);
+  const size_t q_bytes = (size_t)n_src * 32 + (size_t)nq * (sizeof(ProjQuery) + 4 + 4 + 4 + 4) + 256;
+  uint8_t* qb = m->scratch<uint8_t>(9, q_bytes);
+  int* gstart = m->scratch<int>(4, (size_t)n_cams * (GRID_CELLS + 1));
+  uint16_t* gitems = m->scratch<uint16_t>(5, (size_t)n_cams * n);
+  int* misc = m->scratch<int>(10, 8);
+  if (!fb || !qb || !gstart || !gitems || !misc) return ORBX_E_CUDA;
+  uint8_t* dd = fb;
+  orbx_keypoint* dk = reinterpret_cast<orbx_keypoint*>(dd + (size_t)n * 32);
+  float* dur = reinterpret_cast<float*>(dk + n);
+  int32_t* dcam = reinterpret_cast<int32_t*>(dur + n);
+  int32_t* dfmp = dcam + n;
+  int32_t* dfobs = dfmp + n;
+  uint8_t* dheld = reinterpret_cast<uint8_t*>(dfobs + n);
+  uint8_t* dsd = qb;
+  ProjQuery* dq = reinterpret_cast<ProjQuery*>(dsd + (size_t)n_src * 32);
+  int* drow_cnt = reinterpret_cast<int*>(dq + nq);
+  int* drow_off = drow_cnt + nq;
+  int32_t* dacc_idx = drow_off + nq;
+  int32_t* dacc_bin = dacc_idx + nq;
+  cudaMemcpyAsync(dk, k, sizeof(orbx_keypoint) * n, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dd, desc, (size_t)n * 32, cudaMemcpyHostToDevice, st);
+  if (u_right) cudaMemcpyAsync(dur, u_right, sizeof(float) * n, cudaMemcpyHostToDevice, st);
+  if (cam_of) cudaMemcpyAsync(dcam, cam_of, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dfmp, frame_mp, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
+  if (frame_mp_obs) cudaMemcpyAsync(dfobs, frame_mp_obs, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dsd, src_desc, (size_t)n_src * 32, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dq, q.data(), sizeof(ProjQuery) * nq, cudaMemcpyHostToDevice, st);
+  for (int c = 0; c < n_cams; ++c) {
+    k_build_grid<<<1, 256, 0, st>>>(dk, nullptr, n, n, bounds, gstart + (size_t)c * (GRID_CELLS + 1), gitems + (size_t)c * n,
+                                    cam_of ? dcam : nullptr, c);
+    m->launches++;
+  }
+  const int blocks = (nq + 7) / 8;
+  k_query_candidates<<<blocks, 256, 0, st>>>(dk, dd, u_right ? dur : nullptr, bounds, gstart, gitems, n, dq, dsd, nq, 1,
+                                             drow_cnt, nullptr, nullptr);
+  k_scan_exclusive<<<1, 1024, 0, st>>>(drow_cnt, drow_off, nq, misc);
+  m->launches += 2;
+  int total = 0;
+  cudaMemcpyAsync(&total, misc, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (!m->check(cudaStreamSynchronize(st), "projected search (count)")) return ORBX_E_CUDA;
+  uint32_t* rows = m->scratch<uint32_t>(6, (size_t)total);
+  if (!rows) return ORBX_E_CUDA;
+  k_query_candidates<<<blocks, 256, 0, st>>>(dk, dd, u_right ? dur : nullptr, bounds, gstart, gitems, n, dq, dsd, nq, 0,
+                                             drow_cnt, drow_off, rows);
+  k_query_resolve_best<<<1, 32, 0, st>>>(dq, drow_cnt, drow_off, rows, nq, n, dk, th_dist, check_ori, any_point_blocks, dfmp,
+                                         frame_mp_obs ? dfobs : nullptr, dheld, dacc_idx, dacc_bin, misc + 1);
+  m->launches += 2;
+  cudaMemcpyAsync(frame_mp, dfmp, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(nmatches, misc + 1, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (!m->check(cudaStreamSynchronize(st), "projected search")) return ORBX_E_CUDA;
+  return m->check(cudaGetLastError(), "projected search launch") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int orbm_search_by_projection_frame_host(orbm_matcher* m, const orbx_keypoint* cur_k, const uint8_t* cur_desc,
+                                         const float* cur_uright, const int32_t* cur_cam, int n_cur, orbm_bounds b,
+                                         const float* scale_factors, int nlevels, orbm_camera cam, const float* Tcw_cur,
+                                         const float* Tcw_last, const orbx_keypoint* last_k, const int32_t* last_cam,
+                                         const int32_t* last_valid, const float* last_xyz, const uint8_t* last_desc,
+                                         const int32_t* last_obs, int n_last, const float* calib, float th, int mono,
+                                         int check_ori, int32_t* cur_mp, const int32_t* cur_mp_obs, int* nmatches) {
+  if (!m || !cur_k || !cur_desc || !scale_factors || !Tcw_cur || !Tcw_last || !calib || !cur_mp || !nmatches || n_cur < 0 ||
+      n_cur > 65535 || n_last < 0 || (n_last && (!last_k || !last_valid || !last_xyz || !last_desc)))
+    return ORBX_E_INVALID;
+  // host-side projection: src/ORBmatcher.cc:3464-3531, same float evaluation order
+  float Rcam21[9], tcam21[3];
+  for (int i = 0; i < 3; ++i)
+    for (int k = 0; k < 3; ++k) Rcam21[i * 3 + k] = calib[k * 3 + i];
+  mat3_mul_vec_add(Rcam21, 3, calib + 9, nullptr, -1.f, tcam21);
+  const float tcw[3] = {Tcw_cur[3], Tcw_cur[7], Tcw_cur[11]}, tlw[3] = {Tcw_last[3], Tcw_last[7], Tcw_last[11]};
+  float twc[3], tlc[3];
+  mat3t_mul_vec(Tcw_cur, 4, tcw, -1.f, twc);
+  mat3_mul_vec_add(Tcw_last, 4, twc, tlw, 1.f, tlc);
+  const bool fwd[2] = {tlc[2] > cam.mb && !mono, tlc[0] > cam.mb && !mono};
+  const bool bwd[2] = {-tlc[2] > cam.mb && !mono, -tlc[0] > cam.mb && !mono};
+  std::vector<ProjQuery> q;
+  q.reserve(n_last);
+  for (int i = 0; i < n_last; ++i) {
+    if (!last_valid[i]) continue;
+    const int c = last_cam ? last_cam[i] : 0;
+    if (c < 0 || c > 1 || last_k[i].octave < 0 || last_k[i].octave >= nlevels) { m->err = "bad camera / octave in last frame"; return ORBX_E_INVALID; }
+    float x3Dc[3];
+    mat3_mul_vec_add(Tcw_cur, 4, last_xyz + 3 * i, tcw, 1.f, x3Dc);
+    if (c == 1) {
+      float tmp[3];
+      mat3_mul_vec_add(Rcam21, 3, x3Dc, tcam21, 1.f, tmp);
+      x3Dc[0] = tmp[0]; x3Dc[1] = tmp[1]; x3Dc[2] = tmp[2];
+    }
+    const float xc = x3Dc[0], yc = x3Dc[1];
+    const float invzc = (float)(1.0 / x3Dc[2]);
+    if (invzc < 0) continue;
+    const float u = cam.fx * xc * invzc + cam.cx;
+    const float v = cam.fy * yc * invzc + cam.cy;
+    if (u < b.min_x || u > b.max_x) continue;
+    if (v < b.min_y || v > b.max_y) continue;
+    const int oct = last_k[i].octave;
+    ProjQuery p;
+    p.u = u; p.v = v;
+    p.radius = th * scale_factors[oct];
+    p.ur = u - cam.mbf * invzc;
+    p.use_ur = 1;
+    p.angle = last_k[i].angle;
+    if (fwd[c]) { p.min_level = oct; p.max_level = -1; }
+    else if (bwd[c]) { p.min_level = 0; p.max_level = oct; }
+    else { p.min_level = oct - 1; p.max_level = oct + 1; }
+    p.cam = c; p.src = i; p.obs = last_obs ? (last_obs[i] > 0) : 1;
+    q.push_back(p);
+  }
+  return run_projected(m, cur_k, cur_desc, cur_uright, cur_cam, 2, n_cur, b, q, last_desc, n_last, TH_HIGH, check_ori, 0,
+                       cur_mp, cur_mp_obs, nmatches);
+}
+
+int orbm_search_by_projection_keyframe_host(orbm_matcher* m, const orbx_keypoint* cur_k, const uint8_t* cur_desc, int n_cur,
+                                            orbm_bounds b, const float* scale_factors, int nlevels, float log_scale_factor,
+                                            orbm_camera cam, const float* Tcw_cur, const int32_t* kf_valid,
+                                            const float* kf_xyz, const float* kf_max_dist, const float* kf_min_dist,
+                                            const float* kf_max_d, const float* kf_angle, const uint8_t* kf_desc, int n_kf,
+                                            float th, int orb_dist, int check_ori, int32_t* cur_mp, int* nmatches) {
+  if (!m || !cur_k || !cur_desc || !scale_factors || !Tcw_cur || !cur_mp || !nmatches || n_cur < 0 || n_cur > 65535 ||
+      n_kf < 0 || nlevels < 1 || (n_kf && (!kf_valid || !kf_xyz || !kf_max_dist || !kf_min_dist || !kf_max_d || !kf_angle || !kf_desc)))
+    return ORBX_E_INVALID;
+  // host-side projection and scale prediction: src/ORBmatcher.cc:3814-3866, src/MapPoint.cc:602-617
+  const float tcw[3] = {Tcw_cur[3], Tcw_cur[7], Tcw_cur[11]};
+  float Ow[3];
+  mat3t_mul_vec(Tcw_cur, 4, tcw, -1.f, Ow);
+  std::vector<ProjQuery> q;
+  q.reserve(n_kf);
+  for (int i = 0; i < n_kf; ++i) {
+    if (!kf_valid[i]) continue;
+    const float* x3Dw = kf_xyz + 3 * i;
+    float x3Dc[3];
+    mat3_mul_vec_add(Tcw_cur, 4, x3Dw, tcw, 1.f, x3Dc);
+    const float xc = x3Dc[0], yc = x3Dc[1];
+    const float invzc = (float)(1.0 / x3Dc[2]);
+    const float u = cam.fx * xc * invzc + cam.cx;
+    const float v = cam.fy * yc * invzc + cam.cy;
+    if (u < b.min_x || u > b.max_x) continue;
+    if (v < b.min_y || v > b.max_y) continue;
+    double n2 = 0;
+    for (int k = 0; k < 3; ++k) { const float d = x3Dw[k] - Ow[k]; n2 += (double)d * (double)d; }
+    const float dist3D = (float)std::sqrt(n2);
+    if (dist3D < kf_min_dist[i] || dist3D > kf_max_dist[i]) continue;
+    const float ratio = kf_max_d[i] / dist3D;
+    int lvl = (int)std::ceil(std::log(ratio) / log_scale_factor);
+    if (lvl < 0) lvl = 0;
+    else if (lvl >= nlevels) lvl = nlevels - 1;
+    ProjQuery p;
+    p.u = u; p.v = v;
+    p.radius = th * scale_factors[lvl];
+    p.ur = 0.f; p.use_ur = 0;
+    p.angle = kf_angle[i];
+    p.min_level = lvl - 1; p.max_level = lvl + 1;
+    p.cam = 0; p.src = i; p.obs = 1;
+    q.push_back(p);
+  }
+  return run_projected(m, cur_k, cur_desc, nullptr, nullptr, 1, n_cur, b, q, kf_desc, n_kf, orb_dist, check_ori, 1, cur_mp,
+                       nullptr, nmatches);
 }
 
 #pragma GCC visibility pop

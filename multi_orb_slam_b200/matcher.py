@@ -11,7 +11,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import KP_DTYPE, MP_DTYPE, Bounds, check_m, lib
+from ._lib import KP_DTYPE, MP_DTYPE, Bounds, Camera, check_m, lib
 
 
 @dataclass
@@ -182,4 +182,51 @@ class ORBmatcher:
             None if obs is None else obs.ctypes.data, len(vpMapPoints.fields), float(th), self.mfNNratio,
             fmp.ctypes.data, None if fobs is None else fobs.ctypes.data, C.byref(nm)))
         F.mvpMapPoints = fmp
+        return nm.value
+
+    # -- SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono, CalibMatrix) ---
+    def SearchByProjectionFrame(self, cur: Frame, cur_cam, camera: Camera, Tcw_cur, Tcw_last, last_keys, last_cam,
+                                last_valid, last_xyz, last_desc, last_obs, calib, th: float, bMono: bool = False) -> int:
+        """src/ORBmatcher.cc:3448-3641 over flat arrays.  `cur` holds the concatenated keypoints of
+        all cameras (mvKeysUn_total / descriptors per global index / mvuRight_total); cur.mvpMapPoints
+        is updated in place with indices into the last-frame arrays.  Returns nmatches."""
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        i32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+        n, nl = cur.N, len(last_keys)
+        sf = f32(cur.mvScaleFactors)
+        ur = None if cur.mvuRight is None else f32(cur.mvuRight)
+        ccam, lcam, lval, lobs = i32(cur_cam), i32(last_cam), i32(last_valid), i32(last_obs)
+        fobs = i32(cur.mvpMapPointsObserved)
+        fmp = np.ascontiguousarray(cur.mvpMapPoints, dtype=np.int32)
+        lk = np.ascontiguousarray(last_keys, dtype=KP_DTYPE)
+        lxyz, ldesc = f32(last_xyz), np.ascontiguousarray(last_desc, dtype=np.uint8)
+        tc, tl, cal = f32(Tcw_cur), f32(Tcw_last), f32(calib)
+        p = lambda a: None if a is None else a.ctypes.data
+        nm = C.c_int(0)
+        check_m(self._h, lib.orbm_search_by_projection_frame_host(
+            self._h, cur.mvKeysUn.ctypes.data, cur.mDescriptors.ctypes.data, p(ur), p(ccam), n, cur.bounds, sf.ctypes.data,
+            len(sf), camera, tc.ctypes.data, tl.ctypes.data, lk.ctypes.data, p(lcam), lval.ctypes.data, lxyz.ctypes.data,
+            ldesc.ctypes.data, p(lobs), nl, cal.ctypes.data, float(th), int(bMono), int(self.mbCheckOrientation),
+            fmp.ctypes.data, p(fobs), C.byref(nm)))
+        cur.mvpMapPoints = fmp
+        return nm.value
+
+    # -- SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, sAlreadyFound, th, ORBdist) -----------
+    def SearchByProjectionKeyFrame(self, cur: Frame, camera: Camera, Tcw_cur, log_scale_factor: float, kf_valid, kf_xyz,
+                                   kf_max_dist, kf_min_dist, kf_max_d, kf_angle, kf_desc, th: float, ORBdist: int) -> int:
+        """src/ORBmatcher.cc:3809-3937 over flat arrays; cur.mvpMapPoints updated in place."""
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        sf = f32(cur.mvScaleFactors)
+        fmp = np.ascontiguousarray(cur.mvpMapPoints, dtype=np.int32)
+        val = np.ascontiguousarray(kf_valid, dtype=np.int32)
+        xyz, mx, mn, md, ang = f32(kf_xyz), f32(kf_max_dist), f32(kf_min_dist), f32(kf_max_d), f32(kf_angle)
+        desc = np.ascontiguousarray(kf_desc, dtype=np.uint8)
+        tc = f32(Tcw_cur)
+        nm = C.c_int(0)
+        check_m(self._h, lib.orbm_search_by_projection_keyframe_host(
+            self._h, cur.mvKeysUn.ctypes.data, cur.mDescriptors.ctypes.data, cur.N, cur.bounds, sf.ctypes.data, len(sf),
+            float(log_scale_factor), camera, tc.ctypes.data, val.ctypes.data, xyz.ctypes.data, mx.ctypes.data,
+            mn.ctypes.data, md.ctypes.data, ang.ctypes.data, desc.ctypes.data, len(val), float(th), int(ORBdist),
+            int(self.mbCheckOrientation), fmp.ctypes.data, C.byref(nm)))
+        cur.mvpMapPoints = fmp
         return nm.value

@@ -239,4 +239,194 @@ int om_search_by_projection_points(const oo_keypoint* k, const uint8_t* d, const
   return nmatches;
 }
 
+// ---- pose-based overloads ------------------------------------------------------------------
+// cv::Mat float algebra as OpenCV 4.13 evaluates it for these tiny matrices (probed against
+// cv2.gemm, tools/make_golden.py header): a product row is accumulated in float32 left to right
+// starting from 0, then the addend is added; cv::norm accumulates squares in double.
+namespace {
+inline void mat3_mul_vec_add(const float* R /*3x3 row-major, row stride rs*/, int rs, const float* x, const float* t,
+                             float alpha, float* out) {
+  for (int i = 0; i < 3; ++i) {
+    float s = 0.f;
+    for (int k = 0; k < 3; ++k) s += R[i * rs + k] * x[k];
+    s *= alpha;
+    out[i] = t ? s + t[i] : s;
+  }
+}
+inline void mat3t_mul_vec(const float* R, int rs, const float* x, float alpha, float* out) {  // alpha * R^T x
+  for (int i = 0; i < 3; ++i) {
+    float s = 0.f;
+    for (int k = 0; k < 3; ++k) s += R[k * rs + i] * x[k];
+    out[i] = s * alpha;
+  }
+}
+struct Grid2 {  // mGrids[c]: per-camera grids over the concatenated keypoints (src/Frame.cc:384-393)
+  Grid g0, g1;
+  Grid2(const float* x, const float* y, const int* oct, const int* cam, int n, om_bounds b)
+      : g0(x, y, oct, 0, b), g1(x, y, oct, 0, b) {
+    g0.kx = g1.kx = x; g0.ky = g1.ky = y; g0.koct = g1.koct = oct;
+    for (int i = 0; i < n; ++i) {
+      Grid& g = (cam && cam[i] == 1) ? g1 : g0;
+      const int px = (int)std::round((x[i] - g.min_x) * g.inv_w);
+      const int py = (int)std::round((y[i] - g.min_y) * g.inv_h);
+      if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;
+      g.cell[px][py].push_back(i);
+    }
+  }
+};
+}  // namespace
+
+// src/ORBmatcher.cc:3448-3641
+int om_search_by_projection_frame(const oo_keypoint* cur_k, const uint8_t* cur_desc, const float* cur_uright,
+                                  const int32_t* cur_cam, int n_cur, om_bounds b, const float* scale_factors,
+                                  int nlevels, om_camera cam, const float* Tcw_cur, const float* Tcw_last,
+                                  const oo_keypoint* last_k, const int32_t* last_cam, const int32_t* last_valid,
+                                  const float* last_xyz, const uint8_t* last_desc, const int32_t* last_obs,
+                                  int n_last, const float* calib, float th, int mono, int check_ori,
+                                  int32_t* cur_mp, const int32_t* cur_mp_obs) {
+  (void)nlevels;
+  int nmatches = 0;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  const float factor = 1.0f / HISTO_LENGTH;
+  // mRcam21 = Rcam12.t(); mtcam21 = -mRcam21 * tcam12  (:3464-3471)
+  float Rcam21[9], tcam21[3];
+  for (int i = 0; i < 3; ++i)
+    for (int k = 0; k < 3; ++k) Rcam21[i * 3 + k] = calib[k * 3 + i];
+  mat3_mul_vec_add(Rcam21, 3, calib + 9, nullptr, -1.f, tcam21);
+  float tcw[3] = {Tcw_cur[3], Tcw_cur[7], Tcw_cur[11]}, tlw[3] = {Tcw_last[3], Tcw_last[7], Tcw_last[11]};
+  float twc[3], tlc[3];
+  mat3t_mul_vec(Tcw_cur, 4, tcw, -1.f, twc);             // twc = -Rcw.t()*tcw
+  mat3_mul_vec_add(Tcw_last, 4, twc, tlw, 1.f, tlc);     // tlc = Rlw*twc+tlw
+  const bool fwd[2] = {tlc[2] > cam.mb && !mono, tlc[0] > cam.mb && !mono};
+  const bool bwd[2] = {-tlc[2] > cam.mb && !mono, -tlc[0] > cam.mb && !mono};
+  SoA s(cur_k, n_cur);
+  Grid2 grids(s.x.data(), s.y.data(), s.oct.data(), cur_cam, n_cur, b);
+  std::vector<char> held(n_cur, 0);
+  for (int i = 0; i < n_cur; ++i) held[i] = cur_mp[i] >= 0 && cur_mp_obs && cur_mp_obs[i] > 0;
+  std::vector<int> cand;
+  for (int i = 0; i < n_last; ++i) {
+    if (!last_valid[i]) continue;
+    const int c = last_cam ? last_cam[i] : 0;
+    float x3Dc[3];
+    mat3_mul_vec_add(Tcw_cur, 4, last_xyz + 3 * i, tcw, 1.f, x3Dc);  // Rcw*x3Dw+tcw
+    if (c == 1) {
+      float tmp[3];
+      mat3_mul_vec_add(Rcam21, 3, x3Dc, tcam21, 1.f, tmp);
+      x3Dc[0] = tmp[0]; x3Dc[1] = tmp[1]; x3Dc[2] = tmp[2];
+    }
+    const float xc = x3Dc[0], yc = x3Dc[1];
+    const float invzc = (float)(1.0 / x3Dc[2]);
+    if (invzc < 0) continue;
+    const float u = cam.fx * xc * invzc + cam.cx;
+    const float v = cam.fy * yc * invzc + cam.cy;
+    if (u < b.min_x || u > b.max_x) continue;
+    if (v < b.min_y || v > b.max_y) continue;
+    const int nLastOctave = last_k[i].octave;
+    const float radius = th * scale_factors[nLastOctave];
+    const Grid& g = c == 1 ? grids.g1 : grids.g0;
+    if (fwd[c]) g.query(u, v, radius, nLastOctave, -1, cand);           // default maxLevel = -1
+    else if (bwd[c]) g.query(u, v, radius, 0, nLastOctave, cand);
+    else g.query(u, v, radius, nLastOctave - 1, nLastOctave + 1, cand);
+    if (cand.empty()) continue;
+    int bestDist = 256, bestIdx2 = -1;
+    for (int i2 : cand) {
+      if (held[i2]) continue;
+      if (cur_uright && cur_uright[i2] > 0) {
+        const float ur = u - cam.mbf * invzc;
+        const float er = std::fabs(ur - cur_uright[i2]);
+        if (er > radius) continue;
+      }
+      const int dist = om_distance(last_desc + (size_t)i * 32, cur_desc + (size_t)i2 * 32);
+      if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+    }
+    if (bestDist <= TH_HIGH) {
+      cur_mp[bestIdx2] = i;
+      held[bestIdx2] = last_obs ? (last_obs[i] > 0) : 1;
+      nmatches++;
+      if (check_ori) {
+        float rot = last_k[i].angle - cur_k[bestIdx2].angle;
+        if (rot < 0.0) rot += 360.0f;
+        int bin = (int)std::round(rot * factor);
+        if (bin == HISTO_LENGTH) bin = 0;
+        rotHist[bin].push_back(bestIdx2);
+      }
+    }
+  }
+  if (check_ori) {
+    int counts[HISTO_LENGTH], i1, i2, i3;
+    for (int i = 0; i < HISTO_LENGTH; ++i) counts[i] = (int)rotHist[i].size();
+    om_three_maxima(counts, HISTO_LENGTH, &i1, &i2, &i3);
+    for (int i = 0; i < HISTO_LENGTH; ++i)
+      if (i != i1 && i != i2 && i != i3)
+        for (int idx : rotHist[i]) { cur_mp[idx] = -1; nmatches--; }
+  }
+  return nmatches;
+}
+
+// src/ORBmatcher.cc:3809-3937 (+ MapPoint::PredictScale, src/MapPoint.cc:602-617)
+int om_search_by_projection_keyframe(const oo_keypoint* cur_k, const uint8_t* cur_desc, int n_cur, om_bounds b,
+                                     const float* scale_factors, int nlevels, float log_scale_factor, om_camera cam,
+                                     const float* Tcw_cur, const int32_t* kf_valid, const float* kf_xyz,
+                                     const float* kf_max_dist, const float* kf_min_dist, const float* kf_max_d,
+                                     const float* kf_angle, const uint8_t* kf_desc, int n_kf, float th, int orb_dist,
+                                     int check_ori, int32_t* cur_mp) {
+  int nmatches = 0;
+  float tcw[3] = {Tcw_cur[3], Tcw_cur[7], Tcw_cur[11]}, Ow[3];
+  mat3t_mul_vec(Tcw_cur, 4, tcw, -1.f, Ow);  // Ow = -Rcw.t()*tcw
+  std::vector<int> rotHist[HISTO_LENGTH];
+  const float factor = 1.0f / HISTO_LENGTH;
+  SoA s(cur_k, n_cur);
+  Grid grid(s.x.data(), s.y.data(), s.oct.data(), n_cur, b);
+  std::vector<int> cand;
+  for (int i = 0; i < n_kf; ++i) {
+    if (!kf_valid[i]) continue;
+    const float* x3Dw = kf_xyz + 3 * i;
+    float x3Dc[3];
+    mat3_mul_vec_add(Tcw_cur, 4, x3Dw, tcw, 1.f, x3Dc);
+    const float xc = x3Dc[0], yc = x3Dc[1];
+    const float invzc = (float)(1.0 / x3Dc[2]);
+    const float u = cam.fx * xc * invzc + cam.cx;
+    const float v = cam.fy * yc * invzc + cam.cy;
+    if (u < b.min_x || u > b.max_x) continue;
+    if (v < b.min_y || v > b.max_y) continue;
+    double n2 = 0;
+    for (int k = 0; k < 3; ++k) { const float d = x3Dw[k] - Ow[k]; n2 += (double)d * (double)d; }
+    const float dist3D = (float)std::sqrt(n2);
+    if (dist3D < kf_min_dist[i] || dist3D > kf_max_dist[i]) continue;
+    const float ratio = kf_max_d[i] / dist3D;
+    int nPredictedLevel = (int)std::ceil(std::log(ratio) / log_scale_factor);
+    if (nPredictedLevel < 0) nPredictedLevel = 0;
+    else if (nPredictedLevel >= nlevels) nPredictedLevel = nlevels - 1;
+    const float radius = th * scale_factors[nPredictedLevel];
+    grid.query(u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1, cand);
+    if (cand.empty()) continue;
+    int bestDist = 256, bestIdx2 = -1;
+    for (int i2 : cand) {
+      if (cur_mp[i2] >= 0) continue;
+      const int dist = om_distance(kf_desc + (size_t)i * 32, cur_desc + (size_t)i2 * 32);
+      if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+    }
+    if (bestDist <= orb_dist) {
+      cur_mp[bestIdx2] = i;
+      nmatches++;
+      if (check_ori) {
+        float rot = kf_angle[i] - cur_k[bestIdx2].angle;
+        if (rot < 0.0) rot += 360.0f;
+        int bin = (int)std::round(rot * factor);
+        if (bin == HISTO_LENGTH) bin = 0;
+        rotHist[bin].push_back(bestIdx2);
+      }
+    }
+  }
+  if (check_ori) {
+    int counts[HISTO_LENGTH], i1, i2, i3;
+    for (int i = 0; i < HISTO_LENGTH; ++i) counts[i] = (int)rotHist[i].size();
+    om_three_maxima(counts, HISTO_LENGTH, &i1, &i2, &i3);
+    for (int i = 0; i < HISTO_LENGTH; ++i)
+      if (i != i1 && i != i2 && i != i3)
+        for (int idx : rotHist[i]) { cur_mp[idx] = -1; nmatches--; }
+  }
+  return nmatches;
+}
+
 }  // extern "C"

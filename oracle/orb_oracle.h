@@ -94,6 +94,42 @@ int om_search_by_projection_points(const oo_keypoint* k, const uint8_t* d, const
                                    int nmp, float th, float nnratio, int* frame_mp,
                                    const int* frame_mp_obs);
 
+// Flattened inputs of the pose-based SearchByProjection overloads.
+typedef struct {
+  float fx, fy, cx, cy, mb, mbf;  // Frame::fx.., mb (baseline), mbf
+} om_camera;
+
+// ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono, CalibMatrix)
+// (src/ORBmatcher.cc:3448-3641), the tracking matcher of the two-camera rig.
+//  current frame: keypoints of all cameras concatenated (mvKeysUn_total), descriptor per global
+//    index, u_right (mvuRight_total), cur_cam[i] (keypoint_to_cam), Tcw_cur (4x4 row-major),
+//    cur_mp (n_cur, in/out: index into the last-frame arrays or -1), cur_mp_obs (Observations()>0
+//    of the initially held points; may be NULL);
+//  last frame: Tcw_last, last_k (octave and angle used), last_cam, last_valid[i] = has a map point
+//    and is not an outlier, last_xyz (n_last x 3 world position), last_desc (MapPoint descriptor),
+//    last_obs (Observations()>0 of that point);
+//  calib: 4x3 row-major (rows 0-2 = R_cam12, row 3 = t_cam12; src/System.cc:63-72).
+int om_search_by_projection_frame(const oo_keypoint* cur_k, const uint8_t* cur_desc, const float* cur_uright,
+                                  const int32_t* cur_cam, int n_cur, om_bounds b, const float* scale_factors,
+                                  int nlevels, om_camera cam, const float* Tcw_cur, const float* Tcw_last,
+                                  const oo_keypoint* last_k, const int32_t* last_cam, const int32_t* last_valid,
+                                  const float* last_xyz, const uint8_t* last_desc, const int32_t* last_obs,
+                                  int n_last, const float* calib, float th, int mono, int check_ori,
+                                  int32_t* cur_mp, const int32_t* cur_mp_obs);
+
+// ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, sAlreadyFound, th, ORBdist)
+// (src/ORBmatcher.cc:3809-3937), relocalisation refinement (camera-1 data only).
+//  kf_valid[i] = map point exists, !isBad(), not in sAlreadyFound; kf_xyz world position;
+//  kf_max_dist / kf_min_dist = GetMaxDistanceInvariance() / GetMinDistanceInvariance();
+//  kf_max_d = mfMaxDistance (PredictScale, src/MapPoint.cc:602-617); kf_angle = pKF->mvKeysUn[i].angle;
+//  log_scale_factor = Frame::mfLogScaleFactor.  cur_mp (n_cur, in/out): any value >= 0 = occupied.
+int om_search_by_projection_keyframe(const oo_keypoint* cur_k, const uint8_t* cur_desc, int n_cur, om_bounds b,
+                                     const float* scale_factors, int nlevels, float log_scale_factor, om_camera cam,
+                                     const float* Tcw_cur, const int32_t* kf_valid, const float* kf_xyz,
+                                     const float* kf_max_dist, const float* kf_min_dist, const float* kf_max_d,
+                                     const float* kf_angle, const uint8_t* kf_desc, int n_kf, float th, int orb_dist,
+                                     int check_ori, int32_t* cur_mp);
+
 // ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:3948-3989) on bin counts.
 void om_three_maxima(const int* counts, int L, int* ind1, int* ind2, int* ind3);
 

@@ -222,6 +222,51 @@ def search_by_projection_points(k, d, u_right, bounds, scale_factors, mp, mp_des
     return nm, fmp
 
 
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("mb", C.c_float),
+                ("mbf", C.c_float)]
+
+
+def search_by_projection_frame(cur_k, cur_desc, cur_uright, cur_cam, bounds, sf, cam, Tcw_cur, Tcw_last, last_k, last_cam,
+                               last_valid, last_xyz, last_desc, last_obs, calib, th, mono, check_ori, cur_mp, cur_mp_obs):
+    lib = load("port")
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    cur_k, last_k = np.ascontiguousarray(cur_k, dtype=KP_DTYPE), np.ascontiguousarray(last_k, dtype=KP_DTYPE)
+    cur_desc, last_desc = np.ascontiguousarray(cur_desc, dtype=np.uint8), np.ascontiguousarray(last_desc, dtype=np.uint8)
+    ur, sf, tc, tl, xyz, cal = f32(cur_uright), f32(sf), f32(Tcw_cur), f32(Tcw_last), f32(last_xyz), f32(calib)
+    ccam, lcam, lval, lobs, fobs = i32(cur_cam), i32(last_cam), i32(last_valid), i32(last_obs), i32(cur_mp_obs)
+    fmp = i32(cur_mp).copy()
+    f = lib.om_search_by_projection_frame
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p] * 4 + [C.c_int, Bounds, C.c_void_p, C.c_int, Camera] + [C.c_void_p] * 8 + \
+                 [C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    nm = f(cur_k.ctypes.data, cur_desc.ctypes.data, ur.ctypes.data, ccam.ctypes.data, len(cur_k), Bounds(*bounds),
+           sf.ctypes.data, len(sf), Camera(*cam), tc.ctypes.data, tl.ctypes.data, last_k.ctypes.data, lcam.ctypes.data,
+           lval.ctypes.data, xyz.ctypes.data, last_desc.ctypes.data, lobs.ctypes.data, len(last_k), cal.ctypes.data, th,
+           int(mono), int(check_ori), fmp.ctypes.data, fobs.ctypes.data)
+    return nm, fmp
+
+
+def search_by_projection_keyframe(cur_k, cur_desc, bounds, sf, log_sf, cam, Tcw_cur, kf_valid, kf_xyz, kf_max_dist,
+                                  kf_min_dist, kf_max_d, kf_angle, kf_desc, th, orb_dist, check_ori, cur_mp):
+    lib = load("port")
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    cur_k = np.ascontiguousarray(cur_k, dtype=KP_DTYPE)
+    cur_desc, kf_desc = np.ascontiguousarray(cur_desc, dtype=np.uint8), np.ascontiguousarray(kf_desc, dtype=np.uint8)
+    sf, tc, xyz, mx, mn, md, ang = f32(sf), f32(Tcw_cur), f32(kf_xyz), f32(kf_max_dist), f32(kf_min_dist), f32(kf_max_d), f32(kf_angle)
+    val = np.ascontiguousarray(kf_valid, dtype=np.int32)
+    fmp = np.ascontiguousarray(cur_mp, dtype=np.int32).copy()
+    f = lib.om_search_by_projection_keyframe
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, Bounds, C.c_void_p, C.c_int, C.c_float, Camera] + [C.c_void_p] * 8 + \
+                 [C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p]
+    nm = f(cur_k.ctypes.data, cur_desc.ctypes.data, len(cur_k), Bounds(*bounds), sf.ctypes.data, len(sf), log_sf,
+           Camera(*cam), tc.ctypes.data, val.ctypes.data, xyz.ctypes.data, mx.ctypes.data, mn.ctypes.data, md.ctypes.data,
+           ang.ctypes.data, kf_desc.ctypes.data, len(val), th, orb_dist, int(check_ori), fmp.ctypes.data)
+    return nm, fmp
+
+
 def three_maxima(counts):
     lib = load("port")
     c = np.ascontiguousarray(counts, dtype=np.int32)
