@@ -238,6 +238,21 @@ int orbm_search_by_projection_keyframe_host(orbm_matcher* m, const orbx_keypoint
                                             const float* kf_max_d, const float* kf_angle, const uint8_t* kf_desc, int n_kf,
                                             float th, int orb_dist, int check_ori, int32_t* cur_mp, int* nmatches);
 
+/* ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, vpPoints, vLoopMPCams, vpMatched, th, CalibMatrix)
+ * (src/ORBmatcher.cc:566-752) — loop-closing search (src/LoopClosing.cc:536): every map point is
+ * projected through the Sim3 into BOTH cameras of the key frame, best candidate over cameras,
+ * TH_LOW.  Key frame: concatenated keypoints (mvKeysUn_total), descriptor per global index, kf_cam
+ * (keypoint_to_cam); matched (n_kf, in/out: index into the point arrays or -1 = vpMatched).
+ * Points: mp_valid[i] = !isBad() && not already in vpMatched; GetWorldPos, GetNormal,
+ * Get{Max,Min}DistanceInvariance, mfMaxDistance, GetDescriptor.  Scw 4x4 row-major. */
+int orbm_search_by_projection_sim3_host(orbm_matcher* m, const orbx_keypoint* kf_k, const uint8_t* kf_desc,
+                                        const int32_t* kf_cam, int n_kf, orbm_bounds b, const float* scale_factors,
+                                        int nlevels, float log_scale_factor, orbm_camera cam, const float* Scw,
+                                        const float* calib, const int32_t* mp_valid, const float* mp_xyz,
+                                        const float* mp_normal, const float* mp_max_dist, const float* mp_min_dist,
+                                        const float* mp_max_d, const uint8_t* mp_desc, int n_mp, int th, int32_t* matched,
+                                        int* nmatches);
+
 #ifdef __cplusplus
 }
 #endif

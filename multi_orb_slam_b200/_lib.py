@@ -86,6 +86,8 @@ _SIGS = {
                                                  _vp, _vp, _vp, _vp, _i, _vp, _f, _i, _i, _vp, _vp, C.POINTER(_i)]),
     "orbm_search_by_projection_keyframe_host": (_i, [_vp, _vp, _vp, _i, Bounds, _vp, _i, _f, Camera, _vp, _vp, _vp, _vp, _vp,
                                                     _vp, _vp, _vp, _i, _f, _i, _i, _vp, C.POINTER(_i)]),
+    "orbm_search_by_projection_sim3_host": (_i, [_vp, _vp, _vp, _vp, _i, Bounds, _vp, _i, _f, Camera, _vp, _vp, _vp, _vp, _vp,
+                                                _vp, _vp, _vp, _vp, _i, _i, _vp, C.POINTER(_i)]),
 }
 EXPORTS = tuple(_SIGS)
 for _name, (_res, _args) in _SIGS.items():

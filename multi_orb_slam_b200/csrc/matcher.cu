@@ -745,28 +745,40 @@ __global__ void __launch_bounds__(32) k_query_resolve_best(const ProjQuery* __re
   if (lane < HISTO_LENGTH) s_hist[lane] = 0;
   __syncwarp();
   int nmatches = 0, nacc = 0;
-  for (int i = 0; i < nq; ++i) {
-    const int cnt = row_cnt[i];
-    if (cnt == 0) continue;
-    const uint32_t* row = rows + row_off[i];
-    uint32_t best = 0xFFFFFFFFu;
-    int my_idx = -1;
-    for (int c = lane; c < cnt; c += 32) {
-      const uint32_t e = row[c];
-      if (held[e & 0xFFFFu]) continue;
-      const uint32_t key = (e >> 16) << 16 | (uint32_t)c;  // dist, then traversal position (strict <)
-      if (key < best) { best = key; my_idx = (int)(e & 0xFFFFu); }
-    }
-    const uint32_t mine = best;
+  // Consecutive queries with the same source point form one group (the Sim3 overload projects a
+  // point into both cameras and keeps the best over cameras, :629-735); elsewhere groups are single.
+  for (int i = 0; i < nq;) {
+    const int src = q[i].src;
+    uint32_t gbest = 0xFFFFFFFFu;  // dist << 16 | (anything): only the distance decides across rows (strict <)
+    int gidx = -1, glast = i;
+    for (; glast < nq && q[glast].src == src; ++glast) {
+      const int cnt = row_cnt[glast];
+      if (cnt == 0) continue;
+      const uint32_t* row = rows + row_off[glast];
+      uint32_t best = 0xFFFFFFFFu;
+      int my_idx = -1;
+      for (int c = lane; c < cnt; c += 32) {
+        const uint32_t e = row[c];
+        if (held[e & 0xFFFFu]) continue;
+        const uint32_t key = (e >> 16) << 16 | (uint32_t)c;  // dist, then traversal position (strict <)
+        if (key < best) { best = key; my_idx = (int)(e & 0xFFFFu); }
+      }
+      const uint32_t mine = best;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if (best == 0xFFFFFFFFu) continue;
-    const int bestDist = (int)(best >> 16);
+      for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+      if (best == 0xFFFFFFFFu) continue;
+      const unsigned owner = __ballot_sync(0xffffffffu, mine == best);
+      const int row_idx = __shfl_sync(0xffffffffu, my_idx, __ffs(owner) - 1);
+      if ((best >> 16) < (gbest >> 16) || gbest == 0xFFFFFFFFu) { gbest = best; gidx = row_idx; }
+    }
+    const int qi = i;
+    i = glast;
+    if (gbest == 0xFFFFFFFFu) continue;
+    const int bestDist = (int)(gbest >> 16);
     if (bestDist > th_dist) continue;
-    const unsigned owner = __ballot_sync(0xffffffffu, mine == best);
-    const int bestIdx = __shfl_sync(0xffffffffu, my_idx, __ffs(owner) - 1);
+    const int bestIdx = gidx;
     if (lane == 0) {
-      const ProjQuery p = q[i];
+      const ProjQuery p = q[qi];
       frame_mp[bestIdx] = p.src;
       held[bestIdx] = any_point_blocks ? 1 : (p.obs ? 1 : 0);
       if (check_ori) {
@@ -1301,6 +1313,86 @@ int orbm_search_by_projection_keyframe_host(orbm_matcher* m, const orbx_keypoint
   }
   return run_projected(m, cur_k, cur_desc, nullptr, nullptr, 1, n_cur, b, q, kf_desc, n_kf, orb_dist, check_ori, 1, cur_mp,
                        nullptr, nmatches);
+}
+
+int orbm_search_by_projection_sim3_host(orbm_matcher* m, const orbx_keypoint* kf_k, const uint8_t* kf_desc,
+                                        const int32_t* kf_cam, int n_kf, orbm_bounds b, const float* scale_factors,
+                                        int nlevels, float log_scale_factor, orbm_camera cam, const float* Scw,
+                                        const float* calib, const int32_t* mp_valid, const float* mp_xyz,
+                                        const float* mp_normal, const float* mp_max_dist, const float* mp_min_dist,
+                                        const float* mp_max_d, const uint8_t* mp_desc, int n_mp, int th, int32_t* matched,
+                                        int* nmatches) {
+  if (!m || !kf_k || !kf_desc || !scale_factors || !Scw || !calib || !matched || !nmatches || n_kf < 0 || n_kf > 65535 ||
+      n_mp < 0 || nlevels < 1 ||
+      (n_mp && (!mp_valid || !mp_xyz || !mp_normal || !mp_max_dist || !mp_min_dist || !mp_max_d || !mp_desc)))
+    return ORBX_E_INVALID;
+  // host-side projection into both cameras: src/ORBmatcher.cc:581-704, same evaluation order
+  float Rcam21[9], tcam21[3];
+  {
+    double S[9];
+    for (int i = 0; i < 9; ++i) S[i] = calib[i];
+    double d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
+    d = 1. / d;  // cv::Mat::inv() of a 3x3 CV_32F matrix: closed form in double
+    Rcam21[0] = (float)((S[4] * S[8] - S[5] * S[7]) * d); Rcam21[1] = (float)((S[2] * S[7] - S[1] * S[8]) * d);
+    Rcam21[2] = (float)((S[1] * S[5] - S[2] * S[4]) * d); Rcam21[3] = (float)((S[5] * S[6] - S[3] * S[8]) * d);
+    Rcam21[4] = (float)((S[0] * S[8] - S[2] * S[6]) * d); Rcam21[5] = (float)((S[2] * S[3] - S[0] * S[5]) * d);
+    Rcam21[6] = (float)((S[3] * S[7] - S[4] * S[6]) * d); Rcam21[7] = (float)((S[1] * S[6] - S[0] * S[7]) * d);
+    Rcam21[8] = (float)((S[0] * S[4] - S[1] * S[3]) * d);
+  }
+  mat3_mul_vec_add(Rcam21, 3, calib + 9, nullptr, -1.f, tcam21);
+  double ss = 0;
+  for (int k = 0; k < 3; ++k) ss += (double)Scw[k] * (double)Scw[k];
+  const float scw = (float)std::sqrt(ss);
+  const float inv_s = (float)(1.0 / scw);
+  float Rcw[16] = {0}, tcw[3], Ow[3];
+  for (int i = 0; i < 3; ++i) {
+    for (int k = 0; k < 3; ++k) Rcw[i * 4 + k] = Scw[i * 4 + k] * inv_s;
+    tcw[i] = Scw[i * 4 + 3] * inv_s;
+  }
+  mat3t_mul_vec(Rcw, 4, tcw, -1.f, Ow);
+  std::vector<ProjQuery> q;
+  q.reserve(2 * (size_t)n_mp);
+  for (int i = 0; i < n_mp; ++i) {
+    if (!mp_valid[i]) continue;
+    const float* p3Dw = mp_xyz + 3 * i;
+    for (int camidx = 0; camidx < 2; ++camidx) {
+      float p3Dc[3];
+      mat3_mul_vec_add(Rcw, 4, p3Dw, tcw, 1.f, p3Dc);
+      if (camidx == 1) {
+        float tmp[3];
+        mat3_mul_vec_add(Rcam21, 3, p3Dc, tcam21, 1.f, tmp);
+        p3Dc[0] = tmp[0]; p3Dc[1] = tmp[1]; p3Dc[2] = tmp[2];
+      }
+      if (p3Dc[2] < 0.0) continue;
+      const float invz = 1 / p3Dc[2];
+      const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
+      const float u = cam.fx * x + cam.cx, v = cam.fy * y + cam.cy;
+      if (!(u >= b.min_x && u < b.max_x && v >= b.min_y && v < b.max_y)) continue;
+      float PO[3];
+      double n2 = 0, dotn = 0;
+      for (int k = 0; k < 3; ++k) {
+        PO[k] = p3Dw[k] - Ow[k];
+        n2 += (double)PO[k] * (double)PO[k];
+        dotn += (double)PO[k] * (double)mp_normal[3 * i + k];
+      }
+      const float dist = (float)std::sqrt(n2);
+      if (dist < mp_min_dist[i] || dist > mp_max_dist[i]) continue;
+      if (dotn < 0.5 * dist) continue;
+      const float ratio = mp_max_d[i] / dist;
+      int lvl = (int)std::ceil(std::log(ratio) / log_scale_factor);
+      if (lvl < 0) lvl = 0;
+      else if (lvl >= nlevels) lvl = nlevels - 1;
+      ProjQuery p;
+      p.u = u; p.v = v;
+      p.radius = th * scale_factors[lvl];
+      p.ur = 0.f; p.use_ur = 0; p.angle = 0.f;
+      p.min_level = lvl - 1; p.max_level = lvl;  // the post-filter of :716-718 folded into the query
+      p.cam = camidx; p.src = i; p.obs = 1;
+      q.push_back(p);
+    }
+  }
+  return run_projected(m, kf_k, kf_desc, nullptr, kf_cam, 2, n_kf, b, q, mp_desc, n_mp, TH_LOW, 0, 1, matched, nullptr,
+                       nmatches);
 }
 
 #pragma GCC visibility pop

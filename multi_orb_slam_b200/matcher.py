@@ -230,3 +230,24 @@ class ORBmatcher:
             int(self.mbCheckOrientation), fmp.ctypes.data, C.byref(nm)))
         cur.mvpMapPoints = fmp
         return nm.value
+
+    # -- SearchByProjection(KeyFrame*, Scw, vpPoints, vLoopMPCams, vpMatched, th, CalibMatrix) -------
+    def SearchByProjectionSim3(self, kf: Frame, kf_cam, camera: Camera, log_scale_factor: float, Scw, calib, mp_valid, mp_xyz,
+                               mp_normal, mp_max_dist, mp_min_dist, mp_max_d, mp_desc, th: int) -> int:
+        """src/ORBmatcher.cc:566-752 over flat arrays; kf.mvpMapPoints plays vpMatched (updated in place)."""
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        sf = f32(kf.mvScaleFactors)
+        cam_of = np.ascontiguousarray(kf_cam, dtype=np.int32)
+        matched = np.ascontiguousarray(kf.mvpMapPoints, dtype=np.int32)
+        val = np.ascontiguousarray(mp_valid, dtype=np.int32)
+        xyz, nrm, mx, mn, md = f32(mp_xyz), f32(mp_normal), f32(mp_max_dist), f32(mp_min_dist), f32(mp_max_d)
+        desc = np.ascontiguousarray(mp_desc, dtype=np.uint8)
+        S, cal = f32(Scw), f32(calib)
+        nm = C.c_int(0)
+        check_m(self._h, lib.orbm_search_by_projection_sim3_host(
+            self._h, kf.mvKeysUn.ctypes.data, kf.mDescriptors.ctypes.data, cam_of.ctypes.data, kf.N, kf.bounds, sf.ctypes.data,
+            len(sf), float(log_scale_factor), camera, S.ctypes.data, cal.ctypes.data, val.ctypes.data, xyz.ctypes.data,
+            nrm.ctypes.data, mx.ctypes.data, mn.ctypes.data, md.ctypes.data, desc.ctypes.data, len(val), int(th),
+            matched.ctypes.data, C.byref(nm)))
+        kf.mvpMapPoints = matched
+        return nm.value

@@ -429,4 +429,87 @@ int om_search_by_projection_keyframe(const oo_keypoint* cur_k, const uint8_t* cu
   return nmatches;
 }
 
+// src/ORBmatcher.cc:566-752.  cv::Mat::inv() of the 3x3 float matrix = OpenCV's closed form in
+// double (pinned against cv2.invert); Mat::dot and cv::norm accumulate in double; A/s is taken as
+// A * (float)(1/s) (OpenCV's scaled convertTo) — the last three are NOT pinnable from Python.
+int om_search_by_projection_sim3(const oo_keypoint* kf_k, const uint8_t* kf_desc, const int32_t* kf_cam, int n_kf,
+                                 om_bounds b, const float* scale_factors, int nlevels, float log_scale_factor,
+                                 om_camera cam, const float* Scw, const float* calib, const int32_t* mp_valid,
+                                 const float* mp_xyz, const float* mp_normal, const float* mp_max_dist,
+                                 const float* mp_min_dist, const float* mp_max_d, const uint8_t* mp_desc, int n_mp,
+                                 int th, int32_t* matched) {
+  float Rcam21[9], tcam21[3];
+  {
+    double S[9];
+    for (int i = 0; i < 9; ++i) S[i] = calib[i];
+    double d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
+    d = 1. / d;
+    Rcam21[0] = (float)((S[4] * S[8] - S[5] * S[7]) * d); Rcam21[1] = (float)((S[2] * S[7] - S[1] * S[8]) * d);
+    Rcam21[2] = (float)((S[1] * S[5] - S[2] * S[4]) * d); Rcam21[3] = (float)((S[5] * S[6] - S[3] * S[8]) * d);
+    Rcam21[4] = (float)((S[0] * S[8] - S[2] * S[6]) * d); Rcam21[5] = (float)((S[2] * S[3] - S[0] * S[5]) * d);
+    Rcam21[6] = (float)((S[3] * S[7] - S[4] * S[6]) * d); Rcam21[7] = (float)((S[1] * S[6] - S[0] * S[7]) * d);
+    Rcam21[8] = (float)((S[0] * S[4] - S[1] * S[3]) * d);
+  }
+  mat3_mul_vec_add(Rcam21, 3, calib + 9, nullptr, -1.f, tcam21);
+  double ss = 0;
+  for (int k = 0; k < 3; ++k) ss += (double)Scw[k] * (double)Scw[k];
+  const float scw = (float)std::sqrt(ss);
+  const float inv_s = (float)(1.0 / scw);
+  float Rcw[16] = {0}, tcw[3], Ow[3];
+  for (int i = 0; i < 3; ++i) {
+    for (int k = 0; k < 3; ++k) Rcw[i * 4 + k] = Scw[i * 4 + k] * inv_s;
+    tcw[i] = Scw[i * 4 + 3] * inv_s;
+  }
+  mat3t_mul_vec(Rcw, 4, tcw, -1.f, Ow);
+  SoA s(kf_k, n_kf);
+  Grid2 grids(s.x.data(), s.y.data(), s.oct.data(), kf_cam, n_kf, b);
+  int nmatches = 0;
+  std::vector<int> cand;
+  for (int i = 0; i < n_mp; ++i) {
+    if (!mp_valid[i]) continue;
+    const float* p3Dw = mp_xyz + 3 * i;
+    int bestDist = 256, bestIdxs = -1;
+    for (int camidx = 0; camidx < 2; ++camidx) {
+      float p3Dc[3];
+      mat3_mul_vec_add(Rcw, 4, p3Dw, tcw, 1.f, p3Dc);
+      if (camidx == 1) {
+        float tmp[3];
+        mat3_mul_vec_add(Rcam21, 3, p3Dc, tcam21, 1.f, tmp);
+        p3Dc[0] = tmp[0]; p3Dc[1] = tmp[1]; p3Dc[2] = tmp[2];
+      }
+      if (p3Dc[2] < 0.0) continue;
+      const float invz = 1 / p3Dc[2];
+      const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
+      const float u = cam.fx * x + cam.cx, v = cam.fy * y + cam.cy;
+      if (!(u >= b.min_x && u < b.max_x && v >= b.min_y && v < b.max_y)) continue;  // KeyFrame::IsInImage
+      float PO[3];
+      double n2 = 0, dotn = 0;
+      for (int k = 0; k < 3; ++k) {
+        PO[k] = p3Dw[k] - Ow[k];
+        n2 += (double)PO[k] * (double)PO[k];
+        dotn += (double)PO[k] * (double)mp_normal[3 * i + k];
+      }
+      const float dist = (float)std::sqrt(n2);
+      if (dist < mp_min_dist[i] || dist > mp_max_dist[i]) continue;
+      if (dotn < 0.5 * dist) continue;
+      const float ratio = mp_max_d[i] / dist;
+      int lvl = (int)std::ceil(std::log(ratio) / log_scale_factor);
+      if (lvl < 0) lvl = 0;
+      else if (lvl >= nlevels) lvl = nlevels - 1;
+      const float radius = th * scale_factors[lvl];
+      const Grid& g = camidx == 1 ? grids.g1 : grids.g0;
+      g.query(u, v, radius, -1, -1, cand);
+      for (int idx : cand) {
+        if (matched[idx] >= 0) continue;
+        const int kpLevel = kf_k[idx].octave;
+        if (kpLevel < lvl - 1 || kpLevel > lvl) continue;
+        const int dd = om_distance(mp_desc + (size_t)i * 32, kf_desc + (size_t)idx * 32);
+        if (dd < bestDist) { bestDist = dd; bestIdxs = idx; }
+      }
+    }
+    if (bestDist <= TH_LOW) { matched[bestIdxs] = i; nmatches++; }
+  }
+  return nmatches;
+}
+
 }  // extern "C"

@@ -130,6 +130,20 @@ int om_search_by_projection_keyframe(const oo_keypoint* cur_k, const uint8_t* cu
                                      const float* kf_angle, const uint8_t* kf_desc, int n_kf, float th, int orb_dist,
                                      int check_ori, int32_t* cur_mp);
 
+// ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, vpPoints, vLoopMPCams, vpMatched, th, CalibMatrix)
+// (src/ORBmatcher.cc:566-752): loop-closing search in BOTH cameras of the key frame, best over cameras.
+//  key frame: concatenated keypoints (mvKeysUn_total), descriptor per global index, kf_cam
+//    (keypoint_to_cam), matched (n_kf, in/out: index into the point arrays or -1 = vpMatched);
+//  points: mp_valid[i] = !isBad() && not already in vpMatched; world position, normal
+//    (GetNormal), GetMax/MinDistanceInvariance, mfMaxDistance, descriptor;
+//  Scw: 4x4 row-major Sim3 (s*R | t); calib as above; log_scale_factor = KeyFrame::mfLogScaleFactor.
+int om_search_by_projection_sim3(const oo_keypoint* kf_k, const uint8_t* kf_desc, const int32_t* kf_cam, int n_kf,
+                                 om_bounds b, const float* scale_factors, int nlevels, float log_scale_factor,
+                                 om_camera cam, const float* Scw, const float* calib, const int32_t* mp_valid,
+                                 const float* mp_xyz, const float* mp_normal, const float* mp_max_dist,
+                                 const float* mp_min_dist, const float* mp_max_d, const uint8_t* mp_desc, int n_mp,
+                                 int th, int32_t* matched);
+
 // ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:3948-3989) on bin counts.
 void om_three_maxima(const int* counts, int L, int* ind1, int* ind2, int* ind3);
 

@@ -267,6 +267,25 @@ def search_by_projection_keyframe(cur_k, cur_desc, bounds, sf, log_sf, cam, Tcw_
     return nm, fmp
 
 
+def search_by_projection_sim3(kf_k, kf_desc, kf_cam, bounds, sf, log_sf, cam, Scw, calib, mp_valid, mp_xyz, mp_normal,
+                              mp_max_dist, mp_min_dist, mp_max_d, mp_desc, th, matched):
+    lib = load("port")
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    kf_k = np.ascontiguousarray(kf_k, dtype=KP_DTYPE)
+    kf_desc, mp_desc = np.ascontiguousarray(kf_desc, dtype=np.uint8), np.ascontiguousarray(mp_desc, dtype=np.uint8)
+    kcam, val = np.ascontiguousarray(kf_cam, dtype=np.int32), np.ascontiguousarray(mp_valid, dtype=np.int32)
+    sf, S, cal, xyz, nrm, mx, mn, md = (f32(a) for a in (sf, Scw, calib, mp_xyz, mp_normal, mp_max_dist, mp_min_dist, mp_max_d))
+    out = np.ascontiguousarray(matched, dtype=np.int32).copy()
+    f = lib.om_search_by_projection_sim3
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, Bounds, C.c_void_p, C.c_int, C.c_float, Camera] + \
+                 [C.c_void_p] * 9 + [C.c_int, C.c_int, C.c_void_p]
+    nm = f(kf_k.ctypes.data, kf_desc.ctypes.data, kcam.ctypes.data, len(kf_k), Bounds(*bounds), sf.ctypes.data, len(sf), log_sf,
+           Camera(*cam), S.ctypes.data, cal.ctypes.data, val.ctypes.data, xyz.ctypes.data, nrm.ctypes.data, mx.ctypes.data,
+           mn.ctypes.data, md.ctypes.data, mp_desc.ctypes.data, len(val), int(th), out.ctypes.data)
+    return nm, out
+
+
 def three_maxima(counts):
     lib = load("port")
     c = np.ascontiguousarray(counts, dtype=np.int32)

@@ -303,3 +303,35 @@ def test_search_by_projection_keyframe_vs_oracle(O, th, orb_dist, check_ori):
     gn = m.SearchByProjectionKeyFrame(F, Camera(*CAM), s["Tcw"], log_sf, valid, xyz, kf_max, kf_min, max_d, ang, desc, th, orb_dist)
     assert gn == rn and np.array_equal(F.mvpMapPoints, rfmp)
     assert rn > 100
+
+
+@pytest.mark.parametrize("th,scale", [(10, 1.0), (4, 1.7)])
+def test_search_by_projection_sim3_vs_oracle(O, th, scale):
+    from multi_orb_slam_b200._lib import Camera
+    from multi_orb_slam_b200.matcher import Frame, ORBmatcher
+    s = _rig_scene(O, 13, 1800, (0, 0, 0))
+    rng = s["rng"]
+    n, nmp = s["n"], len(s["last_xyz"])
+    sf = O.extractor("port").scale_tables()[0]
+    Scw = s["Tcw"].astype(np.float64).copy()
+    Scw[:3, :] *= scale                          # Sim3: s*R | s*t ; map points live in the scaled world
+    xyz = s["last_xyz"].astype(np.float64)
+    Ow = -s["Tcw"][:3, :3].T.astype(np.float64) @ s["Tcw"][:3, 3].astype(np.float64)
+    PO = xyz - Ow
+    dist = np.linalg.norm(PO, axis=1)
+    normal = PO / dist[:, None] + rng.normal(0, 0.3, (nmp, 3))
+    normal /= np.linalg.norm(normal, axis=1)[:, None]
+    max_d = (dist * rng.uniform(0.8, 4.0, nmp)).astype(np.float32)
+    kf_max, kf_min = (1.2 * max_d).astype(np.float32), (0.8 * max_d / 1.2 ** 7).astype(np.float32)
+    valid = (rng.random(nmp) < 0.9).astype(np.int32)
+    matched0 = np.full(n, -1, np.int32)
+    matched0[rng.random(n) < 0.1] = 3
+    log_sf = float(np.log(np.float32(1.2)))
+    rn, rout = O.search_by_projection_sim3(s["cur_k"], s["cur_d"], s["cur_cam"], (0, 640, 0, 480), sf, log_sf, CAM, Scw, CALIB,
+                                           valid, xyz, normal, kf_max, kf_min, max_d, s["last_desc"], th, matched0)
+    F = Frame(s["cur_k"], s["cur_d"], 640, 480, mvScaleFactors=sf, mvpMapPoints=matched0.copy())
+    m = ORBmatcher(0.9, True)
+    gn = m.SearchByProjectionSim3(F, s["cur_cam"], Camera(*CAM), log_sf, Scw, CALIB, valid, xyz, normal, kf_max, kf_min, max_d,
+                                  s["last_desc"], th)
+    assert gn == rn and np.array_equal(F.mvpMapPoints, rout)
+    assert rn > 50
