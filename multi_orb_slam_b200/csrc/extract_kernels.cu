@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) k_pyr_resize(int level, const OrbGeom* __
 
 // ------------------------------------------------------------------------------------------
 // K3 per-cell FAST-9/16 with NMS and the iniThFAST -> minThFAST fallback (:790-830).
-// One CTA (4 warps) per (cell, frame).  The arc measure m = max over the 16 cyclic 9-arcs of
+// One CTA (FAST_NT threads = one warp) per (cell, frame).  The arc measure m = max over the 16 cyclic 9-arcs of
 // min(+-diff) is threshold independent: corner iff m > th, score m-1 (OpenCV cornerScore<16>);
 // a corner survives the 3x3 NMS iff its m is strictly greater than its 8 neighbours' m
 // (neighbours outside this cell's tested area count as 0 — NMS is per cell).
@@ -154,21 +154,27 @@ __global__ void __launch_bounds__(256) k_pyr_resize(int level, const OrbGeom* __
 //   phase B  queued pixels only: full arc measure with 3-input min/max (VIMNMX3), dense again;
 //   NMS      ballots over the linearised tested area, ordered compaction = reference order.
 // The pass runs at iniThFAST; only a cell that kept nothing reruns at minThFAST (:813-817).
-#define FAST_PITCH 80
+#ifndef FAST_NT
+#define FAST_NT 32  // threads per cell CTA: ONE warp per cell.  Measured with the 48-byte pitch (128 frames, ms):
+                    // 32 -> 0.42, 64 -> 0.48, 96 -> 0.49, 128 -> 0.50, 160 -> 0.56, 256 -> 0.74: a cell is ~1000 px,
+                    // more warps only add barrier and tail idle time
+#endif
+#define FAST_NW (FAST_NT / 32)
 
 struct FastSmem {
-  uint8_t* img;        // [rows][FAST_PITCH], same word alignment as the global rows
+  uint8_t* img;        // [rows][PITCH] (PITCH = 48 or 80 bytes), same word alignment as the global rows
   uint8_t* m;          // arc measure map, 0 = not a corner at the pass threshold
   uint16_t* queue;     // phase-A survivors (byte offsets into img / m)
   uint16_t* kept;      // NMS survivors (byte offsets), unordered
-  int* misc;           // [1] kept count, [4..7] per-warp queue lengths
+  int* misc;           // [1] kept count, [4..4+FAST_NW) per-warp queue lengths
 };
 
+template <int PITCH>
 __device__ __forceinline__ int fast_arc_measure(const uint8_t* p) {
-  constexpr int RO[16] = {3 * FAST_PITCH,      3 * FAST_PITCH + 1,  2 * FAST_PITCH + 2,  FAST_PITCH + 3,
-                          3,                   -FAST_PITCH + 3,     -2 * FAST_PITCH + 2, -3 * FAST_PITCH + 1,
-                          -3 * FAST_PITCH,     -3 * FAST_PITCH - 1, -2 * FAST_PITCH - 2, -FAST_PITCH - 3,
-                          -3,                  FAST_PITCH - 3,      2 * FAST_PITCH - 2,  3 * FAST_PITCH - 1};
+  constexpr int RO[16] = {3 * PITCH,      3 * PITCH + 1,  2 * PITCH + 2,  PITCH + 3,
+                          3,                   -PITCH + 3,     -2 * PITCH + 2, -3 * PITCH + 1,
+                          -3 * PITCH,     -3 * PITCH - 1, -2 * PITCH - 2, -PITCH - 3,
+                          -3,                  PITCH - 3,      2 * PITCH - 2,  3 * PITCH - 1};
   const int c = p[0];
   int d[16];
 #pragma unroll
@@ -206,6 +212,7 @@ __device__ __forceinline__ void fast_push(bool pred, uint16_t value, uint16_t* l
 
 // One threshold pass over the tested area (tw x thh pixels starting at sub-image (3,3)).
 // Returns the number of NMS survivors, left (unordered) in sm.kept.
+template <int PITCH>
 __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int thh, int a0, bool second_pass) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned lt = (1u << lane) - 1u;
@@ -213,17 +220,17 @@ __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int
   // so a bright (dark) arc needs min over pairs of max(a,b) > c+th  (max over pairs of min < c-th).
   // Each warp appends its survivors to its own queue segment (running count in a register: no
   // atomics, no shuffles).  Loads are unconditional (lanes beyond tw stay inside the pitched row).
-  const int qseg = ((thh + 3) >> 2) * tw;
+  const int qseg = ((thh + FAST_NW - 1) / FAST_NW) * tw;
   uint16_t* myq = sm.queue + warp * qseg;
   int wcount = 0;
-  for (int ty = warp; ty < thh; ty += 4) {
-    const uint8_t* prow = sm.img + (ty + 3) * FAST_PITCH + a0 + 3 + lane;
+  for (int ty = warp; ty < thh; ty += FAST_NW) {
+    const uint8_t* prow = sm.img + (ty + 3) * PITCH + a0 + 3 + lane;
     for (int tx0 = 0; tx0 < tw; tx0 += 32) {
       const uint8_t* p = prow + tx0;
       const int c = p[0];
-      const int r0 = p[3 * FAST_PITCH], r8 = p[-3 * FAST_PITCH], r4 = p[3], r12 = p[-3];
-      const int r2 = p[2 * FAST_PITCH + 2], r10 = p[-2 * FAST_PITCH - 2], r6 = p[-2 * FAST_PITCH + 2],
-                r14 = p[2 * FAST_PITCH - 2];
+      const int r0 = p[3 * PITCH], r8 = p[-3 * PITCH], r4 = p[3], r12 = p[-3];
+      const int r2 = p[2 * PITCH + 2], r10 = p[-2 * PITCH - 2], r6 = p[-2 * PITCH + 2],
+                r14 = p[2 * PITCH - 2];
       const int mn = __vimin3_s32(max(r0, r8), max(r4, r12), min(max(r2, r10), max(r6, r14)));
       const int mx = __vimax3_s32(min(r0, r8), min(r4, r12), max(min(r2, r10), min(r6, r14)));
       bool pass = ((mn > c + th) | (mx < c - th)) & (tx0 + lane < tw);
@@ -238,21 +245,27 @@ __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int
   if (tid == 0) sm.misc[1] = 0;
   __syncthreads();
   // phase B: full measure for the survivors (dense lanes over the four segments)
-  const int n0 = sm.misc[4], n1 = n0 + sm.misc[5], n2 = n1 + sm.misc[6], nq = n2 + sm.misc[7];
+  int pre[FAST_NW + 1];  // prefix sums of the per-warp queue lengths
+  pre[0] = 0;
+#pragma unroll
+  for (int w = 0; w < FAST_NW; ++w) pre[w + 1] = pre[w] + sm.misc[4 + w];
+  const int nq = pre[FAST_NW];
   auto entry = [&](int q) -> int {
-    const int seg = (q >= n0) + (q >= n1) + (q >= n2);
-    const int base = seg == 0 ? 0 : (seg == 1 ? n0 : (seg == 2 ? n1 : n2));
+    int seg = 0, base = 0;
+#pragma unroll
+    for (int w = 1; w < FAST_NW; ++w)
+      if (q >= pre[w]) { seg = w; base = pre[w]; }
     return sm.queue[seg * qseg + (q - base)];
   };
-  for (int q = tid; q < nq; q += 128) {
+  for (int q = tid; q < nq; q += FAST_NT) {
     const int off = entry(q);
-    const int m = fast_arc_measure(sm.img + off);
+    const int m = fast_arc_measure<PITCH>(sm.img + off);
     if (m > th) sm.m[off] = (uint8_t)m;
   }
   __syncthreads();
   // phase C: 3x3 NMS of the corners.  Neighbours outside the tested area hold 0; comparing raw m
   // values equals comparing thresholded scores because every stored m exceeds the pass threshold.
-  for (int q0 = 0; q0 < nq; q0 += 128) {
+  for (int q0 = 0; q0 < nq; q0 += FAST_NT) {
     const int q = q0 + tid;
     bool keep = false;
     int off = 0;
@@ -261,9 +274,9 @@ __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int
       const uint8_t* c = sm.m + off;
       const int mv = c[0];
       if (mv > th) {
-        const int n1_ = __vimax3_s32((int)c[-1], (int)c[1], (int)c[-FAST_PITCH]);
-        const int n2_ = __vimax3_s32((int)c[FAST_PITCH], (int)c[-FAST_PITCH - 1], (int)c[-FAST_PITCH + 1]);
-        const int n3_ = __vimax3_s32((int)c[FAST_PITCH - 1], (int)c[FAST_PITCH + 1], n1_);
+        const int n1_ = __vimax3_s32((int)c[-1], (int)c[1], (int)c[-PITCH]);
+        const int n2_ = __vimax3_s32((int)c[PITCH], (int)c[-PITCH - 1], (int)c[-PITCH + 1]);
+        const int n3_ = __vimax3_s32((int)c[PITCH - 1], (int)c[PITCH + 1], n1_);
         keep = mv > max(n2_, n3_);
       }
     }
@@ -273,16 +286,17 @@ __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int
   return sm.misc[1];
 }
 
-__global__ void __launch_bounds__(128) k_fast_cells(const OrbCell* __restrict__ cells, const uint8_t* __restrict__ pyr,
+template <int PITCH>
+__global__ void __launch_bounds__(FAST_NT) k_fast_cells(const OrbCell* __restrict__ cells, const uint8_t* __restrict__ pyr,
                                                     uint32_t* __restrict__ cand, int* __restrict__ cell_count,
                                                     size_t pyr_frame_bytes, size_t cand_frame_u32, int n_cells,
                                                     int ini_th, int min_th, int rows_max, int t_max) {
   extern __shared__ __align__(16) unsigned char fsm[];
   FastSmem sm;
   sm.img = fsm;
-  sm.m = sm.img + rows_max * FAST_PITCH;
-  sm.queue = reinterpret_cast<uint16_t*>(sm.m + rows_max * FAST_PITCH);
-  sm.kept = sm.queue + ((t_max + 4 * ORB_CELL_MAX + 7) & ~7);
+  sm.m = sm.img + rows_max * PITCH;
+  sm.queue = reinterpret_cast<uint16_t*>(sm.m + rows_max * PITCH);
+  sm.kept = sm.queue + ((t_max + FAST_NW * ORB_CELL_MAX + 7) & ~7);
   sm.misc = reinterpret_cast<int*>(sm.kept + ((t_max / 2 + 8) & ~7));
 
   // one 32-byte record tells the CTA everything about its cell
@@ -298,29 +312,29 @@ __global__ void __launch_bounds__(128) k_fast_cells(const OrbCell* __restrict__ 
   const uint8_t* base = pyr + (size_t)frame * pyr_frame_bytes + cell.tile_off;
   const int nw = (a0 + cw + 3) >> 2;
   for (int wq = tid & 15; wq < nw; wq += 16)
-    for (int y = tid >> 4; y < ch; y += 8)
-      reinterpret_cast<uint32_t*>(sm.img + y * FAST_PITCH)[wq] =
+    for (int y = tid >> 4; y < ch; y += FAST_NT / 16)
+      reinterpret_cast<uint32_t*>(sm.img + y * PITCH)[wq] =
           __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)y * pitch) + wq);
-  for (int i = tid; i < ch * (FAST_PITCH / 16); i += 128) reinterpret_cast<uint4*>(sm.m)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < ch * (PITCH / 16); i += FAST_NT) reinterpret_cast<uint4*>(sm.m)[i] = make_uint4(0, 0, 0, 0);
   const int tw = cw - 6, thh = ch - 6;
   int total = 0, th = ini_th;
   __syncthreads();
   if (tw > 0 && thh > 0) {
-    total = fast_pass(sm, th, tw, thh, a0, false);
+    total = fast_pass<PITCH>(sm, th, tw, thh, a0, false);
     if (total == 0 && min_th < th) {
       th = min_th;
-      total = fast_pass(sm, th, tw, thh, a0, true);
+      total = fast_pass<PITCH>(sm, th, tw, thh, a0, true);
     }
   }
   // ordered write-out: rank of each survivor = number of survivors before it in row-major order
   // (byte offsets into the pitched map are monotone in (y, x)) = cv::FAST's output order
   total = min(total, (int)cell.cand_cap);
   uint32_t* out = cand + (size_t)frame * cand_frame_u32 + cell.cand_slot_off;
-  for (int i = tid; i < total; i += 128) {
+  for (int i = tid; i < total; i += FAST_NT) {
     const int off = sm.kept[i];
     int rank = 0;
     for (int j = 0; j < total; ++j) rank += sm.kept[j] < off;
-    const int y = off / FAST_PITCH, x = off - y * FAST_PITCH - a0;
+    const int y = off / PITCH, x = off - y * PITCH - a0;
     out[rank] = (uint32_t)(x + cell.off_x) | (uint32_t)(y + cell.off_y) << 12 | ((uint32_t)sm.m[off] - 1u) << 24;
   }
   if (tid == 0) cell_count[(size_t)frame * n_cells + blockIdx.x] = total;
@@ -621,18 +635,24 @@ void launch_pyramid(const OrbGeomHost& gh, const uint8_t* d_src, size_t frame_st
 
 void launch_fast(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, uint32_t* d_cand, int* d_cell_count,
                  cudaStream_t st, long long* launches) {
-  // shared memory sized for this geometry's largest cell (rows x FAST_PITCH image + measure map,
-  // survivor queue, ballots): ~10 KB at 640x480, so 16 CTAs stay resident per SM
-  int rows_max = 0, t_max = 1;
+  // shared memory sized for this geometry's largest cell (rows x pitch image + measure map,
+  // survivor queue, kept list): ~7 KB at 640x480, so ~30 cell CTAs stay resident per SM
+  int rows_max = 0, t_max = 1, cw_max = 0;
   for (int l = 0; l < gh.g.nlevels; ++l) {
     rows_max = max(rows_max, gh.g.lv[l].h_cell + 6);
+    cw_max = max(cw_max, gh.g.lv[l].w_cell + 6);
     t_max = max(t_max, gh.g.lv[l].w_cell * gh.g.lv[l].h_cell);
   }
-  const size_t smem = (size_t)2 * rows_max * FAST_PITCH + 2 * (size_t)((t_max + 4 * ORB_CELL_MAX + 7) & ~7) +
-                      2 * (size_t)((t_max / 2 + 8) & ~7) + 32;
-  k_fast_cells<<<dim3(gh.g.n_cells, n_frames), 128, smem, st>>>(gh.d_cells, d_pyr, d_cand, d_cell_count,
-                                                                  gh.g.pyr_frame_bytes, gh.g.cand_frame_u32, gh.g.n_cells,
-                                                                  gh.g.ini_th, gh.g.min_th, rows_max, t_max);
+  const int pitch = cw_max + 3 <= 48 ? 48 : 80;  // + up to 3 bytes of word misalignment
+  const size_t smem = (size_t)2 * rows_max * pitch + 2 * (size_t)((t_max + FAST_NW * ORB_CELL_MAX + 7) & ~7) +
+                      2 * (size_t)((t_max / 2 + 8) & ~7) + 64;
+  const dim3 grid(gh.g.n_cells, n_frames);
+  if (pitch == 48)
+    k_fast_cells<48><<<grid, FAST_NT, smem, st>>>(gh.d_cells, d_pyr, d_cand, d_cell_count, gh.g.pyr_frame_bytes,
+                                                  gh.g.cand_frame_u32, gh.g.n_cells, gh.g.ini_th, gh.g.min_th, rows_max, t_max);
+  else
+    k_fast_cells<80><<<grid, FAST_NT, smem, st>>>(gh.d_cells, d_pyr, d_cand, d_cell_count, gh.g.pyr_frame_bytes,
+                                                  gh.g.cand_frame_u32, gh.g.n_cells, gh.g.ini_th, gh.g.min_th, rows_max, t_max);
   ++*launches;
 }
 
