@@ -51,92 +51,98 @@ __global__ void __launch_bounds__(256) k_pyr_level0(const uint8_t* __restrict__ 
 }
 
 // K1/K2 level l >= 1: cv::resize(level l-1 -> l, INTER_LINEAR) (:1122) fused with the
-// REFLECT_101 border (:1124).  One CTA produces a strip of PYR_R consecutive rows of the
-// BORDERED destination buffer:
-//   1. the (<= PYR_NSRC) source rows the strip needs are staged in shared memory with 128-bit
-//      coalesced loads (border rows map to their mirror row, so the range stays contiguous);
-//   2. each thread owns fixed destination columns (taps in registers) and walks the strip's rows;
-//      the horizontal pass of a source row is reused when the next output row shares it;
-//   3. the left/right border is mirrored inside shared memory and the rows leave as 128-bit stores.
-#define PYR_R 8
-#define PYR_NSRC 24
+// REFLECT_101 border (:1124).  One WARP per tile of 32 words x PYR_ROWS rows of the BORDERED
+// destination buffer, no shared memory, no barriers (the layout that worked for the blur):
+//   * a lane owns one aligned 32-bit word = four adjacent destination columns; border columns
+//     and rows are produced by the same arithmetic at their mirrored interior position;
+//   * its four horizontal taps live in registers; per source row it loads the three aligned words
+//     that cover its taps and picks each tap pair with one byte-permute + dp2a
+//     (h = a0*S[sx] + a1*S[sx+1]);
+//   * walking down the rows, the horizontal pass of a source row is reused when the next output
+//     row shares it (5 rows out of 6 at scale 1.2).
+#define PYR_ROWS 32
 
-__global__ void __launch_bounds__(256) k_pyr_resize(int level, const OrbGeom* __restrict__ g,
+__global__ void __launch_bounds__(128) k_pyr_resize(int level, const OrbGeom* __restrict__ g,
                                                     const OrbXTap* __restrict__ xtab,
                                                     const OrbYTap* __restrict__ ytab, uint8_t* __restrict__ pyr) {
-  extern __shared__ __align__(16) unsigned char psm[];
   const OrbLevelGeom& D = g->lv[level];
   const OrbLevelGeom& S = g->lv[level - 1];
-  uint8_t* s_src = psm;                              // [PYR_NSRC][S.pitch] bordered source rows
-  uint8_t* s_out = psm + (size_t)PYR_NSRC * S.pitch;  // [PYR_R][D.pitch] bordered destination rows
-  __shared__ OrbYTap s_ty[PYR_R];
-  __shared__ int s_range[2];
-  const int tid = threadIdx.x;
-  const int by0 = blockIdx.x * PYR_R, rows_total = D.h + 2 * ORB_EDGE;
-  const int nrows = min(PYR_R, rows_total - by0);
+  const int lane = threadIdx.x & 31;
+  const int words = D.pitch >> 2, rows_total = D.h + 2 * ORB_EDGE;
+  const int tiles_x = (words + 31) >> 5;
+  const int tile = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int ty_ = tile / tiles_x, tx_ = tile - ty_ * tiles_x;
+  const int by0 = ty_ * PYR_ROWS;
+  if (by0 >= rows_total) return;                        // whole warp
+  const bool active = tx_ * 32 + lane < words;         // lanes past the row end idle but stay for the shuffles
+  const int wq = min(tx_ * 32 + lane, words - 1);
   uint8_t* frame = pyr + (size_t)blockIdx.y * g->pyr_frame_bytes;
-  if (tid < 32) {
-    OrbYTap ty = {0, 0, 0, 0};
-    int lo = 1 << 30, hi = -1;
-    if (tid < nrows) {
-      ty = ytab[D.ytab_off + reflect101(by0 + tid - ORB_EDGE, D.h)];
-      s_ty[tid] = ty;
-      lo = min(ty.sy0, ty.sy1);
-      hi = max(ty.sy0, ty.sy1);
-    }
+  // horizontal taps of the four columns (pitch padding beyond w+38 is written as 0)
+  uint32_t a01[4];
+  int sxb[4];  // bordered source column of the left tap
+  int lo_col = 1 << 30;
+  bool live[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  for (int k = 0; k < 4; ++k) {
+    const int bx = 4 * wq + k;
+    live[k] = bx < D.w + 2 * ORB_EDGE;
+    // padding columns reuse the last border column's tap so the four taps stay within 12 source bytes
+    const OrbXTap t = xtab[D.xtab_off + reflect101(min(bx, D.w + 2 * ORB_EDGE - 1) - ORB_EDGE, D.w)];
+    a01[k] = (uint32_t)t.a0 | (uint32_t)t.a1 << 16;
+    sxb[k] = ORB_EDGE + t.sx;
+    lo_col = min(lo_col, sxb[k]);
+  }
+  const int w0 = min(lo_col >> 2, (S.pitch >> 2) - 3);  // three words from here cover all four tap pairs
+  uint32_t sel[4];
+  bool upper[4];  // tap pair taken from words (1,2) instead of (0,1)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int o = sxb[k] - 4 * w0;  // byte offset of the left tap inside the 12 staged bytes, 0..10
+    upper[k] = o > 6;
+    o -= upper[k] ? 4 : 0;
+    sel[k] = (uint32_t)o | (uint32_t)(o + 1) << 4 | 0x4400u;
+  }
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(frame + S.pyr_off + (size_t)ORB_EDGE * S.pitch) + w0;
+  const int spw = S.pitch >> 2;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(frame + D.pyr_off) + wq;
+  auto hpass = [&](int sy, uint32_t (&h)[4]) {
+    const uint32_t* r = src + (size_t)sy * spw;
+    const uint32_t x0 = __ldg(r), x1 = __ldg(r + 1), x2 = __ldg(r + 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t pair = __byte_perm(upper[k] ? x1 : x0, upper[k] ? x2 : x1, sel[k]);
+      h[k] = __dp2a_lo(a01[k], pair, 0u) >> 4;
     }
-    if (tid == 0) { s_range[0] = lo; s_range[1] = hi; }
-  }
-  __syncthreads();
-  const int smin = s_range[0], nsrc = min(s_range[1] - smin + 1, PYR_NSRC);
-  // 1. stage bordered source rows (interior row sy = bordered row sy + 19)
-  {
-    const int q_per_row = S.pitch >> 4;
-    const uint8_t* src = frame + S.pyr_off + (size_t)(smin + ORB_EDGE) * S.pitch;
-    for (int i = tid; i < nsrc * q_per_row; i += 256)
-      reinterpret_cast<uint4*>(s_src)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
-  }
-  __syncthreads();
-  // 2. bilinear taps; thread-owned columns
-  for (int x = tid; x < D.w; x += 256) {
-    const OrbXTap tx = xtab[D.xtab_off + x];
-    const int c0 = ORB_EDGE + tx.sx;  // bordered column of the left tap; c0+1 is a border column when sx==sw-1 (a1==0)
-    const int a0 = tx.a0, a1 = tx.a1;
-    int prev_row = -1, prev_h = 0;
-    for (int r = 0; r < nrows; ++r) {
-      const OrbYTap ty = s_ty[r];
-      const uint8_t* r0 = s_src + (ty.sy0 - smin) * S.pitch + c0;
-      const uint8_t* r1 = s_src + (ty.sy1 - smin) * S.pitch + c0;
-      const int h0 = (ty.sy0 == prev_row) ? prev_h : r0[0] * a0 + r0[1] * a1;
-      const int h1 = r1[0] * a0 + r1[1] * a1;
-      prev_row = ty.sy1;
-      prev_h = h1;
-      const int val = ((((int)ty.b0 * (h0 >> 4)) >> 16) + (((int)ty.b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-      s_out[r * D.pitch + ORB_EDGE + x] = (uint8_t)val;
+  };
+  uint32_t hprev[4] = {0, 0, 0, 0};
+  int prev_row = -1;
+  const int nrows = min(PYR_ROWS, rows_total - by0);
+  // vertical taps of the tile's rows: lane r fetches row r's entry (one coalesced load), rows then
+  // broadcast it by shuffle — no dependent global load in front of every row's source fetch
+  uint2 my_t = make_uint2(0, 0);
+  if (lane < nrows) my_t = __ldg(reinterpret_cast<const uint2*>(ytab + D.ytab_off + reflect101(by0 + lane - ORB_EDGE, D.h)));
+#pragma unroll 4
+  for (int r = 0; r < nrows; ++r) {
+    const uint32_t tlo = __shfl_sync(0xffffffffu, my_t.x, r), thi = __shfl_sync(0xffffffffu, my_t.y, r);
+    const int sy0 = tlo & 0xffff, sy1 = tlo >> 16;
+    const uint32_t b0 = thi & 0xffff, b1 = thi >> 16;
+    uint32_t h0[4], h1[4];
+    if (sy0 == prev_row) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) h0[k] = hprev[k];
+    } else {
+      hpass(sy0, h0);
     }
-  }
-  __syncthreads();
-  // 3. mirror the left/right border, zero the pitch padding
-  for (int i = tid; i < nrows * 2 * ORB_EDGE; i += 256) {
-    const int r = i / (2 * ORB_EDGE), k = i - r * (2 * ORB_EDGE);
-    uint8_t* row = s_out + r * D.pitch + ORB_EDGE;
-    if (k < ORB_EDGE) row[-1 - k] = row[1 + k];
-    else row[D.w + (k - ORB_EDGE)] = row[D.w - 2 - (k - ORB_EDGE)];
-  }
-  const int pad = D.pitch - (D.w + 2 * ORB_EDGE);
-  for (int i = tid; i < nrows * pad; i += 256) {
-    const int r = i / pad, k = i - r * pad;
-    s_out[r * D.pitch + D.w + 2 * ORB_EDGE + k] = 0;
-  }
-  __syncthreads();
-  {
-    const int q = nrows * (D.pitch >> 4);
-    uint4* dst = reinterpret_cast<uint4*>(frame + D.pyr_off + (size_t)by0 * D.pitch);
-    for (int i = tid; i < q; i += 256) dst[i] = reinterpret_cast<const uint4*>(s_out)[i];
+    hpass(sy1, h1);
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t v = (((b0 * h0[k]) >> 16) + ((b1 * h1[k]) >> 16) + 2u) >> 2;
+      out |= (live[k] ? v : 0u) << (8 * k);
+      hprev[k] = h1[k];
+    }
+    prev_row = sy1;
+    if (active) dst[(size_t)(by0 + r) * words] = out;
   }
 }
 
@@ -626,9 +632,8 @@ void launch_pyramid(const OrbGeomHost& gh, const uint8_t* d_src, size_t frame_st
   }
   for (int l = 1; l < gh.g.nlevels; ++l) {
     const OrbLevelGeom& L = gh.g.lv[l];
-    const int strips = (L.h + 2 * ORB_EDGE + PYR_R - 1) / PYR_R;
-    const size_t smem = (size_t)PYR_NSRC * gh.g.lv[l - 1].pitch + (size_t)PYR_R * L.pitch;
-    k_pyr_resize<<<dim3(strips, n_frames), 256, smem, st>>>(l, gh.d_geom, gh.d_xtab, gh.d_ytab, d_pyr);
+    const int tiles = (((L.pitch >> 2) + 31) >> 5) * ((L.h + 2 * ORB_EDGE + PYR_ROWS - 1) / PYR_ROWS);
+    k_pyr_resize<<<dim3((tiles + 3) / 4, n_frames), 128, 0, st>>>(l, gh.d_geom, gh.d_xtab, gh.d_ytab, d_pyr);
     ++*launches;
   }
 }
@@ -667,20 +672,10 @@ size_t octree_smem_bytes(const OrbGeom& g) {
   return (size_t)ot_layout(s, g.ot_cap, g.ot_scan_cap, 256) + (size_t)octree_smem_keys(g) * 6;
 }
 
+cudaError_t prepare_pyramid(const OrbGeom&) { return cudaSuccess; }  // the pyramid kernels use no shared memory
+
 // The opt-in limit is a property of the FUNCTION (per device), shared by every handle: only ever
 // raise it, so a handle with a smaller nfeatures cannot shrink it under another handle's feet.
-cudaError_t prepare_pyramid(const OrbGeom& g) {
-  static int raised[64] = {0};
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  const int need = g.nlevels > 1 ? (int)((size_t)PYR_NSRC * g.lv[0].pitch + (size_t)PYR_R * g.lv[1].pitch) : 0;
-  if (need <= 48 * 1024 || (dev < 64 && need <= raised[dev])) return cudaSuccess;
-  e = cudaFuncSetAttribute(k_pyr_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
-  if (e == cudaSuccess && dev < 64) raised[dev] = need;
-  return e;
-}
-
 cudaError_t prepare_octree(const OrbGeom& g) {
   static int raised[64] = {0};
   int dev = 0;
