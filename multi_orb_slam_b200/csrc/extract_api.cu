@@ -52,6 +52,9 @@ struct orbx_extractor {
   int* d_counts = nullptr;
   int stage_cap = 0;
   int last_batch = 0;  // frames resident in the workspace (for taps)
+  orbk::OrbLevel0 last_l0 = {nullptr, 0, 0};  // level-0 view of the last batch
+  uint8_t* d_l0 = nullptr;  // aligned copy of the frames, only when the caller's buffer is not 4-byte aligned
+  int img_pitch = 0;         // row pitch of d_img / d_l0 (width rounded up to 16)
   // per-stage device timing: a ring of event sets, harvested into running sums
   static const int kRing = 32;
   bool profiling = false;
@@ -161,10 +164,10 @@ bool build_geometry(orbx_extractor* h, std::vector<OrbCell>& cells, std::vector<
     L.w = cv_round((float)g.width * h->inv_scale[l]);
     L.h = cv_round((float)g.height * h->inv_scale[l]);
     if (L.w > 4000 || L.h > 4000) { h->err = "image larger than 4000 px is not supported"; return false; }
-    L.pitch = (int)align_up(L.w + 2 * ORB_EDGE, 16);
+    L.pitch = (int)align_up(L.w, 16);  // levels are stored without the 19-px border (see extract_kernels.cu)
     L.bpitch = (int)align_up(L.w, 16);
     L.pyr_off = (unsigned)pyr_off;
-    pyr_off += align_up((size_t)L.pitch * (L.h + 2 * ORB_EDGE), 256);
+    if (l > 0) pyr_off += align_up((size_t)L.pitch * L.h, 256);  // level 0 = the caller's frame, read in place
     L.blur_off = (unsigned)blur_off;
     blur_off += align_up((size_t)L.bpitch * L.h, 256);
     L.scale = h->scale[l];
@@ -215,9 +218,8 @@ bool build_geometry(orbx_extractor* h, std::vector<OrbCell>& cells, std::vector<
     L.key_cap = L.n_cells * L.cand_cap;
     for (int ci = L.cell_base; ci < (int)cells.size(); ++ci) {
       OrbCell& c = cells[ci];
-      const int bx = ORB_EDGE + c.ini_x;
-      c.a0 = (short)(bx & 3);
-      c.tile_off = L.pyr_off + (unsigned)(ORB_EDGE + c.ini_y) * (unsigned)L.pitch + (unsigned)(bx - c.a0);
+      c.a0 = (short)(c.ini_x & 3);
+      c.tile_off = L.pyr_off + (unsigned)c.ini_y * (unsigned)L.pitch + (unsigned)(c.ini_x - c.a0);  // levels >= 1
       c.pitch = (unsigned short)L.pitch;
       c.cand_cap = (unsigned short)L.cand_cap;
       c.cand_slot_off = (unsigned)cand_off + (unsigned)c.slot * (unsigned)L.cand_cap;
@@ -253,7 +255,7 @@ bool build_geometry(orbx_extractor* h, std::vector<OrbCell>& cells, std::vector<
   g.n_blur_tiles = tile_base;
   g.ot_scan_cap = std::max(g.ot_cap, max_cells_level) + 1;
   g.kp_cap_frame = sel_off;
-  g.pyr_frame_bytes = pyr_off;
+  g.pyr_frame_bytes = pyr_off + 256;  // slack: the resize window may touch a few bytes past a level's last row
   g.blur_frame_bytes = blur_off;
   g.cand_frame_u32 = cand_off;
   g.key_frame_u32 = key_off;
@@ -282,22 +284,34 @@ bool ensure_staging(orbx_extractor* h, int cap) {
 int run_batch(orbx_extractor* h, const uint8_t* d_images, int n_frames, size_t frame_stride, size_t row_stride,
               orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_counts, int cap) {
   cudaStream_t st = h->stream;
+  const int W = h->cfg.width, H = h->cfg.height;
+  // level 0 is read in place when the frames are 4-byte aligned; otherwise through an aligned copy
+  orbk::OrbLevel0 l0 = {d_images, frame_stride, (int)row_stride};
+  if ((reinterpret_cast<uintptr_t>(d_images) & 3) || (row_stride & 3) || (frame_stride & 3)) {
+    if (!h->d_l0 && !h->check(cudaMalloc((void**)&h->d_l0, (size_t)h->cfg.max_batch * h->img_pitch * H), "cudaMalloc(aligned level 0)"))
+      return ORBX_E_CUDA;
+    for (int f = 0; f < n_frames; ++f)
+      if (!h->check(cudaMemcpy2DAsync(h->d_l0 + (size_t)f * h->img_pitch * H, h->img_pitch, d_images + (size_t)f * frame_stride,
+                                      row_stride, W, H, cudaMemcpyDeviceToDevice, st), "align level 0"))
+        return ORBX_E_CUDA;
+    l0 = {h->d_l0, (size_t)h->img_pitch * H, h->img_pitch};
+  }
   const bool prof = h->profiling;
   cudaEvent_t* ev = h->ev[h->ev_next];
   if (prof) {
     if (!h->harvest(h->ev_next)) return ORBX_E_CUDA;
     cudaEventRecord(ev[0], st);
   }
-  orbk::launch_pyramid(h->gh, d_images, frame_stride, row_stride, n_frames, h->d_pyr, st, &h->launches);
+  orbk::launch_pyramid(h->gh, l0, n_frames, h->d_pyr, st, &h->launches);
   if (prof) cudaEventRecord(ev[1], st);
-  orbk::launch_fast(h->gh, n_frames, h->d_pyr, h->d_cand, h->d_cell_count, st, &h->launches);
+  orbk::launch_fast(h->gh, l0, n_frames, h->d_pyr, h->d_cand, h->d_cell_count, st, &h->launches);
   if (prof) cudaEventRecord(ev[2], st);
   orbk::launch_octree(h->gh, n_frames, h->d_cand, h->d_cell_count, h->d_keys, h->d_knode, h->d_sel, h->d_sel_count, st,
                       &h->launches);
   if (prof) cudaEventRecord(ev[3], st);
-  orbk::launch_blur(h->gh, n_frames, h->d_pyr, h->d_blur, st, &h->launches);
+  orbk::launch_blur(h->gh, l0, n_frames, h->d_pyr, h->d_blur, st, &h->launches);
   if (prof) cudaEventRecord(ev[4], st);
-  orbk::launch_orient_describe(h->gh, n_frames, h->d_pyr, h->d_blur, h->d_sel, h->d_sel_count, d_kps, d_desc, d_counts,
+  orbk::launch_orient_describe(h->gh, l0, n_frames, h->d_pyr, h->d_blur, h->d_sel, h->d_sel_count, d_kps, d_desc, d_counts,
                                cap, st, &h->launches);
   if (prof) {
     cudaEventRecord(ev[5], st);
@@ -305,6 +319,7 @@ int run_batch(orbx_extractor* h, const uint8_t* d_images, int n_frames, size_t f
     h->ev_next = (h->ev_next + 1) % orbx_extractor::kRing;
   }
   h->last_batch = n_frames;
+  h->last_l0 = l0;
   if (!h->check(cudaGetLastError(), "kernel launch")) return ORBX_E_CUDA;
   return ORBX_OK;
 }
@@ -350,6 +365,7 @@ int orbx_create(const orbx_config* cfg, orbx_extractor** out) {
       if (!h->check(cudaEventCreate(&e), "cudaEventCreate")) return fail(ORBX_E_CUDA);
   const OrbGeom& g = h->gh.g;
   const size_t B = (size_t)cfg->max_batch;
+  h->img_pitch = (int)align_up(cfg->width, 16);
   bool ok = dev_alloc(h, &h->gh.d_geom, 1, "cudaMalloc(geom)") &&
             dev_alloc(h, &h->gh.d_cells, cells.size(), "cudaMalloc(cells)") &&
             dev_alloc(h, &h->gh.d_xtab, xt.size(), "cudaMalloc(xtab)") &&
@@ -362,14 +378,13 @@ int orbx_create(const orbx_config* cfg, orbx_extractor** out) {
             dev_alloc(h, &h->d_knode, B * g.key_frame_u32, "cudaMalloc(key nodes)") &&
             dev_alloc(h, &h->d_sel, B * g.kp_cap_frame, "cudaMalloc(selection)") &&
             dev_alloc(h, &h->d_sel_count, B * g.nlevels, "cudaMalloc(selection counts)") &&
-            dev_alloc(h, &h->d_img, B * (size_t)cfg->width * cfg->height, "cudaMalloc(image staging)") &&
+            dev_alloc(h, &h->d_img, B * (size_t)h->img_pitch * cfg->height, "cudaMalloc(image staging)") &&
             dev_alloc(h, &h->d_counts, B, "cudaMalloc(counts)");
   if (!ok) return fail(ORBX_E_CUDA);
   ok = h->check(cudaMemcpy(h->gh.d_geom, &g, sizeof(g), cudaMemcpyHostToDevice), "copy geom") &&
        h->check(cudaMemcpy(h->gh.d_cells, cells.data(), cells.size() * sizeof(OrbCell), cudaMemcpyHostToDevice), "copy cells") &&
        h->check(cudaMemcpy(h->gh.d_xtab, xt.data(), xt.size() * sizeof(OrbXTap), cudaMemcpyHostToDevice), "copy xtab") &&
        h->check(cudaMemcpy(h->gh.d_ytab, yt.data(), yt.size() * sizeof(OrbYTap), cudaMemcpyHostToDevice), "copy ytab") &&
-       h->check(cudaMemset(h->d_pyr, 0, B * g.pyr_frame_bytes), "clear pyramid") &&
        h->check(orbk::prepare_octree(g), "octree shared-memory opt-in") &&
        h->check(orbk::prepare_pyramid(g), "pyramid shared-memory opt-in");
   if (!ok) return fail(ORBX_E_CUDA);
@@ -386,7 +401,7 @@ void orbx_destroy(orbx_extractor* h) {
   cudaFree(h->gh.d_geom); cudaFree(h->gh.d_cells); cudaFree(h->gh.d_xtab); cudaFree(h->gh.d_ytab);
   cudaFree(h->d_pyr); cudaFree(h->d_blur); cudaFree(h->d_cand); cudaFree(h->d_cell_count);
   cudaFree(h->d_keys); cudaFree(h->d_knode); cudaFree(h->d_sel); cudaFree(h->d_sel_count);
-  cudaFree(h->d_img); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts);
+  cudaFree(h->d_img); cudaFree(h->d_l0); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts);
   for (auto& set : h->ev)
     for (auto& e : set)
       if (e) cudaEventDestroy(e);
@@ -446,18 +461,20 @@ int orbx_extract_batch_host(orbx_extractor* h, const uint8_t* images, int n_fram
   for (int f0 = 0; f0 < n_frames; f0 += h->cfg.max_batch) {
     const int nb = std::min(h->cfg.max_batch, n_frames - f0);
     const uint8_t* src = images + (size_t)f0 * frame_stride;
-    // H2D: rows packed to width (one 2D copy per batch when frames are contiguous rows)
+    // H2D into the staging buffer (row pitch rounded up to 16: level 0 is then read in place);
+    // one 2D copy per batch when the frames are contiguous rows
+    const int P = h->img_pitch;
     if (frame_stride == row_stride * (size_t)H) {
-      if (!h->check(cudaMemcpy2DAsync(h->d_img, W, src, row_stride, W, (size_t)H * nb, cudaMemcpyHostToDevice, h->stream),
+      if (!h->check(cudaMemcpy2DAsync(h->d_img, P, src, row_stride, W, (size_t)H * nb, cudaMemcpyHostToDevice, h->stream),
                     "H2D images"))
         return ORBX_E_CUDA;
     } else {
       for (int f = 0; f < nb; ++f)
-        if (!h->check(cudaMemcpy2DAsync(h->d_img + (size_t)f * W * H, W, src + (size_t)f * frame_stride, row_stride, W, H,
+        if (!h->check(cudaMemcpy2DAsync(h->d_img + (size_t)f * P * H, P, src + (size_t)f * frame_stride, row_stride, W, H,
                                         cudaMemcpyHostToDevice, h->stream), "H2D image"))
           return ORBX_E_CUDA;
     }
-    const int rc = run_batch(h, h->d_img, nb, (size_t)W * H, W, h->d_kps, h->d_desc, h->d_counts, cap);
+    const int rc = run_batch(h, h->d_img, nb, (size_t)P * H, P, h->d_kps, h->d_desc, h->d_counts, cap);
     if (rc != ORBX_OK) return rc;
     if (!h->check(cudaMemcpyAsync(counts + f0, h->d_counts, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, h->stream), "D2H counts") ||
         !h->check(cudaMemcpyAsync(kps + (size_t)f0 * cap, h->d_kps, sizeof(orbx_keypoint) * (size_t)nb * cap, cudaMemcpyDeviceToHost, h->stream), "D2H keypoints") ||
@@ -506,18 +523,45 @@ int orbx_get_pyramid_level(orbx_extractor* h, int frame, int level, int with_bor
                            int* w, int* hgt) {
   if (!h || level < 0 || level >= h->cfg.nlevels) return ORBX_E_INVALID;
   const OrbLevelGeom& L = h->gh.g.lv[level];
-  const int ow = L.w + (with_border ? 2 * ORB_EDGE : 0), oh = L.h + (with_border ? 2 * ORB_EDGE : 0);
+  const int B = with_border ? ORB_EDGE : 0;
+  const int ow = L.w + 2 * B, oh = L.h + 2 * B;
   if (w) *w = ow;
   if (hgt) *hgt = oh;
   if (!dst) return ORBX_OK;
   if (frame < 0 || frame >= h->last_batch) { h->err = "no such frame in the last batch"; return ORBX_E_STATE; }
   if (dst_stride < (size_t)ow) return ORBX_E_INVALID;
   cudaSetDevice(h->device);
-  const uint8_t* src = h->d_pyr + (size_t)frame * h->gh.g.pyr_frame_bytes + L.pyr_off +
-                       (with_border ? 0 : (size_t)ORB_EDGE * L.pitch + ORB_EDGE);
+  // The levels are stored without the EDGE_THRESHOLD border (level 0 is the caller's frame): copy the
+  // interior into place, then mirror it outwards exactly as copyMakeBorder(BORDER_REFLECT_101) does
+  // (src/ORBextractor.cc:1124-1130).  This accessor is not on the hot path.
+  const uint8_t* src;
+  size_t spitch;
+  if (level == 0) {
+    if (!h->last_l0.base) return ORBX_E_STATE;
+    src = h->last_l0.base + (size_t)frame * h->last_l0.frame_stride;
+    spitch = (size_t)h->last_l0.pitch;
+  } else {
+    src = h->d_pyr + (size_t)frame * h->gh.g.pyr_frame_bytes + L.pyr_off;
+    spitch = (size_t)L.pitch;
+  }
+  uint8_t* interior = dst + (size_t)B * dst_stride + B;
   if (!h->check(cudaStreamSynchronize(h->stream), "sync") ||
-      !h->check(cudaMemcpy2D(dst, dst_stride, src, L.pitch, ow, oh, cudaMemcpyDeviceToHost), "D2H pyramid level"))
+      !h->check(cudaMemcpy2D(interior, dst_stride, src, spitch, L.w, L.h, cudaMemcpyDeviceToHost), "D2H pyramid level"))
     return ORBX_E_CUDA;
+  if (B) {
+    auto refl = [](int p, int n) { p = p < 0 ? -p : p; return p >= n ? 2 * (n - 1) - p : p; };
+    for (int y = 0; y < L.h; ++y) {
+      uint8_t* row = interior + (size_t)y * dst_stride;
+      for (int k = 1; k <= B; ++k) {
+        row[-k] = row[refl(-k, L.w)];
+        row[L.w - 1 + k] = row[refl(L.w - 1 + k, L.w)];
+      }
+    }
+    for (int k = 1; k <= B; ++k) {
+      std::memcpy(dst + (size_t)(B - k) * dst_stride, dst + (size_t)(B + refl(-k, L.h)) * dst_stride, ow);
+      std::memcpy(dst + (size_t)(B + L.h - 1 + k) * dst_stride, dst + (size_t)(B + refl(L.h - 1 + k, L.h)) * dst_stride, ow);
+    }
+  }
   return ORBX_OK;
 }
 

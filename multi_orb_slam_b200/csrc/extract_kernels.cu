@@ -28,47 +28,45 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K1/K2 level 0: input frame -> bordered level-0 buffer (copyMakeBorder REFLECT_101, :1129).
-// One thread writes one aligned 32-bit word of the bordered buffer.
-__global__ void __launch_bounds__(256) k_pyr_level0(const uint8_t* __restrict__ src, size_t frame_stride,
-                                                    size_t row_stride, const OrbGeom* __restrict__ g,
-                                                    uint8_t* __restrict__ pyr) {
-  const OrbLevelGeom& L = g->lv[0];
-  const int words = L.pitch >> 2, rows = L.h + 2 * ORB_EDGE;
-  const int id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= words * rows) return;
-  const int by = id / words, wx = id - by * words;
-  const int iy = reflect101(by - ORB_EDGE, L.h);
-  const uint8_t* s = src + (size_t)blockIdx.y * frame_stride + (size_t)iy * row_stride;
-  uint32_t v = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int bx = wx * 4 + k;
-    if (bx < L.w + 2 * ORB_EDGE) v |= (uint32_t)__ldg(s + reflect101(bx - ORB_EDGE, L.w)) << (8 * k);
+// Pyramid storage: level 0 is the caller's frame, read in place; levels >= 1 are stored WITHOUT
+// the EDGE_THRESHOLD border (rows padded to 16 bytes).  Nothing inside the extractor reads the
+// border (FAST cells stay in [16, w-16), the orientation disc and the descriptor pattern stay
+// >= 4 px inside, the blur mirrors at the edge itself), so it is synthesised only when a caller
+// asks for mvImagePyramid with its border (orbx_get_pyramid_level).
+struct LevelView {
+  const uint8_t* base;  // row 0, column 0 of this frame's level
+  int pitch;
+};
+__device__ __forceinline__ LevelView level_view(const OrbGeom* __restrict__ g, const OrbLevel0& l0,
+                                                const uint8_t* __restrict__ pyr, int level, int frame) {
+  LevelView v;
+  if (level == 0) {
+    v.base = l0.base + (size_t)frame * l0.frame_stride;
+    v.pitch = l0.pitch;
+  } else {
+    v.base = pyr + (size_t)frame * g->pyr_frame_bytes + g->lv[level].pyr_off;
+    v.pitch = g->lv[level].pitch;
   }
-  uint8_t* d = pyr + (size_t)blockIdx.y * g->pyr_frame_bytes + L.pyr_off + (size_t)by * L.pitch;
-  reinterpret_cast<uint32_t*>(d)[wx] = v;
+  return v;
 }
 
-// K1/K2 level l >= 1: cv::resize(level l-1 -> l, INTER_LINEAR) (:1122) fused with the
-// REFLECT_101 border (:1124).  One WARP per tile of 32 words x PYR_ROWS rows of the BORDERED
-// destination buffer, no shared memory, no barriers (the layout that worked for the blur):
-//   * a lane owns one aligned 32-bit word = four adjacent destination columns; border columns
-//     and rows are produced by the same arithmetic at their mirrored interior position;
+// K1 level l >= 1: cv::resize(level l-1 -> l, INTER_LINEAR) (:1122).  One WARP per tile of
+// 32 words x PYR_ROWS rows of the destination level, no shared memory, no barriers:
+//   * a lane owns one aligned 32-bit word = four adjacent destination columns;
 //   * its four horizontal taps live in registers; per source row it loads the three aligned words
 //     that cover its taps and picks each tap pair with one byte-permute + dp2a
 //     (h = a0*S[sx] + a1*S[sx+1]);
 //   * walking down the rows, the horizontal pass of a source row is reused when the next output
-//     row shares it (5 rows out of 6 at scale 1.2).
+//     row shares it (5 rows out of 6 at scale 1.2); the rows' vertical taps are fetched once per
+//     tile (lane r holds row r) and broadcast by shuffle.
 #define PYR_ROWS 32
 
-__global__ void __launch_bounds__(128) k_pyr_resize(int level, const OrbGeom* __restrict__ g,
+__global__ void __launch_bounds__(128) k_pyr_resize(int level, const OrbGeom* __restrict__ g, OrbLevel0 l0,
                                                     const OrbXTap* __restrict__ xtab,
                                                     const OrbYTap* __restrict__ ytab, uint8_t* __restrict__ pyr) {
   const OrbLevelGeom& D = g->lv[level];
-  const OrbLevelGeom& S = g->lv[level - 1];
   const int lane = threadIdx.x & 31;
-  const int words = D.pitch >> 2, rows_total = D.h + 2 * ORB_EDGE;
+  const int words = D.pitch >> 2, rows_total = D.h;
   const int tiles_x = (words + 31) >> 5;
   const int tile = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int ty_ = tile / tiles_x, tx_ = tile - ty_ * tiles_x;
@@ -76,35 +74,38 @@ __global__ void __launch_bounds__(128) k_pyr_resize(int level, const OrbGeom* __
   if (by0 >= rows_total) return;                        // whole warp
   const bool active = tx_ * 32 + lane < words;         // lanes past the row end idle but stay for the shuffles
   const int wq = min(tx_ * 32 + lane, words - 1);
-  uint8_t* frame = pyr + (size_t)blockIdx.y * g->pyr_frame_bytes;
-  // horizontal taps of the four columns (pitch padding beyond w+38 is written as 0)
+  const LevelView S = level_view(g, l0, pyr, level - 1, blockIdx.y);
+  uint8_t* drow = pyr + (size_t)blockIdx.y * g->pyr_frame_bytes + D.pyr_off;
+  // horizontal taps of the four columns (row padding beyond w is written as 0)
   uint32_t a01[4];
-  int sxb[4];  // bordered source column of the left tap
+  int sx[4];
   int lo_col = 1 << 30;
   bool live[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int bx = 4 * wq + k;
-    live[k] = bx < D.w + 2 * ORB_EDGE;
-    // padding columns reuse the last border column's tap so the four taps stay within 12 source bytes
-    const OrbXTap t = xtab[D.xtab_off + reflect101(min(bx, D.w + 2 * ORB_EDGE - 1) - ORB_EDGE, D.w)];
+    const int x = 4 * wq + k;
+    live[k] = x < D.w;
+    const OrbXTap t = xtab[D.xtab_off + min(x, D.w - 1)];  // padding columns reuse the last column's tap
     a01[k] = (uint32_t)t.a0 | (uint32_t)t.a1 << 16;
-    sxb[k] = ORB_EDGE + t.sx;
-    lo_col = min(lo_col, sxb[k]);
+    sx[k] = t.sx;
+    lo_col = min(lo_col, sx[k]);
   }
   const int w0 = min(lo_col >> 2, (S.pitch >> 2) - 3);  // three words from here cover all four tap pairs
   uint32_t sel[4];
   bool upper[4];  // tap pair taken from words (1,2) instead of (0,1)
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    int o = sxb[k] - 4 * w0;  // byte offset of the left tap inside the 12 staged bytes, 0..10
+    int o = sx[k] - 4 * w0;  // byte offset of the left tap inside the 12 staged bytes, 0..11
     upper[k] = o > 6;
     o -= upper[k] ? 4 : 0;
-    sel[k] = (uint32_t)o | (uint32_t)(o + 1) << 4 | 0x4400u;
+    // the right tap of the last source column has weight 0 (OpenCV clamps sx to sw-1 with fx = 0):
+    // point it at the left tap so the window never has to reach past the row
+    const int o1 = (a01[k] >> 16) ? o + 1 : o;
+    sel[k] = (uint32_t)o | (uint32_t)o1 << 4 | 0x4400u;
   }
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(frame + S.pyr_off + (size_t)ORB_EDGE * S.pitch) + w0;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(S.base) + w0;
   const int spw = S.pitch >> 2;
-  uint32_t* dst = reinterpret_cast<uint32_t*>(frame + D.pyr_off) + wq;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(drow) + wq;
   auto hpass = [&](int sy, uint32_t (&h)[4]) {
     const uint32_t* r = src + (size_t)sy * spw;
     const uint32_t x0 = __ldg(r), x1 = __ldg(r + 1), x2 = __ldg(r + 2);
@@ -117,10 +118,8 @@ __global__ void __launch_bounds__(128) k_pyr_resize(int level, const OrbGeom* __
   uint32_t hprev[4] = {0, 0, 0, 0};
   int prev_row = -1;
   const int nrows = min(PYR_ROWS, rows_total - by0);
-  // vertical taps of the tile's rows: lane r fetches row r's entry (one coalesced load), rows then
-  // broadcast it by shuffle — no dependent global load in front of every row's source fetch
   uint2 my_t = make_uint2(0, 0);
-  if (lane < nrows) my_t = __ldg(reinterpret_cast<const uint2*>(ytab + D.ytab_off + reflect101(by0 + lane - ORB_EDGE, D.h)));
+  if (lane < nrows) my_t = __ldg(reinterpret_cast<const uint2*>(ytab + D.ytab_off + by0 + lane));
 #pragma unroll 4
   for (int r = 0; r < nrows; ++r) {
     const uint32_t tlo = __shfl_sync(0xffffffffu, my_t.x, r), thi = __shfl_sync(0xffffffffu, my_t.y, r);
@@ -293,7 +292,8 @@ __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int
 }
 
 template <int PITCH>
-__global__ void __launch_bounds__(FAST_NT) k_fast_cells(const OrbCell* __restrict__ cells, const uint8_t* __restrict__ pyr,
+__global__ void __launch_bounds__(FAST_NT) k_fast_cells(const OrbCell* __restrict__ cells, OrbLevel0 l0,
+                                                    const uint8_t* __restrict__ pyr,
                                                     uint32_t* __restrict__ cand, int* __restrict__ cell_count,
                                                     size_t pyr_frame_bytes, size_t cand_frame_u32, int n_cells,
                                                     int ini_th, int min_th, int rows_max, int t_max) {
@@ -312,10 +312,13 @@ __global__ void __launch_bounds__(FAST_NT) k_fast_cells(const OrbCell* __restric
   reinterpret_cast<uint4*>(&cell)[0] = c0;
   reinterpret_cast<uint4*>(&cell)[1] = c1;
   const int frame = blockIdx.y;
-  const int cw = cell.cw, ch = cell.ch, a0 = cell.a0, pitch = cell.pitch;
+  const int cw = cell.cw, ch = cell.ch, a0 = cell.a0;
   const int tid = threadIdx.x;
-  // aligned word copy of the sub-image rows (16 lanes per row)
-  const uint8_t* base = pyr + (size_t)frame * pyr_frame_bytes + cell.tile_off;
+  // aligned word copy of the sub-image rows (16 lanes per row); level-0 cells read the caller's frame
+  const int pitch = cell.level == 0 ? l0.pitch : cell.pitch;
+  const uint8_t* base = cell.level == 0
+                            ? l0.base + (size_t)frame * l0.frame_stride + (size_t)cell.ini_y * l0.pitch + (cell.ini_x - a0)
+                            : pyr + (size_t)frame * pyr_frame_bytes + cell.tile_off;
   const int nw = (a0 + cw + 3) >> 2;
   for (int wq = tid & 15; wq < nw; wq += 16)
     for (int y = tid >> 4; y < ch; y += FAST_NT / 16)
@@ -411,13 +414,75 @@ __global__ void __launch_bounds__(256) k_octree(const OrbGeom* __restrict__ g, c
 
 // ------------------------------------------------------------------------------------------
 // K6 GaussianBlur 7x7 sigma 2, OpenCV 4.x fixed-point path: taps {18,34,48,56,48,34,18}/256 per
-// pass, H pass u8 -> 8.8 (16 bit), V pass -> 16.16, (v + 32768) >> 16.  Reads the bordered
-// pyramid level: its REFLECT_101 border supplies exactly the blur's own border pixels.
+// pass, H pass u8 -> 8.8 (16 bit), V pass -> 16.16, (v + 32768) >> 16, BORDER_REFLECT_101.
 // One WARP per 128 x 32 output tile, no shared memory, no barriers: a lane owns four adjacent
 // columns and walks down the rows; the H pass of each new row (dp4a on packed bytes) enters a
-// 7-row register window from which the V pass is taken.  Rows are fully unrolled so the window
-// rotation is register renaming.
-__global__ void __launch_bounds__(128) k_blur(const OrbGeom* __restrict__ g, const uint8_t* __restrict__ pyr,
+// 7-row register window from which the V pass is taken.  Rows are fully unrolled (the window
+// rotation is register renaming) and branch-free, so the loads of many rows are in flight at once.
+// Rows mirror by index.  Columns: a lane needs image columns x-4..x+7 as three words (a, b, c).
+// Warps that lie fully inside the image take them as three aligned loads; warps touching the
+// left/right edge run the EDGE variant, where every lane loads four aligned words around its
+// window and builds a, b, c with lane-constant word picks + byte permutes (the mirrored source
+// columns of each word lie within <= 4 adjacent columns).
+// VARIANT 0: warp fully inside the image; 1: warp at the left edge (only lane 0 mirrors: columns
+// -4..-1 are columns 4..1, one byte permute of its own words); 2: generic edge (right edge, or
+// levels narrower than a tile).
+template <int VARIANT>
+__device__ __forceinline__ void blur_rows(const uint32_t* __restrict__ src, int spw, int y0, int h, const int (&ia)[3],
+                                          const uint32_t (&esel)[3], uint8_t* __restrict__ dst, int bpitch, int x,
+                                          bool col_ok) {
+  const uint32_t K0123 = 18u | 34u << 8 | 48u << 16 | 56u << 24, K456 = 48u | 34u << 8 | 18u << 16;
+  // 7-row register window, rows processed in blocks of 7 so that the slot of row r is r % 7 at
+  // compile time (ORB_BLUR_TH + 6 is a multiple of 7); the block loop stays rolled to keep the
+  // code of all three variants inside the instruction cache.
+  uint32_t win[7][4];
+  for (int rb = 0; rb < ORB_BLUR_TH + 6; rb += 7) {
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int r = rb + j;
+      // H pass of image row y0 - 3 + r (mirrored at the top/bottom edge)
+      const int iy = reflect101(min(y0 - 3 + r, h + 2), h);
+      const uint32_t* row = src + (size_t)iy * spw;
+      uint32_t a, b, c;
+      if (VARIANT == 0) {
+        a = __ldg(row); b = __ldg(row + 1); c = __ldg(row + 2);
+      } else if (VARIANT == 1) {
+        // lane 0 (x == 0) was pointed at word 0: its q0, q1 are columns 0..7
+        const uint32_t q0 = __ldg(row), q1 = __ldg(row + 1), q2 = __ldg(row + 2);
+        const bool is_left = x == 0;
+        a = is_left ? __byte_perm(q0, q1, 0x1234) : q0;
+        b = is_left ? q0 : q1;
+        c = is_left ? q1 : q2;
+      } else {
+        const uint32_t q0 = __ldg(row), q1 = __ldg(row + 1), q2 = __ldg(row + 2), q3 = __ldg(row + 3);
+        auto lo = [&](int i) { return i == 0 ? q0 : (i == 1 ? q1 : q2); };
+        auto hi = [&](int i) { return i == 0 ? q1 : (i == 1 ? q2 : q3); };
+        a = __byte_perm(lo(ia[0]), hi(ia[0]), esel[0]);
+        b = __byte_perm(lo(ia[1]), hi(ia[1]), esel[1]);
+        c = __byte_perm(lo(ia[2]), hi(ia[2]), esel[2]);
+      }
+      win[j][0] = __dp4a(__byte_perm(a, b, 0x4321), K0123, __dp4a(__byte_perm(b, c, 0x4321), K456, 0u));
+      win[j][1] = __dp4a(__byte_perm(a, b, 0x5432), K0123, __dp4a(__byte_perm(b, c, 0x5432), K456, 0u));
+      win[j][2] = __dp4a(__byte_perm(a, b, 0x6543), K0123, __dp4a(__byte_perm(b, c, 0x6543), K456, 0u));
+      win[j][3] = __dp4a(b, K0123, __dp4a(c, K456, 0u));
+      if (r >= 6) {
+        // rows r-6 .. r sit in slots (j+1)%7 .. (j+7)%7
+        const int y = y0 + r - 6;
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t v = 18u * (win[(j + 1) % 7][i] + win[j][i]) + 34u * (win[(j + 2) % 7][i] + win[(j + 6) % 7][i]) +
+                             48u * (win[(j + 3) % 7][i] + win[(j + 5) % 7][i]) + 56u * win[(j + 4) % 7][i] + 32768u;
+          o[i] = v >> 16;
+        }
+        if (col_ok && y < h)
+          reinterpret_cast<uint32_t*>(dst + (size_t)y * bpitch)[x >> 2] = o[0] | o[1] << 8 | o[2] << 16 | o[3] << 24;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_blur(const OrbGeom* __restrict__ g, OrbLevel0 l0, const uint8_t* __restrict__ pyr,
                                               uint8_t* __restrict__ blur) {
   const int tile = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (tile >= g->n_blur_tiles) return;
@@ -429,45 +494,40 @@ __global__ void __launch_bounds__(128) k_blur(const OrbGeom* __restrict__ g, con
   const int ty = t / L.blur_tiles_x, tx = t - ty * L.blur_tiles_x;
   const int x = tx * ORB_BLUR_TW + 4 * lane, y0 = ty * ORB_BLUR_TH;
   const int frame = blockIdx.y;
-  const int pitch_w = L.pitch >> 2;
-  // image columns x-3 .. x+6 are bordered columns x+16 .. x+25: three aligned words from word (x+16)/4
-  const int w0 = min((x + 16) >> 2, pitch_w - 3);
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(pyr + (size_t)frame * g->pyr_frame_bytes + L.pyr_off) + w0;
+  const LevelView S = level_view(g, l0, pyr, level, frame);
+  const int w = L.w, h = L.h;
   uint8_t* dst = blur + (size_t)frame * g->blur_frame_bytes + L.blur_off;
   const bool col_ok = x < L.bpitch;
-  const int last_row = L.h + 2 * ORB_EDGE - 1;
-  const uint32_t K0123 = 18u | 34u << 8 | 48u << 16 | 56u << 24, K456 = 48u | 34u << 8 | 18u << 16;
-  uint32_t win[7][4];
-#pragma unroll
-  for (int r = 0; r < ORB_BLUR_TH + 6; ++r) {
-    // H pass of image row y0 - 3 + r (bordered row + 19)
-    const int by = min(y0 - 3 + r + ORB_EDGE, last_row);
-    const uint32_t* row = src + (size_t)by * pitch_w;
-    const uint32_t a = __ldg(row), b = __ldg(row + 1), c = __ldg(row + 2);
-    uint32_t h[4];
-    h[0] = __dp4a(a, K0123, __dp4a(b, K456, 0u));
-    h[1] = __dp4a(__byte_perm(a, b, 0x4321), K0123, __dp4a(__byte_perm(b, c, 0x4321), K456, 0u));
-    h[2] = __dp4a(__byte_perm(a, b, 0x5432), K0123, __dp4a(__byte_perm(b, c, 0x5432), K456, 0u));
-    h[3] = __dp4a(__byte_perm(a, b, 0x6543), K0123, __dp4a(__byte_perm(b, c, 0x6543), K456, 0u));
-#pragma unroll
-    for (int j = 0; j < 6; ++j)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) win[j][i] = win[j + 1][i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) win[6][i] = h[i];
-    if (r >= 6) {
-      const int y = y0 + r - 6;
-      uint32_t o[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t v = 18u * (win[0][i] + win[6][i]) + 34u * (win[1][i] + win[5][i]) +
-                           48u * (win[2][i] + win[4][i]) + 56u * win[3][i] + 32768u;
-        o[i] = v >> 16;
-      }
-      if (col_ok && y < L.h)
-        reinterpret_cast<uint32_t*>(dst + (size_t)y * L.bpitch)[x >> 2] = o[0] | o[1] << 8 | o[2] << 16 | o[3] << 24;
-    }
+  const int spw = S.pitch >> 2;
+  int ia[3] = {0, 1, 2};
+  uint32_t esel[3] = {0x3210u, 0x3210u, 0x3210u};
+  const bool right_ok = tx * ORB_BLUR_TW + ORB_BLUR_TW + 3 < w;  // warp-uniform: no lane reaches past the right edge
+  if (right_ok) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(S.base) + (max(x - 4, 0) >> 2);
+    if (tx > 0) blur_rows<0>(src, spw, y0, h, ia, esel, dst, L.bpitch, x, col_ok);
+    else blur_rows<1>(src, spw, y0, h, ia, esel, dst, L.bpitch, x, col_ok);
+    return;
   }
+  // lane constants of the edge variant: four words from `wb` cover every (mirrored) source column
+  int col[12], lo = 1 << 30;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    col[k] = reflect101(min(max(x - 4 + k, -18), w + 18), w);
+    lo = min(lo, col[k]);
+  }
+  const int wb = min(lo >> 2, max(0, spw - 4));
+#pragma unroll
+  for (int gi = 0; gi < 3; ++gi) {
+    int mo = 1 << 30;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mo = min(mo, col[4 * gi + k] - 4 * wb);
+    ia[gi] = min(mo >> 2, 2);
+    uint32_t sv = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sv |= (uint32_t)((col[4 * gi + k] - 4 * wb - 4 * ia[gi]) & 7) << (4 * k);
+    esel[gi] = sv;
+  }
+  blur_rows<2>(reinterpret_cast<const uint32_t*>(S.base) + wb, spw, y0, h, ia, esel, dst, L.bpitch, x, col_ok);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -546,7 +606,8 @@ __device__ __forceinline__ void glibc_sincosf(float y, float* sinp, float* cosp)
   *cosp = (float)sincos_poly(xs, x2, neg, n ^ 1);
 }
 
-__global__ void __launch_bounds__(256) k_orient_describe(const OrbGeom* __restrict__ g, const uint8_t* __restrict__ pyr,
+__global__ void __launch_bounds__(256) k_orient_describe(const OrbGeom* __restrict__ g, OrbLevel0 l0,
+                                                         const uint8_t* __restrict__ pyr,
                                                          const uint8_t* __restrict__ blur,
                                                          const uint32_t* __restrict__ sel,
                                                          const int* __restrict__ sel_count,
@@ -569,8 +630,8 @@ __global__ void __launch_bounds__(256) k_orient_describe(const OrbGeom* __restri
   const int kx = OT_KEY_X(key) + ORB_MIN_BORDER, ky = OT_KEY_Y(key) + ORB_MIN_BORDER;  // :843-844
 
   // IC_Angle on the un-blurred level: lane = u + 15
-  const uint8_t* center = pyr + (size_t)frame * g->pyr_frame_bytes + L.pyr_off +
-                          (size_t)(ky + ORB_EDGE) * L.pitch + kx + ORB_EDGE;
+  const LevelView S = level_view(g, l0, pyr, level, frame);
+  const uint8_t* center = S.base + (size_t)ky * S.pitch + kx;
   const int u = lane - ORB_HALF_PATCH;
   int m10 = 0, m01 = 0;
   if (lane < 31) {
@@ -578,7 +639,7 @@ __global__ void __launch_bounds__(256) k_orient_describe(const OrbGeom* __restri
 #pragma unroll
     for (int v = 1; v <= ORB_HALF_PATCH; ++v) {
       if (abs(u) <= c_umax[v]) {
-        const int plus = center[u + v * L.pitch], minus = center[u - v * L.pitch];
+        const int plus = center[u + v * S.pitch], minus = center[u - v * S.pitch];
         m10 += u * (plus + minus);
         m01 += v * (plus - minus);
       }
@@ -622,24 +683,18 @@ __global__ void __launch_bounds__(256) k_orient_describe(const OrbGeom* __restri
 
 // ------------------------------------------------------------------------------------------
 // launch wrappers (host)
-void launch_pyramid(const OrbGeomHost& gh, const uint8_t* d_src, size_t frame_stride, size_t row_stride,
-                    int n_frames, uint8_t* d_pyr, cudaStream_t st, long long* launches) {
-  {
-    const OrbLevelGeom& L = gh.g.lv[0];
-    const int n = (L.pitch >> 2) * (L.h + 2 * ORB_EDGE);
-    k_pyr_level0<<<dim3((n + 255) / 256, n_frames), 256, 0, st>>>(d_src, frame_stride, row_stride, gh.d_geom, d_pyr);
-    ++*launches;
-  }
+void launch_pyramid(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, uint8_t* d_pyr, cudaStream_t st,
+                    long long* launches) {
   for (int l = 1; l < gh.g.nlevels; ++l) {
     const OrbLevelGeom& L = gh.g.lv[l];
-    const int tiles = (((L.pitch >> 2) + 31) >> 5) * ((L.h + 2 * ORB_EDGE + PYR_ROWS - 1) / PYR_ROWS);
-    k_pyr_resize<<<dim3((tiles + 3) / 4, n_frames), 128, 0, st>>>(l, gh.d_geom, gh.d_xtab, gh.d_ytab, d_pyr);
+    const int tiles = (((L.pitch >> 2) + 31) >> 5) * ((L.h + PYR_ROWS - 1) / PYR_ROWS);
+    k_pyr_resize<<<dim3((tiles + 3) / 4, n_frames), 128, 0, st>>>(l, gh.d_geom, l0, gh.d_xtab, gh.d_ytab, d_pyr);
     ++*launches;
   }
 }
 
-void launch_fast(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, uint32_t* d_cand, int* d_cell_count,
-                 cudaStream_t st, long long* launches) {
+void launch_fast(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, const uint8_t* d_pyr, uint32_t* d_cand,
+                 int* d_cell_count, cudaStream_t st, long long* launches) {
   // shared memory sized for this geometry's largest cell (rows x pitch image + measure map,
   // survivor queue, kept list): ~7 KB at 640x480, so ~30 cell CTAs stay resident per SM
   int rows_max = 0, t_max = 1, cw_max = 0;
@@ -653,10 +708,10 @@ void launch_fast(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, uint
                       2 * (size_t)((t_max / 2 + 8) & ~7) + 64;
   const dim3 grid(gh.g.n_cells, n_frames);
   if (pitch == 48)
-    k_fast_cells<48><<<grid, FAST_NT, smem, st>>>(gh.d_cells, d_pyr, d_cand, d_cell_count, gh.g.pyr_frame_bytes,
+    k_fast_cells<48><<<grid, FAST_NT, smem, st>>>(gh.d_cells, l0, d_pyr, d_cand, d_cell_count, gh.g.pyr_frame_bytes,
                                                   gh.g.cand_frame_u32, gh.g.n_cells, gh.g.ini_th, gh.g.min_th, rows_max, t_max);
   else
-    k_fast_cells<80><<<grid, FAST_NT, smem, st>>>(gh.d_cells, d_pyr, d_cand, d_cell_count, gh.g.pyr_frame_bytes,
+    k_fast_cells<80><<<grid, FAST_NT, smem, st>>>(gh.d_cells, l0, d_pyr, d_cand, d_cell_count, gh.g.pyr_frame_bytes,
                                                   gh.g.cand_frame_u32, gh.g.n_cells, gh.g.ini_th, gh.g.min_th, rows_max, t_max);
   ++*launches;
 }
@@ -719,17 +774,17 @@ void dump_octree_marks() {
 }
 #endif
 
-void launch_blur(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, uint8_t* d_blur, cudaStream_t st,
-                 long long* launches) {
-  k_blur<<<dim3((gh.g.n_blur_tiles + 3) / 4, n_frames), 128, 0, st>>>(gh.d_geom, d_pyr, d_blur);
+void launch_blur(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, const uint8_t* d_pyr, uint8_t* d_blur,
+                 cudaStream_t st, long long* launches) {
+  k_blur<<<dim3((gh.g.n_blur_tiles + 3) / 4, n_frames), 128, 0, st>>>(gh.d_geom, l0, d_pyr, d_blur);
   ++*launches;
 }
 
-void launch_orient_describe(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, const uint8_t* d_blur,
+void launch_orient_describe(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, const uint8_t* d_pyr, const uint8_t* d_blur,
                             const uint32_t* d_sel, const int* d_sel_count, orbx_keypoint* d_kps, uint8_t* d_desc,
                             int* d_counts, int cap, cudaStream_t st, long long* launches) {
   const int max_kp = gh.g.kp_cap_frame;  // upper bound of keypoints per frame
-  k_orient_describe<<<dim3((max_kp + 7) / 8, n_frames), 256, 0, st>>>(gh.d_geom, d_pyr, d_blur, d_sel, d_sel_count,
+  k_orient_describe<<<dim3((max_kp + 7) / 8, n_frames), 256, 0, st>>>(gh.d_geom, l0, d_pyr, d_blur, d_sel, d_sel_count,
                                                                         d_kps, d_desc, d_counts, cap);
   ++*launches;
 }

@@ -8,6 +8,14 @@
 
 namespace orbk {
 
+// Level 0 of the pyramid is the caller's frame itself, read in place (mvImagePyramid[0] is the
+// input image; the reference only copies it to add a border nobody inside the extractor reads).
+struct OrbLevel0 {
+  const uint8_t* base;   // frame 0, row 0 (4-byte aligned)
+  size_t frame_stride;   // bytes between frames
+  int pitch;             // bytes per row (multiple of 4)
+};
+
 struct OrbGeomHost {
   OrbGeom g;               // host copy
   OrbGeom* d_geom;         // device copy
@@ -16,19 +24,19 @@ struct OrbGeomHost {
   OrbYTap* d_ytab;
 };
 
-void launch_pyramid(const OrbGeomHost& gh, const uint8_t* d_src, size_t frame_stride, size_t row_stride,
-                    int n_frames, uint8_t* d_pyr, cudaStream_t st, long long* launches);
-void launch_fast(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, uint32_t* d_cand, int* d_cell_count,
-                 cudaStream_t st, long long* launches);
+void launch_pyramid(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, uint8_t* d_pyr, cudaStream_t st,
+                    long long* launches);
+void launch_fast(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, const uint8_t* d_pyr, uint32_t* d_cand,
+                 int* d_cell_count, cudaStream_t st, long long* launches);
 size_t octree_smem_bytes(const OrbGeom& g);
 cudaError_t prepare_octree(const OrbGeom& g);
 cudaError_t prepare_pyramid(const OrbGeom& g);
 void launch_octree(const OrbGeomHost& gh, int n_frames, const uint32_t* d_cand, const int* d_cell_count,
                    uint32_t* d_keys, uint16_t* d_knode, uint32_t* d_sel, int* d_sel_count, cudaStream_t st,
                    long long* launches);
-void launch_blur(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, uint8_t* d_blur, cudaStream_t st,
-                 long long* launches);
-void launch_orient_describe(const OrbGeomHost& gh, int n_frames, const uint8_t* d_pyr, const uint8_t* d_blur,
+void launch_blur(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, const uint8_t* d_pyr, uint8_t* d_blur,
+                 cudaStream_t st, long long* launches);
+void launch_orient_describe(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, const uint8_t* d_pyr, const uint8_t* d_blur,
                             const uint32_t* d_sel, const int* d_sel_count, orbx_keypoint* d_kps, uint8_t* d_desc,
                             int* d_counts, int cap, cudaStream_t st, long long* launches);
 

@@ -72,4 +72,4 @@ struct OrbXTap { unsigned short sx, a0, a1, pad; };     // dst x -> src x, weigh
 struct OrbYTap { unsigned short sy0, sy1, b0, b1; };    // dst y -> src rows (clipped), weights
 
 #define ORB_BLUR_TW 128
-#define ORB_BLUR_TH 32
+#define ORB_BLUR_TH 36  // + 6 halo rows = 42 = 6 blocks of 7 (the blur's register window period)
