@@ -405,6 +405,13 @@ def main():
                        "gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)}
     stages["search_for_initialization"] = {"ms": round(match_ms, 4)}
     dom = max(names, key=lambda n: stages[n]["ms"])
+    # DRAM traffic of the dominant kernel from the committed ncu capture (per launch = per handle call)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        per_frame = json.load(open(tpath))["dram_bytes_per_camera_frame"].get(dom)
+        if per_frame:
+            traffic = int(per_frame * F)
     total_alg = sum(sb[n] for n in names) * 2 * F
     pipe_gbs = total_alg / (ms_step * 1e-3) / 1e9
     out = {
@@ -423,7 +430,8 @@ def main():
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": stages[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                     "frac": stages[dom]["frac_of_hbm_peak"], "traffic": traffic,
+                     "algorithmic_bytes_per_launch": int(sb[dom] * F), "launches_per_step": 2, "peak_source": peak_src,
                      "pipeline": {"algorithmic_bytes_per_frame": int(sum(sb[n] for n in names)),
                                   "achieved": round(pipe_gbs, 1), "frac": round(pipe_gbs / (peak * 1.0), 4)}},
         "stages": stages,
