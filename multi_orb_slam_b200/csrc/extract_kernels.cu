@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(128) k_pyr_resize(int level, const OrbGeom* __
 //
 // Work is split the way the arithmetic cost falls (measured on the synthetic frames: at th=20
 // only ~13 % of pixels survive the 4-pair high-speed test and ~6 % are corners):
-//   phase A  every tested pixel: opposite-pair rejection test (dense lanes, ~30 instr/px),
-//            survivors appended to a shared-memory queue;
+//   phase A  every tested pixel: opposite-pair rejection test on packed bytes, four pixels per
+//            lane (~12 instr/px), survivors appended to a shared-memory queue;
 //   phase B  queued pixels only: full arc measure with 3-input min/max (VIMNMX3), dense again;
 //   NMS      ballots over the linearised tested area, ordered compaction = reference order.
 // The pass runs at iniThFAST; only a cell that kept nothing reruns at minThFAST (:813-817).
@@ -167,11 +167,17 @@ __global__ void __launch_bounds__(128) k_pyr_resize(int level, const OrbGeom* __
 #define FAST_NW (FAST_NT / 32)
 
 struct FastSmem {
-  uint8_t* img;        // [rows][PITCH] (PITCH = 48 or 80 bytes), same word alignment as the global rows
-  uint8_t* m;          // arc measure map, 0 = not a corner at the pass threshold
-  uint16_t* queue;     // phase-A survivors (byte offsets into img / m)
-  uint16_t* kept;      // NMS survivors (byte offsets), unordered
-  int* misc;           // [1] kept count, [4..4+FAST_NW) per-warp queue lengths
+  // Three regions of shared memory, each reused once its first tenant is dead (6 KB per cell CTA
+  // at 640x480, so the SM's limit of 32 resident CTAs is reached):
+  uint8_t* img;        // [rows][PITCH] (PITCH = 48 or 80 bytes); sub-image column sx sits at byte 1 + sx, so the
+                       // tested area (sx >= 3) starts on a word boundary
+  uint16_t* kept;      // (aliases img) NMS survivors (byte offsets), unordered: written after the last read of
+                       // img, and only by a pass that is not followed by another
+  uint8_t* hv;         // img with every byte halved (p >> 1): input of the packed rejection test
+  uint16_t* queue;     // (aliases hv) phase-A survivors (byte offsets into img / m), written after phase A
+  uint8_t* m;          // arc measure map, 0 = not a corner at the pass threshold; zeroed after phase A
+  uint16_t* eq;        // (aliases m) phase A's word entries
+  int* misc;           // [1] kept count
 };
 
 template <int PITCH>
@@ -180,17 +186,17 @@ __device__ __forceinline__ int fast_arc_measure(const uint8_t* p) {
                           3,                   -PITCH + 3,     -2 * PITCH + 2, -3 * PITCH + 1,
                           -3 * PITCH,     -3 * PITCH - 1, -2 * PITCH - 2, -PITCH - 3,
                           -3,                  PITCH - 3,      2 * PITCH - 2,  3 * PITCH - 1};
-  const int c = p[0];
+  // min / max over the raw ring values; the centre is subtracted once at the end
   int d[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) d[k] = (int)p[RO[k]] - c;
+  for (int k = 0; k < 16; ++k) d[k] = (int)p[RO[k]];
   int lo3[16], hi3[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     lo3[k] = __vimin3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
     hi3[k] = __vimax3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
   }
-  int mb = -256, md = 256;  // max over arcs of min(d) (bright ring), min over arcs of max(d) (dark ring)
+  int mb = 0, md = 255;  // max over arcs of min(ring) (bright arc), min over arcs of max(ring) (dark arc)
 #pragma unroll
   for (int k = 0; k < 16; k += 2) {
     const int a0 = __vimin3_s32(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
@@ -200,7 +206,8 @@ __device__ __forceinline__ int fast_arc_measure(const uint8_t* p) {
     const int b1 = __vimax3_s32(hi3[k + 1], hi3[(k + 4) & 15], hi3[(k + 7) & 15]);
     md = __vimin3_s32(md, b0, b1);
   }
-  return max(mb, -md);
+  const int c = p[0];
+  return max(mb - c, c - md);
 }
 
 // Warp-aggregated append to a shared-memory list.
@@ -218,64 +225,90 @@ __device__ __forceinline__ void fast_push(bool pred, uint16_t value, uint16_t* l
 // One threshold pass over the tested area (tw x thh pixels starting at sub-image (3,3)).
 // Returns the number of NMS survivors, left (unordered) in sm.kept.
 template <int PITCH>
-__device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int thh, int a0, bool second_pass) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int thh, int ch) {
+  static_assert(FAST_NT == 32, "one warp per cell");
+  constexpr int PW = PITCH / 4;
+  const int lane = threadIdx.x;
   const unsigned lt = (1u << lane) - 1u;
-  // phase A: high-speed rejection.  A 9-arc contains one pixel of every opposite pair (k, k+8),
-  // so a bright (dark) arc needs min over pairs of max(a,b) > c+th  (max over pairs of min < c-th).
-  // Each warp appends its survivors to its own queue segment (running count in a register: no
-  // atomics, no shuffles).  Loads are unconditional (lanes beyond tw stay inside the pitched row).
-  const int qseg = ((thh + FAST_NW - 1) / FAST_NW) * tw;
-  uint16_t* myq = sm.queue + warp * qseg;
-  int wcount = 0;
-  for (int ty = warp; ty < thh; ty += FAST_NW) {
-    const uint8_t* prow = sm.img + (ty + 3) * PITCH + a0 + 3 + lane;
-    for (int tx0 = 0; tx0 < tw; tx0 += 32) {
-      const uint8_t* p = prow + tx0;
-      const int c = p[0];
-      const int r0 = p[3 * PITCH], r8 = p[-3 * PITCH], r4 = p[3], r12 = p[-3];
-      const int r2 = p[2 * PITCH + 2], r10 = p[-2 * PITCH - 2], r6 = p[-2 * PITCH + 2],
-                r14 = p[2 * PITCH - 2];
-      const int mn = __vimin3_s32(max(r0, r8), max(r4, r12), min(max(r2, r10), max(r6, r14)));
-      const int mx = __vimax3_s32(min(r0, r8), min(r4, r12), max(min(r2, r10), min(r6, r14)));
-      bool pass = ((mn > c + th) | (mx < c - th)) & (tx0 + lane < tw);
-      // corners already measured by the first pass stay in play for the second pass's NMS
-      if (second_pass) pass = pass | ((sm.m[p - sm.img] != 0) & (tx0 + lane < tw));
-      const unsigned bm = __ballot_sync(0xffffffffu, pass);
-      if (pass) myq[wcount + __popc(bm & lt)] = (uint16_t)(p - sm.img);
-      wcount += __popc(bm);
-    }
+  // phase A: packed rejection test, four pixels (one word) per lane.  A 9-arc contains one pixel
+  // of every opposite pair (k, k+8), so a corner has |p - c| > th for at least one pixel of each
+  // of the pairs 0/8, 4/12, 2/10, 6/14.  On the halved bytes (a' = a >> 1) |a - c| > th implies
+  // |a' - c'| >= th >> 1, one VABSDIFF4 + one add per ring word: the add carries into bit 7 of a
+  // byte exactly when the halved difference reaches T (all sums stay below 256, so bytes do not
+  // interact).  The test only has to be a superset of the corners: phase B measures exactly.
+  const int T = th >> 1;
+  const uint32_t K = 0x01010101u * (uint32_t)(128 - min(T, 127));
+  const int WPR = (tw + 3) >> 2;  // words per tested row
+  const int items = thh * WPR;
+  const int dr = 32 / WPR, dw = 32 - dr * WPR;
+  const uint32_t last_mask = 0x80808080u >> (8 * (4 * WPR - tw));  // valid pixels of a row's last word
+  int row = lane / WPR, w = lane - row * WPR;
+  const uint32_t* hw = reinterpret_cast<const uint32_t*>(sm.hv);
+  uint16_t* eq = sm.eq;  // word entries: word offset << 4 | pixel nibble
+  int ecount = 0;
+  for (int i0 = 0; i0 < items; i0 += 32) {
+    const bool valid = i0 + lane < items;
+    const int woff = ((valid ? row : 0) + 3) * PW + 1 + w;
+    const uint32_t* p = hw + woff;
+    const uint32_t c = p[0];
+    const uint32_t u3 = p[-3 * PW], d3 = p[3 * PW], lw = p[-1], rw = p[1];
+    const uint32_t ul = p[-2 * PW - 1], uc = p[-2 * PW], ur = p[-2 * PW + 1];
+    const uint32_t dl = p[2 * PW - 1], dc = p[2 * PW], dq = p[2 * PW + 1];
+    const uint32_t f0 = __vabsdiffu4(d3, c) + K, f8 = __vabsdiffu4(u3, c) + K;
+    const uint32_t f4 = __vabsdiffu4(__byte_perm(c, rw, 0x6543), c) + K;
+    const uint32_t f12 = __vabsdiffu4(__byte_perm(lw, c, 0x4321), c) + K;
+    const uint32_t f2 = __vabsdiffu4(__byte_perm(dc, dq, 0x5432), c) + K;
+    const uint32_t f10 = __vabsdiffu4(__byte_perm(ul, uc, 0x5432), c) + K;
+    const uint32_t f6 = __vabsdiffu4(__byte_perm(uc, ur, 0x5432), c) + K;
+    const uint32_t f14 = __vabsdiffu4(__byte_perm(dl, dc, 0x5432), c) + K;
+    uint32_t pass = (f0 | f8) & (f4 | f12) & (f2 | f10) & (f6 | f14) & (w == WPR - 1 ? last_mask : 0x80808080u);
+    if (!valid) pass = 0;
+    const unsigned bm = __ballot_sync(0xffffffffu, pass != 0);
+    if (pass) eq[ecount + __popc(bm & lt)] = (uint16_t)(woff << 4 | ((pass >> 7) * 0x10204080u) >> 28);
+    ecount += __popc(bm);
+    w += dw;
+    row += dr;
+    if (w >= WPR) { w -= WPR; ++row; }
   }
-  if (lane == 0) sm.misc[4 + warp] = wcount;
-  if (tid == 0) sm.misc[1] = 0;
-  __syncthreads();
-  // phase B: full measure for the survivors (dense lanes over the four segments)
-  int pre[FAST_NW + 1];  // prefix sums of the per-warp queue lengths
-  pre[0] = 0;
+  __syncwarp();
+  // expand the word entries into one queue entry per surviving pixel
+  int nq = 0;
+  for (int e0 = 0; e0 < ecount; e0 += 32) {
+    const int e = e0 + lane < ecount ? eq[e0 + lane] : 0;
+    const int nib = e & 15, cnt = __popc(nib);
+    int incl = cnt;
 #pragma unroll
-  for (int w = 0; w < FAST_NW; ++w) pre[w + 1] = pre[w] + sm.misc[4 + w];
-  const int nq = pre[FAST_NW];
-  auto entry = [&](int q) -> int {
-    int seg = 0, base = 0;
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    int pos = nq + incl - cnt;
+    const int boff = (e >> 4) * 4;
 #pragma unroll
-    for (int w = 1; w < FAST_NW; ++w)
-      if (q >= pre[w]) { seg = w; base = pre[w]; }
-    return sm.queue[seg * qseg + (q - base)];
-  };
-  for (int q = tid; q < nq; q += FAST_NT) {
-    const int off = entry(q);
+    for (int k = 0; k < 4; ++k)
+      if (nib >> k & 1) sm.queue[pos++] = (uint16_t)(boff + k);
+    nq += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) sm.misc[1] = 0;
+  __syncwarp();
+  // the entries are consumed: their region becomes the (zeroed) measure map
+  for (int i = lane; i < ch * (PITCH / 16); i += 32) reinterpret_cast<uint4*>(sm.m)[i] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  // phase B: full measure for the survivors (dense lanes)
+  for (int q = lane; q < nq; q += 32) {
+    const int off = sm.queue[q];
     const int m = fast_arc_measure<PITCH>(sm.img + off);
     if (m > th) sm.m[off] = (uint8_t)m;
   }
-  __syncthreads();
+  __syncwarp();
   // phase C: 3x3 NMS of the corners.  Neighbours outside the tested area hold 0; comparing raw m
   // values equals comparing thresholded scores because every stored m exceeds the pass threshold.
-  for (int q0 = 0; q0 < nq; q0 += FAST_NT) {
-    const int q = q0 + tid;
+  for (int q0 = 0; q0 < nq; q0 += 32) {
+    const int q = q0 + lane;
     bool keep = false;
     int off = 0;
     if (q < nq) {
-      off = entry(q);
+      off = sm.queue[q];
       const uint8_t* c = sm.m + off;
       const int mv = c[0];
       if (mv > th) {
@@ -287,7 +320,7 @@ __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int
     }
     fast_push(keep, (uint16_t)off, sm.kept, &sm.misc[1]);
   }
-  __syncthreads();
+  __syncwarp();
   return sm.misc[1];
 }
 
@@ -299,11 +332,14 @@ __global__ void __launch_bounds__(FAST_NT) k_fast_cells(const OrbCell* __restric
                                                     int ini_th, int min_th, int rows_max, int t_max) {
   extern __shared__ __align__(16) unsigned char fsm[];
   FastSmem sm;
+  const int r_img = rows_max * PITCH, r_q = max(r_img, (2 * t_max + 31) & ~15);
   sm.img = fsm;
-  sm.m = sm.img + rows_max * PITCH;
-  sm.queue = reinterpret_cast<uint16_t*>(sm.m + rows_max * PITCH);
-  sm.kept = sm.queue + ((t_max + FAST_NW * ORB_CELL_MAX + 7) & ~7);
-  sm.misc = reinterpret_cast<int*>(sm.kept + ((t_max / 2 + 8) & ~7));
+  sm.kept = reinterpret_cast<uint16_t*>(fsm);
+  sm.hv = fsm + r_img;
+  sm.queue = reinterpret_cast<uint16_t*>(sm.hv);
+  sm.m = sm.hv + r_q;
+  sm.eq = reinterpret_cast<uint16_t*>(sm.m);
+  sm.misc = reinterpret_cast<int*>(sm.m + r_img);
 
   // one 32-byte record tells the CTA everything about its cell
   const uint4* crec = reinterpret_cast<const uint4*>(cells + blockIdx.x);
@@ -314,25 +350,46 @@ __global__ void __launch_bounds__(FAST_NT) k_fast_cells(const OrbCell* __restric
   const int frame = blockIdx.y;
   const int cw = cell.cw, ch = cell.ch, a0 = cell.a0;
   const int tid = threadIdx.x;
-  // aligned word copy of the sub-image rows (16 lanes per row); level-0 cells read the caller's frame
+  // Word copy of the sub-image rows (16 lanes per row), shifted so that sub-image column 0 lands
+  // on byte 1 of the shared row: global word grid -> shared word grid by one byte permute of two
+  // adjacent global words.  Level-0 cells read the caller's frame.
   const int pitch = cell.level == 0 ? l0.pitch : cell.pitch;
   const uint8_t* base = cell.level == 0
                             ? l0.base + (size_t)frame * l0.frame_stride + (size_t)cell.ini_y * l0.pitch + (cell.ini_x - a0)
                             : pyr + (size_t)frame * pyr_frame_bytes + cell.tile_off;
-  const int nw = (a0 + cw + 3) >> 2;
-  for (int wq = tid & 15; wq < nw; wq += 16)
-    for (int y = tid >> 4; y < ch; y += FAST_NT / 16)
-      reinterpret_cast<uint32_t*>(sm.img + y * PITCH)[wq] =
-          __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)y * pitch) + wq);
-  for (int i = tid; i < ch * (PITCH / 16); i += FAST_NT) reinterpret_cast<uint4*>(sm.m)[i] = make_uint4(0, 0, 0, 0);
+  {
+    const int shift = a0 - 1;  // -1..2 bytes between the two grids
+    const int o = shift < 0 ? -1 : 0;
+    const uint32_t sel = shift == 0 ? 0x3210u : (shift == 1 ? 0x4321u : (shift == 2 ? 0x5432u : 0x6543u));
+    const int nsw = (cw + 4) >> 2, ngw = (a0 + cw + 3) >> 2;
+    const int pw = pitch >> 2, y_first = tid >> 4;
+    for (int wq = tid & 15; wq < nsw; wq += 16) {
+      const int i0 = max(wq + o, 0), d1 = min(wq + o + 1, ngw - 1) - i0;
+      const uint32_t* gp = reinterpret_cast<const uint32_t*>(base) + (size_t)y_first * pw + i0;
+      uint32_t* sp = reinterpret_cast<uint32_t*>(sm.img) + y_first * (PITCH / 4) + wq;
+      for (int y = y_first; y < ch; y += FAST_NT / 16) {
+        const uint32_t v = __byte_perm(__ldg(gp), __ldg(gp + d1), sel);
+        sp[0] = v;
+        sp[r_img >> 2] = (v >> 1) & 0x7f7f7f7fu;
+        gp += 2 * pw;
+        sp += 2 * (PITCH / 4);
+      }
+    }
+  }
   const int tw = cw - 6, thh = ch - 6;
   int total = 0, th = ini_th;
   __syncthreads();
   if (tw > 0 && thh > 0) {
-    total = fast_pass<PITCH>(sm, th, tw, thh, a0, false);
+    total = fast_pass<PITCH>(sm, th, tw, thh, ch);
     if (total == 0 && min_th < th) {
+      // Every corner of the first pass is a corner at the lower threshold too, so the second pass
+      // re-measures it (same value) and its NMS sees the complete map.  The queue has overwritten
+      // the halved image: rebuild it.
+      for (int i = tid; i < ch * (PITCH / 4); i += FAST_NT)
+        reinterpret_cast<uint32_t*>(sm.hv)[i] = (reinterpret_cast<const uint32_t*>(sm.img)[i] >> 1) & 0x7f7f7f7fu;
+      __syncthreads();
       th = min_th;
-      total = fast_pass<PITCH>(sm, th, tw, thh, a0, true);
+      total = fast_pass<PITCH>(sm, th, tw, thh, ch);
     }
   }
   // ordered write-out: rank of each survivor = number of survivors before it in row-major order
@@ -343,7 +400,7 @@ __global__ void __launch_bounds__(FAST_NT) k_fast_cells(const OrbCell* __restric
     const int off = sm.kept[i];
     int rank = 0;
     for (int j = 0; j < total; ++j) rank += sm.kept[j] < off;
-    const int y = off / PITCH, x = off - y * PITCH - a0;
+    const int y = off / PITCH, x = off - y * PITCH - 1;
     out[rank] = (uint32_t)(x + cell.off_x) | (uint32_t)(y + cell.off_y) << 12 | ((uint32_t)sm.m[off] - 1u) << 24;
   }
   if (tid == 0) cell_count[(size_t)frame * n_cells + blockIdx.x] = total;
@@ -696,7 +753,7 @@ void launch_pyramid(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, uint8_t* 
 void launch_fast(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, const uint8_t* d_pyr, uint32_t* d_cand,
                  int* d_cell_count, cudaStream_t st, long long* launches) {
   // shared memory sized for this geometry's largest cell (rows x pitch image + measure map,
-  // survivor queue, kept list): ~7 KB at 640x480, so ~30 cell CTAs stay resident per SM
+  // survivor queue, kept list, overlaid): ~6 KB at 640x480, so 32 cell CTAs stay resident per SM
   int rows_max = 0, t_max = 1, cw_max = 0;
   for (int l = 0; l < gh.g.nlevels; ++l) {
     rows_max = max(rows_max, gh.g.lv[l].h_cell + 6);
@@ -704,8 +761,8 @@ void launch_fast(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, const uint8_
     t_max = max(t_max, gh.g.lv[l].w_cell * gh.g.lv[l].h_cell);
   }
   const int pitch = cw_max + 3 <= 48 ? 48 : 80;  // + up to 3 bytes of word misalignment
-  const size_t smem = (size_t)2 * rows_max * pitch + 2 * (size_t)((t_max + FAST_NW * ORB_CELL_MAX + 7) & ~7) +
-                      2 * (size_t)((t_max / 2 + 8) & ~7) + 64;
+  const size_t r_img = (size_t)rows_max * pitch;
+  const size_t smem = 2 * r_img + max(r_img, (size_t)((2 * t_max + 31) & ~15)) + 16;
   const dim3 grid(gh.g.n_cells, n_frames);
   if (pitch == 48)
     k_fast_cells<48><<<grid, FAST_NT, smem, st>>>(gh.d_cells, l0, d_pyr, d_cand, d_cell_count, gh.g.pyr_frame_bytes,
