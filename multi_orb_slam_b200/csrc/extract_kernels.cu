@@ -186,28 +186,24 @@ __device__ __forceinline__ int fast_arc_measure(const uint8_t* p) {
                           3,                   -PITCH + 3,     -2 * PITCH + 2, -3 * PITCH + 1,
                           -3 * PITCH,     -3 * PITCH - 1, -2 * PITCH - 2, -PITCH - 3,
                           -3,                  PITCH - 3,      2 * PITCH - 2,  3 * PITCH - 1};
-  // min / max over the raw ring values; the centre is subtracted once at the end
-  int d[16];
+  // Both polarities at once on 16-bit pairs: a ring value p travels as (p, 255 - p), so one
+  // packed minimum over an arc yields min(p) (bright arc) and 255 - max(p) (dark arc), and the
+  // centre is subtracted once at the end.  VIMNMX3.S16x2: 40 three-input ops per pixel.
+  uint32_t d[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) d[k] = (int)p[RO[k]];
-  int lo3[16], hi3[16];
+  for (int k = 0; k < 16; ++k) d[k] = (uint32_t)p[RO[k]] * 0xFFFF0001u + 0x00FF0000u;
+  uint32_t lo3[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    lo3[k] = __vimin3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-    hi3[k] = __vimax3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-  }
-  int mb = 0, md = 255;  // max over arcs of min(ring) (bright arc), min over arcs of max(ring) (dark arc)
+  for (int k = 0; k < 16; ++k) lo3[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+  uint32_t best = 0;  // max over the 16 arcs of the packed arc minimum
 #pragma unroll
   for (int k = 0; k < 16; k += 2) {
-    const int a0 = __vimin3_s32(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
-    const int a1 = __vimin3_s32(lo3[k + 1], lo3[(k + 4) & 15], lo3[(k + 7) & 15]);
-    mb = __vimax3_s32(mb, a0, a1);
-    const int b0 = __vimax3_s32(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
-    const int b1 = __vimax3_s32(hi3[k + 1], hi3[(k + 4) & 15], hi3[(k + 7) & 15]);
-    md = __vimin3_s32(md, b0, b1);
+    const uint32_t a0 = __vimin3_s16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+    const uint32_t a1 = __vimin3_s16x2(lo3[k + 1], lo3[(k + 4) & 15], lo3[(k + 7) & 15]);
+    best = __vimax3_s16x2(best, a0, a1);
   }
   const int c = p[0];
-  return max(mb - c, c - md);
+  return max((int)(best & 0xffffu) - c, (int)(best >> 16) - 255 + c);
 }
 
 // Warp-aggregated append to a shared-memory list.
