@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--ref-rig-frames", type=int, default=64, help="rig-frames per CPU reference step")
     ap.add_argument("--cpu-rig-frames", type=int, default=256, help="rig-frames of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=1, help="chunks per step of the streaming end-to-end leg")
     ap.add_argument("--bf-size", type=int, default=65536, help="N of the N x N brute-force matching leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -238,14 +239,6 @@ def main():
     m12 = torch.empty((F - 1, caps[0]), dtype=torch.int32, device=dev)
     nmatch = torch.empty((F - 1,), dtype=torch.int32, device=dev)
     bounds = Bounds(0.0, float(W), 0.0, float(H))
-    # pinned result buffers for the e2e leg
-    h_kps = [torch.empty((F, c, 6), dtype=torch.float32).pin_memory() for c in caps]
-    h_desc = [torch.empty((F, c, 32), dtype=torch.uint8).pin_memory() for c in caps]
-    h_counts = [torch.empty((F,), dtype=torch.int32).pin_memory() for _ in caps]
-    h_m12 = torch.empty((F - 1, caps[0]), dtype=torch.int32).pin_memory()
-    h_nmatch = torch.empty((F - 1,), dtype=torch.int32).pin_memory()
-    e2e_img = [torch.empty_like(t) for t in d_img]
-
     def run_match():
         # pairs (t, t+1) of camera 1's stream: F2 arrays are the same buffers shifted by one frame
         matcher.search_for_initialization_device(F - 1, caps[0], kps[0], desc[0], counts[0], kps[0][1:], desc[0][1:],
@@ -260,47 +253,35 @@ def main():
         if match_events:
             match_events[1].record(stream)
 
-    # End-to-end leg: the frames start in pinned host memory every step and the results end in pinned
-    # host memory.  Two lanes (stream + its own pair of extractor handles) take alternate chunks of
-    # the batch, so the H2D copy of one chunk overlaps the kernels of the other; the matcher runs
-    # once both lanes are done.
-    n_lanes, n_chunks = 2, 4
-    chunk = (F + n_chunks - 1) // n_chunks
-    lane_streams = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)]
-    lane_ex = []
-    for ls in lane_streams:
-        pair = [ORBextractor(NF0, SCALE, NLEVELS, INI_TH, MIN_TH, image_size=(W, H), max_batch=chunk, device=local_rank),
-                ORBextractor(NF1, SCALE, NLEVELS, INI_TH, MIN_TH, image_size=(W, H), max_batch=chunk, device=local_rank)]
-        for e in pair:
-            e.set_stream(ls.cuda_stream)
-        lane_ex.append(pair)
+    # End-to-end leg: the package's streaming front end (multi_orb_slam_b200/pipeline.py).  Every step
+    # the frames start in pinned host memory and the results end in pinned host memory; the copies
+    # of step k+1 overlap the kernels of step k (three streams, two-deep buffers).
+    from multi_orb_slam_b200.pipeline import RigPipeline
+    pipe = RigPipeline((NF0, NF1), SCALE, NLEVELS, INI_TH, MIN_TH, image_size=(W, H), rig_frames=F,
+                       n_chunks=args.e2e_chunks, depth=2, window=WINDOW, nnratio=NNRATIO, device=local_rank)
 
-    def e2e_step():
-        done = []
-        for ci in range(n_chunks):
-            f0, f1 = ci * chunk, min(F, (ci + 1) * chunk)
-            if f0 >= f1:
-                continue
-            lane = ci % n_lanes
-            ls = lane_streams[lane]
-            with torch.cuda.stream(ls):
-                for c in range(2):
-                    e2e_img[c][f0:f1].copy_(h_img[c][f0:f1], non_blocking=True)
-                    lane_ex[lane][c].extract_batch_device(e2e_img[c][f0:f1], kps[c][f0:f1], desc[c][f0:f1], counts[c][f0:f1])
-                    h_kps[c][f0:f1].copy_(kps[c][f0:f1], non_blocking=True)
-                    h_desc[c][f0:f1].copy_(desc[c][f0:f1], non_blocking=True)
-                    h_counts[c][f0:f1].copy_(counts[c][f0:f1], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(ls)
-                done.append(ev)
-        with torch.cuda.stream(stream):
-            for ev in done:
-                stream.wait_event(ev)
-            matcher.search_for_initialization_device(F - 1, caps[0], kps[0], desc[0], counts[0], kps[0][1:], desc[0][1:],
-                                                     counts[0][1:], bounds, None, WINDOW, m12, nmatch)
-            h_m12.copy_(m12, non_blocking=True)
-            h_nmatch.copy_(nmatch, non_blocking=True)
-        stream.synchronize()
+    def e2e_run(steps):
+        """K pipelined steps; returns (device ms per step, wall ms per step, last result)."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(pipe.s_in)        # first activity of a step: its H2D copies
+        ticket = -1
+        for k in range(steps):
+            ticket = pipe.submit(h_img)
+            if k >= 1:
+                pipe.result(ticket - 1)   # the consumer reads step k-1 while step k is in flight
+        res = pipe.result(ticket)
+        e1.record(pipe.s_out)       # last activity: the D2H copies of the last step
+        pipe.drain()
+        wall = (time.perf_counter() - t0) / steps * 1e3
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms, wall], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0].item()), float(t[1].item())
+        return ms, wall, res
 
     def barrier():
         if world > 1:
@@ -308,7 +289,7 @@ def main():
         torch.cuda.synchronize()
 
     def launches():
-        return sum(e.launch_count for e in ex) + sum(e.launch_count for pair in lane_ex for e in pair) + matcher.launch_count
+        return sum(e.launch_count for e in ex) + matcher.launch_count + pipe.launch_count
 
     def timed(fn, steps, sync_each):
         barrier()
@@ -357,15 +338,22 @@ def main():
     n_kp = [int(c.sum().item()) for c in counts]
 
     # ---- end-to-end leg (pinned host -> device -> pinned host every step) -----------------------
-    for _ in range(2):
-        e2e_step()
+    e2e_run(2)
+    e2e_ms_dev, e2e_wall, e2e_res = e2e_run(args.steps)
+    if int(e2e_res.nmatches.sum().item()) != total_matches or [int(c.sum().item()) for c in e2e_res.counts] != n_kp:
+        raise SystemExit("bench.py: end-to-end results differ from the device-resident leg")
+    # the raw H2D copy of one step's frames, for reference (the PCIe floor of the end-to-end leg)
     barrier()
-    t0 = time.perf_counter()
-    e2e_ms_dev = timed(e2e_step, args.steps, True)
-    e2e_wall = (time.perf_counter() - t0) / args.steps * 1e3
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        c0.record(stream)
+        for c in range(2):
+            d_img[c].copy_(h_img[c], non_blocking=True)
+        c1.record(stream)
+    stream.synchronize()
+    h2d_ms = c0.elapsed_time(c1)
     clocks = sampler.stop() if rank == 0 else None  # sampled over the device leg and the end-to-end leg
-    h2d = sum(t.numel() for t in h_img)
-    d2h = sum(t.numel() * t.element_size() for t in h_kps + h_desc + h_counts + [h_m12, h_nmatch])
+    h2d, d2h = pipe.h2d_bytes_per_step, pipe.d2h_bytes_per_step
 
     # ---- Hamming matches/s: brute-force leg (BASELINE.json configs[2] upper end) ----------------
     from multi_orb_slam_b200.synth import perturbed_descriptors, random_descriptors
@@ -426,7 +414,9 @@ def main():
                    "parallelism": f"rig-frames sharded over {world} GPU(s), no data-path collective",
                    "keypoints_per_step_rank0": n_kp, "init_matches_per_step_rank0": total_matches},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_ms_dev, "wall_ms_per_step": e2e_wall},
+                "ms_per_step": e2e_ms_dev, "wall_ms_per_step": e2e_wall,
+                "api": "multi_orb_slam_b200.pipeline.RigPipeline.submit/result", "chunks_per_step": pipe.n_chunks,
+                "pipeline_depth": pipe.depth, "h2d_copy_alone_ms": h2d_ms},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
