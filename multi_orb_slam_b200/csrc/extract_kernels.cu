@@ -103,11 +103,13 @@ __global__ void __launch_bounds__(128) k_pyr_resize(int level, const OrbGeom* __
     const int o1 = (a01[k] >> 16) ? o + 1 : o;
     sel[k] = (uint32_t)o | (uint32_t)o1 << 4 | 0x4400u;
   }
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(S.base) + w0;
-  const int spw = S.pitch >> 2;
-  uint32_t* dst = reinterpret_cast<uint32_t*>(drow) + wq;
-  auto hpass = [&](int sy, uint32_t (&h)[4]) {
-    const uint32_t* r = src + (size_t)sy * spw;
+  const unsigned char* src = S.base + 4 * (size_t)w0;
+  const uint32_t spitch = (uint32_t)S.pitch;
+  uint32_t live_mask = 0;  // bytes of the output word that are image columns (row padding is written as 0)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) live_mask |= live[k] ? 0xffu << (8 * k) : 0u;
+  auto hpass = [&](uint32_t sy, uint32_t (&h)[4]) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(src + (size_t)(sy * spitch));
     const uint32_t x0 = __ldg(r), x1 = __ldg(r + 1), x2 = __ldg(r + 2);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -116,15 +118,17 @@ __global__ void __launch_bounds__(128) k_pyr_resize(int level, const OrbGeom* __
     }
   };
   uint32_t hprev[4] = {0, 0, 0, 0};
-  int prev_row = -1;
+  uint32_t prev_row = 0xffffffffu;
   const int nrows = min(PYR_ROWS, rows_total - by0);
   uint2 my_t = make_uint2(0, 0);
   if (lane < nrows) my_t = __ldg(reinterpret_cast<const uint2*>(ytab + D.ytab_off + by0 + lane));
+  uint32_t* dst = reinterpret_cast<uint32_t*>(drow) + (size_t)by0 * words + wq;
 #pragma unroll 4
   for (int r = 0; r < nrows; ++r) {
     const uint32_t tlo = __shfl_sync(0xffffffffu, my_t.x, r), thi = __shfl_sync(0xffffffffu, my_t.y, r);
-    const int sy0 = tlo & 0xffff, sy1 = tlo >> 16;
-    const uint32_t b0 = thi & 0xffff, b1 = thi >> 16;
+    const uint32_t sy0 = tlo & 0xffff, sy1 = tlo >> 16;
+    // vertical weights pre-shifted by 16: (b * h) >> 16 becomes the high word of (b << 16) * h
+    const uint32_t b0 = thi << 16, b1 = thi & 0xffff0000u;
     uint32_t h0[4], h1[4];
     if (sy0 == prev_row) {
 #pragma unroll
@@ -133,15 +137,16 @@ __global__ void __launch_bounds__(128) k_pyr_resize(int level, const OrbGeom* __
       hpass(sy0, h0);
     }
     hpass(sy1, h1);
-    uint32_t out = 0;
+    uint32_t v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const uint32_t v = (((b0 * h0[k]) >> 16) + ((b1 * h1[k]) >> 16) + 2u) >> 2;
-      out |= (live[k] ? v : 0u) << (8 * k);
+      v[k] = (__umulhi(b0, h0[k]) + __umulhi(b1, h1[k]) + 2u) >> 2;  // <= 255 by construction of the weights
       hprev[k] = h1[k];
     }
     prev_row = sy1;
-    if (active) dst[(size_t)(by0 + r) * words] = out;
+    const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+    if (active) *dst = out & live_mask;
+    dst += words;
   }
 }
 

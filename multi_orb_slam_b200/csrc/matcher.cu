@@ -390,8 +390,11 @@ __global__ void __launch_bounds__(256) k_init_candidates(int cap, const orbx_key
 }
 
 #define INIT_SMEM_CAND 12288  // candidate entries staged in shared memory per pair (48 KB)
+#define INIT_NT 512           // threads of the resolve CTA: the staging of the candidate rows is a chain of
+                              // global-load latencies per warp (a row per iteration), so it wants many warps;
+                              // the ordered walk itself runs on warp 0
 
-__global__ void __launch_bounds__(128) k_init_resolve(int cap, const orbx_keypoint* __restrict__ k1_all,
+__global__ void __launch_bounds__(INIT_NT) k_init_resolve(int cap, const orbx_keypoint* __restrict__ k1_all,
                                                       const int32_t* __restrict__ n1_arr,
                                                       const orbx_keypoint* __restrict__ k2_all,
                                                       const int32_t* __restrict__ n2_arr, float* __restrict__ prev_all,
@@ -404,7 +407,7 @@ __global__ void __launch_bounds__(128) k_init_resolve(int cap, const orbx_keypoi
   __shared__ int s_hist[HISTO_LENGTH];
   __shared__ int s_keep[HISTO_LENGTH];
   __shared__ int s_nmatch, s_total;
-  __shared__ int s_wsum[4];
+  __shared__ int s_wsum[INIT_NT / 32];
   const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n1 = min(n1_arr[pair], cap), n2 = min(n2_arr[pair], cap);
   const orbx_keypoint* k1 = k1_all + (size_t)pair * cap;
@@ -423,7 +426,7 @@ __global__ void __launch_bounds__(128) k_init_resolve(int cap, const orbx_keypoi
   float* s_ang1 = reinterpret_cast<float*>(s_dyn + 7 * cap);
   float* s_ang2 = reinterpret_cast<float*>(s_dyn + 8 * cap);
   uint32_t* s_cand = reinterpret_cast<uint32_t*>(s_dyn + 9 * cap);
-  for (int i = tid; i < cap; i += 128) {
+  for (int i = tid; i < cap; i += INIT_NT) {
     s_mdist[i] = 0x7FFFFFFF;
     s_m21[i] = -1;
     s_bin[i] = -1;
@@ -437,7 +440,7 @@ __global__ void __launch_bounds__(128) k_init_resolve(int cap, const orbx_keypoi
   __syncthreads();
   // exclusive scan of the candidate counts (each thread owns a contiguous chunk of queries)
   {
-    const int chunk = (cap + 127) / 128, lo = tid * chunk, hi = min(cap, lo + chunk);
+    const int chunk = (cap + INIT_NT - 1) / INIT_NT, lo = min(cap, tid * chunk), hi = min(cap, lo + chunk);
     int s = 0;
     for (int i = lo; i < hi; ++i) s += s_cnt[i];
     int incl = s;
@@ -450,13 +453,13 @@ __global__ void __launch_bounds__(128) k_init_resolve(int cap, const orbx_keypoi
     __syncthreads();
     int run = incl - s;
     for (int w = 0; w < warp; ++w) run += s_wsum[w];
-    if (tid == 127) s_total = run + s;
+    if (tid == INIT_NT - 1) s_total = run + s;
     for (int i = lo; i < hi; ++i) { s_off[i] = run; run += s_cnt[i]; }
   }
   __syncthreads();
   const bool staged = s_total <= INIT_SMEM_CAND;
   if (staged) {  // all candidate rows of the pair into shared memory, a warp per row
-    for (int i1 = warp; i1 < n1; i1 += 4) {
+    for (int i1 = warp; i1 < n1; i1 += INIT_NT / 32) {
       const int cnt = s_cnt[i1], off = s_off[i1];
       const uint32_t* row = cand + (size_t)i1 * cap;
       for (int c = lane; c < cnt; c += 32) s_cand[off + c] = row[c];
@@ -536,7 +539,7 @@ __global__ void __launch_bounds__(128) k_init_resolve(int cap, const orbx_keypoi
     }
   }
   __syncthreads();
-  for (int i1 = tid; i1 < n1; i1 += 128) {
+  for (int i1 = tid; i1 < n1; i1 += INIT_NT) {
     int m = s_m12[i1];
     if (check_ori) {
       const int bin = s_bin[i1];
@@ -1008,7 +1011,7 @@ int orbm_search_for_initialization_device(orbm_matcher* m, int n_pairs, int cap,
     k_init_candidates<<<dim3((cap + 7) / 8, np), 256, 0, m->stream>>>(cap, d_k1 + o, d_d1 + o * 32, d_n1 + p0, d_k2 + o,
                                                                         d_d2 + o * 32, bounds2, gstart, gitems, prev,
                                                                         (float)window, cand, cand_cnt);
-    k_init_resolve<<<np, 128, smem, m->stream>>>(cap, d_k1 + o, d_n1 + p0, d_k2 + o, d_n2 + p0, prev, nnratio, check_ori,
+    k_init_resolve<<<np, INIT_NT, smem, m->stream>>>(cap, d_k1 + o, d_n1 + p0, d_k2 + o, d_n2 + p0, prev, nnratio, check_ori,
                                                  cand, cand_cnt, d_matches12 + o, d_nmatches + p0);
     m->launches += 3;
   }
