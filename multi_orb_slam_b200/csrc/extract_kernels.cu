@@ -51,18 +51,22 @@ __device__ __forceinline__ LevelView level_view(const OrbGeom* __restrict__ g, c
 }
 
 // K1 level l >= 1: cv::resize(level l-1 -> l, INTER_LINEAR) (:1122).  One WARP per tile of
-// 32 words x PYR_ROWS rows of the destination level, no shared memory, no barriers:
+// 32 words x `rows_per_tile` (<= 32) rows of the destination level, no shared memory, no barriers:
 //   * a lane owns one aligned 32-bit word = four adjacent destination columns;
 //   * its four horizontal taps live in registers; per source row it loads the three aligned words
 //     that cover its taps and picks each tap pair with one byte-permute + dp2a
 //     (h = a0*S[sx] + a1*S[sx+1]);
-//   * walking down the rows, the horizontal pass of a source row is reused when the next output
-//     row shares it (5 rows out of 6 at scale 1.2); the rows' vertical taps are fetched once per
-//     tile (lane r holds row r) and broadcast by shuffle.
+//   * the loop runs over the SOURCE rows the tile touches, each loaded and filtered exactly once,
+//     the loads of the next four rows in flight while four rows are processed (the kernel is bound
+//     by load latency, not by issue slots); an output row is emitted when its lower source row
+//     arrives (sy1 = sy0 + 1 except at the clamped bottom edge, where both taps are the last row);
+//   * the rows' vertical taps are fetched once per tile (lane r holds row r) and broadcast by
+//     shuffle.
 #define PYR_ROWS 32
+#define PYR_PREFETCH 4
 
-__global__ void __launch_bounds__(128) k_pyr_resize(int level, const OrbGeom* __restrict__ g, OrbLevel0 l0,
-                                                    const OrbXTap* __restrict__ xtab,
+__global__ void __launch_bounds__(128) k_pyr_resize(int level, int rows_per_tile, const OrbGeom* __restrict__ g,
+                                                    OrbLevel0 l0, const OrbXTap* __restrict__ xtab,
                                                     const OrbYTap* __restrict__ ytab, uint8_t* __restrict__ pyr) {
   const OrbLevelGeom& D = g->lv[level];
   const int lane = threadIdx.x & 31;
@@ -70,7 +74,7 @@ __global__ void __launch_bounds__(128) k_pyr_resize(int level, const OrbGeom* __
   const int tiles_x = (words + 31) >> 5;
   const int tile = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int ty_ = tile / tiles_x, tx_ = tile - ty_ * tiles_x;
-  const int by0 = ty_ * PYR_ROWS;
+  const int by0 = ty_ * rows_per_tile;
   if (by0 >= rows_total) return;                        // whole warp
   const bool active = tx_ * 32 + lane < words;         // lanes past the row end idle but stay for the shuffles
   const int wq = min(tx_ * 32 + lane, words - 1);
@@ -80,11 +84,11 @@ __global__ void __launch_bounds__(128) k_pyr_resize(int level, const OrbGeom* __
   uint32_t a01[4];
   int sx[4];
   int lo_col = 1 << 30;
-  bool live[4];
+  uint32_t live_mask = 0;  // bytes of the output word that are image columns
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int x = 4 * wq + k;
-    live[k] = x < D.w;
+    live_mask |= x < D.w ? 0xffu << (8 * k) : 0u;
     const OrbXTap t = xtab[D.xtab_off + min(x, D.w - 1)];  // padding columns reuse the last column's tap
     a01[k] = (uint32_t)t.a0 | (uint32_t)t.a1 << 16;
     sx[k] = t.sx;
@@ -105,48 +109,60 @@ __global__ void __launch_bounds__(128) k_pyr_resize(int level, const OrbGeom* __
   }
   const unsigned char* src = S.base + 4 * (size_t)w0;
   const uint32_t spitch = (uint32_t)S.pitch;
-  uint32_t live_mask = 0;  // bytes of the output word that are image columns (row padding is written as 0)
-#pragma unroll
-  for (int k = 0; k < 4; ++k) live_mask |= live[k] ? 0xffu << (8 * k) : 0u;
-  auto hpass = [&](uint32_t sy, uint32_t (&h)[4]) {
-    const uint32_t* r = reinterpret_cast<const uint32_t*>(src + (size_t)(sy * spitch));
-    const uint32_t x0 = __ldg(r), x1 = __ldg(r + 1), x2 = __ldg(r + 2);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t pair = __byte_perm(upper[k] ? x1 : x0, upper[k] ? x2 : x1, sel[k]);
-      h[k] = __dp2a_lo(a01[k], pair, 0u) >> 4;
-    }
-  };
-  uint32_t hprev[4] = {0, 0, 0, 0};
-  uint32_t prev_row = 0xffffffffu;
-  const int nrows = min(PYR_ROWS, rows_total - by0);
-  uint2 my_t = make_uint2(0, 0);
+  const int nrows = min(rows_per_tile, rows_total - by0);
+  uint2 my_t = make_uint2(0xffffffffu, 0);  // lanes without a row: sy1 = 0xffff never arrives
   if (lane < nrows) my_t = __ldg(reinterpret_cast<const uint2*>(ytab + D.ytab_off + by0 + lane));
+  const uint32_t s_lo = __shfl_sync(0xffffffffu, my_t.x, 0) & 0xffffu;
+  const uint32_t s_hi = __shfl_sync(0xffffffffu, my_t.x, nrows - 1) >> 16;
+  auto load = [&](uint32_t sy, uint32_t (&x)[3]) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(src + (size_t)(min(sy, s_hi) * spitch));
+    x[0] = __ldg(r); x[1] = __ldg(r + 1); x[2] = __ldg(r + 2);
+  };
+  uint32_t cur[PYR_PREFETCH][3];
+#pragma unroll
+  for (int j = 0; j < PYR_PREFETCH; ++j) load(s_lo + j, cur[j]);
   uint32_t* dst = reinterpret_cast<uint32_t*>(drow) + (size_t)by0 * words + wq;
-#pragma unroll 4
-  for (int r = 0; r < nrows; ++r) {
-    const uint32_t tlo = __shfl_sync(0xffffffffu, my_t.x, r), thi = __shfl_sync(0xffffffffu, my_t.y, r);
-    const uint32_t sy0 = tlo & 0xffff, sy1 = tlo >> 16;
-    // vertical weights pre-shifted by 16: (b * h) >> 16 becomes the high word of (b << 16) * h
-    const uint32_t b0 = thi << 16, b1 = thi & 0xffff0000u;
-    uint32_t h0[4], h1[4];
-    if (sy0 == prev_row) {
+  // taps of the next output row to emit
+  int r = 0;
+  uint32_t tlo = __shfl_sync(0xffffffffu, my_t.x, 0), thi = __shfl_sync(0xffffffffu, my_t.y, 0);
+  uint32_t hprev[4] = {0, 0, 0, 0};
+  for (uint32_t s = s_lo; s <= s_hi; s += PYR_PREFETCH) {
+    uint32_t nxt[PYR_PREFETCH][3];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) h0[k] = hprev[k];
-    } else {
-      hpass(sy0, h0);
-    }
-    hpass(sy1, h1);
-    uint32_t v[4];
+    for (int j = 0; j < PYR_PREFETCH; ++j) load(s + PYR_PREFETCH + j, nxt[j]);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      v[k] = (__umulhi(b0, h0[k]) + __umulhi(b1, h1[k]) + 2u) >> 2;  // <= 255 by construction of the weights
-      hprev[k] = h1[k];
+    for (int j = 0; j < PYR_PREFETCH; ++j) {
+      if (s + j <= s_hi) {  // warp-uniform
+        uint32_t h[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t pair = __byte_perm(upper[k] ? cur[j][1] : cur[j][0], upper[k] ? cur[j][2] : cur[j][1], sel[k]);
+          h[k] = __dp2a_lo(a01[k], pair, 0u) >> 4;
+        }
+        while ((tlo >> 16) == s + j) {  // at most twice (clamped bottom rows)
+          // vertical weights pre-shifted by 16: (b * h) >> 16 becomes the high word of (b << 16) * h
+          const uint32_t b0 = thi << 16, b1 = thi & 0xffff0000u;
+          const bool same = (tlo & 0xffffu) == s + j;  // both taps on this source row
+          uint32_t v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // <= 255 by construction of the weights
+            v[k] = (__umulhi(b0, same ? h[k] : hprev[k]) + __umulhi(b1, h[k]) + 2u) >> 2;
+          const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+          if (active) *dst = out & live_mask;
+          dst += words;
+          ++r;
+          tlo = __shfl_sync(0xffffffffu, my_t.x, r & 31);
+          thi = __shfl_sync(0xffffffffu, my_t.y, r & 31);
+          if (r >= nrows) tlo = 0xffffffffu;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hprev[k] = h[k];
+      }
     }
-    prev_row = sy1;
-    const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
-    if (active) *dst = out & live_mask;
-    dst += words;
+#pragma unroll
+    for (int j = 0; j < PYR_PREFETCH; ++j)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) cur[j][i] = nxt[j][i];
   }
 }
 
@@ -745,8 +761,13 @@ void launch_pyramid(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, uint8_t* 
                     long long* launches) {
   for (int l = 1; l < gh.g.nlevels; ++l) {
     const OrbLevelGeom& L = gh.g.lv[l];
-    const int tiles = (((L.pitch >> 2) + 31) >> 5) * ((L.h + PYR_ROWS - 1) / PYR_ROWS);
-    k_pyr_resize<<<dim3((tiles + 3) / 4, n_frames), 128, 0, st>>>(l, gh.d_geom, l0, gh.d_xtab, gh.d_ytab, d_pyr);
+    // tile height: the tallest of 32 / 16 / 8 rows that still gives every SM several waves of warps
+    // (a level's launch ends with a partial wave; short tiles keep that tail small on the small levels)
+    const int tiles_x = ((L.pitch >> 2) + 31) >> 5;
+    int rows = PYR_ROWS;
+    while (rows > 8 && (long long)tiles_x * ((L.h + rows - 1) / rows) * n_frames < 4LL * 148 * 24) rows >>= 1;
+    const int tiles = tiles_x * ((L.h + rows - 1) / rows);
+    k_pyr_resize<<<dim3((tiles + 3) / 4, n_frames), 128, 0, st>>>(l, rows, gh.d_geom, l0, gh.d_xtab, gh.d_ytab, d_pyr);
     ++*launches;
   }
 }
