@@ -76,8 +76,7 @@ __global__ void __launch_bounds__(128) k_pyr_resize(int level, int rows_per_tile
   const int ty_ = tile / tiles_x, tx_ = tile - ty_ * tiles_x;
   const int by0 = ty_ * rows_per_tile;
   if (by0 >= rows_total) return;                        // whole warp
-  const bool active = tx_ * 32 + lane < words;         // lanes past the row end idle but stay for the shuffles
-  const int wq = min(tx_ * 32 + lane, words - 1);
+  const int wq = min(tx_ * 32 + lane, words - 1);       // lanes past the row end duplicate the row's last word
   const LevelView S = level_view(g, l0, pyr, level - 1, blockIdx.y);
   uint8_t* drow = pyr + (size_t)blockIdx.y * g->pyr_frame_bytes + D.pyr_off;
   // horizontal taps of the four columns (row padding beyond w is written as 0)
@@ -95,13 +94,22 @@ __global__ void __launch_bounds__(128) k_pyr_resize(int level, int rows_per_tile
     lo_col = min(lo_col, sx[k]);
   }
   const int w0 = min(lo_col >> 2, (S.pitch >> 2) - 3);  // three words from here cover all four tap pairs
+  // Tap pair k starts at byte o = sx[k] - 4*w0 of the 12 staged bytes.  Unless the row end clamped
+  // w0 (only the last lanes of a row), o - (lo_col & 3) <= 6: the warp then aligns the staged bytes to
+  // lo_col with two funnel shifts and every pair is one byte-permute of the aligned 8 bytes.  Warps
+  // with a clamped lane pick each pair from words (0,1) or (1,2) with selects instead.
+  const int sh_bytes = lo_col - 4 * w0;
+  const int span = max(max(sx[0], sx[1]), max(sx[2], sx[3])) - lo_col;  // <= 6 up to scale factor 2
+  const bool aligned_path = __all_sync(0xffffffffu, sh_bytes < 4 && span <= 6);
+  const uint32_t sh8 = 8u * (uint32_t)(sh_bytes & 3);
   uint32_t sel[4];
-  bool upper[4];  // tap pair taken from words (1,2) instead of (0,1)
+  bool upper[4];  // tap pair taken from words (1,2) instead of (0,1) (select path)
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    int o = sx[k] - 4 * w0;  // byte offset of the left tap inside the 12 staged bytes, 0..11
+    int o = sx[k] - 4 * w0;  // 0..11
     upper[k] = o > 6;
     o -= upper[k] ? 4 : 0;
+    if (aligned_path) o = sx[k] - lo_col;  // 0..6
     // the right tap of the last source column has weight 0 (OpenCV clamps sx to sw-1 with fx = 0):
     // point it at the left tap so the window never has to reach past the row
     const int o1 = (a01[k] >> 16) ? o + 1 : o;
@@ -114,56 +122,72 @@ __global__ void __launch_bounds__(128) k_pyr_resize(int level, int rows_per_tile
   if (lane < nrows) my_t = __ldg(reinterpret_cast<const uint2*>(ytab + D.ytab_off + by0 + lane));
   const uint32_t s_lo = __shfl_sync(0xffffffffu, my_t.x, 0) & 0xffffu;
   const uint32_t s_hi = __shfl_sync(0xffffffffu, my_t.x, nrows - 1) >> 16;
-  auto load = [&](uint32_t sy, uint32_t (&x)[3]) {
-    const uint32_t* r = reinterpret_cast<const uint32_t*>(src + (size_t)(min(sy, s_hi) * spitch));
+  // source rows are walked by a 32-bit byte offset that saturates at the tile's last row
+  // (the prefetch runs up to seven rows ahead)
+  const uint32_t off_last = s_hi * spitch;
+  uint32_t off = s_lo * spitch;
+  auto load = [&](uint32_t (&x)[3]) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(src + off);
     x[0] = __ldg(r); x[1] = __ldg(r + 1); x[2] = __ldg(r + 2);
+    off = min(off + spitch, off_last);
   };
-  uint32_t cur[PYR_PREFETCH][3];
+  auto hcalc = [&](const uint32_t (&x)[3], uint32_t (&h)[4]) {
+    if (aligned_path) {
+      const uint32_t w_lo = __funnelshift_r(x[0], x[1], sh8), w_hi = __funnelshift_r(x[1], x[2], sh8);
 #pragma unroll
-  for (int j = 0; j < PYR_PREFETCH; ++j) load(s_lo + j, cur[j]);
+      for (int k = 0; k < 4; ++k) h[k] = __dp2a_lo(a01[k], __byte_perm(w_lo, w_hi, sel[k]), 0u) >> 4;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t pair = __byte_perm(upper[k] ? x[1] : x[0], upper[k] ? x[2] : x[1], sel[k]);
+        h[k] = __dp2a_lo(a01[k], pair, 0u) >> 4;
+      }
+    }
+  };
   uint32_t* dst = reinterpret_cast<uint32_t*>(drow) + (size_t)by0 * words + wq;
   // taps of the next output row to emit
   int r = 0;
   uint32_t tlo = __shfl_sync(0xffffffffu, my_t.x, 0), thi = __shfl_sync(0xffffffffu, my_t.y, 0);
-  uint32_t hprev[4] = {0, 0, 0, 0};
-  for (uint32_t s = s_lo; s <= s_hi; s += PYR_PREFETCH) {
-    uint32_t nxt[PYR_PREFETCH][3];
+  auto emit = [&](const uint32_t (&h0)[4], const uint32_t (&h1)[4]) {
+    // vertical weights pre-shifted by 16: (b * h) >> 16 becomes the high word of (b << 16) * h
+    const uint32_t b0 = thi << 16, b1 = thi & 0xffff0000u;
+    uint32_t v[4];
 #pragma unroll
-    for (int j = 0; j < PYR_PREFETCH; ++j) load(s + PYR_PREFETCH + j, nxt[j]);
+    for (int k = 0; k < 4; ++k)  // <= 255 by construction of the weights
+      v[k] = (__umulhi(b1, h1[k]) + (__umulhi(b0, h0[k]) + 2u)) >> 2;
+    const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+    *dst = out & live_mask;  // lanes past the row end repeat the last word's store (same address, same value)
+    dst += words;
+    ++r;  // r == 32 wraps to row 0, whose source rows lie behind: it never matches again
+    tlo = __shfl_sync(0xffffffffu, my_t.x, r);
+    thi = __shfl_sync(0xffffffffu, my_t.y, r);
+  };
+  uint32_t s = s_lo;
+  // one source row: horizontal pass into HN, then every output row whose lower tap is this row
+  // (at most two, at the clamped bottom edge, where the upper tap can be this row as well)
+#define PYR_ROW(X, HP, HN)                                  \
+  if (s <= s_hi) {                                          \
+    hcalc(X, HN);                                           \
+    while ((tlo >> 16) == s) {                              \
+      if ((tlo & 0xffffu) == s) emit(HN, HN);               \
+      else emit(HP, HN);                                    \
+    }                                                       \
+  }                                                         \
+  ++s;
+  uint32_t xa[PYR_PREFETCH][3], xb[PYR_PREFETCH][3];
+  uint32_t hA[4] = {0, 0, 0, 0}, hB[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int j = 0; j < PYR_PREFETCH; ++j) {
-      if (s + j <= s_hi) {  // warp-uniform
-        uint32_t h[4];
+  for (int j = 0; j < PYR_PREFETCH; ++j) load(xa[j]);
+  while (s <= s_hi) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t pair = __byte_perm(upper[k] ? cur[j][1] : cur[j][0], upper[k] ? cur[j][2] : cur[j][1], sel[k]);
-          h[k] = __dp2a_lo(a01[k], pair, 0u) >> 4;
-        }
-        while ((tlo >> 16) == s + j) {  // at most twice (clamped bottom rows)
-          // vertical weights pre-shifted by 16: (b * h) >> 16 becomes the high word of (b << 16) * h
-          const uint32_t b0 = thi << 16, b1 = thi & 0xffff0000u;
-          const bool same = (tlo & 0xffffu) == s + j;  // both taps on this source row
-          uint32_t v[4];
+    for (int j = 0; j < PYR_PREFETCH; ++j) load(xb[j]);
+    PYR_ROW(xa[0], hB, hA) PYR_ROW(xa[1], hA, hB) PYR_ROW(xa[2], hB, hA) PYR_ROW(xa[3], hA, hB)
+    if (s > s_hi) break;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // <= 255 by construction of the weights
-            v[k] = (__umulhi(b0, same ? h[k] : hprev[k]) + __umulhi(b1, h[k]) + 2u) >> 2;
-          const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
-          if (active) *dst = out & live_mask;
-          dst += words;
-          ++r;
-          tlo = __shfl_sync(0xffffffffu, my_t.x, r & 31);
-          thi = __shfl_sync(0xffffffffu, my_t.y, r & 31);
-          if (r >= nrows) tlo = 0xffffffffu;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) hprev[k] = h[k];
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < PYR_PREFETCH; ++j)
-#pragma unroll
-      for (int i = 0; i < 3; ++i) cur[j][i] = nxt[j][i];
+    for (int j = 0; j < PYR_PREFETCH; ++j) load(xa[j]);
+    PYR_ROW(xb[0], hB, hA) PYR_ROW(xb[1], hA, hB) PYR_ROW(xb[2], hB, hA) PYR_ROW(xb[3], hA, hB)
   }
+#undef PYR_ROW
 }
 
 // ------------------------------------------------------------------------------------------
