@@ -222,7 +222,6 @@ struct FastSmem {
   uint16_t* queue;     // (aliases hv) phase-A survivors (byte offsets into img / m), written after phase A
   uint8_t* m;          // arc measure map, 0 = not a corner at the pass threshold; zeroed after phase A
   uint16_t* eq;        // (aliases m) phase A's word entries
-  int* misc;           // [1] kept count
 };
 
 template <int PITCH>
@@ -249,18 +248,6 @@ __device__ __forceinline__ int fast_arc_measure(const uint8_t* p) {
   }
   const int c = p[0];
   return max((int)(best & 0xffffu) - c, (int)(best >> 16) - 255 + c);
-}
-
-// Warp-aggregated append to a shared-memory list.
-__device__ __forceinline__ void fast_push(bool pred, uint16_t value, uint16_t* list, int* counter) {
-  const unsigned bm = __ballot_sync(0xffffffffu, pred);
-  if (bm) {
-    const int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(counter, __popc(bm));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (pred) list[base + __popc(bm & ((1u << lane) - 1u))] = value;
-  }
 }
 
 // One threshold pass over the tested area (tw x thh pixels starting at sub-image (3,3)).
@@ -330,39 +317,48 @@ __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int
       if (nib >> k & 1) sm.queue[pos++] = (uint16_t)(boff + k);
     nq += __shfl_sync(0xffffffffu, incl, 31);
   }
-  if (lane == 0) sm.misc[1] = 0;
   __syncwarp();
   // the entries are consumed: their region becomes the (zeroed) measure map
   for (int i = lane; i < ch * (PITCH / 16); i += 32) reinterpret_cast<uint4*>(sm.m)[i] = make_uint4(0, 0, 0, 0);
   __syncwarp();
-  // phase B: full measure for the survivors (dense lanes)
-  for (int q = lane; q < nq; q += 32) {
-    const int off = sm.queue[q];
+  // phase B: full measure for the survivors (dense lanes); the corners are compacted in place at
+  // the front of the queue (the write position never passes the read position)
+  int nc = 0;
+  for (int q0 = 0; q0 < nq; q0 += 32) {
+    const bool valid = q0 + lane < nq;
+    const int off = valid ? sm.queue[q0 + lane] : 3 * PITCH + 4;  // idle lanes measure the first tested pixel
     const int m = fast_arc_measure<PITCH>(sm.img + off);
-    if (m > th) sm.m[off] = (uint8_t)m;
+    const bool corner = valid && m > th;
+    if (corner) sm.m[off] = (uint8_t)m;
+    const unsigned bm = __ballot_sync(0xffffffffu, corner);
+    __syncwarp();
+    if (corner) sm.queue[nc + __popc(bm & lt)] = (uint16_t)off;
+    nc += __popc(bm);
   }
   __syncwarp();
   // phase C: 3x3 NMS of the corners.  Neighbours outside the tested area hold 0; comparing raw m
   // values equals comparing thresholded scores because every stored m exceeds the pass threshold.
-  for (int q0 = 0; q0 < nq; q0 += 32) {
+  // Queue, corner list and survivor list all stay in row-major order (one warp, ordered
+  // compaction) = cv::FAST's output order.
+  int nk = 0;
+  for (int q0 = 0; q0 < nc; q0 += 32) {
     const int q = q0 + lane;
     bool keep = false;
     int off = 0;
-    if (q < nq) {
+    if (q < nc) {
       off = sm.queue[q];
       const uint8_t* c = sm.m + off;
-      const int mv = c[0];
-      if (mv > th) {
-        const int n1_ = __vimax3_s32((int)c[-1], (int)c[1], (int)c[-PITCH]);
-        const int n2_ = __vimax3_s32((int)c[PITCH], (int)c[-PITCH - 1], (int)c[-PITCH + 1]);
-        const int n3_ = __vimax3_s32((int)c[PITCH - 1], (int)c[PITCH + 1], n1_);
-        keep = mv > max(n2_, n3_);
-      }
+      const int n1_ = __vimax3_s32((int)c[-1], (int)c[1], (int)c[-PITCH]);
+      const int n2_ = __vimax3_s32((int)c[PITCH], (int)c[-PITCH - 1], (int)c[-PITCH + 1]);
+      const int n3_ = __vimax3_s32((int)c[PITCH - 1], (int)c[PITCH + 1], n1_);
+      keep = (int)c[0] > max(n2_, n3_);
     }
-    fast_push(keep, (uint16_t)off, sm.kept, &sm.misc[1]);
+    const unsigned bm = __ballot_sync(0xffffffffu, keep);
+    if (keep) sm.kept[nk + __popc(bm & lt)] = (uint16_t)off;
+    nk += __popc(bm);
   }
   __syncwarp();
-  return sm.misc[1];
+  return nk;
 }
 
 template <int PITCH>
@@ -380,7 +376,6 @@ __global__ void __launch_bounds__(FAST_NT) k_fast_cells(const OrbCell* __restric
   sm.queue = reinterpret_cast<uint16_t*>(sm.hv);
   sm.m = sm.hv + r_q;
   sm.eq = reinterpret_cast<uint16_t*>(sm.m);
-  sm.misc = reinterpret_cast<int*>(sm.m + r_img);
 
   // one 32-byte record tells the CTA everything about its cell
   const uint4* crec = reinterpret_cast<const uint4*>(cells + blockIdx.x);
@@ -433,16 +428,14 @@ __global__ void __launch_bounds__(FAST_NT) k_fast_cells(const OrbCell* __restric
       total = fast_pass<PITCH>(sm, th, tw, thh, ch);
     }
   }
-  // ordered write-out: rank of each survivor = number of survivors before it in row-major order
-  // (byte offsets into the pitched map are monotone in (y, x)) = cv::FAST's output order
+  // write-out: the survivor list is already in row-major order (byte offsets into the pitched
+  // map are monotone in (y, x))
   total = min(total, (int)cell.cand_cap);
   uint32_t* out = cand + (size_t)frame * cand_frame_u32 + cell.cand_slot_off;
   for (int i = tid; i < total; i += FAST_NT) {
     const int off = sm.kept[i];
-    int rank = 0;
-    for (int j = 0; j < total; ++j) rank += sm.kept[j] < off;
     const int y = off / PITCH, x = off - y * PITCH - 1;
-    out[rank] = (uint32_t)(x + cell.off_x) | (uint32_t)(y + cell.off_y) << 12 | ((uint32_t)sm.m[off] - 1u) << 24;
+    out[i] = (uint32_t)(x + cell.off_x) | (uint32_t)(y + cell.off_y) << 12 | ((uint32_t)sm.m[off] - 1u) << 24;
   }
   if (tid == 0) cell_count[(size_t)frame * n_cells + blockIdx.x] = total;
 }
