@@ -327,15 +327,15 @@ __device__ __forceinline__ void grid_query(const GridView& gv, const orbx_keypoi
   }
 }
 
-// Warp-wide lexicographic top-2 over packed keys (smaller = better); all lanes get the result.
+// Warp-wide top-2 over packed keys (smaller = better); all lanes get the result.  Keys carry the
+// candidate position, so they are unique except for the empty marker 0xFFFFFFFF: the warp's second
+// best is the minimum over each lane's runner-up, where the lane that owns the best contributes
+// its own second.  Two REDUX instructions instead of a ten-shuffle butterfly (this sits on the
+// serial chain of the ordered resolve kernels).
 __device__ __forceinline__ void warp_top2(uint32_t& best, uint32_t& second) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o);
-    const uint32_t nb = min(best, ob);
-    second = min(max(best, ob), min(second, os));
-    best = nb;
-  }
+  const uint32_t gb = __reduce_min_sync(0xffffffffu, best);
+  second = __reduce_min_sync(0xffffffffu, best == gb ? second : best);
+  best = gb;
 }
 
 // ---- SearchForInitialization ----------------------------------------------------------------
