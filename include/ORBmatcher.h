@@ -7,14 +7,16 @@
  *   DescriptorDistance(a, b)                                       src/ORBmatcher.cc:3994-4010
  *   SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, w) src/ORBmatcher.cc:868-983
  *   SearchByProjection(F, vpMapPoints, th)                          src/ORBmatcher.cc:62-149
+ *   SearchByBoW_cam1(pKF, F, vpMapPointMatches)                     src/ORBmatcher.cc:390-565
  * It is a template over the caller's Frame / MapPoint types so it compiles against the reference's
  * own include/Frame.h and include/MapPoint.h without modification (members used are listed at each
- * function).  Everything else in the reference's ORBmatcher (BoW, Fuse, Sim3 searches) is outside
- * this drop-in and stays with the reference implementation.
+ * function).  The other SearchByBoW / SearchByProjection variants are reachable through the flat
+ * entry points of orb_b200.h; Fuse and the Sim3 searches stay with the reference implementation.
  */
 #ifndef ORBMATCHER_B200_H
 #define ORBMATCHER_B200_H
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -113,7 +115,59 @@ class ORBmatcherB200 {
     return nmatches;
   }
 
+  /* int SearchByBoW_cam1(KeyFrame* pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches)   (:390-565)
+   * reads pKF->GetMapPointMatches_cam1(), mFeatVec_cam1, mDescriptors, mvKeysUn, N;
+   *       F.mFeatVec_cam1, F.mDescriptors, F.mvKeys, F.N; isBad() of the key frame's map points.
+   * FeatureVector = std::map<node id, std::vector<unsigned int>> (DBoW2), walked in map order. */
+  template <class KeyFrameT, class FrameT, class MapPointT>
+  int SearchByBoW_cam1(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches) {
+    const std::vector<MapPointT*> vpMapPointsKF = pKF->GetMapPointMatches_cam1();
+    const int n1 = (int)pKF->N, n2 = (int)F.N;
+    vpMapPointMatches.assign(n2, static_cast<MapPointT*>(nullptr));
+    std::vector<int32_t> valid1(std::max(n1, 1), 0);
+    for (int i = 0; i < n1; ++i) valid1[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad();
+    std::vector<float> a1(std::max(n1, 1)), a2(std::max(n2, 1));
+    std::vector<uint8_t> d1((size_t)std::max(n1, 1) * 32), d2((size_t)std::max(n2, 1) * 32);
+    for (int i = 0; i < n1; ++i) {
+      a1[i] = pKF->mvKeysUn[i].angle;
+      std::copy(pKF->mDescriptors.ptr(i), pKF->mDescriptors.ptr(i) + 32, d1.begin() + (size_t)i * 32);
+    }
+    for (int i = 0; i < n2; ++i) {
+      a2[i] = F.mvKeys[i].angle;
+      std::copy(F.mDescriptors.ptr(i), F.mDescriptors.ptr(i) + 32, d2.begin() + (size_t)i * 32);
+    }
+    FlatFeatVec f1, f2;
+    f1.fill(pKF->mFeatVec_cam1, n1);  // indices >= N (camera 2) are dropped, like `realIdxKF >= pKF->N` (:432)
+    f2.fill(F.mFeatVec_cam1, n2);
+    std::vector<int32_t> m12(std::max(n1, 1)), m21(std::max(n2, 1));
+    int nmatches = 0;
+    check(orbm_search_by_bow_host(m_, d1.data(), a1.data(), valid1.data(), n1, f1.view(), d2.data(), a2.data(), nullptr, n2,
+                                  f2.view(), mfNNratio, mbCheckOrientation ? 1 : 0, TH_LOW, m12.data(), m21.data(),
+                                  &nmatches));
+    for (int i = 0; i < n2; ++i)
+      if (m21[i] >= 0) vpMapPointMatches[i] = vpMapPointsKF[m21[i]];
+    return nmatches;
+  }
+
  protected:
+  struct FlatFeatVec {  // DBoW2::FeatureVector -> CSR
+    std::vector<int32_t> node, start, items;
+    template <class MapT>
+    void fill(const MapT& fv, int n_limit) {
+      start.push_back(0);
+      for (typename MapT::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+        node.push_back((int32_t)it->first);
+        for (size_t j = 0; j < it->second.size(); ++j)
+          if ((int)it->second[j] < n_limit) items.push_back((int32_t)it->second[j]);
+        start.push_back((int32_t)items.size());
+      }
+    }
+    orbm_featvec view() const {
+      orbm_featvec v = {node.data(), start.data(), items.data(), (int32_t)node.size()};
+      return v;
+    }
+  };
+
   void check(int rc) {
     if (rc != ORBX_OK) throw std::runtime_error(std::string("orb_b200: ") + orbm_last_error(m_));
   }

@@ -253,6 +253,33 @@ int orbm_search_by_projection_sim3_host(orbm_matcher* m, const orbx_keypoint* kf
                                         const float* mp_max_d, const uint8_t* mp_desc, int n_mp, int th, int32_t* matched,
                                         int* nmatches);
 
+/* DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned int>>, Thirdparty/DBoW2/DBoW2/FeatureVector.h)
+ * flattened to CSR: node ids ascending (the map's order), start[n_nodes + 1], items = feature indices in
+ * vector order.  A feature index occurs at most once per vector (DBoW2 guarantees it). */
+typedef struct {
+  const int32_t* node_id;
+  const int32_t* start;
+  const int32_t* items;
+  int32_t n_nodes;
+} orbm_featvec;
+
+/* ORBmatcher::SearchByBoW, all four variants:
+ *   SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches)        src/ORBmatcher.cc:206-388   (Tracking.cc:1238, 2031)
+ *   SearchByBoW_cam1(KeyFrame*, Frame&, vpMapPointMatches)   src/ORBmatcher.cc:390-565
+ *   SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12)           src/ORBmatcher.cc:996-1163  (LoopClosing.cc:329)
+ *   SearchByBoW_cam1(KeyFrame*, KeyFrame*, vpMatches12)      src/ORBmatcher.cc:1180-1363
+ * Side 1 = the key frame whose map points are searched for, side 2 = the frame / second key frame.
+ *   valid1[i] = map point exists && !isBad() (&& i < N for the _cam1 variants; NULL = all valid);
+ *   valid2[i] likewise for the KeyFrame variants, (i < N) for SearchByBoW_cam1(KeyFrame*, Frame&), NULL = all;
+ *   angle = mvKeysUn(_total)[i].angle of side 1, mvKeys(_total)[i].angle of side 2;
+ *   max_dist = TH_LOW (Frame variants, `bestDist1<=TH_LOW`) or TH_LOW-1 (KeyFrame variants, `bestDist1<TH_LOW`).
+ * matches12 (n1): matched side-2 feature or -1 (vpMatches12[i1] = vpMapPoints2[matches12[i1]]);
+ * matches21 (n2, may be NULL): matched side-1 feature or -1 (vpMapPointMatches[i2] = map point of it). */
+int orbm_search_by_bow_host(orbm_matcher* m, const uint8_t* desc1, const float* angle1, const int32_t* valid1, int n1,
+                            orbm_featvec fv1, const uint8_t* desc2, const float* angle2, const int32_t* valid2, int n2,
+                            orbm_featvec fv2, float nnratio, int check_ori, int max_dist, int32_t* matches12,
+                            int32_t* matches21, int* nmatches);
+
 #ifdef __cplusplus
 }
 #endif

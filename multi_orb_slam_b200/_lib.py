@@ -35,6 +35,11 @@ class Camera(C.Structure):
                 ("mbf", C.c_float)]
 
 
+class FeatVec(C.Structure):
+    """orbm_featvec: DBoW2::FeatureVector flattened to CSR (node ids ascending)."""
+    _fields_ = [("node_id", C.c_void_p), ("start", C.c_void_p), ("items", C.c_void_p), ("n_nodes", C.c_int32)]
+
+
 class Bounds(C.Structure):
     _fields_ = [("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
 
@@ -88,6 +93,8 @@ _SIGS = {
                                                     _vp, _vp, _vp, _i, _f, _i, _i, _vp, C.POINTER(_i)]),
     "orbm_search_by_projection_sim3_host": (_i, [_vp, _vp, _vp, _vp, _i, Bounds, _vp, _i, _f, Camera, _vp, _vp, _vp, _vp, _vp,
                                                 _vp, _vp, _vp, _vp, _i, _i, _vp, C.POINTER(_i)]),
+    "orbm_search_by_bow_host": (_i, [_vp, _vp, _vp, _vp, _i, FeatVec, _vp, _vp, _vp, _i, FeatVec, _f, _i, _i, _vp, _vp,
+                                    C.POINTER(_i)]),
 }
 EXPORTS = tuple(_SIGS)
 for _name, (_res, _args) in _SIGS.items():

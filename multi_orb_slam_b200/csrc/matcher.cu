@@ -338,6 +338,19 @@ __device__ __forceinline__ void warp_top2(uint32_t& best, uint32_t& second) {
   best = gb;
 }
 
+__device__ __forceinline__ void three_maxima_keep(const int* hist, int* keep) {  // :3948-3989, one thread
+  int max1 = 0, max2 = 0, max3 = 0, i1_ = -1, i2_ = -1, i3_ = -1;
+  for (int i = 0; i < HISTO_LENGTH; ++i) {
+    const int s = hist[i];
+    if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3_ = i2_; i2_ = i1_; i1_ = i; }
+    else if (s > max2) { max3 = max2; max2 = s; i3_ = i2_; i2_ = i; }
+    else if (s > max3) { max3 = s; i3_ = i; }
+  }
+  if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2_ = -1; i3_ = -1; }
+  else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { i3_ = -1; }
+  for (int i = 0; i < HISTO_LENGTH; ++i) keep[i] = (i == i1_ || i == i2_ || i == i3_);
+}
+
 // ---- SearchForInitialization ----------------------------------------------------------------
 // Phase A (k_init_candidates, one warp per (pair, i1), whole GPU): for each level-0 keypoint i1
 // of F1, the window query on F2's grid and the Hamming distances; candidates are stored in the
@@ -524,18 +537,7 @@ __global__ void __launch_bounds__(INIT_NT) k_init_resolve(int cap, const orbx_ke
     }
     if (lane == 0) {
       s_nmatch = nmatches;
-      if (check_ori) {  // ComputeThreeMaxima (:3948-3989)
-        int max1 = 0, max2 = 0, max3 = 0, i1_ = -1, i2_ = -1, i3_ = -1;
-        for (int i = 0; i < HISTO_LENGTH; ++i) {
-          const int s = s_hist[i];
-          if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3_ = i2_; i2_ = i1_; i1_ = i; }
-          else if (s > max2) { max3 = max2; max2 = s; i3_ = i2_; i2_ = i; }
-          else if (s > max3) { max3 = s; i3_ = i; }
-        }
-        if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2_ = -1; i3_ = -1; }
-        else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { i3_ = -1; }
-        for (int i = 0; i < HISTO_LENGTH; ++i) s_keep[i] = (i == i1_ || i == i2_ || i == i3_);
-      }
+      if (check_ori) three_maxima_keep(s_hist, s_keep);  // ComputeThreeMaxima (:3948-3989)
     }
   }
   __syncthreads();
@@ -556,6 +558,123 @@ __global__ void __launch_bounds__(INIT_NT) k_init_resolve(int cap, const orbx_ke
   }
   __syncthreads();
   if (tid == 0) nmatches_out[pair] = s_nmatch;
+}
+
+// ---- SearchByBoW (:206-388, 390-565, 996-1163, 1180-1363) ------------------------------------
+// The host walks the two feature vectors (node ids are a few hundred ints) and emits one query
+// per valid side-1 feature of a common node: {idx1, first side-2 item, item count, row offset}.
+// Phase A (k_bow_candidates, warp per query): distances to the node's side-2 features, stored in
+// vector order as (dist << 16 | idx2), dist = 0xFFFF for features that are not valid.
+// Phase B (k_bow_resolve, one CTA; warp 0 walks the queries in the reference's order): skip
+// side-2 features already matched (:296-297, :1061), strict-< best / second from 256, acceptance,
+// rotation histogram; then three maxima and the removal pass in parallel.
+struct BowQuery {
+  int32_t idx1, t0, cnt, off;
+};
+
+__global__ void __launch_bounds__(256) k_bow_candidates(const BowQuery* __restrict__ q, int nq,
+                                                        const uint8_t* __restrict__ d1, const uint8_t* __restrict__ d2,
+                                                        const int32_t* __restrict__ valid2,
+                                                        const int32_t* __restrict__ items2, uint32_t* __restrict__ rows) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= nq) return;
+  const BowQuery bq = q[i];
+  const uint4* qp = reinterpret_cast<const uint4*>(d1 + (size_t)bq.idx1 * 32);
+  const uint4 qa = __ldg(qp), qb = __ldg(qp + 1);
+  for (int c = lane; c < bq.cnt; c += 32) {
+    const int idx2 = items2[bq.t0 + c];
+    uint32_t dist = 0xFFFFu;
+    if (!valid2 || valid2[idx2]) {
+      const uint4* tp = reinterpret_cast<const uint4*>(d2 + (size_t)idx2 * 32);
+      dist = (uint32_t)hamming256(qa, qb, __ldg(tp), __ldg(tp + 1));
+    }
+    rows[bq.off + c] = dist << 16 | (uint32_t)idx2;
+  }
+}
+
+#define BOW_SMEM_ROWS 12288  // candidate entries staged in shared memory (48 KB)
+
+__global__ void __launch_bounds__(256) k_bow_resolve(const BowQuery* __restrict__ q, int nq, int total_rows,
+                                                     const uint32_t* __restrict__ rows, const float* __restrict__ angle1,
+                                                     const float* __restrict__ angle2, int n2, float nnratio, int check_ori,
+                                                     int max_dist, int32_t* __restrict__ matches12,
+                                                     int32_t* __restrict__ matches21, int32_t* __restrict__ q_bin,
+                                                     int* __restrict__ nmatches_out) {
+  extern __shared__ uint32_t s_bow[];  // [n2 / 32 + 1] matched bits of side 2, then the staged rows
+  __shared__ int s_hist[HISTO_LENGTH];
+  __shared__ int s_keep[HISTO_LENGTH];
+  __shared__ int s_nmatch;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nwords = n2 / 32 + 1;
+  uint32_t* s_taken = s_bow;
+  uint32_t* s_rows = s_bow + nwords;
+  const bool staged = total_rows <= BOW_SMEM_ROWS;
+  for (int i = tid; i < nwords; i += 256) s_taken[i] = 0;
+  if (staged)
+    for (int i = tid; i < total_rows; i += 256) s_rows[i] = rows[i];
+  if (tid < HISTO_LENGTH) s_hist[tid] = 0;
+  __syncthreads();
+  const uint32_t* R = staged ? s_rows : rows;
+  if (tid < 32) {
+    int nmatches = 0;
+    for (int j = 0; j < nq; ++j) {
+      const BowQuery bq = q[j];
+      // key = dist << 16 | position in the node's vector: the strict-< scan order (:311-321)
+      uint32_t best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
+      for (int c = lane; c < bq.cnt; c += 32) {
+        const uint32_t e = R[bq.off + c];
+        const uint32_t idx2 = e & 0xFFFFu;
+        if ((e >> 16) == 0xFFFFu || (s_taken[idx2 >> 5] >> (idx2 & 31) & 1u)) continue;
+        const uint32_t key = (e & 0xFFFF0000u) | (uint32_t)c;
+        second = min(second, max(best, key));
+        best = min(best, key);
+      }
+      warp_top2(best, second);
+      int bin = -1;
+      if (best != 0xFFFFFFFFu) {
+        const int bestDist1 = (int)(best >> 16);
+        const int bestDist2 = second == 0xFFFFFFFFu ? 256 : (int)(second >> 16);
+        if (bestDist1 <= max_dist && (float)bestDist1 < __fmul_rn(nnratio, (float)bestDist2)) {
+          const int idx2 = (int)(R[bq.off + (int)(best & 0xFFFFu)] & 0xFFFFu);
+          if (lane == 0) {
+            s_taken[idx2 >> 5] |= 1u << (idx2 & 31);
+            matches12[bq.idx1] = idx2;
+            bin = HISTO_LENGTH;  // matched, no orientation bin
+            if (check_ori) {
+              float rot = __fsub_rn(angle1[bq.idx1], angle2[idx2]);
+              if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+              bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
+              if (bin == HISTO_LENGTH) bin = 0;
+              s_hist[bin]++;
+            }
+          }
+          nmatches++;
+          __syncwarp();
+        }
+      }
+      if (lane == 0) q_bin[j] = bin;
+    }
+    if (lane == 0) {
+      s_nmatch = nmatches;
+      if (check_ori) three_maxima_keep(s_hist, s_keep);
+    }
+  }
+  __syncthreads();
+  // removal pass (:365-383) and the side-2 view of the matches
+  for (int j = tid; j < nq; j += 256) {
+    const int bin = q_bin[j];
+    if (bin < 0) continue;
+    const int idx1 = q[j].idx1;
+    if (check_ori && !s_keep[bin]) {
+      matches12[idx1] = -1;
+      atomicSub(&s_nmatch, 1);
+    } else {
+      matches21[matches12[idx1]] = idx1;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) *nmatches_out = s_nmatch;
 }
 
 // ---- SearchByProjection(Frame&, vector<MapPoint*>&, th) ------------------------------------
@@ -1118,6 +1237,81 @@ int orbm_search_by_projection_points_host(orbm_matcher* m, const orbx_keypoint* 
   cudaMemcpyAsync(nmatches, misc + 1, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (!m->check(cudaStreamSynchronize(st), "search_by_projection")) return ORBX_E_CUDA;
   return m->check(cudaGetLastError(), "search_by_projection launch") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+int orbm_search_by_bow_host(orbm_matcher* m, const uint8_t* desc1, const float* angle1, const int32_t* valid1, int n1,
+                            orbm_featvec fv1, const uint8_t* desc2, const float* angle2, const int32_t* valid2, int n2,
+                            orbm_featvec fv2, float nnratio, int check_ori, int max_dist, int32_t* matches12,
+                            int32_t* matches21, int* nmatches) {
+  if (!m || !matches12 || !nmatches || n1 < 0 || n2 < 0 || n1 > 65535 || n2 > 65535 || fv1.n_nodes < 0 || fv2.n_nodes < 0 ||
+      (n1 && (!desc1 || !angle1)) || (n2 && (!desc2 || !angle2)) ||
+      (fv1.n_nodes && (!fv1.node_id || !fv1.start || !fv1.items)) || (fv2.n_nodes && (!fv2.node_id || !fv2.start || !fv2.items)))
+    return ORBX_E_INVALID;
+  *nmatches = 0;
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  if (matches21)
+    for (int i = 0; i < n2; ++i) matches21[i] = -1;
+  // the walk of the two std::map's with lower_bound jumps (:350-359), emitting the queries
+  std::vector<BowQuery> queries;
+  int total = 0, a = 0, b = 0;
+  while (a < fv1.n_nodes && b < fv2.n_nodes) {
+    const int32_t na = fv1.node_id[a], nb = fv2.node_id[b];
+    if (na == nb) {
+      const int t0 = fv2.start[b], cnt = fv2.start[b + 1] - t0;
+      for (int p = fv1.start[a]; p < fv1.start[a + 1]; ++p) {
+        const int idx1 = fv1.items[p];
+        if (idx1 < 0 || idx1 >= n1) { m->err = "feature vector 1: index out of range"; return ORBX_E_INVALID; }
+        if (valid1 && !valid1[idx1]) continue;
+        if (cnt > 0) { queries.push_back({idx1, t0, cnt, total}); total += cnt; }
+      }
+      ++a; ++b;
+    } else if (na < nb) {
+      a = (int)(std::lower_bound(fv1.node_id + a, fv1.node_id + fv1.n_nodes, nb) - fv1.node_id);
+    } else {
+      b = (int)(std::lower_bound(fv2.node_id + b, fv2.node_id + fv2.n_nodes, na) - fv2.node_id);
+    }
+  }
+  const int nq = (int)queries.size();
+  if (nq == 0) return ORBX_OK;
+  const int n_items2 = fv2.start[fv2.n_nodes];
+  for (int i = 0; i < n_items2; ++i)
+    if (fv2.items[i] < 0 || fv2.items[i] >= n2) { m->err = "feature vector 2: index out of range"; return ORBX_E_INVALID; }
+  cudaSetDevice(m->device);
+  cudaStream_t st = m->stream;
+  uint8_t* dd = m->scratch<uint8_t>(8, ((size_t)n1 + n2) * 32);
+  float* dang = m->scratch<float>(9, (size_t)n1 + n2);
+  int32_t* dints = m->scratch<int32_t>(4, (size_t)n2 + n_items2 + n1 + n2 + nq + 8);
+  BowQuery* dq = m->scratch<BowQuery>(5, nq);
+  uint32_t* rows = m->scratch<uint32_t>(6, (size_t)total);
+  if (!dd || !dang || !dints || !dq || !rows) return ORBX_E_CUDA;
+  uint8_t *dd1 = dd, *dd2 = dd + (size_t)n1 * 32;
+  float *da1 = dang, *da2 = dang + n1;
+  int32_t* dvalid2 = dints;
+  int32_t* ditems2 = dvalid2 + n2;
+  int32_t* dm12 = ditems2 + n_items2;
+  int32_t* dm21 = dm12 + n1;
+  int32_t* dbin = dm21 + n2;
+  int* dnm = dbin + nq;
+  cudaMemcpyAsync(dd1, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dd2, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(da1, angle1, sizeof(float) * n1, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(da2, angle2, sizeof(float) * n2, cudaMemcpyHostToDevice, st);
+  if (valid2) cudaMemcpyAsync(dvalid2, valid2, sizeof(int32_t) * n2, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(ditems2, fv2.items, sizeof(int32_t) * n_items2, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dq, queries.data(), sizeof(BowQuery) * nq, cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(dm12, 0xFF, sizeof(int32_t) * ((size_t)n1 + n2), st);  // matches12 and matches21 = -1
+  const size_t smem = sizeof(uint32_t) * ((size_t)(n2 / 32 + 1) + (total <= BOW_SMEM_ROWS ? total : 0));
+  if (smem > 48 * 1024 &&
+      !m->check(cudaFuncSetAttribute(k_bow_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "smem opt-in"))
+    return ORBX_E_CUDA;
+  k_bow_candidates<<<(nq + 7) / 8, 256, 0, st>>>(dq, nq, dd1, dd2, valid2 ? dvalid2 : nullptr, ditems2, rows);
+  k_bow_resolve<<<1, 256, smem, st>>>(dq, nq, total, rows, da1, da2, n2, nnratio, check_ori, max_dist, dm12, dm21, dbin, dnm);
+  m->launches += 2;
+  cudaMemcpyAsync(matches12, dm12, sizeof(int32_t) * n1, cudaMemcpyDeviceToHost, st);
+  if (matches21) cudaMemcpyAsync(matches21, dm21, sizeof(int32_t) * n2, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(nmatches, dnm, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (!m->check(cudaStreamSynchronize(st), "search_by_bow")) return ORBX_E_CUDA;
+  return m->check(cudaGetLastError(), "search_by_bow launch") ? ORBX_OK : ORBX_E_CUDA;
 }
 
 // ---- pose-based SearchByProjection overloads ------------------------------------------------

@@ -251,3 +251,38 @@ class ORBmatcher:
             matched.ctypes.data, C.byref(nm)))
         kf.mvpMapPoints = matched
         return nm.value
+
+    # -- SearchByBoW, Frame and KeyFrame variants (src/ORBmatcher.cc:206-388, 390-565, 996-1163, 1180-1363) --
+    def SearchByBoW(self, desc1, angle1, valid1, featvec1, desc2, angle2, valid2, featvec2, *, keyframe_pair: bool = False):
+        """Side 1 = key frame whose map points are searched (valid1[i] = map point exists and is not
+        bad), side 2 = frame (keyframe_pair=False: `bestDist1<=TH_LOW`, :324) or second key frame
+        (keyframe_pair=True: `bestDist1<TH_LOW`, :1107).  featvec = (node_ids ascending, start, items),
+        the CSR form of DBoW2::FeatureVector (see synth.feature_vector).  For the _cam1 variants clear
+        valid1/valid2 for indices >= N.  Returns (nmatches, matches12 [n1], matches21 [n2])."""
+        d1 = np.ascontiguousarray(desc1, dtype=np.uint8).reshape(-1, 32)
+        d2 = np.ascontiguousarray(desc2, dtype=np.uint8).reshape(-1, 32)
+        a1 = np.ascontiguousarray(angle1, dtype=np.float32)
+        a2 = np.ascontiguousarray(angle2, dtype=np.float32)
+        n1, n2 = len(d1), len(d2)
+        if len(a1) != n1 or len(a2) != n2:
+            raise ValueError("angle arrays must match the descriptor counts")
+        v1 = None if valid1 is None else np.ascontiguousarray(valid1, dtype=np.int32)
+        v2 = None if valid2 is None else np.ascontiguousarray(valid2, dtype=np.int32)
+        keep = []
+
+        def fv(t):
+            arrs = [np.ascontiguousarray(x, dtype=np.int32) for x in t]
+            if len(arrs[1]) != len(arrs[0]) + 1:
+                raise ValueError("feature vector: start must have n_nodes + 1 entries")
+            keep.extend(arrs)
+            return _lib.FeatVec(arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, len(arrs[0]))
+
+        m12 = np.empty(n1, dtype=np.int32)
+        m21 = np.empty(n2, dtype=np.int32)
+        nm = C.c_int(0)
+        check_m(self._h, lib.orbm_search_by_bow_host(
+            self._h, d1.ctypes.data, a1.ctypes.data, None if v1 is None else v1.ctypes.data, n1, fv(featvec1),
+            d2.ctypes.data, a2.ctypes.data, None if v2 is None else v2.ctypes.data, n2, fv(featvec2),
+            self.mfNNratio, int(self.mbCheckOrientation), self.TH_LOW - 1 if keyframe_pair else self.TH_LOW,
+            m12.ctypes.data, m21.ctypes.data, C.byref(nm)))
+        return nm.value, m12, m21

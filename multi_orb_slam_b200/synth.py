@@ -100,3 +100,33 @@ def perturbed_descriptors(desc: np.ndarray, seed: int, max_flips: int = 80, perm
     flip = np.argsort(np.argsort(r, axis=1), axis=1) < k[:, None]
     bits ^= flip.astype(np.uint8)
     return np.packbits(bits, axis=1), perm
+
+
+def feature_vector(node_of_feature: np.ndarray):
+    """DBoW2::FeatureVector (std::map<node id, vector<feature index>>) flattened to CSR:
+    (node_ids ascending, start[nn + 1], items) with the items of a node in ascending feature
+    index, the order DBoW2's transform() appends them.  Features with node id < 0 are left out."""
+    node_of_feature = np.asarray(node_of_feature, dtype=np.int64)
+    idx = np.nonzero(node_of_feature >= 0)[0]
+    order = idx[np.argsort(node_of_feature[idx], kind="stable")]
+    nodes, counts = np.unique(node_of_feature[order], return_counts=True)
+    start = np.zeros(len(nodes) + 1, dtype=np.int32)
+    start[1:] = np.cumsum(counts)
+    return nodes.astype(np.int32), start, order.astype(np.int32)
+
+
+def bow_scene(n1: int, n2: int, n_nodes: int, seed: int, p_same_node: float = 0.85, max_flips: int = 70):
+    """Two feature sets for SearchByBoW: side 2 holds noisy copies of random side-1 features, most
+    of them in the same vocabulary node.  Returns dict(d1, a1, node1, d2, a2, node2, src)."""
+    rng = np.random.default_rng(seed)
+    d1 = random_descriptors(n1, seed + 1)
+    a1 = rng.uniform(0, 360, n1).astype(np.float32)
+    node1 = rng.integers(0, n_nodes, n1)
+    src = rng.integers(0, n1, n2)
+    bits = np.unpackbits(d1[src], axis=1)
+    flips = rng.integers(0, max_flips + 1, n2)
+    bits ^= (np.argsort(np.argsort(rng.random((n2, 256)), axis=1), axis=1) < flips[:, None]).astype(np.uint8)
+    d2 = np.packbits(bits, axis=1)
+    a2 = ((a1[src] + rng.normal(0, 15, n2)) % 360).astype(np.float32)
+    node2 = np.where(rng.random(n2) < p_same_node, node1[src], rng.integers(0, n_nodes, n2))
+    return dict(d1=d1, a1=a1, node1=node1, d2=d2, a2=a2, node2=node2, src=src)

@@ -11,6 +11,7 @@
 #include <climits>
 #include <cmath>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 namespace {
@@ -185,6 +186,78 @@ int om_search_for_initialization(const oo_keypoint* k1, const uint8_t* d1, int n
       prev_xy[2 * i1] = k2[matches12[i1]].x;
       prev_xy[2 * i1 + 1] = k2[matches12[i1]].y;
     }
+  return nmatches;
+}
+
+// ORBmatcher::SearchByBoW — the four variants share one loop:
+//   (KeyFrame*, Frame&, vpMapPointMatches)            src/ORBmatcher.cc:206-388   (all cameras)
+//   SearchByBoW_cam1(KeyFrame*, Frame&, ...)           src/ORBmatcher.cc:390-565   (indices < N only)
+//   (KeyFrame*, KeyFrame*, vpMatches12)                src/ORBmatcher.cc:996-1163  (all cameras)
+//   SearchByBoW_cam1(KeyFrame*, KeyFrame*, ...)        src/ORBmatcher.cc:1180-1363
+// Walk of the two DBoW2 feature vectors (std::map<node id, vector<feature index>>, flattened here
+// to CSR with ascending node ids) with the map's lower_bound jumps (:350-359); inside a common
+// node every valid feature of side 1 scans the node's side-2 features that are valid and not yet
+// matched, strict-< best / second best starting from 256 (:286-321), accepted when
+// best <= max_dist (TH_LOW for the Frame variants :324,487, TH_LOW-1 for the KeyFrame variants'
+// `bestDist1<TH_LOW` :1107,1292) and best < ratio * second (:328); then the rotation histogram.
+int om_search_by_bow(const uint8_t* d1, const float* angle1, const int32_t* valid1, int n1,
+                     const int32_t* node1, const int32_t* start1, const int32_t* items1, int nn1,
+                     const uint8_t* d2, const float* angle2, const int32_t* valid2, int n2,
+                     const int32_t* node2, const int32_t* start2, const int32_t* items2, int nn2,
+                     float nnratio, int check_ori, int max_dist, int32_t* matches12, int32_t* matches21) {
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  for (int i = 0; i < n2; ++i) matches21[i] = -1;
+  int nmatches = 0;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  const float factor = 1.0f / HISTO_LENGTH;
+  int a = 0, b = 0;
+  while (a < nn1 && b < nn2) {
+    if (node1[a] == node2[b]) {
+      for (int p = start1[a]; p < start1[a + 1]; ++p) {
+        const int idx1 = items1[p];
+        if (valid1 && !valid1[idx1]) continue;
+        int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+        for (int q = start2[b]; q < start2[b + 1]; ++q) {
+          const int idx2 = items2[q];
+          if (matches21[idx2] >= 0) continue;
+          if (valid2 && !valid2[idx2]) continue;
+          const int dist = om_distance(d1 + (size_t)idx1 * 32, d2 + (size_t)idx2 * 32);
+          if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+          else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist1 <= max_dist && (float)bestDist1 < nnratio * (float)bestDist2) {
+          matches12[idx1] = bestIdx2;
+          matches21[bestIdx2] = idx1;
+          if (check_ori) {
+            float rot = angle1[idx1] - angle2[bestIdx2];
+            if (rot < 0.0) rot += 360.0f;
+            int bin = (int)std::round(rot * factor);
+            if (bin == HISTO_LENGTH) bin = 0;
+            rotHist[bin].push_back(idx1);
+          }
+          nmatches++;
+        }
+      }
+      ++a;
+      ++b;
+    } else if (node1[a] < node2[b]) {
+      a = (int)(std::lower_bound(node1 + a, node1 + nn1, node2[b]) - node1);
+    } else {
+      b = (int)(std::lower_bound(node2 + b, node2 + nn2, node1[a]) - node2);
+    }
+  }
+  if (check_ori) {
+    int counts[HISTO_LENGTH], i1, i2, i3;
+    for (int i = 0; i < HISTO_LENGTH; ++i) counts[i] = (int)rotHist[i].size();
+    om_three_maxima(counts, HISTO_LENGTH, &i1, &i2, &i3);
+    for (int i = 0; i < HISTO_LENGTH; ++i)
+      if (i != i1 && i != i2 && i != i3)
+        for (int idx1 : rotHist[i]) {
+          matches21[matches12[idx1]] = -1;
+          matches12[idx1] = -1;
+          nmatches--;
+        }
+  }
   return nmatches;
 }
 

@@ -144,6 +144,22 @@ int om_search_by_projection_sim3(const oo_keypoint* kf_k, const uint8_t* kf_desc
                                  const float* mp_min_dist, const float* mp_max_d, const uint8_t* mp_desc, int n_mp,
                                  int th, int32_t* matched);
 
+// ORBmatcher::SearchByBoW / SearchByBoW_cam1, Frame and KeyFrame variants (src/ORBmatcher.cc:206-388,
+// 390-565, 996-1163, 1180-1363).  Side 1 = the key frame whose map points are searched, side 2 = the
+// frame / second key frame.  Feature vectors are DBoW2::FeatureVector flattened to CSR: node ids
+// ascending (std::map order), start[nn+1], items = feature indices in vector order.
+//  valid1[i] = map point exists && !isBad() (&& i < N for the _cam1 variants); valid2 likewise for the
+//  KeyFrame variants, (i < N) for SearchByBoW_cam1(KeyFrame*, Frame&), NULL = all valid.
+//  max_dist = TH_LOW (Frame variants, `<=`) or TH_LOW-1 (KeyFrame variants, `<`).
+//  matches12 (n1): matched side-2 feature or -1; matches21 (n2): matched side-1 feature or -1
+//  (vpMapPointMatches[i2] = map point of side-1 feature matches21[i2]).  A feature index must occur at
+//  most once per feature vector (DBoW2 guarantees it).
+int om_search_by_bow(const uint8_t* d1, const float* angle1, const int32_t* valid1, int n1,
+                     const int32_t* node1, const int32_t* start1, const int32_t* items1, int nn1,
+                     const uint8_t* d2, const float* angle2, const int32_t* valid2, int n2,
+                     const int32_t* node2, const int32_t* start2, const int32_t* items2, int nn2,
+                     float nnratio, int check_ori, int max_dist, int32_t* matches12, int32_t* matches21);
+
 // ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:3948-3989) on bin counts.
 void om_three_maxima(const int* counts, int L, int* ind1, int* ind2, int* ind3);
 

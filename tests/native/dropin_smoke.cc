@@ -4,6 +4,7 @@
 //   dropin_smoke <image.bin: int32 w, int32 h, bytes> <out.bin>
 // Output: int32 n, n x orbx_keypoint, n x 32 descriptor bytes, int32 self-match count.
 #include <cstdio>
+#include <map>
 #include <vector>
 
 #include "ORBextractor.h"
@@ -15,6 +16,18 @@ struct MiniFrame {  // the members of ORB_SLAM2::Frame the matcher template read
   static float mnMinX, mnMaxX, mnMinY, mnMaxY;
 };
 float MiniFrame::mnMinX = 0, MiniFrame::mnMaxX = 0, MiniFrame::mnMinY = 0, MiniFrame::mnMaxY = 0;
+
+struct MiniMapPoint {
+  bool isBad() const { return false; }
+};
+struct MiniKeyFrame {  // the members of ORB_SLAM2::KeyFrame / Frame that SearchByBoW_cam1 reads
+  int N = 0;
+  std::vector<cv::KeyPoint> mvKeysUn, mvKeys;
+  cv::Mat mDescriptors;
+  std::map<unsigned int, std::vector<unsigned int>> mFeatVec_cam1;  // DBoW2::FeatureVector
+  std::vector<MiniMapPoint*> points;
+  std::vector<MiniMapPoint*> GetMapPointMatches_cam1() const { return points; }
+};
 
 int main(int argc, char** argv) {
   if (argc < 3) return 2;
@@ -36,6 +49,21 @@ int main(int argc, char** argv) {
   std::vector<int> m12;
   const int nm = matcher.SearchForInitialization(F1, F2, prev, m12, 100);
   const int d01 = matcher.DescriptorDistance(F1.mDescriptors.rowRange(0, 1), F1.mDescriptors.rowRange(1, 2));
+  // SearchByBoW_cam1 of the frame against itself: vocabulary node = octave, every keypoint holds a point
+  MiniKeyFrame KF;
+  KF.N = (int)F1.mvKeysUn.size();
+  KF.mvKeysUn = KF.mvKeys = F1.mvKeysUn;
+  KF.mDescriptors = F1.mDescriptors;
+  std::vector<MiniMapPoint> store(KF.N);
+  for (int i = 0; i < KF.N; ++i) {
+    KF.points.push_back(&store[i]);
+    KF.mFeatVec_cam1[(unsigned)F1.mvKeysUn[i].octave].push_back((unsigned)i);
+  }
+  std::vector<MiniMapPoint*> bow_matches;
+  ORB_SLAM2::ORBmatcherB200 bow_matcher(0.7f, true);
+  const int nbow = bow_matcher.SearchByBoW_cam1(&KF, KF, bow_matches);
+  int bow_self = 0;
+  for (int i = 0; i < KF.N; ++i) bow_self += bow_matches[i] == &store[i];
   FILE* o = fopen(argv[2], "wb");
   const int n = (int)F1.mvKeysUn.size();
   fwrite(&n, 4, 1, o);
@@ -53,7 +81,10 @@ int main(int argc, char** argv) {
   const int pw = ex.mvImagePyramid[3].cols, ph = ex.mvImagePyramid[3].rows;
   fwrite(&pw, 4, 1, o);
   fwrite(&ph, 4, 1, o);
+  fwrite(&nbow, 4, 1, o);
+  fwrite(&bow_self, 4, 1, o);
   fclose(o);
-  printf("dropin: %d keypoints, %d init matches (%d self), d01=%d, pyramid[3]=%dx%d\n", n, nm, self, d01, pw, ph);
+  printf("dropin: %d keypoints, %d init matches (%d self), d01=%d, pyramid[3]=%dx%d, %d BoW matches (%d self)\n", n, nm,
+         self, d01, pw, ph, nbow, bow_self);
   return 0;
 }

@@ -286,6 +286,30 @@ def search_by_projection_sim3(kf_k, kf_desc, kf_cam, bounds, sf, log_sf, cam, Sc
     return nm, out
 
 
+def search_by_bow(d1, angle1, valid1, fv1, d2, angle2, valid2, fv2, nnratio=0.7, check_ori=True, max_dist=50):
+    """fv = (node_ids, start, items) CSR feature vector.  Returns (nmatches, matches12, matches21)."""
+    lib = load("port")
+    d1 = np.ascontiguousarray(d1, dtype=np.uint8)
+    d2 = np.ascontiguousarray(d2, dtype=np.uint8)
+    a1 = np.ascontiguousarray(angle1, dtype=np.float32)
+    a2 = np.ascontiguousarray(angle2, dtype=np.float32)
+    v1 = None if valid1 is None else np.ascontiguousarray(valid1, dtype=np.int32)
+    v2 = None if valid2 is None else np.ascontiguousarray(valid2, dtype=np.int32)
+    f1 = [np.ascontiguousarray(a, dtype=np.int32) for a in fv1]
+    f2 = [np.ascontiguousarray(a, dtype=np.int32) for a in fv2]
+    n1, n2 = len(d1), len(d2)
+    m12, m21 = np.zeros(n1, dtype=np.int32), np.zeros(n2, dtype=np.int32)
+    f = lib.om_search_by_bow
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] * 2 + \
+        [C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    n = f(d1.ctypes.data, a1.ctypes.data, None if v1 is None else v1.ctypes.data, n1, f1[0].ctypes.data, f1[1].ctypes.data,
+          f1[2].ctypes.data, len(f1[0]),
+          d2.ctypes.data, a2.ctypes.data, None if v2 is None else v2.ctypes.data, n2, f2[0].ctypes.data, f2[1].ctypes.data,
+          f2[2].ctypes.data, len(f2[0]), nnratio, int(check_ori), int(max_dist), m12.ctypes.data, m21.ctypes.data)
+    return n, m12, m21
+
+
 def three_maxima(counts):
     lib = load("port")
     c = np.ascontiguousarray(counts, dtype=np.int32)

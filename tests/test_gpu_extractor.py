@@ -172,10 +172,15 @@ def test_cpp_dropin_classes_run(O, tmp_path):
     n = struct.unpack_from("<i", raw, 0)[0]
     k = np.frombuffer(raw, dtype=KP_DTYPE, count=n, offset=4)
     d = np.frombuffer(raw, dtype=np.uint8, count=n * 32, offset=4 + 24 * n).reshape(n, 32)
-    nm, d01, self_m, pw, ph = struct.unpack_from("<5i", raw, 4 + 56 * n)
+    nm, d01, self_m, pw, ph, nbow, bow_self = struct.unpack_from("<7i", raw, 4 + 56 * n)
     k_ref, d_ref, _ = O.extractor("port").extract(img)
     _assert_same_features(k, d, k_ref, d_ref, "C++ drop-in")
     prev = np.stack([k_ref["x"], k_ref["y"]], axis=1).astype(np.float32)
     rn, rm12, _ = O.search_for_initialization(k_ref, d_ref, k_ref, d_ref, (0, 640, 0, 480), prev, 100, 0.9, True)
     assert nm == rn and self_m == int((rm12 == np.arange(len(rm12))).sum())
     assert d01 == O.distance(d_ref[0], d_ref[1]) and (pw, ph) == (370, 278)
+    # SearchByBoW_cam1 of the frame against itself, vocabulary node = octave
+    from multi_orb_slam_b200.synth import feature_vector
+    fv = feature_vector(k_ref["octave"])
+    bn, bm12, bm21 = O.search_by_bow(d_ref, k_ref["angle"], None, fv, d_ref, k_ref["angle"], None, fv, 0.7, True, 50)
+    assert nbow == bn and bow_self == int((bm21 == np.arange(len(bm21))).sum())

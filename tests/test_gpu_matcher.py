@@ -335,3 +335,57 @@ def test_search_by_projection_sim3_vs_oracle(O, th, scale):
                                   s["last_desc"], th)
     assert gn == rn and np.array_equal(F.mvpMapPoints, rout)
     assert rn > 50
+
+
+# ---- SearchByBoW (src/ORBmatcher.cc:206-388, 390-565, 996-1163, 1180-1363) ----------------------
+@pytest.mark.parametrize("n1,n2,n_nodes,check_ori,kf_pair,with_valid", [
+    (1000, 1100, 100, True, False, False),   # Frame variant, DBoW2 level-4 like node count
+    (2000, 2000, 100, True, True, True),     # KeyFrame pair: strict threshold, both sides filtered
+    (1500, 1500, 3, True, False, True),      # huge nodes: candidate rows stay in HBM (> 12288 entries)
+    (300, 5000, 1000, False, False, False),  # sparse nodes, no orientation check
+])
+def test_search_by_bow_vs_oracle(O, n1, n2, n_nodes, check_ori, kf_pair, with_valid):
+    from multi_orb_slam_b200.matcher import ORBmatcher
+    from multi_orb_slam_b200.synth import bow_scene, feature_vector
+    sc = bow_scene(n1, n2, n_nodes, 5 + n1)
+    rng = np.random.default_rng(n2)
+    node1 = np.where(rng.random(n1) < 0.03, -1, sc["node1"])
+    node2 = np.where(sc["node2"] % 11 == 5, -1, sc["node2"])  # nodes missing on one side: lower_bound jumps
+    fv1, fv2 = feature_vector(node1), feature_vector(node2)
+    v1 = (rng.random(n1) < 0.8).astype(np.int32) if with_valid else None
+    v2 = (rng.random(n2) < 0.9).astype(np.int32) if with_valid else None
+    m = ORBmatcher(0.7, check_ori)
+    nm, m12, m21 = m.SearchByBoW(sc["d1"], sc["a1"], v1, fv1, sc["d2"], sc["a2"], v2, fv2, keyframe_pair=kf_pair)
+    rn, rm12, rm21 = O.search_by_bow(sc["d1"], sc["a1"], v1, fv1, sc["d2"], sc["a2"], v2, fv2, 0.7, check_ori,
+                                     49 if kf_pair else 50)
+    assert nm == rn and rn > 20
+    assert np.array_equal(m12, rm12) and np.array_equal(m21, rm21)
+
+
+def test_search_by_bow_edge_cases(O):
+    from multi_orb_slam_b200.matcher import ORBmatcher
+    from multi_orb_slam_b200.synth import bow_scene, feature_vector
+    m = ORBmatcher(0.7, True)
+    sc = bow_scene(50, 60, 4, 3)
+    fv1, fv2 = feature_vector(sc["node1"]), feature_vector(sc["node2"] + 1000)  # no common node
+    nm, m12, m21 = m.SearchByBoW(sc["d1"], sc["a1"], None, fv1, sc["d2"], sc["a2"], None, fv2)
+    assert nm == 0 and (m12 == -1).all() and (m21 == -1).all()
+    empty = (np.zeros(0, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32))
+    nm, m12, m21 = m.SearchByBoW(sc["d1"], sc["a1"], None, empty, sc["d2"], sc["a2"], None, feature_vector(sc["node2"]))
+    assert nm == 0 and (m12 == -1).all()
+    # every side-1 feature invalid
+    nm, m12, _ = m.SearchByBoW(sc["d1"], sc["a1"], np.zeros(50, np.int32), fv1, sc["d2"], sc["a2"], None,
+                               feature_vector(sc["node2"]))
+    assert nm == 0 and (m12 == -1).all()
+    # identical sets in one node: ties resolved by vector order like the reference
+    d = np.repeat(sc["d1"][:1], 8, axis=0)
+    fv = feature_vector(np.zeros(8, np.int64))
+    a = np.zeros(8, np.float32)
+    got = m.SearchByBoW(d, a, None, fv, d, a, None, fv)
+    ref = O.search_by_bow(d, a, None, fv, d, a, None, fv, 0.7, True, 50)
+    assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+    # bad index in a feature vector is rejected
+    from multi_orb_slam_b200._lib import OrbError
+    bad = (np.zeros(1, np.int32), np.array([0, 1], np.int32), np.array([99], np.int32))
+    with pytest.raises(OrbError):
+        m.SearchByBoW(sc["d1"], sc["a1"], None, bad, sc["d2"], sc["a2"], None, feature_vector(np.zeros(60, np.int64)))

@@ -184,3 +184,86 @@ def test_search_for_initialization_vs_python(O, seed, window, check_ori):
     assert rn == int((rm12 >= 0).sum())
     for i1 in np.nonzero(rm12 >= 0)[0]:
         assert rprev[i1, 0] == k2["x"][rm12[i1]] and rprev[i1, 1] == k2["y"][rm12[i1]]
+
+
+# ---- SearchByBoW (src/ORBmatcher.cc:206-388, 390-565, 996-1163, 1180-1363) ----------------------
+def _py_search_by_bow(d1, a1, valid1, fv1, d2, a2, valid2, fv2, ratio, check_ori, max_dist):
+    """Transliteration over real std::map-like containers (dict + sorted keys + bisect = lower_bound)."""
+    import bisect
+    map1 = {int(n): [int(i) for i in fv1[2][fv1[1][k]:fv1[1][k + 1]]] for k, n in enumerate(fv1[0])}
+    map2 = {int(n): [int(i) for i in fv2[2][fv2[1][k]:fv2[1][k + 1]]] for k, n in enumerate(fv2[0])}
+    keys1, keys2 = sorted(map1), sorted(map2)
+    m12, m21 = [-1] * len(d1), [-1] * len(d2)
+    hist = [[] for _ in range(30)]
+    dist = lambda x, y: int(np.unpackbits(x ^ y).sum())
+    nm, ia, ib = 0, 0, 0
+    while ia < len(keys1) and ib < len(keys2):
+        if keys1[ia] == keys2[ib]:
+            for idx1 in map1[keys1[ia]]:
+                if valid1 is not None and not valid1[idx1]:
+                    continue
+                best1, bi, best2 = 256, -1, 256
+                for idx2 in map2[keys2[ib]]:
+                    if m21[idx2] >= 0 or (valid2 is not None and not valid2[idx2]):
+                        continue
+                    dd = dist(d1[idx1], d2[idx2])
+                    if dd < best1:
+                        best2, best1, bi = best1, dd, idx2
+                    elif dd < best2:
+                        best2 = dd
+                if best1 <= max_dist and np.float32(best1) < np.float32(ratio) * np.float32(best2):
+                    m12[idx1], m21[bi] = bi, idx1
+                    if check_ori:
+                        rot = np.float32(a1[idx1]) - np.float32(a2[bi])
+                        if rot < 0:
+                            rot = np.float32(rot + np.float32(360.0))
+                        b = int(math.floor(np.float32(rot * np.float32(1.0 / 30)) + 0.5))
+                        hist[0 if b == 30 else b].append(idx1)
+                    nm += 1
+            ia, ib = ia + 1, ib + 1
+        elif keys1[ia] < keys2[ib]:
+            ia = bisect.bisect_left(keys1, keys2[ib])
+        else:
+            ib = bisect.bisect_left(keys2, keys1[ia])
+    if check_ori:
+        import oracle_lib
+        keep = set(oracle_lib.three_maxima([len(h) for h in hist]))
+        for b in range(30):
+            if b not in keep:
+                for idx1 in hist[b]:
+                    m21[m12[idx1]] = -1
+                    m12[idx1] = -1
+                    nm -= 1
+    return nm, m12, m21
+
+
+@pytest.mark.parametrize("seed,n_nodes,check_ori,max_dist,with_valid", [(0, 12, True, 50, False), (1, 40, True, 49, True),
+                                                                       (2, 5, False, 50, True), (3, 200, True, 50, False)])
+def test_search_by_bow_vs_python(O, seed, n_nodes, check_ori, max_dist, with_valid):
+    from multi_orb_slam_b200.synth import bow_scene, feature_vector
+    sc = bow_scene(150, 170, n_nodes, seed)
+    rng = np.random.default_rng(100 + seed)
+    # leave some features out of the vectors and make the two node sets differ (lower_bound jumps)
+    node1 = np.where(rng.random(150) < 0.05, -1, sc["node1"])
+    node2 = np.where(rng.random(170) < 0.05, -1, sc["node2"])
+    node2 = np.where(node2 % 7 == 3, -1, node2)
+    fv1, fv2 = feature_vector(node1), feature_vector(node2)
+    v1 = (rng.random(150) < 0.8).astype(np.int32) if with_valid else None
+    v2 = (rng.random(170) < 0.9).astype(np.int32) if with_valid else None
+    rn, rm12, rm21 = O.search_by_bow(sc["d1"], sc["a1"], v1, fv1, sc["d2"], sc["a2"], v2, fv2, 0.7, check_ori, max_dist)
+    pn, pm12, pm21 = _py_search_by_bow(sc["d1"], sc["a1"], v1, fv1, sc["d2"], sc["a2"], v2, fv2, 0.7, check_ori, max_dist)
+    assert rn == pn and list(rm12) == pm12 and list(rm21) == pm21
+    assert rn == int((rm12 >= 0).sum()) == int((rm21 >= 0).sum()) and rn > 10
+    for i1 in np.nonzero(rm12 >= 0)[0]:
+        assert rm21[rm12[i1]] == i1
+
+
+def test_search_by_bow_degenerate(O):
+    from multi_orb_slam_b200.synth import bow_scene, feature_vector
+    sc = bow_scene(20, 20, 3, 9)
+    fv1, fv2 = feature_vector(sc["node1"]), feature_vector(sc["node2"] + 100)  # no common node
+    rn, rm12, rm21 = O.search_by_bow(sc["d1"], sc["a1"], None, fv1, sc["d2"], sc["a2"], None, fv2)
+    assert rn == 0 and (rm12 == -1).all() and (rm21 == -1).all()
+    empty = (np.zeros(0, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32))
+    rn, rm12, _ = O.search_by_bow(sc["d1"], sc["a1"], None, empty, sc["d2"], sc["a2"], None, fv2)
+    assert rn == 0 and (rm12 == -1).all()
