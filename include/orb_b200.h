@@ -280,6 +280,24 @@ int orbm_search_by_bow_host(orbm_matcher* m, const uint8_t* desc1, const float* 
                             orbm_featvec fv2, float nnratio, int check_ori, int max_dist, int32_t* matches12,
                             int32_t* matches21, int* nmatches);
 
+/* ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, vMatchedPairs, bOnlyStereo, vbCam)
+ * (src/ORBmatcher.cc:1364-1720, called from LocalMapping.cc:361) with CheckDistEpipolarLine (:167-184).
+ * Key frames: concatenated keypoints (mvKeysUn_total; pt, angle, octave are read), descriptor per global index,
+ * has_mp[i] = (GetMapPoint(i) != NULL), cam[i] = keypoint_to_cam (0/1), uright[i] = mvuRight_total, mFeatVec as CSR.
+ * F12s: the two row-major 3x3 fundamental matrices F12s[cam] = K1^-T [t12]x R12 K2^-1 (:1421-1423) and
+ * epipoles = {ex, ey, ex_cam2, ey_cam2} (:1441-1449): cv::Mat algebra on the key-frame poses, evaluated by the
+ * caller with its own OpenCV (the reference takes F12 as an argument as well).  scale_factors2 / level_sigma2_2 =
+ * pKF2->mvScaleFactors / mvLevelSigma2 (nlevels entries); cam_enabled = vbCam (2 entries).
+ * matches12 (n1) = vMatches12: key-frame-2 feature or -1; vMatchedPairs = its entries >= 0 in index order.
+ * The reference never marks key-frame-2 features as matched (:1452), so they may repeat. */
+int orbm_search_for_triangulation_host(orbm_matcher* m, const orbx_keypoint* k1, const uint8_t* desc1, const int32_t* has_mp1,
+                                       const int32_t* cam1, const float* uright1, int n1, orbm_featvec fv1,
+                                       const orbx_keypoint* k2, const uint8_t* desc2, const int32_t* has_mp2,
+                                       const int32_t* cam2, const float* uright2, int n2, orbm_featvec fv2, const float* F12s,
+                                       const float* epipoles, const float* scale_factors2, const float* level_sigma2_2,
+                                       int nlevels, int only_stereo, const int32_t* cam_enabled, int check_ori,
+                                       int32_t* matches12, int* nmatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,6 +95,8 @@ _SIGS = {
                                                 _vp, _vp, _vp, _vp, _i, _i, _vp, C.POINTER(_i)]),
     "orbm_search_by_bow_host": (_i, [_vp, _vp, _vp, _vp, _i, FeatVec, _vp, _vp, _vp, _i, FeatVec, _f, _i, _i, _vp, _vp,
                                     C.POINTER(_i)]),
+    "orbm_search_for_triangulation_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, FeatVec, _vp, _vp, _vp, _vp, _vp, _i,
+                                               FeatVec, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, C.POINTER(_i)]),
 }
 EXPORTS = tuple(_SIGS)
 for _name, (_res, _args) in _SIGS.items():

@@ -677,6 +677,103 @@ __global__ void __launch_bounds__(256) k_bow_resolve(const BowQuery* __restrict_
   if (tid == 0) *nmatches_out = s_nmatch;
 }
 
+// ---- SearchForTriangulation (:1364-1720) ------------------------------------------------------
+// The reference never sets vbMatched2 (:1452), so every key-frame-1 feature is independent: a warp
+// per query evaluates the node's key-frame-2 features in parallel (skip tests :1481-1500, distance
+// gate :1505, epipole distance :1509-1520, CheckDistEpipolarLine :167-184) and the scan's result is
+// the minimum distance among the passing candidates, the LAST one on ties (`dist>bestDist` lets
+// equal distances through) = min over the key dist << 16 | (0xFFFF - position).
+struct TriSide {
+  const orbx_keypoint* k;
+  const uint8_t* d;
+  const int32_t* has_mp;
+  const int32_t* cam;
+  const float* uright;
+};
+
+__global__ void __launch_bounds__(256) k_tri_match(const BowQuery* __restrict__ q, int nq, TriSide s1, TriSide s2,
+                                                   const int32_t* __restrict__ items2, const float* __restrict__ consts,
+                                                   int only_stereo, int check_ori, int32_t* __restrict__ matches12,
+                                                   int32_t* __restrict__ q_bin, int* __restrict__ hist) {
+  // consts: F12s[18], epipoles[4], scale_factors2[16], level_sigma2_2[16]
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= nq) return;
+  const BowQuery bq = q[i];
+  const int idx1 = bq.idx1;
+  const orbx_keypoint kp1 = s1.k[idx1];
+  const int camIdx1 = s1.cam[idx1];
+  const bool bStereo1 = s1.uright[idx1] >= 0;
+  const float* F12 = consts + 9 * camIdx1;
+  // line of kp1 in image 2 (:170-172), float, left to right, no contraction
+  const float a = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, F12[0]), __fmul_rn(kp1.y, F12[3])), F12[6]);
+  const float b = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, F12[1]), __fmul_rn(kp1.y, F12[4])), F12[7]);
+  const float c = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, F12[2]), __fmul_rn(kp1.y, F12[5])), F12[8]);
+  const float den = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+  const uint4* qp = reinterpret_cast<const uint4*>(s1.d + (size_t)idx1 * 32);
+  const uint4 qa = __ldg(qp), qb = __ldg(qp + 1);
+  uint32_t best = 0xFFFFFFFFu;
+  for (int p = lane; p < bq.cnt; p += 32) {
+    const int idx2 = items2[bq.t0 + p];
+    if (s2.has_mp[idx2] || s2.cam[idx2] != camIdx1) continue;
+    const bool bStereo2 = s2.uright[idx2] >= 0;
+    if (only_stereo && !bStereo2) continue;
+    const uint4* tp = reinterpret_cast<const uint4*>(s2.d + (size_t)idx2 * 32);
+    const int dist = hamming256(qa, qb, __ldg(tp), __ldg(tp + 1));
+    if (dist > TH_LOW) continue;
+    const orbx_keypoint kp2 = s2.k[idx2];
+    if (!bStereo1 && !bStereo2) {
+      const float dx = __fsub_rn(consts[18 + 2 * camIdx1], kp2.x), dy = __fsub_rn(consts[19 + 2 * camIdx1], kp2.y);
+      if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, consts[22 + kp2.octave])) continue;
+    }
+    if (den == 0.f) continue;
+    const float num = __fadd_rn(__fadd_rn(__fmul_rn(a, kp2.x), __fmul_rn(b, kp2.y)), c);
+    const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+    if (!((double)dsqr < __dmul_rn(3.84, (double)consts[38 + kp2.octave]))) continue;
+    best = min(best, (uint32_t)dist << 16 | (uint32_t)(0xFFFF - p));
+  }
+  best = __reduce_min_sync(0xffffffffu, best);
+  if (lane == 0) {
+    int bin = -1;
+    if (best != 0xFFFFFFFFu) {
+      const int idx2 = items2[bq.t0 + (0xFFFF - (int)(best & 0xFFFFu))];
+      matches12[idx1] = idx2;
+      bin = HISTO_LENGTH;
+      if (check_ori) {
+        float rot = __fsub_rn(kp1.angle, s2.k[idx2].angle);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
+        if (bin == HISTO_LENGTH) bin = 0;
+        atomicAdd(&hist[bin], 1);
+      }
+    }
+    q_bin[i] = bin;
+  }
+}
+
+// rotation filter (:1701-1716) and the match count
+__global__ void __launch_bounds__(256) k_tri_finish(const BowQuery* __restrict__ q, int nq, int check_ori,
+                                                    const int32_t* __restrict__ q_bin, const int* __restrict__ hist,
+                                                    int32_t* __restrict__ matches12, int* __restrict__ nmatches_out) {
+  __shared__ int s_keep[HISTO_LENGTH];
+  __shared__ int s_n;
+  if (threadIdx.x == 0) {
+    s_n = 0;
+    if (check_ori) three_maxima_keep(hist, s_keep);
+  }
+  __syncthreads();
+  int mine = 0;
+  for (int j = threadIdx.x; j < nq; j += 256) {
+    const int bin = q_bin[j];
+    if (bin < 0) continue;
+    if (check_ori && !s_keep[bin]) matches12[q[j].idx1] = -1;
+    else ++mine;
+  }
+  atomicAdd(&s_n, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) *nmatches_out = s_n;
+}
+
 // ---- SearchByProjection(Frame&, vector<MapPoint*>&, th) ------------------------------------
 // Phase A (warp per map point, whole grid): window query at levels [pred-1, pred], stereo gate
 // (:111-116), distances; candidates kept in traversal order as dist<<20 | octave<<16 | idx.
@@ -1312,6 +1409,104 @@ int orbm_search_by_bow_host(orbm_matcher* m, const uint8_t* desc1, const float* 
   cudaMemcpyAsync(nmatches, dnm, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (!m->check(cudaStreamSynchronize(st), "search_by_bow")) return ORBX_E_CUDA;
   return m->check(cudaGetLastError(), "search_by_bow launch") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+int orbm_search_for_triangulation_host(orbm_matcher* m, const orbx_keypoint* k1, const uint8_t* desc1, const int32_t* has_mp1,
+                                       const int32_t* cam1, const float* uright1, int n1, orbm_featvec fv1,
+                                       const orbx_keypoint* k2, const uint8_t* desc2, const int32_t* has_mp2,
+                                       const int32_t* cam2, const float* uright2, int n2, orbm_featvec fv2, const float* F12s,
+                                       const float* epipoles, const float* scale_factors2, const float* level_sigma2_2,
+                                       int nlevels, int only_stereo, const int32_t* cam_enabled, int check_ori,
+                                       int32_t* matches12, int* nmatches) {
+  if (!m || !matches12 || !nmatches || n1 < 0 || n2 < 0 || n1 > 65535 || n2 > 65535 || fv1.n_nodes < 0 || fv2.n_nodes < 0 ||
+      nlevels < 1 || nlevels > ORBX_MAX_LEVELS || !F12s || !epipoles || !scale_factors2 || !level_sigma2_2 || !cam_enabled ||
+      (n1 && (!k1 || !desc1 || !has_mp1 || !cam1 || !uright1)) || (n2 && (!k2 || !desc2 || !has_mp2 || !cam2 || !uright2)) ||
+      (fv1.n_nodes && (!fv1.node_id || !fv1.start || !fv1.items)) || (fv2.n_nodes && (!fv2.node_id || !fv2.start || !fv2.items)))
+    return ORBX_E_INVALID;
+  *nmatches = 0;
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  for (int i = 0; i < n1; ++i)
+    if (cam1[i] < 0 || cam1[i] > 1) { m->err = "key frame 1: camera index out of range"; return ORBX_E_INVALID; }
+  for (int i = 0; i < n2; ++i)
+    if (k2[i].octave < 0 || k2[i].octave >= nlevels) { m->err = "key frame 2: octave out of range"; return ORBX_E_INVALID; }
+  // feature-vector walk (:1456-1700): one query per key-frame-1 feature that passes the side-1 tests (:1468-1480)
+  std::vector<BowQuery> queries;
+  int a = 0, b = 0;
+  while (a < fv1.n_nodes && b < fv2.n_nodes) {
+    const int32_t na = fv1.node_id[a], nb = fv2.node_id[b];
+    if (na == nb) {
+      const int t0 = fv2.start[b], cnt = fv2.start[b + 1] - t0;
+      if (cnt > 65535) { m->err = "feature vector 2: node with more than 65535 features"; return ORBX_E_INVALID; }
+      for (int p = fv1.start[a]; p < fv1.start[a + 1]; ++p) {
+        const int idx1 = fv1.items[p];
+        if (idx1 < 0 || idx1 >= n1) { m->err = "feature vector 1: index out of range"; return ORBX_E_INVALID; }
+        if (has_mp1[idx1] || !cam_enabled[cam1[idx1]]) continue;
+        if (only_stereo && !(uright1[idx1] >= 0)) continue;
+        if (cnt > 0) queries.push_back({idx1, t0, cnt, 0});
+      }
+      ++a; ++b;
+    } else if (na < nb) {
+      a = (int)(std::lower_bound(fv1.node_id + a, fv1.node_id + fv1.n_nodes, nb) - fv1.node_id);
+    } else {
+      b = (int)(std::lower_bound(fv2.node_id + b, fv2.node_id + fv2.n_nodes, na) - fv2.node_id);
+    }
+  }
+  const int nq = (int)queries.size();
+  if (nq == 0) return ORBX_OK;
+  const int n_items2 = fv2.start[fv2.n_nodes];
+  for (int i = 0; i < n_items2; ++i)
+    if (fv2.items[i] < 0 || fv2.items[i] >= n2) { m->err = "feature vector 2: index out of range"; return ORBX_E_INVALID; }
+  cudaSetDevice(m->device);
+  cudaStream_t st = m->stream;
+  const size_t per_kp = 32 + sizeof(orbx_keypoint) + 4 + 4 + 4;
+  uint8_t* sb = m->scratch<uint8_t>(8, ((size_t)n1 + n2) * per_kp + 512);
+  int32_t* dints = m->scratch<int32_t>(4, (size_t)n_items2 + n1 + nq + HISTO_LENGTH + 8);
+  BowQuery* dq = m->scratch<BowQuery>(5, nq);
+  float* dconst = m->scratch<float>(9, 64);
+  if (!sb || !dints || !dq || !dconst) return ORBX_E_CUDA;
+  auto place = [&](uint8_t*& cur, int n, const orbx_keypoint* k, const uint8_t* d, const int32_t* mp, const int32_t* cam,
+                   const float* ur) {
+    TriSide s;
+    uint8_t* dd = cur;  // descriptors first: uint4 loads need 16-byte alignment
+    orbx_keypoint* dk = reinterpret_cast<orbx_keypoint*>(dd + (size_t)n * 32);
+    int32_t* dmp = reinterpret_cast<int32_t*>(dk + n);
+    int32_t* dcam = dmp + n;
+    float* dur = reinterpret_cast<float*>(dcam + n);
+    cudaMemcpyAsync(dd, d, (size_t)n * 32, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dk, k, sizeof(orbx_keypoint) * n, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dmp, mp, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dcam, cam, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dur, ur, sizeof(float) * n, cudaMemcpyHostToDevice, st);
+    s.d = dd; s.k = dk; s.has_mp = dmp; s.cam = dcam; s.uright = dur;
+    cur = reinterpret_cast<uint8_t*>(dur + n);
+    cur += (16 - (reinterpret_cast<uintptr_t>(cur) & 15)) & 15;
+    return s;
+  };
+  uint8_t* cur = sb;
+  const TriSide s1 = place(cur, n1, k1, desc1, has_mp1, cam1, uright1);
+  const TriSide s2 = place(cur, n2, k2, desc2, has_mp2, cam2, uright2);
+  float hconst[54] = {0};
+  std::copy(F12s, F12s + 18, hconst);
+  std::copy(epipoles, epipoles + 4, hconst + 18);
+  std::copy(scale_factors2, scale_factors2 + nlevels, hconst + 22);
+  std::copy(level_sigma2_2, level_sigma2_2 + nlevels, hconst + 38);
+  int32_t* ditems2 = dints;
+  int32_t* dm12 = ditems2 + n_items2;
+  int32_t* dbin = dm12 + n1;
+  int* dhist = dbin + nq;
+  int* dnm = dhist + HISTO_LENGTH;
+  cudaMemcpyAsync(dconst, hconst, sizeof(hconst), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(ditems2, fv2.items, sizeof(int32_t) * n_items2, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dq, queries.data(), sizeof(BowQuery) * nq, cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(dm12, 0xFF, sizeof(int32_t) * n1, st);
+  cudaMemsetAsync(dhist, 0, sizeof(int) * (HISTO_LENGTH + 1), st);
+  k_tri_match<<<(nq + 7) / 8, 256, 0, st>>>(dq, nq, s1, s2, ditems2, dconst, only_stereo, check_ori, dm12, dbin, dhist);
+  k_tri_finish<<<1, 256, 0, st>>>(dq, nq, check_ori, dbin, dhist, dm12, dnm);
+  m->launches += 2;
+  cudaMemcpyAsync(matches12, dm12, sizeof(int32_t) * n1, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(nmatches, dnm, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (!m->check(cudaStreamSynchronize(st), "search_for_triangulation")) return ORBX_E_CUDA;
+  return m->check(cudaGetLastError(), "search_for_triangulation launch") ? ORBX_OK : ORBX_E_CUDA;
 }
 
 // ---- pose-based SearchByProjection overloads ------------------------------------------------

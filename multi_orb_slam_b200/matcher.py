@@ -286,3 +286,42 @@ class ORBmatcher:
             self.mfNNratio, int(self.mbCheckOrientation), self.TH_LOW - 1 if keyframe_pair else self.TH_LOW,
             m12.ctypes.data, m21.ctypes.data, C.byref(nm)))
         return nm.value, m12, m21
+
+    # -- SearchForTriangulation (src/ORBmatcher.cc:1364-1720) ---------------------------------------------------
+    def SearchForTriangulation(self, k1, desc1, has_mp1, cam1, uright1, featvec1, k2, desc2, has_mp2, cam2, uright2, featvec2,
+                               F12s, epipoles, scale_factors2, level_sigma2_2, bOnlyStereo: bool = False, vbCam=(True, True)):
+        """Key frames as flat arrays (see include/orb_b200.h: orbm_search_for_triangulation_host); F12s [2,3,3]
+        and epipoles [4] come from the caller's pose algebra.  Returns (nmatches, vMatches12 [n1],
+        vMatchedPairs [nmatches, 2])."""
+        c = lambda a, t: np.ascontiguousarray(a, dtype=t)
+        k1, k2 = c(k1, KP_DTYPE), c(k2, KP_DTYPE)
+        d1, d2 = c(desc1, np.uint8).reshape(-1, 32), c(desc2, np.uint8).reshape(-1, 32)
+        n1, n2 = len(k1), len(k2)
+        side1 = [c(has_mp1, np.int32), c(cam1, np.int32), c(uright1, np.float32)]
+        side2 = [c(has_mp2, np.int32), c(cam2, np.int32), c(uright2, np.float32)]
+        if any(len(a) != n1 for a in side1 + [d1]) or any(len(a) != n2 for a in side2 + [d2]):
+            raise ValueError("per-keypoint arrays must match the keypoint counts")
+        F = c(F12s, np.float32).reshape(2, 3, 3)
+        epi = c(epipoles, np.float32).reshape(4)
+        sf, ls = c(scale_factors2, np.float32), c(level_sigma2_2, np.float32)
+        if len(sf) != len(ls):
+            raise ValueError("scale_factors2 and level_sigma2_2 must have nlevels entries each")
+        en = c([int(bool(v)) for v in vbCam], np.int32)
+        keep = []
+
+        def fv(t):
+            arrs = [np.ascontiguousarray(x, dtype=np.int32) for x in t]
+            if len(arrs[1]) != len(arrs[0]) + 1:
+                raise ValueError("feature vector: start must have n_nodes + 1 entries")
+            keep.extend(arrs)
+            return _lib.FeatVec(arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, len(arrs[0]))
+
+        m12 = np.empty(n1, dtype=np.int32)
+        nm = C.c_int(0)
+        p = lambda a: a.ctypes.data
+        check_m(self._h, lib.orbm_search_for_triangulation_host(
+            self._h, p(k1), p(d1), p(side1[0]), p(side1[1]), p(side1[2]), n1, fv(featvec1),
+            p(k2), p(d2), p(side2[0]), p(side2[1]), p(side2[2]), n2, fv(featvec2), p(F), p(epi), p(sf), p(ls), len(sf),
+            int(bOnlyStereo), p(en), int(self.mbCheckOrientation), p(m12), C.byref(nm)))
+        idx = np.nonzero(m12 >= 0)[0]
+        return nm.value, m12, np.stack([idx, m12[idx]], axis=1)

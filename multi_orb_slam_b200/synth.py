@@ -130,3 +130,68 @@ def bow_scene(n1: int, n2: int, n_nodes: int, seed: int, p_same_node: float = 0.
     a2 = ((a1[src] + rng.normal(0, 15, n2)) % 360).astype(np.float32)
     node2 = np.where(rng.random(n2) < p_same_node, node1[src], rng.integers(0, n_nodes, n2))
     return dict(d1=d1, a1=a1, node1=node1, d2=d2, a2=a2, node2=node2, src=src)
+
+
+# orbx_keypoint rows (include/orb_b200.h), same as _lib.KP_DTYPE (not imported: synth must work without the library)
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4")])
+
+
+def triangulation_scene(n1: int, n2: int, n_nodes: int, seed: int, n_levels: int = 8):
+    """Two two-camera key frames observing the same 3-D points from slightly different poses, for
+    SearchForTriangulation: side 2 holds noisy re-observations of random side-1 features (same
+    camera, mostly the same vocabulary node).  Returns a dict of the flat arrays the C-ABI takes,
+    including the two fundamental matrices and epipoles computed the way the reference does
+    (F12 = K^-T [t12]x R12 K^-1, src/ORBmatcher.cc:1421-1423) in float64, rounded to float32."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = 520.0, 520.0, 320.0, 240.0
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    Kinv = np.linalg.inv(K)
+
+    def skew(t):
+        return np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+
+    def rot(rx, ry, rz):
+        cxr, sxr, cyr, syr, czr, szr = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
+        Rx = np.array([[1, 0, 0], [0, cxr, -sxr], [0, sxr, cxr]])
+        Ry = np.array([[cyr, 0, syr], [0, 1, 0], [-syr, 0, cyr]])
+        Rz = np.array([[czr, -szr, 0], [szr, czr, 0], [0, 0, 1]])
+        return Rz @ Ry @ Rx
+
+    # per camera: X1 = R12 X2 + t12 (coordinates of a point in key frame 1 from key frame 2)
+    R12 = [rot(0.01, -0.02, 0.015), rot(-0.015, 0.01, 0.02)]
+    t12 = [np.array([0.25, 0.02, 0.03]), np.array([0.03, 0.02, 0.28])]
+    F12s = np.stack([Kinv.T @ skew(t12[c]) @ R12[c] @ Kinv for c in range(2)])
+    epi = []
+    for c in range(2):
+        C2 = -R12[c].T @ t12[c]  # centre of camera 1 in the frame of camera 2
+        epi += [fx * C2[0] / C2[2] + cx, fy * C2[1] / C2[2] + cy]
+    cam1 = rng.integers(0, 2, n1)
+    X2 = np.stack([rng.uniform(-2, 2, n1), rng.uniform(-1.5, 1.5, n1), rng.uniform(2, 8, n1)], axis=1)
+    X1 = np.stack([R12[c] @ x + t12[c] for c, x in zip(cam1, X2)])
+    p1 = (K @ (X1 / X1[:, 2:3]).T).T[:, :2]
+    p2_true = (K @ (X2 / X2[:, 2:3]).T).T[:, :2]
+    k1 = np.zeros(n1, KP_DTYPE)
+    k1["x"], k1["y"] = p1[:, 0], p1[:, 1]
+    k1["octave"] = rng.integers(0, 4, n1)
+    k1["angle"] = rng.uniform(0, 360, n1)
+    d1 = random_descriptors(n1, seed + 1)
+    node1 = rng.integers(0, n_nodes, n1)
+    src = rng.integers(0, n1, n2)
+    k2 = np.zeros(n2, KP_DTYPE)
+    noise = rng.normal(0, 1.0, (n2, 2)) * np.where(rng.random(n2) < 0.8, 0.4, 6.0)[:, None]
+    k2["x"], k2["y"] = p2_true[src, 0] + noise[:, 0], p2_true[src, 1] + noise[:, 1]
+    k2["octave"] = np.clip(k1["octave"][src] + rng.integers(-1, 2, n2), 0, n_levels - 1)
+    k2["angle"] = (k1["angle"][src] + rng.normal(0, 12, n2)) % 360
+    bits = np.unpackbits(d1[src], axis=1)
+    flips = rng.integers(0, 60, n2)
+    bits ^= (np.argsort(np.argsort(rng.random((n2, 256)), axis=1), axis=1) < flips[:, None]).astype(np.uint8)
+    d2 = np.packbits(bits, axis=1)
+    cam2 = np.where(rng.random(n2) < 0.9, cam1[src], 1 - cam1[src])
+    node2 = np.where(rng.random(n2) < 0.85, node1[src], rng.integers(0, n_nodes, n2))
+    sf = (1.2 ** np.arange(n_levels)).astype(np.float32)
+    return dict(k1=k1, d1=d1, has_mp1=(rng.random(n1) < 0.3).astype(np.int32), cam1=cam1.astype(np.int32),
+                uright1=np.where(rng.random(n1) < 0.2, k1["x"] - 5, -1).astype(np.float32), node1=node1,
+                k2=k2, d2=d2, has_mp2=(rng.random(n2) < 0.3).astype(np.int32), cam2=cam2.astype(np.int32),
+                uright2=np.where(rng.random(n2) < 0.2, k2["x"] - 5, -1).astype(np.float32), node2=node2,
+                F12s=F12s.astype(np.float32), epipoles=np.array(epi, dtype=np.float32), scale_factors=sf,
+                level_sigma2=(sf * sf).astype(np.float32), src=src)

@@ -261,6 +261,101 @@ int om_search_by_bow(const uint8_t* d1, const float* angle1, const int32_t* vali
   return nmatches;
 }
 
+// ORBmatcher::CheckDistEpipolarLine (src/ORBmatcher.cc:167-184); F12 row-major 3x3.
+static bool check_dist_epipolar_line(const oo_keypoint& kp1, const oo_keypoint& kp2, const float* F12,
+                                     const float* level_sigma2) {
+  const float a = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+  const float b = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+  const float c = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+  const float num = a * kp2.x + b * kp2.y + c;
+  const float den = a * a + b * b;
+  if (den == 0) return false;
+  const float dsqr = num * num / den;
+  return dsqr < 3.84 * level_sigma2[kp2.octave];
+}
+
+// ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:1364-1720), from the feature-vector walk
+// on (:1433-1700).  The fundamental matrices F12s[cam] (:1421-1423) and the epipoles (ex, ey) of
+// both cameras (:1441-1449) are inputs: they are cv::Mat algebra on the key-frame poses that the
+// caller evaluates with its own OpenCV (the reference's F12 argument, which it recomputes).
+// Note vbMatched2 is never set in the reference (:1452 only declares it), so key-frame-2 features
+// can be matched by several key-frame-1 features.
+int om_search_for_triangulation(const oo_keypoint* k1, const uint8_t* d1, const int32_t* has_mp1, const int32_t* cam1,
+                                const float* uright1, int n1, const int32_t* node1, const int32_t* start1,
+                                const int32_t* items1, int nn1, const oo_keypoint* k2, const uint8_t* d2,
+                                const int32_t* has_mp2, const int32_t* cam2, const float* uright2, int n2,
+                                const int32_t* node2, const int32_t* start2, const int32_t* items2, int nn2,
+                                const float* F12s, const float* epipoles, const float* scale_factors2,
+                                const float* level_sigma2_2, int only_stereo, const int32_t* cam_enabled, int check_ori,
+                                int32_t* matches12) {
+  (void)n2;
+  int nmatches = 0;
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  const float factor = 1.0f / HISTO_LENGTH;
+  int a = 0, b = 0;
+  while (a < nn1 && b < nn2) {
+    if (node1[a] == node2[b]) {
+      for (int p = start1[a]; p < start1[a + 1]; ++p) {
+        const int idx1 = items1[p];
+        if (has_mp1[idx1]) continue;
+        const int camIdx1 = cam1[idx1];
+        if (!cam_enabled[camIdx1]) continue;
+        const bool bStereo1 = uright1[idx1] >= 0;
+        if (only_stereo && !bStereo1) continue;
+        const oo_keypoint& kp1 = k1[idx1];
+        int bestDist = TH_LOW, bestIdx2 = -1;
+        for (int q = start2[b]; q < start2[b + 1]; ++q) {
+          const int idx2 = items2[q];
+          if (has_mp2[idx2]) continue;
+          const int camIdx2 = cam2[idx2];
+          if (camIdx1 != camIdx2) continue;
+          const bool bStereo2 = uright2[idx2] >= 0;
+          if (only_stereo && !bStereo2) continue;
+          const int dist = om_distance(d1 + (size_t)idx1 * 32, d2 + (size_t)idx2 * 32);
+          if (dist > TH_LOW || dist > bestDist) continue;
+          const oo_keypoint& kp2 = k2[idx2];
+          if (!bStereo1 && !bStereo2) {
+            const float distex = epipoles[2 * camIdx2] - kp2.x;
+            const float distey = epipoles[2 * camIdx2 + 1] - kp2.y;
+            if (distex * distex + distey * distey < 100 * scale_factors2[kp2.octave]) continue;
+          }
+          if (check_dist_epipolar_line(kp1, kp2, F12s + 9 * camIdx1, level_sigma2_2)) {
+            bestIdx2 = idx2;
+            bestDist = dist;
+          }
+        }
+        if (bestIdx2 >= 0) {
+          matches12[idx1] = bestIdx2;
+          nmatches++;
+          if (check_ori) {
+            float rot = kp1.angle - k2[bestIdx2].angle;
+            if (rot < 0.0) rot += 360.0f;
+            int bin = (int)std::round(rot * factor);
+            if (bin == HISTO_LENGTH) bin = 0;
+            rotHist[bin].push_back(idx1);
+          }
+        }
+      }
+      ++a;
+      ++b;
+    } else if (node1[a] < node2[b]) {
+      a = (int)(std::lower_bound(node1 + a, node1 + nn1, node2[b]) - node1);
+    } else {
+      b = (int)(std::lower_bound(node2 + b, node2 + nn2, node1[a]) - node2);
+    }
+  }
+  if (check_ori) {
+    int counts[HISTO_LENGTH], i1, i2, i3;
+    for (int i = 0; i < HISTO_LENGTH; ++i) counts[i] = (int)rotHist[i].size();
+    om_three_maxima(counts, HISTO_LENGTH, &i1, &i2, &i3);
+    for (int i = 0; i < HISTO_LENGTH; ++i)
+      if (i != i1 && i != i2 && i != i3)
+        for (int idx1 : rotHist[i]) { matches12[idx1] = -1; nmatches--; }
+  }
+  return nmatches;
+}
+
 // src/ORBmatcher.cc:62-157
 int om_search_by_projection_points(const oo_keypoint* k, const uint8_t* d, const float* u_right,
                                    int n, om_bounds b, const float* scale_factors, int nlevels,

@@ -160,6 +160,23 @@ int om_search_by_bow(const uint8_t* d1, const float* angle1, const int32_t* vali
                      const int32_t* node2, const int32_t* start2, const int32_t* items2, int nn2,
                      float nnratio, int check_ori, int max_dist, int32_t* matches12, int32_t* matches21);
 
+// ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:1364-1720) with CheckDistEpipolarLine (:167-184).
+//  key frames: concatenated keypoints (mvKeysUn_total: pt, angle, octave used), descriptor per global
+//    index, has_mp[i] = GetMapPoint(i) != NULL, cam[i] = keypoint_to_cam, uright[i] = mvuRight_total, CSR
+//    feature vector (mFeatVec);
+//  F12s: two row-major 3x3 fundamental matrices (camera 0, camera 1; :1421-1423); epipoles: (ex, ey) of
+//    camera 0 then camera 1 (:1441-1449); scale_factors2 / level_sigma2_2 = pKF2->mvScaleFactors /
+//    mvLevelSigma2; cam_enabled = vbCam; matches12 (n1) = vMatches12 (vMatchedPairs = its non-negative
+//    entries in index order).
+int om_search_for_triangulation(const oo_keypoint* k1, const uint8_t* d1, const int32_t* has_mp1, const int32_t* cam1,
+                                const float* uright1, int n1, const int32_t* node1, const int32_t* start1,
+                                const int32_t* items1, int nn1, const oo_keypoint* k2, const uint8_t* d2,
+                                const int32_t* has_mp2, const int32_t* cam2, const float* uright2, int n2,
+                                const int32_t* node2, const int32_t* start2, const int32_t* items2, int nn2,
+                                const float* F12s, const float* epipoles, const float* scale_factors2,
+                                const float* level_sigma2_2, int only_stereo, const int32_t* cam_enabled, int check_ori,
+                                int32_t* matches12);
+
 // ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:3948-3989) on bin counts.
 void om_three_maxima(const int* counts, int L, int* ind1, int* ind2, int* ind3);
 

@@ -310,6 +310,31 @@ def search_by_bow(d1, angle1, valid1, fv1, d2, angle2, valid2, fv2, nnratio=0.7,
     return n, m12, m21
 
 
+def search_for_triangulation(sc, fv1, fv2, only_stereo=False, cam_enabled=(1, 1), check_ori=True):
+    """sc: dict of synth.triangulation_scene arrays.  Returns (nmatches, matches12)."""
+    lib = load("port")
+    c = lambda a, t: np.ascontiguousarray(a, dtype=t)
+    k1, k2 = c(sc["k1"], KP_DTYPE), c(sc["k2"], KP_DTYPE)
+    d1, d2 = c(sc["d1"], np.uint8), c(sc["d2"], np.uint8)
+    arrs = [k1, d1, c(sc["has_mp1"], np.int32), c(sc["cam1"], np.int32), c(sc["uright1"], np.float32)]
+    f1 = [c(a, np.int32) for a in fv1]
+    arrs2 = [k2, d2, c(sc["has_mp2"], np.int32), c(sc["cam2"], np.int32), c(sc["uright2"], np.float32)]
+    f2 = [c(a, np.int32) for a in fv2]
+    tail = [c(sc["F12s"], np.float32), c(sc["epipoles"], np.float32), c(sc["scale_factors"], np.float32),
+            c(sc["level_sigma2"], np.float32)]
+    en = c(cam_enabled, np.int32)
+    m12 = np.zeros(len(k1), dtype=np.int32)
+    f = lib.om_search_for_triangulation
+    f.restype = C.c_int
+    side = [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int]
+    f.argtypes = side + side + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    p = lambda a: a.ctypes.data
+    n = f(*[p(a) for a in arrs], len(k1), p(f1[0]), p(f1[1]), p(f1[2]), len(f1[0]),
+          *[p(a) for a in arrs2], len(k2), p(f2[0]), p(f2[1]), p(f2[2]), len(f2[0]),
+          *[p(a) for a in tail], int(only_stereo), p(en), int(check_ori), p(m12))
+    return n, m12
+
+
 def three_maxima(counts):
     lib = load("port")
     c = np.ascontiguousarray(counts, dtype=np.int32)

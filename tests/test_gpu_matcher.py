@@ -389,3 +389,46 @@ def test_search_by_bow_edge_cases(O):
     bad = (np.zeros(1, np.int32), np.array([0, 1], np.int32), np.array([99], np.int32))
     with pytest.raises(OrbError):
         m.SearchByBoW(sc["d1"], sc["a1"], None, bad, sc["d2"], sc["a2"], None, feature_vector(np.zeros(60, np.int64)))
+
+
+# ---- SearchForTriangulation (src/ORBmatcher.cc:1364-1720) ---------------------------------------
+@pytest.mark.parametrize("n1,n2,n_nodes,only_stereo,cam_enabled,check_ori", [
+    (2000, 2200, 100, False, (True, True), True),
+    (2000, 2000, 40, False, (True, False), True),     # vbCam disables camera 2
+    (1500, 1500, 10, True, (True, True), False),      # bOnlyStereo
+    (500, 6000, 2, False, (True, True), True),        # very large nodes
+])
+def test_search_for_triangulation_vs_oracle(O, n1, n2, n_nodes, only_stereo, cam_enabled, check_ori):
+    from multi_orb_slam_b200.matcher import ORBmatcher
+    from multi_orb_slam_b200.synth import feature_vector, triangulation_scene
+    sc = triangulation_scene(n1, n2, n_nodes, 11 + n_nodes)
+    node2 = np.where(sc["node2"] % 9 == 4, -1, sc["node2"])
+    fv1, fv2 = feature_vector(sc["node1"]), feature_vector(node2)
+    m = ORBmatcher(0.6, check_ori)
+    nm, m12, pairs = m.SearchForTriangulation(sc["k1"], sc["d1"], sc["has_mp1"], sc["cam1"], sc["uright1"], fv1,
+                                              sc["k2"], sc["d2"], sc["has_mp2"], sc["cam2"], sc["uright2"], fv2,
+                                              sc["F12s"], sc["epipoles"], sc["scale_factors"], sc["level_sigma2"],
+                                              bOnlyStereo=only_stereo, vbCam=cam_enabled)
+    rn, rm12 = O.search_for_triangulation(sc, fv1, fv2, only_stereo, [int(v) for v in cam_enabled], check_ori)
+    assert nm == rn and np.array_equal(m12, rm12)
+    assert len(pairs) == nm and np.array_equal(pairs[:, 1], rm12[pairs[:, 0]])
+    if not only_stereo:
+        assert nm > 50
+    # nothing matched where the reference forbids it
+    assert not sc["has_mp1"][pairs[:, 0]].any() and not sc["has_mp2"][pairs[:, 1]].any()
+    assert np.array_equal(sc["cam1"][pairs[:, 0]], sc["cam2"][pairs[:, 1]])
+
+
+def test_search_for_triangulation_degenerate(O):
+    from multi_orb_slam_b200.matcher import ORBmatcher
+    from multi_orb_slam_b200.synth import feature_vector, triangulation_scene
+    sc = triangulation_scene(60, 60, 3, 2)
+    m = ORBmatcher(0.6, True)
+    fv1 = feature_vector(sc["node1"])
+    args = lambda fv2, F: (sc["k1"], sc["d1"], sc["has_mp1"], sc["cam1"], sc["uright1"], fv1, sc["k2"], sc["d2"], sc["has_mp2"],
+                           sc["cam2"], sc["uright2"], fv2, F, sc["epipoles"], sc["scale_factors"], sc["level_sigma2"])
+    nm, m12, pairs = m.SearchForTriangulation(*args(feature_vector(sc["node2"] + 50), sc["F12s"]))  # no common node
+    assert nm == 0 and (m12 == -1).all() and pairs.shape == (0, 2)
+    # zero fundamental matrix: den == 0 -> CheckDistEpipolarLine is false for every pair (:178-179)
+    nm, m12, _ = m.SearchForTriangulation(*args(feature_vector(sc["node2"]), np.zeros((2, 3, 3), np.float32)))
+    assert nm == 0 and (m12 == -1).all()

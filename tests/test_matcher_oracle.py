@@ -267,3 +267,94 @@ def test_search_by_bow_degenerate(O):
     empty = (np.zeros(0, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32))
     rn, rm12, _ = O.search_by_bow(sc["d1"], sc["a1"], None, empty, sc["d2"], sc["a2"], None, fv2)
     assert rn == 0 and (rm12 == -1).all()
+
+
+# ---- SearchForTriangulation (src/ORBmatcher.cc:1364-1720, CheckDistEpipolarLine :167-184) -------
+def _py_search_for_triangulation(sc, fv1, fv2, only_stereo, cam_enabled, check_ori):
+    import bisect
+    f32 = np.float32
+    map1 = {int(n): [int(i) for i in fv1[2][fv1[1][k]:fv1[1][k + 1]]] for k, n in enumerate(fv1[0])}
+    map2 = {int(n): [int(i) for i in fv2[2][fv2[1][k]:fv2[1][k + 1]]] for k, n in enumerate(fv2[0])}
+    keys1, keys2 = sorted(map1), sorted(map2)
+    k1, k2, F, epi = sc["k1"], sc["k2"], sc["F12s"], sc["epipoles"]
+    m12 = [-1] * len(k1)
+    hist = [[] for _ in range(30)]
+    dist = lambda x, y: int(np.unpackbits(x ^ y).sum())
+
+    def epipolar_ok(i1, i2, Fc):
+        x1, y1, x2, y2 = f32(k1["x"][i1]), f32(k1["y"][i1]), f32(k2["x"][i2]), f32(k2["y"][i2])
+        a = f32(f32(f32(x1 * Fc[0, 0]) + f32(y1 * Fc[1, 0])) + Fc[2, 0])
+        b = f32(f32(f32(x1 * Fc[0, 1]) + f32(y1 * Fc[1, 1])) + Fc[2, 1])
+        c = f32(f32(f32(x1 * Fc[0, 2]) + f32(y1 * Fc[1, 2])) + Fc[2, 2])
+        num = f32(f32(f32(a * x2) + f32(b * y2)) + c)
+        den = f32(f32(a * a) + f32(b * b))
+        if den == 0:
+            return False
+        dsqr = f32(f32(num * num) / den)
+        return float(dsqr) < 3.84 * float(sc["level_sigma2"][k2["octave"][i2]])
+
+    nm, ia, ib = 0, 0, 0
+    while ia < len(keys1) and ib < len(keys2):
+        if keys1[ia] == keys2[ib]:
+            for i1 in map1[keys1[ia]]:
+                if sc["has_mp1"][i1] or not cam_enabled[sc["cam1"][i1]]:
+                    continue
+                st1 = sc["uright1"][i1] >= 0
+                if only_stereo and not st1:
+                    continue
+                best, bi = 50, -1
+                for i2 in map2[keys2[ib]]:
+                    if sc["has_mp2"][i2] or sc["cam2"][i2] != sc["cam1"][i1]:
+                        continue
+                    st2 = sc["uright2"][i2] >= 0
+                    if only_stereo and not st2:
+                        continue
+                    dd = dist(sc["d1"][i1], sc["d2"][i2])
+                    if dd > 50 or dd > best:
+                        continue
+                    if not st1 and not st2:
+                        c2 = sc["cam2"][i2]
+                        ex = f32(epi[2 * c2] - f32(k2["x"][i2]))
+                        ey = f32(epi[2 * c2 + 1] - f32(k2["y"][i2]))
+                        if f32(f32(ex * ex) + f32(ey * ey)) < f32(f32(100) * sc["scale_factors"][k2["octave"][i2]]):
+                            continue
+                    if epipolar_ok(i1, i2, F[sc["cam1"][i1]]):
+                        bi, best = i2, dd
+                if bi >= 0:
+                    m12[i1] = bi
+                    nm += 1
+                    if check_ori:
+                        rot = f32(k1["angle"][i1]) - f32(k2["angle"][bi])
+                        if rot < 0:
+                            rot = f32(rot + f32(360.0))
+                        b = int(math.floor(f32(rot * f32(1.0 / 30)) + 0.5))
+                        hist[0 if b == 30 else b].append(i1)
+            ia, ib = ia + 1, ib + 1
+        elif keys1[ia] < keys2[ib]:
+            ia = bisect.bisect_left(keys1, keys2[ib])
+        else:
+            ib = bisect.bisect_left(keys2, keys1[ia])
+    if check_ori:
+        import oracle_lib
+        keep = set(oracle_lib.three_maxima([len(h) for h in hist]))
+        for b in range(30):
+            if b not in keep:
+                for i1 in hist[b]:
+                    m12[i1] = -1
+                    nm -= 1
+    return nm, m12
+
+
+@pytest.mark.parametrize("seed,n_nodes,only_stereo,cam_enabled,check_ori", [
+    (0, 10, False, (1, 1), True), (1, 30, False, (1, 0), True), (2, 6, True, (1, 1), False), (3, 15, False, (1, 1), False)])
+def test_search_for_triangulation_vs_python(O, seed, n_nodes, only_stereo, cam_enabled, check_ori):
+    from multi_orb_slam_b200.synth import feature_vector, triangulation_scene
+    sc = triangulation_scene(160, 200, n_nodes, seed)
+    node2 = np.where(sc["node2"] % 5 == 2, -1, sc["node2"])
+    fv1, fv2 = feature_vector(sc["node1"]), feature_vector(node2)
+    rn, rm12 = O.search_for_triangulation(sc, fv1, fv2, only_stereo, cam_enabled, check_ori)
+    pn, pm12 = _py_search_for_triangulation(sc, fv1, fv2, only_stereo, cam_enabled, check_ori)
+    assert rn == pn and list(rm12) == pm12
+    assert rn == int((rm12 >= 0).sum())
+    if not only_stereo:
+        assert rn > 10
