@@ -253,6 +253,35 @@ int orbm_search_by_projection_sim3_host(orbm_matcher* m, const orbx_keypoint* kf
                                         const float* mp_max_d, const uint8_t* mp_desc, int n_mp, int th, int32_t* matched,
                                         int* nmatches);
 
+/* ---- Frame glue between the extractor and the matchers (src/Frame.cc), device-resident batches laid out
+ * like the extractor's batch outputs (n_frames x cap keypoints, counts per frame) ------------------------- */
+
+/* Frame::UndistortKeyPoints{,_cam2} (src/Frame.cc:673-706, 708-741): cv::undistortPoints(mat, mat, mK,
+ * mDistCoef, Mat(), mK), OpenCV 4.x, default criteria (5 iterations), double arithmetic; dist5 (host) =
+ * mDistCoef (k1, k2, p1, p2, k3; k3 = 0 for the four-parameter model); k1 == 0 copies (:675-679).  Every other
+ * keypoint field is carried over.  The _host variant takes one frame in host memory. */
+int orbm_undistort_keypoints_device(orbm_matcher* m, int n_frames, int cap, const orbx_keypoint* d_kps,
+                                    const int32_t* d_counts, float fx, float fy, float cx, float cy, const float* dist5,
+                                    orbx_keypoint* d_kps_un);
+int orbm_undistort_keypoints_host(orbm_matcher* m, const orbx_keypoint* k, int n, float fx, float fy, float cx, float cy,
+                                  const float* dist5, orbx_keypoint* k_un);
+/* Frame::ComputeImageBounds (src/Frame.cc:743-779): mnMinX/mnMaxX/mnMinY/mnMaxY from the undistorted corners. */
+int orbm_compute_image_bounds_host(orbm_matcher* m, int cols, int rows, float fx, float fy, float cx, float cy,
+                                   const float* dist5, orbm_bounds* out);
+/* Frame::ComputeStereoFromRGBD{,_cam2} (src/Frame.cc:959-985, 987-1010): d_depth = CV_32F depth images
+ * (n_frames x rows x row_stride floats, already scaled by mDepthMapFactor) read at the DISTORTED keypoint
+ * truncated to int; writes mvuRight and mvDepth (-1 where depth <= 0 and beyond counts[f]). */
+int orbm_compute_stereo_from_rgbd_device(orbm_matcher* m, int n_frames, int cap, const orbx_keypoint* d_kps,
+                                         const orbx_keypoint* d_kps_un, const int32_t* d_counts, const float* d_depth,
+                                         int cols, int rows, size_t row_stride_floats, size_t frame_stride_floats, float mbf,
+                                         float* d_uright, float* d_depth_out);
+/* Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:348-395, 632-642): per frame a CSR grid over
+ * cell = ix*48 + iy (d_cell_start: n_frames x (64*48 + 1) ints; d_items: n_frames x cap u16 keypoint indices,
+ * insertion order inside a cell = mGrid[ix][iy]). */
+int orbm_assign_features_to_grid_device(orbm_matcher* m, int n_frames, int cap, const orbx_keypoint* d_kps_un,
+                                        const int32_t* d_counts, orbm_bounds bounds, int32_t* d_cell_start,
+                                        uint16_t* d_items);
+
 /* DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned int>>, Thirdparty/DBoW2/DBoW2/FeatureVector.h)
  * flattened to CSR: node ids ascending (the map's order), start[n_nodes + 1], items = feature indices in
  * vector order.  A feature index occurs at most once per vector (DBoW2 guarantees it). */

@@ -560,6 +560,76 @@ __global__ void __launch_bounds__(INIT_NT) k_init_resolve(int cap, const orbx_ke
   if (tid == 0) nmatches_out[pair] = s_nmatch;
 }
 
+// ---- Frame glue between extractor and matchers (src/Frame.cc) ---------------------------------
+// Frame::UndistortKeyPoints (:673-706): cv::undistortPoints(mat, mat, mK, mDistCoef, Mat(), mK) with the
+// default criteria = five fixed-point iterations of OpenCV 4.x cvUndistortPointsInternal, all in double
+// without contraction (the restatement in oracle/cvprim.cc is pinned bit-exact against cv2 4.13).
+// Terms that are exactly zero for a (k1, k2, p1, p2, k3) model are dropped: the rational numerator is 1,
+// k8..k11 = 0, the tilt matrices are the identity, and RR = K * I = K so ww = 1.
+struct UndistortParams {
+  double fx, fy, cx, cy, ifx, ify, k0, k1, k2, k3, k4;
+};
+
+__global__ void __launch_bounds__(256) k_undistort(const orbx_keypoint* __restrict__ kps, const int32_t* __restrict__ counts,
+                                                   int n_fixed, int cap, UndistortParams P, int identity,
+                                                   orbx_keypoint* __restrict__ out) {
+  const int frame = blockIdx.y;
+  const int n = counts ? min(counts[frame], cap) : n_fixed;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  orbx_keypoint kp = kps[(size_t)frame * cap + i];
+  if (!identity) {
+    const double u = (double)kp.x, v = (double)kp.y;
+    double x = __dmul_rn(__dsub_rn(u, P.cx), P.ifx), y = __dmul_rn(__dsub_rn(v, P.cy), P.ify);
+    const double x0 = x, y0 = y;
+#pragma unroll 1
+    for (int j = 0; j < 5; ++j) {
+      const double xx = __dmul_rn(x, x), yy = __dmul_rn(y, y);
+      const double r2 = __dadd_rn(xx, yy);
+      const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(P.k4, r2), P.k1), r2), P.k0), r2));
+      const double icdist = __ddiv_rn(1.0, den);
+      if (icdist < 0) {
+        x = x0;  // (u - cx) * ifx, the value x0 holds
+        y = y0;
+        break;
+      }
+      // deltaX = 2*k2*x*y + k3*(r2 + 2*x*x);  deltaY = k2*(r2 + 2*y*y) + 2*k3*x*y   (left to right)
+      const double dX = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, P.k2), x), y),
+                                  __dmul_rn(P.k3, __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x))));
+      const double dY = __dadd_rn(__dmul_rn(P.k2, __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y))),
+                                  __dmul_rn(__dmul_rn(__dmul_rn(2.0, P.k3), x), y));
+      x = __dmul_rn(__dsub_rn(x0, dX), icdist);
+      y = __dmul_rn(__dsub_rn(y0, dY), icdist);
+    }
+    kp.x = (float)__dadd_rn(__dmul_rn(P.fx, x), P.cx);
+    kp.y = (float)__dadd_rn(__dmul_rn(P.fy, y), P.cy);
+  }
+  out[(size_t)frame * cap + i] = kp;
+}
+
+// Frame::ComputeStereoFromRGBD (:959-985): depth at the distorted keypoint (coordinates truncated).
+__global__ void __launch_bounds__(256) k_stereo_rgbd(const orbx_keypoint* __restrict__ kps,
+                                                     const orbx_keypoint* __restrict__ kps_un,
+                                                     const int32_t* __restrict__ counts, int cap,
+                                                     const float* __restrict__ depth, size_t row_stride, size_t frame_stride,
+                                                     float mbf, float* __restrict__ uright, float* __restrict__ depth_out) {
+  const int frame = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= cap) return;
+  const size_t o = (size_t)frame * cap + i;
+  float ur = -1.f, dz = -1.f;
+  if (i < min(counts[frame], cap)) {
+    const orbx_keypoint kp = kps[o];
+    const float d = depth[(size_t)frame * frame_stride + (size_t)(int)kp.y * row_stride + (int)kp.x];
+    if (d > 0) {
+      dz = d;
+      ur = __fsub_rn(kps_un[o].x, __fdiv_rn(mbf, d));
+    }
+  }
+  uright[o] = ur;
+  depth_out[o] = dz;
+}
+
 // ---- SearchByBoW (:206-388, 390-565, 996-1163, 1180-1363) ------------------------------------
 // The host walks the two feature vectors (node ids are a few hundred ints) and emits one query
 // per valid side-1 feature of a common node: {idx1, first side-2 item, item count, row offset}.
@@ -1507,6 +1577,99 @@ int orbm_search_for_triangulation_host(orbm_matcher* m, const orbx_keypoint* k1,
   cudaMemcpyAsync(nmatches, dnm, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (!m->check(cudaStreamSynchronize(st), "search_for_triangulation")) return ORBX_E_CUDA;
   return m->check(cudaGetLastError(), "search_for_triangulation launch") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+// ---- Frame glue -------------------------------------------------------------------------------
+}  // extern "C"
+#pragma GCC visibility pop
+namespace {
+UndistortParams undistort_params(float fx, float fy, float cx, float cy, const float* dist5) {
+  UndistortParams P;
+  P.fx = fx; P.fy = fy; P.cx = cx; P.cy = cy;
+  P.ifx = 1. / P.fx; P.ify = 1. / P.fy;
+  P.k0 = dist5[0]; P.k1 = dist5[1]; P.k2 = dist5[2]; P.k3 = dist5[3]; P.k4 = dist5[4];
+  return P;
+}
+}  // namespace
+extern "C" {
+#pragma GCC visibility push(default)
+
+int orbm_undistort_keypoints_device(orbm_matcher* m, int n_frames, int cap, const orbx_keypoint* d_kps,
+                                    const int32_t* d_counts, float fx, float fy, float cx, float cy, const float* dist5,
+                                    orbx_keypoint* d_kps_un) {
+  if (!m || n_frames < 0 || cap < 1 || !d_kps || !d_counts || !dist5 || !d_kps_un || fx == 0.f || fy == 0.f)
+    return ORBX_E_INVALID;
+  if (n_frames == 0) return ORBX_OK;
+  cudaSetDevice(m->device);
+  k_undistort<<<dim3((cap + 255) / 256, n_frames), 256, 0, m->stream>>>(d_kps, d_counts, 0, cap,
+                                                                        undistort_params(fx, fy, cx, cy, dist5),
+                                                                        dist5[0] == 0.0f, d_kps_un);  // :675-679
+  m->launches += 1;
+  return m->check(cudaGetLastError(), "undistort launch") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+int orbm_undistort_keypoints_host(orbm_matcher* m, const orbx_keypoint* k, int n, float fx, float fy, float cx, float cy,
+                                  const float* dist5, orbx_keypoint* k_un) {
+  if (!m || n < 0 || (n && (!k || !k_un)) || !dist5 || fx == 0.f || fy == 0.f) return ORBX_E_INVALID;
+  if (n == 0) return ORBX_OK;
+  cudaSetDevice(m->device);
+  cudaStream_t st = m->stream;
+  orbx_keypoint* d = m->scratch<orbx_keypoint>(8, 2 * (size_t)n);
+  if (!d) return ORBX_E_CUDA;
+  cudaMemcpyAsync(d, k, sizeof(orbx_keypoint) * n, cudaMemcpyHostToDevice, st);
+  k_undistort<<<dim3((n + 255) / 256, 1), 256, 0, st>>>(d, nullptr, n, n, undistort_params(fx, fy, cx, cy, dist5),
+                                                        dist5[0] == 0.0f, d + n);
+  m->launches += 1;
+  cudaMemcpyAsync(k_un, d + n, sizeof(orbx_keypoint) * n, cudaMemcpyDeviceToHost, st);
+  if (!m->check(cudaStreamSynchronize(st), "undistort")) return ORBX_E_CUDA;
+  return m->check(cudaGetLastError(), "undistort launch") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+int orbm_compute_image_bounds_host(orbm_matcher* m, int cols, int rows, float fx, float fy, float cx, float cy,
+                                   const float* dist5, orbm_bounds* out) {
+  if (!m || !dist5 || !out || cols < 1 || rows < 1) return ORBX_E_INVALID;
+  if (dist5[0] == 0.0f) {  // :772-778
+    out->min_x = 0.0f; out->max_x = (float)cols; out->min_y = 0.0f; out->max_y = (float)rows;
+    return ORBX_OK;
+  }
+  orbx_keypoint c[4] = {}, u[4];
+  c[1].x = (float)cols; c[2].y = (float)rows; c[3].x = (float)cols; c[3].y = (float)rows;  // :749-757
+  const int rc = orbm_undistort_keypoints_host(m, c, 4, fx, fy, cx, cy, dist5, u);
+  if (rc != ORBX_OK) return rc;
+  out->min_x = std::min(u[0].x, u[2].x);  // :766-769
+  out->max_x = std::max(u[1].x, u[3].x);
+  out->min_y = std::min(u[0].y, u[1].y);
+  out->max_y = std::max(u[2].y, u[3].y);
+  return ORBX_OK;
+}
+
+int orbm_compute_stereo_from_rgbd_device(orbm_matcher* m, int n_frames, int cap, const orbx_keypoint* d_kps,
+                                         const orbx_keypoint* d_kps_un, const int32_t* d_counts, const float* d_depth,
+                                         int cols, int rows, size_t row_stride_floats, size_t frame_stride_floats, float mbf,
+                                         float* d_uright, float* d_depth_out) {
+  if (!m || n_frames < 0 || cap < 1 || !d_kps || !d_kps_un || !d_counts || !d_depth || !d_uright || !d_depth_out ||
+      cols < 1 || rows < 1 || row_stride_floats < (size_t)cols)
+    return ORBX_E_INVALID;
+  if (n_frames == 0) return ORBX_OK;
+  cudaSetDevice(m->device);
+  k_stereo_rgbd<<<dim3((cap + 255) / 256, n_frames), 256, 0, m->stream>>>(d_kps, d_kps_un, d_counts, cap, d_depth,
+                                                                          row_stride_floats, frame_stride_floats, mbf,
+                                                                          d_uright, d_depth_out);
+  m->launches += 1;
+  return m->check(cudaGetLastError(), "stereo-from-rgbd launch") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+int orbm_assign_features_to_grid_device(orbm_matcher* m, int n_frames, int cap, const orbx_keypoint* d_kps_un,
+                                        const int32_t* d_counts, orbm_bounds bounds, int32_t* d_cell_start,
+                                        uint16_t* d_items) {
+  if (!m || n_frames < 0 || cap < 1 || cap > 65535 || !d_kps_un || !d_counts || !d_cell_start || !d_items ||
+      !(bounds.max_x > bounds.min_x) || !(bounds.max_y > bounds.min_y))
+    return ORBX_E_INVALID;
+  if (n_frames == 0) return ORBX_OK;
+  cudaSetDevice(m->device);
+  k_build_grid<<<n_frames, 256, 0, m->stream>>>(d_kps_un, d_counts, 0, cap, bounds, d_cell_start, d_items);
+  m->launches += 1;
+  return m->check(cudaGetLastError(), "grid launch") ? ORBX_OK : ORBX_E_CUDA;
 }
 
 // ---- pose-based SearchByProjection overloads ------------------------------------------------

@@ -234,3 +234,42 @@ void fast9_16(const uint8_t* img, size_t step, int w, int h, int threshold, bool
 }
 
 }  // namespace cvp
+
+namespace cvp {
+void undistort_points(const float* src_xy, int n, float fxf, float fyf, float cxf, float cyf, const float* dist5,
+                      float* dst_xy) {
+  // A = K converted to double; k[0..4] = k1 k2 p1 p2 k3, k[5..13] = 0 (rational / thin-prism / tilt terms unused)
+  const double fx = fxf, fy = fyf, cx = cxf, cy = cyf;
+  const double ifx = 1. / fx, ify = 1. / fy;
+  double k[14] = {0};
+  for (int i = 0; i < 5; ++i) k[i] = dist5[i];
+  // RR = P * R with R = I, P = K (cvMatMul in double; the products by the zeros and the one are exact)
+  const double RR[3][3] = {{fx, 0, cx}, {0, fy, cy}, {0, 0, 1}};
+  for (int i = 0; i < n; ++i) {
+    double x = src_xy[2 * i], y = src_xy[2 * i + 1];
+    const double u = x, v = y;
+    x = (x - cx) * ifx;
+    y = (y - cy) * ify;
+    // tilt compensation with the identity matrix: vecUntilt = (x, y, 1), invProj = 1
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; ++j) {
+      const double r2 = x * x + y * y;
+      const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+      if (icdist < 0) {  // OpenCV regression 14583
+        x = (u - cx) * ifx;
+        y = (v - cy) * ify;
+        break;
+      }
+      const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+      const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+      x = (x0 - deltaX) * icdist;
+      y = (y0 - deltaY) * icdist;
+    }
+    const double xx = RR[0][0] * x + RR[0][1] * y + RR[0][2];
+    const double yy = RR[1][0] * x + RR[1][1] * y + RR[1][2];
+    const double ww = 1. / (RR[2][0] * x + RR[2][1] * y + RR[2][2]);
+    dst_xy[2 * i] = (float)(xx * ww);
+    dst_xy[2 * i + 1] = (float)(yy * ww);
+  }
+}
+}  // namespace cvp

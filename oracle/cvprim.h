@@ -47,3 +47,11 @@ void fast9_16(const uint8_t* img, size_t step, int w, int h, int threshold, bool
 int fast9_arc_measure(const uint8_t* p, size_t step);
 
 }  // namespace cvp
+
+namespace cvp {
+// cv::undistortPoints(src, dst, K, dist, noArray(), K) for CV_32FC2 points with the default
+// termination criteria (COUNT, 5 iterations), OpenCV 4.x cvUndistortPointsInternal: everything in
+// double, K = [fx 0 cx; 0 fy cy; 0 0 1], dist = (k1, k2, p1, p2, k3); result rounded to float.
+void undistort_points(const float* src_xy, int n, float fx, float fy, float cx, float cy, const float* dist5,
+                      float* dst_xy);
+}  // namespace cvp

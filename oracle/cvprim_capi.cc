@@ -25,3 +25,8 @@ void cvp_sincos_libm(const float* a, float* c, float* s, int n) {
 }
 int cvp_round(float v) { return cvp::round_f(v); }
 }
+
+extern "C" void cvp_undistort_points(const float* src_xy, int n, float fx, float fy, float cx, float cy, const float* dist5,
+                                     float* dst_xy) {
+  cvp::undistort_points(src_xy, n, fx, fy, cx, cy, dist5, dst_xy);
+}

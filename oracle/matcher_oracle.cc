@@ -7,6 +7,7 @@
 // functions.  Pins we add: hand-checkable known-answer tests in
 // tests/test_matcher_oracle.py.
 #include "orb_oracle.h"
+#include "cvprim.h"
 
 #include <climits>
 #include <cmath>
@@ -187,6 +188,69 @@ int om_search_for_initialization(const oo_keypoint* k1, const uint8_t* d1, int n
       prev_xy[2 * i1 + 1] = k2[matches12[i1]].y;
     }
   return nmatches;
+}
+
+// ---- Frame glue between the extractor and the matchers (src/Frame.cc) -----------------------
+// Frame::UndistortKeyPoints (src/Frame.cc:673-706; _cam2 :708-741 is the same on camera 2's arrays).
+void om_undistort_keypoints(const oo_keypoint* k, int n, float fx, float fy, float cx, float cy, const float* dist5,
+                            oo_keypoint* k_un) {
+  for (int i = 0; i < n; ++i) k_un[i] = k[i];
+  if (dist5[0] == 0.0) return;  // :675-679
+  std::vector<float> mat(2 * (size_t)n), out(2 * (size_t)n);
+  for (int i = 0; i < n; ++i) { mat[2 * i] = k[i].x; mat[2 * i + 1] = k[i].y; }
+  cvp::undistort_points(mat.data(), n, fx, fy, cx, cy, dist5, out.data());  // cv::undistortPoints(mat,mat,mK,mDistCoef,Mat(),mK)
+  for (int i = 0; i < n; ++i) { k_un[i].x = out[2 * i]; k_un[i].y = out[2 * i + 1]; }
+}
+
+// Frame::ComputeImageBounds (src/Frame.cc:743-779).
+void om_compute_image_bounds(int cols, int rows, float fx, float fy, float cx, float cy, const float* dist5, om_bounds* b) {
+  if (dist5[0] != 0.0) {
+    const float mat[8] = {0.f, 0.f, (float)cols, 0.f, 0.f, (float)rows, (float)cols, (float)rows};
+    float o[8];
+    cvp::undistort_points(mat, 4, fx, fy, cx, cy, dist5, o);
+    b->min_x = std::min(o[0], o[4]);
+    b->max_x = std::max(o[2], o[6]);
+    b->min_y = std::min(o[1], o[3]);
+    b->max_y = std::max(o[5], o[7]);
+  } else {
+    b->min_x = 0.0f;
+    b->max_x = (float)cols;
+    b->min_y = 0.0f;
+    b->max_y = (float)rows;
+  }
+}
+
+// Frame::ComputeStereoFromRGBD (src/Frame.cc:959-985; _cam2 :987-1010): depth is the CV_32F depth image
+// (already scaled by mDepthMapFactor), indexed by the DISTORTED keypoint truncated to int.
+void om_compute_stereo_from_rgbd(const oo_keypoint* k, const oo_keypoint* k_un, int n, const float* depth, int cols,
+                                 int rows, size_t stride_floats, float mbf, float* uright, float* depth_out) {
+  (void)cols; (void)rows;
+  for (int i = 0; i < n; ++i) {
+    uright[i] = -1;
+    depth_out[i] = -1;
+    const float v = k[i].y, u = k[i].x;
+    const float d = depth[(size_t)(int)v * stride_floats + (int)u];
+    if (d > 0) {
+      depth_out[i] = d;
+      uright[i] = k_un[i].x - mbf / d;
+    }
+  }
+}
+
+// Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:348-395, 632-642): CSR over cell = ix*48 + iy,
+// items in insertion (keypoint index) order.  cell_start has 64*48 + 1 entries.
+void om_assign_features_to_grid(const oo_keypoint* k_un, int n, om_bounds b, int32_t* cell_start, int32_t* items) {
+  std::vector<float> x(n), y(n);
+  std::vector<int> oct(n, 0);
+  for (int i = 0; i < n; ++i) { x[i] = k_un[i].x; y[i] = k_un[i].y; }
+  Grid g(x.data(), y.data(), oct.data(), n, b);
+  int run = 0;
+  for (int ix = 0; ix < GRID_COLS; ++ix)
+    for (int iy = 0; iy < GRID_ROWS; ++iy) {
+      cell_start[ix * GRID_ROWS + iy] = run;
+      for (int idx : g.cell[ix][iy]) items[run++] = idx;
+    }
+  cell_start[GRID_COLS * GRID_ROWS] = run;
 }
 
 // ORBmatcher::SearchByBoW — the four variants share one loop:

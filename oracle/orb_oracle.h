@@ -144,6 +144,16 @@ int om_search_by_projection_sim3(const oo_keypoint* kf_k, const uint8_t* kf_desc
                                  const float* mp_min_dist, const float* mp_max_d, const uint8_t* mp_desc, int n_mp,
                                  int th, int32_t* matched);
 
+// Frame glue (src/Frame.cc): UndistortKeyPoints :673-706, ComputeImageBounds :743-779,
+// ComputeStereoFromRGBD :959-985, AssignFeaturesToGrid :348-395.  dist5 = mDistCoef (k1, k2, p1, p2, k3).
+void om_undistort_keypoints(const oo_keypoint* k, int n, float fx, float fy, float cx, float cy, const float* dist5,
+                            oo_keypoint* k_un);
+void om_compute_image_bounds(int cols, int rows, float fx, float fy, float cx, float cy, const float* dist5, om_bounds* b);
+void om_compute_stereo_from_rgbd(const oo_keypoint* k, const oo_keypoint* k_un, int n, const float* depth, int cols,
+                                 int rows, size_t stride_floats, float mbf, float* uright, float* depth_out);
+// CSR over cell = ix*48 + iy (cell_start: 64*48 + 1 entries), items in insertion order.
+void om_assign_features_to_grid(const oo_keypoint* k_un, int n, om_bounds b, int32_t* cell_start, int32_t* items);
+
 // ORBmatcher::SearchByBoW / SearchByBoW_cam1, Frame and KeyFrame variants (src/ORBmatcher.cc:206-388,
 // 390-565, 996-1163, 1180-1363).  Side 1 = the key frame whose map points are searched, side 2 = the
 // frame / second key frame.  Feature vectors are DBoW2::FeatureVector flattened to CSR: node ids

@@ -286,6 +286,57 @@ def search_by_projection_sim3(kf_k, kf_desc, kf_cam, bounds, sf, log_sf, cam, Sc
     return nm, out
 
 
+def undistort_points(pts, fx, fy, cx, cy, dist5):
+    lib = load("port")
+    p = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 2)
+    d = np.ascontiguousarray(dist5, dtype=np.float32)
+    out = np.empty_like(p)
+    lib.cvp_undistort_points.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    lib.cvp_undistort_points(p.ctypes.data, len(p), fx, fy, cx, cy, d.ctypes.data, out.ctypes.data)
+    return out
+
+
+def undistort_keypoints(k, fx, fy, cx, cy, dist5):
+    lib = load("port")
+    k = np.ascontiguousarray(k, dtype=KP_DTYPE)
+    d = np.ascontiguousarray(dist5, dtype=np.float32)
+    out = np.empty_like(k)
+    lib.om_undistort_keypoints.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    lib.om_undistort_keypoints(k.ctypes.data, len(k), fx, fy, cx, cy, d.ctypes.data, out.ctypes.data)
+    return out
+
+
+def compute_image_bounds(cols, rows, fx, fy, cx, cy, dist5):
+    lib = load("port")
+    d = np.ascontiguousarray(dist5, dtype=np.float32)
+    b = Bounds()
+    lib.om_compute_image_bounds.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                            C.POINTER(Bounds)]
+    lib.om_compute_image_bounds(cols, rows, fx, fy, cx, cy, d.ctypes.data, C.byref(b))
+    return (b.min_x, b.max_x, b.min_y, b.max_y)
+
+
+def compute_stereo_from_rgbd(k, k_un, depth, mbf):
+    lib = load("port")
+    k, k_un = np.ascontiguousarray(k, dtype=KP_DTYPE), np.ascontiguousarray(k_un, dtype=KP_DTYPE)
+    depth = np.ascontiguousarray(depth, dtype=np.float32)
+    ur, dz = np.empty(len(k), np.float32), np.empty(len(k), np.float32)
+    lib.om_compute_stereo_from_rgbd.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t,
+                                                C.c_float, C.c_void_p, C.c_void_p]
+    lib.om_compute_stereo_from_rgbd(k.ctypes.data, k_un.ctypes.data, len(k), depth.ctypes.data, depth.shape[1], depth.shape[0],
+                                    depth.shape[1], mbf, ur.ctypes.data, dz.ctypes.data)
+    return ur, dz
+
+
+def assign_features_to_grid(k_un, bounds):
+    lib = load("port")
+    k_un = np.ascontiguousarray(k_un, dtype=KP_DTYPE)
+    start, items = np.zeros(64 * 48 + 1, np.int32), np.zeros(max(len(k_un), 1), np.int32)
+    lib.om_assign_features_to_grid.argtypes = [C.c_void_p, C.c_int, Bounds, C.c_void_p, C.c_void_p]
+    lib.om_assign_features_to_grid(k_un.ctypes.data, len(k_un), Bounds(*bounds), start.ctypes.data, items.ctypes.data)
+    return start, items[: start[-1]]
+
+
 def search_by_bow(d1, angle1, valid1, fv1, d2, angle2, valid2, fv2, nnratio=0.7, check_ori=True, max_dist=50):
     """fv = (node_ids, start, items) CSR feature vector.  Returns (nmatches, matches12, matches21)."""
     lib = load("port")

@@ -100,3 +100,18 @@ def test_fast_atan2(lib):
     got = np.zeros_like(x)
     lib.cvp_atan2(C.c_void_p(y.ctypes.data), C.c_void_p(x.ctypes.data), C.c_void_p(got.ctypes.data), len(x))
     assert np.array_equal(got, want)
+
+
+def test_undistort_points(oracle_port):
+    """cv::undistortPoints(src, dst, K, dist, Mat(), K) (Frame::UndistortKeyPoints, src/Frame.cc:692)."""
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        fx, fy, cx, cy = (np.float32(v) for v in (rng.uniform(300, 900), rng.uniform(300, 900), rng.uniform(250, 700),
+                                                  rng.uniform(180, 400)))
+        dist = np.array([rng.uniform(-0.4, 0.4), rng.uniform(-0.3, 0.3), rng.uniform(-0.01, 0.01), rng.uniform(-0.01, 0.01),
+                         rng.uniform(-0.2, 0.2) if trial % 2 else 0], dtype=np.float32)
+        pts = np.stack([rng.uniform(-50, 1330, 300), rng.uniform(-50, 770, 300)], axis=1).astype(np.float32)
+        K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], dtype=np.float32)
+        want = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, dist if trial % 2 else dist[:4], None, K).reshape(-1, 2)
+        got = oracle_port.undistort_points(pts, fx, fy, cx, cy, dist)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"trial {trial}"

@@ -96,3 +96,16 @@ def test_known_constants(oracle_port):
     port.extract(textured(640, 480, 0))
     sizes = [(port.pyramid_level(l).shape[1] - 38, port.pyramid_level(l).shape[0] - 38) for l in range(8)]
     assert sizes == [(640, 480), (533, 400), (444, 333), (370, 278), (309, 231), (257, 193), (214, 161), (179, 134)]
+
+
+def test_undistort_points_golden(oracle_port):
+    """cv::undistortPoints as Frame::UndistortKeyPoints calls it (tools/make_golden_undistort.py)."""
+    g = np.load(os.path.join(GOLD, "cv2_undistort.npz"))
+    for i, c in enumerate(g["cams"]):
+        got = oracle_port.undistort_points(g[f"pts_{i}"], c[0], c[1], c[2], c[3], c[4:9])
+        assert np.array_equal(got.view(np.uint32), g[f"und_{i}"].view(np.uint32)), f"camera model {i}"
+        # ComputeImageBounds from the four corners (src/Frame.cc:766-769)
+        w, h = g[f"size_{i}"]
+        u = g[f"und_{i}"][:4]
+        want = (min(u[0, 0], u[2, 0]), max(u[1, 0], u[3, 0]), min(u[0, 1], u[1, 1]), max(u[2, 1], u[3, 1]))
+        assert oracle_port.compute_image_bounds(int(w), int(h), c[0], c[1], c[2], c[3], c[4:9]) == tuple(float(v) for v in want)

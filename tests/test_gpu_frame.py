@@ -1,0 +1,85 @@
+"""GPU parity tests of the Frame glue kernels (multi_orb_slam_b200/frame.py over the C-ABI) against the
+oracle restatements of src/Frame.cc: UndistortKeyPoints (bit-exact with cv2 4.13 via the committed golden
+vectors), ComputeImageBounds, ComputeStereoFromRGBD, AssignFeaturesToGrid — device-resident batches in the
+extractor's output layout."""
+import os
+
+import numpy as np
+import pytest
+
+from multi_orb_slam_b200.synth import KP_DTYPE, camera_sequence
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TUM1 = (517.306408, 516.469215, 318.643040, 255.313989)
+TUM1_DIST = (0.262383, -0.953104, -0.005358, 0.002628, 1.163314)
+
+
+def test_undistort_matches_cv2_golden():
+    from multi_orb_slam_b200.frame import FrameGlue
+    g = np.load(os.path.join(GOLD, "cv2_undistort.npz"))
+    for i, c in enumerate(g["cams"]):
+        glue = FrameGlue(c[0], c[1], c[2], c[3], c[4:9])
+        k = np.zeros(len(g[f"pts_{i}"]), KP_DTYPE)
+        k["x"], k["y"] = g[f"pts_{i}"][:, 0], g[f"pts_{i}"][:, 1]
+        k["angle"], k["octave"] = 12.5, 3
+        un = glue.UndistortKeyPoints(k)
+        want = g[f"und_{i}"]
+        assert np.array_equal(un["x"].view(np.uint32), want[:, 0].view(np.uint32)), f"camera {i}: x"
+        assert np.array_equal(un["y"].view(np.uint32), want[:, 1].view(np.uint32)), f"camera {i}: y"
+        assert (un["angle"] == 12.5).all() and (un["octave"] == 3).all()
+        w, h = g[f"size_{i}"]
+        b = glue.ComputeImageBounds(int(w), int(h))
+        u = want[:4]
+        assert (b.min_x, b.max_x, b.min_y, b.max_y) == (min(u[0, 0], u[2, 0]), max(u[1, 0], u[3, 0]), min(u[0, 1], u[1, 1]),
+                                                        max(u[2, 1], u[3, 1]))
+
+
+def test_no_distortion_is_identity(oracle_port):
+    from multi_orb_slam_b200.frame import FrameGlue
+    glue = FrameGlue(500, 500, 320, 240, (0, 0.2, 0.1, 0.1))  # k1 == 0 (:675-679, :772-778)
+    k = np.zeros(10, KP_DTYPE)
+    k["x"], k["y"] = np.arange(10) * 60.5, np.arange(10) * 40.25
+    assert glue.UndistortKeyPoints(k).tobytes() == k.tobytes()
+    b = glue.ComputeImageBounds(640, 480)
+    assert (b.min_x, b.max_x, b.min_y, b.max_y) == (0.0, 640.0, 0.0, 480.0)
+
+
+def test_extract_undistort_stereo_grid_on_device(oracle_port):
+    """extractor -> UndistortKeyPoints -> ComputeStereoFromRGBD -> AssignFeaturesToGrid without leaving the GPU."""
+    import torch
+    from multi_orb_slam_b200.extractor import ORBextractor
+    from multi_orb_slam_b200.frame import FrameGlue
+    O = oracle_port
+    F, W, H = 5, 640, 480
+    imgs = camera_sequence(W, H, F, 77)
+    ex = ORBextractor(1000, 1.2, 8, 20, 7, image_size=(W, H), max_batch=F)
+    kps, desc, counts = ex.extract_batch_device(torch.from_numpy(imgs).cuda())
+    ex.sync()
+    glue = FrameGlue(*TUM1, TUM1_DIST, mbf=40.0)
+    rng = np.random.default_rng(8)
+    depth = np.where(rng.random((F, H, W)) < 0.75, rng.uniform(0.3, 9, (F, H, W)), 0).astype(np.float32)
+    d_depth = torch.from_numpy(depth).cuda()
+    kps_un = glue.undistort_batch_device(kps, counts)
+    uright, dz = glue.stereo_from_rgbd_batch_device(kps, kps_un, counts, d_depth)
+    bounds = glue.ComputeImageBounds(W, H)
+    cell_start, items = glue.assign_features_to_grid_batch_device(kps_un, counts, bounds)
+    glue.sync()
+    n = counts.cpu().numpy()
+    h_k, h_un = kps.cpu().numpy(), kps_un.cpu().numpy()
+    h_ur, h_dz = uright.cpu().numpy(), dz.cpu().numpy()
+    h_start, h_items = cell_start.cpu().numpy(), items.cpu().numpy().view(np.uint16)
+    ob = O.compute_image_bounds(W, H, *TUM1, TUM1_DIST)
+    assert (bounds.min_x, bounds.max_x, bounds.min_y, bounds.max_y) == ob
+    for f in range(F):
+        k = np.ascontiguousarray(h_k[f, : n[f]]).view(KP_DTYPE).reshape(-1)
+        un = np.ascontiguousarray(h_un[f, : n[f]]).view(KP_DTYPE).reshape(-1)
+        ref_un = O.undistort_keypoints(k, *TUM1, TUM1_DIST)
+        assert un.tobytes() == ref_un.tobytes(), f"frame {f}: undistorted keypoints"
+        r_ur, r_dz = O.compute_stereo_from_rgbd(k, ref_un, depth[f], 40.0)
+        assert np.array_equal(h_ur[f, : n[f]], r_ur) and np.array_equal(h_dz[f, : n[f]], r_dz), f"frame {f}: stereo"
+        assert (h_ur[f, n[f]:] == -1).all() and (h_dz[f, n[f]:] == -1).all()
+        r_start, r_items = O.assign_features_to_grid(ref_un, ob)
+        assert np.array_equal(h_start[f], r_start), f"frame {f}: grid cell starts"
+        assert np.array_equal(h_items[f, : r_start[-1]].astype(np.int32), r_items), f"frame {f}: grid items"
+    assert (h_dz > 0).sum() > 1000
