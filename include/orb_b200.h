@@ -282,6 +282,14 @@ int orbm_assign_features_to_grid_device(orbm_matcher* m, int n_frames, int cap, 
                                         const int32_t* d_counts, orbm_bounds bounds, int32_t* d_cell_start,
                                         uint16_t* d_items);
 
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:325-438), the arithmetic part (:381-424), batched over
+ * map points: the observed descriptors of point p (vDescriptors, in std::map<KeyFrame*,size_t> iteration order, bad
+ * key frames left out) are rows offsets[p] .. offsets[p+1]-1 of desc (offsets[0] = 0).  best_idx[p] = BestIdx relative
+ * to offsets[p]: the first descriptor whose median distance to the set (element int(0.5*(N-1)) of the sorted row,
+ * self-distance included) is least; -1 for an empty set.  mDescriptor = vDescriptors[BestIdx]. */
+int orbm_compute_distinctive_descriptors_host(orbm_matcher* m, const uint8_t* desc, const int32_t* offsets, int n_points,
+                                              int32_t* best_idx);
+
 /* DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned int>>, Thirdparty/DBoW2/DBoW2/FeatureVector.h)
  * flattened to CSR: node ids ascending (the map's order), start[n_nodes + 1], items = feature indices in
  * vector order.  A feature index occurs at most once per vector (DBoW2 guarantees it). */

@@ -560,6 +560,73 @@ __global__ void __launch_bounds__(INIT_NT) k_init_resolve(int cap, const orbx_ke
   if (tid == 0) nmatches_out[pair] = s_nmatch;
 }
 
+// ---- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:381-424) ------------------------
+// One CTA per map point: the N x N distance matrix (u16) in shared memory (N <= DD_SMEM_N) or in a
+// global scratch block; a warp per row finds the row median (element int(0.5*(N-1)) of the sorted row)
+// from a 257-bin histogram of the row; the first row with the least median wins (:414-420).
+#define DD_SMEM_N 160
+__global__ void __launch_bounds__(128) k_distinctive(const uint8_t* __restrict__ desc, const int32_t* __restrict__ offsets,
+                                                     uint16_t* __restrict__ big, const int* __restrict__ big_off,
+                                                     int32_t* __restrict__ best_idx) {
+  extern __shared__ uint16_t s_dd[];  // [N*N] if N <= DD_SMEM_N
+  __shared__ int s_hist[4][264];
+  __shared__ unsigned s_best;
+  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int o = offsets[p], N = offsets[p + 1] - o;
+  if (N <= 0) {
+    if (tid == 0) best_idx[p] = -1;
+    return;
+  }
+  uint16_t* D = N <= DD_SMEM_N ? s_dd : big + big_off[p];
+  if (tid == 0) s_best = 0xFFFFFFFFu;
+  const uint8_t* d = desc + (size_t)o * 32;
+  for (int e = tid; e < N * N; e += 128) {
+    const int i = e / N, j = e - i * N;
+    if (j < i) continue;
+    int dist = 0;
+    if (j > i) {
+      const uint4* a = reinterpret_cast<const uint4*>(d + (size_t)i * 32);
+      const uint4* b = reinterpret_cast<const uint4*>(d + (size_t)j * 32);
+      dist = hamming256(__ldg(a), __ldg(a + 1), __ldg(b), __ldg(b + 1));
+    }
+    D[i * N + j] = (uint16_t)dist;
+    D[j * N + i] = (uint16_t)dist;
+  }
+  __syncthreads();
+  const int kth = (int)(0.5 * (N - 1));
+  int* hist = s_hist[warp];
+  for (int i = warp; i < N; i += 4) {
+    for (int b = lane; b < 264; b += 32) hist[b] = 0;
+    __syncwarp();
+    for (int j = lane; j < N; j += 32) atomicAdd(&hist[D[i * N + j]], 1);
+    __syncwarp();
+    // smallest value v with #(row <= v) > kth: each lane owns 9 consecutive bins (257 = 28*9 + 5)
+    int cnt = 0;
+#pragma unroll
+    for (int b = 0; b < 9; ++b) cnt += lane * 9 + b < 257 ? hist[lane * 9 + b] : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, s);
+      if (lane >= s) incl += t;
+    }
+    const unsigned owner = __ballot_sync(0xffffffffu, incl > kth);
+    const int ol = __ffs(owner) - 1;
+    int median = 0;
+    if (lane == ol) {
+      int run = incl - cnt;
+      for (int b = 0; b < 9; ++b) {
+        run += hist[lane * 9 + b];
+        if (run > kth) { median = lane * 9 + b; break; }
+      }
+      atomicMin(&s_best, (unsigned)median << 16 | (unsigned)i);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (tid == 0) best_idx[p] = (int)(s_best & 0xFFFFu);
+}
+
 // ---- Frame glue between extractor and matchers (src/Frame.cc) ---------------------------------
 // Frame::UndistortKeyPoints (:673-706): cv::undistortPoints(mat, mat, mK, mDistCoef, Mat(), mK) with the
 // default criteria = five fixed-point iterations of OpenCV 4.x cvUndistortPointsInternal, all in double
@@ -1577,6 +1644,46 @@ int orbm_search_for_triangulation_host(orbm_matcher* m, const orbx_keypoint* k1,
   cudaMemcpyAsync(nmatches, dnm, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (!m->check(cudaStreamSynchronize(st), "search_for_triangulation")) return ORBX_E_CUDA;
   return m->check(cudaGetLastError(), "search_for_triangulation launch") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+int orbm_compute_distinctive_descriptors_host(orbm_matcher* m, const uint8_t* desc, const int32_t* offsets, int n_points,
+                                              int32_t* best_idx) {
+  if (!m || n_points < 0 || (n_points && (!offsets || !best_idx))) return ORBX_E_INVALID;
+  if (n_points == 0) return ORBX_OK;
+  const int total = offsets[n_points];
+  if (offsets[0] != 0 || total < 0 || (total && !desc)) return ORBX_E_INVALID;
+  int n_max = 0;
+  size_t big_total = 0;
+  std::vector<int> big_off(n_points, 0);
+  for (int p = 0; p < n_points; ++p) {
+    const int N = offsets[p + 1] - offsets[p];
+    if (N < 0 || N > 65535) { m->err = "descriptor set size out of range"; return ORBX_E_INVALID; }
+    if (N > DD_SMEM_N) { big_off[p] = (int)big_total; big_total += (size_t)N * N; }
+    if (big_total > 0x7FFFFFFFu) { m->err = "descriptor sets too large"; return ORBX_E_CAPACITY; }
+    n_max = std::max(n_max, std::min(N, DD_SMEM_N));
+  }
+  cudaSetDevice(m->device);
+  cudaStream_t st = m->stream;
+  uint8_t* dd = m->scratch<uint8_t>(8, (size_t)std::max(total, 1) * 32);
+  int32_t* dints = m->scratch<int32_t>(4, (size_t)3 * n_points + 2);
+  uint16_t* dbig = m->scratch<uint16_t>(6, big_total);
+  if (!dd || !dints || !dbig) return ORBX_E_CUDA;
+  int32_t* doff = dints;
+  int32_t* dbigoff = doff + n_points + 1;
+  int32_t* dbest = dbigoff + n_points;
+  cudaMemcpyAsync(dd, desc, (size_t)total * 32, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(doff, offsets, sizeof(int32_t) * (n_points + 1), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dbigoff, big_off.data(), sizeof(int32_t) * n_points, cudaMemcpyHostToDevice, st);
+  const size_t smem = (size_t)n_max * n_max * sizeof(uint16_t);
+  if (smem > 40 * 1024 &&
+      !m->check(cudaFuncSetAttribute(k_distinctive, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     DD_SMEM_N * DD_SMEM_N * (int)sizeof(uint16_t)), "smem opt-in"))
+    return ORBX_E_CUDA;
+  k_distinctive<<<n_points, 128, smem, st>>>(dd, doff, dbig, dbigoff, dbest);
+  m->launches += 1;
+  cudaMemcpyAsync(best_idx, dbest, sizeof(int32_t) * n_points, cudaMemcpyDeviceToHost, st);
+  if (!m->check(cudaStreamSynchronize(st), "compute_distinctive_descriptors")) return ORBX_E_CUDA;
+  return m->check(cudaGetLastError(), "compute_distinctive_descriptors launch") ? ORBX_OK : ORBX_E_CUDA;
 }
 
 // ---- Frame glue -------------------------------------------------------------------------------

@@ -325,3 +325,17 @@ class ORBmatcher:
             int(bOnlyStereo), p(en), int(self.mbCheckOrientation), p(m12), C.byref(nm)))
         idx = np.nonzero(m12 >= 0)[0]
         return nm.value, m12, np.stack([idx, m12[idx]], axis=1)
+
+
+    # -- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:325-438) --------------------------------------
+    def ComputeDistinctiveDescriptors(self, desc, offsets):
+        """Batched over map points: rows offsets[p]:offsets[p+1] of desc are the observed descriptors of
+        point p.  Returns best_idx [P] (relative to offsets[p]; -1 for an empty set)."""
+        d = np.ascontiguousarray(desc, dtype=np.uint8).reshape(-1, 32)
+        off = np.ascontiguousarray(offsets, dtype=np.int32)
+        if len(off) < 1 or off[0] != 0 or off[-1] != len(d) or (np.diff(off) < 0).any():
+            raise ValueError("offsets must start at 0, be non-decreasing and end at the descriptor count")
+        best = np.empty(len(off) - 1, dtype=np.int32)
+        check_m(self._h, lib.orbm_compute_distinctive_descriptors_host(self._h, d.ctypes.data, off.ctypes.data, len(off) - 1,
+                                                                       best.ctypes.data))
+        return best

@@ -190,6 +190,30 @@ int om_search_for_initialization(const oo_keypoint* k1, const uint8_t* d1, int n
   return nmatches;
 }
 
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:325-438), the arithmetic part (:381-424): for one
+// map point's observed descriptors, all pair distances, the median of every row (element int(0.5*(N-1)) of the
+// sorted row, the zero self-distance included) and the first row with the least median.  Batched over points:
+// the descriptors of point p are rows offsets[p] .. offsets[p+1]-1; best_idx[p] is relative to offsets[p],
+// -1 for an empty set (:369-370 returns early).
+void om_compute_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int n_points, int32_t* best_idx) {
+  std::vector<int> row;
+  for (int p = 0; p < n_points; ++p) {
+    const int N = offsets[p + 1] - offsets[p];
+    best_idx[p] = -1;
+    if (N <= 0) continue;
+    const uint8_t* d = desc + (size_t)offsets[p] * 32;
+    int BestMedian = INT_MAX, BestIdx = 0;
+    for (int i = 0; i < N; ++i) {
+      row.assign(N, 0);
+      for (int j = 0; j < N; ++j) row[j] = i == j ? 0 : om_distance(d + (size_t)i * 32, d + (size_t)j * 32);
+      std::sort(row.begin(), row.end());
+      const int median = row[(size_t)(0.5 * (N - 1))];
+      if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+    }
+    best_idx[p] = BestIdx;
+  }
+}
+
 // ---- Frame glue between the extractor and the matchers (src/Frame.cc) -----------------------
 // Frame::UndistortKeyPoints (src/Frame.cc:673-706; _cam2 :708-741 is the same on camera 2's arrays).
 void om_undistort_keypoints(const oo_keypoint* k, int n, float fx, float fy, float cx, float cy, const float* dist5,

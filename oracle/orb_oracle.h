@@ -144,6 +144,10 @@ int om_search_by_projection_sim3(const oo_keypoint* kf_k, const uint8_t* kf_desc
                                  const float* mp_min_dist, const float* mp_max_d, const uint8_t* mp_desc, int n_mp,
                                  int th, int32_t* matched);
 
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:381-424), batched: descriptors of point p are rows
+// offsets[p] .. offsets[p+1]-1 of desc; best_idx[p] = chosen row relative to offsets[p] (-1 for an empty set).
+void om_compute_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int n_points, int32_t* best_idx);
+
 // Frame glue (src/Frame.cc): UndistortKeyPoints :673-706, ComputeImageBounds :743-779,
 // ComputeStereoFromRGBD :959-985, AssignFeaturesToGrid :348-395.  dist5 = mDistCoef (k1, k2, p1, p2, k3).
 void om_undistort_keypoints(const oo_keypoint* k, int n, float fx, float fy, float cx, float cy, const float* dist5,

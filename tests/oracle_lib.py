@@ -286,6 +286,16 @@ def search_by_projection_sim3(kf_k, kf_desc, kf_cam, bounds, sf, log_sf, cam, Sc
     return nm, out
 
 
+def compute_distinctive_descriptors(desc, offsets):
+    lib = load("port")
+    d = np.ascontiguousarray(desc, dtype=np.uint8).reshape(-1, 32)
+    off = np.ascontiguousarray(offsets, dtype=np.int32)
+    best = np.empty(len(off) - 1, dtype=np.int32)
+    lib.om_compute_distinctive_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.om_compute_distinctive_descriptors(d.ctypes.data, off.ctypes.data, len(off) - 1, best.ctypes.data)
+    return best
+
+
 def undistort_points(pts, fx, fy, cx, cy, dist5):
     lib = load("port")
     p = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 2)

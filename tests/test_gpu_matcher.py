@@ -432,3 +432,18 @@ def test_search_for_triangulation_degenerate(O):
     # zero fundamental matrix: den == 0 -> CheckDistEpipolarLine is false for every pair (:178-179)
     nm, m12, _ = m.SearchForTriangulation(*args(feature_vector(sc["node2"]), np.zeros((2, 3, 3), np.float32)))
     assert nm == 0 and (m12 == -1).all()
+
+
+# ---- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:381-424) --------------------------
+def test_compute_distinctive_descriptors_vs_oracle(M, O):
+    from test_matcher_oracle import _distinctive_sets
+    rng = np.random.default_rng(4)
+    sizes = [1, 2, 0, 3, 160, 161, 400, 33] + [int(v) for v in rng.integers(1, 60, 3000)]
+    desc, off = _distinctive_sets(1, sizes)
+    got = M.ComputeDistinctiveDescriptors(desc, off)
+    ref = O.compute_distinctive_descriptors(desc, off)
+    assert np.array_equal(got, ref)
+    assert got[2] == -1 and (got[np.array(sizes) > 0] >= 0).all()
+    # all-identical set: every median is 0, the first descriptor wins
+    same = np.repeat(random_descriptors(1, 3), 9, axis=0)
+    assert M.ComputeDistinctiveDescriptors(same, [0, 9])[0] == 0

@@ -358,3 +358,31 @@ def test_search_for_triangulation_vs_python(O, seed, n_nodes, only_stereo, cam_e
     assert rn == int((rm12 >= 0).sum())
     if not only_stereo:
         assert rn > 10
+
+
+# ---- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:381-424) --------------------------
+def _distinctive_sets(seed, sizes):
+    from multi_orb_slam_b200.synth import perturbed_descriptors
+    rng = np.random.default_rng(seed)
+    blocks = []
+    for n in sizes:
+        base = random_descriptors(1, int(rng.integers(1 << 30)))
+        if n:
+            rows, _ = perturbed_descriptors(np.repeat(base, n, axis=0), int(rng.integers(1 << 30)), max_flips=60, permute=False)
+            blocks.append(rows)
+    desc = np.concatenate(blocks) if blocks else np.zeros((0, 32), np.uint8)
+    return desc, np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+
+
+def test_compute_distinctive_descriptors_vs_numpy(O):
+    sizes = [1, 2, 3, 0, 7, 20, 33, 64, 5, 2, 100]
+    desc, off = _distinctive_sets(0, sizes)
+    got = O.compute_distinctive_descriptors(desc, off)
+    for p, n in enumerate(sizes):
+        if n == 0:
+            assert got[p] == -1
+            continue
+        d = desc[off[p]:off[p + 1]]
+        D = np.unpackbits(d[:, None, :] ^ d[None, :, :], axis=2).sum(axis=2)
+        med = np.sort(D, axis=1)[:, int(0.5 * (n - 1))]
+        assert got[p] == int(np.argmin(med)), f"point {p} (N={n})"  # argmin = first minimum (:414-420)
