@@ -153,6 +153,87 @@ def cpu_reference_run(cams, n_rig, threads):
     return 2 * n_rig / dt, dt, kind
 
 
+def widened_rows_leg(matcher, device, with_cpu):
+    """The "next" rows of SURVEY.md 8(f) that are built: one representative call each through the C-ABI
+    (host arrays in, host arrays out, copies included), with the CPU restatement of the same call timed
+    beside it on one core.  Small, latency-bound calls: reported for completeness, not part of `value`."""
+    from multi_orb_slam_b200.frame import FrameGlue
+    from multi_orb_slam_b200.synth import KP_DTYPE, bow_scene, feature_vector, triangulation_scene
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        oracle_lib.build_oracle()
+
+    def best_ms(fn, n=5):
+        fn()
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            fn()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        return float(min(ts))
+
+    out = {}
+    sc = bow_scene(2000, 2000, 100, 31)
+    fv1, fv2 = feature_vector(sc["node1"]), feature_vector(sc["node2"])
+    row = {"workload": "SearchByBoW, 2000 x 2000 features, 100 vocabulary nodes",
+           "gpu_ms": best_ms(lambda: matcher.SearchByBoW(sc["d1"], sc["a1"], None, fv1, sc["d2"], sc["a2"], None, fv2))}
+    if with_cpu:
+        row["cpu_ms"] = best_ms(lambda: oracle_lib.search_by_bow(sc["d1"], sc["a1"], None, fv1, sc["d2"], sc["a2"], None, fv2,
+                                                                  matcher.mfNNratio, True, 50), 3)
+    out["search_by_bow"] = row
+    bow_pairs = []
+    for i in range(32):  # e.g. the candidate key frames of one relocalisation / loop detection
+        b = bow_scene(2000, 2000, 100, 100 + i)
+        bow_pairs.append((b["d1"], b["a1"], None, feature_vector(b["node1"]), b["d2"], b["a2"], None, feature_vector(b["node2"])))
+    row = {"workload": "SearchByBoW, batch of 32 pairs of 2000 x 2000 features in one call",
+           "gpu_ms": best_ms(lambda: matcher.SearchByBoW_batch(bow_pairs))}
+    if with_cpu:
+        row["cpu_ms"] = best_ms(lambda: [oracle_lib.search_by_bow(*bp, matcher.mfNNratio, True, 50) for bp in bow_pairs], 2)
+    out["search_by_bow_batch32"] = row
+    tr = triangulation_scene(2000, 2000, 100, 32)
+    tf1, tf2 = feature_vector(tr["node1"]), feature_vector(tr["node2"])
+    row = {"workload": "SearchForTriangulation, 2000 x 2000 features, 100 vocabulary nodes, two cameras",
+           "gpu_ms": best_ms(lambda: matcher.SearchForTriangulation(
+               tr["k1"], tr["d1"], tr["has_mp1"], tr["cam1"], tr["uright1"], tf1, tr["k2"], tr["d2"], tr["has_mp2"], tr["cam2"],
+               tr["uright2"], tf2, tr["F12s"], tr["epipoles"], tr["scale_factors"], tr["level_sigma2"]))}
+    if with_cpu:
+        row["cpu_ms"] = best_ms(lambda: oracle_lib.search_for_triangulation(tr, tf1, tf2), 3)
+    out["search_for_triangulation"] = row
+    tri_scenes = []
+    for i in range(20):  # the neighbours of one new key frame (src/LocalMapping.cc:300)
+        t = triangulation_scene(2000, 2000, 100, 200 + i)
+        t["fv1"], t["fv2"] = feature_vector(t["node1"]), feature_vector(t["node2"])
+        tri_scenes.append(t)
+    row = {"workload": "SearchForTriangulation, batch of 20 key-frame pairs of 2000 x 2000 features in one call",
+           "gpu_ms": best_ms(lambda: matcher.SearchForTriangulation_batch(tri_scenes))}
+    if with_cpu:
+        row["cpu_ms"] = best_ms(lambda: [oracle_lib.search_for_triangulation(t, t["fv1"], t["fv2"]) for t in tri_scenes], 2)
+    out["search_for_triangulation_batch20"] = row
+    rng = np.random.default_rng(33)
+    sizes = rng.integers(2, 40, 20000)
+    desc = rng.integers(0, 256, size=(int(sizes.sum()), 32), dtype=np.uint8)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    row = {"workload": "ComputeDistinctiveDescriptors, 20000 map points x 2..39 observations",
+           "gpu_ms": best_ms(lambda: matcher.ComputeDistinctiveDescriptors(desc, off))}
+    if with_cpu:
+        row["cpu_ms"] = best_ms(lambda: oracle_lib.compute_distinctive_descriptors(desc, off), 2)
+    out["compute_distinctive_descriptors"] = row
+    glue = FrameGlue(517.306408, 516.469215, 318.643040, 255.313989, (0.262383, -0.953104, -0.005358, 0.002628, 1.163314),
+                     device=device)
+    k = np.zeros(100000, KP_DTYPE)
+    k["x"], k["y"] = rng.uniform(0, 640, len(k)), rng.uniform(0, 480, len(k))
+    row = {"workload": "UndistortKeyPoints (cv::undistortPoints), 100000 keypoints",
+           "gpu_ms": best_ms(lambda: glue.UndistortKeyPoints(k))}
+    if with_cpu:
+        row["cpu_ms"] = best_ms(lambda: oracle_lib.undistort_keypoints(k, glue.fx, glue.fy, glue.cx, glue.cy, glue.dist), 3)
+    out["undistort_keypoints"] = row
+    for r in out.values():
+        if "cpu_ms" in r:
+            r["cpu_cores"] = 1
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -372,6 +453,8 @@ def main():
     bf_pairs = float(nbf) * nbf * world / (bf_ms * 1e-3)
     bf_accepted = int((bf_idx >= 0).sum().item())
 
+    widened = widened_rows_leg(matcher, local_rank, not args.no_cpu_baseline) if rank == 0 else None
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -433,6 +516,7 @@ def main():
                        "roofline": {"bound": "popc", "achieved": bf_pairs, "peak": popc_peak * world,
                                     "unit": "pairs/s", "frac": bf_pairs / (popc_peak * world),
                                     "peak_source": f"148 SM x 16 POPC/clk x {sm_max:.0f} MHz / 8 words"}}
+    out["widened_rows"] = widened
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         n_rig = min(args.cpu_rig_frames, F)

@@ -317,6 +317,19 @@ int orbm_search_by_bow_host(orbm_matcher* m, const uint8_t* desc1, const float* 
                             orbm_featvec fv2, float nnratio, int check_ori, int max_dist, int32_t* matches12,
                             int32_t* matches21, int* nmatches);
 
+/* The same for a batch of independent pairs in one call (e.g. the relocalisation candidates of
+ * Tracking::Relocalization, src/Tracking.cc:2010-2040, or the loop candidates of LoopClosing::ComputeSim3,
+ * src/LoopClosing.cc:310-340, each against its own partner): the ordered part of the search runs
+ * concurrently, one CTA per pair.  Fields as the arguments above; nmatches is written per pair. */
+typedef struct {
+  const uint8_t* desc1; const float* angle1; const int32_t* valid1; int32_t n1; orbm_featvec fv1;
+  const uint8_t* desc2; const float* angle2; const int32_t* valid2; int32_t n2; orbm_featvec fv2;
+  int32_t* matches12; int32_t* matches21; /* out (matches21 may be NULL) */
+  int32_t nmatches;                       /* out */
+} orbm_bow_pair;
+int orbm_search_by_bow_batch_host(orbm_matcher* m, orbm_bow_pair* pairs, int n_pairs, float nnratio, int check_ori,
+                                  int max_dist);
+
 /* ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, vMatchedPairs, bOnlyStereo, vbCam)
  * (src/ORBmatcher.cc:1364-1720, called from LocalMapping.cc:361) with CheckDistEpipolarLine (:167-184).
  * Key frames: concatenated keypoints (mvKeysUn_total; pt, angle, octave are read), descriptor per global index,
@@ -334,6 +347,20 @@ int orbm_search_for_triangulation_host(orbm_matcher* m, const orbx_keypoint* k1,
                                        const float* epipoles, const float* scale_factors2, const float* level_sigma2_2,
                                        int nlevels, int only_stereo, const int32_t* cam_enabled, int check_ori,
                                        int32_t* matches12, int* nmatches);
+
+/* The same for a batch of independent key-frame pairs in one call (LocalMapping::CreateNewMapPoints matches the
+ * current key frame against every neighbour, src/LocalMapping.cc:300-361).  Fields as the arguments above. */
+typedef struct {
+  const orbx_keypoint* k1; const uint8_t* desc1; const int32_t* has_mp1; const int32_t* cam1; const float* uright1;
+  int32_t n1; orbm_featvec fv1;
+  const orbx_keypoint* k2; const uint8_t* desc2; const int32_t* has_mp2; const int32_t* cam2; const float* uright2;
+  int32_t n2; orbm_featvec fv2;
+  const float* F12s; const float* epipoles; const float* scale_factors2; const float* level_sigma2_2;
+  int32_t* matches12; /* out */
+  int32_t nmatches;   /* out */
+} orbm_tri_pair;
+int orbm_search_for_triangulation_batch_host(orbm_matcher* m, orbm_tri_pair* pairs, int n_pairs, int nlevels, int only_stereo,
+                                             const int32_t* cam_enabled, int check_ori);
 
 #ifdef __cplusplus
 }

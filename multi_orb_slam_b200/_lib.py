@@ -40,6 +40,23 @@ class FeatVec(C.Structure):
     _fields_ = [("node_id", C.c_void_p), ("start", C.c_void_p), ("items", C.c_void_p), ("n_nodes", C.c_int32)]
 
 
+class BowPair(C.Structure):
+    """orbm_bow_pair (include/orb_b200.h)."""
+    _fields_ = [("desc1", C.c_void_p), ("angle1", C.c_void_p), ("valid1", C.c_void_p), ("n1", C.c_int32), ("fv1", FeatVec),
+                ("desc2", C.c_void_p), ("angle2", C.c_void_p), ("valid2", C.c_void_p), ("n2", C.c_int32), ("fv2", FeatVec),
+                ("matches12", C.c_void_p), ("matches21", C.c_void_p), ("nmatches", C.c_int32)]
+
+
+class TriPair(C.Structure):
+    """orbm_tri_pair (include/orb_b200.h)."""
+    _fields_ = [("k1", C.c_void_p), ("desc1", C.c_void_p), ("has_mp1", C.c_void_p), ("cam1", C.c_void_p), ("uright1", C.c_void_p),
+                ("n1", C.c_int32), ("fv1", FeatVec),
+                ("k2", C.c_void_p), ("desc2", C.c_void_p), ("has_mp2", C.c_void_p), ("cam2", C.c_void_p), ("uright2", C.c_void_p),
+                ("n2", C.c_int32), ("fv2", FeatVec),
+                ("F12s", C.c_void_p), ("epipoles", C.c_void_p), ("scale_factors2", C.c_void_p), ("level_sigma2_2", C.c_void_p),
+                ("matches12", C.c_void_p), ("nmatches", C.c_int32)]
+
+
 class Bounds(C.Structure):
     _fields_ = [("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
 
@@ -101,6 +118,8 @@ _SIGS = {
     "orbm_compute_image_bounds_host": (_i, [_vp, _i, _i, _f, _f, _f, _f, _vp, C.POINTER(Bounds)]),
     "orbm_compute_stereo_from_rgbd_device": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _sz, _sz, _f, _vp, _vp]),
     "orbm_assign_features_to_grid_device": (_i, [_vp, _i, _i, _vp, _vp, Bounds, _vp, _vp]),
+    "orbm_search_by_bow_batch_host": (_i, [_vp, _vp, _i, _f, _i, _i]),
+    "orbm_search_for_triangulation_batch_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
     "orbm_search_for_triangulation_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, FeatVec, _vp, _vp, _vp, _vp, _vp, _i,
                                                FeatVec, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, C.POINTER(_i)]),
 }

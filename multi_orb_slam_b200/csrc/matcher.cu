@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -706,12 +707,13 @@ __global__ void __launch_bounds__(256) k_stereo_rgbd(const orbx_keypoint* __rest
 // side-2 features already matched (:296-297, :1061), strict-< best / second from 256, acceptance,
 // rotation histogram; then three maxima and the removal pass in parallel.
 struct BowQuery {
-  int32_t idx1, t0, cnt, off;
+  int32_t idx1, t0, cnt, off;  // side-1 feature, first side-2 item, item count, row offset (all batch-global)
+  int32_t o2, pad0, pad1, pad2;  // first side-2 feature of the query's pair
 };
 
 __global__ void __launch_bounds__(256) k_bow_candidates(const BowQuery* __restrict__ q, int nq,
                                                         const uint8_t* __restrict__ d1, const uint8_t* __restrict__ d2,
-                                                        const int32_t* __restrict__ valid2,
+                                                        const uint8_t* __restrict__ valid2,
                                                         const int32_t* __restrict__ items2, uint32_t* __restrict__ rows) {
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -720,39 +722,44 @@ __global__ void __launch_bounds__(256) k_bow_candidates(const BowQuery* __restri
   const uint4* qp = reinterpret_cast<const uint4*>(d1 + (size_t)bq.idx1 * 32);
   const uint4 qa = __ldg(qp), qb = __ldg(qp + 1);
   for (int c = lane; c < bq.cnt; c += 32) {
-    const int idx2 = items2[bq.t0 + c];
+    const int idx2 = items2[bq.t0 + c];  // batch-global
     uint32_t dist = 0xFFFFu;
-    if (!valid2 || valid2[idx2]) {
+    if (valid2[idx2]) {
       const uint4* tp = reinterpret_cast<const uint4*>(d2 + (size_t)idx2 * 32);
       dist = (uint32_t)hamming256(qa, qb, __ldg(tp), __ldg(tp + 1));
     }
-    rows[bq.off + c] = dist << 16 | (uint32_t)idx2;
+    rows[bq.off + c] = dist << 16 | (uint32_t)(idx2 - bq.o2);  // index local to the pair: fits 16 bits
   }
 }
 
 #define BOW_SMEM_ROWS 12288  // candidate entries staged in shared memory (48 KB)
 
-__global__ void __launch_bounds__(256) k_bow_resolve(const BowQuery* __restrict__ q, int nq, int total_rows,
-                                                     const uint32_t* __restrict__ rows, const float* __restrict__ angle1,
-                                                     const float* __restrict__ angle2, int n2, float nnratio, int check_ori,
+// One CTA per pair of the batch.  pair_info[p] = {first query, query count, first row, row count, o1, o2, n2, 0}.
+__global__ void __launch_bounds__(256) k_bow_resolve(const BowQuery* __restrict__ q_all, const int32_t* __restrict__ pair_info,
+                                                     const uint32_t* __restrict__ rows_all, const float* __restrict__ angle1,
+                                                     const float* __restrict__ angle2, float nnratio, int check_ori,
                                                      int max_dist, int32_t* __restrict__ matches12,
-                                                     int32_t* __restrict__ matches21, int32_t* __restrict__ q_bin,
+                                                     int32_t* __restrict__ matches21, int32_t* __restrict__ q_bin_all,
                                                      int* __restrict__ nmatches_out) {
   extern __shared__ uint32_t s_bow[];  // [n2 / 32 + 1] matched bits of side 2, then the staged rows
   __shared__ int s_hist[HISTO_LENGTH];
   __shared__ int s_keep[HISTO_LENGTH];
   __shared__ int s_nmatch;
   const int tid = threadIdx.x, lane = tid & 31;
+  const int32_t* info = pair_info + 8 * blockIdx.x;
+  const int q0 = info[0], nq = info[1], r0 = info[2], total_rows = info[3], o2 = info[5], n2 = info[6];
+  const BowQuery* q = q_all + q0;
+  int32_t* q_bin = q_bin_all + q0;
   const int nwords = n2 / 32 + 1;
   uint32_t* s_taken = s_bow;
   uint32_t* s_rows = s_bow + nwords;
   const bool staged = total_rows <= BOW_SMEM_ROWS;
   for (int i = tid; i < nwords; i += 256) s_taken[i] = 0;
   if (staged)
-    for (int i = tid; i < total_rows; i += 256) s_rows[i] = rows[i];
+    for (int i = tid; i < total_rows; i += 256) s_rows[i] = rows_all[r0 + i];
   if (tid < HISTO_LENGTH) s_hist[tid] = 0;
   __syncthreads();
-  const uint32_t* R = staged ? s_rows : rows;
+  const uint32_t* R = staged ? s_rows : rows_all + r0;  // indexed by row offsets relative to the pair
   if (tid < 32) {
     int nmatches = 0;
     for (int j = 0; j < nq; ++j) {
@@ -760,7 +767,7 @@ __global__ void __launch_bounds__(256) k_bow_resolve(const BowQuery* __restrict_
       // key = dist << 16 | position in the node's vector: the strict-< scan order (:311-321)
       uint32_t best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
       for (int c = lane; c < bq.cnt; c += 32) {
-        const uint32_t e = R[bq.off + c];
+        const uint32_t e = R[bq.off - r0 + c];
         const uint32_t idx2 = e & 0xFFFFu;
         if ((e >> 16) == 0xFFFFu || (s_taken[idx2 >> 5] >> (idx2 & 31) & 1u)) continue;
         const uint32_t key = (e & 0xFFFF0000u) | (uint32_t)c;
@@ -773,13 +780,13 @@ __global__ void __launch_bounds__(256) k_bow_resolve(const BowQuery* __restrict_
         const int bestDist1 = (int)(best >> 16);
         const int bestDist2 = second == 0xFFFFFFFFu ? 256 : (int)(second >> 16);
         if (bestDist1 <= max_dist && (float)bestDist1 < __fmul_rn(nnratio, (float)bestDist2)) {
-          const int idx2 = (int)(R[bq.off + (int)(best & 0xFFFFu)] & 0xFFFFu);
+          const int idx2 = (int)(R[bq.off - r0 + (int)(best & 0xFFFFu)] & 0xFFFFu);
           if (lane == 0) {
             s_taken[idx2 >> 5] |= 1u << (idx2 & 31);
             matches12[bq.idx1] = idx2;
             bin = HISTO_LENGTH;  // matched, no orientation bin
             if (check_ori) {
-              float rot = __fsub_rn(angle1[bq.idx1], angle2[idx2]);
+              float rot = __fsub_rn(angle1[bq.idx1], angle2[o2 + idx2]);
               if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
               bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
               if (bin == HISTO_LENGTH) bin = 0;
@@ -799,6 +806,7 @@ __global__ void __launch_bounds__(256) k_bow_resolve(const BowQuery* __restrict_
   }
   __syncthreads();
   // removal pass (:365-383) and the side-2 view of the matches
+  const int o1 = info[4];
   for (int j = tid; j < nq; j += 256) {
     const int bin = q_bin[j];
     if (bin < 0) continue;
@@ -807,11 +815,11 @@ __global__ void __launch_bounds__(256) k_bow_resolve(const BowQuery* __restrict_
       matches12[idx1] = -1;
       atomicSub(&s_nmatch, 1);
     } else {
-      matches21[matches12[idx1]] = idx1;
+      matches21[o2 + matches12[idx1]] = idx1 - o1;
     }
   }
   __syncthreads();
-  if (tid == 0) *nmatches_out = s_nmatch;
+  if (tid == 0) nmatches_out[blockIdx.x] = s_nmatch;
 }
 
 // ---- SearchForTriangulation (:1364-1720) ------------------------------------------------------
@@ -829,14 +837,17 @@ struct TriSide {
 };
 
 __global__ void __launch_bounds__(256) k_tri_match(const BowQuery* __restrict__ q, int nq, TriSide s1, TriSide s2,
-                                                   const int32_t* __restrict__ items2, const float* __restrict__ consts,
+                                                   const int32_t* __restrict__ items2, const float* __restrict__ consts_all,
                                                    int only_stereo, int check_ori, int32_t* __restrict__ matches12,
-                                                   int32_t* __restrict__ q_bin, int* __restrict__ hist) {
-  // consts: F12s[18], epipoles[4], scale_factors2[16], level_sigma2_2[16]
+                                                   int32_t* __restrict__ q_bin, int* __restrict__ hist_all) {
+  // per pair: consts = F12s[18], epipoles[4], scale_factors2[16], level_sigma2_2[16] (54 floats, stride 56);
+  // all feature indices are batch-global, bq.o2 = first key-frame-2 feature of the pair, bq.pad0 = pair
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i >= nq) return;
   const BowQuery bq = q[i];
+  const float* consts = consts_all + 56 * bq.pad0;
+  int* hist = hist_all + HISTO_LENGTH * bq.pad0;
   const int idx1 = bq.idx1;
   const orbx_keypoint kp1 = s1.k[idx1];
   const int camIdx1 = s1.cam[idx1];
@@ -874,7 +885,7 @@ __global__ void __launch_bounds__(256) k_tri_match(const BowQuery* __restrict__ 
     int bin = -1;
     if (best != 0xFFFFFFFFu) {
       const int idx2 = items2[bq.t0 + (0xFFFF - (int)(best & 0xFFFFu))];
-      matches12[idx1] = idx2;
+      matches12[idx1] = idx2 - bq.o2;
       bin = HISTO_LENGTH;
       if (check_ori) {
         float rot = __fsub_rn(kp1.angle, s2.k[idx2].angle);
@@ -889,14 +900,18 @@ __global__ void __launch_bounds__(256) k_tri_match(const BowQuery* __restrict__ 
 }
 
 // rotation filter (:1701-1716) and the match count
-__global__ void __launch_bounds__(256) k_tri_finish(const BowQuery* __restrict__ q, int nq, int check_ori,
-                                                    const int32_t* __restrict__ q_bin, const int* __restrict__ hist,
-                                                    int32_t* __restrict__ matches12, int* __restrict__ nmatches_out) {
+__global__ void __launch_bounds__(256) k_tri_finish(const BowQuery* __restrict__ q_all, const int32_t* __restrict__ pair_q,
+                                                    int check_ori, const int32_t* __restrict__ q_bin_all,
+                                                    const int* __restrict__ hist_all, int32_t* __restrict__ matches12,
+                                                    int* __restrict__ nmatches_out) {
   __shared__ int s_keep[HISTO_LENGTH];
   __shared__ int s_n;
+  const int p = blockIdx.x, q0 = pair_q[p], nq = pair_q[p + 1] - q0;
+  const BowQuery* q = q_all + q0;
+  const int32_t* q_bin = q_bin_all + q0;
   if (threadIdx.x == 0) {
     s_n = 0;
-    if (check_ori) three_maxima_keep(hist, s_keep);
+    if (check_ori) three_maxima_keep(hist_all + HISTO_LENGTH * p, s_keep);
   }
   __syncthreads();
   int mine = 0;
@@ -908,7 +923,7 @@ __global__ void __launch_bounds__(256) k_tri_finish(const BowQuery* __restrict__
   }
   atomicAdd(&s_n, mine);
   __syncthreads();
-  if (threadIdx.x == 0) *nmatches_out = s_n;
+  if (threadIdx.x == 0) nmatches_out[p] = s_n;
 }
 
 // ---- SearchByProjection(Frame&, vector<MapPoint*>&, th) ------------------------------------
@@ -1473,79 +1488,283 @@ int orbm_search_by_projection_points_host(orbm_matcher* m, const orbx_keypoint* 
   return m->check(cudaGetLastError(), "search_by_projection launch") ? ORBX_OK : ORBX_E_CUDA;
 }
 
+int orbm_search_by_bow_batch_host(orbm_matcher* m, orbm_bow_pair* pairs, int n_pairs, float nnratio, int check_ori,
+                                  int max_dist) {
+  if (!m || n_pairs < 0 || (n_pairs && !pairs)) return ORBX_E_INVALID;
+  std::vector<BowQuery> queries;
+  std::vector<int32_t> info((size_t)n_pairs * 8, 0), items2;
+  size_t G1 = 0, G2 = 0;
+  int total = 0, max_n2 = 0, max_rows = 0;
+  for (int p = 0; p < n_pairs; ++p) {
+    orbm_bow_pair& P = pairs[p];
+    const orbm_featvec &fv1 = P.fv1, &fv2 = P.fv2;
+    if (!P.matches12 || P.n1 < 0 || P.n2 < 0 || P.n1 > 65535 || P.n2 > 65535 || fv1.n_nodes < 0 || fv2.n_nodes < 0 ||
+        (P.n1 && (!P.desc1 || !P.angle1)) || (P.n2 && (!P.desc2 || !P.angle2)) ||
+        (fv1.n_nodes && (!fv1.node_id || !fv1.start || !fv1.items)) || (fv2.n_nodes && (!fv2.node_id || !fv2.start || !fv2.items)))
+      return ORBX_E_INVALID;
+    P.nmatches = 0;
+    for (int i = 0; i < P.n1; ++i) P.matches12[i] = -1;
+    if (P.matches21)
+      for (int i = 0; i < P.n2; ++i) P.matches21[i] = -1;
+    int32_t* I = &info[(size_t)p * 8];
+    I[0] = (int32_t)queries.size();
+    I[2] = total;
+    I[4] = (int32_t)G1;
+    I[5] = (int32_t)G2;
+    I[6] = P.n2;
+    // the walk of the two std::map's with lower_bound jumps (:350-359), emitting the queries
+    const int items_base = (int)items2.size();
+    const int n_items2 = fv2.n_nodes ? fv2.start[fv2.n_nodes] : 0;
+    for (int i = 0; i < n_items2; ++i) {
+      if (fv2.items[i] < 0 || fv2.items[i] >= P.n2) { m->err = "feature vector 2: index out of range"; return ORBX_E_INVALID; }
+      items2.push_back((int32_t)G2 + fv2.items[i]);
+    }
+    int a = 0, b = 0;
+    while (a < fv1.n_nodes && b < fv2.n_nodes) {
+      const int32_t na = fv1.node_id[a], nb = fv2.node_id[b];
+      if (na == nb) {
+        const int t0 = fv2.start[b], cnt = fv2.start[b + 1] - t0;
+        for (int q = fv1.start[a]; q < fv1.start[a + 1]; ++q) {
+          const int idx1 = fv1.items[q];
+          if (idx1 < 0 || idx1 >= P.n1) { m->err = "feature vector 1: index out of range"; return ORBX_E_INVALID; }
+          if (P.valid1 && !P.valid1[idx1]) continue;
+          if (cnt > 0) {
+            queries.push_back({(int32_t)G1 + idx1, items_base + t0, cnt, total, (int32_t)G2, 0, 0, 0});
+            total += cnt;
+          }
+        }
+        ++a; ++b;
+      } else if (na < nb) {
+        a = (int)(std::lower_bound(fv1.node_id + a, fv1.node_id + fv1.n_nodes, nb) - fv1.node_id);
+      } else {
+        b = (int)(std::lower_bound(fv2.node_id + b, fv2.node_id + fv2.n_nodes, na) - fv2.node_id);
+      }
+    }
+    I[1] = (int32_t)queries.size() - I[0];
+    I[3] = total - I[2];
+    max_n2 = std::max(max_n2, P.n2);
+    max_rows = std::max(max_rows, I[3] <= BOW_SMEM_ROWS ? I[3] : 0);
+    G1 += P.n1;
+    G2 += P.n2;
+  }
+  const int nq = (int)queries.size();
+  if (nq == 0) return ORBX_OK;
+  // pack the per-pair arrays into batch-global ones
+  std::vector<uint8_t> hd((G1 + G2) * 32), hvalid2(G2, 1);
+  std::vector<float> hang(G1 + G2);
+  {
+    size_t o1 = 0, o2 = 0;
+    for (int p = 0; p < n_pairs; ++p) {
+      const orbm_bow_pair& P = pairs[p];
+      if (P.n1) { std::memcpy(&hd[o1 * 32], P.desc1, (size_t)P.n1 * 32); std::memcpy(&hang[o1], P.angle1, sizeof(float) * P.n1); }
+      if (P.n2) {
+        std::memcpy(&hd[(G1 + o2) * 32], P.desc2, (size_t)P.n2 * 32);
+        std::memcpy(&hang[G1 + o2], P.angle2, sizeof(float) * P.n2);
+        if (P.valid2)
+          for (int i = 0; i < P.n2; ++i) hvalid2[o2 + i] = P.valid2[i] ? 1 : 0;
+      }
+      o1 += P.n1;
+      o2 += P.n2;
+    }
+  }
+  cudaSetDevice(m->device);
+  cudaStream_t st = m->stream;
+  uint8_t* dd = m->scratch<uint8_t>(8, (G1 + G2) * 32 + G2 + 64);
+  float* dang = m->scratch<float>(9, G1 + G2);
+  int32_t* dints = m->scratch<int32_t>(4, items2.size() + G1 + G2 + nq + (size_t)n_pairs * 9 + 8);
+  BowQuery* dq = m->scratch<BowQuery>(5, nq);
+  uint32_t* rows = m->scratch<uint32_t>(6, (size_t)total);
+  if (!dd || !dang || !dints || !dq || !rows) return ORBX_E_CUDA;
+  uint8_t *dd1 = dd, *dd2 = dd + G1 * 32, *dvalid2 = dd + (G1 + G2) * 32;
+  float *da1 = dang, *da2 = dang + G1;
+  int32_t* ditems2 = dints;
+  int32_t* dm12 = ditems2 + items2.size();
+  int32_t* dm21 = dm12 + G1;
+  int32_t* dbin = dm21 + G2;
+  int32_t* dinfo = dbin + nq;
+  int* dnm = dinfo + (size_t)n_pairs * 8;
+  cudaMemcpyAsync(dd, hd.data(), hd.size(), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dvalid2, hvalid2.data(), G2, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dang, hang.data(), sizeof(float) * hang.size(), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(ditems2, items2.data(), sizeof(int32_t) * items2.size(), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dq, queries.data(), sizeof(BowQuery) * nq, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dinfo, info.data(), sizeof(int32_t) * info.size(), cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(dm12, 0xFF, sizeof(int32_t) * (G1 + G2), st);  // matches12 and matches21 = -1
+  cudaMemsetAsync(dnm, 0, sizeof(int) * n_pairs, st);
+  const size_t smem = sizeof(uint32_t) * ((size_t)(max_n2 / 32 + 1) + max_rows);
+  if (smem > 48 * 1024 &&
+      !m->check(cudaFuncSetAttribute(k_bow_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "smem opt-in"))
+    return ORBX_E_CUDA;
+  k_bow_candidates<<<(nq + 7) / 8, 256, 0, st>>>(dq, nq, dd1, dd2, dvalid2, ditems2, rows);
+  k_bow_resolve<<<n_pairs, 256, smem, st>>>(dq, dinfo, rows, da1, da2, nnratio, check_ori, max_dist, dm12, dm21, dbin, dnm);
+  m->launches += 2;
+  std::vector<int32_t> hm(G1 + G2), hnm(n_pairs);
+  cudaMemcpyAsync(hm.data(), dm12, sizeof(int32_t) * (G1 + G2), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(hnm.data(), dnm, sizeof(int) * n_pairs, cudaMemcpyDeviceToHost, st);
+  if (!m->check(cudaStreamSynchronize(st), "search_by_bow")) return ORBX_E_CUDA;
+  {
+    size_t o1 = 0, o2 = 0;
+    for (int p = 0; p < n_pairs; ++p) {
+      orbm_bow_pair& P = pairs[p];
+      std::copy(hm.begin() + o1, hm.begin() + o1 + P.n1, P.matches12);
+      if (P.matches21) std::copy(hm.begin() + G1 + o2, hm.begin() + G1 + o2 + P.n2, P.matches21);
+      P.nmatches = hnm[p];
+      o1 += P.n1;
+      o2 += P.n2;
+    }
+  }
+  return m->check(cudaGetLastError(), "search_by_bow launch") ? ORBX_OK : ORBX_E_CUDA;
+}
+
 int orbm_search_by_bow_host(orbm_matcher* m, const uint8_t* desc1, const float* angle1, const int32_t* valid1, int n1,
                             orbm_featvec fv1, const uint8_t* desc2, const float* angle2, const int32_t* valid2, int n2,
                             orbm_featvec fv2, float nnratio, int check_ori, int max_dist, int32_t* matches12,
                             int32_t* matches21, int* nmatches) {
-  if (!m || !matches12 || !nmatches || n1 < 0 || n2 < 0 || n1 > 65535 || n2 > 65535 || fv1.n_nodes < 0 || fv2.n_nodes < 0 ||
-      (n1 && (!desc1 || !angle1)) || (n2 && (!desc2 || !angle2)) ||
-      (fv1.n_nodes && (!fv1.node_id || !fv1.start || !fv1.items)) || (fv2.n_nodes && (!fv2.node_id || !fv2.start || !fv2.items)))
-    return ORBX_E_INVALID;
-  *nmatches = 0;
-  for (int i = 0; i < n1; ++i) matches12[i] = -1;
-  if (matches21)
-    for (int i = 0; i < n2; ++i) matches21[i] = -1;
-  // the walk of the two std::map's with lower_bound jumps (:350-359), emitting the queries
+  if (!nmatches) return ORBX_E_INVALID;
+  orbm_bow_pair P = {desc1, angle1, valid1, n1, fv1, desc2, angle2, valid2, n2, fv2, matches12, matches21, 0};
+  const int rc = orbm_search_by_bow_batch_host(m, &P, 1, nnratio, check_ori, max_dist);
+  *nmatches = P.nmatches;
+  return rc;
+}
+
+int orbm_search_for_triangulation_batch_host(orbm_matcher* m, orbm_tri_pair* pairs, int n_pairs, int nlevels, int only_stereo,
+                                             const int32_t* cam_enabled, int check_ori) {
+  if (!m || n_pairs < 0 || (n_pairs && !pairs) || nlevels < 1 || nlevels > ORBX_MAX_LEVELS || !cam_enabled) return ORBX_E_INVALID;
   std::vector<BowQuery> queries;
-  int total = 0, a = 0, b = 0;
-  while (a < fv1.n_nodes && b < fv2.n_nodes) {
-    const int32_t na = fv1.node_id[a], nb = fv2.node_id[b];
-    if (na == nb) {
-      const int t0 = fv2.start[b], cnt = fv2.start[b + 1] - t0;
-      for (int p = fv1.start[a]; p < fv1.start[a + 1]; ++p) {
-        const int idx1 = fv1.items[p];
-        if (idx1 < 0 || idx1 >= n1) { m->err = "feature vector 1: index out of range"; return ORBX_E_INVALID; }
-        if (valid1 && !valid1[idx1]) continue;
-        if (cnt > 0) { queries.push_back({idx1, t0, cnt, total}); total += cnt; }
-      }
-      ++a; ++b;
-    } else if (na < nb) {
-      a = (int)(std::lower_bound(fv1.node_id + a, fv1.node_id + fv1.n_nodes, nb) - fv1.node_id);
-    } else {
-      b = (int)(std::lower_bound(fv2.node_id + b, fv2.node_id + fv2.n_nodes, na) - fv2.node_id);
+  std::vector<int32_t> pair_q(n_pairs + 1, 0), items2;
+  std::vector<float> hconst((size_t)n_pairs * 56, 0.f);
+  size_t G1 = 0, G2 = 0;
+  for (int p = 0; p < n_pairs; ++p) {
+    orbm_tri_pair& P = pairs[p];
+    const orbm_featvec &fv1 = P.fv1, &fv2 = P.fv2;
+    if (!P.matches12 || P.n1 < 0 || P.n2 < 0 || P.n1 > 65535 || P.n2 > 65535 || fv1.n_nodes < 0 || fv2.n_nodes < 0 || !P.F12s ||
+        !P.epipoles || !P.scale_factors2 || !P.level_sigma2_2 ||
+        (P.n1 && (!P.k1 || !P.desc1 || !P.has_mp1 || !P.cam1 || !P.uright1)) ||
+        (P.n2 && (!P.k2 || !P.desc2 || !P.has_mp2 || !P.cam2 || !P.uright2)) ||
+        (fv1.n_nodes && (!fv1.node_id || !fv1.start || !fv1.items)) || (fv2.n_nodes && (!fv2.node_id || !fv2.start || !fv2.items)))
+      return ORBX_E_INVALID;
+    P.nmatches = 0;
+    for (int i = 0; i < P.n1; ++i) P.matches12[i] = -1;
+    for (int i = 0; i < P.n1; ++i)
+      if (P.cam1[i] < 0 || P.cam1[i] > 1) { m->err = "key frame 1: camera index out of range"; return ORBX_E_INVALID; }
+    for (int i = 0; i < P.n2; ++i)
+      if (P.k2[i].octave < 0 || P.k2[i].octave >= nlevels) { m->err = "key frame 2: octave out of range"; return ORBX_E_INVALID; }
+    float* hc = &hconst[(size_t)p * 56];
+    std::copy(P.F12s, P.F12s + 18, hc);
+    std::copy(P.epipoles, P.epipoles + 4, hc + 18);
+    std::copy(P.scale_factors2, P.scale_factors2 + nlevels, hc + 22);
+    std::copy(P.level_sigma2_2, P.level_sigma2_2 + nlevels, hc + 38);
+    pair_q[p] = (int32_t)queries.size();
+    const int items_base = (int)items2.size();
+    const int n_items2 = fv2.n_nodes ? fv2.start[fv2.n_nodes] : 0;
+    for (int i = 0; i < n_items2; ++i) {
+      if (fv2.items[i] < 0 || fv2.items[i] >= P.n2) { m->err = "feature vector 2: index out of range"; return ORBX_E_INVALID; }
+      items2.push_back((int32_t)G2 + fv2.items[i]);
     }
+    // feature-vector walk (:1456-1700): one query per key-frame-1 feature that passes the side-1 tests (:1468-1480)
+    int a = 0, b = 0;
+    while (a < fv1.n_nodes && b < fv2.n_nodes) {
+      const int32_t na = fv1.node_id[a], nb = fv2.node_id[b];
+      if (na == nb) {
+        const int t0 = fv2.start[b], cnt = fv2.start[b + 1] - t0;
+        if (cnt > 65535) { m->err = "feature vector 2: node with more than 65535 features"; return ORBX_E_INVALID; }
+        for (int q = fv1.start[a]; q < fv1.start[a + 1]; ++q) {
+          const int idx1 = fv1.items[q];
+          if (idx1 < 0 || idx1 >= P.n1) { m->err = "feature vector 1: index out of range"; return ORBX_E_INVALID; }
+          if (P.has_mp1[idx1] || !cam_enabled[P.cam1[idx1]]) continue;
+          if (only_stereo && !(P.uright1[idx1] >= 0)) continue;
+          if (cnt > 0) queries.push_back({(int32_t)G1 + idx1, items_base + t0, cnt, 0, (int32_t)G2, p, 0, 0});
+        }
+        ++a; ++b;
+      } else if (na < nb) {
+        a = (int)(std::lower_bound(fv1.node_id + a, fv1.node_id + fv1.n_nodes, nb) - fv1.node_id);
+      } else {
+        b = (int)(std::lower_bound(fv2.node_id + b, fv2.node_id + fv2.n_nodes, na) - fv2.node_id);
+      }
+    }
+    G1 += P.n1;
+    G2 += P.n2;
   }
+  pair_q[n_pairs] = (int32_t)queries.size();
   const int nq = (int)queries.size();
   if (nq == 0) return ORBX_OK;
-  const int n_items2 = fv2.start[fv2.n_nodes];
-  for (int i = 0; i < n_items2; ++i)
-    if (fv2.items[i] < 0 || fv2.items[i] >= n2) { m->err = "feature vector 2: index out of range"; return ORBX_E_INVALID; }
+  // key-frame-2 features follow all key-frame-1 features in the packed arrays
+  for (int32_t& v : items2) v += (int32_t)G1;
+  for (BowQuery& bq : queries) bq.o2 += (int32_t)G1;
+  // pack both sides into batch-global arrays: descriptors, keypoints, has_mp, cam, uright
+  const size_t G = G1 + G2;
+  std::vector<uint8_t> hd(G * 32);
+  std::vector<orbx_keypoint> hk(G);
+  std::vector<int32_t> hmp(G), hcam(G);
+  std::vector<float> hur(G);
+  {
+    size_t o1 = 0, o2 = G1;
+    for (int p = 0; p < n_pairs; ++p) {
+      const orbm_tri_pair& P = pairs[p];
+      if (P.n1) {
+        std::memcpy(&hd[o1 * 32], P.desc1, (size_t)P.n1 * 32);
+        std::copy(P.k1, P.k1 + P.n1, hk.begin() + o1);
+        std::copy(P.has_mp1, P.has_mp1 + P.n1, hmp.begin() + o1);
+        std::copy(P.cam1, P.cam1 + P.n1, hcam.begin() + o1);
+        std::copy(P.uright1, P.uright1 + P.n1, hur.begin() + o1);
+      }
+      if (P.n2) {
+        std::memcpy(&hd[o2 * 32], P.desc2, (size_t)P.n2 * 32);
+        std::copy(P.k2, P.k2 + P.n2, hk.begin() + o2);
+        std::copy(P.has_mp2, P.has_mp2 + P.n2, hmp.begin() + o2);
+        std::copy(P.cam2, P.cam2 + P.n2, hcam.begin() + o2);
+        std::copy(P.uright2, P.uright2 + P.n2, hur.begin() + o2);
+      }
+      o1 += P.n1;
+      o2 += P.n2;
+    }
+  }
   cudaSetDevice(m->device);
   cudaStream_t st = m->stream;
-  uint8_t* dd = m->scratch<uint8_t>(8, ((size_t)n1 + n2) * 32);
-  float* dang = m->scratch<float>(9, (size_t)n1 + n2);
-  int32_t* dints = m->scratch<int32_t>(4, (size_t)n2 + n_items2 + n1 + n2 + nq + 8);
+  uint8_t* sb = m->scratch<uint8_t>(8, G * (32 + sizeof(orbx_keypoint) + 12) + 256);
+  int32_t* dints = m->scratch<int32_t>(4, items2.size() + G1 + nq + (size_t)n_pairs * (HISTO_LENGTH + 2) + 8);
   BowQuery* dq = m->scratch<BowQuery>(5, nq);
-  uint32_t* rows = m->scratch<uint32_t>(6, (size_t)total);
-  if (!dd || !dang || !dints || !dq || !rows) return ORBX_E_CUDA;
-  uint8_t *dd1 = dd, *dd2 = dd + (size_t)n1 * 32;
-  float *da1 = dang, *da2 = dang + n1;
-  int32_t* dvalid2 = dints;
-  int32_t* ditems2 = dvalid2 + n2;
-  int32_t* dm12 = ditems2 + n_items2;
-  int32_t* dm21 = dm12 + n1;
-  int32_t* dbin = dm21 + n2;
-  int* dnm = dbin + nq;
-  cudaMemcpyAsync(dd1, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dd2, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(da1, angle1, sizeof(float) * n1, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(da2, angle2, sizeof(float) * n2, cudaMemcpyHostToDevice, st);
-  if (valid2) cudaMemcpyAsync(dvalid2, valid2, sizeof(int32_t) * n2, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(ditems2, fv2.items, sizeof(int32_t) * n_items2, cudaMemcpyHostToDevice, st);
+  float* dconst = m->scratch<float>(9, hconst.size());
+  if (!sb || !dints || !dq || !dconst) return ORBX_E_CUDA;
+  uint8_t* dd = sb;  // descriptors first: uint4 loads need 16-byte alignment
+  orbx_keypoint* dk = reinterpret_cast<orbx_keypoint*>(dd + G * 32);
+  int32_t* dmp = reinterpret_cast<int32_t*>(dk + G);
+  int32_t* dcam = dmp + G;
+  float* dur = reinterpret_cast<float*>(dcam + G);
+  cudaMemcpyAsync(dd, hd.data(), hd.size(), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dk, hk.data(), sizeof(orbx_keypoint) * G, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dmp, hmp.data(), sizeof(int32_t) * G, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dcam, hcam.data(), sizeof(int32_t) * G, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dur, hur.data(), sizeof(float) * G, cudaMemcpyHostToDevice, st);
+  const TriSide s1 = {dk, dd, dmp, dcam, dur};  // both sides share the arrays (batch-global indices)
+  int32_t* ditems2 = dints;
+  int32_t* dm12 = ditems2 + items2.size();
+  int32_t* dbin = dm12 + G1;
+  int32_t* dpq = dbin + nq;
+  int* dhist = dpq + n_pairs + 1;
+  int* dnm = dhist + (size_t)n_pairs * HISTO_LENGTH;
+  cudaMemcpyAsync(dconst, hconst.data(), sizeof(float) * hconst.size(), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(ditems2, items2.data(), sizeof(int32_t) * items2.size(), cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(dq, queries.data(), sizeof(BowQuery) * nq, cudaMemcpyHostToDevice, st);
-  cudaMemsetAsync(dm12, 0xFF, sizeof(int32_t) * ((size_t)n1 + n2), st);  // matches12 and matches21 = -1
-  const size_t smem = sizeof(uint32_t) * ((size_t)(n2 / 32 + 1) + (total <= BOW_SMEM_ROWS ? total : 0));
-  if (smem > 48 * 1024 &&
-      !m->check(cudaFuncSetAttribute(k_bow_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "smem opt-in"))
-    return ORBX_E_CUDA;
-  k_bow_candidates<<<(nq + 7) / 8, 256, 0, st>>>(dq, nq, dd1, dd2, valid2 ? dvalid2 : nullptr, ditems2, rows);
-  k_bow_resolve<<<1, 256, smem, st>>>(dq, nq, total, rows, da1, da2, n2, nnratio, check_ori, max_dist, dm12, dm21, dbin, dnm);
+  cudaMemcpyAsync(dpq, pair_q.data(), sizeof(int32_t) * (n_pairs + 1), cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(dm12, 0xFF, sizeof(int32_t) * G1, st);
+  cudaMemsetAsync(dhist, 0, sizeof(int) * ((size_t)n_pairs * (HISTO_LENGTH + 1)), st);
+  k_tri_match<<<(nq + 7) / 8, 256, 0, st>>>(dq, nq, s1, s1, ditems2, dconst, only_stereo, check_ori, dm12, dbin, dhist);
+  k_tri_finish<<<n_pairs, 256, 0, st>>>(dq, dpq, check_ori, dbin, dhist, dm12, dnm);
   m->launches += 2;
-  cudaMemcpyAsync(matches12, dm12, sizeof(int32_t) * n1, cudaMemcpyDeviceToHost, st);
-  if (matches21) cudaMemcpyAsync(matches21, dm21, sizeof(int32_t) * n2, cudaMemcpyDeviceToHost, st);
-  cudaMemcpyAsync(nmatches, dnm, sizeof(int), cudaMemcpyDeviceToHost, st);
-  if (!m->check(cudaStreamSynchronize(st), "search_by_bow")) return ORBX_E_CUDA;
-  return m->check(cudaGetLastError(), "search_by_bow launch") ? ORBX_OK : ORBX_E_CUDA;
+  std::vector<int32_t> hm(G1), hnm(n_pairs);
+  cudaMemcpyAsync(hm.data(), dm12, sizeof(int32_t) * G1, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(hnm.data(), dnm, sizeof(int) * n_pairs, cudaMemcpyDeviceToHost, st);
+  if (!m->check(cudaStreamSynchronize(st), "search_for_triangulation")) return ORBX_E_CUDA;
+  {
+    size_t o1 = 0;
+    for (int p = 0; p < n_pairs; ++p) {
+      std::copy(hm.begin() + o1, hm.begin() + o1 + pairs[p].n1, pairs[p].matches12);
+      pairs[p].nmatches = hnm[p];
+      o1 += pairs[p].n1;
+    }
+  }
+  return m->check(cudaGetLastError(), "search_for_triangulation launch") ? ORBX_OK : ORBX_E_CUDA;
 }
 
 int orbm_search_for_triangulation_host(orbm_matcher* m, const orbx_keypoint* k1, const uint8_t* desc1, const int32_t* has_mp1,
@@ -1555,95 +1774,12 @@ int orbm_search_for_triangulation_host(orbm_matcher* m, const orbx_keypoint* k1,
                                        const float* epipoles, const float* scale_factors2, const float* level_sigma2_2,
                                        int nlevels, int only_stereo, const int32_t* cam_enabled, int check_ori,
                                        int32_t* matches12, int* nmatches) {
-  if (!m || !matches12 || !nmatches || n1 < 0 || n2 < 0 || n1 > 65535 || n2 > 65535 || fv1.n_nodes < 0 || fv2.n_nodes < 0 ||
-      nlevels < 1 || nlevels > ORBX_MAX_LEVELS || !F12s || !epipoles || !scale_factors2 || !level_sigma2_2 || !cam_enabled ||
-      (n1 && (!k1 || !desc1 || !has_mp1 || !cam1 || !uright1)) || (n2 && (!k2 || !desc2 || !has_mp2 || !cam2 || !uright2)) ||
-      (fv1.n_nodes && (!fv1.node_id || !fv1.start || !fv1.items)) || (fv2.n_nodes && (!fv2.node_id || !fv2.start || !fv2.items)))
-    return ORBX_E_INVALID;
-  *nmatches = 0;
-  for (int i = 0; i < n1; ++i) matches12[i] = -1;
-  for (int i = 0; i < n1; ++i)
-    if (cam1[i] < 0 || cam1[i] > 1) { m->err = "key frame 1: camera index out of range"; return ORBX_E_INVALID; }
-  for (int i = 0; i < n2; ++i)
-    if (k2[i].octave < 0 || k2[i].octave >= nlevels) { m->err = "key frame 2: octave out of range"; return ORBX_E_INVALID; }
-  // feature-vector walk (:1456-1700): one query per key-frame-1 feature that passes the side-1 tests (:1468-1480)
-  std::vector<BowQuery> queries;
-  int a = 0, b = 0;
-  while (a < fv1.n_nodes && b < fv2.n_nodes) {
-    const int32_t na = fv1.node_id[a], nb = fv2.node_id[b];
-    if (na == nb) {
-      const int t0 = fv2.start[b], cnt = fv2.start[b + 1] - t0;
-      if (cnt > 65535) { m->err = "feature vector 2: node with more than 65535 features"; return ORBX_E_INVALID; }
-      for (int p = fv1.start[a]; p < fv1.start[a + 1]; ++p) {
-        const int idx1 = fv1.items[p];
-        if (idx1 < 0 || idx1 >= n1) { m->err = "feature vector 1: index out of range"; return ORBX_E_INVALID; }
-        if (has_mp1[idx1] || !cam_enabled[cam1[idx1]]) continue;
-        if (only_stereo && !(uright1[idx1] >= 0)) continue;
-        if (cnt > 0) queries.push_back({idx1, t0, cnt, 0});
-      }
-      ++a; ++b;
-    } else if (na < nb) {
-      a = (int)(std::lower_bound(fv1.node_id + a, fv1.node_id + fv1.n_nodes, nb) - fv1.node_id);
-    } else {
-      b = (int)(std::lower_bound(fv2.node_id + b, fv2.node_id + fv2.n_nodes, na) - fv2.node_id);
-    }
-  }
-  const int nq = (int)queries.size();
-  if (nq == 0) return ORBX_OK;
-  const int n_items2 = fv2.start[fv2.n_nodes];
-  for (int i = 0; i < n_items2; ++i)
-    if (fv2.items[i] < 0 || fv2.items[i] >= n2) { m->err = "feature vector 2: index out of range"; return ORBX_E_INVALID; }
-  cudaSetDevice(m->device);
-  cudaStream_t st = m->stream;
-  const size_t per_kp = 32 + sizeof(orbx_keypoint) + 4 + 4 + 4;
-  uint8_t* sb = m->scratch<uint8_t>(8, ((size_t)n1 + n2) * per_kp + 512);
-  int32_t* dints = m->scratch<int32_t>(4, (size_t)n_items2 + n1 + nq + HISTO_LENGTH + 8);
-  BowQuery* dq = m->scratch<BowQuery>(5, nq);
-  float* dconst = m->scratch<float>(9, 64);
-  if (!sb || !dints || !dq || !dconst) return ORBX_E_CUDA;
-  auto place = [&](uint8_t*& cur, int n, const orbx_keypoint* k, const uint8_t* d, const int32_t* mp, const int32_t* cam,
-                   const float* ur) {
-    TriSide s;
-    uint8_t* dd = cur;  // descriptors first: uint4 loads need 16-byte alignment
-    orbx_keypoint* dk = reinterpret_cast<orbx_keypoint*>(dd + (size_t)n * 32);
-    int32_t* dmp = reinterpret_cast<int32_t*>(dk + n);
-    int32_t* dcam = dmp + n;
-    float* dur = reinterpret_cast<float*>(dcam + n);
-    cudaMemcpyAsync(dd, d, (size_t)n * 32, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dk, k, sizeof(orbx_keypoint) * n, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dmp, mp, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dcam, cam, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dur, ur, sizeof(float) * n, cudaMemcpyHostToDevice, st);
-    s.d = dd; s.k = dk; s.has_mp = dmp; s.cam = dcam; s.uright = dur;
-    cur = reinterpret_cast<uint8_t*>(dur + n);
-    cur += (16 - (reinterpret_cast<uintptr_t>(cur) & 15)) & 15;
-    return s;
-  };
-  uint8_t* cur = sb;
-  const TriSide s1 = place(cur, n1, k1, desc1, has_mp1, cam1, uright1);
-  const TriSide s2 = place(cur, n2, k2, desc2, has_mp2, cam2, uright2);
-  float hconst[54] = {0};
-  std::copy(F12s, F12s + 18, hconst);
-  std::copy(epipoles, epipoles + 4, hconst + 18);
-  std::copy(scale_factors2, scale_factors2 + nlevels, hconst + 22);
-  std::copy(level_sigma2_2, level_sigma2_2 + nlevels, hconst + 38);
-  int32_t* ditems2 = dints;
-  int32_t* dm12 = ditems2 + n_items2;
-  int32_t* dbin = dm12 + n1;
-  int* dhist = dbin + nq;
-  int* dnm = dhist + HISTO_LENGTH;
-  cudaMemcpyAsync(dconst, hconst, sizeof(hconst), cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(ditems2, fv2.items, sizeof(int32_t) * n_items2, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dq, queries.data(), sizeof(BowQuery) * nq, cudaMemcpyHostToDevice, st);
-  cudaMemsetAsync(dm12, 0xFF, sizeof(int32_t) * n1, st);
-  cudaMemsetAsync(dhist, 0, sizeof(int) * (HISTO_LENGTH + 1), st);
-  k_tri_match<<<(nq + 7) / 8, 256, 0, st>>>(dq, nq, s1, s2, ditems2, dconst, only_stereo, check_ori, dm12, dbin, dhist);
-  k_tri_finish<<<1, 256, 0, st>>>(dq, nq, check_ori, dbin, dhist, dm12, dnm);
-  m->launches += 2;
-  cudaMemcpyAsync(matches12, dm12, sizeof(int32_t) * n1, cudaMemcpyDeviceToHost, st);
-  cudaMemcpyAsync(nmatches, dnm, sizeof(int), cudaMemcpyDeviceToHost, st);
-  if (!m->check(cudaStreamSynchronize(st), "search_for_triangulation")) return ORBX_E_CUDA;
-  return m->check(cudaGetLastError(), "search_for_triangulation launch") ? ORBX_OK : ORBX_E_CUDA;
+  if (!nmatches) return ORBX_E_INVALID;
+  orbm_tri_pair P = {k1, desc1, has_mp1, cam1, uright1, n1, fv1, k2, desc2, has_mp2, cam2, uright2, n2, fv2,
+                     F12s, epipoles, scale_factors2, level_sigma2_2, matches12, 0};
+  const int rc = orbm_search_for_triangulation_batch_host(m, &P, 1, nlevels, only_stereo, cam_enabled, check_ori);
+  *nmatches = P.nmatches;
+  return rc;
 }
 
 int orbm_compute_distinctive_descriptors_host(orbm_matcher* m, const uint8_t* desc, const int32_t* offsets, int n_points,

@@ -287,6 +287,38 @@ class ORBmatcher:
             m12.ctypes.data, m21.ctypes.data, C.byref(nm)))
         return nm.value, m12, m21
 
+    def SearchByBoW_batch(self, pairs, *, keyframe_pair: bool = False):
+        """pairs: sequence of (desc1, angle1, valid1, featvec1, desc2, angle2, valid2, featvec2) tuples, one per
+        independent (key frame, frame) pair; one library call, the ordered searches run concurrently on the
+        GPU.  Returns a list of (nmatches, matches12, matches21)."""
+        keep, structs, outs = [], (_lib.BowPair * len(pairs))(), []
+        c = lambda a, t: np.ascontiguousarray(a, dtype=t)
+
+        def fv(t):
+            arrs = [c(x, np.int32) for x in t]
+            if len(arrs[1]) != len(arrs[0]) + 1:
+                raise ValueError("feature vector: start must have n_nodes + 1 entries")
+            keep.extend(arrs)
+            return _lib.FeatVec(arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, len(arrs[0]))
+
+        for i, (d1, a1, v1, f1, d2, a2, v2, f2) in enumerate(pairs):
+            d1, d2 = c(d1, np.uint8).reshape(-1, 32), c(d2, np.uint8).reshape(-1, 32)
+            a1, a2 = c(a1, np.float32), c(a2, np.float32)
+            if len(a1) != len(d1) or len(a2) != len(d2):
+                raise ValueError("angle arrays must match the descriptor counts")
+            v1 = None if v1 is None else c(v1, np.int32)
+            v2 = None if v2 is None else c(v2, np.int32)
+            m12, m21 = np.empty(len(d1), np.int32), np.empty(len(d2), np.int32)
+            keep.extend([d1, d2, a1, a2, v1, v2])
+            outs.append((m12, m21))
+            structs[i] = _lib.BowPair(d1.ctypes.data, a1.ctypes.data, None if v1 is None else v1.ctypes.data, len(d1), fv(f1),
+                                      d2.ctypes.data, a2.ctypes.data, None if v2 is None else v2.ctypes.data, len(d2), fv(f2),
+                                      m12.ctypes.data, m21.ctypes.data, 0)
+        check_m(self._h, lib.orbm_search_by_bow_batch_host(self._h, structs, len(pairs), self.mfNNratio,
+                                                           int(self.mbCheckOrientation),
+                                                           self.TH_LOW - 1 if keyframe_pair else self.TH_LOW))
+        return [(structs[i].nmatches, outs[i][0], outs[i][1]) for i in range(len(pairs))]
+
     # -- SearchForTriangulation (src/ORBmatcher.cc:1364-1720) ---------------------------------------------------
     def SearchForTriangulation(self, k1, desc1, has_mp1, cam1, uright1, featvec1, k2, desc2, has_mp2, cam2, uright2, featvec2,
                                F12s, epipoles, scale_factors2, level_sigma2_2, bOnlyStereo: bool = False, vbCam=(True, True)):
@@ -339,3 +371,40 @@ class ORBmatcher:
         check_m(self._h, lib.orbm_compute_distinctive_descriptors_host(self._h, d.ctypes.data, off.ctypes.data, len(off) - 1,
                                                                        best.ctypes.data))
         return best
+
+    def SearchForTriangulation_batch(self, scenes, bOnlyStereo: bool = False, vbCam=(True, True)):
+        """scenes: sequence of dicts with the keys of synth.triangulation_scene plus "fv1"/"fv2" (CSR feature
+        vectors): one independent key-frame pair each, all with the same number of pyramid levels.  One
+        library call.  Returns a list of (nmatches, vMatches12)."""
+        c = lambda a, t: np.ascontiguousarray(a, dtype=t)
+        keep, structs, outs = [], (_lib.TriPair * len(scenes))(), []
+        nlevels = None
+
+        def fv(t):
+            arrs = [c(x, np.int32) for x in t]
+            keep.extend(arrs)
+            return _lib.FeatVec(arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, len(arrs[0]))
+
+        p = lambda a: a.ctypes.data
+        for i, sc in enumerate(scenes):
+            k1, k2 = c(sc["k1"], KP_DTYPE), c(sc["k2"], KP_DTYPE)
+            a = [k1, c(sc["d1"], np.uint8), c(sc["has_mp1"], np.int32), c(sc["cam1"], np.int32), c(sc["uright1"], np.float32),
+                 k2, c(sc["d2"], np.uint8), c(sc["has_mp2"], np.int32), c(sc["cam2"], np.int32), c(sc["uright2"], np.float32),
+                 c(sc["F12s"], np.float32), c(sc["epipoles"], np.float32), c(sc["scale_factors"], np.float32),
+                 c(sc["level_sigma2"], np.float32)]
+            if nlevels is None:
+                nlevels = len(a[12])
+            if len(a[12]) != nlevels or len(a[13]) != nlevels:
+                raise ValueError("all pairs must share the number of pyramid levels")
+            m12 = np.empty(len(k1), np.int32)
+            keep.extend(a)
+            outs.append(m12)
+            structs[i] = _lib.TriPair(p(a[0]), p(a[1]), p(a[2]), p(a[3]), p(a[4]), len(k1), fv(sc["fv1"]),
+                                      p(a[5]), p(a[6]), p(a[7]), p(a[8]), p(a[9]), len(k2), fv(sc["fv2"]),
+                                      p(a[10]), p(a[11]), p(a[12]), p(a[13]), p(m12), 0)
+        if not scenes:
+            return []
+        en = c([int(bool(v)) for v in vbCam], np.int32)
+        check_m(self._h, lib.orbm_search_for_triangulation_batch_host(self._h, structs, len(scenes), nlevels, int(bOnlyStereo),
+                                                                      p(en), int(self.mbCheckOrientation)))
+        return [(structs[i].nmatches, outs[i]) for i in range(len(scenes))]

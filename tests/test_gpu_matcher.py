@@ -447,3 +447,45 @@ def test_compute_distinctive_descriptors_vs_oracle(M, O):
     # all-identical set: every median is 0, the first descriptor wins
     same = np.repeat(random_descriptors(1, 3), 9, axis=0)
     assert M.ComputeDistinctiveDescriptors(same, [0, 9])[0] == 0
+
+
+def test_search_by_bow_batch_vs_oracle(O):
+    """A batch of independent (key frame, frame) pairs of different sizes in one call."""
+    from multi_orb_slam_b200.matcher import ORBmatcher
+    from multi_orb_slam_b200.synth import bow_scene, feature_vector
+    m = ORBmatcher(0.7, True)
+    pairs, refs = [], []
+    rng = np.random.default_rng(6)
+    for p, (n1, n2, nodes) in enumerate([(1000, 1100, 100), (50, 40, 5), (2000, 1500, 64), (0, 30, 4), (700, 700, 2), (300, 0, 9)]
+                                        + [(int(a), int(b), 50) for a, b in rng.integers(200, 1500, (10, 2))]):
+        sc = bow_scene(max(n1, 1), max(n2, 1), nodes, 40 + p)
+        d1, a1, node1 = sc["d1"][:n1], sc["a1"][:n1], sc["node1"][:n1]
+        d2, a2, node2 = sc["d2"][:n2], sc["a2"][:n2], sc["node2"][:n2]
+        v1 = (rng.random(n1) < 0.85).astype(np.int32) if p % 2 else None
+        v2 = (rng.random(n2) < 0.9).astype(np.int32) if p % 3 == 0 else None
+        fv1, fv2 = feature_vector(node1), feature_vector(np.where(node2 % 13 == 1, -1, node2))
+        pairs.append((d1, a1, v1, fv1, d2, a2, v2, fv2))
+        refs.append(O.search_by_bow(d1, a1, v1, fv1, d2, a2, v2, fv2, 0.7, True, 50))
+    got = m.SearchByBoW_batch(pairs)
+    assert len(got) == len(refs)
+    for p, ((nm, m12, m21), (rn, rm12, rm21)) in enumerate(zip(got, refs)):
+        assert nm == rn and np.array_equal(m12, rm12) and np.array_equal(m21, rm21), f"pair {p}"
+    assert sum(g[0] for g in got) > 500
+    assert m.SearchByBoW_batch([]) == []
+
+
+def test_search_for_triangulation_batch_vs_oracle(O):
+    from multi_orb_slam_b200.matcher import ORBmatcher
+    from multi_orb_slam_b200.synth import feature_vector, triangulation_scene
+    m = ORBmatcher(0.6, True)
+    scenes, refs = [], []
+    for p, (n1, n2, nodes) in enumerate([(1500, 1600, 80), (40, 50, 3), (2000, 900, 30), (600, 2500, 4)] + [(800, 800, 50)] * 8):
+        sc = triangulation_scene(n1, n2, nodes, 60 + p)
+        sc["fv1"], sc["fv2"] = feature_vector(sc["node1"]), feature_vector(np.where(sc["node2"] % 7 == 3, -1, sc["node2"]))
+        scenes.append(sc)
+        refs.append(O.search_for_triangulation(sc, sc["fv1"], sc["fv2"], False, (1, 1), True))
+    got = m.SearchForTriangulation_batch(scenes)
+    for p, ((nm, m12), (rn, rm12)) in enumerate(zip(got, refs)):
+        assert nm == rn and np.array_equal(m12, rm12), f"pair {p}"
+    assert sum(g[0] for g in got) > 300
+    assert m.SearchForTriangulation_batch([]) == []
