@@ -453,7 +453,8 @@ def main():
     bf_pairs = float(nbf) * nbf * world / (bf_ms * 1e-3)
     bf_accepted = int((bf_idx >= 0).sum().item())
 
-    widened = widened_rows_leg(matcher, local_rank, not args.no_cpu_baseline) if rank == 0 else None
+    # single-GPU runs only (like cpu_baseline): small latency-bound calls, nothing to shard
+    widened = widened_rows_leg(matcher, local_rank, not args.no_cpu_baseline) if world == 1 else None
 
     if rank != 0:
         if world > 1:
@@ -516,7 +517,8 @@ def main():
                        "roofline": {"bound": "popc", "achieved": bf_pairs, "peak": popc_peak * world,
                                     "unit": "pairs/s", "frac": bf_pairs / (popc_peak * world),
                                     "peak_source": f"148 SM x 16 POPC/clk x {sm_max:.0f} MHz / 8 words"}}
-    out["widened_rows"] = widened
+    if widened is not None:
+        out["widened_rows"] = widened
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         n_rig = min(args.cpu_rig_frames, F)

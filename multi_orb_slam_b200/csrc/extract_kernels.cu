@@ -9,6 +9,7 @@
 // Batch layout: every kernel covers ALL frames of a batch in one launch (blockIdx.y or .z =
 // frame) so the small per-frame work fills the 148 SMs.
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -815,7 +816,9 @@ void launch_fast(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, const uint8_
 int octree_smem_keys(const OrbGeom& g) {
   int m = 0;
   for (int l = 0; l < g.nlevels; ++l) m = max(m, g.lv[l].key_cap);
-  return min(m, 6144);  // 36 KB of keys + labels keeps ~3 CTAs resident per SM
+  int cap_keys = 6144;  // 36 KB of keys + labels keeps ~3 CTAs resident per SM
+  if (const char* e = getenv("ORB_OT_SMEM_KEYS")) cap_keys = max(256, atoi(e));  // tuning knob (levels above it use HBM)
+  return min(m, cap_keys);
 }
 
 size_t octree_smem_bytes(const OrbGeom& g) {
