@@ -453,6 +453,33 @@ def main():
     bf_pairs = float(nbf) * nbf * world / (bf_ms * 1e-3)
     bf_accepted = int((bf_idx >= 0).sum().item())
 
+    # ---- the one collective of the path (config 5): all-gather of per-camera descriptor blocks ---
+    allgather = None
+    if world > 1:
+        from multi_orb_slam_b200.dist import allgather_camera_blocks
+        blk = (counts[0][None], kps[0][None], desc[0][None])  # this rank's camera stream: [1, F, ...]
+
+        def ag_step():
+            allgather_camera_blocks(*blk, n_cams=world)
+
+        for _ in range(3):
+            ag_step()
+        with torch.cuda.stream(torch.cuda.current_stream()):
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(10):
+                ag_step()
+            a1.record()
+            torch.cuda.synchronize()
+        ag = torch.tensor([a0.elapsed_time(a1) / 10], dtype=torch.float64, device=dev)
+        dist.all_reduce(ag, op=dist.ReduceOp.MAX)
+        per_rank = sum(t.numel() * t.element_size() for t in blk)
+        allgather = {"workload": f"NCCL all_gather_into_tensor of one camera stream per rank ({F} frames: counts, keypoints, "
+                                 "descriptors), the exchange before cross-camera matching",
+                     "ms": float(ag.item()), "bytes_per_rank": per_rank,
+                     "algbw_GBps": per_rank * (world - 1) / (float(ag.item()) * 1e-3) / 1e9}
+
     # single-GPU runs only (like cpu_baseline): small latency-bound calls, nothing to shard
     widened = widened_rows_leg(matcher, local_rank, not args.no_cpu_baseline) if world == 1 else None
 
@@ -519,6 +546,8 @@ def main():
                                     "peak_source": f"148 SM x 16 POPC/clk x {sm_max:.0f} MHz / 8 words"}}
     if widened is not None:
         out["widened_rows"] = widened
+    if allgather is not None:
+        out["allgather"] = allgather
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         n_rig = min(args.cpu_rig_frames, F)
