@@ -282,6 +282,23 @@ int orbm_assign_features_to_grid_device(orbm_matcher* m, int n_frames, int cap, 
                                         const int32_t* d_counts, orbm_bounds bounds, int32_t* d_cell_start,
                                         uint16_t* d_items);
 
+/* ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, CalibMatrix, th) (src/ORBmatcher.cc:1986-2190,
+ * called from LocalMapping::SearchInNeighbors, src/LocalMapping.cc:741,772), the search part: for every map point and
+ * both cameras of the key frame, best_idx[2*i + cam] = the key-frame feature the point fuses with, or -1; *n_fused = number
+ * of entries >= 0 (= nFused).  The side effects (:2160-2186: Replace / AddObservation / AddMapPoint, applied in map-point
+ * order, camera 0 before camera 1) do not feed back into the search and stay with the caller.
+ * Key frame: concatenated keypoints (mvKeysUn_total), descriptor per global index, kf_uright (mvuRight_total), kf_cam
+ * (keypoint_to_cam, NULL = one camera), bounds (mnMinX..), mvScaleFactors, mvInvLevelSigma2, mfLogScaleFactor, camera
+ * (fx, fy, cx, cy, mbf), Tcw 4x4 row-major, Ow = {GetCameraCenter(), GetCameraCenter_cam2()} (6 floats), calib 4x3.
+ * Map points: mp_valid[i] = pMP && !isBad() && !IsInKeyFrame(pKF); GetWorldPos, GetNormal,
+ * Get{Max,Min}DistanceInvariance, mfMaxDistance, GetDescriptor. */
+int orbm_fuse_host(orbm_matcher* m, const orbx_keypoint* kf_k, const uint8_t* kf_desc, const float* kf_uright,
+                   const int32_t* kf_cam, int n_kf, orbm_bounds b, const float* scale_factors, const float* inv_level_sigma2,
+                   int nlevels, float log_scale_factor, orbm_camera cam, const float* Tcw, const float* Ow, const float* calib,
+                   const int32_t* mp_valid, const float* mp_xyz, const float* mp_normal, const float* mp_max_dist,
+                   const float* mp_min_dist, const float* mp_max_d, const uint8_t* mp_desc, int n_mp, float th,
+                   int32_t* best_idx, int* n_fused);
+
 /* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:325-438), the arithmetic part (:381-424), batched over
  * map points: the observed descriptors of point p (vDescriptors, in std::map<KeyFrame*,size_t> iteration order, bad
  * key frames left out) are rows offsets[p] .. offsets[p+1]-1 of desc (offsets[0] = 0).  best_idx[p] = BestIdx relative

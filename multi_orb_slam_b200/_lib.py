@@ -112,6 +112,8 @@ _SIGS = {
                                                 _vp, _vp, _vp, _vp, _i, _i, _vp, C.POINTER(_i)]),
     "orbm_search_by_bow_host": (_i, [_vp, _vp, _vp, _vp, _i, FeatVec, _vp, _vp, _vp, _i, FeatVec, _f, _i, _i, _vp, _vp,
                                     C.POINTER(_i)]),
+    "orbm_fuse_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, Bounds, _vp, _vp, _i, _f, Camera, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                           _vp, _vp, _i, _f, _vp, C.POINTER(_i)]),
     "orbm_compute_distinctive_descriptors_host": (_i, [_vp, _vp, _vp, _i, _vp]),
     "orbm_undistort_keypoints_device": (_i, [_vp, _i, _i, _vp, _vp, _f, _f, _f, _f, _vp, _vp]),
     "orbm_undistort_keypoints_host": (_i, [_vp, _vp, _i, _f, _f, _f, _f, _vp, _vp]),

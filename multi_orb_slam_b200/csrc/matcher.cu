@@ -1099,6 +1099,64 @@ __global__ void __launch_bounds__(256) k_query_candidates(const orbx_keypoint* _
   if (lane == 0 && count_only) row_cnt[i] = cnt;
 }
 
+// ORBmatcher::Fuse (:1986-2190), the search of one (map point, camera) query: window query at levels
+// [predicted-1, predicted], reprojection chi-square gate (:2106-2131: 7.8 with a right coordinate, 5.99
+// without), strict-< best Hamming distance in traversal order (:2139-2143), accepted when <= TH_LOW.
+// Nothing here depends on other queries, so a warp per query and no resolve pass.
+struct LevelTable {
+  float v[ORBX_MAX_LEVELS];
+};
+
+__global__ void __launch_bounds__(256) k_fuse_match(const orbx_keypoint* __restrict__ k, const uint8_t* __restrict__ desc,
+                                                    const float* __restrict__ u_right, orbm_bounds b,
+                                                    const int* __restrict__ grid_start,
+                                                    const uint16_t* __restrict__ grid_items, int n_kps,
+                                                    const ProjQuery* __restrict__ q, const uint8_t* __restrict__ q_desc,
+                                                    int nq, LevelTable inv_sigma2, int32_t* __restrict__ best_idx) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= nq) return;
+  const ProjQuery p = q[i];
+  GridView gv;
+  gv.start = grid_start + (size_t)p.cam * (GRID_CELLS + 1);
+  gv.items = grid_items + (size_t)p.cam * n_kps;
+  gv.min_x = b.min_x;
+  gv.min_y = b.min_y;
+  gv.inv_w = __fdiv_rn((float)GRID_COLS, __fsub_rn(b.max_x, b.min_x));
+  gv.inv_h = __fdiv_rn((float)GRID_ROWS, __fsub_rn(b.max_y, b.min_y));
+  const uint4* qd = reinterpret_cast<const uint4*>(q_desc + (size_t)p.src * 32);
+  const uint4 qa = __ldg(qd), qb = __ldg(qd + 1);
+  uint32_t best = 0xFFFFFFFFu;  // dist << 16 | traversal position
+  int my_idx = -1, cnt = 0;
+  grid_query(gv, k, p.u, p.v, p.radius, p.min_level, p.max_level, [&](bool ok, int idx) {
+    if (ok) {
+      const orbx_keypoint kp = k[idx];
+      const float ex = __fsub_rn(p.u, kp.x), ey = __fsub_rn(p.v, kp.y);
+      float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+      const float kpr = u_right[idx];
+      double limit = 5.99;
+      if (kpr >= 0) {
+        const float er = __fsub_rn(p.ur, kpr);
+        e2 = __fadd_rn(e2, __fmul_rn(er, er));
+        limit = 7.8;
+      }
+      if ((double)__fmul_rn(e2, inv_sigma2.v[kp.octave]) > limit) ok = false;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const uint4* tp = reinterpret_cast<const uint4*>(desc + (size_t)idx * 32);
+      const uint32_t key = (uint32_t)hamming256(qa, qb, __ldg(tp), __ldg(tp + 1)) << 16 |
+                           (uint32_t)(cnt + __popc(m & ((1u << lane) - 1u)));
+      if (key < best) { best = key; my_idx = idx; }
+    }
+    cnt += __popc(m);
+  });
+  const uint32_t gb = __reduce_min_sync(0xffffffffu, best);
+  const unsigned owner = __ballot_sync(0xffffffffu, best == gb && my_idx >= 0);
+  const int idx = __shfl_sync(0xffffffffu, my_idx, owner ? __ffs(owner) - 1 : 0);
+  if (lane == 0) best_idx[2 * p.src + p.cam] = (gb != 0xFFFFFFFFu && (int)(gb >> 16) <= TH_LOW) ? idx : -1;
+}
+
 // Ordered resolve, best match only (:3558-3637, :3886-3934): queries ascending; candidates that
 // already hold a point are skipped (any_point_blocks: a15 blocks on any held point, a14 only on
 // points with Observations()>0); accept best <= th_dist; rotation histogram + three maxima.
@@ -2191,6 +2249,128 @@ int orbm_search_by_projection_sim3_host(orbm_matcher* m, const orbx_keypoint* kf
   }
   return run_projected(m, kf_k, kf_desc, nullptr, kf_cam, 2, n_kf, b, q, mp_desc, n_mp, TH_LOW, 0, 1, matched, nullptr,
                        nmatches);
+}
+
+int orbm_fuse_host(orbm_matcher* m, const orbx_keypoint* kf_k, const uint8_t* kf_desc, const float* kf_uright,
+                   const int32_t* kf_cam, int n_kf, orbm_bounds b, const float* scale_factors, const float* inv_level_sigma2,
+                   int nlevels, float log_scale_factor, orbm_camera cam, const float* Tcw, const float* Ow, const float* calib,
+                   const int32_t* mp_valid, const float* mp_xyz, const float* mp_normal, const float* mp_max_dist,
+                   const float* mp_min_dist, const float* mp_max_d, const uint8_t* mp_desc, int n_mp, float th,
+                   int32_t* best_idx, int* n_fused) {
+  if (!m || !scale_factors || !inv_level_sigma2 || !Tcw || !Ow || !calib || !best_idx || !n_fused || n_kf < 0 || n_kf > 65535 ||
+      n_mp < 0 || nlevels < 1 || nlevels > ORBX_MAX_LEVELS || (n_kf && (!kf_k || !kf_desc || !kf_uright)) ||
+      (n_mp && (!mp_valid || !mp_xyz || !mp_normal || !mp_max_dist || !mp_min_dist || !mp_max_d || !mp_desc)))
+    return ORBX_E_INVALID;
+  *n_fused = 0;
+  for (int i = 0; i < 2 * n_mp; ++i) best_idx[i] = -1;
+  if (n_kf == 0 || n_mp == 0) return ORBX_OK;
+  for (int i = 0; i < n_kf; ++i)
+    if (kf_k[i].octave < 0 || kf_k[i].octave >= nlevels) { m->err = "key frame: octave out of range"; return ORBX_E_INVALID; }
+  // host-side projection into both cameras (:1996-2071), float evaluation order of the cv::Mat expressions
+  float Rcam21[9], tcam21[3];
+  {
+    double S[9];
+    for (int i = 0; i < 9; ++i) S[i] = calib[i];
+    double d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
+    d = 1. / d;  // cv::Mat::inv() of a 3x3 CV_32F matrix: closed form in double
+    Rcam21[0] = (float)((S[4] * S[8] - S[5] * S[7]) * d); Rcam21[1] = (float)((S[2] * S[7] - S[1] * S[8]) * d);
+    Rcam21[2] = (float)((S[1] * S[5] - S[2] * S[4]) * d); Rcam21[3] = (float)((S[5] * S[6] - S[3] * S[8]) * d);
+    Rcam21[4] = (float)((S[0] * S[8] - S[2] * S[6]) * d); Rcam21[5] = (float)((S[2] * S[3] - S[0] * S[5]) * d);
+    Rcam21[6] = (float)((S[3] * S[7] - S[4] * S[6]) * d); Rcam21[7] = (float)((S[1] * S[6] - S[0] * S[7]) * d);
+    Rcam21[8] = (float)((S[0] * S[4] - S[1] * S[3]) * d);
+  }
+  mat3_mul_vec_add(Rcam21, 3, calib + 9, nullptr, -1.f, tcam21);
+  const float tcw[3] = {Tcw[3], Tcw[7], Tcw[11]};
+  // camera 2 (:2031): ((Rcam21*Rcw)*p3Dw + Rcam21*tcw) + tcam21, products materialised by cv::MatExpr
+  float M[9], Rt[3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      float acc = 0.f;
+      for (int kk = 0; kk < 3; ++kk) acc += Rcam21[i * 3 + kk] * Tcw[kk * 4 + j];
+      M[i * 3 + j] = acc;
+    }
+  mat3_mul_vec_add(Rcam21, 3, tcw, nullptr, 1.f, Rt);
+  std::vector<ProjQuery> q;
+  q.reserve(2 * (size_t)n_mp);
+  for (int i = 0; i < n_mp; ++i) {
+    if (!mp_valid[i]) continue;
+    const float* p3Dw = mp_xyz + 3 * i;
+    for (int c = 0; c < 2; ++c) {
+      float p3Dc[3];
+      if (c == 0) {
+        mat3_mul_vec_add(Tcw, 4, p3Dw, tcw, 1.f, p3Dc);
+      } else {
+        float m1[3];
+        mat3_mul_vec_add(M, 3, p3Dw, nullptr, 1.f, m1);
+        for (int kk = 0; kk < 3; ++kk) p3Dc[kk] = (m1[kk] + Rt[kk]) + tcam21[kk];
+      }
+      if (p3Dc[2] < 0.0f) continue;
+      const float invz = 1 / p3Dc[2];
+      const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
+      const float u = cam.fx * x + cam.cx, v = cam.fy * y + cam.cy;
+      if (!(u >= b.min_x && u < b.max_x && v >= b.min_y && v < b.max_y)) continue;
+      float PO[3];
+      double n2 = 0, dotn = 0;
+      for (int kk = 0; kk < 3; ++kk) {
+        PO[kk] = p3Dw[kk] - Ow[3 * c + kk];
+        n2 += (double)PO[kk] * (double)PO[kk];
+        dotn += (double)PO[kk] * (double)mp_normal[3 * i + kk];
+      }
+      const float dist3D = (float)std::sqrt(n2);
+      if (dist3D < mp_min_dist[i] || dist3D > mp_max_dist[i]) continue;
+      if (dotn < 0.5 * dist3D) continue;
+      const float ratio = mp_max_d[i] / dist3D;
+      int lvl = (int)std::ceil(std::log(ratio) / log_scale_factor);
+      if (lvl < 0) lvl = 0;
+      else if (lvl >= nlevels) lvl = nlevels - 1;
+      ProjQuery p;
+      p.u = u; p.v = v;
+      p.radius = th * scale_factors[lvl];
+      p.ur = u - cam.mbf * invz;
+      p.use_ur = 1; p.angle = 0.f;
+      p.min_level = lvl - 1; p.max_level = lvl;  // the filter of :2100-2101 folded into the query
+      p.cam = c; p.src = i; p.obs = 1;
+      q.push_back(p);
+    }
+  }
+  const int nq = (int)q.size();
+  if (nq == 0) return ORBX_OK;
+  cudaSetDevice(m->device);
+  cudaStream_t st = m->stream;
+  uint8_t* fb = m->scratch<uint8_t>(8, (size_t)n_kf * (32 + sizeof(orbx_keypoint) + 8) + 256);
+  uint8_t* qb = m->scratch<uint8_t>(9, (size_t)n_mp * (32 + 8) + (size_t)nq * sizeof(ProjQuery) + 256);
+  int* gstart = m->scratch<int>(4, (size_t)2 * (GRID_CELLS + 1));
+  uint16_t* gitems = m->scratch<uint16_t>(5, (size_t)2 * n_kf);
+  if (!fb || !qb || !gstart || !gitems) return ORBX_E_CUDA;
+  uint8_t* dd = fb;
+  orbx_keypoint* dk = reinterpret_cast<orbx_keypoint*>(dd + (size_t)n_kf * 32);
+  float* dur = reinterpret_cast<float*>(dk + n_kf);
+  int32_t* dcam = reinterpret_cast<int32_t*>(dur + n_kf);
+  uint8_t* dmd = qb;
+  int32_t* dbest = reinterpret_cast<int32_t*>(dmd + (size_t)n_mp * 32);
+  ProjQuery* dq = reinterpret_cast<ProjQuery*>(dbest + 2 * (size_t)n_mp);
+  cudaMemcpyAsync(dd, kf_desc, (size_t)n_kf * 32, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dk, kf_k, sizeof(orbx_keypoint) * n_kf, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dur, kf_uright, sizeof(float) * n_kf, cudaMemcpyHostToDevice, st);
+  if (kf_cam) cudaMemcpyAsync(dcam, kf_cam, sizeof(int32_t) * n_kf, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dmd, mp_desc, (size_t)n_mp * 32, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dq, q.data(), sizeof(ProjQuery) * nq, cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(dbest, 0xFF, sizeof(int32_t) * 2 * (size_t)n_mp, st);
+  for (int c = 0; c < 2; ++c) {
+    k_build_grid<<<1, 256, 0, st>>>(dk, nullptr, n_kf, n_kf, b, gstart + (size_t)c * (GRID_CELLS + 1), gitems + (size_t)c * n_kf,
+                                    kf_cam ? dcam : nullptr, c);
+    m->launches++;
+  }
+  LevelTable lt;
+  for (int i = 0; i < ORBX_MAX_LEVELS; ++i) lt.v[i] = i < nlevels ? inv_level_sigma2[i] : 0.f;
+  k_fuse_match<<<(nq + 7) / 8, 256, 0, st>>>(dk, dd, dur, b, gstart, gitems, n_kf, dq, dmd, nq, lt, dbest);
+  m->launches++;
+  cudaMemcpyAsync(best_idx, dbest, sizeof(int32_t) * 2 * (size_t)n_mp, cudaMemcpyDeviceToHost, st);
+  if (!m->check(cudaStreamSynchronize(st), "fuse")) return ORBX_E_CUDA;
+  int nf = 0;
+  for (int i = 0; i < 2 * n_mp; ++i) nf += best_idx[i] >= 0;
+  *n_fused = nf;
+  return m->check(cudaGetLastError(), "fuse launch") ? ORBX_OK : ORBX_E_CUDA;
 }
 
 #pragma GCC visibility pop

@@ -768,4 +768,108 @@ int om_search_by_projection_sim3(const oo_keypoint* kf_k, const uint8_t* kf_desc
   return nmatches;
 }
 
+// ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, CalibMatrix, th) (src/ORBmatcher.cc:1986-2190),
+// the search part: for every map point and both cameras of the key frame, the key-frame feature it fuses with
+// (best_idx[2*i + cam], -1 = none).  The side effects (:2160-2186: Replace / AddObservation / AddMapPoint, in map-point
+// order, camera 0 before camera 1) do not feed back into the search and stay with the caller; nFused = number of
+// entries >= 0.
+//  key frame: concatenated keypoints (mvKeysUn_total), descriptors per global index, uright (mvuRight_total), kf_cam
+//    (keypoint_to_cam), bounds (mnMinX..), mvScaleFactors, mvInvLevelSigma2, mfLogScaleFactor, fx/fy/cx/cy/mbf,
+//    Tcw (4x4 row-major), Ow = {GetCameraCenter(), GetCameraCenter_cam2()} (6 floats), calib 4x3;
+//  map points: mp_valid[i] = pMP && !isBad() && !IsInKeyFrame(pKF); world position, normal, distance invariance
+//    limits, mfMaxDistance, descriptor.
+int om_fuse(const oo_keypoint* kf_k, const uint8_t* kf_desc, const float* kf_uright, const int32_t* kf_cam, int n_kf,
+            om_bounds b, const float* scale_factors, const float* inv_level_sigma2, int nlevels, float log_scale_factor,
+            om_camera cam, const float* Tcw, const float* Ow, const float* calib, const int32_t* mp_valid,
+            const float* mp_xyz, const float* mp_normal, const float* mp_max_dist, const float* mp_min_dist,
+            const float* mp_max_d, const uint8_t* mp_desc, int n_mp, float th, int32_t* best_idx) {
+  // Rcam21 = Rcam12.inv() (3x3 CV_32F: closed form in double), tcam21 = -Rcam21 * tcam12   (:1996-2004)
+  float Rcam21[9], tcam21[3];
+  {
+    double S[9];
+    for (int i = 0; i < 9; ++i) S[i] = calib[i];
+    double d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
+    d = 1. / d;
+    Rcam21[0] = (float)((S[4] * S[8] - S[5] * S[7]) * d); Rcam21[1] = (float)((S[2] * S[7] - S[1] * S[8]) * d);
+    Rcam21[2] = (float)((S[1] * S[5] - S[2] * S[4]) * d); Rcam21[3] = (float)((S[5] * S[6] - S[3] * S[8]) * d);
+    Rcam21[4] = (float)((S[0] * S[8] - S[2] * S[6]) * d); Rcam21[5] = (float)((S[2] * S[3] - S[0] * S[5]) * d);
+    Rcam21[6] = (float)((S[3] * S[7] - S[4] * S[6]) * d); Rcam21[7] = (float)((S[1] * S[6] - S[0] * S[7]) * d);
+    Rcam21[8] = (float)((S[0] * S[4] - S[1] * S[3]) * d);
+  }
+  mat3_mul_vec_add(Rcam21, 3, calib + 9, nullptr, -1.f, tcam21);
+  const float tcw[3] = {Tcw[3], Tcw[7], Tcw[11]};
+  // camera 2 (:2031): p3Dc = Rcam21*Rcw*p3Dw + Rcam21*tcw + tcam21 = ((M*p3Dw) + (Rcam21*tcw)) + tcam21 with the 3x3
+  // product M = Rcam21*Rcw and both matrix-vector products materialised (cv::MatExpr), all float32 left to right
+  float M[9], Rt[3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      float acc = 0.f;
+      for (int k = 0; k < 3; ++k) acc += Rcam21[i * 3 + k] * Tcw[k * 4 + j];
+      M[i * 3 + j] = acc;
+    }
+  mat3_mul_vec_add(Rcam21, 3, tcw, nullptr, 1.f, Rt);
+  SoA s(kf_k, n_kf);
+  Grid2 grids(s.x.data(), s.y.data(), s.oct.data(), kf_cam, n_kf, b);
+  int nFused = 0;
+  std::vector<int> cand;
+  for (int i = 0; i < n_mp; ++i) {
+    best_idx[2 * i] = best_idx[2 * i + 1] = -1;
+    if (!mp_valid[i]) continue;
+    const float* p3Dw = mp_xyz + 3 * i;
+    for (int c = 0; c < 2; ++c) {
+      float p3Dc[3];
+      if (c == 0) {
+        mat3_mul_vec_add(Tcw, 4, p3Dw, tcw, 1.f, p3Dc);
+      } else {
+        float m1[3];
+        mat3_mul_vec_add(M, 3, p3Dw, nullptr, 1.f, m1);
+        for (int k = 0; k < 3; ++k) p3Dc[k] = (m1[k] + Rt[k]) + tcam21[k];
+      }
+      if (p3Dc[2] < 0.0f) continue;
+      const float invz = 1 / p3Dc[2];
+      const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
+      const float u = cam.fx * x + cam.cx, v = cam.fy * y + cam.cy;
+      if (!(u >= b.min_x && u < b.max_x && v >= b.min_y && v < b.max_y)) continue;  // KeyFrame::IsInImage
+      const float ur = u - cam.mbf * invz;
+      float PO[3];
+      double n2 = 0, dotn = 0;
+      for (int k = 0; k < 3; ++k) {
+        PO[k] = p3Dw[k] - Ow[3 * c + k];
+        n2 += (double)PO[k] * (double)PO[k];
+        dotn += (double)PO[k] * (double)mp_normal[3 * i + k];
+      }
+      const float dist3D = (float)std::sqrt(n2);  // cv::norm
+      if (dist3D < mp_min_dist[i] || dist3D > mp_max_dist[i]) continue;
+      if (dotn < 0.5 * dist3D) continue;
+      const float ratio = mp_max_d[i] / dist3D;  // MapPoint::PredictScale (src/MapPoint.cc:584-600)
+      int lvl = (int)std::ceil(std::log(ratio) / log_scale_factor);
+      if (lvl < 0) lvl = 0;
+      else if (lvl >= nlevels) lvl = nlevels - 1;
+      const float radius = th * scale_factors[lvl];
+      const Grid& g = c == 1 ? grids.g1 : grids.g0;
+      g.query(u, v, radius, -1, -1, cand);
+      int bestDist = 256, bestIdx = -1;
+      for (int idx : cand) {
+        const oo_keypoint& kp = kf_k[idx];
+        const int kpLevel = kp.octave;
+        if (kpLevel < lvl - 1 || kpLevel > lvl) continue;
+        if (kf_uright[idx] >= 0) {
+          const float ex = u - kp.x, ey = v - kp.y, er = ur - kf_uright[idx];
+          const float e2 = ex * ex + ey * ey + er * er;
+          if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;
+        } else {
+          const float ex = u - kp.x, ey = v - kp.y;
+          const float e2 = ex * ex + ey * ey;
+          if (e2 * inv_level_sigma2[kpLevel] > 5.99) continue;
+        }
+        const int dd = om_distance(mp_desc + (size_t)i * 32, kf_desc + (size_t)idx * 32);
+        if (dd < bestDist) { bestDist = dd; bestIdx = idx; }
+      }
+      if (bestIdx < 0) continue;
+      if (bestDist <= TH_LOW) { best_idx[2 * i + c] = bestIdx; nFused++; }
+    }
+  }
+  return nFused;
+}
+
 }  // extern "C"

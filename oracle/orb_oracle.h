@@ -191,6 +191,15 @@ int om_search_for_triangulation(const oo_keypoint* k1, const uint8_t* d1, const 
                                 const float* level_sigma2_2, int only_stereo, const int32_t* cam_enabled, int check_ori,
                                 int32_t* matches12);
 
+// ORBmatcher::Fuse(KeyFrame*, vpMapPoints, CalibMatrix, th) (src/ORBmatcher.cc:1986-2190), the search part:
+// best_idx[2*i + cam] = key-frame feature that map point i fuses with in camera cam, or -1; returns nFused.
+// Ow = {GetCameraCenter(), GetCameraCenter_cam2()}.  The Replace/AddObservation side effects stay with the caller.
+int om_fuse(const oo_keypoint* kf_k, const uint8_t* kf_desc, const float* kf_uright, const int32_t* kf_cam, int n_kf,
+            om_bounds b, const float* scale_factors, const float* inv_level_sigma2, int nlevels, float log_scale_factor,
+            om_camera cam, const float* Tcw, const float* Ow, const float* calib, const int32_t* mp_valid,
+            const float* mp_xyz, const float* mp_normal, const float* mp_max_dist, const float* mp_min_dist,
+            const float* mp_max_d, const uint8_t* mp_desc, int n_mp, float th, int32_t* best_idx);
+
 // ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:3948-3989) on bin counts.
 void om_three_maxima(const int* counts, int L, int* ind1, int* ind2, int* ind3);
 

@@ -489,3 +489,43 @@ def test_search_for_triangulation_batch_vs_oracle(O):
         assert nm == rn and np.array_equal(m12, rm12), f"pair {p}"
     assert sum(g[0] for g in got) > 300
     assert m.SearchForTriangulation_batch([]) == []
+
+
+# ---- Fuse(KeyFrame*, vpMapPoints, CalibMatrix, th) (src/ORBmatcher.cc:1986-2190) ----------------
+@pytest.mark.parametrize("th,seed", [(3.0, 21), (6.0, 22)])
+def test_fuse_vs_oracle(O, th, seed):
+    from multi_orb_slam_b200._lib import Camera
+    from multi_orb_slam_b200.matcher import Frame, ORBmatcher
+    s = _rig_scene(O, seed, 2500, (0, 0, 0))
+    rng = s["rng"]
+    n, nmp = s["n"], len(s["last_xyz"])
+    sf, _, sigma2, inv_sigma2 = O.extractor("port").scale_tables()
+    Tcw = s["Tcw"]
+    xyz = s["last_xyz"].astype(np.float64)
+    R, t = Tcw[:3, :3].astype(np.float64), Tcw[:3, 3].astype(np.float64)
+    Ow0 = -R.T @ t
+    R12, t12 = CALIB[:3].astype(np.float64), CALIB[3].astype(np.float64)
+    Ow1 = Ow0 + R.T @ t12  # centre of camera 2 in the world
+    Ow = np.stack([Ow0, Ow1])
+    dist = np.linalg.norm(xyz - Ow0, axis=1)
+    normal = (xyz - Ow0) / dist[:, None] + rng.normal(0, 0.3, (nmp, 3))
+    normal /= np.linalg.norm(normal, axis=1)[:, None]
+    max_d = (dist * rng.uniform(0.8, 4.0, nmp)).astype(np.float32)
+    kf_max, kf_min = (1.2 * max_d).astype(np.float32), (0.8 * max_d / 1.2 ** 7).astype(np.float32)
+    valid = (rng.random(nmp) < 0.9).astype(np.int32)
+    log_sf = float(np.log(np.float32(1.2)))
+    rn, rbest = O.fuse(s["cur_k"], s["cur_d"], s["ur"], s["cur_cam"], (0, 640, 0, 480), sf, inv_sigma2, log_sf, CAM, Tcw, Ow, CALIB,
+                       valid, xyz, normal, kf_max, kf_min, max_d, s["last_desc"], th)
+    F = Frame(s["cur_k"], s["cur_d"], 640, 480, mvuRight=s["ur"], mvScaleFactors=sf)
+    m = ORBmatcher(0.6, True)
+    gn, gbest = m.Fuse(F, s["cur_cam"], Camera(*CAM), log_sf, inv_sigma2, Tcw, Ow, CALIB, valid, xyz, normal, kf_max, kf_min, max_d,
+                       s["last_desc"], th)
+    assert gn == rn and np.array_equal(gbest, rbest)
+    assert rn > 100 and (rbest[valid == 0] == -1).all()
+    # both chi-square branches were exercised (with and without a right coordinate)
+    hit = rbest[rbest >= 0]
+    assert (s["ur"][hit] >= 0).any() and (s["ur"][hit] < 0).any()
+    # nothing to fuse
+    gn, gbest = m.Fuse(F, s["cur_cam"], Camera(*CAM), log_sf, inv_sigma2, Tcw, Ow, CALIB, np.zeros(nmp, np.int32), xyz, normal,
+                       kf_max, kf_min, max_d, s["last_desc"], th)
+    assert gn == 0 and (gbest == -1).all()
