@@ -299,6 +299,16 @@ int orbm_fuse_host(orbm_matcher* m, const orbx_keypoint* kf_k, const uint8_t* kf
                    const float* mp_min_dist, const float* mp_max_d, const uint8_t* mp_desc, int n_mp, float th,
                    int32_t* best_idx, int* n_fused);
 
+/* ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, vpPoints, vLoopMPCams, th, vpReplacePoint, CalibMatrix)
+ * (src/ORBmatcher.cc:2211-2441, called from LoopClosing::SearchAndFuse, src/LoopClosing.cc:841), the search part, same
+ * outputs as orbm_fuse_host.  Scw = 4x4 row-major Sim3 (s*R | t); no reprojection gate in this overload;
+ * mp_valid[i] = !isBad() && !spAlreadyFound.count(pMP).  The caller keeps :2420-2437 (vpReplacePoint / AddObservation). */
+int orbm_fuse_sim3_host(orbm_matcher* m, const orbx_keypoint* kf_k, const uint8_t* kf_desc, const int32_t* kf_cam, int n_kf,
+                        orbm_bounds b, const float* scale_factors, int nlevels, float log_scale_factor, orbm_camera cam,
+                        const float* Scw, const float* calib, const int32_t* mp_valid, const float* mp_xyz,
+                        const float* mp_normal, const float* mp_max_dist, const float* mp_min_dist, const float* mp_max_d,
+                        const uint8_t* mp_desc, int n_mp, float th, int32_t* best_idx, int* n_fused);
+
 /* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:325-438), the arithmetic part (:381-424), batched over
  * map points: the observed descriptors of point p (vDescriptors, in std::map<KeyFrame*,size_t> iteration order, bad
  * key frames left out) are rows offsets[p] .. offsets[p+1]-1 of desc (offsets[0] = 0).  best_idx[p] = BestIdx relative

@@ -1112,7 +1112,9 @@ __global__ void __launch_bounds__(256) k_fuse_match(const orbx_keypoint* __restr
                                                     const int* __restrict__ grid_start,
                                                     const uint16_t* __restrict__ grid_items, int n_kps,
                                                     const ProjQuery* __restrict__ q, const uint8_t* __restrict__ q_desc,
-                                                    int nq, LevelTable inv_sigma2, int32_t* __restrict__ best_idx) {
+                                                    int nq, LevelTable inv_sigma2, int gate,
+                                                    int32_t* __restrict__ best_idx) {
+  // gate != 0: the pose-based overload (:1986); gate == 0: the Sim3 overload (:2211), which has no reprojection test
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= nq) return;
@@ -1129,7 +1131,7 @@ __global__ void __launch_bounds__(256) k_fuse_match(const orbx_keypoint* __restr
   uint32_t best = 0xFFFFFFFFu;  // dist << 16 | traversal position
   int my_idx = -1, cnt = 0;
   grid_query(gv, k, p.u, p.v, p.radius, p.min_level, p.max_level, [&](bool ok, int idx) {
-    if (ok) {
+    if (ok && gate) {
       const orbx_keypoint kp = k[idx];
       const float ex = __fsub_rn(p.u, kp.x), ey = __fsub_rn(p.v, kp.y);
       float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
@@ -1988,11 +1990,13 @@ inline void mat3_mul_vec_add(const float* R, int rs, const float* x, const float
     out[i] = t ? s + t[i] : s;
   }
 }
-inline void mat3t_mul_vec(const float* R, int rs, const float* x, float alpha, float* out) {
+inline void mat3t_mul_vec(const float* R, int rs, const float* x, float alpha, float* out) {  // alpha * R^T x
+  // cv::gemm with a transposed operand leaves the small-matrix float path: products and sums in double,
+  // alpha applied in double, one rounding to float (probed against cv2.gemm(..., GEMM_1_T))
   for (int i = 0; i < 3; ++i) {
-    float s = 0.f;
-    for (int k = 0; k < 3; ++k) s += R[k * rs + i] * x[k];
-    out[i] = s * alpha;
+    double s = 0.0;
+    for (int k = 0; k < 3; ++k) s += (double)R[k * rs + i] * (double)x[k];
+    out[i] = (float)(s * (double)alpha);
   }
 }
 
@@ -2251,6 +2255,57 @@ int orbm_search_by_projection_sim3_host(orbm_matcher* m, const orbx_keypoint* kf
                        nmatches);
 }
 
+}  // extern "C"
+#pragma GCC visibility pop
+namespace {
+// device part shared by the two Fuse overloads: per-camera grids + one warp per (map point, camera) query
+int fuse_run(orbm_matcher* m, const orbx_keypoint* kf_k, const uint8_t* kf_desc, const float* kf_uright, const int32_t* kf_cam,
+             int n_kf, orbm_bounds b, const std::vector<ProjQuery>& q, const uint8_t* mp_desc, int n_mp,
+             const float* inv_level_sigma2, int nlevels, int gate, int32_t* best_idx, int* n_fused) {
+  const int nq = (int)q.size();
+  if (nq == 0) return ORBX_OK;
+  cudaSetDevice(m->device);
+  cudaStream_t st = m->stream;
+  uint8_t* fb = m->scratch<uint8_t>(8, (size_t)n_kf * (32 + sizeof(orbx_keypoint) + 8) + 256);
+  uint8_t* qb = m->scratch<uint8_t>(9, (size_t)n_mp * (32 + 8) + (size_t)nq * sizeof(ProjQuery) + 256);
+  int* gstart = m->scratch<int>(4, (size_t)2 * (GRID_CELLS + 1));
+  uint16_t* gitems = m->scratch<uint16_t>(5, (size_t)2 * n_kf);
+  if (!fb || !qb || !gstart || !gitems) return ORBX_E_CUDA;
+  uint8_t* dd = fb;
+  orbx_keypoint* dk = reinterpret_cast<orbx_keypoint*>(dd + (size_t)n_kf * 32);
+  float* dur = reinterpret_cast<float*>(dk + n_kf);
+  int32_t* dcam = reinterpret_cast<int32_t*>(dur + n_kf);
+  uint8_t* dmd = qb;
+  int32_t* dbest = reinterpret_cast<int32_t*>(dmd + (size_t)n_mp * 32);
+  ProjQuery* dq = reinterpret_cast<ProjQuery*>(dbest + 2 * (size_t)n_mp);
+  cudaMemcpyAsync(dd, kf_desc, (size_t)n_kf * 32, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dk, kf_k, sizeof(orbx_keypoint) * n_kf, cudaMemcpyHostToDevice, st);
+  if (kf_uright) cudaMemcpyAsync(dur, kf_uright, sizeof(float) * n_kf, cudaMemcpyHostToDevice, st);
+  if (kf_cam) cudaMemcpyAsync(dcam, kf_cam, sizeof(int32_t) * n_kf, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dmd, mp_desc, (size_t)n_mp * 32, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dq, q.data(), sizeof(ProjQuery) * nq, cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(dbest, 0xFF, sizeof(int32_t) * 2 * (size_t)n_mp, st);
+  for (int c = 0; c < 2; ++c) {
+    k_build_grid<<<1, 256, 0, st>>>(dk, nullptr, n_kf, n_kf, b, gstart + (size_t)c * (GRID_CELLS + 1), gitems + (size_t)c * n_kf,
+                                    kf_cam ? dcam : nullptr, c);
+    m->launches++;
+  }
+  LevelTable lt;
+  for (int i = 0; i < ORBX_MAX_LEVELS; ++i) lt.v[i] = (inv_level_sigma2 && i < nlevels) ? inv_level_sigma2[i] : 0.f;
+  k_fuse_match<<<(nq + 7) / 8, 256, 0, st>>>(dk, dd, dur, b, gstart, gitems, n_kf, dq, dmd, nq, lt, gate, dbest);
+  m->launches++;
+  cudaMemcpyAsync(best_idx, dbest, sizeof(int32_t) * 2 * (size_t)n_mp, cudaMemcpyDeviceToHost, st);
+  if (!m->check(cudaStreamSynchronize(st), "fuse")) return ORBX_E_CUDA;
+  int nf = 0;
+  for (int i = 0; i < 2 * n_mp; ++i) nf += best_idx[i] >= 0;
+  *n_fused = nf;
+  return m->check(cudaGetLastError(), "fuse launch") ? ORBX_OK : ORBX_E_CUDA;
+}
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
 int orbm_fuse_host(orbm_matcher* m, const orbx_keypoint* kf_k, const uint8_t* kf_desc, const float* kf_uright,
                    const int32_t* kf_cam, int n_kf, orbm_bounds b, const float* scale_factors, const float* inv_level_sigma2,
                    int nlevels, float log_scale_factor, orbm_camera cam, const float* Tcw, const float* Ow, const float* calib,
@@ -2333,44 +2388,103 @@ int orbm_fuse_host(orbm_matcher* m, const orbx_keypoint* kf_k, const uint8_t* kf
       q.push_back(p);
     }
   }
-  const int nq = (int)q.size();
-  if (nq == 0) return ORBX_OK;
-  cudaSetDevice(m->device);
-  cudaStream_t st = m->stream;
-  uint8_t* fb = m->scratch<uint8_t>(8, (size_t)n_kf * (32 + sizeof(orbx_keypoint) + 8) + 256);
-  uint8_t* qb = m->scratch<uint8_t>(9, (size_t)n_mp * (32 + 8) + (size_t)nq * sizeof(ProjQuery) + 256);
-  int* gstart = m->scratch<int>(4, (size_t)2 * (GRID_CELLS + 1));
-  uint16_t* gitems = m->scratch<uint16_t>(5, (size_t)2 * n_kf);
-  if (!fb || !qb || !gstart || !gitems) return ORBX_E_CUDA;
-  uint8_t* dd = fb;
-  orbx_keypoint* dk = reinterpret_cast<orbx_keypoint*>(dd + (size_t)n_kf * 32);
-  float* dur = reinterpret_cast<float*>(dk + n_kf);
-  int32_t* dcam = reinterpret_cast<int32_t*>(dur + n_kf);
-  uint8_t* dmd = qb;
-  int32_t* dbest = reinterpret_cast<int32_t*>(dmd + (size_t)n_mp * 32);
-  ProjQuery* dq = reinterpret_cast<ProjQuery*>(dbest + 2 * (size_t)n_mp);
-  cudaMemcpyAsync(dd, kf_desc, (size_t)n_kf * 32, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dk, kf_k, sizeof(orbx_keypoint) * n_kf, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dur, kf_uright, sizeof(float) * n_kf, cudaMemcpyHostToDevice, st);
-  if (kf_cam) cudaMemcpyAsync(dcam, kf_cam, sizeof(int32_t) * n_kf, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dmd, mp_desc, (size_t)n_mp * 32, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dq, q.data(), sizeof(ProjQuery) * nq, cudaMemcpyHostToDevice, st);
-  cudaMemsetAsync(dbest, 0xFF, sizeof(int32_t) * 2 * (size_t)n_mp, st);
-  for (int c = 0; c < 2; ++c) {
-    k_build_grid<<<1, 256, 0, st>>>(dk, nullptr, n_kf, n_kf, b, gstart + (size_t)c * (GRID_CELLS + 1), gitems + (size_t)c * n_kf,
-                                    kf_cam ? dcam : nullptr, c);
-    m->launches++;
+  return fuse_run(m, kf_k, kf_desc, kf_uright, kf_cam, n_kf, b, q, mp_desc, n_mp, inv_level_sigma2, nlevels, 1, best_idx, n_fused);
+}
+
+int orbm_fuse_sim3_host(orbm_matcher* m, const orbx_keypoint* kf_k, const uint8_t* kf_desc, const int32_t* kf_cam, int n_kf,
+                        orbm_bounds b, const float* scale_factors, int nlevels, float log_scale_factor, orbm_camera cam,
+                        const float* Scw, const float* calib, const int32_t* mp_valid, const float* mp_xyz,
+                        const float* mp_normal, const float* mp_max_dist, const float* mp_min_dist, const float* mp_max_d,
+                        const uint8_t* mp_desc, int n_mp, float th, int32_t* best_idx, int* n_fused) {
+  if (!m || !scale_factors || !Scw || !calib || !best_idx || !n_fused || n_kf < 0 || n_kf > 65535 || n_mp < 0 || nlevels < 1 ||
+      nlevels > ORBX_MAX_LEVELS || (n_kf && (!kf_k || !kf_desc)) ||
+      (n_mp && (!mp_valid || !mp_xyz || !mp_normal || !mp_max_dist || !mp_min_dist || !mp_max_d || !mp_desc)))
+    return ORBX_E_INVALID;
+  *n_fused = 0;
+  for (int i = 0; i < 2 * n_mp; ++i) best_idx[i] = -1;
+  if (n_kf == 0 || n_mp == 0) return ORBX_OK;
+  // host-side projection (:2218-2300), float evaluation order of the cv::Mat expressions
+  float Rcam21[9], tcam21[3];
+  {
+    double S[9];
+    for (int i = 0; i < 9; ++i) S[i] = calib[i];
+    double d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
+    d = 1. / d;
+    Rcam21[0] = (float)((S[4] * S[8] - S[5] * S[7]) * d); Rcam21[1] = (float)((S[2] * S[7] - S[1] * S[8]) * d);
+    Rcam21[2] = (float)((S[1] * S[5] - S[2] * S[4]) * d); Rcam21[3] = (float)((S[5] * S[6] - S[3] * S[8]) * d);
+    Rcam21[4] = (float)((S[0] * S[8] - S[2] * S[6]) * d); Rcam21[5] = (float)((S[2] * S[3] - S[0] * S[5]) * d);
+    Rcam21[6] = (float)((S[3] * S[7] - S[4] * S[6]) * d); Rcam21[7] = (float)((S[1] * S[6] - S[0] * S[7]) * d);
+    Rcam21[8] = (float)((S[0] * S[4] - S[1] * S[3]) * d);
   }
-  LevelTable lt;
-  for (int i = 0; i < ORBX_MAX_LEVELS; ++i) lt.v[i] = i < nlevels ? inv_level_sigma2[i] : 0.f;
-  k_fuse_match<<<(nq + 7) / 8, 256, 0, st>>>(dk, dd, dur, b, gstart, gitems, n_kf, dq, dmd, nq, lt, dbest);
-  m->launches++;
-  cudaMemcpyAsync(best_idx, dbest, sizeof(int32_t) * 2 * (size_t)n_mp, cudaMemcpyDeviceToHost, st);
-  if (!m->check(cudaStreamSynchronize(st), "fuse")) return ORBX_E_CUDA;
-  int nf = 0;
-  for (int i = 0; i < 2 * n_mp; ++i) nf += best_idx[i] >= 0;
-  *n_fused = nf;
-  return m->check(cudaGetLastError(), "fuse launch") ? ORBX_OK : ORBX_E_CUDA;
+  mat3_mul_vec_add(Rcam21, 3, calib + 9, nullptr, -1.f, tcam21);
+  double ss = 0;
+  for (int k = 0; k < 3; ++k) ss += (double)Scw[k] * (double)Scw[k];
+  const float scw = (float)std::sqrt(ss);
+  const float inv_s = (float)(1.0 / scw);
+  float Rcw[16] = {0}, tcw[3], Ow[3];
+  double RtT12[3];  // Rcw.t()*tcam12 in double: `PO - Rcw.t()*tcam12` is one gemm(alpha=-1, C=PO, beta=1, GEMM_1_T)
+  for (int i = 0; i < 3; ++i) {
+    for (int k = 0; k < 3; ++k) Rcw[i * 4 + k] = Scw[i * 4 + k] * inv_s;
+    tcw[i] = Scw[i * 4 + 3] * inv_s;
+  }
+  mat3t_mul_vec(Rcw, 4, tcw, -1.f, Ow);
+  for (int i = 0; i < 3; ++i) {
+    double acc = 0.0;
+    for (int k = 0; k < 3; ++k) acc += (double)Rcw[k * 4 + i] * (double)calib[9 + k];
+    RtT12[i] = acc;
+  }
+  float M[9], Rt[3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      float acc = 0.f;
+      for (int k = 0; k < 3; ++k) acc += Rcam21[i * 3 + k] * Rcw[k * 4 + j];
+      M[i * 3 + j] = acc;
+    }
+  mat3_mul_vec_add(Rcam21, 3, tcw, nullptr, 1.f, Rt);
+  std::vector<ProjQuery> q;
+  q.reserve(2 * (size_t)n_mp);
+  for (int i = 0; i < n_mp; ++i) {
+    if (!mp_valid[i]) continue;
+    const float* p3Dw = mp_xyz + 3 * i;
+    for (int c = 0; c < 2; ++c) {
+      float p3Dc[3];
+      if (c == 0) {
+        mat3_mul_vec_add(Rcw, 4, p3Dw, tcw, 1.f, p3Dc);
+      } else {
+        float m1[3];
+        mat3_mul_vec_add(M, 3, p3Dw, nullptr, 1.f, m1);
+        for (int k = 0; k < 3; ++k) p3Dc[k] = (m1[k] + Rt[k]) + tcam21[k];
+      }
+      if (p3Dc[2] < 0.0f) continue;
+      const float invz = (float)(1.0 / p3Dc[2]);
+      const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
+      const float u = cam.fx * x + cam.cx, v = cam.fy * y + cam.cy;
+      if (!(u >= b.min_x && u < b.max_x && v >= b.min_y && v < b.max_y)) continue;
+      float PO[3];
+      double n2 = 0, dotn = 0;
+      for (int k = 0; k < 3; ++k) {
+        PO[k] = p3Dw[k] - Ow[k];
+        if (c == 1) PO[k] = (float)(-1.0 * RtT12[k] + (double)PO[k]);
+        n2 += (double)PO[k] * (double)PO[k];
+        dotn += (double)PO[k] * (double)mp_normal[3 * i + k];
+      }
+      const float dist3D = (float)std::sqrt(n2);
+      if (dist3D < mp_min_dist[i] || dist3D > mp_max_dist[i]) continue;
+      if (dotn < 0.5 * dist3D) continue;
+      const float ratio = mp_max_d[i] / dist3D;
+      int lvl = (int)std::ceil(std::log(ratio) / log_scale_factor);
+      if (lvl < 0) lvl = 0;
+      else if (lvl >= nlevels) lvl = nlevels - 1;
+      ProjQuery p;
+      p.u = u; p.v = v;
+      p.radius = th * scale_factors[lvl];
+      p.ur = 0.f; p.use_ur = 0; p.angle = 0.f;
+      p.min_level = lvl - 1; p.max_level = lvl;
+      p.cam = c; p.src = i; p.obs = 1;
+      q.push_back(p);
+    }
+  }
+  return fuse_run(m, kf_k, kf_desc, nullptr, kf_cam, n_kf, b, q, mp_desc, n_mp, nullptr, nlevels, 0, best_idx, n_fused);
 }
 
 #pragma GCC visibility pop

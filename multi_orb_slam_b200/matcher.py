@@ -278,6 +278,26 @@ class ORBmatcher:
             best.ctypes.data, C.byref(nf)))
         return nf.value, best
 
+    def FuseSim3(self, kf: Frame, kf_cam, camera: Camera, log_scale_factor: float, Scw, calib, mp_valid, mp_xyz, mp_normal,
+                 mp_max_dist, mp_min_dist, mp_max_d, mp_desc, th: float = 4.0):
+        """Fuse(KeyFrame*, Scw, vpPoints, ..., CalibMatrix) (src/ORBmatcher.cc:2211-2441), the search part.
+        Returns (nFused, best_idx [n_mp, 2])."""
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        sf = f32(kf.mvScaleFactors)
+        cam_of = None if kf_cam is None else np.ascontiguousarray(kf_cam, dtype=np.int32)
+        val = np.ascontiguousarray(mp_valid, dtype=np.int32)
+        xyz, nrm, mx, mn, md = f32(mp_xyz), f32(mp_normal), f32(mp_max_dist), f32(mp_min_dist), f32(mp_max_d)
+        desc = np.ascontiguousarray(mp_desc, dtype=np.uint8)
+        S, cal = f32(Scw), f32(calib)
+        best = np.empty((len(val), 2), dtype=np.int32)
+        nf = C.c_int(0)
+        check_m(self._h, lib.orbm_fuse_sim3_host(
+            self._h, kf.mvKeysUn.ctypes.data, kf.mDescriptors.ctypes.data, None if cam_of is None else cam_of.ctypes.data, kf.N,
+            kf.bounds, sf.ctypes.data, len(sf), float(log_scale_factor), camera, S.ctypes.data, cal.ctypes.data, val.ctypes.data,
+            xyz.ctypes.data, nrm.ctypes.data, mx.ctypes.data, mn.ctypes.data, md.ctypes.data, desc.ctypes.data, len(val), float(th),
+            best.ctypes.data, C.byref(nf)))
+        return nf.value, best
+
     # -- SearchByBoW, Frame and KeyFrame variants (src/ORBmatcher.cc:206-388, 390-565, 996-1163, 1180-1363) --
     def SearchByBoW(self, desc1, angle1, valid1, featvec1, desc2, angle2, valid2, featvec2, *, keyframe_pair: bool = False):
         """Side 1 = key frame whose map points are searched (valid1[i] = map point exists and is not

@@ -510,10 +510,12 @@ inline void mat3_mul_vec_add(const float* R /*3x3 row-major, row stride rs*/, in
   }
 }
 inline void mat3t_mul_vec(const float* R, int rs, const float* x, float alpha, float* out) {  // alpha * R^T x
+  // cv::gemm with a transposed operand leaves the small-matrix float path: products and sums in double,
+  // alpha applied in double, one rounding to float (probed against cv2.gemm(..., GEMM_1_T))
   for (int i = 0; i < 3; ++i) {
-    float s = 0.f;
-    for (int k = 0; k < 3; ++k) s += R[k * rs + i] * x[k];
-    out[i] = s * alpha;
+    double s = 0.0;
+    for (int k = 0; k < 3; ++k) s += (double)R[k * rs + i] * (double)x[k];
+    out[i] = (float)(s * (double)alpha);
   }
 }
 struct Grid2 {  // mGrids[c]: per-camera grids over the concatenated keypoints (src/Frame.cc:384-393)
@@ -870,6 +872,118 @@ int om_fuse(const oo_keypoint* kf_k, const uint8_t* kf_desc, const float* kf_uri
     }
   }
   return nFused;
+}
+
+// ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, vpPoints, vLoopMPCams, th, vpReplacePoint, CalibMatrix)
+// (src/ORBmatcher.cc:2211-2441, called from LoopClosing::SearchAndFuse, src/LoopClosing.cc:841), the search part:
+// best_idx[2*i + cam] as for om_fuse.  Differences from the pose-based overload: the pose is the Sim3 with its
+// scale divided out (:2229-2233), one camera centre Ow = -Rcw^T*tcw with camera 2's at Ow + Rcw^T*tcam12
+// (:2277-2279), no reprojection gate, bestDist starts at INT_MAX (:2334).  mp_valid[i] = !isBad() &&
+// !spAlreadyFound.count(pMP).
+int om_fuse_sim3(const oo_keypoint* kf_k, const uint8_t* kf_desc, const int32_t* kf_cam, int n_kf, om_bounds b,
+                 const float* scale_factors, int nlevels, float log_scale_factor, om_camera cam, const float* Scw,
+                 const float* calib, const int32_t* mp_valid, const float* mp_xyz, const float* mp_normal,
+                 const float* mp_max_dist, const float* mp_min_dist, const float* mp_max_d, const uint8_t* mp_desc, int n_mp,
+                 float th, int32_t* best_idx) {
+  float Rcam21[9], tcam21[3];
+  {
+    double S[9];
+    for (int i = 0; i < 9; ++i) S[i] = calib[i];
+    double d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
+    d = 1. / d;
+    Rcam21[0] = (float)((S[4] * S[8] - S[5] * S[7]) * d); Rcam21[1] = (float)((S[2] * S[7] - S[1] * S[8]) * d);
+    Rcam21[2] = (float)((S[1] * S[5] - S[2] * S[4]) * d); Rcam21[3] = (float)((S[5] * S[6] - S[3] * S[8]) * d);
+    Rcam21[4] = (float)((S[0] * S[8] - S[2] * S[6]) * d); Rcam21[5] = (float)((S[2] * S[3] - S[0] * S[5]) * d);
+    Rcam21[6] = (float)((S[3] * S[7] - S[4] * S[6]) * d); Rcam21[7] = (float)((S[1] * S[6] - S[0] * S[7]) * d);
+    Rcam21[8] = (float)((S[0] * S[4] - S[1] * S[3]) * d);
+  }
+  mat3_mul_vec_add(Rcam21, 3, calib + 9, nullptr, -1.f, tcam21);
+  // scw = sqrt(sRcw.row(0).dot(sRcw.row(0))) (double dot), Rcw = sRcw/scw, tcw = t/scw: cv::Mat / scalar multiplies
+  // by the reciprocal taken in double and rounded to float
+  double ss = 0;
+  for (int k = 0; k < 3; ++k) ss += (double)Scw[k] * (double)Scw[k];
+  const float scw = (float)std::sqrt(ss);
+  const float inv_s = (float)(1.0 / scw);
+  float Rcw[16] = {0}, tcw[3], Ow[3];
+  double RtT12[3];  // Rcw.t() * tcam12, kept in double: `PO - Rcw.t()*tcam12` is ONE gemm(alpha=-1, C=PO, beta=1, GEMM_1_T)
+  for (int i = 0; i < 3; ++i) {
+    for (int k = 0; k < 3; ++k) Rcw[i * 4 + k] = Scw[i * 4 + k] * inv_s;
+    tcw[i] = Scw[i * 4 + 3] * inv_s;
+  }
+  mat3t_mul_vec(Rcw, 4, tcw, -1.f, Ow);
+  for (int i = 0; i < 3; ++i) {
+    double acc = 0.0;
+    for (int k = 0; k < 3; ++k) acc += (double)Rcw[k * 4 + i] * (double)calib[9 + k];
+    RtT12[i] = acc;
+  }
+  float M[9], Rt[3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      float acc = 0.f;
+      for (int k = 0; k < 3; ++k) acc += Rcam21[i * 3 + k] * Rcw[k * 4 + j];
+      M[i * 3 + j] = acc;
+    }
+  mat3_mul_vec_add(Rcam21, 3, tcw, nullptr, 1.f, Rt);
+  SoA s(kf_k, n_kf);
+  Grid2 grids(s.x.data(), s.y.data(), s.oct.data(), kf_cam, n_kf, b);
+  int nFused = 0;
+  std::vector<int> cand;
+  for (int i = 0; i < n_mp; ++i) {
+    best_idx[2 * i] = best_idx[2 * i + 1] = -1;
+    if (!mp_valid[i]) continue;
+    const float* p3Dw = mp_xyz + 3 * i;
+    for (int c = 0; c < 2; ++c) {
+      float p3Dc[3];
+      if (c == 0) {
+        mat3_mul_vec_add(Rcw, 4, p3Dw, tcw, 1.f, p3Dc);
+      } else {
+        float m1[3];
+        mat3_mul_vec_add(M, 3, p3Dw, nullptr, 1.f, m1);
+        for (int k = 0; k < 3; ++k) p3Dc[k] = (m1[k] + Rt[k]) + tcam21[k];
+      }
+      if (p3Dc[2] < 0.0f) continue;
+      const float invz = (float)(1.0 / p3Dc[2]);
+      const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
+      const float u = cam.fx * x + cam.cx, v = cam.fy * y + cam.cy;
+      if (!(u >= b.min_x && u < b.max_x && v >= b.min_y && v < b.max_y)) continue;
+      float PO[3];
+      double n2 = 0, dotn = 0;
+      for (int k = 0; k < 3; ++k) {
+        PO[k] = p3Dw[k] - Ow[k];
+        if (c == 1) PO[k] = (float)(-1.0 * RtT12[k] + (double)PO[k]);
+        n2 += (double)PO[k] * (double)PO[k];
+        dotn += (double)PO[k] * (double)mp_normal[3 * i + k];
+      }
+      const float dist3D = (float)std::sqrt(n2);
+      if (dist3D < mp_min_dist[i] || dist3D > mp_max_dist[i]) continue;
+      if (dotn < 0.5 * dist3D) continue;
+      const float ratio = mp_max_d[i] / dist3D;
+      int lvl = (int)std::ceil(std::log(ratio) / log_scale_factor);
+      if (lvl < 0) lvl = 0;
+      else if (lvl >= nlevels) lvl = nlevels - 1;
+      const float radius = th * scale_factors[lvl];
+      const Grid& g = c == 1 ? grids.g1 : grids.g0;
+      g.query(u, v, radius, -1, -1, cand);
+      int bestDist = INT_MAX, bestIdx = -1;
+      for (int idx : cand) {
+        const int kpLevel = kf_k[idx].octave;
+        if (kpLevel < lvl - 1 || kpLevel > lvl) continue;
+        const int dd = om_distance(mp_desc + (size_t)i * 32, kf_desc + (size_t)idx * 32);
+        if (dd < bestDist) { bestDist = dd; bestIdx = idx; }
+      }
+      if (bestIdx < 0) continue;
+      if (bestDist <= TH_LOW) { best_idx[2 * i + c] = bestIdx; nFused++; }
+    }
+  }
+  return nFused;
+}
+
+// Test hook: the cv::Mat small-matrix algebra helpers above, so that tests can pin them against cv2.gemm.
+//   transpose_a == 0: out = alpha * (A x) + c   (float32 path of cv::gemm for tiny non-transposed operands)
+//   transpose_a == 1: out = alpha * (A^T x)     (double-accumulating generic path; c must be NULL)
+void om_gemm3_probe(const float* A, const float* x, const float* c, float alpha, int transpose_a, float* out) {
+  if (transpose_a) mat3t_mul_vec(A, 3, x, alpha, out);
+  else mat3_mul_vec_add(A, 3, x, c, alpha, out);
 }
 
 }  // extern "C"

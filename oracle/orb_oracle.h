@@ -200,6 +200,17 @@ int om_fuse(const oo_keypoint* kf_k, const uint8_t* kf_desc, const float* kf_uri
             const float* mp_xyz, const float* mp_normal, const float* mp_max_dist, const float* mp_min_dist,
             const float* mp_max_d, const uint8_t* mp_desc, int n_mp, float th, int32_t* best_idx);
 
+// ORBmatcher::Fuse(KeyFrame*, Scw, vpPoints, vLoopMPCams, th, vpReplacePoint, CalibMatrix) (src/ORBmatcher.cc:2211-2441),
+// the search part; Scw 4x4 row-major Sim3 (s*R | t).  mp_valid[i] = !isBad() && !spAlreadyFound.count(pMP).
+int om_fuse_sim3(const oo_keypoint* kf_k, const uint8_t* kf_desc, const int32_t* kf_cam, int n_kf, om_bounds b,
+                 const float* scale_factors, int nlevels, float log_scale_factor, om_camera cam, const float* Scw,
+                 const float* calib, const int32_t* mp_valid, const float* mp_xyz, const float* mp_normal,
+                 const float* mp_max_dist, const float* mp_min_dist, const float* mp_max_d, const uint8_t* mp_desc, int n_mp,
+                 float th, int32_t* best_idx);
+
+// Test hook for the cv::Mat 3x3 algebra emulation used by the pose-based searches (pinned against cv2.gemm).
+void om_gemm3_probe(const float* A, const float* x, const float* c, float alpha, int transpose_a, float* out);
+
 // ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:3948-3989) on bin counts.
 void om_three_maxima(const int* counts, int L, int* ind1, int* ind2, int* ind3);
 

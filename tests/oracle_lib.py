@@ -307,6 +307,25 @@ def fuse(kf_k, kf_desc, kf_uright, kf_cam, bounds, sf, inv_sigma2, log_sf, cam, 
     return n, best
 
 
+def fuse_sim3(kf_k, kf_desc, kf_cam, bounds, sf, log_sf, cam, Scw, calib, mp_valid, mp_xyz, mp_normal, mp_max_dist, mp_min_dist,
+              mp_max_d, mp_desc, th):
+    lib = load("port")
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    kf_k = np.ascontiguousarray(kf_k, dtype=KP_DTYPE)
+    kf_desc, mp_desc = np.ascontiguousarray(kf_desc, dtype=np.uint8), np.ascontiguousarray(mp_desc, dtype=np.uint8)
+    kcam, val = np.ascontiguousarray(kf_cam, dtype=np.int32), np.ascontiguousarray(mp_valid, dtype=np.int32)
+    sf, S, cal, xyz, nrm, mx, mn, md = (f32(a) for a in (sf, Scw, calib, mp_xyz, mp_normal, mp_max_dist, mp_min_dist, mp_max_d))
+    best = np.empty((len(val), 2), dtype=np.int32)
+    f = lib.om_fuse_sim3
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, Bounds, C.c_void_p, C.c_int, C.c_float, Camera] + \
+                 [C.c_void_p] * 9 + [C.c_int, C.c_float, C.c_void_p]
+    n = f(kf_k.ctypes.data, kf_desc.ctypes.data, kcam.ctypes.data, len(kf_k), Bounds(*bounds), sf.ctypes.data, len(sf), log_sf,
+          Camera(*cam), S.ctypes.data, cal.ctypes.data, val.ctypes.data, xyz.ctypes.data, nrm.ctypes.data, mx.ctypes.data,
+          mn.ctypes.data, md.ctypes.data, mp_desc.ctypes.data, len(val), float(th), best.ctypes.data)
+    return n, best
+
+
 def compute_distinctive_descriptors(desc, offsets):
     lib = load("port")
     d = np.ascontiguousarray(desc, dtype=np.uint8).reshape(-1, 32)

@@ -115,3 +115,22 @@ def test_undistort_points(oracle_port):
         want = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, dist if trial % 2 else dist[:4], None, K).reshape(-1, 2)
         got = oracle_port.undistort_points(pts, fx, fy, cx, cy, dist)
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"trial {trial}"
+
+
+def test_small_matrix_algebra_matches_cv_gemm(oracle_port):
+    """cv::Mat expressions of the pose-based searches: `R*x + t` takes cv::gemm's float32 small-matrix path,
+    `-R.t()*x` (camera centres, src/ORBmatcher.cc:595, 2235, 3755, 4285) the double-accumulating generic one."""
+    lib = oracle_port.load("port")
+    lib.om_gemm3_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(9)
+    for trial in range(500):
+        A = rng.normal(0, 1, (3, 3)).astype(np.float32)
+        x = rng.normal(0, 5, (3, 1)).astype(np.float32)
+        c = rng.normal(0, 5, (3, 1)).astype(np.float32)
+        out = np.zeros(3, np.float32)
+        lib.om_gemm3_probe(A.ctypes.data, x.ctypes.data, c.ctypes.data, 1.0, 0, out.ctypes.data)
+        assert np.array_equal(out, cv2.gemm(A, x, 1, c, 1)[:, 0]), "R*x + t"
+        lib.om_gemm3_probe(A.ctypes.data, x.ctypes.data, None, -1.0, 0, out.ctypes.data)
+        assert np.array_equal(out, cv2.gemm(A, x, -1, None, 0)[:, 0]), "-R*x"
+        lib.om_gemm3_probe(A.ctypes.data, x.ctypes.data, None, -1.0, 1, out.ctypes.data)
+        assert np.array_equal(out, cv2.gemm(A, x, -1, None, 0, flags=cv2.GEMM_1_T)[:, 0]), "-R.t()*x"

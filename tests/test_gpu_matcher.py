@@ -529,3 +529,32 @@ def test_fuse_vs_oracle(O, th, seed):
     gn, gbest = m.Fuse(F, s["cur_cam"], Camera(*CAM), log_sf, inv_sigma2, Tcw, Ow, CALIB, np.zeros(nmp, np.int32), xyz, normal,
                        kf_max, kf_min, max_d, s["last_desc"], th)
     assert gn == 0 and (gbest == -1).all()
+
+
+@pytest.mark.parametrize("th,scale", [(4.0, 1.0), (4.0, 1.6)])
+def test_fuse_sim3_vs_oracle(O, th, scale):
+    """Fuse(KeyFrame*, Scw, ...) (src/ORBmatcher.cc:2211-2441): the loop-closing overload."""
+    from multi_orb_slam_b200._lib import Camera
+    from multi_orb_slam_b200.matcher import Frame, ORBmatcher
+    s = _rig_scene(O, 31, 2500, (0, 0, 0))
+    rng = s["rng"]
+    nmp = len(s["last_xyz"])
+    sf = O.extractor("port").scale_tables()[0]
+    Scw = s["Tcw"].astype(np.float64).copy()
+    Scw[:3, :] *= scale
+    xyz = s["last_xyz"].astype(np.float64)
+    Ow = -s["Tcw"][:3, :3].T.astype(np.float64) @ s["Tcw"][:3, 3].astype(np.float64)
+    dist = np.linalg.norm(xyz - Ow, axis=1)
+    normal = (xyz - Ow) / dist[:, None] + rng.normal(0, 0.3, (nmp, 3))
+    normal /= np.linalg.norm(normal, axis=1)[:, None]
+    max_d = (dist * rng.uniform(0.8, 4.0, nmp)).astype(np.float32)
+    kf_max, kf_min = (1.2 * max_d).astype(np.float32), (0.8 * max_d / 1.2 ** 7).astype(np.float32)
+    valid = (rng.random(nmp) < 0.9).astype(np.int32)
+    log_sf = float(np.log(np.float32(1.2)))
+    rn, rbest = O.fuse_sim3(s["cur_k"], s["cur_d"], s["cur_cam"], (0, 640, 0, 480), sf, log_sf, CAM, Scw, CALIB, valid, xyz, normal,
+                            kf_max, kf_min, max_d, s["last_desc"], th)
+    F = Frame(s["cur_k"], s["cur_d"], 640, 480, mvScaleFactors=sf)
+    gn, gbest = ORBmatcher(0.6, True).FuseSim3(F, s["cur_cam"], Camera(*CAM), log_sf, Scw, CALIB, valid, xyz, normal, kf_max, kf_min,
+                                                max_d, s["last_desc"], th)
+    assert gn == rn and np.array_equal(gbest, rbest)
+    assert rn > 100 and (rbest[:, 0] >= 0).any() and (rbest[:, 1] >= 0).any()
