@@ -309,6 +309,25 @@ int orbm_fuse_sim3_host(orbm_matcher* m, const orbx_keypoint* kf_k, const uint8_
                         const float* mp_normal, const float* mp_max_dist, const float* mp_min_dist, const float* mp_max_d,
                         const uint8_t* mp_desc, int n_mp, float th, int32_t* best_idx, int* n_fused);
 
+/* ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th, CalibMatrix) (src/ORBmatcher.cc:2814-3136,
+ * called from LoopClosing::ComputeSim3, src/LoopClosing.cc:402): the map points of each key frame are projected into
+ * the other through the Sim3 (s12, R12 3x3 row-major, t12), searched in the grid of their own camera within
+ * th * mvScaleFactors[predicted level], best distance <= TH_HIGH, and only mutual pairs are kept.
+ * Key frame x: concatenated keypoints / descriptors, camx (keypoint_to_cam, NULL = one camera), Txw (4x4 row-major).
+ * Map-point arrays are aligned with the keypoints (GetMapPointMatches): mpx_valid[i] = point exists, !isBad() and not
+ * already matched (vbAlreadyMatched1/2, :2846-2861); GetWorldPos, Get{Max,Min}DistanceInvariance, mfMaxDistance,
+ * GetDescriptor.  match12 (n1) out: the key-frame-2 feature of every new mutual match, else -1
+ * (vpMatches12[i1] = vpMapPoints2[match12[i1]]); *n_found = nFound. */
+int orbm_search_by_sim3_host(orbm_matcher* m, const orbx_keypoint* k1, const uint8_t* d1, const int32_t* cam1, int n1,
+                             const float* T1w, const orbx_keypoint* k2, const uint8_t* d2, const int32_t* cam2, int n2,
+                             const float* T2w, orbm_bounds b, const float* scale_factors, int nlevels, float log_scale_factor,
+                             orbm_camera cam, float s12, const float* R12, const float* t12, const float* calib,
+                             const int32_t* mp1_valid, const float* mp1_xyz, const float* mp1_max_dist,
+                             const float* mp1_min_dist, const float* mp1_max_d, const uint8_t* mp1_desc,
+                             const int32_t* mp2_valid, const float* mp2_xyz, const float* mp2_max_dist,
+                             const float* mp2_min_dist, const float* mp2_max_d, const uint8_t* mp2_desc, float th,
+                             int32_t* match12, int* n_found);
+
 /* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:325-438), the arithmetic part (:381-424), batched over
  * map points: the observed descriptors of point p (vDescriptors, in std::map<KeyFrame*,size_t> iteration order, bad
  * key frames left out) are rows offsets[p] .. offsets[p+1]-1 of desc (offsets[0] = 0).  best_idx[p] = BestIdx relative

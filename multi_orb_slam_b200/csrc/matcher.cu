@@ -1112,7 +1112,7 @@ __global__ void __launch_bounds__(256) k_fuse_match(const orbx_keypoint* __restr
                                                     const int* __restrict__ grid_start,
                                                     const uint16_t* __restrict__ grid_items, int n_kps,
                                                     const ProjQuery* __restrict__ q, const uint8_t* __restrict__ q_desc,
-                                                    int nq, LevelTable inv_sigma2, int gate,
+                                                    int nq, LevelTable inv_sigma2, int gate, int th_dist,
                                                     int32_t* __restrict__ best_idx) {
   // gate != 0: the pose-based overload (:1986); gate == 0: the Sim3 overload (:2211), which has no reprojection test
   const int lane = threadIdx.x & 31;
@@ -1156,7 +1156,7 @@ __global__ void __launch_bounds__(256) k_fuse_match(const orbx_keypoint* __restr
   const uint32_t gb = __reduce_min_sync(0xffffffffu, best);
   const unsigned owner = __ballot_sync(0xffffffffu, best == gb && my_idx >= 0);
   const int idx = __shfl_sync(0xffffffffu, my_idx, owner ? __ffs(owner) - 1 : 0);
-  if (lane == 0) best_idx[2 * p.src + p.cam] = (gb != 0xFFFFFFFFu && (int)(gb >> 16) <= TH_LOW) ? idx : -1;
+  if (lane == 0) best_idx[2 * p.src + p.cam] = (gb != 0xFFFFFFFFu && (int)(gb >> 16) <= th_dist) ? idx : -1;
 }
 
 // Ordered resolve, best match only (:3558-3637, :3886-3934): queries ascending; candidates that
@@ -2261,7 +2261,7 @@ namespace {
 // device part shared by the two Fuse overloads: per-camera grids + one warp per (map point, camera) query
 int fuse_run(orbm_matcher* m, const orbx_keypoint* kf_k, const uint8_t* kf_desc, const float* kf_uright, const int32_t* kf_cam,
              int n_kf, orbm_bounds b, const std::vector<ProjQuery>& q, const uint8_t* mp_desc, int n_mp,
-             const float* inv_level_sigma2, int nlevels, int gate, int32_t* best_idx, int* n_fused) {
+             const float* inv_level_sigma2, int nlevels, int gate, int32_t* best_idx, int* n_fused, int th_dist = TH_LOW) {
   const int nq = (int)q.size();
   if (nq == 0) return ORBX_OK;
   cudaSetDevice(m->device);
@@ -2292,7 +2292,7 @@ int fuse_run(orbm_matcher* m, const orbx_keypoint* kf_k, const uint8_t* kf_desc,
   }
   LevelTable lt;
   for (int i = 0; i < ORBX_MAX_LEVELS; ++i) lt.v[i] = (inv_level_sigma2 && i < nlevels) ? inv_level_sigma2[i] : 0.f;
-  k_fuse_match<<<(nq + 7) / 8, 256, 0, st>>>(dk, dd, dur, b, gstart, gitems, n_kf, dq, dmd, nq, lt, gate, dbest);
+  k_fuse_match<<<(nq + 7) / 8, 256, 0, st>>>(dk, dd, dur, b, gstart, gitems, n_kf, dq, dmd, nq, lt, gate, th_dist, dbest);
   m->launches++;
   cudaMemcpyAsync(best_idx, dbest, sizeof(int32_t) * 2 * (size_t)n_mp, cudaMemcpyDeviceToHost, st);
   if (!m->check(cudaStreamSynchronize(st), "fuse")) return ORBX_E_CUDA;
@@ -2485,6 +2485,108 @@ int orbm_fuse_sim3_host(orbm_matcher* m, const orbx_keypoint* kf_k, const uint8_
     }
   }
   return fuse_run(m, kf_k, kf_desc, nullptr, kf_cam, n_kf, b, q, mp_desc, n_mp, nullptr, nlevels, 0, best_idx, n_fused);
+}
+
+int orbm_search_by_sim3_host(orbm_matcher* m, const orbx_keypoint* k1, const uint8_t* d1, const int32_t* cam1, int n1,
+                             const float* T1w, const orbx_keypoint* k2, const uint8_t* d2, const int32_t* cam2, int n2,
+                             const float* T2w, orbm_bounds b, const float* scale_factors, int nlevels, float log_scale_factor,
+                             orbm_camera cam, float s12, const float* R12, const float* t12, const float* calib,
+                             const int32_t* mp1_valid, const float* mp1_xyz, const float* mp1_max_dist,
+                             const float* mp1_min_dist, const float* mp1_max_d, const uint8_t* mp1_desc,
+                             const int32_t* mp2_valid, const float* mp2_xyz, const float* mp2_max_dist,
+                             const float* mp2_min_dist, const float* mp2_max_d, const uint8_t* mp2_desc, float th,
+                             int32_t* match12, int* n_found) {
+  if (!m || !T1w || !T2w || !scale_factors || !R12 || !t12 || !calib || !match12 || !n_found || n1 < 0 || n2 < 0 || n1 > 65535 ||
+      n2 > 65535 || nlevels < 1 || nlevels > ORBX_MAX_LEVELS || s12 == 0.f ||
+      (n1 && (!k1 || !d1 || !mp1_valid || !mp1_xyz || !mp1_max_dist || !mp1_min_dist || !mp1_max_d || !mp1_desc)) ||
+      (n2 && (!k2 || !d2 || !mp2_valid || !mp2_xyz || !mp2_max_dist || !mp2_min_dist || !mp2_max_d || !mp2_desc)))
+    return ORBX_E_INVALID;
+  *n_found = 0;
+  for (int i = 0; i < n1; ++i) match12[i] = -1;
+  if (n1 == 0 || n2 == 0) return ORBX_OK;
+  float Rcam21[9], tcam21[3];
+  {
+    double S[9];
+    for (int i = 0; i < 9; ++i) S[i] = calib[i];
+    double d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
+    d = 1. / d;
+    Rcam21[0] = (float)((S[4] * S[8] - S[5] * S[7]) * d); Rcam21[1] = (float)((S[2] * S[7] - S[1] * S[8]) * d);
+    Rcam21[2] = (float)((S[1] * S[5] - S[2] * S[4]) * d); Rcam21[3] = (float)((S[5] * S[6] - S[3] * S[8]) * d);
+    Rcam21[4] = (float)((S[0] * S[8] - S[2] * S[6]) * d); Rcam21[5] = (float)((S[2] * S[3] - S[0] * S[5]) * d);
+    Rcam21[6] = (float)((S[3] * S[7] - S[4] * S[6]) * d); Rcam21[7] = (float)((S[1] * S[6] - S[0] * S[7]) * d);
+    Rcam21[8] = (float)((S[0] * S[4] - S[1] * S[3]) * d);
+  }
+  mat3_mul_vec_add(Rcam21, 3, calib + 9, nullptr, -1.f, tcam21);
+  // sR12 = s12*R12; sR21 = (1.0/s12)*R12.t(); t21 = -sR21*t12   (:2838-2840)
+  float sR12[9], sR21[9], t21[3];
+  const float inv_s12 = (float)(1.0 / (double)s12);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      sR12[i * 3 + j] = R12[i * 3 + j] * s12;
+      sR21[i * 3 + j] = R12[j * 3 + i] * inv_s12;
+    }
+  mat3_mul_vec_add(sR21, 3, t12, nullptr, -1.f, t21);
+  const float t1w[3] = {T1w[3], T1w[7], T1w[11]}, t2w[3] = {T2w[3], T2w[7], T2w[11]};
+  // queries of one direction (:2867-2900 / :2990-3023): points of key frame A into key frame B
+  auto project = [&](int nA, const int32_t* camA, const float* TAw, const float* tAw, const float* sRBA, const float* tBA,
+                     const int32_t* valid, const float* xyz, const float* maxd, const float* mind, const float* maxD,
+                     std::vector<ProjQuery>& q) {
+    q.clear();
+    for (int i = 0; i < nA; ++i) {
+      if (!valid[i]) continue;
+      const int camIdx = camA ? camA[i] : 0;
+      if (camIdx < 0 || camIdx > 1) continue;
+      float pA[3], pB[3];
+      mat3_mul_vec_add(TAw, 4, xyz + 3 * i, tAw, 1.f, pA);
+      mat3_mul_vec_add(sRBA, 3, pA, tBA, 1.f, pB);
+      if (camIdx == 1) {
+        float tmp[3];
+        mat3_mul_vec_add(Rcam21, 3, pB, tcam21, 1.f, tmp);
+        pB[0] = tmp[0]; pB[1] = tmp[1]; pB[2] = tmp[2];
+      }
+      if (pB[2] < 0.0) continue;
+      const float invz = (float)(1.0 / pB[2]);
+      const float x = pB[0] * invz, y = pB[1] * invz;
+      const float u = cam.fx * x + cam.cx, v = cam.fy * y + cam.cy;
+      if (!(u >= b.min_x && u < b.max_x && v >= b.min_y && v < b.max_y)) continue;
+      double n2s = 0;
+      for (int k = 0; k < 3; ++k) n2s += (double)pB[k] * (double)pB[k];
+      const float dist3D = (float)std::sqrt(n2s);
+      if (dist3D < mind[i] || dist3D > maxd[i]) continue;
+      const float ratio = maxD[i] / dist3D;
+      int lvl = (int)std::ceil(std::log(ratio) / log_scale_factor);
+      if (lvl < 0) lvl = 0;
+      else if (lvl >= nlevels) lvl = nlevels - 1;
+      ProjQuery p;
+      p.u = u; p.v = v;
+      p.radius = th * scale_factors[lvl];
+      p.ur = 0.f; p.use_ur = 0; p.angle = 0.f;
+      p.min_level = lvl - 1; p.max_level = lvl;
+      p.cam = camIdx; p.src = i; p.obs = 1;
+      q.push_back(p);
+    }
+  };
+  std::vector<ProjQuery> q;
+  std::vector<int32_t> best1(2 * (size_t)n1, -1), best2(2 * (size_t)n2, -1);
+  int dummy = 0;
+  project(n1, cam1, T1w, t1w, sR21, t21, mp1_valid, mp1_xyz, mp1_max_dist, mp1_min_dist, mp1_max_d, q);
+  int rc = fuse_run(m, k2, d2, nullptr, cam2, n2, b, q, mp1_desc, n1, nullptr, nlevels, 0, best1.data(), &dummy, TH_HIGH);
+  if (rc != ORBX_OK) return rc;
+  project(n2, cam2, T2w, t2w, sR12, t12, mp2_valid, mp2_xyz, mp2_max_dist, mp2_min_dist, mp2_max_d, q);
+  rc = fuse_run(m, k1, d1, nullptr, cam1, n1, b, q, mp2_desc, n2, nullptr, nlevels, 0, best2.data(), &dummy, TH_HIGH);
+  if (rc != ORBX_OK) return rc;
+  // mutual consistency (:3107-3122); a point has one query, in the grid of its own camera
+  auto match_of = [](const std::vector<int32_t>& best, const int32_t* camA, int i) {
+    const int c = camA ? camA[i] : 0;
+    return (c == 0 || c == 1) ? best[2 * (size_t)i + c] : -1;
+  };
+  int nf = 0;
+  for (int i1 = 0; i1 < n1; ++i1) {
+    const int idx2 = match_of(best1, cam1, i1);
+    if (idx2 >= 0 && match_of(best2, cam2, idx2) == i1) { match12[i1] = idx2; nf++; }
+  }
+  *n_found = nf;
+  return ORBX_OK;
 }
 
 #pragma GCC visibility pop

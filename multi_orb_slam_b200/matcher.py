@@ -298,6 +298,29 @@ class ORBmatcher:
             best.ctypes.data, C.byref(nf)))
         return nf.value, best
 
+    # -- SearchBySim3 (src/ORBmatcher.cc:2814-3136) -------------------------------------------------------------
+    def SearchBySim3(self, kf1: Frame, cam1, T1w, kf2: Frame, cam2, T2w, camera: Camera, log_scale_factor: float, s12: float,
+                     R12, t12, calib, mp1, mp2, th: float = 7.5):
+        """mpX = dict(valid, xyz, max_dist, min_dist, max_d, desc) aligned with the keypoints of key frame X.
+        Returns (nFound, match12 [n1]) with match12[i1] = key-frame-2 feature of each new mutual match or -1."""
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        i32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+        sf = f32(kf1.mvScaleFactors)
+        c1, c2 = i32(cam1), i32(cam2)
+        A = [f32(T1w), f32(T2w), f32(R12), f32(t12), f32(calib)]
+        P = []
+        for mp in (mp1, mp2):
+            P += [i32(mp["valid"]), f32(mp["xyz"]), f32(mp["max_dist"]), f32(mp["min_dist"]), f32(mp["max_d"]),
+                  np.ascontiguousarray(mp["desc"], dtype=np.uint8)]
+        m12 = np.empty(kf1.N, dtype=np.int32)
+        nf = C.c_int(0)
+        p = lambda a: None if a is None else a.ctypes.data
+        check_m(self._h, lib.orbm_search_by_sim3_host(
+            self._h, p(kf1.mvKeysUn), p(kf1.mDescriptors), p(c1), kf1.N, p(A[0]), p(kf2.mvKeysUn), p(kf2.mDescriptors), p(c2),
+            kf2.N, p(A[1]), kf1.bounds, p(sf), len(sf), float(log_scale_factor), camera, float(s12), p(A[2]), p(A[3]), p(A[4]),
+            *[p(a) for a in P], float(th), p(m12), C.byref(nf)))
+        return nf.value, m12
+
     # -- SearchByBoW, Frame and KeyFrame variants (src/ORBmatcher.cc:206-388, 390-565, 996-1163, 1180-1363) --
     def SearchByBoW(self, desc1, angle1, valid1, featvec1, desc2, angle2, valid2, featvec2, *, keyframe_pair: bool = False):
         """Side 1 = key frame whose map points are searched (valid1[i] = map point exists and is not

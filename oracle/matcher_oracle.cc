@@ -986,4 +986,97 @@ void om_gemm3_probe(const float* A, const float* x, const float* c, float alpha,
   else mat3_mul_vec_add(A, 3, x, c, alpha, out);
 }
 
+// ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th, CalibMatrix) (src/ORBmatcher.cc:2814-3136,
+// called from LoopClosing::ComputeSim3, src/LoopClosing.cc:402): map points of each key frame are projected into the
+// other one through the Sim3, searched in the per-camera grid of their own camera index within th * scale, best
+// distance <= TH_HIGH, and only mutually consistent pairs are kept (:3107-3122).
+//  key frame x: concatenated keypoints, descriptor per global index, cam (keypoint_to_cam), Txw (4x4 row-major);
+//  map points are aligned with the keypoints (GetMapPointMatches): mpx_valid[i] = point exists, !isBad() and not
+//  already matched (vbAlreadyMatched, :2846-2861); world position, distance invariance limits, mfMaxDistance, descriptor.
+//  match12 (n1) out: key-frame-2 feature of every NEW mutual match, else -1 (vpMatches12[i1] = vpMapPoints2[match12[i1]]).
+int om_search_by_sim3(const oo_keypoint* k1, const uint8_t* d1, const int32_t* cam1, int n1, const float* T1w,
+                      const oo_keypoint* k2, const uint8_t* d2, const int32_t* cam2, int n2, const float* T2w, om_bounds b,
+                      const float* scale_factors, int nlevels, float log_scale_factor, om_camera cam, float s12,
+                      const float* R12, const float* t12, const float* calib, const int32_t* mp1_valid, const float* mp1_xyz,
+                      const float* mp1_max_dist, const float* mp1_min_dist, const float* mp1_max_d, const uint8_t* mp1_desc,
+                      const int32_t* mp2_valid, const float* mp2_xyz, const float* mp2_max_dist, const float* mp2_min_dist,
+                      const float* mp2_max_d, const uint8_t* mp2_desc, float th, int32_t* match12) {
+  float Rcam21[9], tcam21[3];
+  {
+    double S[9];
+    for (int i = 0; i < 9; ++i) S[i] = calib[i];
+    double d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
+    d = 1. / d;
+    Rcam21[0] = (float)((S[4] * S[8] - S[5] * S[7]) * d); Rcam21[1] = (float)((S[2] * S[7] - S[1] * S[8]) * d);
+    Rcam21[2] = (float)((S[1] * S[5] - S[2] * S[4]) * d); Rcam21[3] = (float)((S[5] * S[6] - S[3] * S[8]) * d);
+    Rcam21[4] = (float)((S[0] * S[8] - S[2] * S[6]) * d); Rcam21[5] = (float)((S[2] * S[3] - S[0] * S[5]) * d);
+    Rcam21[6] = (float)((S[3] * S[7] - S[4] * S[6]) * d); Rcam21[7] = (float)((S[1] * S[6] - S[0] * S[7]) * d);
+    Rcam21[8] = (float)((S[0] * S[4] - S[1] * S[3]) * d);
+  }
+  mat3_mul_vec_add(Rcam21, 3, calib + 9, nullptr, -1.f, tcam21);
+  // sR12 = s12*R12; sR21 = (1.0/s12)*R12.t(); t21 = -sR21*t12   (:2838-2840): scalings are float multiplies by the
+  // scalar rounded to float, the last product takes gemm's float path
+  float sR12[9], sR21[9], t21[3];
+  const float inv_s12 = (float)(1.0 / (double)s12);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      sR12[i * 3 + j] = R12[i * 3 + j] * s12;
+      sR21[i * 3 + j] = R12[j * 3 + i] * inv_s12;
+    }
+  mat3_mul_vec_add(sR21, 3, t12, nullptr, -1.f, t21);
+  const float t1w[3] = {T1w[3], T1w[7], T1w[11]}, t2w[3] = {T2w[3], T2w[7], T2w[11]};
+  SoA s1(k1, n1), s2(k2, n2);
+  Grid2 g1(s1.x.data(), s1.y.data(), s1.oct.data(), cam1, n1, b), g2(s2.x.data(), s2.y.data(), s2.oct.data(), cam2, n2, b);
+  std::vector<int> vnMatch1(n1, -1), vnMatch2(n2, -1), cand;
+  // one direction: points of key frame A (pose TAw) into key frame B through (sRBA, tBA)
+  auto pass = [&](int nA, const int32_t* camA, const float* TAw, const float* tAw, const float* sRBA, const float* tBA,
+                  const int32_t* valid, const float* xyz, const float* maxd, const float* mind, const float* maxD,
+                  const uint8_t* mpdesc, const oo_keypoint* kB, const uint8_t* dB, const Grid2& gB, std::vector<int>& out) {
+    for (int i = 0; i < nA; ++i) {
+      if (!valid[i]) continue;
+      const int camIdx = camA ? camA[i] : 0;
+      float pA[3], pB[3];
+      mat3_mul_vec_add(TAw, 4, xyz + 3 * i, tAw, 1.f, pA);
+      mat3_mul_vec_add(sRBA, 3, pA, tBA, 1.f, pB);
+      if (camIdx == 1) {
+        float tmp[3];
+        mat3_mul_vec_add(Rcam21, 3, pB, tcam21, 1.f, tmp);
+        pB[0] = tmp[0]; pB[1] = tmp[1]; pB[2] = tmp[2];
+      }
+      if (pB[2] < 0.0) continue;
+      const float invz = (float)(1.0 / pB[2]);
+      const float x = pB[0] * invz, y = pB[1] * invz;
+      const float u = cam.fx * x + cam.cx, v = cam.fy * y + cam.cy;
+      if (!(u >= b.min_x && u < b.max_x && v >= b.min_y && v < b.max_y)) continue;
+      double n2s = 0;
+      for (int k = 0; k < 3; ++k) n2s += (double)pB[k] * (double)pB[k];
+      const float dist3D = (float)std::sqrt(n2s);
+      if (dist3D < mind[i] || dist3D > maxd[i]) continue;
+      const float ratio = maxD[i] / dist3D;
+      int lvl = (int)std::ceil(std::log(ratio) / log_scale_factor);
+      if (lvl < 0) lvl = 0;
+      else if (lvl >= nlevels) lvl = nlevels - 1;
+      const float radius = th * scale_factors[lvl];
+      const Grid& g = camIdx == 1 ? gB.g1 : gB.g0;
+      g.query(u, v, radius, -1, -1, cand);
+      int bestDist = INT_MAX, bestIdx = -1;
+      for (int idx : cand) {
+        if (kB[idx].octave < lvl - 1 || kB[idx].octave > lvl) continue;
+        const int dd = om_distance(mpdesc + (size_t)i * 32, dB + (size_t)idx * 32);
+        if (dd < bestDist) { bestDist = dd; bestIdx = idx; }
+      }
+      if (bestDist <= TH_HIGH) out[i] = bestIdx;
+    }
+  };
+  pass(n1, cam1, T1w, t1w, sR21, t21, mp1_valid, mp1_xyz, mp1_max_dist, mp1_min_dist, mp1_max_d, mp1_desc, k2, d2, g2, vnMatch1);
+  pass(n2, cam2, T2w, t2w, sR12, t12, mp2_valid, mp2_xyz, mp2_max_dist, mp2_min_dist, mp2_max_d, mp2_desc, k1, d1, g1, vnMatch2);
+  int nFound = 0;
+  for (int i1 = 0; i1 < n1; ++i1) {
+    match12[i1] = -1;
+    const int idx2 = vnMatch1[i1];
+    if (idx2 >= 0 && vnMatch2[idx2] == i1) { match12[i1] = idx2; nFound++; }
+  }
+  return nFound;
+}
+
 }  // extern "C"

@@ -208,6 +208,17 @@ int om_fuse_sim3(const oo_keypoint* kf_k, const uint8_t* kf_desc, const int32_t*
                  const float* mp_max_dist, const float* mp_min_dist, const float* mp_max_d, const uint8_t* mp_desc, int n_mp,
                  float th, int32_t* best_idx);
 
+// ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:2814-3136): mutual projection search between two key frames through a
+// Sim3 (s12, R12 row-major 3x3, t12).  Map-point arrays are aligned with the keypoints of their key frame;
+// mpx_valid[i] = point exists, !isBad(), not already matched.  match12 (n1): new mutual matches (idx2) or -1.
+int om_search_by_sim3(const oo_keypoint* k1, const uint8_t* d1, const int32_t* cam1, int n1, const float* T1w,
+                      const oo_keypoint* k2, const uint8_t* d2, const int32_t* cam2, int n2, const float* T2w, om_bounds b,
+                      const float* scale_factors, int nlevels, float log_scale_factor, om_camera cam, float s12,
+                      const float* R12, const float* t12, const float* calib, const int32_t* mp1_valid, const float* mp1_xyz,
+                      const float* mp1_max_dist, const float* mp1_min_dist, const float* mp1_max_d, const uint8_t* mp1_desc,
+                      const int32_t* mp2_valid, const float* mp2_xyz, const float* mp2_max_dist, const float* mp2_min_dist,
+                      const float* mp2_max_d, const uint8_t* mp2_desc, float th, int32_t* match12);
+
 // Test hook for the cv::Mat 3x3 algebra emulation used by the pose-based searches (pinned against cv2.gemm).
 void om_gemm3_probe(const float* A, const float* x, const float* c, float alpha, int transpose_a, float* out);
 

@@ -326,6 +326,30 @@ def fuse_sim3(kf_k, kf_desc, kf_cam, bounds, sf, log_sf, cam, Scw, calib, mp_val
     return n, best
 
 
+def search_by_sim3(k1, d1, cam1, T1w, k2, d2, cam2, T2w, bounds, sf, log_sf, cam, s12, R12, t12, calib, mp1, mp2, th):
+    lib = load("port")
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    k1, k2 = np.ascontiguousarray(k1, dtype=KP_DTYPE), np.ascontiguousarray(k2, dtype=KP_DTYPE)
+    d1, d2 = np.ascontiguousarray(d1, dtype=np.uint8), np.ascontiguousarray(d2, dtype=np.uint8)
+    c1, c2, sf = i32(cam1), i32(cam2), f32(sf)
+    A = [f32(T1w), f32(T2w), f32(R12), f32(t12), f32(calib)]
+    P = []
+    for mp in (mp1, mp2):
+        P += [i32(mp["valid"]), f32(mp["xyz"]), f32(mp["max_dist"]), f32(mp["min_dist"]), f32(mp["max_d"]),
+              np.ascontiguousarray(mp["desc"], dtype=np.uint8)]
+    m12 = np.empty(len(k1), dtype=np.int32)
+    f = lib.om_search_by_sim3
+    f.restype = C.c_int
+    side = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    f.argtypes = side + side + [Bounds, C.c_void_p, C.c_int, C.c_float, Camera, C.c_float] + [C.c_void_p] * 3 + [C.c_void_p] * 12 + \
+        [C.c_float, C.c_void_p]
+    p = lambda a: a.ctypes.data
+    n = f(p(k1), p(d1), p(c1), len(k1), p(A[0]), p(k2), p(d2), p(c2), len(k2), p(A[1]), Bounds(*bounds), p(sf), len(sf), log_sf,
+          Camera(*cam), float(s12), p(A[2]), p(A[3]), p(A[4]), *[p(a) for a in P], float(th), p(m12))
+    return n, m12
+
+
 def compute_distinctive_descriptors(desc, offsets):
     lib = load("port")
     d = np.ascontiguousarray(desc, dtype=np.uint8).reshape(-1, 32)

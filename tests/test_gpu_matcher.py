@@ -558,3 +558,74 @@ def test_fuse_sim3_vs_oracle(O, th, scale):
                                                 max_d, s["last_desc"], th)
     assert gn == rn and np.array_equal(gbest, rbest)
     assert rn > 100 and (rbest[:, 0] >= 0).any() and (rbest[:, 1] >= 0).any()
+
+
+# ---- SearchBySim3 (src/ORBmatcher.cc:2814-3136) -------------------------------------------------
+@pytest.mark.parametrize("s12,th", [(1.0, 7.5), (1.3, 7.5), (0.8, 3.0)])
+def test_search_by_sim3_vs_oracle(O, s12, th):
+    """Two two-camera key frames observing the same points; key frame 2 = key frame 1 moved by a Sim3."""
+    from multi_orb_slam_b200._lib import Camera, KP_DTYPE
+    from multi_orb_slam_b200.matcher import Frame, ORBmatcher
+    rng = np.random.default_rng(int(s12 * 10 + th))
+    fx, fy, cx, cy, mb, mbf = CAM
+    port0, port1 = O.extractor("port", nfeatures=1000), O.extractor("port", nfeatures=500)
+    kA0, dA0, _ = port0.extract(textured(640, 480, 41))
+    kA1, dA1, _ = port1.extract(textured(640, 480, 141))
+    k1, d1 = np.concatenate([kA0, kA1]), np.concatenate([dA0, dA1])
+    cam1 = np.concatenate([np.zeros(len(kA0), np.int32), np.ones(len(kA1), np.int32)])
+    n1 = len(k1)
+    sf = port0.scale_tables()[0]
+    # 3-D point of every key-frame-1 feature, in the frame of its own camera, then in the world (T1w = identity-ish)
+    T1w = np.eye(4)
+    T1w[:3, :3], T1w[:3, 3] = _rot(0.01, 0.02, -0.01), [0.1, 0.0, -0.05]
+    R12c, t12c = CALIB[:3].astype(np.float64), CALIB[3].astype(np.float64)
+    z = rng.uniform(1.5, 7.0, n1)
+    Xown = np.stack([(k1["x"] - cx) / fx * z, (k1["y"] - cy) / fy * z, z], axis=1)
+    Xc0 = np.where((cam1 == 1)[:, None], Xown @ R12c.T + t12c, Xown)   # camera-2 frame -> rig frame: R12 x + t12
+    Xw = (Xc0 - T1w[:3, 3]) @ T1w[:3, :3]
+    # Sim3 between the key frames: X1 = s12 * R12 * X2 + t12
+    R12 = _rot(0.02, -0.015, 0.01)
+    t12 = np.array([0.15, -0.03, 0.05])
+    T2w = np.eye(4)
+    R21 = R12.T
+    T2w[:3, :3] = R21 @ T1w[:3, :3]
+    T2w[:3, 3] = R21 @ (T1w[:3, 3] - t12) / 1.0
+    # key frame 2: re-observations of random key-frame-1 features, projected with the inverse Sim3
+    n2 = 1400
+    src = rng.integers(0, n1, n2)
+    X1 = Xw[src] @ T1w[:3, :3].T + T1w[:3, 3]
+    X2 = ((X1 - t12) @ R12) / s12                                        # R12^T (X1 - t12) / s
+    is1 = cam1[src] == 1
+    R21c, t21c = np.linalg.inv(R12c), -np.linalg.inv(R12c) @ t12c
+    X2own = np.where(is1[:, None], X2 @ R21c.T + t21c, X2)
+    k2 = np.zeros(n2, KP_DTYPE)
+    k2["x"] = fx * X2own[:, 0] / X2own[:, 2] + cx + rng.normal(0, 1.5, n2)
+    k2["y"] = fy * X2own[:, 1] / X2own[:, 2] + cy + rng.normal(0, 1.5, n2)
+    k2["octave"] = np.clip(k1["octave"][src] + rng.integers(-1, 2, n2), 0, 7)
+    k2["angle"], k2["size"] = k1["angle"][src], 31
+    bits = np.unpackbits(d1[src], axis=1)
+    flips = rng.integers(0, 80, n2)
+    bits ^= (np.argsort(np.argsort(rng.random((n2, 256)), axis=1), axis=1) < flips[:, None]).astype(np.uint8)
+    d2 = np.packbits(bits, axis=1)
+    cam2 = cam1[src].copy()
+    # world points of key frame 2's map points (in ITS world: the reference uses each key frame's own pose)
+    Xw2 = (X2 - T2w[:3, 3]) @ T2w[:3, :3]
+
+    def points(xyz, Tw, n, desc, octave):
+        Xc = xyz @ Tw[:3, :3].T + Tw[:3, 3]
+        dist = np.linalg.norm(Xc, axis=1)
+        max_d = (dist * 1.2 ** octave * rng.uniform(0.9, 1.1, n)).astype(np.float32)
+        return dict(valid=(rng.random(n) < 0.85).astype(np.int32), xyz=xyz.astype(np.float32),
+                    max_dist=(3.0 * max_d).astype(np.float32), min_dist=(0.2 * max_d / 1.2 ** 7).astype(np.float32), max_d=max_d,
+                    desc=desc)
+
+    mp1, mp2 = points(Xw, T1w, n1, d1, k1["octave"]), points(Xw2, T2w, n2, d2, k2["octave"])
+    log_sf = float(np.log(np.float32(1.2)))
+    rn, rm12 = O.search_by_sim3(k1, d1, cam1, T1w, k2, d2, cam2, T2w, (0, 640, 0, 480), sf, log_sf, CAM, s12, R12, t12, CALIB,
+                                mp1, mp2, th)
+    F1 = Frame(k1, d1, 640, 480, mvScaleFactors=sf)
+    F2 = Frame(k2, d2, 640, 480, mvScaleFactors=sf)
+    gn, gm12 = ORBmatcher(0.75, True).SearchBySim3(F1, cam1, T1w, F2, cam2, T2w, Camera(*CAM), log_sf, s12, R12, t12, CALIB, mp1, mp2, th)
+    assert gn == rn and np.array_equal(gm12, rm12)
+    if s12 == 1.0:
+        assert rn > 30
