@@ -346,6 +346,21 @@ typedef struct {
   int32_t n_nodes;
 } orbm_featvec;
 
+/* DBoW2 vocabulary transform, the producer of the feature vectors above: Frame::ComputeBoW / KeyFrame::ComputeBoW
+ * (src/Frame.cc:649-671, src/KeyFrame.cc) call ORBVocabulary::transform(vCurrentDesc, mBowVec, mFeatVec, 4)
+ * (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1195; tree descent :1218-1259; BowVector.cpp:34-46, 62-84).
+ * orbm_set_vocabulary uploads the tree once: children of node i = child_ids[child_start[i] .. child_start[i+1]) in
+ * m_nodes[i].children order (node 0 = root), node descriptors (32 bytes each), word id of the leaves (-1 for inner
+ * nodes), node weights (WordValue), L = depth levels (m_L).  TF / TF_IDF weighting with L1 scoring (ORBvoc.txt).
+ * orbm_bow_transform_host: per feature word / node at level L - levelsup / weight (each may be NULL), the BowVector
+ * (bow_word ascending, bow_value L1-normalised, capacity n) and the FeatureVector as CSR (fv_node ascending, capacity n;
+ * fv_start n + 1; fv_items n), features with weight 0 (stopped words) left out. */
+int orbm_set_vocabulary(orbm_matcher* m, const int32_t* child_start, const int32_t* child_ids, const uint8_t* node_desc,
+                        const int32_t* word_id, const double* node_weight, int n_nodes, int L);
+int orbm_bow_transform_host(orbm_matcher* m, const uint8_t* desc, int n, int levelsup, int32_t* word, int32_t* node, double* weight,
+                            int32_t* bow_word, double* bow_value, int32_t* n_bow, int32_t* fv_node, int32_t* fv_start,
+                            int32_t* fv_items, int32_t* n_fv);
+
 /* ORBmatcher::SearchByBoW, all four variants:
  *   SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches)        src/ORBmatcher.cc:206-388   (Tracking.cc:1238, 2031)
  *   SearchByBoW_cam1(KeyFrame*, Frame&, vpMapPointMatches)   src/ORBmatcher.cc:390-565

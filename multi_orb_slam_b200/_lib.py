@@ -118,6 +118,8 @@ _SIGS = {
                                 _f, _vp, C.POINTER(_i)]),
     "orbm_search_by_sim3_host": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, Bounds, _vp, _i, _f, Camera, _f, _vp, _vp,
                                      _vp] + [_vp] * 12 + [_f, _vp, C.POINTER(_i)]),
+    "orbm_set_vocabulary": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "orbm_bow_transform_host": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i), _vp, _vp, _vp, C.POINTER(_i)]),
     "orbm_compute_distinctive_descriptors_host": (_i, [_vp, _vp, _vp, _i, _vp]),
     "orbm_undistort_keypoints_device": (_i, [_vp, _i, _i, _vp, _vp, _f, _f, _f, _f, _vp, _vp]),
     "orbm_undistort_keypoints_host": (_i, [_vp, _vp, _i, _f, _f, _f, _f, _vp, _vp]),

@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/orb_b200.h"
@@ -626,6 +627,39 @@ __global__ void __launch_bounds__(128) k_distinctive(const uint8_t* __restrict__
   }
   __syncthreads();
   if (tid == 0) best_idx[p] = (int)(s_best & 0xFFFFu);
+}
+
+// ---- DBoW2 vocabulary descent (TemplatedVocabulary.h:1218-1259) --------------------------------
+// Warp per feature: at every level the lanes take the node's children (k = 10 in ORBvoc), the child with the
+// least Hamming distance wins, the first one on ties (`d < best_d`) = min over dist << 8 | child position.
+__global__ void __launch_bounds__(256) k_bow_descend(const int32_t* __restrict__ child_start, const int32_t* __restrict__ child_ids,
+                                                     const uint8_t* __restrict__ node_desc, const uint8_t* __restrict__ desc, int n,
+                                                     int nid_level, int32_t* __restrict__ leaf, int32_t* __restrict__ node) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const uint4* qp = reinterpret_cast<const uint4*>(desc + (size_t)i * 32);
+  const uint4 qa = __ldg(qp), qb = __ldg(qp + 1);
+  int final_id = 0, level = 0, nid = 0;
+  int c0 = child_start[0], c1 = child_start[1];
+  while (c0 != c1) {  // !isLeaf()
+    ++level;
+    uint32_t best = 0xFFFFFFFFu;
+    for (int c = c0 + lane; c < c1; c += 32) {
+      const int id = child_ids[c];
+      const uint4* tp = reinterpret_cast<const uint4*>(node_desc + (size_t)id * 32);
+      best = min(best, (uint32_t)hamming256(qa, qb, __ldg(tp), __ldg(tp + 1)) << 20 | (uint32_t)(c - c0));
+    }
+    best = __reduce_min_sync(0xffffffffu, best);
+    final_id = child_ids[c0 + (int)(best & 0xFFFFFu)];
+    if (level == nid_level) nid = final_id;
+    c0 = child_start[final_id];
+    c1 = child_start[final_id + 1];
+  }
+  if (lane == 0) {
+    leaf[i] = final_id;
+    node[i] = nid;
+  }
 }
 
 // ---- Frame glue between extractor and matchers (src/Frame.cc) ---------------------------------
@@ -1261,6 +1295,13 @@ struct orbm_matcher {
   // growable device scratch
   void* buf[12] = {nullptr};
   size_t buf_bytes[12] = {0};
+  // DBoW2 vocabulary tree (orbm_set_vocabulary)
+  int voc_nodes = 0, voc_L = 0;
+  int32_t* voc_child_start = nullptr;
+  int32_t* voc_child_ids = nullptr;
+  uint8_t* voc_desc = nullptr;
+  std::vector<int32_t> voc_word;
+  std::vector<double> voc_weight;
 
   bool check(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return true;
@@ -1329,6 +1370,7 @@ int orbm_create(int device, orbm_matcher** out) {
 }
 
 void orbm_destroy(orbm_matcher* m) {
+  if (m) { cudaFree(m->voc_child_start); cudaFree(m->voc_child_ids); cudaFree(m->voc_desc); }
   if (!m) return;
   cudaStreamSynchronize(m->stream);
   for (auto& b : m->buf) cudaFree(b);
@@ -2586,6 +2628,94 @@ int orbm_search_by_sim3_host(orbm_matcher* m, const orbx_keypoint* k1, const uin
     if (idx2 >= 0 && match_of(best2, cam2, idx2) == i1) { match12[i1] = idx2; nf++; }
   }
   *n_found = nf;
+  return ORBX_OK;
+}
+
+int orbm_set_vocabulary(orbm_matcher* m, const int32_t* child_start, const int32_t* child_ids, const uint8_t* node_desc,
+                        const int32_t* word_id, const double* node_weight, int n_nodes, int L) {
+  if (!m || !child_start || !node_desc || !word_id || !node_weight || n_nodes < 1 || L < 1 || child_start[0] != 0) return ORBX_E_INVALID;
+  const int n_children = child_start[n_nodes];
+  if (n_children < 0 || (n_children && !child_ids)) return ORBX_E_INVALID;
+  for (int i = 0; i < n_nodes; ++i)
+    if (child_start[i + 1] < child_start[i] || child_start[i + 1] - child_start[i] > 0xFFFFF) { m->err = "vocabulary: bad child table"; return ORBX_E_INVALID; }
+  for (int c = 0; c < n_children; ++c)
+    if (child_ids[c] <= 0 || child_ids[c] >= n_nodes) { m->err = "vocabulary: child id out of range"; return ORBX_E_INVALID; }
+  if (child_start[1] == 0) { m->err = "vocabulary: the root has no children"; return ORBX_E_INVALID; }
+  cudaSetDevice(m->device);
+  cudaStreamSynchronize(m->stream);
+  cudaFree(m->voc_child_start); cudaFree(m->voc_child_ids); cudaFree(m->voc_desc);
+  m->voc_child_start = m->voc_child_ids = nullptr; m->voc_desc = nullptr; m->voc_nodes = 0;
+  if (!m->check(cudaMalloc(&m->voc_child_start, sizeof(int32_t) * (n_nodes + 1)), "cudaMalloc(vocabulary)") ||
+      !m->check(cudaMalloc(&m->voc_child_ids, sizeof(int32_t) * std::max(n_children, 1)), "cudaMalloc(vocabulary)") ||
+      !m->check(cudaMalloc(&m->voc_desc, (size_t)n_nodes * 32), "cudaMalloc(vocabulary)"))
+    return ORBX_E_CUDA;
+  cudaMemcpy(m->voc_child_start, child_start, sizeof(int32_t) * (n_nodes + 1), cudaMemcpyHostToDevice);
+  if (n_children) cudaMemcpy(m->voc_child_ids, child_ids, sizeof(int32_t) * n_children, cudaMemcpyHostToDevice);
+  cudaMemcpy(m->voc_desc, node_desc, (size_t)n_nodes * 32, cudaMemcpyHostToDevice);
+  m->voc_word.assign(word_id, word_id + n_nodes);
+  m->voc_weight.assign(node_weight, node_weight + n_nodes);
+  m->voc_nodes = n_nodes;
+  m->voc_L = L;
+  return m->check(cudaGetLastError(), "vocabulary upload") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+int orbm_bow_transform_host(orbm_matcher* m, const uint8_t* desc, int n, int levelsup, int32_t* word, int32_t* node, double* weight,
+                            int32_t* bow_word, double* bow_value, int32_t* n_bow, int32_t* fv_node, int32_t* fv_start,
+                            int32_t* fv_items, int32_t* n_fv) {
+  if (!m || n < 0 || (n && !desc) || !n_bow || !n_fv || !fv_start || (n && (!bow_word || !bow_value || !fv_node || !fv_items)))
+    return ORBX_E_INVALID;
+  if (!m->voc_nodes) { m->err = "no vocabulary set (orbm_set_vocabulary)"; return ORBX_E_STATE; }
+  *n_bow = *n_fv = 0;
+  fv_start[0] = 0;
+  if (n == 0) return ORBX_OK;
+  cudaSetDevice(m->device);
+  cudaStream_t st = m->stream;
+  uint8_t* dd = m->scratch<uint8_t>(8, (size_t)n * 32);
+  int32_t* dout = m->scratch<int32_t>(4, 2 * (size_t)n);
+  if (!dd || !dout) return ORBX_E_CUDA;
+  cudaMemcpyAsync(dd, desc, (size_t)n * 32, cudaMemcpyHostToDevice, st);
+  const int nid_level = m->voc_L - levelsup;
+  k_bow_descend<<<(n + 7) / 8, 256, 0, st>>>(m->voc_child_start, m->voc_child_ids, m->voc_desc, dd, n, nid_level, dout, dout + n);
+  m->launches += 1;
+  std::vector<int32_t> h(2 * (size_t)n);
+  cudaMemcpyAsync(h.data(), dout, sizeof(int32_t) * 2 * n, cudaMemcpyDeviceToHost, st);
+  if (!m->check(cudaStreamSynchronize(st), "bow transform")) return ORBX_E_CUDA;
+  if (!m->check(cudaGetLastError(), "bow transform launch")) return ORBX_E_CUDA;
+  // BowVector / FeatureVector assembly (TemplatedVocabulary.h:1149-1194, BowVector.cpp:34-46, 62-84): std::map
+  // semantics on sorted vectors, weights summed in feature order, L1 norm summed in word order, all in double
+  std::vector<std::pair<int, double>> bow;
+  std::vector<std::pair<int, std::vector<int>>> fv;
+  for (int i = 0; i < n; ++i) {
+    const int leaf_id = h[i], nid = nid_level <= 0 ? 0 : h[n + i];
+    const int w_id = m->voc_word[leaf_id];
+    const double w = m->voc_weight[leaf_id];
+    if (word) word[i] = w_id;
+    if (node) node[i] = nid;
+    if (weight) weight[i] = w;
+    if (w > 0) {
+      auto vit = std::lower_bound(bow.begin(), bow.end(), w_id, [](const std::pair<int, double>& a, int b) { return a.first < b; });
+      if (vit != bow.end() && vit->first == w_id) vit->second += w;
+      else bow.insert(vit, std::make_pair(w_id, w));
+      auto fit = std::lower_bound(fv.begin(), fv.end(), nid,
+                                  [](const std::pair<int, std::vector<int>>& a, int b) { return a.first < b; });
+      if (fit != fv.end() && fit->first == nid) fit->second.push_back(i);
+      else fv.insert(fit, std::make_pair(nid, std::vector<int>(1, i)));
+    }
+  }
+  double norm = 0.0;
+  for (auto& e : bow) norm += std::fabs(e.second);
+  if (norm > 0.0)
+    for (auto& e : bow) e.second /= norm;
+  *n_bow = (int)bow.size();
+  for (size_t j = 0; j < bow.size(); ++j) { bow_word[j] = bow[j].first; bow_value[j] = bow[j].second; }
+  *n_fv = (int)fv.size();
+  int run = 0;
+  for (size_t j = 0; j < fv.size(); ++j) {
+    fv_node[j] = fv[j].first;
+    fv_start[j] = run;
+    for (int idx : fv[j].second) fv_items[run++] = idx;
+  }
+  fv_start[fv.size()] = run;
   return ORBX_OK;
 }
 

@@ -298,6 +298,32 @@ class ORBmatcher:
             best.ctypes.data, C.byref(nf)))
         return nf.value, best
 
+    # -- DBoW2 vocabulary transform (Frame::ComputeBoW, src/Frame.cc:649-659) ----------------------------------
+    def set_vocabulary(self, child_start, child_ids, node_desc, word_id, node_weight, L: int) -> None:
+        """Upload the vocabulary tree (see include/orb_b200.h: orbm_set_vocabulary; synth.random_vocabulary)."""
+        cs, ci = np.ascontiguousarray(child_start, dtype=np.int32), np.ascontiguousarray(child_ids, dtype=np.int32)
+        nd = np.ascontiguousarray(node_desc, dtype=np.uint8).reshape(-1, 32)
+        wi, ww = np.ascontiguousarray(word_id, dtype=np.int32), np.ascontiguousarray(node_weight, dtype=np.float64)
+        if len(cs) != len(nd) + 1 or len(wi) != len(nd) or len(ww) != len(nd):
+            raise ValueError("vocabulary arrays must have n_nodes (+1 for child_start) entries")
+        check_m(self._h, lib.orbm_set_vocabulary(self._h, cs.ctypes.data, ci.ctypes.data, nd.ctypes.data, wi.ctypes.data,
+                                                 ww.ctypes.data, len(nd), int(L)))
+
+    def ComputeBoW(self, desc, levelsup: int = 4):
+        """mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, levelsup).  Returns a dict: word, node,
+        weight (per feature), bow = (word ids ascending, L1-normalised values), featvec = (node ids, start, items)."""
+        d = np.ascontiguousarray(desc, dtype=np.uint8).reshape(-1, 32)
+        n = len(d)
+        word, node, weight = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.float64)
+        bw, bv = np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.float64)
+        fn, fs, fi = np.empty(max(n, 1), np.int32), np.empty(n + 1, np.int32), np.empty(max(n, 1), np.int32)
+        nb, nf = C.c_int(0), C.c_int(0)
+        check_m(self._h, lib.orbm_bow_transform_host(self._h, d.ctypes.data, n, int(levelsup), word.ctypes.data, node.ctypes.data,
+                                                     weight.ctypes.data, bw.ctypes.data, bv.ctypes.data, C.byref(nb),
+                                                     fn.ctypes.data, fs.ctypes.data, fi.ctypes.data, C.byref(nf)))
+        return dict(word=word, node=node, weight=weight, bow=(bw[: nb.value].copy(), bv[: nb.value].copy()),
+                    featvec=(fn[: nf.value].copy(), fs[: nf.value + 1].copy(), fi[: fs[nf.value]].copy()))
+
     # -- SearchBySim3 (src/ORBmatcher.cc:2814-3136) -------------------------------------------------------------
     def SearchBySim3(self, kf1: Frame, cam1, T1w, kf2: Frame, cam2, T2w, camera: Camera, log_scale_factor: float, s12: float,
                      R12, t12, calib, mp1, mp2, th: float = 7.5):

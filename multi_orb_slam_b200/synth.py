@@ -195,3 +195,44 @@ def triangulation_scene(n1: int, n2: int, n_nodes: int, seed: int, n_levels: int
                 uright2=np.where(rng.random(n2) < 0.2, k2["x"] - 5, -1).astype(np.float32), node2=node2,
                 F12s=F12s.astype(np.float32), epipoles=np.array(epi, dtype=np.float32), scale_factors=sf,
                 level_sigma2=(sf * sf).astype(np.float32), src=src)
+
+
+def random_vocabulary(k: int, L: int, seed: int, p_stop: float = 0.02, p_short: float = 0.05):
+    """A DBoW2-shaped vocabulary tree for tests (the real ORBvoc.txt, k = 10, L = 6, is not shipped with the
+    reference): node 0 is the root, every inner node has 2..k children whose descriptors are noisy copies of the
+    parent's (like k-means centres of a cluster), a few branches end early (leaves above depth L, as DBoW2
+    produces for small clusters), a few words carry weight 0 (stopped).  Nodes are numbered in creation order,
+    depth first like TemplatedVocabulary::HKmeansStep; words in leaf creation order."""
+    rng = np.random.default_rng(seed)
+    desc, children, depth = [rng.integers(0, 256, 32, dtype=np.uint8)], [[]], [0]
+
+    def grow(node):
+        if depth[node] == L or (depth[node] >= 1 and rng.random() < p_short):
+            return
+        n_child = k if rng.random() < 0.8 else int(rng.integers(2, k + 1))
+        ids = []
+        for _ in range(n_child):
+            bits = np.unpackbits(desc[node])
+            flip = rng.random(256) < 0.5 ** (depth[node] + 1) * 0.6
+            desc.append(np.packbits(bits ^ flip.astype(np.uint8)))
+            children.append([])
+            depth.append(depth[node] + 1)
+            ids.append(len(desc) - 1)
+        children[node] = ids
+        for c in ids:
+            grow(c)
+
+    import sys
+    sys.setrecursionlimit(10000)
+    grow(0)
+    n = len(desc)
+    child_start = np.zeros(n + 1, dtype=np.int32)
+    child_start[1:] = np.cumsum([len(c) for c in children])
+    child_ids = np.array([c for cs in children for c in cs], dtype=np.int32)
+    word_id = np.full(n, -1, dtype=np.int32)
+    leaves = [i for i in range(n) if not children[i]]
+    word_id[leaves] = np.arange(len(leaves))
+    weight = np.zeros(n, dtype=np.float64)
+    weight[leaves] = np.where(rng.random(len(leaves)) < p_stop, 0.0, rng.uniform(0.5, 9.0, len(leaves)))
+    return dict(child_start=child_start, child_ids=child_ids, node_desc=np.stack(desc), word_id=word_id, node_weight=weight,
+                L=L, depth=np.array(depth))

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstring>
 #include <algorithm>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -1077,6 +1078,69 @@ int om_search_by_sim3(const oo_keypoint* k1, const uint8_t* d1, const int32_t* c
     if (idx2 >= 0 && vnMatch2[idx2] == i1) { match12[i1] = idx2; nFound++; }
   }
   return nFound;
+}
+
+// DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>::transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1195
+// with the per-feature tree descent :1218-1259), as Frame::ComputeBoW calls it (src/Frame.cc:649-659, levelsup = 4;
+// ORBvoc: k = 10, L = 6, TF_IDF weighting, L1 scoring).  The vocabulary tree is given as flat arrays: children of node
+// i = child_ids[child_start[i] .. child_start[i+1]) in m_nodes[i].children order, node descriptors (32 bytes), word id
+// of the leaves (-1 for inner nodes) and node weights (WordValue = double).
+//  per feature: word[i], node[i] (the ancestor at level L - levelsup; 0 when that level is <= 0 or is never reached,
+//  where the reference leaves nid uninitialised), weight[i].
+//  BowVector (TF / TF_IDF + L1): bow_word/bow_value sorted by word id, *n_bow entries (capacity n): addWeight in
+//  feature order (BowVector.cpp:34-46), then normalize(L1) (:62-84).
+//  FeatureVector as CSR: fv_node (capacity n) ascending, fv_start (n+1), fv_items (n), *n_fv nodes.
+void om_bow_transform(const int32_t* child_start, const int32_t* child_ids, const uint8_t* node_desc, const int32_t* word_id,
+                      const double* node_weight, int n_nodes, int L, const uint8_t* desc, int n, int levelsup, int32_t* word,
+                      int32_t* node, double* weight, int32_t* bow_word, double* bow_value, int32_t* n_bow, int32_t* fv_node,
+                      int32_t* fv_start, int32_t* fv_items, int32_t* n_fv) {
+  (void)n_nodes;
+  const int nid_level = L - levelsup;
+  std::vector<std::pair<int, double>> bow;                 // BowVector = std::map<WordId, WordValue>
+  std::vector<std::pair<int, std::vector<int>>> fv;        // FeatureVector = std::map<NodeId, vector<unsigned>>
+  for (int i = 0; i < n; ++i) {
+    const uint8_t* f = desc + (size_t)i * 32;
+    int nid = 0;  // reference: uninitialised unless nid_level is reached
+    int final_id = 0, current_level = 0;
+    do {
+      ++current_level;
+      const int c0 = child_start[final_id], c1 = child_start[final_id + 1];
+      final_id = child_ids[c0];
+      double best_d = om_distance(f, node_desc + (size_t)final_id * 32);
+      for (int c = c0 + 1; c < c1; ++c) {
+        const int id = child_ids[c];
+        const double d = om_distance(f, node_desc + (size_t)id * 32);
+        if (d < best_d) { best_d = d; final_id = id; }
+      }
+      if (current_level == nid_level) nid = final_id;
+    } while (child_start[final_id] != child_start[final_id + 1]);
+    word[i] = word_id[final_id];
+    weight[i] = node_weight[final_id];
+    node[i] = nid;
+    if (weight[i] > 0) {  // not stopped (:1158)
+      auto vit = std::lower_bound(bow.begin(), bow.end(), word[i], [](const std::pair<int, double>& a, int b) { return a.first < b; });
+      if (vit != bow.end() && vit->first == word[i]) vit->second += weight[i];
+      else bow.insert(vit, std::make_pair(word[i], weight[i]));
+      auto fit = std::lower_bound(fv.begin(), fv.end(), nid,
+                                  [](const std::pair<int, std::vector<int>>& a, int b) { return a.first < b; });
+      if (fit != fv.end() && fit->first == nid) fit->second.push_back(i);
+      else fv.insert(fit, std::make_pair(nid, std::vector<int>(1, i)));
+    }
+  }
+  double norm = 0.0;  // normalize(L1)
+  for (auto& e : bow) norm += std::fabs(e.second);
+  if (norm > 0.0)
+    for (auto& e : bow) e.second /= norm;
+  *n_bow = (int)bow.size();
+  for (size_t j = 0; j < bow.size(); ++j) { bow_word[j] = bow[j].first; bow_value[j] = bow[j].second; }
+  *n_fv = (int)fv.size();
+  int run = 0;
+  for (size_t j = 0; j < fv.size(); ++j) {
+    fv_node[j] = fv[j].first;
+    fv_start[j] = run;
+    for (int idx : fv[j].second) fv_items[run++] = idx;
+  }
+  fv_start[fv.size()] = run;
 }
 
 }  // extern "C"

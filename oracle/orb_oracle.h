@@ -219,6 +219,13 @@ int om_search_by_sim3(const oo_keypoint* k1, const uint8_t* d1, const int32_t* c
                       const int32_t* mp2_valid, const float* mp2_xyz, const float* mp2_max_dist, const float* mp2_min_dist,
                       const float* mp2_max_d, const uint8_t* mp2_desc, float th, int32_t* match12);
 
+// DBoW2 vocabulary transform as Frame::ComputeBoW calls it (TemplatedVocabulary.h:1127-1195, 1218-1259; src/Frame.cc:657):
+// per-feature word / node (level L - levelsup) / weight, the L1-normalised TF-IDF BowVector and the FeatureVector (CSR).
+void om_bow_transform(const int32_t* child_start, const int32_t* child_ids, const uint8_t* node_desc, const int32_t* word_id,
+                      const double* node_weight, int n_nodes, int L, const uint8_t* desc, int n, int levelsup, int32_t* word,
+                      int32_t* node, double* weight, int32_t* bow_word, double* bow_value, int32_t* n_bow, int32_t* fv_node,
+                      int32_t* fv_start, int32_t* fv_items, int32_t* n_fv);
+
 // Test hook for the cv::Mat 3x3 algebra emulation used by the pose-based searches (pinned against cv2.gemm).
 void om_gemm3_probe(const float* A, const float* x, const float* c, float alpha, int transpose_a, float* out);
 

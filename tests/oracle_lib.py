@@ -350,6 +350,29 @@ def search_by_sim3(k1, d1, cam1, T1w, k2, d2, cam2, T2w, bounds, sf, log_sf, cam
     return n, m12
 
 
+def bow_transform(voc, desc, levelsup=4):
+    """voc: dict(child_start, child_ids, node_desc, word_id, node_weight, L) as synth.random_vocabulary returns."""
+    lib = load("port")
+    cs, ci = np.ascontiguousarray(voc["child_start"], dtype=np.int32), np.ascontiguousarray(voc["child_ids"], dtype=np.int32)
+    nd = np.ascontiguousarray(voc["node_desc"], dtype=np.uint8)
+    wi, ww = np.ascontiguousarray(voc["word_id"], dtype=np.int32), np.ascontiguousarray(voc["node_weight"], dtype=np.float64)
+    d = np.ascontiguousarray(desc, dtype=np.uint8).reshape(-1, 32)
+    n = len(d)
+    word, node, weight = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.float64)
+    bw, bv = np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.float64)
+    fn, fs, fi = np.empty(max(n, 1), np.int32), np.empty(n + 1, np.int32), np.empty(max(n, 1), np.int32)
+    nb, nf = C.c_int(0), C.c_int(0)
+    f = lib.om_bow_transform
+    f.restype = None
+    f.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.POINTER(C.c_int)] + \
+        [C.c_void_p] * 3 + [C.POINTER(C.c_int)]
+    f(cs.ctypes.data, ci.ctypes.data, nd.ctypes.data, wi.ctypes.data, ww.ctypes.data, len(nd), int(voc["L"]), d.ctypes.data, n,
+      int(levelsup), word.ctypes.data, node.ctypes.data, weight.ctypes.data, bw.ctypes.data, bv.ctypes.data, C.byref(nb),
+      fn.ctypes.data, fs.ctypes.data, fi.ctypes.data, C.byref(nf))
+    return dict(word=word, node=node, weight=weight, bow=(bw[: nb.value].copy(), bv[: nb.value].copy()),
+                featvec=(fn[: nf.value].copy(), fs[: nf.value + 1].copy(), fi[: fs[nf.value]].copy()))
+
+
 def compute_distinctive_descriptors(desc, offsets):
     lib = load("port")
     d = np.ascontiguousarray(desc, dtype=np.uint8).reshape(-1, 32)

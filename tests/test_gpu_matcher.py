@@ -629,3 +629,36 @@ def test_search_by_sim3_vs_oracle(O, s12, th):
     assert gn == rn and np.array_equal(gm12, rm12)
     if s12 == 1.0:
         assert rn > 30
+
+
+# ---- DBoW2 vocabulary transform (Frame::ComputeBoW) ----------------------------------------------
+@pytest.mark.parametrize("k,L,levelsup,n", [(10, 4, 2, 2000), (10, 3, 4, 500), (4, 6, 4, 1500), (10, 5, 4, 3000)])
+def test_compute_bow_vs_oracle(O, k, L, levelsup, n):
+    from multi_orb_slam_b200.matcher import ORBmatcher
+    from multi_orb_slam_b200.synth import random_vocabulary
+    voc = random_vocabulary(k, L, 10 * k + L)
+    rng = np.random.default_rng(n)
+    leaves = np.nonzero(voc["word_id"] >= 0)[0]
+    base = voc["node_desc"][rng.choice(leaves, n)]
+    desc = np.packbits(np.unpackbits(base, axis=1) ^ (rng.random((n, 256)) < 0.05).astype(np.uint8), axis=1)
+    m = ORBmatcher(0.7, True)
+    m.set_vocabulary(voc["child_start"], voc["child_ids"], voc["node_desc"], voc["word_id"], voc["node_weight"], voc["L"])
+    got = m.ComputeBoW(desc, levelsup)
+    ref = O.bow_transform(voc, desc, levelsup)
+    for key in ("word", "node", "weight"):
+        assert np.array_equal(got[key], ref[key]), key
+    assert np.array_equal(got["bow"][0], ref["bow"][0]) and np.array_equal(got["bow"][1], ref["bow"][1])  # doubles, bit for bit
+    for a, b in zip(got["featvec"], ref["featvec"]):
+        assert np.array_equal(a, b)
+    # the feature vector feeds SearchByBoW: the frame against itself matches (almost) every feature to itself
+    ang = np.zeros(n, np.float32)
+    nm, m12, _ = m.SearchByBoW(desc, ang, None, got["featvec"], desc, ang, None, got["featvec"])
+    rn, rm12, _ = O.search_by_bow(desc, ang, None, ref["featvec"], desc, ang, None, ref["featvec"], 0.7, True, 50)
+    assert nm == rn and np.array_equal(m12, rm12)
+
+
+def test_compute_bow_requires_vocabulary():
+    from multi_orb_slam_b200._lib import OrbError
+    from multi_orb_slam_b200.matcher import ORBmatcher
+    with pytest.raises(OrbError):
+        ORBmatcher(0.7, True).ComputeBoW(np.zeros((3, 32), np.uint8))

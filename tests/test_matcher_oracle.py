@@ -386,3 +386,45 @@ def test_compute_distinctive_descriptors_vs_numpy(O):
         D = np.unpackbits(d[:, None, :] ^ d[None, :, :], axis=2).sum(axis=2)
         med = np.sort(D, axis=1)[:, int(0.5 * (n - 1))]
         assert got[p] == int(np.argmin(med)), f"point {p} (N={n})"  # argmin = first minimum (:414-420)
+
+
+# ---- DBoW2 vocabulary transform (TemplatedVocabulary.h:1127-1195, 1218-1259) ---------------------
+def test_bow_transform_vs_python(O):
+    from multi_orb_slam_b200.synth import random_vocabulary
+    voc = random_vocabulary(6, 4, 3)
+    rng = np.random.default_rng(4)
+    leaves = np.nonzero(voc["word_id"] >= 0)[0]
+    base = voc["node_desc"][rng.choice(leaves, 300)]
+    bits = np.unpackbits(base, axis=1) ^ (rng.random((300, 256)) < 0.04).astype(np.uint8)
+    desc = np.packbits(bits, axis=1)
+    got = O.bow_transform(voc, desc, levelsup=2)
+    cs, ci = voc["child_start"], voc["child_ids"]
+    dist = lambda a, b: int(np.unpackbits(a ^ b).sum())
+    bow, fv = {}, {}
+    for i in range(len(desc)):
+        node, level, nid = 0, 0, 0
+        while cs[node] != cs[node + 1]:
+            level += 1
+            kids = ci[cs[node]:cs[node + 1]]
+            best, node = dist(desc[i], voc["node_desc"][kids[0]]), int(kids[0])
+            for c in kids[1:]:
+                d = dist(desc[i], voc["node_desc"][c])
+                if d < best:
+                    best, node = d, int(c)
+            if level == voc["L"] - 2:
+                nid = node
+        assert got["word"][i] == voc["word_id"][node] and got["node"][i] == nid and got["weight"][i] == voc["node_weight"][node]
+        w = voc["node_weight"][node]
+        if w > 0:
+            bow[int(voc["word_id"][node])] = bow.get(int(voc["word_id"][node]), 0.0) + w
+            fv.setdefault(nid, []).append(i)
+    words = sorted(bow)
+    norm = 0.0
+    for wd in words:
+        norm += abs(bow[wd])
+    assert list(got["bow"][0]) == words and list(got["bow"][1]) == [bow[wd] / norm for wd in words]
+    nodes = sorted(fv)
+    assert list(got["featvec"][0]) == nodes
+    for j, nd in enumerate(nodes):
+        assert list(got["featvec"][2][got["featvec"][1][j]:got["featvec"][1][j + 1]]) == fv[nd]
+    assert abs(sum(got["bow"][1]) - 1.0) < 1e-12 and len(nodes) > 5
