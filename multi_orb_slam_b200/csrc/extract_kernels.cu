@@ -198,19 +198,20 @@ __global__ void __launch_bounds__(128) k_pyr_resize(int level, int rows_per_tile
 // a corner survives the 3x3 NMS iff its m is strictly greater than its 8 neighbours' m
 // (neighbours outside this cell's tested area count as 0 — NMS is per cell).
 //
-// Work is split the way the arithmetic cost falls (measured on the synthetic frames: at th=20
-// only ~13 % of pixels survive the 4-pair high-speed test and ~6 % are corners):
+// Work is split the way the arithmetic cost falls (on the synthetic frames 16-30 % of the pixels
+// of a level survive the rejection test at th=20 and 5-12 % are corners):
 //   phase A  every tested pixel: opposite-pair rejection test on packed bytes, four pixels per
-//            lane (~12 instr/px), survivors appended to a shared-memory queue;
-//   phase B  queued pixels only: full arc measure with 3-input min/max (VIMNMX3), dense again;
-//   NMS      ballots over the linearised tested area, ordered compaction = reference order.
-// The pass runs at iniThFAST; only a cell that kept nothing reruns at minThFAST (:813-817).
-#ifndef FAST_NT
-#define FAST_NT 32  // threads per cell CTA: ONE warp per cell.  Measured with the 48-byte pitch (128 frames, ms):
+//            lane (~16 lane-instr/px), surviving words queued, then expanded to one entry per pixel;
+//   phase B  queued pixels only: full arc measure on 16-bit pairs carrying both polarities
+//            (VIMNMX3.S16x2), corners compacted in place;
+//   phase C  3x3 NMS over the corner list.
+// One warp walks the cell in row-major order and every compaction is ordered, so all lists stay in
+// cv::FAST's output order.  The pass runs at iniThFAST; only a cell that kept nothing reruns at
+// minThFAST (:813-817).  (Trimming the per-cell setup - float-reciprocal divisions, flat-indexed
+// tile load - was measured and changes nothing: 1.126 vs 1.118 ms.)
+#define FAST_NT 32  // threads per cell CTA: ONE warp per cell.  Measured with more warps per cell (128 frames, ms):
                     // 32 -> 0.42, 64 -> 0.48, 96 -> 0.49, 128 -> 0.50, 160 -> 0.56, 256 -> 0.74: a cell is ~1000 px,
                     // more warps only add barrier and tail idle time
-#endif
-#define FAST_NW (FAST_NT / 32)
 
 struct FastSmem {
   // Three regions of shared memory, each reused once its first tenant is dead (6 KB per cell CTA
