@@ -125,10 +125,12 @@ _libs = {}
 
 
 def load(kind: str = "port"):
-    """kind: 'port' (restatement) or 'ref' (verbatim reference build; None if absent)."""
+    """kind: 'port' (restatement), 'ref' (verbatim ORBextractor.cc build) or 'mref' (verbatim ORBmatcher.cc build);
+    the verbatim builds are None where oracle/_ref was not built."""
     if kind in _libs:
         return _libs[kind]
-    path = os.path.join(ORACLE_DIR, "liborb_oracle.so" if kind == "port" else "_ref/liborb_ref.so")
+    path = os.path.join(ORACLE_DIR, {"port": "liborb_oracle.so", "ref": "_ref/liborb_ref.so",
+                                     "mref": "_ref/libmatcher_ref.so"}[kind])
     if kind == "port" and not os.path.exists(path):
         build_oracle()
     lib = C.CDLL(path) if os.path.exists(path) else None
@@ -182,15 +184,15 @@ def features_in_area(kx, ky, koct, bounds, x, y, r, min_level, max_level):
     return out[:n].copy()
 
 
-def search_for_initialization(k1, d1, k2, d2, bounds2, prev_xy, window=100, nnratio=0.9, check_ori=True):
-    lib = load("port")
+def search_for_initialization(k1, d1, k2, d2, bounds2, prev_xy, window=100, nnratio=0.9, check_ori=True, impl="port"):
+    lib = load("port" if impl == "port" else "mref")
     k1 = np.ascontiguousarray(k1, dtype=KP_DTYPE)
     k2 = np.ascontiguousarray(k2, dtype=KP_DTYPE)
     d1 = np.ascontiguousarray(d1, dtype=np.uint8)
     d2 = np.ascontiguousarray(d2, dtype=np.uint8)
     prev = np.ascontiguousarray(prev_xy, dtype=np.float32).copy()
     m12 = np.zeros(len(k1), dtype=np.int32)
-    f = lib.om_search_for_initialization
+    f = getattr(lib, ("om_" if impl == "port" else "omr_") + "search_for_initialization")
     f.restype = C.c_int
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, Bounds, C.c_void_p,
                   C.c_int, C.c_float, C.c_int, C.c_void_p]
@@ -200,8 +202,8 @@ def search_for_initialization(k1, d1, k2, d2, bounds2, prev_xy, window=100, nnra
 
 
 def search_by_projection_points(k, d, u_right, bounds, scale_factors, mp, mp_desc, mp_obs, th, nnratio,
-                                frame_mp=None, frame_mp_obs=None):
-    lib = load("port")
+                                frame_mp=None, frame_mp_obs=None, impl="port"):
+    lib = load("port" if impl == "port" else "mref")
     k = np.ascontiguousarray(k, dtype=KP_DTYPE)
     d = np.ascontiguousarray(d, dtype=np.uint8)
     n = len(k)
@@ -212,7 +214,7 @@ def search_by_projection_points(k, d, u_right, bounds, scale_factors, mp, mp_des
     mp_obs = np.ascontiguousarray(mp_obs, dtype=np.int32)
     fmp = np.full(n, -1, dtype=np.int32) if frame_mp is None else np.ascontiguousarray(frame_mp, dtype=np.int32).copy()
     fobs = np.zeros(n, dtype=np.int32) if frame_mp_obs is None else np.ascontiguousarray(frame_mp_obs, dtype=np.int32)
-    f = lib.om_search_by_projection_points
+    f = getattr(lib, ("om_" if impl == "port" else "omr_") + "search_by_projection_points")
     f.restype = C.c_int
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, Bounds, C.c_void_p, C.c_int, C.c_void_p,
                   C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
@@ -228,8 +230,8 @@ class Camera(C.Structure):
 
 
 def search_by_projection_frame(cur_k, cur_desc, cur_uright, cur_cam, bounds, sf, cam, Tcw_cur, Tcw_last, last_k, last_cam,
-                               last_valid, last_xyz, last_desc, last_obs, calib, th, mono, check_ori, cur_mp, cur_mp_obs):
-    lib = load("port")
+                               last_valid, last_xyz, last_desc, last_obs, calib, th, mono, check_ori, cur_mp, cur_mp_obs, impl="port"):
+    lib = load("port" if impl == "port" else "mref")
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
     i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
     cur_k, last_k = np.ascontiguousarray(cur_k, dtype=KP_DTYPE), np.ascontiguousarray(last_k, dtype=KP_DTYPE)
@@ -237,7 +239,7 @@ def search_by_projection_frame(cur_k, cur_desc, cur_uright, cur_cam, bounds, sf,
     ur, sf, tc, tl, xyz, cal = f32(cur_uright), f32(sf), f32(Tcw_cur), f32(Tcw_last), f32(last_xyz), f32(calib)
     ccam, lcam, lval, lobs, fobs = i32(cur_cam), i32(last_cam), i32(last_valid), i32(last_obs), i32(cur_mp_obs)
     fmp = i32(cur_mp).copy()
-    f = lib.om_search_by_projection_frame
+    f = getattr(lib, ("om_" if impl == "port" else "omr_") + "search_by_projection_frame")
     f.restype = C.c_int
     f.argtypes = [C.c_void_p] * 4 + [C.c_int, Bounds, C.c_void_p, C.c_int, Camera] + [C.c_void_p] * 8 + \
                  [C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -249,15 +251,15 @@ def search_by_projection_frame(cur_k, cur_desc, cur_uright, cur_cam, bounds, sf,
 
 
 def search_by_projection_keyframe(cur_k, cur_desc, bounds, sf, log_sf, cam, Tcw_cur, kf_valid, kf_xyz, kf_max_dist,
-                                  kf_min_dist, kf_max_d, kf_angle, kf_desc, th, orb_dist, check_ori, cur_mp):
-    lib = load("port")
+                                  kf_min_dist, kf_max_d, kf_angle, kf_desc, th, orb_dist, check_ori, cur_mp, impl="port"):
+    lib = load("port" if impl == "port" else "mref")
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
     cur_k = np.ascontiguousarray(cur_k, dtype=KP_DTYPE)
     cur_desc, kf_desc = np.ascontiguousarray(cur_desc, dtype=np.uint8), np.ascontiguousarray(kf_desc, dtype=np.uint8)
     sf, tc, xyz, mx, mn, md, ang = f32(sf), f32(Tcw_cur), f32(kf_xyz), f32(kf_max_dist), f32(kf_min_dist), f32(kf_max_d), f32(kf_angle)
     val = np.ascontiguousarray(kf_valid, dtype=np.int32)
     fmp = np.ascontiguousarray(cur_mp, dtype=np.int32).copy()
-    f = lib.om_search_by_projection_keyframe
+    f = getattr(lib, ("om_" if impl == "port" else "omr_") + "search_by_projection_keyframe")
     f.restype = C.c_int
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, Bounds, C.c_void_p, C.c_int, C.c_float, Camera] + [C.c_void_p] * 8 + \
                  [C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p]
@@ -268,15 +270,15 @@ def search_by_projection_keyframe(cur_k, cur_desc, bounds, sf, log_sf, cam, Tcw_
 
 
 def search_by_projection_sim3(kf_k, kf_desc, kf_cam, bounds, sf, log_sf, cam, Scw, calib, mp_valid, mp_xyz, mp_normal,
-                              mp_max_dist, mp_min_dist, mp_max_d, mp_desc, th, matched):
-    lib = load("port")
+                              mp_max_dist, mp_min_dist, mp_max_d, mp_desc, th, matched, impl="port"):
+    lib = load("port" if impl == "port" else "mref")
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
     kf_k = np.ascontiguousarray(kf_k, dtype=KP_DTYPE)
     kf_desc, mp_desc = np.ascontiguousarray(kf_desc, dtype=np.uint8), np.ascontiguousarray(mp_desc, dtype=np.uint8)
     kcam, val = np.ascontiguousarray(kf_cam, dtype=np.int32), np.ascontiguousarray(mp_valid, dtype=np.int32)
     sf, S, cal, xyz, nrm, mx, mn, md = (f32(a) for a in (sf, Scw, calib, mp_xyz, mp_normal, mp_max_dist, mp_min_dist, mp_max_d))
     out = np.ascontiguousarray(matched, dtype=np.int32).copy()
-    f = lib.om_search_by_projection_sim3
+    f = getattr(lib, ("om_" if impl == "port" else "omr_") + "search_by_projection_sim3")
     f.restype = C.c_int
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, Bounds, C.c_void_p, C.c_int, C.c_float, Camera] + \
                  [C.c_void_p] * 9 + [C.c_int, C.c_int, C.c_void_p]
@@ -481,6 +483,32 @@ def search_for_triangulation(sc, fv1, fv2, only_stereo=False, cam_enabled=(1, 1)
           *[p(a) for a in arrs2], len(k2), p(f2[0]), p(f2[1]), p(f2[2]), len(f2[0]),
           *[p(a) for a in tail], int(only_stereo), p(en), int(check_ori), p(m12))
     return n, m12
+
+
+def search_by_bow_ref(variant, d1, angle1, valid1, fv1, d2, angle2, valid2, fv2, nnratio=0.7, check_ori=True):
+    """The reference's own SearchByBoW (verbatim build): variant 0 = (KeyFrame*, Frame&), 1 = (KeyFrame*, KeyFrame*)."""
+    lib = load("mref")
+    c = lambda a, t: np.ascontiguousarray(a, dtype=t)
+    d1, d2, a1, a2 = c(d1, np.uint8), c(d2, np.uint8), c(angle1, np.float32), c(angle2, np.float32)
+    v1 = None if valid1 is None else c(valid1, np.int32)
+    v2 = None if valid2 is None else c(valid2, np.int32)
+    f1, f2 = [c(a, np.int32) for a in fv1], [c(a, np.int32) for a in fv2]
+    m12, m21 = np.zeros(len(d1), np.int32), np.zeros(len(d2), np.int32)
+    f = lib.omr_search_by_bow
+    f.restype = C.c_int
+    side = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    f.argtypes = [C.c_int] + side + side + [C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    p = lambda a: None if a is None else a.ctypes.data
+    n = f(variant, p(d1), p(a1), p(v1), len(d1), p(f1[0]), p(f1[1]), p(f1[2]), len(f1[0]),
+          p(d2), p(a2), p(v2), len(d2), p(f2[0]), p(f2[1]), p(f2[2]), len(f2[0]), nnratio, int(check_ori), p(m12), p(m21))
+    return n, m12, m21
+
+
+def distance_ref(a, b):
+    lib = load("mref")
+    a, b = np.ascontiguousarray(a, dtype=np.uint8), np.ascontiguousarray(b, dtype=np.uint8)
+    lib.omr_distance.argtypes = [C.c_void_p, C.c_void_p]
+    return lib.omr_distance(a.ctypes.data, b.ctypes.data)
 
 
 def three_maxima(counts):

@@ -1,0 +1,144 @@
+"""Pins the matcher restatement (oracle/matcher_oracle.cc, the checker of every GPU matcher test) against the
+reference's OWN src/ORBmatcher.cc, compiled verbatim from /root/reference into oracle/_ref/libmatcher_ref.so
+(oracle/Makefile; OpenCV-API shim + Frame/KeyFrame/MapPoint stand-ins in oracle/shim_matcher).  Same seeded
+scenes as tests/test_gpu_matcher.py.  Skipped where the verbatim build is absent."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from test_gpu_matcher import CALIB, CAM, _frame_pair, _projection_case, _rig_scene
+
+pytestmark = pytest.mark.skipif(O.load("mref") is None, reason="oracle/_ref/libmatcher_ref.so not built (no /root/reference)")
+
+
+def test_descriptor_distance():
+    rng = np.random.default_rng(0)
+    a, b = rng.integers(0, 256, (200, 32), dtype=np.uint8), rng.integers(0, 256, (200, 32), dtype=np.uint8)
+    for x, y in zip(a, b):
+        assert O.distance_ref(x, y) == O.distance(x, y)
+    assert O.distance_ref(np.zeros(32, np.uint8), np.full(32, 255, np.uint8)) == 256
+
+
+@pytest.mark.parametrize("seed,window,check_ori", [(0, 100, True), (1, 30, True), (2, 100, False), (3, 1000, True), (4, 10, True)])
+def test_search_for_initialization(seed, window, check_ori):
+    k1, d1, k2, d2 = _frame_pair(O, seed)
+    prev = np.stack([k1["x"], k1["y"]], axis=1).astype(np.float32)
+    a = O.search_for_initialization(k1, d1, k2, d2, (0, 640, 0, 480), prev, window, 0.9, check_ori)
+    b = O.search_for_initialization(k1, d1, k2, d2, (0, 640, 0, 480), prev, window, 0.9, check_ori, impl="ref")
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert a[0] > 20 or window == 10
+    # second round with the updated vbPrevMatched, like Tracking::MonocularInitialization re-entering
+    a2 = O.search_for_initialization(k1, d1, k2, d2, (0, 640, 0, 480), a[2], window, 0.9, check_ori)
+    b2 = O.search_for_initialization(k1, d1, k2, d2, (0, 640, 0, 480), b[2], window, 0.9, check_ori, impl="ref")
+    assert a2[0] == b2[0] and np.array_equal(a2[1], b2[1]) and np.array_equal(a2[2], b2[2])
+
+
+@pytest.mark.parametrize("nmp,th,with_stereo,with_obs", [(3000, 3.0, False, False), (3000, 1.0, True, True), (8000, 5.0, True, True)])
+def test_search_by_projection_points(nmp, th, with_stereo, with_obs):
+    k, d, mp, mp_desc, rng = _projection_case(O, 7, nmp)
+    n = len(k)
+    sf = O.extractor("port").scale_tables()[0]
+    ur = np.where(rng.random(n) < 0.6, k["x"] - rng.uniform(0, 12, n), -1).astype(np.float32) if with_stereo else None
+    fmp0 = np.full(n, -1, np.int32)
+    fobs0 = np.zeros(n, np.int32)
+    mobs = np.ones(nmp, np.int32)
+    if with_obs:
+        held = rng.random(n) < 0.15
+        fmp0[held] = 0
+        fobs0[held] = rng.random(held.sum()) < 0.6
+        mobs = (rng.random(nmp) < 0.8).astype(np.int32)
+    a = O.search_by_projection_points(k, d, ur, (0, 1241, 0, 376), sf, mp, mp_desc, mobs, th, 0.8, fmp0, fobs0)
+    b = O.search_by_projection_points(k, d, ur, (0, 1241, 0, 376), sf, mp, mp_desc, mobs, th, 0.8, fmp0, fobs0, impl="ref")
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    assert a[0] > 50
+
+
+@pytest.mark.parametrize("offset,th,mono,check_ori", [((0, 0, 0), 15.0, False, True), ((0, 0, 0.5), 15.0, False, True),
+                                                      ((0, 0, -0.5), 7.0, False, True), ((0.5, 0, 0), 15.0, True, False)])
+def test_search_by_projection_frame(offset, th, mono, check_ori):
+    s = _rig_scene(O, 3, 1500, offset)
+    sf = O.extractor("port").scale_tables()[0]
+    n = s["n"]
+    fmp0 = np.full(n, -1, np.int32)
+    fobs0 = np.zeros(n, np.int32)
+    held = s["rng"].random(n) < 0.1
+    fmp0[held] = 0
+    fobs0[held] = s["rng"].random(held.sum()) < 0.5
+    args = (s["cur_k"], s["cur_d"], s["ur"], s["cur_cam"], (0, 640, 0, 480), sf, CAM, s["Tcw"], s["Tlw"], s["last_k"], s["last_cam"],
+            s["last_valid"], s["last_xyz"], s["last_desc"], s["last_obs"], CALIB, th, mono, check_ori, fmp0, fobs0)
+    a = O.search_by_projection_frame(*args)
+    b = O.search_by_projection_frame(*args, impl="ref")
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    assert a[0] > 100
+
+
+@pytest.mark.parametrize("th,orb_dist,check_ori", [(10.0, 100, True), (3.0, 64, True), (10.0, 100, False)])
+def test_search_by_projection_keyframe(th, orb_dist, check_ori):
+    s = _rig_scene(O, 9, 1200, (0, 0, 0))
+    sel = s["cur_cam"] == 0
+    cur_k, cur_d = s["cur_k"][sel], s["cur_d"][sel]
+    keep = s["last_cam"] == 0
+    xyz, desc, ang = s["last_xyz"][keep], s["last_desc"][keep], s["last_k"]["angle"][keep]
+    nk = len(xyz)
+    rng = s["rng"]
+    sf = O.extractor("port").scale_tables()[0]
+    Ow = -s["Tcw"][:3, :3].T @ s["Tcw"][:3, 3]
+    dist = np.linalg.norm(xyz - Ow, axis=1)
+    max_d = (dist * rng.uniform(0.8, 4.0, nk)).astype(np.float32)
+    kf_max, kf_min = (1.2 * max_d).astype(np.float32), (0.8 * max_d / 1.2 ** 7).astype(np.float32)
+    valid = (rng.random(nk) < 0.9).astype(np.int32)
+    fmp0 = np.full(len(cur_k), -1, np.int32)
+    fmp0[rng.random(len(cur_k)) < 0.1] = 5
+    log_sf = float(np.log(np.float32(1.2)))
+    args = (cur_k, cur_d, (0, 640, 0, 480), sf, log_sf, CAM, s["Tcw"], valid, xyz, kf_max, kf_min, max_d, ang, desc, th, orb_dist,
+            check_ori, fmp0)
+    a = O.search_by_projection_keyframe(*args)
+    b = O.search_by_projection_keyframe(*args, impl="ref")
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    assert a[0] > 100
+
+
+@pytest.mark.parametrize("th,scale", [(10, 1.0), (4, 1.7)])
+def test_search_by_projection_sim3(th, scale):
+    s = _rig_scene(O, 13, 1800, (0, 0, 0))
+    rng = s["rng"]
+    n, nmp = s["n"], len(s["last_xyz"])
+    sf = O.extractor("port").scale_tables()[0]
+    Scw = s["Tcw"].astype(np.float64).copy()
+    Scw[:3, :] *= scale
+    xyz = s["last_xyz"].astype(np.float64)
+    Ow = -s["Tcw"][:3, :3].T.astype(np.float64) @ s["Tcw"][:3, 3].astype(np.float64)
+    PO = xyz - Ow
+    dist = np.linalg.norm(PO, axis=1)
+    normal = PO / dist[:, None] + rng.normal(0, 0.3, (nmp, 3))
+    normal /= np.linalg.norm(normal, axis=1)[:, None]
+    max_d = (dist * rng.uniform(0.8, 4.0, nmp)).astype(np.float32)
+    kf_max, kf_min = (1.2 * max_d).astype(np.float32), (0.8 * max_d / 1.2 ** 7).astype(np.float32)
+    valid = (rng.random(nmp) < 0.9).astype(np.int32)
+    matched0 = np.full(n, -1, np.int32)
+    matched0[rng.random(n) < 0.1] = 3
+    log_sf = float(np.log(np.float32(1.2)))
+    args = (s["cur_k"], s["cur_d"], s["cur_cam"], (0, 640, 0, 480), sf, log_sf, CAM, Scw, CALIB, valid, xyz, normal, kf_max, kf_min,
+            max_d, s["last_desc"], th, matched0)
+    a = O.search_by_projection_sim3(*args)
+    b = O.search_by_projection_sim3(*args, impl="ref")
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    assert a[0] > 50
+
+
+@pytest.mark.parametrize("seed,n_nodes,check_ori,variant", [(0, 12, True, 0), (1, 40, True, 1), (2, 5, False, 0), (3, 200, True, 1),
+                                                           (4, 100, True, 0)])
+def test_search_by_bow(seed, n_nodes, check_ori, variant):
+    from multi_orb_slam_b200.synth import bow_scene, feature_vector
+    n1, n2 = 900, 1000
+    sc = bow_scene(n1, n2, n_nodes, seed)
+    rng = np.random.default_rng(100 + seed)
+    node1 = np.where(rng.random(n1) < 0.05, -1, sc["node1"])
+    node2 = np.where(sc["node2"] % 7 == 3, -1, sc["node2"])
+    fv1, fv2 = feature_vector(node1), feature_vector(node2)
+    v1 = (rng.random(n1) < 0.8).astype(np.int32)
+    v2 = (rng.random(n2) < 0.9).astype(np.int32) if variant == 1 else None
+    a = O.search_by_bow(sc["d1"], sc["a1"], v1, fv1, sc["d2"], sc["a2"], v2, fv2, 0.7, check_ori, 50 if variant == 0 else 49)
+    b = O.search_by_bow_ref(variant, sc["d1"], sc["a1"], v1, fv1, sc["d2"], sc["a2"], v2, fv2, 0.7, check_ori)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert a[0] > 20
