@@ -5,6 +5,7 @@
 // object graph the reference expects, calls the reference and flattens the result, so that
 // tests/test_matcher_ref.py can pin the restatement (and through it the GPU kernels) to the reference code.
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 
@@ -309,6 +310,145 @@ int omr_search_by_bow(int variant, const uint8_t* d1, const float* angle1, const
     }
   }
   return nm;
+}
+
+// ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:1364-1720).  Poses instead of the fundamental matrices (the
+// reference recomputes them, :1376-1449): T1w / T2w = Tcw of camera 1 then camera 2 (2 x 16 floats), Cw1 = camera
+// centres of key frame 1 (2 x 3).  F12s_out / epipoles_out return what those lines compute, evaluated here with the
+// same expressions on the same shim, for feeding the flat-array implementations.
+int omr_search_for_triangulation(const oo_keypoint* k1, const uint8_t* d1, const int32_t* has_mp1, const int32_t* cam1,
+                                 const float* uright1, int n1, const int32_t* node1, const int32_t* start1,
+                                 const int32_t* items1, int nn1, const oo_keypoint* k2, const uint8_t* d2,
+                                 const int32_t* has_mp2, const int32_t* cam2, const float* uright2, int n2,
+                                 const int32_t* node2, const int32_t* start2, const int32_t* items2, int nn2,
+                                 const float* T1w, const float* T2w, const float* Cw1, om_camera cam, const float* scale_factors2,
+                                 const float* level_sigma2_2, int nlevels, int only_stereo, const int32_t* cam_enabled,
+                                 int check_ori, int32_t* matches12, float* F12s_out, float* epipoles_out) {
+  const om_bounds b = {0.f, 640.f, 0.f, 480.f};
+  KeyFrame KF1, KF2;
+  fill_rig(KF1, k1, d1, cam1, uright1, n1, b);
+  fill_rig(KF2, k2, d2, cam2, uright2, n2, b);
+  KF1.mFeatVec = featvec(node1, start1, items1, nn1);
+  KF2.mFeatVec = featvec(node2, start2, items2, nn2);
+  std::vector<MapPoint> p1(n1), p2(n2);
+  KF1.mvpMapPoints.assign(n1, nullptr);
+  KF2.mvpMapPoints.assign(n2, nullptr);
+  for (int i = 0; i < n1; ++i) if (has_mp1[i]) KF1.mvpMapPoints[i] = &p1[i];
+  for (int i = 0; i < n2; ++i) if (has_mp2[i]) KF2.mvpMapPoints[i] = &p2[i];
+  const float Kf[9] = {cam.fx, 0, cam.cx, 0, cam.fy, cam.cy, 0, 0, 1};
+  KF1.mK = fmat(Kf, 3, 3); KF2.mK = fmat(Kf, 3, 3);
+  set_camera(KF1, cam, b); set_camera(KF2, cam, b);
+  KF1.Tcw = fmat(T1w, 4, 4); KF1.Tcw_cam2 = fmat(T1w + 16, 4, 4);
+  KF2.Tcw = fmat(T2w, 4, 4); KF2.Tcw_cam2 = fmat(T2w + 16, 4, 4);
+  KF1.Ow = fmat(Cw1, 3, 1); KF1.Ow_cam2 = fmat(Cw1 + 3, 3, 1);
+  KF2.mvScaleFactors.assign(scale_factors2, scale_factors2 + nlevels);
+  KF2.mvLevelSigma2.assign(level_sigma2_2, level_sigma2_2 + nlevels);
+  // the quantities of :1376-1449, same expressions
+  for (int c = 0; c < 2; ++c) {
+    cv::Mat R1w = c ? KF1.GetRotation_cam2() : KF1.GetRotation(), t1w = c ? KF1.GetTranslation_cam2() : KF1.GetTranslation();
+    cv::Mat R2w = c ? KF2.GetRotation_cam2() : KF2.GetRotation(), t2w = c ? KF2.GetTranslation_cam2() : KF2.GetTranslation();
+    cv::Mat R12 = R1w * R2w.t();
+    cv::Mat t12 = -R1w * R2w.t() * t2w + t1w;
+    cv::Mat t12x = (cv::Mat_<float>(3, 3) << 0, -t12.at<float>(2), t12.at<float>(1), t12.at<float>(2), 0, -t12.at<float>(0),
+                    -t12.at<float>(1), t12.at<float>(0), 0);
+    cv::Mat F12 = KF1.mK.t().inv() * t12x * R12 * KF2.mK.inv();
+    for (int i = 0; i < 9; ++i) F12s_out[9 * c + i] = F12.at<float>(i / 3, i % 3);
+    cv::Mat Cw = c ? KF1.GetCameraCenter_cam2() : KF1.GetCameraCenter();
+    cv::Mat C2 = R2w * Cw + t2w;
+    const float invz = 1.0f / C2.at<float>(2);
+    epipoles_out[2 * c] = KF2.fx * C2.at<float>(0) * invz + KF2.cx;
+    epipoles_out[2 * c + 1] = KF2.fy * C2.at<float>(1) * invz + KF2.cy;
+  }
+  std::vector<std::pair<size_t, size_t>> pairs;
+  std::vector<bool> vbCam = {cam_enabled[0] != 0, cam_enabled[1] != 0};
+  ORBmatcher matcher(0.6f, check_ori != 0);
+  const int nm = matcher.SearchForTriangulation(&KF1, &KF2, cv::Mat(), pairs, only_stereo != 0, vbCam);
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  for (auto& pr : pairs) matches12[pr.first] = (int32_t)pr.second;
+  return nm;
+}
+
+// ORBmatcher::Fuse, both two-camera overloads (src/ORBmatcher.cc:1986-2190 with Tcw / Ow; :2211-2441 with sim3 != 0,
+// where pose = Scw and Ow is ignored).  kf_held[i] != 0: the key-frame feature already holds a map point (with more
+// observations than the candidates when kf_held[i] == 2).  best_idx as om_fuse, read back from a call trace.
+int omr_fuse(int sim3, const oo_keypoint* kf_k, const uint8_t* kf_desc, const float* kf_uright, const int32_t* kf_cam,
+             const int32_t* kf_held, int n_kf, om_bounds b, const float* scale_factors, const float* inv_level_sigma2, int nlevels,
+             float log_scale_factor, om_camera cam, const float* pose, const float* Ow, const float* calib,
+             const int32_t* mp_valid, const float* mp_xyz, const float* mp_normal, const float* mp_max_dist,
+             const float* mp_min_dist, const float* mp_max_d, const uint8_t* mp_desc, int n_mp, float th, int32_t* best_idx) {
+  set_bounds(b);
+  KeyFrame KF;
+  fill_rig(KF, kf_k, kf_desc, kf_cam, kf_uright, n_kf, b);
+  set_levels(KF, scale_factors, nlevels, log_scale_factor);
+  KF.mvInvLevelSigma2.assign(nlevels, 1.f);
+  if (inv_level_sigma2) KF.mvInvLevelSigma2.assign(inv_level_sigma2, inv_level_sigma2 + nlevels);
+  set_camera(KF, cam, b);
+  std::vector<MapPoint> held(n_kf), pts(n_mp);
+  KF.mvpMapPoints.assign(n_kf, nullptr);
+  for (int i = 0; i < n_kf; ++i)
+    if (kf_held && kf_held[i]) { held[i].nObs = kf_held[i] == 2 ? 100 : 0; KF.mvpMapPoints[i] = &held[i]; }
+  std::vector<MapPoint*> vp(n_mp);
+  for (int i = 0; i < n_mp; ++i) {
+    pts[i] = make_point(mp_xyz + 3 * i, mp_normal + 3 * i, mp_max_dist[i], mp_min_dist[i], mp_max_d[i], mp_desc + (size_t)i * 32, 3,
+                        !mp_valid[i]);
+    vp[i] = &pts[i];
+  }
+  for (int i = 0; i < 2 * n_mp; ++i) best_idx[i] = -1;
+  MapPoint::trace().clear();
+  ORBmatcher matcher(0.6f, true);
+  int nf;
+  std::vector<MapPoint*> vpReplace(n_mp, nullptr);
+  if (!sim3) {
+    KF.Tcw = fmat(pose, 4, 4);
+    KF.Ow = fmat(Ow, 3, 1); KF.Ow_cam2 = fmat(Ow + 3, 3, 1);
+    nf = matcher.Fuse(&KF, vp, fmat(calib, 4, 3), th);
+  } else {
+    std::vector<int> cams(n_mp, 0);
+    nf = matcher.Fuse(&KF, fmat(pose, 4, 4), vp, cams, th, vpReplace, fmat(calib, 4, 3));
+  }
+  // read the fused (map point, feature) pairs back from the trace
+  int cur = -1;
+  for (const MapPoint::Trace& t : MapPoint::trace()) {
+    if (t.kind == 0) cur = index_in(pts, static_cast<const MapPoint*>(t.p));
+    else if (cur >= 0) best_idx[2 * cur + KF.keypoint_to_cam[(size_t)t.idx]] = (int32_t)t.idx;
+  }
+  return nf;
+}
+
+// ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:2814-3136); arguments as om_search_by_sim3.
+int omr_search_by_sim3(const oo_keypoint* k1, const uint8_t* d1, const int32_t* cam1, int n1, const float* T1w,
+                       const oo_keypoint* k2, const uint8_t* d2, const int32_t* cam2, int n2, const float* T2w, om_bounds b,
+                       const float* scale_factors, int nlevels, float log_scale_factor, om_camera cam, float s12,
+                       const float* R12, const float* t12, const float* calib, const int32_t* mp1_valid, const float* mp1_xyz,
+                       const float* mp1_max_dist, const float* mp1_min_dist, const float* mp1_max_d, const uint8_t* mp1_desc,
+                       const int32_t* mp2_valid, const float* mp2_xyz, const float* mp2_max_dist, const float* mp2_min_dist,
+                       const float* mp2_max_d, const uint8_t* mp2_desc, float th, int32_t* match12) {
+  set_bounds(b);
+  KeyFrame KF1, KF2;
+  fill_rig(KF1, k1, d1, cam1, nullptr, n1, b);
+  fill_rig(KF2, k2, d2, cam2, nullptr, n2, b);
+  set_levels(KF1, scale_factors, nlevels, log_scale_factor);
+  set_levels(KF2, scale_factors, nlevels, log_scale_factor);
+  set_camera(KF1, cam, b); set_camera(KF2, cam, b);
+  KF1.Tcw = fmat(T1w, 4, 4); KF2.Tcw = fmat(T2w, 4, 4);
+  std::vector<MapPoint> p1(n1), p2(n2);
+  KF1.mvpMapPoints.assign(n1, nullptr);
+  KF2.mvpMapPoints.assign(n2, nullptr);
+  for (int i = 0; i < n1; ++i)
+    if (mp1_valid[i]) {
+      p1[i] = make_point(mp1_xyz + 3 * i, nullptr, mp1_max_dist[i], mp1_min_dist[i], mp1_max_d[i], mp1_desc + (size_t)i * 32, 1, false);
+      KF1.mvpMapPoints[i] = &p1[i];
+    }
+  for (int i = 0; i < n2; ++i)
+    if (mp2_valid[i]) {
+      p2[i] = make_point(mp2_xyz + 3 * i, nullptr, mp2_max_dist[i], mp2_min_dist[i], mp2_max_d[i], mp2_desc + (size_t)i * 32, 1, false);
+      KF2.mvpMapPoints[i] = &p2[i];
+    }
+  std::vector<MapPoint*> vpMatches12(n1, nullptr);
+  ORBmatcher matcher(0.75f, true);
+  const int nf = matcher.SearchBySim3(&KF1, &KF2, vpMatches12, s12, fmat(R12, 3, 3), fmat(t12, 3, 1), th, fmat(calib, 4, 3));
+  for (int i = 0; i < n1; ++i) match12[i] = index_in(p2, vpMatches12[i]);
+  return nf;
 }
 
 }  // extern "C"

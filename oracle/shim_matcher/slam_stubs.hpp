@@ -21,6 +21,19 @@
 
 using namespace std;  // the reference's headers do (include/Frame.h, include/KeyFrame.h)
 
+// The reference's progress prints (`cout << ... << nFound << endl`) are swallowed: the toolchain here links
+// libstdc++ statically into the .so, whose iostream number formatting crashes when the process also holds the
+// shared libstdc++ (GNU-unique locale ids), and the prints are noise in a test log anyway.  A macro, so that the
+// reference source itself stays untouched.
+namespace orb_shim {
+struct NullStream {
+  template <class T> NullStream& operator<<(const T&) { return *this; }
+  NullStream& operator<<(std::ostream& (*)(std::ostream&)) { return *this; }
+};
+inline NullStream& null_stream() { static NullStream s; return s; }
+}  // namespace orb_shim
+#define cout orb_shim::null_stream()
+
 namespace ORB_SLAM2 {
 #define FRAME_GRID_ROWS 48
 #define FRAME_GRID_COLS 64
@@ -116,7 +129,7 @@ class MapPoint {
   MapPoint* replaced = nullptr;
   bool isBad() { return bad; }
   cv::Mat GetDescriptor() { return descriptor.clone(); }
-  cv::Mat GetWorldPos() { return worldPos.clone(); }
+  cv::Mat GetWorldPos() { trace().push_back(Trace{0, this, -1}); return worldPos.clone(); }
   cv::Mat GetNormal() { return normal.clone(); }
   int Observations() { return nObs; }
   float GetMinDistanceInvariance() { return minInvariance; }
@@ -124,16 +137,17 @@ class MapPoint {
   bool IsInKeyFrame(KeyFrame* pKF) { return observations.count(pKF) != 0; }
   int GetIndexInKeyFrame(KeyFrame* pKF) { return observations.count(pKF) ? (int)observations[pKF] : -1; }
   int GetIndexInKeyFrame_cam1(KeyFrame* pKF) { return GetIndexInKeyFrame(pKF); }
-  void AddObservation(KeyFrame* pKF, size_t idx) {
-    if (observations.count(pKF)) return;
-    observations[pKF] = idx;
-    nObs++;
-  }
-  void Replace(MapPoint* pMP) { replaced = pMP; bad = true; }
+  // Fuse's effects on the map are not applied (AddObservation / Replace do nothing); instead a trace records which
+  // candidate is being processed (GetWorldPos opens every candidate's iteration, :2015 / :2247) and which key-frame
+  // features it asks for (GetMapPoint, :2164 / :2425), so a test can read back the fused (point, feature) pairs
+  struct Trace { int kind; const void* p; long idx; };  // kind 0: candidate p; kind 1: feature idx
+  static std::vector<Trace>& trace() { static std::vector<Trace> t; return t; }
+  void AddObservation(KeyFrame*, size_t) {}
+  void Replace(MapPoint*) {}
   int PredictScale(const float& currentDist, KeyFrame* pKF);  // src/MapPoint.cc:584-600
   int PredictScale(const float& currentDist, Frame* pF) {     // src/MapPoint.cc:602-617
     const float ratio = mfMaxDistance / currentDist;
-    int nScale = ceil(log(ratio) / pF->mfLogScaleFactor);
+    int nScale = ceil(std::log(ratio) / pF->mfLogScaleFactor);
     if (nScale < 0) nScale = 0;
     else if (nScale >= pF->mnScaleLevels) nScale = pF->mnScaleLevels - 1;
     return nScale;
@@ -168,7 +182,7 @@ class KeyFrame {
   bool IsInImage(const float& x, const float& y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }
   vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
   vector<MapPoint*> GetMapPointMatches_cam1() { return vector<MapPoint*>(mvpMapPoints.begin(), mvpMapPoints.begin() + N); }
-  MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+  MapPoint* GetMapPoint(const size_t& idx) { MapPoint::trace().push_back(MapPoint::Trace{1, nullptr, (long)idx}); return mvpMapPoints[idx]; }
   std::set<MapPoint*> GetMapPoints() {
     std::set<MapPoint*> s;
     for (MapPoint* p : mvpMapPoints)
@@ -187,7 +201,7 @@ class KeyFrame {
 
 inline int MapPoint::PredictScale(const float& currentDist, KeyFrame* pKF) {
   const float ratio = mfMaxDistance / currentDist;
-  int nScale = ceil(log(ratio) / pKF->mfLogScaleFactor);
+  int nScale = ceil(std::log(ratio) / pKF->mfLogScaleFactor);
   if (nScale < 0) nScale = 0;
   else if (nScale >= pKF->mnScaleLevels) nScale = pKF->mnScaleLevels - 1;
   return nScale;

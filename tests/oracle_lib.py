@@ -207,7 +207,7 @@ def search_by_projection_points(k, d, u_right, bounds, scale_factors, mp, mp_des
     k = np.ascontiguousarray(k, dtype=KP_DTYPE)
     d = np.ascontiguousarray(d, dtype=np.uint8)
     n = len(k)
-    u_right = np.ascontiguousarray(u_right, dtype=np.float32)
+    u_right = None if u_right is None else np.ascontiguousarray(u_right, dtype=np.float32)  # NULL = monocular frame
     sf = np.ascontiguousarray(scale_factors, dtype=np.float32)
     mp = np.ascontiguousarray(mp, dtype=MP_DTYPE)
     mp_desc = np.ascontiguousarray(mp_desc, dtype=np.uint8)
@@ -218,8 +218,8 @@ def search_by_projection_points(k, d, u_right, bounds, scale_factors, mp, mp_des
     f.restype = C.c_int
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, Bounds, C.c_void_p, C.c_int, C.c_void_p,
                   C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
-    nm = f(k.ctypes.data, d.ctypes.data, u_right.ctypes.data, n, Bounds(*bounds), sf.ctypes.data, len(sf),
-           mp.ctypes.data, mp_desc.ctypes.data, mp_obs.ctypes.data, len(mp), th, nnratio, fmp.ctypes.data,
+    nm = f(k.ctypes.data, d.ctypes.data, None if u_right is None else u_right.ctypes.data, n, Bounds(*bounds), sf.ctypes.data,
+           len(sf), mp.ctypes.data, mp_desc.ctypes.data, mp_obs.ctypes.data, len(mp), th, nnratio, fmp.ctypes.data,
            fobs.ctypes.data)
     return nm, fmp
 
@@ -328,8 +328,8 @@ def fuse_sim3(kf_k, kf_desc, kf_cam, bounds, sf, log_sf, cam, Scw, calib, mp_val
     return n, best
 
 
-def search_by_sim3(k1, d1, cam1, T1w, k2, d2, cam2, T2w, bounds, sf, log_sf, cam, s12, R12, t12, calib, mp1, mp2, th):
-    lib = load("port")
+def search_by_sim3(k1, d1, cam1, T1w, k2, d2, cam2, T2w, bounds, sf, log_sf, cam, s12, R12, t12, calib, mp1, mp2, th, impl="port"):
+    lib = load("port" if impl == "port" else "mref")
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
     i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
     k1, k2 = np.ascontiguousarray(k1, dtype=KP_DTYPE), np.ascontiguousarray(k2, dtype=KP_DTYPE)
@@ -341,7 +341,7 @@ def search_by_sim3(k1, d1, cam1, T1w, k2, d2, cam2, T2w, bounds, sf, log_sf, cam
         P += [i32(mp["valid"]), f32(mp["xyz"]), f32(mp["max_dist"]), f32(mp["min_dist"]), f32(mp["max_d"]),
               np.ascontiguousarray(mp["desc"], dtype=np.uint8)]
     m12 = np.empty(len(k1), dtype=np.int32)
-    f = lib.om_search_by_sim3
+    f = getattr(lib, ("om_" if impl == "port" else "omr_") + "search_by_sim3")
     f.restype = C.c_int
     side = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     f.argtypes = side + side + [Bounds, C.c_void_p, C.c_int, C.c_float, Camera, C.c_float] + [C.c_void_p] * 3 + [C.c_void_p] * 12 + \
@@ -502,6 +502,49 @@ def search_by_bow_ref(variant, d1, angle1, valid1, fv1, d2, angle2, valid2, fv2,
     n = f(variant, p(d1), p(a1), p(v1), len(d1), p(f1[0]), p(f1[1]), p(f1[2]), len(f1[0]),
           p(d2), p(a2), p(v2), len(d2), p(f2[0]), p(f2[1]), p(f2[2]), len(f2[0]), nnratio, int(check_ori), p(m12), p(m21))
     return n, m12, m21
+
+
+def search_for_triangulation_ref(sc, fv1, fv2, T1w, T2w, Cw1, cam, only_stereo=False, cam_enabled=(1, 1), check_ori=True):
+    """The reference's SearchForTriangulation on poses.  Returns (nmatches, matches12, F12s [2,3,3], epipoles [4])."""
+    lib = load("mref")
+    c = lambda a, t: np.ascontiguousarray(a, dtype=t)
+    k1, k2 = c(sc["k1"], KP_DTYPE), c(sc["k2"], KP_DTYPE)
+    a1 = [k1, c(sc["d1"], np.uint8), c(sc["has_mp1"], np.int32), c(sc["cam1"], np.int32), c(sc["uright1"], np.float32)]
+    a2 = [k2, c(sc["d2"], np.uint8), c(sc["has_mp2"], np.int32), c(sc["cam2"], np.int32), c(sc["uright2"], np.float32)]
+    f1, f2 = [c(a, np.int32) for a in fv1], [c(a, np.int32) for a in fv2]
+    T1, T2, Cw = c(T1w, np.float32), c(T2w, np.float32), c(Cw1, np.float32)
+    sf, ls, en = c(sc["scale_factors"], np.float32), c(sc["level_sigma2"], np.float32), c(cam_enabled, np.int32)
+    m12, F, epi = np.zeros(len(k1), np.int32), np.zeros((2, 3, 3), np.float32), np.zeros(4, np.float32)
+    f = lib.omr_search_for_triangulation
+    f.restype = C.c_int
+    side = [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int]
+    f.argtypes = side + side + [C.c_void_p] * 3 + [Camera, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 3
+    p = lambda a: a.ctypes.data
+    n = f(*[p(a) for a in a1], len(k1), p(f1[0]), p(f1[1]), p(f1[2]), len(f1[0]), *[p(a) for a in a2], len(k2), p(f2[0]), p(f2[1]),
+          p(f2[2]), len(f2[0]), p(T1), p(T2), p(Cw), Camera(*cam), p(sf), p(ls), len(sf), int(only_stereo), p(en), int(check_ori),
+          p(m12), p(F), p(epi))
+    return n, m12, F, epi
+
+
+def fuse_ref(sim3, kf_k, kf_desc, kf_uright, kf_cam, kf_held, bounds, sf, inv_sigma2, log_sf, cam, pose, Ow, calib, mp_valid, mp_xyz,
+             mp_normal, mp_max_dist, mp_min_dist, mp_max_d, mp_desc, th):
+    lib = load("mref")
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+    i32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+    kf_k = np.ascontiguousarray(kf_k, dtype=KP_DTYPE)
+    kf_desc, mp_desc = np.ascontiguousarray(kf_desc, dtype=np.uint8), np.ascontiguousarray(mp_desc, dtype=np.uint8)
+    A = [f32(kf_uright), i32(kf_cam), i32(kf_held)]
+    B = [f32(sf), f32(inv_sigma2)]
+    Cc = [f32(pose), f32(Ow), f32(calib), i32(mp_valid), f32(mp_xyz), f32(mp_normal), f32(mp_max_dist), f32(mp_min_dist), f32(mp_max_d)]
+    best = np.empty((len(Cc[3]), 2), dtype=np.int32)
+    f = lib.omr_fuse
+    f.restype = C.c_int
+    f.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_int, Bounds, C.c_void_p, C.c_void_p, C.c_int, C.c_float, Camera] + \
+        [C.c_void_p] * 10 + [C.c_int, C.c_float, C.c_void_p]
+    p = lambda a: None if a is None else a.ctypes.data
+    n = f(int(sim3), p(kf_k), p(kf_desc), p(A[0]), p(A[1]), p(A[2]), len(kf_k), Bounds(*bounds), p(B[0]), p(B[1]), len(B[0]), log_sf,
+          Camera(*cam), *[p(a) for a in Cc], p(mp_desc), len(Cc[3]), float(th), p(best))
+    return n, best
 
 
 def distance_ref(a, b):

@@ -561,11 +561,9 @@ def test_fuse_sim3_vs_oracle(O, th, scale):
 
 
 # ---- SearchBySim3 (src/ORBmatcher.cc:2814-3136) -------------------------------------------------
-@pytest.mark.parametrize("s12,th", [(1.0, 7.5), (1.3, 7.5), (0.8, 3.0)])
-def test_search_by_sim3_vs_oracle(O, s12, th):
+def _sim3_scene(O, s12, th):
     """Two two-camera key frames observing the same points; key frame 2 = key frame 1 moved by a Sim3."""
-    from multi_orb_slam_b200._lib import Camera, KP_DTYPE
-    from multi_orb_slam_b200.matcher import Frame, ORBmatcher
+    from multi_orb_slam_b200.synth import KP_DTYPE
     rng = np.random.default_rng(int(s12 * 10 + th))
     fx, fy, cx, cy, mb, mbf = CAM
     port0, port1 = O.extractor("port", nfeatures=1000), O.extractor("port", nfeatures=500)
@@ -620,7 +618,17 @@ def test_search_by_sim3_vs_oracle(O, s12, th):
                     desc=desc)
 
     mp1, mp2 = points(Xw, T1w, n1, d1, k1["octave"]), points(Xw2, T2w, n2, d2, k2["octave"])
-    log_sf = float(np.log(np.float32(1.2)))
+    return dict(k1=k1, d1=d1, cam1=cam1, T1w=T1w, k2=k2, d2=d2, cam2=cam2, T2w=T2w, sf=sf, R12=R12, t12=t12, mp1=mp1, mp2=mp2,
+                log_sf=float(np.log(np.float32(1.2))))
+
+
+@pytest.mark.parametrize("s12,th", [(1.0, 7.5), (1.3, 7.5), (0.8, 3.0)])
+def test_search_by_sim3_vs_oracle(O, s12, th):
+    from multi_orb_slam_b200._lib import Camera
+    from multi_orb_slam_b200.matcher import Frame, ORBmatcher
+    c = _sim3_scene(O, s12, th)
+    k1, d1, cam1, T1w, k2, d2, cam2, T2w, sf, R12, t12, mp1, mp2, log_sf = (c[k] for k in (
+        "k1", "d1", "cam1", "T1w", "k2", "d2", "cam2", "T2w", "sf", "R12", "t12", "mp1", "mp2", "log_sf"))
     rn, rm12 = O.search_by_sim3(k1, d1, cam1, T1w, k2, d2, cam2, T2w, (0, 640, 0, 480), sf, log_sf, CAM, s12, R12, t12, CALIB,
                                 mp1, mp2, th)
     F1 = Frame(k1, d1, 640, 480, mvScaleFactors=sf)

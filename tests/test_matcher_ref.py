@@ -142,3 +142,101 @@ def test_search_by_bow(seed, n_nodes, check_ori, variant):
     b = O.search_by_bow_ref(variant, sc["d1"], sc["a1"], v1, fv1, sc["d2"], sc["a2"], v2, fv2, 0.7, check_ori)
     assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert a[0] > 20
+
+
+@pytest.mark.parametrize("seed,n_nodes,only_stereo,cam_enabled,check_ori", [(0, 30, False, (1, 1), True), (1, 8, False, (1, 0), True),
+                                                                          (2, 15, True, (1, 1), False)])
+def test_search_for_triangulation(seed, n_nodes, only_stereo, cam_enabled, check_ori):
+    """The reference recomputes F12 and the epipoles from the poses (:1376-1449); the flat implementations take them as
+    inputs, so the verbatim run also returns them (same expressions, same shim) for the restatement to consume."""
+    from multi_orb_slam_b200.synth import feature_vector, triangulation_scene
+    sc = triangulation_scene(900, 1000, n_nodes, seed)
+    fv1, fv2 = feature_vector(sc["node1"]), feature_vector(np.where(sc["node2"] % 5 == 2, -1, sc["node2"]))
+    # poses with key frame 2 at the origin: R12 = R1w, t12 = t1w per camera (X1 = R12 X2 + t12)
+    fx, fy, cx, cy = 520.0, 520.0, 320.0, 240.0
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    T1w, Cw1 = np.zeros((2, 4, 4)), np.zeros((2, 3))
+    for c in range(2):
+        E = np.linalg.inv(K.T) @ np.zeros((3, 3))  # placeholder to keep K in scope
+        F = sc["F12s"][c].astype(np.float64)
+        # recover [t12]x R12 = K^T F K and split it with the generator's known rotation convention
+        M = K.T @ F @ K
+        U, S, Vt = np.linalg.svd(M)
+        W = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1.0]])
+        cands = [(U @ W @ Vt, U[:, 2]), (U @ W.T @ Vt, U[:, 2])]
+        R = min((r * np.sign(np.linalg.det(r)) for r, _ in cands), key=lambda r: np.linalg.norm(r - np.eye(3)))
+        tx = M @ R.T
+        t = np.array([tx[2, 1], tx[0, 2], tx[1, 0]])
+        T1w[c, :3, :3], T1w[c, :3, 3], T1w[c, 3, 3] = R, t, 1
+        Cw1[c] = -R.T @ t
+    T2w = np.stack([np.eye(4), np.eye(4)])
+    cam = (fx, fy, cx, cy, 0.08, 40.0)
+    rn, rm12, F12s, epi = O.search_for_triangulation_ref(sc, fv1, fv2, T1w, T2w, Cw1, cam, only_stereo, cam_enabled, check_ori)
+    sc2 = dict(sc, F12s=F12s, epipoles=epi)
+    pn, pm12 = O.search_for_triangulation(sc2, fv1, fv2, only_stereo, cam_enabled, check_ori)
+    assert pn == rn and np.array_equal(pm12, rm12)
+    if not only_stereo:
+        assert rn > 20
+    # the recomputed fundamental matrices are the generator's up to scale
+    for c in range(2):
+        a, b = F12s[c].astype(np.float64).ravel(), sc["F12s"][c].astype(np.float64).ravel()
+        assert abs(abs(a @ b) / (np.linalg.norm(a) * np.linalg.norm(b)) - 1) < 1e-3
+
+
+def _fuse_scene(seed):
+    s = _rig_scene(O, seed, 2500, (0, 0, 0))
+    rng = s["rng"]
+    nmp = len(s["last_xyz"])
+    Tcw = s["Tcw"]
+    xyz = s["last_xyz"].astype(np.float64)
+    R, t = Tcw[:3, :3].astype(np.float64), Tcw[:3, 3].astype(np.float64)
+    Ow0 = -R.T @ t
+    Ow = np.stack([Ow0, Ow0 + R.T @ CALIB[3].astype(np.float64)])
+    dist = np.linalg.norm(xyz - Ow0, axis=1)
+    normal = (xyz - Ow0) / dist[:, None] + rng.normal(0, 0.3, (nmp, 3))
+    normal /= np.linalg.norm(normal, axis=1)[:, None]
+    max_d = (dist * rng.uniform(0.8, 4.0, nmp)).astype(np.float32)
+    return dict(s=s, xyz=xyz, Ow=Ow, normal=normal, max_d=max_d, kf_max=(1.2 * max_d).astype(np.float32),
+                kf_min=(0.8 * max_d / 1.2 ** 7).astype(np.float32), valid=(rng.random(nmp) < 0.9).astype(np.int32),
+                held=rng.integers(0, 3, s["n"]).astype(np.int32) * (rng.random(s["n"]) < 0.4), log_sf=float(np.log(np.float32(1.2))))
+
+
+@pytest.mark.parametrize("th,seed", [(3.0, 21), (6.0, 22)])
+def test_fuse(th, seed):
+    f = _fuse_scene(seed)
+    s = f["s"]
+    sf, _, _, inv_sigma2 = O.extractor("port").scale_tables()
+    a = O.fuse(s["cur_k"], s["cur_d"], s["ur"], s["cur_cam"], (0, 640, 0, 480), sf, inv_sigma2, f["log_sf"], CAM, s["Tcw"], f["Ow"],
+               CALIB, f["valid"], f["xyz"], f["normal"], f["kf_max"], f["kf_min"], f["max_d"], s["last_desc"], th)
+    b = O.fuse_ref(0, s["cur_k"], s["cur_d"], s["ur"], s["cur_cam"], f["held"], (0, 640, 0, 480), sf, inv_sigma2, f["log_sf"], CAM,
+                   s["Tcw"], f["Ow"], CALIB, f["valid"], f["xyz"], f["normal"], f["kf_max"], f["kf_min"], f["max_d"], s["last_desc"], th)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    assert a[0] > 100
+
+
+@pytest.mark.parametrize("th,scale", [(4.0, 1.0), (4.0, 1.6)])
+def test_fuse_sim3(th, scale):
+    f = _fuse_scene(31)
+    s = f["s"]
+    sf = O.extractor("port").scale_tables()[0]
+    Scw = s["Tcw"].astype(np.float64).copy()
+    Scw[:3, :] *= scale
+    a = O.fuse_sim3(s["cur_k"], s["cur_d"], s["cur_cam"], (0, 640, 0, 480), sf, f["log_sf"], CAM, Scw, CALIB, f["valid"], f["xyz"],
+                    f["normal"], f["kf_max"], f["kf_min"], f["max_d"], s["last_desc"], th)
+    b = O.fuse_ref(1, s["cur_k"], s["cur_d"], None, s["cur_cam"], f["held"], (0, 640, 0, 480), sf, None, f["log_sf"], CAM, Scw,
+                   np.zeros(6), CALIB, f["valid"], f["xyz"], f["normal"], f["kf_max"], f["kf_min"], f["max_d"], s["last_desc"], th)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    assert a[0] > 100
+
+
+@pytest.mark.parametrize("s12,th", [(1.0, 7.5), (1.3, 7.5), (0.8, 3.0)])
+def test_search_by_sim3(s12, th):
+    from test_gpu_matcher import _sim3_scene
+    c = _sim3_scene(O, s12, th)
+    args = (c["k1"], c["d1"], c["cam1"], c["T1w"], c["k2"], c["d2"], c["cam2"], c["T2w"], (0, 640, 0, 480), c["sf"], c["log_sf"], CAM,
+            s12, c["R12"], c["t12"], CALIB, c["mp1"], c["mp2"], th)
+    a = O.search_by_sim3(*args)
+    b = O.search_by_sim3(*args, impl="ref")
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    if s12 == 1.0:
+        assert a[0] > 30
