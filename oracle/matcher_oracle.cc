@@ -1,11 +1,13 @@
 // TEST INFRASTRUCTURE — CPU oracle, not product code.
 //
-// Flat-array restatement of the reference's matcher hot path.  The reference's
-// src/ORBmatcher.cc cannot be compiled standalone (it drags in Frame/KeyFrame/MapPoint/DBoW2),
-// so this file follows it line by line over plain arrays; each function cites its source.
-// "Parity unpinned" by the reference itself: it ships no tests or golden vectors for these
-// functions.  Pins we add: hand-checkable known-answer tests in
-// tests/test_matcher_oracle.py.
+// Flat-array restatement of the reference's matcher hot path (src/ORBmatcher.cc, src/Frame.cc grid functions,
+// src/MapPoint.cc, DBoW2 transform); each function cites its source lines.
+// The reference ships no tests or golden vectors for these functions.  Pins: the reference's
+// own src/ORBmatcher.cc compiled VERBATIM (oracle/_ref/libmatcher_ref.so, oracle/matcher_ref_capi.cc) returns the
+// same results as this restatement on the seeded scenes of tests/test_matcher_ref.py (DescriptorDistance,
+// SearchForInitialization, the four SearchByProjection overloads, SearchByBoW x2, SearchForTriangulation,
+// Fuse x2, SearchBySim3); plus hand-checkable known answers and an independent pure-Python transliteration on
+// small cases (tests/test_matcher_oracle.py); cv2 for the OpenCV primitives.
 #include "orb_oracle.h"
 #include "cvprim.h"
 

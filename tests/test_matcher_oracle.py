@@ -1,5 +1,6 @@
 """Known-answer tests for the matcher restatement (oracle/matcher_oracle.cc).  The reference ships
-no tests or vectors for these functions ("parity unpinned"), so the pins are
+no tests or vectors for these functions; the primary pin is the verbatim build of the
+reference's ORBmatcher.cc (tests/test_matcher_ref.py).  Here:
 (1) hand-checkable cases and (2) an independent pure-Python transliteration of
 src/ORBmatcher.cc:868-983 / src/Frame.cc:510-566,632-642 written from the reference text, run on
 small random cases."""
