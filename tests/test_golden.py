@@ -109,3 +109,13 @@ def test_undistort_points_golden(oracle_port):
         u = g[f"und_{i}"][:4]
         want = (min(u[0, 0], u[2, 0]), max(u[1, 0], u[3, 0]), min(u[0, 1], u[1, 1]), max(u[2, 1], u[3, 1]))
         assert oracle_port.compute_image_bounds(int(w), int(h), c[0], c[1], c[2], c[3], c[4:9]) == tuple(float(v) for v in want)
+
+
+def test_matcher_restatement_equals_reference_golden(oracle_port):
+    """Outputs of the reference's own ORBmatcher.cc (verbatim build) recorded by tools/make_golden_matcher.py."""
+    from golden_matcher_cases import CASES
+    g = np.load(os.path.join(GOLD, "ref_matcher.npz"))
+    for name, run in CASES.items():
+        res = run(oracle_port, "port")
+        for j, a in enumerate(res):
+            assert np.array_equal(np.asarray(a), g[f"{name}_{j}"]), f"{name}[{j}]"
