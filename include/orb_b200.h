@@ -238,6 +238,10 @@ int orbm_search_by_projection_keyframe_host(orbm_matcher* m, const orbx_keypoint
                                             const float* kf_max_d, const float* kf_angle, const uint8_t* kf_desc, int n_kf,
                                             float th, int orb_dist, int check_ori, int32_t* cur_mp, int* nmatches);
 
+/* Note on bounds for the KeyFrame-side searches below (SearchByProjection with Scw, Fuse, SearchBySim3): the reference's
+ * KeyFrame stores mnMinX/mnMinY/mnMaxX/mnMaxY as ints (include/KeyFrame.h:234-237, truncated copies of the Frame's floats)
+ * while its grid cell sizes come from the Frame's float bounds.  These entry points take one orbm_bounds and are exact when
+ * the bounds are integral — undistorted or pre-rectified input, where ComputeImageBounds returns (0, cols, 0, rows). */
 /* ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, vpPoints, vLoopMPCams, vpMatched, th, CalibMatrix)
  * (src/ORBmatcher.cc:566-752) — loop-closing search (src/LoopClosing.cc:536): every map point is
  * projected through the Sim3 into BOTH cameras of the key frame, best candidate over cameras,
