@@ -100,7 +100,13 @@ int index_in(const std::vector<MapPoint>& pool, const MapPoint* p) {
 }
 }  // namespace
 
+int g_cam1 = 0;  // != 0: the wrappers call the reference's camera-1-only twins (_cam1) instead
+
 extern "C" {
+
+// Select the `_cam1` twins (SearchByProjection_cam1(KeyFrame*, Scw, ...) :753-867, SearchByBoW_cam1 :390-565 and
+// :1180-1363, Fuse_cam1 :2518-2813, SearchBySim3_cam1 :3137-3433) for the following omr_* calls.
+void omr_set_cam1(int on) { g_cam1 = on; }
 
 int omr_distance(const uint8_t* a, const uint8_t* b) { return ORBmatcher::DescriptorDistance(desc_rows(a, 1), desc_rows(b, 1)); }
 
@@ -255,7 +261,8 @@ int omr_search_by_projection_sim3(const oo_keypoint* kf_k, const uint8_t* kf_des
   }
   std::vector<int> cams(n_mp, 0);
   ORBmatcher matcher(0.75f, true);
-  const int nm = matcher.SearchByProjection(&KF, fmat(Scw, 4, 4), vpPoints, cams, vpMatched, th, fmat(calib, 4, 3));
+  const int nm = g_cam1 ? matcher.SearchByProjection_cam1(&KF, fmat(Scw, 4, 4), vpPoints, vpMatched, th)
+                        : matcher.SearchByProjection(&KF, fmat(Scw, 4, 4), vpPoints, cams, vpMatched, th, fmat(calib, 4, 3));
   for (int i = 0; i < n_kf; ++i) {
     const int j = index_in(pts, vpMatched[i]);
     if (j >= 0) matched[i] = j;
@@ -290,7 +297,7 @@ int omr_search_by_bow(int variant, const uint8_t* d1, const float* angle1, const
     fill_rig(F, k2.data(), d2, nullptr, nullptr, n2, b);
     F.mFeatVec = F.mFeatVec_cam1 = featvec(node2, start2, items2, nn2);
     std::vector<MapPoint*> out;
-    nm = matcher.SearchByBoW(&KF1, F, out);
+    nm = g_cam1 ? matcher.SearchByBoW_cam1(&KF1, F, out) : matcher.SearchByBoW(&KF1, F, out);
     for (int i2 = 0; i2 < n2; ++i2) {
       const int i1 = index_in(p1, out[i2]);
       if (i1 >= 0) { matches21[i2] = i1; matches12[i1] = i2; }
@@ -303,7 +310,7 @@ int omr_search_by_bow(int variant, const uint8_t* d1, const float* angle1, const
     for (int i = 0; i < n2; ++i)
       if (!valid2 || valid2[i]) KF2.mvpMapPoints[i] = &p2[i];
     std::vector<MapPoint*> out;
-    nm = matcher.SearchByBoW(&KF1, &KF2, out);
+    nm = g_cam1 ? matcher.SearchByBoW_cam1(&KF1, &KF2, out) : matcher.SearchByBoW(&KF1, &KF2, out);
     for (int i1 = 0; i1 < n1; ++i1) {
       const int i2 = index_in(p2, out[i1]);
       if (i2 >= 0) { matches12[i1] = i2; matches21[i2] = i1; }
@@ -404,7 +411,8 @@ int omr_fuse(int sim3, const oo_keypoint* kf_k, const uint8_t* kf_desc, const fl
     nf = matcher.Fuse(&KF, vp, fmat(calib, 4, 3), th);
   } else {
     std::vector<int> cams(n_mp, 0);
-    nf = matcher.Fuse(&KF, fmat(pose, 4, 4), vp, cams, th, vpReplace, fmat(calib, 4, 3));
+    nf = g_cam1 ? matcher.Fuse_cam1(&KF, fmat(pose, 4, 4), vp, th, vpReplace)
+                : matcher.Fuse(&KF, fmat(pose, 4, 4), vp, cams, th, vpReplace, fmat(calib, 4, 3));
   }
   // read the fused (map point, feature) pairs back from the trace
   int cur = -1;
@@ -446,7 +454,8 @@ int omr_search_by_sim3(const oo_keypoint* k1, const uint8_t* d1, const int32_t* 
     }
   std::vector<MapPoint*> vpMatches12(n1, nullptr);
   ORBmatcher matcher(0.75f, true);
-  const int nf = matcher.SearchBySim3(&KF1, &KF2, vpMatches12, s12, fmat(R12, 3, 3), fmat(t12, 3, 1), th, fmat(calib, 4, 3));
+  const int nf = g_cam1 ? matcher.SearchBySim3_cam1(&KF1, &KF2, vpMatches12, s12, fmat(R12, 3, 3), fmat(t12, 3, 1), th)
+                        : matcher.SearchBySim3(&KF1, &KF2, vpMatches12, s12, fmat(R12, 3, 3), fmat(t12, 3, 1), th, fmat(calib, 4, 3));
   for (int i = 0; i < n1; ++i) match12[i] = index_in(p2, vpMatches12[i]);
   return nf;
 }

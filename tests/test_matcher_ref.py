@@ -240,3 +240,89 @@ def test_search_by_sim3(s12, th):
     assert a[0] == b[0] and np.array_equal(a[1], b[1])
     if s12 == 1.0:
         assert a[0] > 30
+
+
+# ---- the camera-1-only twins: the two-camera restatements fed with camera-1 data only ----------
+@pytest.fixture
+def cam1_twins():
+    lib = O.load("mref")
+    lib.omr_set_cam1(1)
+    yield
+    lib.omr_set_cam1(0)
+
+
+def _cam0_only(s):
+    """Camera-1 subset of a _rig_scene (the reference numbers camera-1 features first)."""
+    sel = s["cur_cam"] == 0
+    return s["cur_k"][sel], s["cur_d"][sel], np.zeros(int(sel.sum()), np.int32)
+
+
+@pytest.mark.parametrize("th,scale", [(10, 1.0), (4, 1.7)])
+def test_search_by_projection_sim3_cam1(cam1_twins, th, scale):
+    s = _rig_scene(O, 13, 1800, (0, 0, 0))
+    k, d, cam = _cam0_only(s)
+    rng = s["rng"]
+    n, nmp = len(k), len(s["last_xyz"])
+    sf = O.extractor("port").scale_tables()[0]
+    Scw = s["Tcw"].astype(np.float64).copy()
+    Scw[:3, :] *= scale
+    xyz = s["last_xyz"].astype(np.float64)
+    Ow = -s["Tcw"][:3, :3].T.astype(np.float64) @ s["Tcw"][:3, 3].astype(np.float64)
+    PO = xyz - Ow
+    dist = np.linalg.norm(PO, axis=1)
+    normal = PO / dist[:, None] + rng.normal(0, 0.3, (nmp, 3))
+    normal /= np.linalg.norm(normal, axis=1)[:, None]
+    max_d = (dist * rng.uniform(0.8, 4.0, nmp)).astype(np.float32)
+    kf_max, kf_min = (1.2 * max_d).astype(np.float32), (0.8 * max_d / 1.2 ** 7).astype(np.float32)
+    valid = (rng.random(nmp) < 0.9).astype(np.int32)
+    matched0 = np.full(n, -1, np.int32)
+    matched0[rng.random(n) < 0.1] = 3
+    args = (k, d, cam, (0, 640, 0, 480), sf, float(np.log(np.float32(1.2))), CAM, Scw, CALIB, valid, xyz, normal, kf_max, kf_min, max_d,
+            s["last_desc"], th, matched0)
+    a = O.search_by_projection_sim3(*args)
+    b = O.search_by_projection_sim3(*args, impl="ref")
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and a[0] > 30
+
+
+@pytest.mark.parametrize("seed,n_nodes,variant", [(0, 12, 0), (1, 40, 1), (4, 100, 0)])
+def test_search_by_bow_cam1(cam1_twins, seed, n_nodes, variant):
+    from multi_orb_slam_b200.synth import bow_scene, feature_vector
+    n1, n2 = 900, 1000
+    sc = bow_scene(n1, n2, n_nodes, seed)
+    rng = np.random.default_rng(100 + seed)
+    fv1, fv2 = feature_vector(sc["node1"]), feature_vector(np.where(sc["node2"] % 7 == 3, -1, sc["node2"]))
+    v1 = (rng.random(n1) < 0.8).astype(np.int32)
+    v2 = (rng.random(n2) < 0.9).astype(np.int32) if variant == 1 else None
+    a = O.search_by_bow(sc["d1"], sc["a1"], v1, fv1, sc["d2"], sc["a2"], v2, fv2, 0.7, True, 50 if variant == 0 else 49)
+    b = O.search_by_bow_ref(variant, sc["d1"], sc["a1"], v1, fv1, sc["d2"], sc["a2"], v2, fv2, 0.7, True)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[0] > 20
+
+
+def test_fuse_cam1(cam1_twins):
+    f = _fuse_scene(31)
+    s = f["s"]
+    k, d, cam = _cam0_only(s)
+    sf = O.extractor("port").scale_tables()[0]
+    Scw = s["Tcw"].astype(np.float64).copy()
+    Scw[:3, :] *= 1.3
+    held = f["held"][s["cur_cam"] == 0]
+    a = O.fuse_sim3(k, d, cam, (0, 640, 0, 480), sf, f["log_sf"], CAM, Scw, CALIB, f["valid"], f["xyz"], f["normal"], f["kf_max"],
+                    f["kf_min"], f["max_d"], s["last_desc"], 4.0)
+    b = O.fuse_ref(1, k, d, None, cam, held, (0, 640, 0, 480), sf, None, f["log_sf"], CAM, Scw, np.zeros(6), CALIB, f["valid"], f["xyz"],
+                   f["normal"], f["kf_max"], f["kf_min"], f["max_d"], s["last_desc"], 4.0)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and a[0] > 50 and (a[1][:, 1] == -1).all()
+
+
+@pytest.mark.parametrize("s12,th", [(1.0, 7.5), (1.3, 7.5)])
+def test_search_by_sim3_cam1(cam1_twins, s12, th):
+    from test_gpu_matcher import _sim3_scene
+    c = _sim3_scene(O, s12, th)
+    s1, s2 = c["cam1"] == 0, c["cam2"] == 0
+    sub = lambda mp, m: {k: v[m] for k, v in mp.items()}
+    args = (c["k1"][s1], c["d1"][s1], np.zeros(int(s1.sum()), np.int32), c["T1w"], c["k2"][s2], c["d2"][s2], np.zeros(int(s2.sum()), np.int32),
+            c["T2w"], (0, 640, 0, 480), c["sf"], c["log_sf"], CAM, s12, c["R12"], c["t12"], CALIB, sub(c["mp1"], s1), sub(c["mp2"], s2), th)
+    a = O.search_by_sim3(*args)
+    b = O.search_by_sim3(*args, impl="ref")
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    if s12 == 1.0:
+        assert a[0] > 20
