@@ -10,6 +10,8 @@
 #include <memory>
 
 #include "ORBmatcher.h"
+#include "Thirdparty/DBoW2/DBoW2/FORB.h"
+#include "Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h"
 #include "orb_oracle.h"
 
 using namespace ORB_SLAM2;
@@ -458,6 +460,33 @@ int omr_search_by_sim3(const oo_keypoint* k1, const uint8_t* d1, const int32_t* 
                         : matcher.SearchBySim3(&KF1, &KF2, vpMatches12, s12, fmat(R12, 3, 3), fmat(t12, 3, 1), th, fmat(calib, 4, 3));
   for (int i = 0; i < n1; ++i) match12[i] = index_in(p2, vpMatches12[i]);
   return nf;
+}
+
+// DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>::transform(features, BowVector, FeatureVector, levelsup)
+// (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1195) as Frame::ComputeBoW calls it, on a vocabulary read with the
+// reference's own loadFromTextFile (:1339-1424, the ORBvoc.txt format).  Outputs as om_bow_transform's vectors.
+int omr_bow_transform(const char* voc_path, const uint8_t* desc, int n, int levelsup, int32_t* bow_word, double* bow_value,
+                      int32_t* n_bow, int32_t* fv_node, int32_t* fv_start, int32_t* fv_items, int32_t* n_fv) {
+  typedef DBoW2::TemplatedVocabulary<DBoW2::FORB::TDescriptor, DBoW2::FORB> ORBVocabulary;
+  ORBVocabulary voc;
+  if (!voc.loadFromTextFile(voc_path) || voc.empty()) return -1;
+  std::vector<cv::Mat> features(n);
+  for (int i = 0; i < n; ++i) features[i] = desc_rows(desc + (size_t)i * 32, 1);
+  DBoW2::BowVector bv;
+  DBoW2::FeatureVector fv;
+  voc.transform(features, bv, fv, levelsup);
+  int j = 0;
+  for (DBoW2::BowVector::const_iterator it = bv.begin(); it != bv.end(); ++it, ++j) { bow_word[j] = (int32_t)it->first; bow_value[j] = it->second; }
+  *n_bow = j;
+  int a = 0, run = 0;
+  for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it, ++a) {
+    fv_node[a] = (int32_t)it->first;
+    fv_start[a] = run;
+    for (size_t q = 0; q < it->second.size(); ++q) fv_items[run++] = (int32_t)it->second[q];
+  }
+  fv_start[a] = run;
+  *n_fv = a;
+  return (int)voc.size();
 }
 
 }  // extern "C"

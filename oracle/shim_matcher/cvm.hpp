@@ -16,7 +16,11 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <fstream>
+#include <iostream>
 #include <memory>
+#include <sstream>
+#include <string>
 #include <vector>
 
 #define CV_8U 0
@@ -98,6 +102,7 @@ class Mat {
     if (dst.rows != rows || dst.cols != cols || dst.type_ != type_) dst.create(rows, cols, type_);
     for (int i = 0; i < rows; ++i) std::memcpy(dst.data + (size_t)i * dst.step, data + (size_t)i * step, (size_t)cols * esz());
   }
+  void release() { rows = cols = 0; store.reset(); data = nullptr; }
   MatT t() const;
   Mat inv() const;  // 3x3 CV_32F: closed form in double
   double dot(const Mat& b) const {
@@ -200,6 +205,31 @@ inline Mat operator-(const Mat& c, const GemmT& g) { return gemm_t(GemmT{g.a, g.
 inline Mat operator-(const GemmT& g, const Mat& c) { return gemm_t(g, &c, -1.0); }
 
 inline double norm(const Mat& a) { return std::sqrt(a.dot(a)); }
+
+// cv::FileStorage / cv::FileNode: only so that DBoW2's YAML save/load members (virtual, hence instantiated with the
+// class) compile; they are never called (the vocabulary is read with loadFromTextFile).
+class FileNode {
+ public:
+  FileNode operator[](const std::string&) const { return FileNode(); }
+  FileNode operator[](const char*) const { return FileNode(); }
+  FileNode operator[](int) const { return FileNode(); }
+  size_t size() const { return 0; }
+  operator int() const { return 0; }
+  operator double() const { return 0; }
+  operator float() const { return 0; }
+  operator std::string() const { return std::string(); }
+};
+class FileStorage {
+ public:
+  enum { READ = 0, WRITE = 1 };
+  FileStorage() {}
+  FileStorage(const std::string&, int) {}
+  bool isOpened() const { return false; }
+  void release() {}
+  FileNode operator[](const std::string&) const { return FileNode(); }
+  FileNode operator[](const char*) const { return FileNode(); }
+};
+template <typename T> inline FileStorage& operator<<(FileStorage& fs, const T&) { return fs; }
 
 template <typename T> class Mat_ : public Mat {
  public:

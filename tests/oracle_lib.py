@@ -547,6 +547,43 @@ def fuse_ref(sim3, kf_k, kf_desc, kf_uright, kf_cam, kf_held, bounds, sf, inv_si
     return n, best
 
 
+def write_vocabulary_text(voc, path, k=None):
+    """The ORBvoc.txt format the reference's loadFromTextFile reads (TemplatedVocabulary.h:1339-1424): header
+    `k L scoring weighting` (L1_NORM = 0, TF_IDF = 0), then one line per node in id order:
+    `parent isLeaf d0 .. d31 weight`.  Weights with 17 significant digits so that they round-trip exactly."""
+    cs, ci = voc["child_start"], voc["child_ids"]
+    n = len(voc["node_desc"])
+    parent = np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        parent[ci[cs[i]:cs[i + 1]]] = i
+    kk = int(max(np.diff(cs).max(), 2)) if k is None else k
+    lines = [f"{kk} {voc['L']} 0 0"]
+    for i in range(1, n):
+        leaf = int(cs[i] == cs[i + 1])
+        lines.append(f"{parent[i]} {leaf} " + " ".join(str(int(b)) for b in voc["node_desc"][i]) + f" {voc['node_weight'][i]:.17g}")
+    with open(path, "w") as f:
+        f.write("\n".join(lines))  # no trailing newline: the loader's `while(!f.eof())` would read it as one more node
+
+
+def bow_transform_ref(voc_path, desc, levelsup=4):
+    """The reference's own DBoW2 transform (verbatim build).  Returns dict(bow=(words, values), featvec=(nodes, start, items))."""
+    lib = load("mref")
+    d = np.ascontiguousarray(desc, dtype=np.uint8).reshape(-1, 32)
+    n = len(d)
+    bw, bv = np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.float64)
+    fn, fs, fi = np.empty(max(n, 1), np.int32), np.empty(n + 1, np.int32), np.empty(max(n, 1), np.int32)
+    nb, nf = C.c_int(0), C.c_int(0)
+    f = lib.omr_bow_transform
+    f.restype = C.c_int
+    f.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.POINTER(C.c_int)]
+    rc = f(str(voc_path).encode(), d.ctypes.data, n, int(levelsup), bw.ctypes.data, bv.ctypes.data, C.byref(nb), fn.ctypes.data,
+           fs.ctypes.data, fi.ctypes.data, C.byref(nf))
+    assert rc > 0, "the reference could not load the vocabulary file"
+    return dict(n_words=rc, bow=(bw[: nb.value].copy(), bv[: nb.value].copy()),
+                featvec=(fn[: nf.value].copy(), fs[: nf.value + 1].copy(), fi[: fs[nf.value]].copy()))
+
+
 def distance_ref(a, b):
     lib = load("mref")
     a, b = np.ascontiguousarray(a, dtype=np.uint8), np.ascontiguousarray(b, dtype=np.uint8)

@@ -326,3 +326,24 @@ def test_search_by_sim3_cam1(cam1_twins, s12, th):
     assert a[0] == b[0] and np.array_equal(a[1], b[1])
     if s12 == 1.0:
         assert a[0] > 20
+
+
+@pytest.mark.parametrize("k,L,levelsup,n", [(10, 4, 2, 1500), (10, 3, 4, 400), (4, 6, 4, 1000), (10, 5, 4, 2000)])
+def test_dbow2_transform(tmp_path, k, L, levelsup, n):
+    """Frame::ComputeBoW: the reference's DBoW2 (TemplatedVocabulary.h, FORB.cpp, BowVector.cpp, FeatureVector.cpp compiled
+    verbatim) loads the synthetic vocabulary from an ORBvoc-format text file and transforms the same descriptors."""
+    from multi_orb_slam_b200.synth import random_vocabulary
+    voc = random_vocabulary(k, L, 10 * k + L)
+    rng = np.random.default_rng(n)
+    leaves = np.nonzero(voc["word_id"] >= 0)[0]
+    base = voc["node_desc"][rng.choice(leaves, n)]
+    desc = np.packbits(np.unpackbits(base, axis=1) ^ (rng.random((n, 256)) < 0.05).astype(np.uint8), axis=1)
+    path = tmp_path / "voc.txt"
+    O.write_vocabulary_text(voc, path, k)
+    b = O.bow_transform_ref(path, desc, levelsup)
+    a = O.bow_transform(voc, desc, levelsup)
+    assert b["n_words"] == int((voc["word_id"] >= 0).sum())
+    assert np.array_equal(a["bow"][0], b["bow"][0]) and np.array_equal(a["bow"][1], b["bow"][1])  # doubles, bit for bit
+    for x, y in zip(a["featvec"], b["featvec"]):
+        assert np.array_equal(x, y)
+    assert len(a["bow"][0]) > 50
