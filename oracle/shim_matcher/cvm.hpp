@@ -103,6 +103,7 @@ class Mat {
     for (int i = 0; i < rows; ++i) std::memcpy(dst.data + (size_t)i * dst.step, data + (size_t)i * step, (size_t)cols * esz());
   }
   void release() { rows = cols = 0; store.reset(); data = nullptr; }
+  Mat reshape(int) const { return *this; }  // N x 2 one-channel <-> N x 1 two-channel: same memory, channels are not modelled
   MatT t() const;
   Mat inv() const;  // 3x3 CV_32F: closed form in double
   double dot(const Mat& b) const {

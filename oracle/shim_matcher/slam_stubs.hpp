@@ -84,6 +84,7 @@ struct GridSet {  // mGrids[cam][ix][iy] = global feature indices in insertion o
   }
 };
 
+#ifndef ORB_REAL_FRAME  // the frame build uses the reference's own include/Frame.h
 class Frame {
  public:
   int N = 0, N_total = 0;
@@ -112,6 +113,10 @@ class Frame {
     return grids.query(mvKeysUn_total, cam, x, y, r, mnMinX, mnMinY, minLevel, maxLevel, true);
   }
 };
+
+#else
+class Frame;
+#endif
 
 class MapPoint {
  public:
@@ -145,13 +150,7 @@ class MapPoint {
   void AddObservation(KeyFrame*, size_t) {}
   void Replace(MapPoint*) {}
   int PredictScale(const float& currentDist, KeyFrame* pKF);  // src/MapPoint.cc:584-600
-  int PredictScale(const float& currentDist, Frame* pF) {     // src/MapPoint.cc:602-617
-    const float ratio = mfMaxDistance / currentDist;
-    int nScale = ceil(std::log(ratio) / pF->mfLogScaleFactor);
-    if (nScale < 0) nScale = 0;
-    else if (nScale >= pF->mnScaleLevels) nScale = pF->mnScaleLevels - 1;
-    return nScale;
-  }
+  int PredictScale(const float& currentDist, Frame* pF);     // src/MapPoint.cc:602-617 (defined once Frame is complete)
 };
 
 class KeyFrame {
@@ -206,4 +205,13 @@ inline int MapPoint::PredictScale(const float& currentDist, KeyFrame* pKF) {
   else if (nScale >= pKF->mnScaleLevels) nScale = pKF->mnScaleLevels - 1;
   return nScale;
 }
+#ifndef ORB_REAL_FRAME
+inline int MapPoint::PredictScale(const float& currentDist, Frame* pF) {
+  const float ratio = mfMaxDistance / currentDist;
+  int nScale = ceil(std::log(ratio) / pF->mfLogScaleFactor);
+  if (nScale < 0) nScale = 0;
+  else if (nScale >= pF->mnScaleLevels) nScale = pF->mnScaleLevels - 1;
+  return nScale;
+}
+#endif
 }  // namespace ORB_SLAM2

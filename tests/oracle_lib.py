@@ -130,7 +130,7 @@ def load(kind: str = "port"):
     if kind in _libs:
         return _libs[kind]
     path = os.path.join(ORACLE_DIR, {"port": "liborb_oracle.so", "ref": "_ref/liborb_ref.so",
-                                     "mref": "_ref/libmatcher_ref.so"}[kind])
+                                     "mref": "_ref/libmatcher_ref.so", "fref": "_ref/libframe_ref.so"}[kind])
     if kind == "port" and not os.path.exists(path):
         build_oracle()
     lib = C.CDLL(path) if os.path.exists(path) else None
@@ -582,6 +582,65 @@ def bow_transform_ref(voc_path, desc, levelsup=4):
     assert rc > 0, "the reference could not load the vocabulary file"
     return dict(n_words=rc, bow=(bw[: nb.value].copy(), bv[: nb.value].copy()),
                 featvec=(fn[: nf.value].copy(), fs[: nf.value + 1].copy(), fi[: fs[nf.value]].copy()))
+
+
+def frame_glue_ref(k0, d0, k1, d1, depth0, depth1, cols, rows, fx, fy, cx, cy, dist, bf, nlevels=8, scale_factor=1.2):
+    """The reference's two-camera RGB-D Frame constructor (verbatim Frame.cc) on flat inputs.  Returns a dict."""
+    lib = load("fref")
+    c = lambda a, t: np.ascontiguousarray(a, dtype=t)
+    k0, k1, d0, d1 = c(k0, KP_DTYPE), c(k1, KP_DTYPE), c(d0, np.uint8), c(d1, np.uint8)
+    z0, z1 = c(depth0, np.float32), c(depth1, np.float32)
+    dist = c(dist, np.float32)
+    n = len(k0) + len(k1)
+    k_un, ur, dz = np.empty(n, KP_DTYPE), np.empty(n, np.float32), np.empty(n, np.float32)
+    cam, loc = np.empty(n, np.int32), np.empty(n, np.int32)
+    b = Bounds()
+    gs, gi = np.zeros((2, 64 * 48 + 1), np.int32), np.zeros((2, max(n, 1)), np.int32)
+    f = lib.ofr_frame_glue
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                  C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p,
+                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Bounds), C.c_void_p, C.c_void_p]
+    p = lambda a: a.ctypes.data
+    rc = f(p(k0), p(d0), len(k0), p(k1), p(d1), len(k1), p(z0), p(z1), cols, rows, fx, fy, cx, cy, p(dist), len(dist), bf, nlevels,
+           scale_factor, p(k_un), p(ur), p(dz), p(cam), p(loc), C.byref(b), p(gs), p(gi))
+    assert rc == n, rc
+    return dict(k_un=k_un, uright=ur, depth=dz, cam=cam, local=loc, bounds=(b.min_x, b.max_x, b.min_y, b.max_y), grid_start=gs,
+                grid_items=gi)
+
+
+def features_in_area_ref(k0, k1, cols, rows, fx, fy, cx, cy, dist, cam, x, y, r, min_level, max_level):
+    lib = load("fref")
+    k0, k1 = np.ascontiguousarray(k0, dtype=KP_DTYPE), np.ascontiguousarray(k1, dtype=KP_DTYPE)
+    dist = np.ascontiguousarray(dist, dtype=np.float32)
+    out = np.empty(len(k0) + len(k1) + 1, np.int32)
+    f = lib.ofr_features_in_area
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                  C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    n = f(k0.ctypes.data, len(k0), k1.ctypes.data, len(k1), cols, rows, fx, fy, cx, cy, dist.ctypes.data, len(dist), cam, x, y, r,
+          min_level, max_level, out.ctypes.data, len(out))
+    assert n >= 0
+    return out[:n].copy()
+
+
+def search_for_initialization_frame_ref(k1, d1, k2, d2, cols, rows, fx, fy, cx, cy, dist, prev_xy, window=100, nnratio=0.9,
+                                        check_ori=True):
+    """SearchForInitialization of the verbatim ORBmatcher.cc over frames built by the verbatim Frame.cc (distorted camera)."""
+    lib = load("fref")
+    k1, k2 = np.ascontiguousarray(k1, dtype=KP_DTYPE), np.ascontiguousarray(k2, dtype=KP_DTYPE)
+    d1, d2 = np.ascontiguousarray(d1, dtype=np.uint8), np.ascontiguousarray(d2, dtype=np.uint8)
+    dist = np.ascontiguousarray(dist, dtype=np.float32)
+    prev = np.ascontiguousarray(prev_xy, dtype=np.float32).copy()
+    m12 = np.zeros(len(k1), dtype=np.int32)
+    f = lib.ofr_search_for_initialization
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                  C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    n = f(k1.ctypes.data, d1.ctypes.data, len(k1), k2.ctypes.data, d2.ctypes.data, len(k2), cols, rows, fx, fy, cx, cy,
+          dist.ctypes.data, len(dist), prev.ctypes.data, window, nnratio, int(check_ori), m12.ctypes.data)
+    assert n >= 0
+    return n, m12, prev
 
 
 def distance_ref(a, b):
