@@ -228,6 +228,35 @@ def widened_rows_leg(matcher, device, with_cpu):
     if with_cpu:
         row["cpu_ms"] = best_ms(lambda: oracle_lib.undistort_keypoints(k, glue.fx, glue.fy, glue.cx, glue.cy, glue.dist), 3)
     out["undistort_keypoints"] = row
+    # Frame::ComputeStereoMatches on KITTI-shaped rectified pairs, device-resident (extraction not included)
+    import torch
+    from multi_orb_slam_b200.extractor import ORBextractor
+    from multi_orb_slam_b200.synth import stereo_pair
+    n_pairs, W, H = 8, 1241, 376
+    pairs = [stereo_pair(W, H, 900 + i, disparities=(5, 12, 26, 44)) for i in range(n_pairs)]
+    exl, exr = (ORBextractor(2000, 1.2, 8, 20, 7, image_size=(W, H), max_batch=n_pairs, device=device) for _ in range(2))
+    dl_, dr_ = (torch.from_numpy(np.stack([p[i] for p in pairs])).to(f"cuda:{device}") for i in range(2))
+    kl, dl, nl = exl.extract_batch_device(dl_)
+    kr, dr, nr = exr.extract_batch_device(dr_)
+    sglue = FrameGlue(718.856, 718.856, 607.1928, 185.2157, (0, 0, 0, 0, 0), mbf=386.1448, device=device)
+
+    def stereo_gpu():
+        sglue.stereo_matches_batch_device(exl, exr, kl, dl, nl, kr, dr, nr)
+        torch.cuda.synchronize(device)
+
+    row = {"workload": f"ComputeStereoMatches, {n_pairs} rectified pairs 1241x376 x 2000 features, device-resident",
+           "gpu_ms": best_ms(stereo_gpu)}
+    if with_cpu:
+        h = [t.cpu().numpy() for t in (kl, dl, nl, kr, dr, nr)]
+        kp = lambda a, n: np.ascontiguousarray(a[:n]).view(KP_DTYPE).reshape(-1)
+        sf, isf = np.asarray(exl.GetScaleFactors(), np.float32), np.asarray(exl.GetInverseScaleFactors(), np.float32)
+        cpu_in = []
+        for f in range(n_pairs):
+            pyr = [[e.pyramid_level(l, f, with_border=True) for l in range(8)] for e in (exl, exr)]
+            cpu_in.append((kp(h[0][f], h[2][f]), h[1][f][:h[2][f]], kp(h[3][f], h[5][f]), h[4][f][:h[5][f]], pyr[0], pyr[1]))
+        mb = float(np.float32(386.1448) / np.float32(718.856))
+        row["cpu_ms"] = best_ms(lambda: [oracle_lib.compute_stereo_matches(*c, sf, isf, 386.1448, mb) for c in cpu_in], 2)
+    out["compute_stereo_matches"] = row
     for r in out.values():
         if "cpu_ms" in r:
             r["cpu_cores"] = 1

@@ -103,6 +103,20 @@ int orbx_set_stream(orbx_extractor* h, void* cuda_stream);
 int orbx_get_pyramid_level(orbx_extractor* h, int frame, int level, int with_border, uint8_t* dst,
                            size_t dst_stride, int* w, int* hgt);
 
+/* Device view of the pyramid the handle holds for its LAST batch: what a consumer of the public member
+ * mvImagePyramid (include/ORBextractor.h:92) reads, without leaving the GPU.  Levels are stored without the
+ * EDGE_THRESHOLD border (a reader reflects out-of-range coordinates as BORDER_REFLECT_101 does); level 0 is the
+ * caller's own frame buffer of that batch, which must still be alive.  Pixel (x, y) of level l of frame f is
+ * base[l][f * frame_stride[l] + y * pitch[l] + x]. */
+typedef struct orbx_pyramid_view {
+  int32_t nlevels, n_frames;
+  int32_t w[ORBX_MAX_LEVELS], h[ORBX_MAX_LEVELS], pitch[ORBX_MAX_LEVELS];
+  const uint8_t* base[ORBX_MAX_LEVELS];
+  size_t frame_stride[ORBX_MAX_LEVELS];
+  float scale[ORBX_MAX_LEVELS], inv_scale[ORBX_MAX_LEVELS]; /* mvScaleFactor / mvInvScaleFactor */
+} orbx_pyramid_view;
+int orbx_get_pyramid_view(orbx_extractor* h, orbx_pyramid_view* out);
+
 /* Stage taps for parity tests (frame of the last batch): FAST candidates fed to the octree in
  * vToDistributeKeys order ((x,y) relative to (16,16)); the blurred working image. */
 int orbx_debug_candidates(orbx_extractor* h, int frame, int level, int32_t* x, int32_t* y, int32_t* score,
@@ -282,6 +296,17 @@ int orbm_compute_stereo_from_rgbd_device(orbm_matcher* m, int n_frames, int cap,
 /* Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:348-395, 632-642): per frame a CSR grid over
  * cell = ix*48 + iy (d_cell_start: n_frames x (64*48 + 1) ints; d_items: n_frames x cap u16 keypoint indices,
  * insertion order inside a cell = mGrid[ix][iy]). */
+/* Frame::ComputeStereoMatches (src/Frame.cc:782-956 — upstream ORB-SLAM2's rectified-stereo association, kept
+ * commented in the fork) for n_frames stereo pairs at once, on the device: left / right are the pyramid views of the
+ * two extractors that produced the keypoints (mpORBextractorLeft / Right ->mvImagePyramid), d_kl/d_dl/d_nl and
+ * d_kr/d_dr/d_nr their batch outputs (strides cap_l, cap_r; cap_r <= 4096).  mbf = baseline * fx, mb = mbf / fx.
+ * Outputs d_uright / d_depth [n_frames][cap_l] = mvuRight / mvDepth (-1 where unmatched).  A pair with no accepted
+ * match skips the median cut (the reference would index an empty vector). */
+int orbm_compute_stereo_matches_device(orbm_matcher* m, const orbx_pyramid_view* left, const orbx_pyramid_view* right,
+                                       int n_frames, int cap_l, const orbx_keypoint* d_kl, const uint8_t* d_dl,
+                                       const int32_t* d_nl, int cap_r, const orbx_keypoint* d_kr, const uint8_t* d_dr,
+                                       const int32_t* d_nr, float mbf, float mb, float* d_uright, float* d_depth);
+
 int orbm_assign_features_to_grid_device(orbm_matcher* m, int n_frames, int cap, const orbx_keypoint* d_kps_un,
                                         const int32_t* d_counts, orbm_bounds bounds, int32_t* d_cell_start,
                                         uint16_t* d_items);

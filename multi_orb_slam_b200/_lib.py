@@ -61,6 +61,13 @@ class Bounds(C.Structure):
     _fields_ = [("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
 
 
+class PyramidView(C.Structure):
+    """orbx_pyramid_view (include/orb_b200.h): device view of an extractor's mvImagePyramid for its last batch."""
+    _fields_ = [("nlevels", C.c_int32), ("n_frames", C.c_int32), ("w", C.c_int32 * 16), ("h", C.c_int32 * 16),
+                ("pitch", C.c_int32 * 16), ("base", C.c_void_p * 16), ("frame_stride", C.c_size_t * 16),
+                ("scale", C.c_float * 16), ("inv_scale", C.c_float * 16)]
+
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} is missing: build it with `python -m multi_orb_slam_b200.build` "
@@ -124,6 +131,9 @@ _SIGS = {
     "orbm_undistort_keypoints_device": (_i, [_vp, _i, _i, _vp, _vp, _f, _f, _f, _f, _vp, _vp]),
     "orbm_undistort_keypoints_host": (_i, [_vp, _vp, _i, _f, _f, _f, _f, _vp, _vp]),
     "orbm_compute_image_bounds_host": (_i, [_vp, _i, _i, _f, _f, _f, _f, _vp, C.POINTER(Bounds)]),
+    "orbx_get_pyramid_view": (_i, [_vp, C.POINTER(PyramidView)]),
+    "orbm_compute_stereo_matches_device": (_i, [_vp, C.POINTER(PyramidView), C.POINTER(PyramidView), _i, _i, _vp, _vp, _vp, _i,
+                                                _vp, _vp, _vp, _f, _f, _vp, _vp]),
     "orbm_compute_stereo_from_rgbd_device": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _sz, _sz, _f, _vp, _vp]),
     "orbm_assign_features_to_grid_device": (_i, [_vp, _i, _i, _vp, _vp, Bounds, _vp, _vp]),
     "orbm_search_by_bow_batch_host": (_i, [_vp, _vp, _i, _f, _i, _i]),

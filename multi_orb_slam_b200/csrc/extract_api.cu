@@ -519,6 +519,31 @@ int orbx_set_stream(orbx_extractor* h, void* cuda_stream) {
   return ORBX_OK;
 }
 
+int orbx_get_pyramid_view(orbx_extractor* h, orbx_pyramid_view* out) {
+  if (!h || !out) return ORBX_E_INVALID;
+  if (!h->last_l0.base || h->last_batch < 1) { h->err = "no batch has been extracted yet"; return ORBX_E_STATE; }
+  std::memset(out, 0, sizeof(*out));
+  out->nlevels = h->cfg.nlevels;
+  out->n_frames = h->last_batch;
+  for (int l = 0; l < h->cfg.nlevels; ++l) {
+    const OrbLevelGeom& L = h->gh.g.lv[l];
+    out->w[l] = L.w;
+    out->h[l] = L.h;
+    out->scale[l] = h->scale[l];
+    out->inv_scale[l] = h->inv_scale[l];
+    if (l == 0) {
+      out->base[0] = h->last_l0.base;
+      out->pitch[0] = h->last_l0.pitch;
+      out->frame_stride[0] = h->last_l0.frame_stride;
+    } else {
+      out->base[l] = h->d_pyr + L.pyr_off;
+      out->pitch[l] = L.pitch;
+      out->frame_stride[l] = (size_t)h->gh.g.pyr_frame_bytes;
+    }
+  }
+  return ORBX_OK;
+}
+
 int orbx_get_pyramid_level(orbx_extractor* h, int frame, int level, int with_border, uint8_t* dst, size_t dst_stride,
                            int* w, int* hgt) {
   if (!h || level < 0 || level >= h->cfg.nlevels) return ORBX_E_INVALID;

@@ -732,6 +732,196 @@ __global__ void __launch_bounds__(256) k_stereo_rgbd(const orbx_keypoint* __rest
   depth_out[o] = dz;
 }
 
+// ---- Frame::ComputeStereoMatches (src/Frame.cc:782-956, commented upstream code of the fork) ----
+// k_stereo_match: one CTA = 64 left keypoints of one stereo pair.  The right keypoints' row bands
+// (:797-810: rows floor(y - 2s) .. ceil(y + 2s)), columns and octaves are staged in shared memory once; a
+// warp then takes one left keypoint at a time: lanes scan the right keypoints (band, octave +-1, disparity
+// range tests, then the Hamming distance), the first minimum in right-keypoint order wins (key = dist<<16 |
+// iR), and 22 lanes evaluate the eleven 11x11 SAD windows from a warp-private copy of the two patches.
+// k_stereo_median: one CTA per pair, exact radix select of the SAD median (the sums are < 2^16) and the
+// 1.5 * 1.4 * median cut (:942-955).
+#define STEREO_MAX_R 4096
+#define STEREO_LPB 64
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+  p = p < 0 ? -p : p;
+  return p >= n ? 2 * (n - 1) - p : p;
+}
+
+__global__ void __launch_bounds__(256) k_stereo_match(orbx_pyramid_view pl, orbx_pyramid_view pr, int cap_l,
+                                                      const orbx_keypoint* __restrict__ kl, const uint8_t* __restrict__ dl,
+                                                      const int32_t* __restrict__ nl, int cap_r,
+                                                      const orbx_keypoint* __restrict__ kr, const uint8_t* __restrict__ dr,
+                                                      const int32_t* __restrict__ nr, float mbf, float mb,
+                                                      float* __restrict__ uright, float* __restrict__ depth,
+                                                      int32_t* __restrict__ sad_out) {
+  __shared__ float s_x[STEREO_MAX_R];
+  __shared__ uint32_t s_rows[STEREO_MAX_R];  // minr | maxr << 16 (an empty band is 1 | 0 << 16)
+  __shared__ uint8_t s_oct[STEREO_MAX_R];
+  __shared__ int16_t s_l[8][11 * 11];
+  __shared__ uint8_t s_r[8][11 * 21 + 1];
+  __shared__ float s_d[8][12];
+  const int frame = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_r = min(nr[frame], cap_r), n_l = min(nl[frame], cap_l);
+  const int n_rows = pl.h[0];
+  const orbx_keypoint* fr = kr + (size_t)frame * cap_r;
+  for (int i = threadIdx.x; i < n_r; i += 256) {
+    const orbx_keypoint k = fr[i];
+    const float r = __fmul_rn(2.0f, pl.scale[k.octave]);  // the frame's mvScaleFactors (left extractor)
+    int maxr = (int)ceilf(__fadd_rn(k.y, r)), minr = (int)floorf(__fsub_rn(k.y, r));
+    minr = max(minr, 0);
+    maxr = min(maxr, n_rows - 1);
+    s_x[i] = k.x;
+    s_oct[i] = (uint8_t)k.octave;
+    s_rows[i] = minr <= maxr ? ((uint32_t)minr | ((uint32_t)maxr << 16)) : 1u;
+  }
+  __syncthreads();
+  const float max_d = __fdiv_rn(mbf, mb);  // :813-815
+  const int i_end = min(n_l, (blockIdx.x + 1) * STEREO_LPB);
+  for (int il = blockIdx.x * STEREO_LPB + warp; il < (blockIdx.x + 1) * STEREO_LPB && il < cap_l; il += 8) {
+    const size_t o = (size_t)frame * cap_l + il;
+    float out_u = -1.0f, out_z = -1.0f;
+    int out_sad = -1;
+    if (il < i_end) {
+      const orbx_keypoint k = kl[o];
+      const int level = k.octave, row = (int)k.y;
+      const float min_u = __fsub_rn(k.x, max_d), max_u = k.x;
+      uint32_t best = (uint32_t)TH_HIGH << 16;
+      if (row >= 0 && row < n_rows && !(max_u < 0.0f)) {
+        const uint4* pa = reinterpret_cast<const uint4*>(dl + 32 * o);
+        const uint4 a0 = pa[0], a1 = pa[1];
+        for (int ir = lane; ir < n_r; ir += 32) {
+          const uint32_t rows = s_rows[ir];
+          const int oc = s_oct[ir];
+          const float ur = s_x[ir];
+          if (row < (int)(rows & 0xffffu) || row > (int)(rows >> 16) || oc < level - 1 || oc > level + 1 ||
+              !(ur >= min_u && ur <= max_u))
+            continue;
+          const uint4* pb = reinterpret_cast<const uint4*>(dr + 32 * ((size_t)frame * cap_r + ir));
+          const uint32_t key = ((uint32_t)hamming256(a0, a1, pb[0], pb[1]) << 16) | (uint32_t)ir;
+          best = min(best, key);
+        }
+      }
+      best = __reduce_min_sync(0xffffffffu, best);
+      if ((int)(best >> 16) < (TH_HIGH + TH_LOW) / 2 && (best >> 16) < (uint32_t)TH_HIGH) {  // :869
+        const float ur0 = s_x[best & 0xffffu];
+        const float isf = pl.inv_scale[level];
+        const int xl = (int)roundf(__fmul_rn(k.x, isf)), yl = (int)roundf(__fmul_rn(k.y, isf));
+        const int xr = (int)roundf(__fmul_rn(ur0, isf));
+        const int wl = pl.w[level], hl = pl.h[level], wr = pr.w[level], hr = pr.h[level];
+        if (!(xr < 0 || xr + 11 >= wr)) {  // iniu < 0 || endu >= cols (:888-891)
+          const uint8_t* il0 = pl.base[level] + (size_t)frame * pl.frame_stride[level];
+          const uint8_t* ir0 = pr.base[level] + (size_t)frame * pr.frame_stride[level];
+          const int cl = il0[(size_t)reflect101(yl, hl) * pl.pitch[level] + reflect101(xl, wl)];
+          for (int t = lane; t < 121; t += 32) {
+            const int dy = t / 11, dx = t - dy * 11;
+            s_l[warp][t] = (int16_t)((int)il0[(size_t)reflect101(yl + dy - 5, hl) * pl.pitch[level] +
+                                              reflect101(xl + dx - 5, wl)] - cl);
+          }
+          for (int t = lane; t < 231; t += 32) {
+            const int dy = t / 21, dx = t - dy * 21;
+            s_r[warp][t] = ir0[(size_t)reflect101(yl + dy - 5, hr) * pr.pitch[level] + reflect101(xr + dx - 10, wr)];
+          }
+          __syncwarp();
+          // lanes 0..10 take rows 0..5 of window lane, lanes 11..21 rows 6..10 of window lane - 11
+          int sad = 0;
+          if (lane < 22) {
+            const int t = lane < 11 ? lane : lane - 11;
+            const int y0 = lane < 11 ? 0 : 6, y1 = lane < 11 ? 6 : 11;
+            const int cr = s_r[warp][5 * 21 + t + 5];
+            for (int dy = y0; dy < y1; ++dy)
+#pragma unroll
+              for (int dx = 0; dx < 11; ++dx) sad += abs((int)s_l[warp][dy * 11 + dx] - ((int)s_r[warp][dy * 21 + t + dx] - cr));
+          }
+          sad += __shfl_down_sync(0xffffffffu, sad, 11);
+          if (lane < 11) s_d[warp][lane] = (float)sad;
+          __syncwarp();
+          if (lane == 0) {
+            int best_inc = 0;
+            float best_sad = 2147483648.0f;
+            for (int t = 0; t < 11; ++t)
+              if (s_d[warp][t] < best_sad) { best_sad = s_d[warp][t]; best_inc = t - 5; }
+            if (best_inc != -5 && best_inc != 5) {  // :910
+              const float d1 = s_d[warp][5 + best_inc - 1], d2 = s_d[warp][5 + best_inc], d3 = s_d[warp][5 + best_inc + 1];
+              const float delta = __fdiv_rn(__fsub_rn(d1, d3),
+                                            __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));  // :918
+              if (!(delta < -1.0f || delta > 1.0f)) {
+                float best_ur = __fmul_rn(pl.scale[level], __fadd_rn(__fadd_rn((float)xr, (float)best_inc), delta));
+                float disparity = __fsub_rn(k.x, best_ur);
+                if (disparity >= 0.0f && disparity < max_d) {  // :928-938
+                  if (disparity <= 0.0f) {
+                    disparity = 0.01f;
+                    best_ur = (float)__dsub_rn((double)k.x, 0.01);
+                  }
+                  out_z = __fdiv_rn(mbf, disparity);
+                  out_u = best_ur;
+                  out_sad = (int)best_sad;
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (lane == 0) {
+      uright[o] = out_u;
+      depth[o] = out_z;
+      sad_out[o] = out_sad;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_stereo_median(int cap_l, const int32_t* __restrict__ nl,
+                                                       const int32_t* __restrict__ sad, float* __restrict__ uright,
+                                                       float* __restrict__ depth) {
+  __shared__ int hist[256];
+  __shared__ int s_sel[2];
+  const int frame = blockIdx.x, tid = threadIdx.x;
+  const int n_l = min(nl[frame], cap_l);
+  const int32_t* fs = sad + (size_t)frame * cap_l;
+  // vDistIdx[size / 2].first of the sorted list: the rank-(n/2) SAD, by two 8-bit radix passes
+  int prefix = 0, rank = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < n_l; i += 256) {
+      const int v = fs[i];
+      if (v < 0) continue;
+      if (pass == 0) atomicAdd(&hist[(v >> 8) & 255], 1);
+      else if ((v >> 8) == prefix) atomicAdd(&hist[v & 255], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (pass == 0) {
+        int n = 0;
+        for (int b = 0; b < 256; ++b) n += hist[b];
+        rank = n / 2;
+        s_sel[1] = n;
+      }
+      int acc = 0, b = 0;
+      for (; b < 255; ++b) {
+        if (acc + hist[b] > rank) break;
+        acc += hist[b];
+      }
+      s_sel[0] = b;
+      rank -= acc;
+    }
+    __syncthreads();
+    prefix = pass == 0 ? s_sel[0] : (prefix << 8) | s_sel[0];
+    __syncthreads();
+  }
+  if (s_sel[1] == 0) return;
+  const float th = __fmul_rn(1.5f * 1.4f, (float)prefix);
+  for (int i = tid; i < n_l; i += 256) {
+    const int v = fs[i];
+    if (v >= 0 && !((float)v < th)) {
+      uright[(size_t)frame * cap_l + i] = -1.0f;
+      depth[(size_t)frame * cap_l + i] = -1.0f;
+    }
+  }
+}
+
 // ---- SearchByBoW (:206-388, 390-565, 996-1163, 1180-1363) ------------------------------------
 // The host walks the two feature vectors (node ids are a few hundred ints) and emits one query
 // per valid side-1 feature of a common node: {idx1, first side-2 item, item count, row offset}.
@@ -2002,6 +2192,25 @@ int orbm_compute_stereo_from_rgbd_device(orbm_matcher* m, int n_frames, int cap,
                                                                           d_uright, d_depth_out);
   m->launches += 1;
   return m->check(cudaGetLastError(), "stereo-from-rgbd launch") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+int orbm_compute_stereo_matches_device(orbm_matcher* m, const orbx_pyramid_view* left, const orbx_pyramid_view* right,
+                                       int n_frames, int cap_l, const orbx_keypoint* d_kl, const uint8_t* d_dl,
+                                       const int32_t* d_nl, int cap_r, const orbx_keypoint* d_kr, const uint8_t* d_dr,
+                                       const int32_t* d_nr, float mbf, float mb, float* d_uright, float* d_depth) {
+  if (!m || !left || !right || n_frames < 0 || cap_l < 1 || cap_r < 1 || cap_r > STEREO_MAX_R || !d_kl || !d_dl || !d_nl ||
+      !d_kr || !d_dr || !d_nr || !d_uright || !d_depth || !(mb > 0.0f) || left->nlevels != right->nlevels ||
+      left->nlevels < 1 || n_frames > left->n_frames || n_frames > right->n_frames)
+    return ORBX_E_INVALID;
+  if (n_frames == 0) return ORBX_OK;
+  cudaSetDevice(m->device);
+  int32_t* sad = m->scratch<int32_t>(8, (size_t)n_frames * cap_l);
+  if (!sad) return ORBX_E_CUDA;
+  k_stereo_match<<<dim3((cap_l + STEREO_LPB - 1) / STEREO_LPB, n_frames), 256, 0, m->stream>>>(
+      *left, *right, cap_l, d_kl, d_dl, d_nl, cap_r, d_kr, d_dr, d_nr, mbf, mb, d_uright, d_depth, sad);
+  k_stereo_median<<<n_frames, 256, 0, m->stream>>>(cap_l, d_nl, sad, d_uright, d_depth);
+  m->launches += 2;
+  return m->check(cudaGetLastError(), "stereo-matches launch") ? ORBX_OK : ORBX_E_CUDA;
 }
 
 int orbm_assign_features_to_grid_device(orbm_matcher* m, int n_frames, int cap, const orbx_keypoint* d_kps_un,

@@ -108,6 +108,13 @@ class ORBextractor:
         check_x(self._h, lib.orbx_get_features_per_level(self._h, out.ctypes.data))
         return out
 
+    def pyramid_view(self):
+        """Device view (orbx_pyramid_view) of mvImagePyramid for the last batch; valid until the next extraction."""
+        from ._lib import PyramidView
+        v = PyramidView()
+        check_x(self._h, lib.orbx_get_pyramid_view(self._h, C.byref(v)))
+        return v
+
     def pyramid_level(self, level: int, frame: int = 0, with_border: bool = False) -> np.ndarray:
         """mvImagePyramid[level] of a frame of the last call (public member, ORBextractor.h:92)."""
         w, h = C.c_int(), C.c_int()

@@ -87,6 +87,24 @@ class FrameGlue:
             depth.shape[1], depth.stride(1), depth.stride(0), self.mbf, uright.data_ptr(), depth_out.data_ptr()))
         return uright, depth_out
 
+    # -- Frame::ComputeStereoMatches (rectified stereo; src/Frame.cc:782-956, commented upstream code) ---
+    def stereo_matches_batch_device(self, ex_left, ex_right, kps_l, desc_l, counts_l, kps_r, desc_r, counts_r, mb=None,
+                                    uright=None, depth_out=None):
+        """Left/right batch outputs of two ORBextractor handles (whose last batch they are) ->
+        (mvuRight, mvDepth) [F, cap_l] f32, all on the device.  mb = baseline in metres (default mbf / fx)."""
+        import torch
+        F, cap_l, cap_r = kps_l.shape[0], kps_l.shape[1], kps_r.shape[1]
+        if uright is None:
+            uright = torch.empty((F, cap_l), dtype=torch.float32, device=kps_l.device)
+        if depth_out is None:
+            depth_out = torch.empty((F, cap_l), dtype=torch.float32, device=kps_l.device)
+        vl, vr = ex_left.pyramid_view(), ex_right.pyramid_view()
+        check_m(self._h, lib.orbm_compute_stereo_matches_device(
+            self._h, C.byref(vl), C.byref(vr), F, cap_l, kps_l.data_ptr(), desc_l.data_ptr(), counts_l.data_ptr(), cap_r,
+            kps_r.data_ptr(), desc_r.data_ptr(), counts_r.data_ptr(), self.mbf, float(np.float32(self.mbf) / np.float32(self.fx)) if mb is None else mb,
+            uright.data_ptr(), depth_out.data_ptr()))
+        return uright, depth_out
+
     # -- Frame::AssignFeaturesToGrid ---------------------------------------------------------------------
     def assign_features_to_grid_batch_device(self, kps_un, counts, bounds: Bounds, cell_start=None, items=None):
         """-> (cell_start [F, 64*48+1] i32, items [F, cap] i16-as-u16): CSR over cell = ix*48 + iy;

@@ -82,6 +82,19 @@ def camera_sequence(width: int, height: int, n_frames: int, seed: int, max_shift
     return np.stack(frames)
 
 
+def stereo_pair(width: int, height: int, seed: int, disparities=(4, 9, 17, 30), sigma: float = 1.5):
+    """Rectified stereo pair: the right image is the left one with horizontal bands shifted by the band's
+    disparity (a feature at column u of the left image sits at u - d in the right one) plus N(0, sigma) noise."""
+    left = textured(width + 64, height, seed)
+    right = np.empty((height, width), np.uint8)
+    rng = np.random.default_rng(seed + 500)
+    edges = np.linspace(0, height, len(disparities) + 1).astype(int)
+    for d, y0, y1 in zip(disparities, edges[:-1], edges[1:]):
+        right[y0:y1] = left[y0:y1, d:d + width]
+    right = np.clip(np.rint(right.astype(np.float32) + rng.normal(0, sigma, right.shape)), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(left[:, :width]), right
+
+
 def random_descriptors(n: int, seed: int) -> np.ndarray:
     """n x 32 bytes of i.i.d. bits (config 3, set A)."""
     return np.random.default_rng(seed).integers(0, 256, size=(n, 32), dtype=np.uint8)

@@ -7,7 +7,10 @@
 // same results as this restatement on the seeded scenes of tests/test_matcher_ref.py (DescriptorDistance,
 // SearchForInitialization, the four SearchByProjection overloads, SearchByBoW x2, SearchForTriangulation,
 // Fuse x2, SearchBySim3); plus hand-checkable known answers and an independent pure-Python transliteration on
-// small cases (tests/test_matcher_oracle.py); cv2 for the OpenCV primitives.
+// small cases (tests/test_matcher_oracle.py); cv2 for the OpenCV primitives; the Frame glue against the
+// reference's own src/Frame.cc compiled verbatim (oracle/_ref/libframe_ref.so, tests/test_frame_ref.py).
+// om_compute_stereo_matches restates code the fork keeps COMMENTED OUT (src/Frame.cc:782-956): parity unpinned
+// against a reference build; pinned by a known-answer test and a pure-Python transliteration only.
 #include "orb_oracle.h"
 #include "cvprim.h"
 
@@ -261,6 +264,101 @@ void om_compute_stereo_from_rgbd(const oo_keypoint* k, const oo_keypoint* k_un, 
       depth_out[i] = d;
       uright[i] = k_un[i].x - mbf / d;
     }
+  }
+}
+
+// Frame::ComputeStereoMatches (src/Frame.cc:782-956, commented upstream code of this fork): row-band Hamming
+// association of left and right keypoints, 11x11 SAD refinement on the pyramid level of the left keypoint with a
+// parabola fit, then the 2.1 x median SAD outlier cut.  Rows outside the image are clamped when a right keypoint's
+// band is listed (the reference would index vRowIndices out of range); the SAD sums are integers, so every
+// accumulation order agrees.
+void om_compute_stereo_matches(const oo_keypoint* kl, const uint8_t* dl, int nl, const oo_keypoint* kr, const uint8_t* dr,
+                               int nr, const om_image* pyr_l, const om_image* pyr_r, int nlevels, const float* scale_factors,
+                               const float* inv_scale_factors, float mbf, float mb, float* uright, float* depth) {
+  (void)nlevels;
+  for (int i = 0; i < nl; ++i) { uright[i] = -1.0f; depth[i] = -1.0f; }           // :784-785
+  const int thOrbDist = (TH_HIGH + TH_LOW) / 2;                                     // :787
+  const int nRows = pyr_l[0].h;                                                     // :789
+  std::vector<std::vector<int> > vRowIndices(nRows);                                // :792-810
+  for (int iR = 0; iR < nr; ++iR) {
+    const float kpY = kr[iR].y;
+    const float r = 2.0f * scale_factors[kr[iR].octave];
+    const int maxr = (int)std::ceil(kpY + r);
+    const int minr = (int)std::floor(kpY - r);
+    for (int yi = std::max(minr, 0); yi <= std::min(maxr, nRows - 1); ++yi) vRowIndices[yi].push_back(iR);
+  }
+  const float minZ = mb, minD = 0, maxD = mbf / minZ;                               // :813-815
+  std::vector<std::pair<int, int> > vDistIdx;
+  for (int iL = 0; iL < nl; ++iL) {                                                 // :821
+    const int levelL = kl[iL].octave;
+    const float vL = kl[iL].y, uL = kl[iL].x;
+    const int row = (int)vL;
+    if (row < 0 || row >= nRows) continue;
+    const std::vector<int>& cand = vRowIndices[row];                                // :828
+    if (cand.empty()) continue;
+    const float minU = uL - maxD, maxU = uL - minD;
+    if (maxU < 0) continue;
+    int bestDist = TH_HIGH;                                                         // :839
+    int bestIdxR = 0;
+    for (size_t iC = 0; iC < cand.size(); ++iC) {                                   // :845-866
+      const int iR = cand[iC];
+      if (kr[iR].octave < levelL - 1 || kr[iR].octave > levelL + 1) continue;
+      const float uR = kr[iR].x;
+      if (uR >= minU && uR <= maxU) {
+        const int dist = om_distance(dl + 32 * (size_t)iL, dr + 32 * (size_t)iR);
+        if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+      }
+    }
+    if (!(bestDist < thOrbDist)) continue;                                          // :869
+    const float uR0 = kr[bestIdxR].x;
+    const float scaleFactor = inv_scale_factors[levelL];
+    const float scaleduL = std::round(uL * scaleFactor);                            // :873-875 (roundf)
+    const float scaledvL = std::round(vL * scaleFactor);
+    const float scaleduR0 = std::round(uR0 * scaleFactor);
+    const int w = 5, L = 5;
+    const om_image& IL = pyr_l[levelL];
+    const om_image& IR = pyr_r[levelL];
+    const int yl = (int)scaledvL, xl = (int)scaleduL, xr = (int)scaleduR0;
+    const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;             // :888-891
+    if (iniu < 0 || endu >= IR.w) continue;
+    auto PL = [&](int y, int x) { return (int)IL.data[(ptrdiff_t)y * (ptrdiff_t)IL.step + x]; };
+    auto PR = [&](int y, int x) { return (int)IR.data[(ptrdiff_t)y * (ptrdiff_t)IR.step + x]; };
+    const int cl = PL(yl, xl);
+    int bestSad = INT_MAX, bestincR = 0;
+    float vDists[2 * 5 + 1];
+    for (int incR = -L; incR <= L; ++incR) {                                        // :893-908
+      const int cr = PR(yl, xr + incR);
+      int sad = 0;
+      for (int dy = -w; dy <= w; ++dy)
+        for (int dx = -w; dx <= w; ++dx) sad += std::abs((PL(yl + dy, xl + dx) - cl) - (PR(yl + dy, xr + incR + dx) - cr));
+      const float dist = (float)sad;
+      if (dist < (float)bestSad) { bestSad = (int)dist; bestincR = incR; }
+      vDists[L + incR] = dist;
+    }
+    if (bestincR == -L || bestincR == L) continue;                                  // :910
+    const float dist1 = vDists[L + bestincR - 1], dist2 = vDists[L + bestincR], dist3 = vDists[L + bestincR + 1];
+    const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2)); // :918
+    if (deltaR < -1 || deltaR > 1) continue;
+    float bestuR = scale_factors[levelL] * ((float)scaleduR0 + (float)bestincR + deltaR);   // :924
+    float disparity = uL - bestuR;
+    if (disparity >= minD && disparity < maxD) {                                    // :928-938
+      if (disparity <= 0) {
+        disparity = 0.01;
+        bestuR = uL - 0.01;   // float - double, rounded once
+      }
+      depth[iL] = mbf / disparity;
+      uright[iL] = bestuR;
+      vDistIdx.push_back(std::make_pair(bestSad, iL));
+    }
+  }
+  if (vDistIdx.empty()) return;
+  std::sort(vDistIdx.begin(), vDistIdx.end());                                      // :942-955
+  const float median = vDistIdx[vDistIdx.size() / 2].first;
+  const float thDist = 1.5f * 1.4f * median;
+  for (int i = (int)vDistIdx.size() - 1; i >= 0; --i) {
+    if (vDistIdx[i].first < thDist) break;
+    uright[vDistIdx[i].second] = -1;
+    depth[vDistIdx[i].second] = -1;
   }
 }
 

@@ -155,6 +155,15 @@ void om_undistort_keypoints(const oo_keypoint* k, int n, float fx, float fy, flo
 void om_compute_image_bounds(int cols, int rows, float fx, float fy, float cx, float cy, const float* dist5, om_bounds* b);
 void om_compute_stereo_from_rgbd(const oo_keypoint* k, const oo_keypoint* k_un, int n, const float* depth, int cols,
                                  int rows, size_t stride_floats, float mbf, float* uright, float* depth_out);
+// Frame::ComputeStereoMatches (src/Frame.cc:782-956; upstream ORB-SLAM2's rectified-stereo association, kept
+// commented in this fork — SURVEY.md §8(f) rank 4).  pyr_l / pyr_r: mvImagePyramid[level] of the two extractors
+// (data -> the level's ROI origin; the 19-px EDGE_THRESHOLD border around it is read by the 11x11 SAD windows).
+// uright / depth: mvuRight / mvDepth (-1 where no match).  An empty match list skips the median filter (the
+// reference would index an empty vector).
+typedef struct { const uint8_t* data; int32_t w, h; size_t step; } om_image;
+void om_compute_stereo_matches(const oo_keypoint* kl, const uint8_t* dl, int nl, const oo_keypoint* kr, const uint8_t* dr,
+                               int nr, const om_image* pyr_l, const om_image* pyr_r, int nlevels, const float* scale_factors,
+                               const float* inv_scale_factors, float mbf, float mb, float* uright, float* depth);
 // CSR over cell = ix*48 + iy (cell_start: 64*48 + 1 entries), items in insertion order.
 void om_assign_features_to_grid(const oo_keypoint* k_un, int n, om_bounds b, int32_t* cell_start, int32_t* items);
 

@@ -427,6 +427,34 @@ def compute_stereo_from_rgbd(k, k_un, depth, mbf):
     return ur, dz
 
 
+class OmImage(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("w", C.c_int32), ("h", C.c_int32), ("step", C.c_size_t)]
+
+
+def compute_stereo_matches(kl, dl, kr, dr, pyr_l, pyr_r, scale, inv_scale, mbf, mb, border=19):
+    """pyr_l / pyr_r: per level the BORDERED level image ((h+2*border) x (w+2*border) u8) of each extractor."""
+    lib = load("port")
+    kl, kr = np.ascontiguousarray(kl, dtype=KP_DTYPE), np.ascontiguousarray(kr, dtype=KP_DTYPE)
+    dl, dr = np.ascontiguousarray(dl, dtype=np.uint8), np.ascontiguousarray(dr, dtype=np.uint8)
+    scale, inv_scale = np.ascontiguousarray(scale, dtype=np.float32), np.ascontiguousarray(inv_scale, dtype=np.float32)
+    keep = [[np.ascontiguousarray(a) for a in p] for p in (pyr_l, pyr_r)]
+    views = []
+    for p in keep:
+        arr = (OmImage * len(p))()
+        for i, a in enumerate(p):
+            arr[i] = OmImage(a.ctypes.data + border * a.strides[0] + border, a.shape[1] - 2 * border, a.shape[0] - 2 * border,
+                             a.strides[0])
+        views.append(arr)
+    uright, depth = np.empty(len(kl), np.float32), np.empty(len(kl), np.float32)
+    f = lib.om_compute_stereo_matches
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                  C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    f(kl.ctypes.data, dl.ctypes.data, len(kl), kr.ctypes.data, dr.ctypes.data, len(kr), views[0], views[1], len(pyr_l),
+      scale.ctypes.data, inv_scale.ctypes.data, mbf, mb, uright.ctypes.data, depth.ctypes.data)
+    return uright, depth
+
+
 def assign_features_to_grid(k_un, bounds):
     lib = load("port")
     k_un = np.ascontiguousarray(k_un, dtype=KP_DTYPE)

@@ -83,3 +83,41 @@ def test_extract_undistort_stereo_grid_on_device(oracle_port):
         assert np.array_equal(h_start[f], r_start), f"frame {f}: grid cell starts"
         assert np.array_equal(h_items[f, : r_start[-1]].astype(np.int32), r_items), f"frame {f}: grid items"
     assert (h_dz > 0).sum() > 1000
+
+
+@pytest.mark.parametrize("W,H,nf,F", [(640, 480, 1000, 3), (1241, 376, 2000, 2)])
+def test_compute_stereo_matches_on_device(oracle_port, W, H, nf, F):
+    """Frame::ComputeStereoMatches (src/Frame.cc:782-956): two extractors -> row-band Hamming association -> SAD
+    refinement on the device-resident pyramids -> median cut, equal to the oracle bit for bit (mvuRight, mvDepth)."""
+    import torch
+    from multi_orb_slam_b200.extractor import ORBextractor
+    from multi_orb_slam_b200.frame import FrameGlue
+    from multi_orb_slam_b200.synth import stereo_pair
+    O = oracle_port
+    pairs = [stereo_pair(W, H, 40 + i, disparities=(3 + i, 11, 24 + 2 * i, 41)) for i in range(F)]
+    exl = ORBextractor(nf, 1.2, 8, 20, 7, image_size=(W, H), max_batch=F)
+    exr = ORBextractor(nf, 1.2, 8, 20, 7, image_size=(W, H), max_batch=F)
+    dev_l = torch.from_numpy(np.stack([p[0] for p in pairs])).cuda()
+    dev_r = torch.from_numpy(np.stack([p[1] for p in pairs])).cuda()
+    kl, dl, nl = exl.extract_batch_device(dev_l)
+    kr, dr, nr = exr.extract_batch_device(dev_r)
+    glue = FrameGlue(718.856, 718.856, 607.1928, 185.2157, (0, 0, 0, 0, 0), mbf=386.1448)
+    ur, z = glue.stereo_matches_batch_device(exl, exr, kl, dl, nl, kr, dr, nr)
+    torch.cuda.synchronize()
+    ur, z, nl = ur.cpu().numpy(), z.cpu().numpy(), nl.cpu().numpy()
+    mb = np.float32(386.1448) / np.float32(718.856)
+    n_ok = 0
+    for f, (left, right) in enumerate(pairs):
+        ref = []
+        for img in (left, right):
+            ex = O.extractor("port", nfeatures=nf)
+            k, d, _ = ex.extract(img)
+            ref.append((k, d, [ex.pyramid_level(l) for l in range(8)], ex.scale_tables()))
+        (k0, d0, p0, t0), (k1, d1, p1, _) = ref
+        assert nl[f] == len(k0)
+        want_u, want_z = O.compute_stereo_matches(k0, d0, k1, d1, p0, p1, t0[0], t0[1], 386.1448, mb)
+        assert np.array_equal(ur[f, : nl[f]].view(np.uint32), want_u.view(np.uint32)), f"pair {f}: mvuRight"
+        assert np.array_equal(z[f, : nl[f]].view(np.uint32), want_z.view(np.uint32)), f"pair {f}: mvDepth"
+        assert (ur[f, nl[f]:] == -1).all()
+        n_ok += int((want_u >= 0).sum())
+    assert n_ok > 0.3 * nl.sum()
