@@ -302,7 +302,11 @@ def main():
     ap.add_argument("--ref-rig-frames", type=int, default=64, help="rig-frames per CPU reference step")
     ap.add_argument("--cpu-rig-frames", type=int, default=256, help="rig-frames of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="steps in flight in the streaming end-to-end leg")
     ap.add_argument("--e2e-chunks", type=int, default=1, help="chunks per step of the streaming end-to-end leg")
+    ap.add_argument("--serial-match", action="store_true",
+                    help="run SearchForInitialization after both cameras on the extractor stream (A/B of the side stream)")
+    ap.add_argument("--split-profile", action="store_true", help="take the per-stage events on separate steps")
     ap.add_argument("--bf-size", type=int, default=65536, help="N of the N x N brute-force matching leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -331,17 +335,23 @@ def main():
     F = args.rig_frames
     cams = make_sequences(F, 2 * rank)  # every rank owns its own rig-frames: independent units, no exchange
     # pinned host copies (e2e leg) and HBM-resident copies (device leg)
-    h_img = [torch.from_numpy(c).pin_memory() for c in cams]
+    from multi_orb_slam_b200.hostmem import numa_local
+    with numa_local(local_rank) as numa_cpus:  # pinned pages on the GPU's NUMA node (matters at N > 1)
+        h_img = [torch.from_numpy(c).pin_memory() for c in cams]
     d_img = [t.to(dev) for t in h_img]
     ex = [ORBextractor(NF0, SCALE, NLEVELS, INI_TH, MIN_TH, image_size=(W, H), max_batch=F, device=local_rank),
           ORBextractor(NF1, SCALE, NLEVELS, INI_TH, MIN_TH, image_size=(W, H), max_batch=F, device=local_rank)]
     matcher = ORBmatcher(NNRATIO, True, device=local_rank)
-    # One stream for both extractors and the matcher.  (Running the two cameras on two streams was
-    # measured: 4.70 ms vs 4.43 ms per step — the kernels already fill the GPU, so it only thrashes.)
+    # One stream for both extractors.  (Running the two cameras on two streams was measured: 4.70 ms
+    # vs 4.43 ms per step — the kernels already fill the GPU, so it only thrashes.)  The matcher of
+    # camera 0 goes to a high-priority side stream as soon as camera 0 is extracted: its ordered
+    # resolve is a serial chain per pair (SMs ~90 % idle), which hides under camera 1's extraction.
     stream = torch.cuda.Stream(device=dev)
+    s_match = stream if args.serial_match else torch.cuda.Stream(device=dev, priority=-1)
     for e in ex:
         e.set_stream(stream.cuda_stream)
-    matcher.set_stream(stream.cuda_stream)
+    matcher.set_stream(s_match.cuda_stream)
+    ev_cam0, ev_matched = torch.cuda.Event(), torch.cuda.Event()
     caps = [e.capacity for e in ex]
     kps = [torch.empty((F, c, 6), dtype=torch.float32, device=dev) for c in caps]
     desc = [torch.empty((F, c, 32), dtype=torch.uint8, device=dev) for c in caps]
@@ -355,20 +365,29 @@ def main():
                                                  counts[0][1:], bounds, None, WINDOW, m12, nmatch)
 
     def device_step(images, match_events=None):
-        for c in range(2):
-            ex[c].extract_batch_device(images[c], kps[c], desc[c], counts[c])
+        ex[0].extract_batch_device(images[0], kps[0], desc[0], counts[0])
+        if args.serial_match:
+            ex[1].extract_batch_device(images[1], kps[1], desc[1], counts[1])
+        else:
+            ev_cam0.record(stream)
+            s_match.wait_event(ev_cam0)
         if match_events:
-            match_events[0].record(stream)
+            match_events[0].record(s_match)
         run_match()
         if match_events:
-            match_events[1].record(stream)
+            match_events[1].record(s_match)
+        if not args.serial_match:
+            ex[1].extract_batch_device(images[1], kps[1], desc[1], counts[1])
+            ev_matched.record(s_match)
+            stream.wait_event(ev_matched)
 
     # End-to-end leg: the package's streaming front end (multi_orb_slam_b200/pipeline.py).  Every step
     # the frames start in pinned host memory and the results end in pinned host memory; the copies
-    # of step k+1 overlap the kernels of step k (three streams, two-deep buffers).
+    # of step k+1 overlap the kernels of step k (four streams, three-deep buffers).
     from multi_orb_slam_b200.pipeline import RigPipeline
-    pipe = RigPipeline((NF0, NF1), SCALE, NLEVELS, INI_TH, MIN_TH, image_size=(W, H), rig_frames=F,
-                       n_chunks=args.e2e_chunks, depth=2, window=WINDOW, nnratio=NNRATIO, device=local_rank)
+    with numa_local(local_rank):
+        pipe = RigPipeline((NF0, NF1), SCALE, NLEVELS, INI_TH, MIN_TH, image_size=(W, H), rig_frames=F,
+                           n_chunks=args.e2e_chunks, depth=args.e2e_depth, window=WINDOW, nnratio=NNRATIO, device=local_rank)
 
     def e2e_run(steps):
         """K pipelined steps; returns (device ms per step, wall ms per step, last result)."""
@@ -377,11 +396,13 @@ def main():
         t0 = time.perf_counter()
         e0.record(pipe.s_in)        # first activity of a step: its H2D copies
         ticket = -1
+        lag = pipe.depth - 1
         for k in range(steps):
             ticket = pipe.submit(h_img)
-            if k >= 1:
-                pipe.result(ticket - 1)   # the consumer reads step k-1 while step k is in flight
-        res = pipe.result(ticket)
+            if k >= lag:
+                pipe.result(ticket - lag)   # the consumer reads step k-lag while the later steps are in flight
+        for t in range(max(ticket - lag + 1, 0), ticket + 1):
+            res = pipe.result(t)
         e1.record(pipe.s_out)       # last activity: the D2H copies of the last step
         pipe.drain()
         wall = (time.perf_counter() - t0) / steps * 1e3
@@ -423,8 +444,6 @@ def main():
         for _ in range(args.warmup):
             device_step(d_img)
     stream.synchronize()
-    for e in ex:
-        e.set_profiling(True)
     m_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     step_i = [0]
 
@@ -436,8 +455,18 @@ def main():
     if rank == 0:
         sampler.start()
     l0 = launches()
-    ms_step = timed(profiled_step, args.steps, False)
-    gpu_launches = launches() - l0
+    if args.split_profile:
+        # the timed steps run free (stages may overlap); the per-stage events are taken on K more steps
+        ms_step = timed(lambda: device_step(d_img), args.steps, False)
+        gpu_launches = launches() - l0
+        for e in ex:
+            e.set_profiling(True)
+        timed(profiled_step, args.steps, False)
+    else:
+        for e in ex:
+            e.set_profiling(True)
+        ms_step = timed(profiled_step, args.steps, False)
+        gpu_launches = launches() - l0
     stage_ms = np.zeros(5)
     for e in ex:
         s, n = e.stage_times_ms()
@@ -468,6 +497,8 @@ def main():
     # ---- Hamming matches/s: brute-force leg (BASELINE.json configs[2] upper end) ----------------
     from multi_orb_slam_b200.synth import perturbed_descriptors, random_descriptors
     nbf = args.bf_size
+    s_match.synchronize()
+    matcher.set_stream(stream.cuda_stream)  # the remaining legs time the matcher on `stream`
     A = random_descriptors(nbf, 7)
     Bq, _ = perturbed_descriptors(A, 8)
     dA, dB = torch.from_numpy(A).to(dev), torch.from_numpy(Bq).to(dev)
@@ -556,7 +587,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms_dev, "wall_ms_per_step": e2e_wall,
                 "api": "multi_orb_slam_b200.pipeline.RigPipeline.submit/result", "chunks_per_step": pipe.n_chunks,
-                "pipeline_depth": pipe.depth, "h2d_copy_alone_ms": h2d_ms},
+                "pipeline_depth": pipe.depth, "h2d_copy_alone_ms": h2d_ms,
+                "pinned_numa_bound_cpus": numa_cpus},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",

@@ -6,12 +6,16 @@ ORBmatcher::SearchForInitialization, src/Tracking.cc:870-871), batched over `rig
 rig-frames per step and software-pipelined over three CUDA streams:
 
     copy-in   H2D of the next chunk of frames            (PCIe, DMA engine)
-    compute   extractor of every camera, then the matcher (all kernels on ONE stream: they fill
-              the GPU on their own, running cameras concurrently only thrashes the caches)
+    compute   extractor of every camera (all extractor kernels on ONE stream: they fill the GPU
+              on their own, running cameras concurrently only thrashes the caches)
+    match     SearchForInitialization of camera 0, on a high-priority side stream as soon as camera
+              0 is extracted: its ordered resolve is a serial chain per pair that leaves the SMs
+              ~90 % idle, so it runs underneath the extraction of the other cameras
     copy-out  D2H of keypoints / descriptors / matches    (PCIe, the other DMA engine)
 
-Device image buffers form a ring of chunks, output buffers are `depth` deep, so the copies of step
-k+1 overlap the kernels of step k; `submit` never blocks the host, `result` waits for one step.
+Device image buffers and output buffers are `depth` (default 3) steps deep, so the copies of step
+k+1 overlap the kernels of step k even while the consumer still waits for step k-1; `submit` never
+blocks the host, `result` waits for one step.
 There is no CPU fallback: the extractor and matcher are the CUDA library's."""
 from __future__ import annotations
 
@@ -36,7 +40,7 @@ class RigStepResult:
 class RigPipeline:
     def __init__(self, nfeatures: Sequence[int] = (1000, 500), scaleFactor: float = 1.2, nlevels: int = 8,
                  iniThFAST: int = 20, minThFAST: int = 7, *, image_size: Tuple[int, int] = (640, 480),
-                 rig_frames: int = 256, n_chunks: int = 1, depth: int = 2, window: int = 100, nnratio: float = 0.9,
+                 rig_frames: int = 256, n_chunks: int = 1, depth: int = 3, window: int = 100, nnratio: float = 0.9,
                  match: bool = True, device: int = 0):
         import torch
         self.torch = torch
@@ -47,18 +51,20 @@ class RigPipeline:
         self.dev = torch.device("cuda", device)
         self.n_cams = len(nfeatures)
         self.s_in, self.s_compute, self.s_out = (torch.cuda.Stream(device=self.dev) for _ in range(3))
+        self.s_match = torch.cuda.Stream(device=self.dev, priority=-1)
         self.ex: List[ORBextractor] = [
             ORBextractor(nf, scaleFactor, nlevels, iniThFAST, minThFAST, image_size=image_size, max_batch=self.chunk,
                          device=device) for nf in nfeatures]
         for e in self.ex:
             e.set_stream(self.s_compute.cuda_stream)
         self.matcher = ORBmatcher(nnratio, True, device=device)
-        self.matcher.set_stream(self.s_compute.cuda_stream)
+        self.matcher.set_stream(self.s_match.cuda_stream)
         self.caps = [e.capacity for e in self.ex]
         self.bounds = Bounds(0.0, float(self.W), 0.0, float(self.H))
         F, dev = self.F, self.dev
-        # ring of chunk-sized device image buffers, two steps deep
-        self.n_ring = 2 * self.n_chunks
+        # ring of chunk-sized device image buffers, `depth` steps deep: with depth 3 the consumer can still be
+        # reading step k-2 while step k-1 computes and the frames of step k are already on their way
+        self.n_ring = self.depth * self.n_chunks
         self.img = [[torch.empty((self.chunk, self.H, self.W), dtype=torch.uint8, device=dev) for _ in range(self.n_cams)]
                     for _ in range(self.n_ring)]
         self.img_ready = [None] * self.n_ring
@@ -97,6 +103,7 @@ class RigPipeline:
         if self.done[slot] is not None:
             # the slot's previous results must have left the device before they are overwritten
             self.s_compute.wait_event(self.done[slot])
+        ev_match = None
         for ci in range(self.n_chunks):
             f0, f1 = ci * self.chunk, min(self.F, (ci + 1) * self.chunk)
             if f0 >= f1:
@@ -114,6 +121,8 @@ class RigPipeline:
                 self.s_compute.wait_event(self.img_ready[b])
                 for c in range(self.n_cams):
                     self.ex[c].extract_batch_device(self.img[b][c][:n], d.kps[c][f0:f1], d.desc[c][f0:f1], d.counts[c][f0:f1])
+                    if c == 0 and f1 == self.F and self.match and self.F > 1:
+                        ev_match = self._launch_match(d)
                 self.img_free[b] = torch.cuda.Event()
                 self.img_free[b].record(self.s_compute)
             with torch.cuda.stream(self.s_out):
@@ -123,20 +132,28 @@ class RigPipeline:
                     h.desc[c][f0:f1].copy_(d.desc[c][f0:f1], non_blocking=True)
                     h.counts[c][f0:f1].copy_(d.counts[c][f0:f1], non_blocking=True)
         if self.match and self.F > 1:
-            with torch.cuda.stream(self.s_compute):
-                # pairs (t, t+1) of camera 0: the F2 arrays are the same buffers shifted by one frame
-                self.matcher.search_for_initialization_device(
-                    self.F - 1, self.caps[0], d.kps[0], d.desc[0], d.counts[0], d.kps[0][1:], d.desc[0][1:], d.counts[0][1:],
-                    self.bounds, None, self.window, d.matches12, d.nmatches)
-                ev = torch.cuda.Event()
-                ev.record(self.s_compute)
             with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(ev)
+                self.s_out.wait_event(ev_match)
                 h.matches12.copy_(d.matches12, non_blocking=True)
                 h.nmatches.copy_(d.nmatches, non_blocking=True)
         self.done[slot] = torch.cuda.Event()
         self.done[slot].record(self.s_out)
         return step
+
+    def _launch_match(self, d: RigStepResult):
+        """Camera 0 of the whole step is extracted (s_compute): match it on the side stream."""
+        torch = self.torch
+        ev0 = torch.cuda.Event()
+        ev0.record(self.s_compute)
+        with torch.cuda.stream(self.s_match):
+            self.s_match.wait_event(ev0)
+            # pairs (t, t+1) of camera 0: the F2 arrays are the same buffers shifted by one frame
+            self.matcher.search_for_initialization_device(
+                self.F - 1, self.caps[0], d.kps[0], d.desc[0], d.counts[0], d.kps[0][1:], d.desc[0][1:], d.counts[0][1:],
+                self.bounds, None, self.window, d.matches12, d.nmatches)
+            ev = torch.cuda.Event()
+            ev.record(self.s_match)
+        return ev
 
     def result(self, ticket: int) -> RigStepResult:
         """Blocks until the step's results are in pinned host memory."""
@@ -151,5 +168,5 @@ class RigPipeline:
         return self.result(self.submit(h_images))
 
     def drain(self) -> None:
-        for s in (self.s_in, self.s_compute, self.s_out):
+        for s in (self.s_in, self.s_compute, self.s_match, self.s_out):
             s.synchronize()

@@ -14,26 +14,29 @@ def _kp(a):
     return np.ascontiguousarray(a).view(KP_DTYPE).reshape(-1)
 
 
-@pytest.mark.parametrize("n_chunks", [1, 3])
-def test_pipeline_steps_match_oracle(oracle_port, n_chunks):
+@pytest.mark.parametrize("n_chunks,depth", [(1, 2), (3, 2), (1, 3)])
+def test_pipeline_steps_match_oracle(oracle_port, n_chunks, depth):
     import torch
     from multi_orb_slam_b200.pipeline import RigPipeline
     O = oracle_port
-    F, W, H, steps = 5, 320, 240, 4
-    pipe = RigPipeline((300, 150), 1.2, 8, 20, 7, image_size=(W, H), rig_frames=F, n_chunks=n_chunks, depth=2,
+    F, W, H, steps = 5, 320, 240, 5
+    pipe = RigPipeline((300, 150), 1.2, 8, 20, 7, image_size=(W, H), rig_frames=F, n_chunks=n_chunks, depth=depth,
                        window=100, nnratio=0.9, device=0)
     seqs = [[torch.from_numpy(camera_sequence(W, H, F, 10 * s + c)).pin_memory() for c in range(2)] for s in range(steps)]
     ports = [O.extractor("port", nfeatures=300), O.extractor("port", nfeatures=150)]
     got = {}
+    def take(t):
+        r = pipe.result(t)
+        got[t] = ([x.numpy().copy() for x in r.kps], [x.numpy().copy() for x in r.desc],
+                  [x.numpy().copy() for x in r.counts], r.matches12.numpy().copy(), r.nmatches.numpy().copy())
+
+    lag = depth - 1
     for s in range(steps):
         t = pipe.submit(seqs[s])
-        if s >= 1:  # consume step s-1 while step s is in flight
-            r = pipe.result(t - 1)
-            got[t - 1] = ([x.numpy().copy() for x in r.kps], [x.numpy().copy() for x in r.desc],
-                          [x.numpy().copy() for x in r.counts], r.matches12.numpy().copy(), r.nmatches.numpy().copy())
-    r = pipe.result(steps - 1)
-    got[steps - 1] = ([x.numpy().copy() for x in r.kps], [x.numpy().copy() for x in r.desc],
-                      [x.numpy().copy() for x in r.counts], r.matches12.numpy().copy(), r.nmatches.numpy().copy())
+        if s >= lag:  # consume step s-lag while the later steps are in flight
+            take(t - lag)
+    for t in range(steps - lag, steps):
+        take(t)
     with pytest.raises(ValueError):
         pipe.result(0)  # slot already reused
     for s in range(steps):
