@@ -466,7 +466,8 @@ __global__ void __launch_bounds__(256) k_octree(const OrbGeom* __restrict__ g, c
                                                 const int* __restrict__ cell_count, uint32_t* __restrict__ keys,
                                                 uint16_t* __restrict__ knode, uint32_t* __restrict__ sel,
                                                 int* __restrict__ sel_count, int smem_keys) {
-  const int level = blockIdx.x, frame = blockIdx.y;
+  // level-major launch order: the big level-0 problems start first and the small top levels fill the tail
+  const int level = blockIdx.y, frame = blockIdx.x;
   const OrbLevelGeom& L = g->lv[level];
   OtScratch s;
   const int scratch_bytes = ot_layout(s, g->ot_cap, g->ot_scan_cap, 256);
@@ -846,7 +847,7 @@ cudaError_t prepare_octree(const OrbGeom& g) {
 void launch_octree(const OrbGeomHost& gh, int n_frames, const uint32_t* d_cand, const int* d_cell_count,
                    uint32_t* d_keys, uint16_t* d_knode, uint32_t* d_sel, int* d_sel_count, cudaStream_t st,
                    long long* launches) {
-  k_octree<<<dim3(gh.g.nlevels, n_frames), 256, octree_smem_bytes(gh.g), st>>>(gh.d_geom, d_cand, d_cell_count, d_keys,
+  k_octree<<<dim3(n_frames, gh.g.nlevels), 256, octree_smem_bytes(gh.g), st>>>(gh.d_geom, d_cand, d_cell_count, d_keys,
                                                                                 d_knode, d_sel, d_sel_count, octree_smem_keys(gh.g));
   ++*launches;
 }

@@ -184,3 +184,46 @@ def test_cpp_dropin_classes_run(O, tmp_path):
     fv = feature_vector(k_ref["octave"])
     bn, bm12, bm21 = O.search_by_bow(d_ref, k_ref["angle"], None, fv, d_ref, k_ref["angle"], None, fv, 0.7, True, 50)
     assert nbow == bn and bow_self == int((bm21 == np.arange(len(bm21))).sum())
+
+
+def test_full_size_batch_is_frame_independent(O):
+    """BASELINE.json configs[1] size — 256 frames per handle, both camera quotas — through the size-independent
+    property of the path: camera-frames are independent units, so a batch of 8 distinct frames repeated in scrambled
+    order must return, in EVERY slot, the oracle's features for the frame in that slot, and consecutive-frame
+    SearchForInitialization over the batch must equal the oracle's result for the same pair of frames."""
+    import torch
+    from multi_orb_slam_b200._lib import KP_DTYPE, Bounds
+    from multi_orb_slam_b200.matcher import ORBmatcher
+    F, D = 256, 8
+    base = np.stack([textured(640, 480, 300 + i) for i in range(D)])
+    order = np.random.default_rng(12).integers(0, D, F)
+    dev = torch.from_numpy(base[order]).cuda()
+    for nf in (1000, 500):
+        ex = _gpu(nfeatures=nf, max_batch=F)
+        kps, desc, counts = ex.extract_batch_device(dev)
+        ex.sync()
+        h_k, h_d, h_n = kps.cpu().numpy(), desc.cpu().numpy(), counts.cpu().numpy()
+        port = O.extractor("port", nfeatures=nf)
+        ref = [port.extract(base[i])[:2] for i in range(D)]
+        for f in range(F):
+            k = h_k[f, : h_n[f]].copy().view(KP_DTYPE).reshape(-1)
+            _assert_same_features(k, h_d[f, : h_n[f]], *ref[order[f]], f"nfeatures {nf} slot {f} (frame {order[f]})")
+        if nf != 1000:
+            continue
+        m = ORBmatcher(0.9, True)
+        cap = kps.shape[1]
+        m12 = torch.empty((F - 1, cap), dtype=torch.int32, device="cuda")
+        nm = torch.empty((F - 1,), dtype=torch.int32, device="cuda")
+        m.search_for_initialization_device(F - 1, cap, kps, desc, counts, kps[1:], desc[1:], counts[1:],
+                                           Bounds(0.0, 640.0, 0.0, 480.0), None, 100, m12, nm)
+        torch.cuda.synchronize()
+        m12, nm = m12.cpu().numpy(), nm.cpu().numpy()
+        cache = {}
+        for f in range(F - 1):
+            key = (int(order[f]), int(order[f + 1]))
+            if key not in cache:
+                (k1, d1), (k2, d2) = ref[key[0]], ref[key[1]]
+                prev = np.stack([k1["x"], k1["y"]], axis=1).astype(np.float32)
+                cache[key] = O.search_for_initialization(k1, d1, k2, d2, (0, 640, 0, 480), prev, 100, 0.9, True)
+            rn, rm12, _ = cache[key]
+            assert nm[f] == rn and np.array_equal(m12[f, : len(rm12)], rm12), f"pair {f} {key}"

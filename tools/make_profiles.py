@@ -72,12 +72,14 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_outpu
 rr = list(csv.reader(raw.splitlines()))
 h = rr[0]
 ki, ri, wi, gi = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("launch__grid_size")
+ii = h.index("smsp__inst_executed.sum")
 units = dict(zip(h, rr[1]))
 scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
 stage_of = {"k_pyr_resize": "pyramid", "k_fast_cells": "fast", "k_octree": "octree", "k_blur": "blur",
             "k_orient_describe": "orient_describe"}
 F = bench["config"]["rig_frames_per_gpu"]
 per = {}
+instr = {}
 seen_handle = {}
 for r in rr[2:]:
     k = short(r[ki]).split("<")[0]
@@ -91,8 +93,9 @@ for r in rr[2:]:
     seen_handle[st] = seen_handle.get(st, 0) + 1
     b = float(r[ri]) * scale.get(units["dram__bytes_read.sum"], 1.0) + float(r[wi]) * scale.get(units["dram__bytes_write.sum"], 1.0)
     per[st] = per.get(st, 0.0) + b / F
+    instr[st] = instr.get(st, 0.0) + float(r[ii]) / F
 json.dump({"source": f"profiles/{tag}_ncu_all_kernels.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of the "
                      f"nFeatures-1000 handle's launches, one launch = {F} camera-frames)",
-           "dram_bytes_per_camera_frame": per}, open(os.path.join(pr, f"{tag}_traffic.json"), "w"), indent=1)
+           "dram_bytes_per_camera_frame": per, "warp_instr_per_camera_frame": instr}, open(os.path.join(pr, f"{tag}_traffic.json"), "w"), indent=1)
 print(open(os.path.join(pr, f"{tag}_launches.md")).read())
 print(json.dumps(per, indent=1))
