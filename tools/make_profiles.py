@@ -39,12 +39,13 @@ rows = list(csv.DictReader(lines))
 open(os.path.join(pr, f"{tag}_launches.csv"), "w").write("\n".join(lines) + "\n")
 # one timed step of the device-resident leg = the launches between the warm-up and the e2e leg;
 # shares are taken over all extractor/matcher launches of the run (same mix every step)
-agg = {}
+agg, other = {}, {}
+STEP_KERNELS = ("k_pyr_resize", "k_fast_cells", "k_octree", "k_blur", "k_orient_describe", "k_build_grid", "k_init_")
 for r in rows:
     k = short(r["Kernel Name"])
-    if k.startswith("k_bruteforce") or k.startswith("k_bf") or "at::" in k or "elementwise" in k or "reduce" in k.lower():
+    if "at::" in k or "elementwise" in k or "reduce" in k.lower():
         continue
-    a = agg.setdefault(k, [0, 0.0])
+    a = (agg if k.startswith(STEP_KERNELS) else other).setdefault(k, [0, 0.0])
     a[0] += 1
     a[1] += float(r["Metric Value"]) / 1e3
 tot = sum(v[1] for v in agg.values())
@@ -52,10 +53,16 @@ with open(os.path.join(pr, f"{tag}_launches.md"), "w") as f:
     f.write(f"# {tag} — ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --bf-size 4096`\n\n"
             "`ncu --metrics gpu__time_duration.sum --clock-control none` — per-launch times are cold-cache and "
             "serialised: compare SHARES with bench.py's `stages`, not absolutes.  Extractor and "
-            "SearchForInitialization kernels of all steps (device-resident leg and streaming leg).\n\n"
+            "SearchForInitialization kernels of all steps (device-resident leg and streaming leg).  In bench.py the "
+            "matcher runs on a side stream underneath camera 2's pyramid / FAST, so its own share and the pyramid's "
+            "read a little higher there than in this serialised list.\n\n"
             "| kernel | launches | total us | avg us | share |\n|---|---|---|---|---|\n")
     for k, (n, us) in agg.items():
         f.write(f"| {k} | {n} | {us:.1f} | {us / n:.1f} | {100 * us / tot:.1f} % |\n")
+    f.write("\nKernels of the other legs of the same run (brute-force leg, widened rows of SURVEY.md 8(f)), not part of a step:\n\n"
+            "| kernel | launches | total us | avg us |\n|---|---|---|---|\n")
+    for k, (n, us) in other.items():
+        f.write(f"| {k} | {n} | {us:.1f} | {us / n:.1f} |\n")
     st = bench.get("stages", {})
     if st:
         ssum = sum(v["ms"] for v in st.values())

@@ -19,6 +19,8 @@ want = [("gpu__time_duration.sum", "time us"), ("launch__grid_size", "grid"), ("
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy %"),
         ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu pipe %"),
         ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu pipe %"),
+        ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lsu data wavefronts %"),
+        ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
         ("smsp__inst_executed.sum", "warp instr"),
         ("smsp__thread_inst_executed_per_inst_executed.ratio", "lanes/instr")]
 idx = [(hdr.index(k), n) for k, n in want if k in hdr]
