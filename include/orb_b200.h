@@ -114,6 +114,7 @@ typedef struct orbx_pyramid_view {
   const uint8_t* base[ORBX_MAX_LEVELS];
   size_t frame_stride[ORBX_MAX_LEVELS];
   float scale[ORBX_MAX_LEVELS], inv_scale[ORBX_MAX_LEVELS]; /* mvScaleFactor / mvInvScaleFactor */
+  void* stream; /* cudaStream_t the batch was produced on: a consumer on another stream must order itself after it */
 } orbx_pyramid_view;
 int orbx_get_pyramid_view(orbx_extractor* h, orbx_pyramid_view* out);
 
@@ -301,7 +302,8 @@ int orbm_compute_stereo_from_rgbd_device(orbm_matcher* m, int n_frames, int cap,
  * two extractors that produced the keypoints (mpORBextractorLeft / Right ->mvImagePyramid), d_kl/d_dl/d_nl and
  * d_kr/d_dr/d_nr their batch outputs (strides cap_l, cap_r; cap_r <= 4096).  mbf = baseline * fx, mb = mbf / fx.
  * Outputs d_uright / d_depth [n_frames][cap_l] = mvuRight / mvDepth (-1 where unmatched).  A pair with no accepted
- * match skips the median cut (the reference would index an empty vector). */
+ * match skips the median cut (the reference would index an empty vector).  The call orders the matcher's stream after
+ * the two extractor streams recorded in the views (an event wait on the device, no host synchronisation). */
 int orbm_compute_stereo_matches_device(orbm_matcher* m, const orbx_pyramid_view* left, const orbx_pyramid_view* right,
                                        int n_frames, int cap_l, const orbx_keypoint* d_kl, const uint8_t* d_dl,
                                        const int32_t* d_nl, int cap_r, const orbx_keypoint* d_kr, const uint8_t* d_dr,

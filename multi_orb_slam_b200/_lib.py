@@ -65,7 +65,7 @@ class PyramidView(C.Structure):
     """orbx_pyramid_view (include/orb_b200.h): device view of an extractor's mvImagePyramid for its last batch."""
     _fields_ = [("nlevels", C.c_int32), ("n_frames", C.c_int32), ("w", C.c_int32 * 16), ("h", C.c_int32 * 16),
                 ("pitch", C.c_int32 * 16), ("base", C.c_void_p * 16), ("frame_stride", C.c_size_t * 16),
-                ("scale", C.c_float * 16), ("inv_scale", C.c_float * 16)]
+                ("scale", C.c_float * 16), ("inv_scale", C.c_float * 16), ("stream", C.c_void_p)]
 
 
 if not os.path.exists(LIB_PATH):

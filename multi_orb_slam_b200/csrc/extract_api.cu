@@ -525,6 +525,7 @@ int orbx_get_pyramid_view(orbx_extractor* h, orbx_pyramid_view* out) {
   std::memset(out, 0, sizeof(*out));
   out->nlevels = h->cfg.nlevels;
   out->n_frames = h->last_batch;
+  out->stream = (void*)h->stream;
   for (int l = 0; l < h->cfg.nlevels; ++l) {
     const OrbLevelGeom& L = h->gh.g.lv[l];
     out->w[l] = L.w;

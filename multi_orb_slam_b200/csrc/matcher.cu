@@ -2206,6 +2206,16 @@ int orbm_compute_stereo_matches_device(orbm_matcher* m, const orbx_pyramid_view*
   cudaSetDevice(m->device);
   int32_t* sad = m->scratch<int32_t>(8, (size_t)n_frames * cap_l);
   if (!sad) return ORBX_E_CUDA;
+  // the keypoints and pyramids come from the extractors' streams: order this stream after them
+  for (const orbx_pyramid_view* v : {left, right}) {
+    if ((cudaStream_t)v->stream == m->stream) continue;
+    cudaEvent_t ev;
+    if (!m->check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate") ||
+        !m->check(cudaEventRecord(ev, (cudaStream_t)v->stream), "cudaEventRecord") ||
+        !m->check(cudaStreamWaitEvent(m->stream, ev, 0), "cudaStreamWaitEvent"))
+      return ORBX_E_CUDA;
+    cudaEventDestroy(ev);  // released once the wait has been satisfied
+  }
   k_stereo_match<<<dim3((cap_l + STEREO_LPB - 1) / STEREO_LPB, n_frames), 256, 0, m->stream>>>(
       *left, *right, cap_l, d_kl, d_dl, d_nl, cap_r, d_kr, d_dr, d_nr, mbf, mb, d_uright, d_depth, sad);
   k_stereo_median<<<n_frames, 256, 0, m->stream>>>(cap_l, d_nl, sad, d_uright, d_depth);
