@@ -578,11 +578,13 @@ def main():
         wi = json.load(open(tpath)).get("warp_instr_per_camera_frame", {})
         sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
         issue_peak = 148 * 4 * sm_clk * 1e6  # one warp instruction per scheduler per clock
-        for nme in names:
-            # captured on the nFeatures-1000 handle; the 500-feature camera runs the same per-pixel work
+        for nme in ("pyramid", "fast", "blur", "orient_describe"):
+            # captured on the nFeatures-1000 handle; the 500-feature camera runs the same per-pixel work, and the
+            # per-keypoint stage scales with its keypoints (the octree depends on the quota: not extrapolated)
             per_frame = wi.get(nme)
             if per_frame and stages[nme]["ms"] > 0:
-                rate = per_frame * 2 * F / (stages[nme]["ms"] * 1e-3)
+                units = 2 * F if nme != "orient_describe" else F * (n_kp[0] + n_kp[1]) / max(n_kp[0], 1)
+                rate = per_frame * units / (stages[nme]["ms"] * 1e-3)
                 stages[nme]["issue_frac"] = round(rate / issue_peak, 3)
         if wi.get(dom) and stages[dom]["ms"] > 0:
             rate = wi[dom] * 2 * F / (stages[dom]["ms"] * 1e-3)

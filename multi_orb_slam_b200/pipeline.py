@@ -67,7 +67,6 @@ class RigPipeline:
         self.n_ring = self.depth * self.n_chunks
         self.img = [[torch.empty((self.chunk, self.H, self.W), dtype=torch.uint8, device=dev) for _ in range(self.n_cams)]
                     for _ in range(self.n_ring)]
-        self.img_ready = [None] * self.n_ring
         self.img_free = [None] * self.n_ring
 
         def outs(pin):
@@ -110,24 +109,28 @@ class RigPipeline:
                 break
             n = f1 - f0
             b = (step * self.n_chunks + ci) % self.n_ring
+            # per-camera events: camera 0 starts computing while camera 1 is still uploading, and its
+            # features leave the device while camera 1 computes
+            ev_in, ev_done = [], []
             with torch.cuda.stream(self.s_in):
                 if self.img_free[b] is not None:
                     self.s_in.wait_event(self.img_free[b])
                 for c in range(self.n_cams):
                     self.img[b][c][:n].copy_(h_images[c][f0:f1], non_blocking=True)
-                self.img_ready[b] = torch.cuda.Event()
-                self.img_ready[b].record(self.s_in)
+                    ev_in.append(torch.cuda.Event())
+                    ev_in[c].record(self.s_in)
             with torch.cuda.stream(self.s_compute):
-                self.s_compute.wait_event(self.img_ready[b])
                 for c in range(self.n_cams):
+                    self.s_compute.wait_event(ev_in[c])
                     self.ex[c].extract_batch_device(self.img[b][c][:n], d.kps[c][f0:f1], d.desc[c][f0:f1], d.counts[c][f0:f1])
+                    ev_done.append(torch.cuda.Event())
+                    ev_done[c].record(self.s_compute)
                     if c == 0 and f1 == self.F and self.match and self.F > 1:
                         ev_match = self._launch_match(d)
-                self.img_free[b] = torch.cuda.Event()
-                self.img_free[b].record(self.s_compute)
+                self.img_free[b] = ev_done[-1]
             with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(self.img_free[b])
                 for c in range(self.n_cams):
+                    self.s_out.wait_event(ev_done[c])
                     h.kps[c][f0:f1].copy_(d.kps[c][f0:f1], non_blocking=True)
                     h.desc[c][f0:f1].copy_(d.desc[c][f0:f1], non_blocking=True)
                     h.counts[c][f0:f1].copy_(d.counts[c][f0:f1], non_blocking=True)
