@@ -66,7 +66,7 @@ __device__ __forceinline__ LevelView level_view(const OrbGeom* __restrict__ g, c
 #define PYR_ROWS 32
 #define PYR_PREFETCH 4
 
-__global__ void __launch_bounds__(128) k_pyr_resize(int level, int rows_per_tile, const OrbGeom* __restrict__ g,
+__global__ void __launch_bounds__(128, 8) k_pyr_resize(int level, int rows_per_tile, const OrbGeom* __restrict__ g,
                                                     OrbLevel0 l0, const OrbXTap* __restrict__ xtab,
                                                     const OrbYTap* __restrict__ ytab, uint8_t* __restrict__ pyr) {
   const OrbLevelGeom& D = g->lv[level];
