@@ -164,6 +164,9 @@ class ORBextractor:
             counts = torch.empty((F,), dtype=torch.int32, device=images.device)
         check_x(self._h, lib.orbx_extract_batch_device(self._h, images.data_ptr(), F, images.stride(0), images.stride(1),
                                                        kps.data_ptr(), desc.data_ptr(), counts.data_ptr(), cap))
+        # The kernels run asynchronously on the handle's stream and level 0 of the pyramid (pyramid_view,
+        # pyramid_level) IS this buffer: hold it until the next batch so a temporary cannot be recycled under them.
+        self._last_images = images
         return kps, desc, counts
 
     def sync(self) -> None:

@@ -121,3 +121,42 @@ def test_compute_stereo_matches_on_device(oracle_port, W, H, nf, F):
         assert (ur[f, nl[f]:] == -1).all()
         n_ok += int((want_u >= 0).sum())
     assert n_ok > 0.3 * nl.sum()
+
+
+def test_compute_stereo_matches_degenerate_pairs(oracle_port):
+    """Empty / unmatched inputs: a constant right image (no right keypoints), a constant left image (no left
+    keypoints), and a right image unrelated to the left one (few or no accepted matches: the median cut must not
+    trip over an empty list) — all -1 or equal to the oracle."""
+    import torch
+    from multi_orb_slam_b200.extractor import ORBextractor
+    from multi_orb_slam_b200.frame import FrameGlue
+    from multi_orb_slam_b200.synth import textured
+    O = oracle_port
+    W, H, nf = 320, 240, 300
+    a, b = textured(W, H, 71), textured(W, H, 72)
+    flat = np.full((H, W), 90, np.uint8)
+    lefts, rights = np.stack([a, flat, a, a]), np.stack([flat, a, b, a])
+    exl = ORBextractor(nf, 1.2, 8, 20, 7, image_size=(W, H), max_batch=4)
+    exr = ORBextractor(nf, 1.2, 8, 20, 7, image_size=(W, H), max_batch=4)
+    dev_l, dev_r = torch.from_numpy(lefts).cuda(), torch.from_numpy(rights).cuda()  # level 0 of the pyramid views: keep alive
+    kl, dl, nl = exl.extract_batch_device(dev_l)
+    kr, dr, nr = exr.extract_batch_device(dev_r)
+    glue = FrameGlue(400.0, 400.0, 160.0, 120.0, (0, 0, 0, 0, 0), mbf=40.0)
+    ur, z = glue.stereo_matches_batch_device(exl, exr, kl, dl, nl, kr, dr, nr)
+    torch.cuda.synchronize()
+    ur, z, nl, nr = ur.cpu().numpy(), z.cpu().numpy(), nl.cpu().numpy(), nr.cpu().numpy()
+    assert nr[0] == 0 and nl[1] == 0 and nl[0] > 100
+    assert (ur[0] == -1).all() and (z[0] == -1).all() and (ur[1] == -1).all()
+    mb = np.float32(40.0) / np.float32(400.0)
+    for f in (2, 3):
+        ref = []
+        for img in (lefts[f], rights[f]):
+            ex = O.extractor("port", nfeatures=nf)
+            k, d, _ = ex.extract(img)
+            ref.append((k, d, [ex.pyramid_level(l) for l in range(8)], ex.scale_tables()))
+        (k0, d0, p0, t0), (k1, d1, p1, _) = ref
+        want_u, want_z = O.compute_stereo_matches(k0, d0, k1, d1, p0, p1, t0[0], t0[1], 40.0, mb)
+        assert np.array_equal(ur[f, : nl[f]].view(np.uint32), want_u.view(np.uint32)), f"pair {f}"
+        assert np.array_equal(z[f, : nl[f]].view(np.uint32), want_z.view(np.uint32)), f"pair {f}"
+    # identical images: every SAD is 0, so the median threshold is 0 and the cut of :945-955 removes every match
+    assert (ur[3, : nl[3]] == -1).all()
