@@ -257,6 +257,70 @@ def widened_rows_leg(matcher, device, with_cpu):
         mb = float(np.float32(386.1448) / np.float32(718.856))
         row["cpu_ms"] = best_ms(lambda: [oracle_lib.compute_stereo_matches(*c, sf, isf, 386.1448, mb) for c in cpu_in], 2)
     out["compute_stereo_matches"] = row
+    # pose-based searches on a two-camera rig scene built from the CUDA extractor's own features
+    from multi_orb_slam_b200._lib import Camera
+    from multi_orb_slam_b200.matcher import Frame
+    from multi_orb_slam_b200.synth import RIG_CALIB, RIG_CAM, random_vocabulary, rig_scene
+    exs = {}
+
+    def gpu_extract(nfeat, image):
+        e = exs.setdefault(nfeat, ORBextractor(nfeat, 1.2, 8, 20, 7, image_size=(640, 480), max_batch=1, device=device))
+        return e(image)
+
+    s = rig_scene(gpu_extract, 3, 1500, (0, 0, 0.5))
+    sf_r = np.asarray(exs[1000].GetScaleFactors(), np.float32)
+    inv_sigma2 = np.asarray(exs[1000].GetInverseScaleSigmaSquares(), np.float32)
+    n_cur = s["n"]
+    fmp0, fobs0 = np.full(n_cur, -1, np.int32), np.zeros(n_cur, np.int32)
+
+    def spf_gpu():
+        fr = Frame(s["cur_k"], s["cur_d"], 640, 480, mvScaleFactors=sf_r, mvuRight=s["ur"], mvpMapPoints=fmp0.copy(),
+                   mvpMapPointsObserved=fobs0)
+        return matcher.SearchByProjectionFrame(fr, s["cur_cam"], Camera(*RIG_CAM), s["Tcw"], s["Tlw"], s["last_k"], s["last_cam"],
+                                               s["last_valid"], s["last_xyz"], s["last_desc"], s["last_obs"], RIG_CALIB, 15.0, False)
+
+    row = {"workload": f"SearchByProjection(CurrentFrame, LastFrame) of TrackWithMotionModel, two cameras, {n_cur} keypoints x "
+                       "1500 last-frame map points", "gpu_ms": best_ms(spf_gpu)}
+    if with_cpu:
+        row["cpu_ms"] = best_ms(lambda: oracle_lib.search_by_projection_frame(
+            s["cur_k"], s["cur_d"], s["ur"], s["cur_cam"], (0, 640, 0, 480), sf_r, RIG_CAM, s["Tcw"], s["Tlw"], s["last_k"],
+            s["last_cam"], s["last_valid"], s["last_xyz"], s["last_desc"], s["last_obs"], RIG_CALIB, 15.0, False, True, fmp0, fobs0), 3)
+    out["search_by_projection_frame"] = row
+    # Fuse(KeyFrame*, vpMapPoints, Calib, th): 2500 map points of the neighbours into one key frame
+    s2 = rig_scene(gpu_extract, 21, 2500, (0, 0, 0))
+    r2 = s2["rng"]
+    nmp = len(s2["last_xyz"])
+    xyz = s2["last_xyz"].astype(np.float64)
+    Rm, tv = s2["Tcw"][:3, :3].astype(np.float64), s2["Tcw"][:3, 3].astype(np.float64)
+    Ow0 = -Rm.T @ tv
+    Ow = np.stack([Ow0, Ow0 + Rm.T @ RIG_CALIB[3].astype(np.float64)])
+    dist = np.linalg.norm(xyz - Ow0, axis=1)
+    normal = (xyz - Ow0) / dist[:, None] + r2.normal(0, 0.3, (nmp, 3))
+    normal /= np.linalg.norm(normal, axis=1)[:, None]
+    max_d = (dist * r2.uniform(0.8, 4.0, nmp)).astype(np.float32)
+    kf_max, kf_min = (1.2 * max_d).astype(np.float32), (0.8 * max_d / 1.2 ** 7).astype(np.float32)
+    valid = (r2.random(nmp) < 0.9).astype(np.int32)
+    log_sf = float(np.log(np.float32(1.2)))
+    kf = Frame(s2["cur_k"], s2["cur_d"], 640, 480, mvuRight=s2["ur"], mvScaleFactors=sf_r)
+    row = {"workload": f"Fuse(KeyFrame, map points, Calib, th=3), two cameras, {s2['n']} keypoints x {nmp} map points",
+           "gpu_ms": best_ms(lambda: matcher.Fuse(kf, s2["cur_cam"], Camera(*RIG_CAM), log_sf, inv_sigma2, s2["Tcw"], Ow, RIG_CALIB, valid,
+                                                  xyz, normal, kf_max, kf_min, max_d, s2["last_desc"], 3.0))}
+    if with_cpu:
+        row["cpu_ms"] = best_ms(lambda: oracle_lib.fuse(s2["cur_k"], s2["cur_d"], s2["ur"], s2["cur_cam"], (0, 640, 0, 480), sf_r, inv_sigma2,
+                                                        log_sf, RIG_CAM, s2["Tcw"], Ow, RIG_CALIB, valid, xyz, normal, kf_max, kf_min, max_d,
+                                                        s2["last_desc"], 3.0), 3)
+    out["fuse"] = row
+    # Frame::ComputeBoW: DBoW2 transform of one frame's descriptors (k = 10, L = 5 synthetic tree, levelsup 4)
+    voc = random_vocabulary(10, 5, 55)
+    leaves = np.nonzero(voc["word_id"] >= 0)[0]
+    bdesc = voc["node_desc"][rng.choice(leaves, 2000)]
+    bdesc = np.packbits(np.unpackbits(bdesc, axis=1) ^ (rng.random((2000, 256)) < 0.05).astype(np.uint8), axis=1)
+    matcher.set_vocabulary(voc["child_start"], voc["child_ids"], voc["node_desc"], voc["word_id"], voc["node_weight"], voc["L"])
+    row = {"workload": "Frame::ComputeBoW (DBoW2 transform), 2000 descriptors, vocabulary k=10 L=5, levelsup 4",
+           "gpu_ms": best_ms(lambda: matcher.ComputeBoW(bdesc, 4))}
+    if with_cpu:
+        row["cpu_ms"] = best_ms(lambda: oracle_lib.bow_transform(voc, bdesc, 4), 3)
+    out["compute_bow"] = row
     for r in out.values():
         if "cpu_ms" in r:
             r["cpu_cores"] = 1

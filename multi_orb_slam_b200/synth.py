@@ -249,3 +249,56 @@ def random_vocabulary(k: int, L: int, seed: int, p_stop: float = 0.02, p_short: 
     weight[leaves] = np.where(rng.random(len(leaves)) < p_stop, 0.0, rng.uniform(0.5, 9.0, len(leaves)))
     return dict(child_start=child_start, child_ids=child_ids, node_desc=np.stack(desc), word_id=word_id, node_weight=weight,
                 L=L, depth=np.array(depth))
+
+
+# ---- two-camera rig scene for the pose-based searches (SearchByProjection overloads, Fuse, SearchBySim3) ----
+RIG_CALIB = np.array([[0.01001086, 0.01371197, 0.99975906], [0.02114039, 0.99964902, -0.01393279],
+                  [-0.99963218, 0.02128624, 0.00971428], [0.1609449, 0.00377988, -0.07087293]], dtype=np.float32)  # OtherFiles/calibration.txt
+RIG_CAM = (517.3, 516.5, 318.6, 255.3, 0.08, 40.0)  # fx fy cx cy mb mbf
+
+
+def rig_rotation(rx, ry, rz):
+    cx, sx, cy, sy, cz, sz = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
+    return (np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @
+            np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]))
+
+
+def rig_scene(extract, seed, n_last, tlast_offset):
+    """Two-camera current frame + last-frame map points that project near current keypoints.
+    extract(nfeatures, image) -> (keypoints[KP_DTYPE], descriptors) supplies the features (the oracle in the
+    tests, the CUDA extractor in bench.py)."""
+    rng = np.random.default_rng(seed)
+    k0, d0 = extract(1000, textured(640, 480, seed))
+    k1, d1 = extract(500, textured(640, 480, seed + 100))
+    cur_k, cur_d = np.concatenate([k0, k1]), np.concatenate([d0, d1])
+    cur_cam = np.concatenate([np.zeros(len(k0), np.int32), np.ones(len(k1), np.int32)])
+    n = len(cur_k)
+    fx, fy, cx, cy, mb, mbf = RIG_CAM
+    Tcw = np.eye(4)
+    Tcw[:3, :3] = rig_rotation(0.02, -0.03, 0.01)
+    Tcw[:3, 3] = [0.05, -0.02, 0.1]
+    Tlw = np.eye(4)
+    Tlw[:3, :3] = rig_rotation(0.0, 0.0, 0.0)
+    Tlw[:3, 3] = np.array([0.05, -0.02, 0.1]) + np.array(tlast_offset)
+    R12, t12 = RIG_CALIB[:3].astype(np.float64), RIG_CALIB[3].astype(np.float64)
+    R21, t21 = R12.T, -R12.T @ t12
+    src = rng.integers(0, n, n_last)
+    z = rng.uniform(1.0, 8.0, n_last)
+    u = cur_k["x"][src] + rng.normal(0, 2.5, n_last)
+    v = cur_k["y"][src] + rng.normal(0, 2.5, n_last)
+    Xc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], axis=1)  # in the source keypoint's camera frame
+    is1 = cur_cam[src] == 1
+    Xc0 = np.where(is1[:, None], (Xc - t21) @ R21, Xc)               # back to the rig (camera 0) frame: R21^T (x - t21)
+    Xw = (Xc0 - Tcw[:3, 3]) @ Tcw[:3, :3]                            # R^T (x - t)
+    Xw[rng.random(n_last) < 0.05] *= -1                               # some behind the camera
+    bits = np.unpackbits(cur_d[src], axis=1)
+    flips = rng.integers(0, 70, n_last)
+    bits ^= (np.argsort(np.argsort(rng.random((n_last, 256)), axis=1), axis=1) < flips[:, None]).astype(np.uint8)
+    last_k = np.zeros(n_last, KP_DTYPE)
+    last_k["octave"] = np.clip(cur_k["octave"][src] + rng.integers(-1, 2, n_last), 0, 7)
+    last_k["angle"] = (cur_k["angle"][src] + rng.normal(0, 15, n_last)) % 360
+    ur = np.where(rng.random(n) < 0.7, cur_k["x"] - mbf / rng.uniform(1, 8, n), -1).astype(np.float32)
+    return dict(cur_k=cur_k, cur_d=cur_d, cur_cam=cur_cam, ur=ur, Tcw=Tcw.astype(np.float32), Tlw=Tlw.astype(np.float32),
+                last_k=last_k, last_cam=cur_cam[src].copy(), last_valid=(rng.random(n_last) < 0.9).astype(np.int32),
+                last_xyz=Xw.astype(np.float32), last_desc=np.packbits(bits, axis=1),
+                last_obs=(rng.random(n_last) < 0.85).astype(np.int32), rng=rng, n=n)

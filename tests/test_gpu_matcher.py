@@ -199,56 +199,18 @@ def test_bruteforce_batch_vs_oracle(O):
 
 
 # ---- pose-based SearchByProjection overloads -------------------------------------------------
-CALIB = np.array([[0.01001086, 0.01371197, 0.99975906], [0.02114039, 0.99964902, -0.01393279],
-                  [-0.99963218, 0.02128624, 0.00971428], [0.1609449, 0.00377988, -0.07087293]], dtype=np.float32)  # OtherFiles/calibration.txt
-CAM = (517.3, 516.5, 318.6, 255.3, 0.08, 40.0)  # fx fy cx cy mb mbf
-
-
-def _rot(rx, ry, rz):
-    cx, sx, cy, sy, cz, sz = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
-    return (np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @
-            np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]))
+from multi_orb_slam_b200.synth import RIG_CALIB as CALIB, RIG_CAM as CAM, rig_rotation as _rot, rig_scene  # noqa: E402
 
 
 def _rig_scene(O, seed, n_last, tlast_offset):
-    """Two-camera current frame + last-frame map points that project near current keypoints."""
-    rng = np.random.default_rng(seed)
-    port0, port1 = O.extractor("port", nfeatures=1000), O.extractor("port", nfeatures=500)
-    k0, d0, _ = port0.extract(textured(640, 480, seed))
-    k1, d1, _ = port1.extract(textured(640, 480, seed + 100))
-    cur_k, cur_d = np.concatenate([k0, k1]), np.concatenate([d0, d1])
-    cur_cam = np.concatenate([np.zeros(len(k0), np.int32), np.ones(len(k1), np.int32)])
-    n = len(cur_k)
-    fx, fy, cx, cy, mb, mbf = CAM
-    Tcw = np.eye(4)
-    Tcw[:3, :3] = _rot(0.02, -0.03, 0.01)
-    Tcw[:3, 3] = [0.05, -0.02, 0.1]
-    Tlw = np.eye(4)
-    Tlw[:3, :3] = _rot(0.0, 0.0, 0.0)
-    Tlw[:3, 3] = np.array([0.05, -0.02, 0.1]) + np.array(tlast_offset)
-    R12, t12 = CALIB[:3].astype(np.float64), CALIB[3].astype(np.float64)
-    R21, t21 = R12.T, -R12.T @ t12
-    src = rng.integers(0, n, n_last)
-    z = rng.uniform(1.0, 8.0, n_last)
-    u = cur_k["x"][src] + rng.normal(0, 2.5, n_last)
-    v = cur_k["y"][src] + rng.normal(0, 2.5, n_last)
-    Xc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], axis=1)  # in the source keypoint's camera frame
-    is1 = cur_cam[src] == 1
-    Xc0 = np.where(is1[:, None], (Xc - t21) @ R21, Xc)               # back to the rig (camera 0) frame: R21^T (x - t21)
-    Xw = (Xc0 - Tcw[:3, 3]) @ Tcw[:3, :3]                            # R^T (x - t)
-    Xw[rng.random(n_last) < 0.05] *= -1                               # some behind the camera
-    bits = np.unpackbits(cur_d[src], axis=1)
-    flips = rng.integers(0, 70, n_last)
-    bits ^= (np.argsort(np.argsort(rng.random((n_last, 256)), axis=1), axis=1) < flips[:, None]).astype(np.uint8)
-    from multi_orb_slam_b200._lib import KP_DTYPE
-    last_k = np.zeros(n_last, KP_DTYPE)
-    last_k["octave"] = np.clip(cur_k["octave"][src] + rng.integers(-1, 2, n_last), 0, 7)
-    last_k["angle"] = (cur_k["angle"][src] + rng.normal(0, 15, n_last)) % 360
-    ur = np.where(rng.random(n) < 0.7, cur_k["x"] - mbf / rng.uniform(1, 8, n), -1).astype(np.float32)
-    return dict(cur_k=cur_k, cur_d=cur_d, cur_cam=cur_cam, ur=ur, Tcw=Tcw.astype(np.float32), Tlw=Tlw.astype(np.float32),
-                last_k=last_k, last_cam=cur_cam[src].copy(), last_valid=(rng.random(n_last) < 0.9).astype(np.int32),
-                last_xyz=Xw.astype(np.float32), last_desc=np.packbits(bits, axis=1),
-                last_obs=(rng.random(n_last) < 0.85).astype(np.int32), rng=rng, n=n)
+    """Two-camera current frame + last-frame map points (synth.rig_scene) on the ORACLE's features."""
+    ports = {}
+
+    def extract(nfeatures, image):
+        port = ports.setdefault(nfeatures, O.extractor("port", nfeatures=nfeatures))
+        return port.extract(image)[:2]
+
+    return rig_scene(extract, seed, n_last, tlast_offset)
 
 
 @pytest.mark.parametrize("offset,th,mono,check_ori", [((0, 0, 0), 15.0, False, True), ((0, 0, 0.5), 15.0, False, True),
