@@ -17,7 +17,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 @pytest.fixture(scope="module")
 def host_lib():
     so = os.path.join(HERE, "native", "liboctree_host.so")
-    subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-o", so, os.path.join(HERE, "native", "octree_host.cc")], check=True)
+    tmp = f"{so}.{os.getpid()}.tmp"  # built aside and renamed: pytest-xdist workers may race here
+    subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-o", tmp, os.path.join(HERE, "native", "octree_host.cc")], check=True)
+    os.replace(tmp, so)
     return C.CDLL(so)
 
 
