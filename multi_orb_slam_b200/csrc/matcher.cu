@@ -1224,19 +1224,55 @@ __global__ void __launch_bounds__(1024) k_scan_exclusive(const int* __restrict__
 
 // Phase B: ordered resolve by one warp, map points ascending: occupancy skip (:107-109),
 // best/second with levels (:122-135), TH_HIGH + same-level ratio (:138-141), assignment (:143).
+constexpr int RESOLVE_WIN = 2048;  // candidate entries per shared-memory window of the ordered resolves
+
+// One dependent chain over the map points, so a step finds its inputs on chip: counts, offsets and
+// observation flags of 32 points are fetched by the 32 lanes at once and broadcast by shuffle, the
+// candidate rows (contiguous in `rows`) stream through a shared-memory window, and the occupancy
+// bytes live in shared memory when they fit.
 __global__ void __launch_bounds__(32) k_proj_resolve(const int* __restrict__ row_cnt, const int* __restrict__ row_off,
-                                                     const uint32_t* __restrict__ rows, const int32_t* __restrict__ mp_obs,
-                                                     int nmp, int n, float nnratio, int32_t* __restrict__ frame_mp,
-                                                     const int32_t* __restrict__ frame_mp_obs, uint8_t* __restrict__ held,
+                                                     const uint32_t* __restrict__ rows, int total_rows,
+                                                     const int32_t* __restrict__ mp_obs, int nmp, int n, float nnratio,
+                                                     int32_t* __restrict__ frame_mp, const int32_t* __restrict__ frame_mp_obs,
+                                                     uint8_t* __restrict__ held_global, int held_in_smem,
                                                      int* __restrict__ nmatches_out) {
+  extern __shared__ __align__(16) uint8_t s_held[];
+  __shared__ uint32_t s_rows[RESOLVE_WIN];
   const int lane = threadIdx.x;
+  uint8_t* held = held_in_smem ? s_held : held_global;
   for (int i = lane; i < n; i += 32) held[i] = (frame_mp[i] >= 0 && frame_mp_obs && frame_mp_obs[i] > 0) ? 1 : 0;
   __syncwarp();
   int nmatches = 0;
+  int win_base = 0, win_end = 0;  // [win_base, win_end) of `rows` is resident in s_rows
+  int l_cnt = 0, l_off = 0, l_obs = 1;
   for (int i = 0; i < nmp; ++i) {
-    const int cnt = row_cnt[i];
+    if ((i & 31) == 0) {
+      const int ii = i + lane;
+      if (ii < nmp) {
+        l_cnt = row_cnt[ii];
+        l_off = row_off[ii];
+        l_obs = mp_obs ? (mp_obs[ii] > 0 ? 1 : 0) : 1;
+      }
+    }
+    const int cnt = __shfl_sync(0xffffffffu, l_cnt, i & 31);
     if (cnt == 0) continue;
-    const uint32_t* row = rows + row_off[i];
+    const int off = __shfl_sync(0xffffffffu, l_off, i & 31);
+    const int obs = __shfl_sync(0xffffffffu, l_obs, i & 31);
+    const uint32_t* row;
+    if (cnt > RESOLVE_WIN) {
+      row = rows + off;  // longer than the window: read in place
+    } else {
+      if (off < win_base || off + cnt > win_end) {
+        __syncwarp();
+        win_base = off;
+        win_end = min(off + RESOLVE_WIN, total_rows);
+        const int len = win_end - win_base;
+#pragma unroll 8
+        for (int c = lane; c < len; c += 32) s_rows[c] = rows[win_base + c];
+        __syncwarp();
+      }
+      row = s_rows + (off - win_base);
+    }
     // key = dist << 16 | position; the level rides along in a second register
     uint32_t best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
     for (int c = lane; c < cnt; c += 32) {
@@ -1260,7 +1296,7 @@ __global__ void __launch_bounds__(32) k_proj_resolve(const int* __restrict__ row
       if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) continue;
       if (lane == 0) {
         frame_mp[bestIdx] = i;
-        held[bestIdx] = mp_obs ? (mp_obs[i] > 0 ? 1 : 0) : 1;
+        held[bestIdx] = (uint8_t)obs;
       }
       nmatches++;
       __syncwarp();
@@ -1386,71 +1422,120 @@ __global__ void __launch_bounds__(256) k_fuse_match(const orbx_keypoint* __restr
 // Ordered resolve, best match only (:3558-3637, :3886-3934): queries ascending; candidates that
 // already hold a point are skipped (any_point_blocks: a15 blocks on any held point, a14 only on
 // points with Observations()>0); accept best <= th_dist; rotation histogram + three maxima.
+// The ordered resolve is one dependent chain over the queries, so everything a step needs sits on chip
+// before the step starts: the query fields of 32 queries are fetched by the 32 lanes at once and
+// broadcast by shuffle, the candidate rows (contiguous in `rows`, exclusive-scan offsets) stream
+// through a shared-memory window, the occupancy bytes live in shared memory when they fit, and the
+// rotation bins (which need the matched keypoint's angle from HBM) are computed after the walk.
 __global__ void __launch_bounds__(32) k_query_resolve_best(const ProjQuery* __restrict__ q, const int* __restrict__ row_cnt,
                                                            const int* __restrict__ row_off, const uint32_t* __restrict__ rows,
-                                                           int nq, int n, const orbx_keypoint* __restrict__ k, int th_dist,
-                                                           int check_ori, int any_point_blocks, int32_t* __restrict__ frame_mp,
-                                                           const int32_t* __restrict__ frame_mp_obs, uint8_t* __restrict__ held,
+                                                           int total_rows, int nq, int n, const orbx_keypoint* __restrict__ k,
+                                                           int th_dist, int check_ori, int any_point_blocks,
+                                                           int32_t* __restrict__ frame_mp, const int32_t* __restrict__ frame_mp_obs,
+                                                           uint8_t* __restrict__ held_global, int held_in_smem,
                                                            int32_t* __restrict__ acc_idx, int32_t* __restrict__ acc_bin,
                                                            int* __restrict__ nmatches_out) {
+  extern __shared__ __align__(16) uint8_t s_held[];
+  __shared__ uint32_t s_rows[RESOLVE_WIN];
   __shared__ int s_hist[HISTO_LENGTH];
   const int lane = threadIdx.x;
+  uint8_t* held = held_in_smem ? s_held : held_global;
   for (int i = lane; i < n; i += 32)
     held[i] = frame_mp[i] >= 0 && (any_point_blocks || (frame_mp_obs && frame_mp_obs[i] > 0)) ? 1 : 0;
   if (lane < HISTO_LENGTH) s_hist[lane] = 0;
   __syncwarp();
   int nmatches = 0, nacc = 0;
+  int win_base = 0, win_end = 0;  // [win_base, win_end) of `rows` is resident in s_rows
   // Consecutive queries with the same source point form one group (the Sim3 overload projects a
   // point into both cameras and keeps the best over cameras, :629-735); elsewhere groups are single.
-  for (int i = 0; i < nq;) {
-    const int src = q[i].src;
-    uint32_t gbest = 0xFFFFFFFFu;  // dist << 16 | (anything): only the distance decides across rows (strict <)
-    int gidx = -1, glast = i;
-    for (; glast < nq && q[glast].src == src; ++glast) {
-      const int cnt = row_cnt[glast];
-      if (cnt == 0) continue;
-      const uint32_t* row = rows + row_off[glast];
-      uint32_t best = 0xFFFFFFFFu;
-      int my_idx = -1;
-      for (int c = lane; c < cnt; c += 32) {
-        const uint32_t e = row[c];
-        if (held[e & 0xFFFFu]) continue;
-        const uint32_t key = (e >> 16) << 16 | (uint32_t)c;  // dist, then traversal position (strict <)
-        if (key < best) { best = key; my_idx = (int)(e & 0xFFFFu); }
-      }
-      const uint32_t mine = best;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-      if (best == 0xFFFFFFFFu) continue;
-      const unsigned owner = __ballot_sync(0xffffffffu, mine == best);
-      const int row_idx = __shfl_sync(0xffffffffu, my_idx, __ffs(owner) - 1);
-      if ((best >> 16) < (gbest >> 16) || gbest == 0xFFFFFFFFu) { gbest = best; gidx = row_idx; }
-    }
-    const int qi = i;
-    i = glast;
-    if (gbest == 0xFFFFFFFFu) continue;
-    const int bestDist = (int)(gbest >> 16);
-    if (bestDist > th_dist) continue;
-    const int bestIdx = gidx;
-    if (lane == 0) {
-      const ProjQuery p = q[qi];
-      frame_mp[bestIdx] = p.src;
-      held[bestIdx] = any_point_blocks ? 1 : (p.obs ? 1 : 0);
-      if (check_ori) {
-        float rot = __fsub_rn(p.angle, k[bestIdx].angle);
-        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-        int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
-        if (bin == HISTO_LENGTH) bin = 0;
-        acc_idx[nacc] = bestIdx;
-        acc_bin[nacc] = bin;
-        s_hist[bin]++;
+  int gsrc = 0, gobs = 0, gidx = -1;
+  float gangle = 0.0f;
+  uint32_t gbest = 0xFFFFFFFFu;  // dist << 16 | (anything): only the distance decides across rows (strict <)
+  bool open = false;
+  int l_src = 0, l_obs = 0, l_cnt = 0, l_off = 0;
+  float l_angle = 0.0f;
+  for (int j = 0; j <= nq; ++j) {
+    if ((j & 31) == 0 && j < nq) {
+      const int jj = j + lane;
+      if (jj < nq) {
+        l_src = q[jj].src; l_obs = q[jj].obs; l_angle = q[jj].angle;
+        l_cnt = row_cnt[jj]; l_off = row_off[jj];
       }
     }
-    ++nacc;
-    ++nmatches;
-    __syncwarp();
+    int src = 0, cnt = 0, off = 0;
+    if (j < nq) {
+      src = __shfl_sync(0xffffffffu, l_src, j & 31);
+      cnt = __shfl_sync(0xffffffffu, l_cnt, j & 31);
+      off = __shfl_sync(0xffffffffu, l_off, j & 31);
+    }
+    if (open && (j == nq || src != gsrc)) {
+      // the group is complete: accept its best (TH_HIGH / ORBdist / TH_LOW gate)
+      open = false;
+      if (gbest != 0xFFFFFFFFu && (int)(gbest >> 16) <= th_dist) {
+        if (lane == 0) {
+          frame_mp[gidx] = gsrc;
+          held[gidx] = any_point_blocks ? 1 : (gobs ? 1 : 0);
+          if (check_ori) {
+            acc_idx[nacc] = gidx;
+            acc_bin[nacc] = __float_as_int(gangle);  // the source angle; turned into the bin below
+          }
+        }
+        ++nacc;
+        ++nmatches;
+        __syncwarp();
+      }
+    }
+    if (j == nq) break;
+    if (!open) {
+      open = true;
+      gsrc = src;
+      gobs = __shfl_sync(0xffffffffu, l_obs, j & 31);
+      gangle = __shfl_sync(0xffffffffu, l_angle, j & 31);
+      gbest = 0xFFFFFFFFu;
+      gidx = -1;
+    }
+    if (cnt == 0) continue;
+    const uint32_t* row;
+    if (cnt > RESOLVE_WIN) {
+      row = rows + off;  // longer than the window: read in place
+    } else {
+      if (off < win_base || off + cnt > win_end) {
+        __syncwarp();
+        win_base = off;
+        win_end = min(off + RESOLVE_WIN, total_rows);
+        const int len = win_end - win_base;
+#pragma unroll 8
+        for (int c = lane; c < len; c += 32) s_rows[c] = rows[win_base + c];
+        __syncwarp();
+      }
+      row = s_rows + (off - win_base);
+    }
+    uint32_t best = 0xFFFFFFFFu;
+    int my_idx = -1;
+    for (int c = lane; c < cnt; c += 32) {
+      const uint32_t e = row[c];
+      if (held[e & 0xFFFFu]) continue;
+      const uint32_t key = (e >> 16) << 16 | (uint32_t)c;  // dist, then traversal position (strict <)
+      if (key < best) { best = key; my_idx = (int)(e & 0xFFFFu); }
+    }
+    const uint32_t mine = best;
+    best = __reduce_min_sync(0xffffffffu, best);
+    if (best == 0xFFFFFFFFu) continue;
+    const unsigned owner = __ballot_sync(0xffffffffu, mine == best);
+    const int row_idx = __shfl_sync(0xffffffffu, my_idx, __ffs(owner) - 1);
+    if ((best >> 16) < (gbest >> 16) || gbest == 0xFFFFFFFFu) { gbest = best; gidx = row_idx; }
   }
   if (check_ori) {
+    __syncwarp();
+    // rotation bins of the accepted matches (:3604-3615), lanes over the matches
+    for (int e = lane; e < nacc; e += 32) {
+      float rot = __fsub_rn(__int_as_float(acc_bin[e]), k[acc_idx[e]].angle);
+      if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+      int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
+      if (bin == HISTO_LENGTH) bin = 0;
+      acc_bin[e] = bin;
+      atomicAdd(&s_hist[bin], 1);
+    }
     __syncwarp();
     int max1 = 0, max2 = 0, max3 = 0, i1_ = -1, i2_ = -1, i3_ = -1;  // every lane computes the same maxima
     for (int i = 0; i < HISTO_LENGTH; ++i) {
@@ -1771,8 +1856,10 @@ int orbm_search_by_projection_points_host(orbm_matcher* m, const orbx_keypoint* 
   if (!rows) return ORBX_E_CUDA;
   k_proj_candidates<<<blocks, 256, 0, st>>>(dk, dd, u_right ? dur : nullptr, bounds, gstart, gitems, dsf, dmp, dmd, nmp, th, 0,
                                             drow_cnt, drow_off, rows);
-  k_proj_resolve<<<1, 32, 0, st>>>(drow_cnt, drow_off, rows, mp_obs ? dmobs : nullptr, nmp, n, nnratio, dfmp,
-                                   frame_mp_obs ? dfobs : nullptr, dheld, misc + 1);
+  const int held_in_smem = n <= 32768;  // occupancy bytes on chip when they fit beside the 8 KB row window
+  k_proj_resolve<<<1, 32, held_in_smem ? (size_t)((n + 15) & ~15) : 0, st>>>(
+      drow_cnt, drow_off, rows, total, mp_obs ? dmobs : nullptr, nmp, n, nnratio, dfmp,
+      frame_mp_obs ? dfobs : nullptr, dheld, held_in_smem, misc + 1);
   m->launches += 2;
   cudaMemcpyAsync(frame_mp, dfmp, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st);
   cudaMemcpyAsync(nmatches, misc + 1, sizeof(int), cudaMemcpyDeviceToHost, st);
@@ -2317,8 +2404,10 @@ int run_projected(orbm_matcher* m, const orbx_keypoint* k, const uint8_t* desc, 
   if (!rows) return ORBX_E_CUDA;
   k_query_candidates<<<blocks, 256, 0, st>>>(dk, dd, u_right ? dur : nullptr, bounds, gstart, gitems, n, dq, dsd, nq, 0,
                                              drow_cnt, drow_off, rows);
-  k_query_resolve_best<<<1, 32, 0, st>>>(dq, drow_cnt, drow_off, rows, nq, n, dk, th_dist, check_ori, any_point_blocks, dfmp,
-                                         frame_mp_obs ? dfobs : nullptr, dheld, dacc_idx, dacc_bin, misc + 1);
+  const int held_in_smem = n <= 32768;  // occupancy bytes on chip when they fit beside the 8 KB row window
+  k_query_resolve_best<<<1, 32, held_in_smem ? (size_t)((n + 15) & ~15) : 0, st>>>(
+      dq, drow_cnt, drow_off, rows, total, nq, n, dk, th_dist, check_ori, any_point_blocks, dfmp,
+      frame_mp_obs ? dfobs : nullptr, dheld, held_in_smem, dacc_idx, dacc_bin, misc + 1);
   m->launches += 2;
   cudaMemcpyAsync(frame_mp, dfmp, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st);
   cudaMemcpyAsync(nmatches, misc + 1, sizeof(int), cudaMemcpyDeviceToHost, st);
