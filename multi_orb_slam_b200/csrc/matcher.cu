@@ -956,7 +956,7 @@ __global__ void __launch_bounds__(256) k_bow_candidates(const BowQuery* __restri
   }
 }
 
-#define BOW_SMEM_ROWS 12288  // candidate entries staged in shared memory (48 KB)
+#define BOW_SMEM_ROWS 55000  // candidate entries staged in shared memory (215 KB of the SM's 227 KB; one CTA per pair)
 
 // One CTA per pair of the batch.  pair_info[p] = {first query, query count, first row, row count, o1, o2, n2, 0}.
 __global__ void __launch_bounds__(256) k_bow_resolve(const BowQuery* __restrict__ q_all, const int32_t* __restrict__ pair_info,
@@ -985,13 +985,23 @@ __global__ void __launch_bounds__(256) k_bow_resolve(const BowQuery* __restrict_
   __syncthreads();
   const uint32_t* R = staged ? s_rows : rows_all + r0;  // indexed by row offsets relative to the pair
   if (tid < 32) {
+    // The walk is one dependent chain, so it touches no HBM on its critical path: offsets and counts
+    // of 32 queries are fetched by the 32 lanes at once and broadcast by shuffle, and the rotation
+    // bins (which need both keypoint angles) are taken afterwards by the whole CTA; during the walk
+    // q_bin[j] only records the matched side-2 index.
     int nmatches = 0;
+    int l_cnt = 0, l_off = 0;
     for (int j = 0; j < nq; ++j) {
-      const BowQuery bq = q[j];
+      if ((j & 31) == 0) {
+        const int jj = j + lane;
+        if (jj < nq) { l_cnt = q[jj].cnt; l_off = q[jj].off; }
+      }
+      const int cnt = __shfl_sync(0xffffffffu, l_cnt, j & 31);
+      const int off = __shfl_sync(0xffffffffu, l_off, j & 31) - r0;
       // key = dist << 16 | position in the node's vector: the strict-< scan order (:311-321)
       uint32_t best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
-      for (int c = lane; c < bq.cnt; c += 32) {
-        const uint32_t e = R[bq.off - r0 + c];
+      for (int c = lane; c < cnt; c += 32) {
+        const uint32_t e = R[off + c];
         const uint32_t idx2 = e & 0xFFFFu;
         if ((e >> 16) == 0xFFFFu || (s_taken[idx2 >> 5] >> (idx2 & 31) & 1u)) continue;
         const uint32_t key = (e & 0xFFFF0000u) | (uint32_t)c;
@@ -999,35 +1009,41 @@ __global__ void __launch_bounds__(256) k_bow_resolve(const BowQuery* __restrict_
         best = min(best, key);
       }
       warp_top2(best, second);
-      int bin = -1;
+      int matched = -1;
       if (best != 0xFFFFFFFFu) {
         const int bestDist1 = (int)(best >> 16);
         const int bestDist2 = second == 0xFFFFFFFFu ? 256 : (int)(second >> 16);
         if (bestDist1 <= max_dist && (float)bestDist1 < __fmul_rn(nnratio, (float)bestDist2)) {
-          const int idx2 = (int)(R[bq.off - r0 + (int)(best & 0xFFFFu)] & 0xFFFFu);
-          if (lane == 0) {
-            s_taken[idx2 >> 5] |= 1u << (idx2 & 31);
-            matches12[bq.idx1] = idx2;
-            bin = HISTO_LENGTH;  // matched, no orientation bin
-            if (check_ori) {
-              float rot = __fsub_rn(angle1[bq.idx1], angle2[o2 + idx2]);
-              if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-              bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
-              if (bin == HISTO_LENGTH) bin = 0;
-              s_hist[bin]++;
-            }
-          }
+          const int idx2 = (int)(R[off + (int)(best & 0xFFFFu)] & 0xFFFFu);
+          if (lane == 0) s_taken[idx2 >> 5] |= 1u << (idx2 & 31);
+          matched = idx2;
           nmatches++;
           __syncwarp();
         }
       }
-      if (lane == 0) q_bin[j] = bin;
+      if (lane == 0) q_bin[j] = matched;
     }
-    if (lane == 0) {
-      s_nmatch = nmatches;
-      if (check_ori) three_maxima_keep(s_hist, s_keep);
-    }
+    if (lane == 0) s_nmatch = nmatches;
   }
+  __syncthreads();
+  // matches and their rotation bins (:330-341), a thread per query
+  for (int j = tid; j < nq; j += 256) {
+    const int idx2 = q_bin[j];
+    if (idx2 < 0) continue;
+    const int idx1 = q[j].idx1;
+    matches12[idx1] = idx2;
+    int bin = HISTO_LENGTH;  // matched, no orientation bin
+    if (check_ori) {
+      float rot = __fsub_rn(angle1[idx1], angle2[o2 + idx2]);
+      if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+      bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
+      if (bin == HISTO_LENGTH) bin = 0;
+      atomicAdd(&s_hist[bin], 1);
+    }
+    q_bin[j] = bin;
+  }
+  __syncthreads();
+  if (tid == 0 && check_ori) three_maxima_keep(s_hist, s_keep);
   __syncthreads();
   // removal pass (:365-383) and the side-2 view of the matches
   const int o1 = info[4];
@@ -1972,7 +1988,7 @@ int orbm_search_by_bow_batch_host(orbm_matcher* m, orbm_bow_pair* pairs, int n_p
   cudaMemsetAsync(dnm, 0, sizeof(int) * n_pairs, st);
   const size_t smem = sizeof(uint32_t) * ((size_t)(max_n2 / 32 + 1) + max_rows);
   if (smem > 48 * 1024 &&
-      !m->check(cudaFuncSetAttribute(k_bow_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "smem opt-in"))
+      !m->check(cudaFuncSetAttribute(k_bow_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in"))
     return ORBX_E_CUDA;
   k_bow_candidates<<<(nq + 7) / 8, 256, 0, st>>>(dq, nq, dd1, dd2, dvalid2, ditems2, rows);
   k_bow_resolve<<<n_pairs, 256, smem, st>>>(dq, dinfo, rows, da1, da2, nnratio, check_ori, max_dist, dm12, dm21, dbin, dnm);
@@ -2348,6 +2364,155 @@ inline void mat3t_mul_vec(const float* R, int rs, const float* x, float alpha, f
   }
 }
 
+// Speculative form of the ordered best-only resolve, for query lists without multi-row groups
+// (every overload except the two-camera Sim3 one).  A query's answer is the least key among its
+// candidates that hold no point, and occupancy only ever grows during the walk, so the least key
+// under the INITIAL occupancy (k_query_static_best, a warp per query, fully parallel) is the answer
+// unless an earlier query of the walk has taken exactly that keypoint.  The walk then handles 32
+// queries per step: lanes whose keypoint is free and not claimed by an earlier lane of the step
+// commit together; the first lane in conflict rescans its row under the current occupancy, and
+// the lanes after it are re-examined.  Commit order, overwrites of keypoints that stay free
+// (Observations()==0, :3565-3567) and the accepted list are those of the sequential loop.
+__global__ void __launch_bounds__(256) k_query_static_best(const int* __restrict__ row_cnt, const int* __restrict__ row_off,
+                                                           const uint32_t* __restrict__ rows, int nq, int any_point_blocks,
+                                                           const int32_t* __restrict__ frame_mp,
+                                                           const int32_t* __restrict__ frame_mp_obs,
+                                                           uint32_t* __restrict__ sbest) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= nq) return;
+  const int cnt = row_cnt[j];
+  const uint32_t* row = rows + row_off[j];
+  uint32_t best = 0xFFFFFFFFu;
+  for (int c = lane; c < cnt; c += 32) {
+    const uint32_t e = row[c];
+    const int i = (int)(e & 0xFFFFu);
+    if (frame_mp[i] >= 0 && (any_point_blocks || (frame_mp_obs && frame_mp_obs[i] > 0))) continue;
+    best = min(best, (e >> 16) << 16 | (uint32_t)c);
+  }
+  best = __reduce_min_sync(0xffffffffu, best);
+  if (lane == 0) sbest[j] = best;
+}
+
+__global__ void __launch_bounds__(32) k_query_resolve_spec(const ProjQuery* __restrict__ q, const int* __restrict__ row_cnt,
+                                                           const int* __restrict__ row_off, const uint32_t* __restrict__ rows,
+                                                           const uint32_t* __restrict__ sbest, int nq, int n,
+                                                           const orbx_keypoint* __restrict__ k, int th_dist, int check_ori,
+                                                           int any_point_blocks, int32_t* __restrict__ frame_mp,
+                                                           const int32_t* __restrict__ frame_mp_obs,
+                                                           uint8_t* __restrict__ held_global, int held_in_smem,
+                                                           int32_t* __restrict__ acc_idx, int32_t* __restrict__ acc_bin,
+                                                           int* __restrict__ nmatches_out) {
+  extern __shared__ __align__(16) uint8_t s_held[];
+  __shared__ int s_hist[HISTO_LENGTH];
+  const int lane = threadIdx.x;
+  const unsigned lt = (1u << lane) - 1u;
+  uint8_t* held = held_in_smem ? s_held : held_global;
+  for (int i = lane; i < n; i += 32)
+    held[i] = frame_mp[i] >= 0 && (any_point_blocks || (frame_mp_obs && frame_mp_obs[i] > 0)) ? 1 : 0;
+  if (lane < HISTO_LENGTH) s_hist[lane] = 0;
+  __syncwarp();
+  int nacc = 0;
+  for (int b0 = 0; b0 < nq; b0 += 32) {
+    const int j = b0 + lane;
+    uint32_t key = 0xFFFFFFFFu;
+    int src = 0, obs = 0, cnt = 0, off = 0, idx = -1;
+    float angle = 0.0f;
+    if (j < nq) {
+      key = sbest[j];
+      src = q[j].src; obs = q[j].obs; angle = q[j].angle;
+      cnt = row_cnt[j]; off = row_off[j];
+    }
+    // a static best above the gate can only get worse: such a query never commits
+    bool pend = key != 0xFFFFFFFFu && (int)(key >> 16) <= th_dist;
+    if (pend) idx = (int)(rows[off + (int)(key & 0xFFFFu)] & 0xFFFFu);
+    const uint8_t hval = any_point_blocks ? 1 : (obs ? 1 : 0);
+    unsigned pending = __ballot_sync(0xffffffffu, pend);
+    while (pending) {
+      const unsigned peers = __match_any_sync(0xffffffffu, pend ? idx : -1 - lane);
+      const bool conflict = pend && (held[idx] || (peers & lt) != 0);
+      const unsigned cm = __ballot_sync(0xffffffffu, conflict);
+      const int first = cm ? __ffs(cm) - 1 : 32;
+      const bool commit = pend && lane < first;
+      const unsigned commits = __ballot_sync(0xffffffffu, commit);
+      if (commit) {
+        frame_mp[idx] = src;
+        held[idx] = hval;
+        if (check_ori) {
+          const int e = nacc + __popc(commits & lt);
+          acc_idx[e] = idx;
+          acc_bin[e] = __float_as_int(angle);  // the source angle; turned into the bin below
+        }
+        pend = false;
+      }
+      nacc += __popc(commits);
+      __syncwarp();
+      if (first < 32) {
+        // the first lane in conflict: its row again, under the occupancy as it stands now
+        const int rcnt = __shfl_sync(0xffffffffu, cnt, first), roff = __shfl_sync(0xffffffffu, off, first);
+        const uint32_t* row = rows + roff;
+        uint32_t best = 0xFFFFFFFFu;
+        int my_idx = -1;
+        for (int c = lane; c < rcnt; c += 32) {
+          const uint32_t e = row[c];
+          if (held[e & 0xFFFFu]) continue;
+          const uint32_t kk = (e >> 16) << 16 | (uint32_t)c;
+          if (kk < best) { best = kk; my_idx = (int)(e & 0xFFFFu); }
+        }
+        const uint32_t mine = best;
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (best != 0xFFFFFFFFu && (int)(best >> 16) <= th_dist) {
+          const unsigned owner = __ballot_sync(0xffffffffu, mine == best);
+          const int ridx = __shfl_sync(0xffffffffu, my_idx, __ffs(owner) - 1);
+          if (lane == first) {
+            frame_mp[ridx] = src;
+            held[ridx] = hval;
+            if (check_ori) {
+              acc_idx[nacc] = ridx;
+              acc_bin[nacc] = __float_as_int(angle);
+            }
+          }
+          ++nacc;
+        }
+        if (lane == first) pend = false;
+        __syncwarp();
+      }
+      pending = __ballot_sync(0xffffffffu, pend);
+    }
+  }
+  int nmatches = nacc;
+  if (check_ori) {
+    __syncwarp();
+    // rotation bins of the accepted matches (:3604-3615), lanes over the matches
+    for (int e = lane; e < nacc; e += 32) {
+      float rot = __fsub_rn(__int_as_float(acc_bin[e]), k[acc_idx[e]].angle);
+      if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+      int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
+      if (bin == HISTO_LENGTH) bin = 0;
+      acc_bin[e] = bin;
+      atomicAdd(&s_hist[bin], 1);
+    }
+    __syncwarp();
+    int max1 = 0, max2 = 0, max3 = 0, i1_ = -1, i2_ = -1, i3_ = -1;  // every lane computes the same maxima
+    for (int i = 0; i < HISTO_LENGTH; ++i) {
+      const int sv = s_hist[i];
+      if (sv > max1) { max3 = max2; max2 = max1; max1 = sv; i3_ = i2_; i2_ = i1_; i1_ = i; }
+      else if (sv > max2) { max3 = max2; max2 = sv; i3_ = i2_; i2_ = i; }
+      else if (sv > max3) { max3 = sv; i3_ = i; }
+    }
+    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2_ = -1; i3_ = -1; }
+    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { i3_ = -1; }
+    int removed = 0;
+    for (int e = lane; e < nacc; e += 32) {
+      const int bin = acc_bin[e];
+      if (bin != i1_ && bin != i2_ && bin != i3_) { frame_mp[acc_idx[e]] = -1; ++removed; }  // :3627-3633
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+    nmatches -= removed;
+  }
+  if (lane == 0) *nmatches_out = nmatches;
+}
+
 // Device side shared by the overloads: per-camera grids, candidates, ordered resolve.
 int run_projected(orbm_matcher* m, const orbx_keypoint* k, const uint8_t* desc, const float* u_right, const int32_t* cam_of,
                   int n_cams, int n, orbm_bounds bounds, const std::vector<ProjQuery>& q, const uint8_t* src_desc, int n_src,
@@ -2360,7 +2525,7 @@ int run_projected(orbm_matcher* m, const orbx_keypoint* k, const uint8_t* desc, 
   cudaStream_t st = m->stream;
   const size_t frame_bytes = (size_t)n * (32 + sizeof(orbx_keypoint) + 4 + 4 + 4 + 4 + 1) + 256;
   uint8_t* fb = m->scratch<uint8_t>(8, frame_bytes);
-  const size_t q_bytes = (size_t)n_src * 32 + (size_t)nq * (sizeof(ProjQuery) + 4 + 4 + 4 + 4) + 256;
+  const size_t q_bytes = (size_t)n_src * 32 + (size_t)nq * (sizeof(ProjQuery) + 4 + 4 + 4 + 4 + 4) + 256;
   uint8_t* qb = m->scratch<uint8_t>(9, q_bytes);
   int* gstart = m->scratch<int>(4, (size_t)n_cams * (GRID_CELLS + 1));
   uint16_t* gitems = m->scratch<uint16_t>(5, (size_t)n_cams * n);
@@ -2379,6 +2544,7 @@ int run_projected(orbm_matcher* m, const orbx_keypoint* k, const uint8_t* desc, 
   int* drow_off = drow_cnt + nq;
   int32_t* dacc_idx = drow_off + nq;
   int32_t* dacc_bin = dacc_idx + nq;
+  uint32_t* dsbest = reinterpret_cast<uint32_t*>(dacc_bin + nq);
   cudaMemcpyAsync(dk, k, sizeof(orbx_keypoint) * n, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(dd, desc, (size_t)n * 32, cudaMemcpyHostToDevice, st);
   if (u_right) cudaMemcpyAsync(dur, u_right, sizeof(float) * n, cudaMemcpyHostToDevice, st);
@@ -2405,9 +2571,21 @@ int run_projected(orbm_matcher* m, const orbx_keypoint* k, const uint8_t* desc, 
   k_query_candidates<<<blocks, 256, 0, st>>>(dk, dd, u_right ? dur : nullptr, bounds, gstart, gitems, n, dq, dsd, nq, 0,
                                              drow_cnt, drow_off, rows);
   const int held_in_smem = n <= 32768;  // occupancy bytes on chip when they fit beside the 8 KB row window
-  k_query_resolve_best<<<1, 32, held_in_smem ? (size_t)((n + 15) & ~15) : 0, st>>>(
-      dq, drow_cnt, drow_off, rows, total, nq, n, dk, th_dist, check_ori, any_point_blocks, dfmp,
-      frame_mp_obs ? dfobs : nullptr, dheld, held_in_smem, dacc_idx, dacc_bin, misc + 1);
+  const size_t held_bytes = held_in_smem ? (size_t)((n + 15) & ~15) : 0;
+  bool grouped = false;  // consecutive queries of one source point (Sim3 overload: best over both cameras)
+  for (int i = 1; i < nq && !grouped; ++i) grouped = q[i].src == q[i - 1].src;
+  if (grouped) {
+    k_query_resolve_best<<<1, 32, held_bytes, st>>>(dq, drow_cnt, drow_off, rows, total, nq, n, dk, th_dist, check_ori,
+                                                    any_point_blocks, dfmp, frame_mp_obs ? dfobs : nullptr, dheld,
+                                                    held_in_smem, dacc_idx, dacc_bin, misc + 1);
+  } else {
+    k_query_static_best<<<blocks, 256, 0, st>>>(drow_cnt, drow_off, rows, nq, any_point_blocks, dfmp,
+                                                frame_mp_obs ? dfobs : nullptr, dsbest);
+    k_query_resolve_spec<<<1, 32, held_bytes, st>>>(dq, drow_cnt, drow_off, rows, dsbest, nq, n, dk, th_dist, check_ori,
+                                                    any_point_blocks, dfmp, frame_mp_obs ? dfobs : nullptr, dheld,
+                                                    held_in_smem, dacc_idx, dacc_bin, misc + 1);
+    m->launches++;
+  }
   m->launches += 2;
   cudaMemcpyAsync(frame_mp, dfmp, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st);
   cudaMemcpyAsync(nmatches, misc + 1, sizeof(int), cudaMemcpyDeviceToHost, st);

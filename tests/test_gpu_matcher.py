@@ -238,6 +238,31 @@ def test_search_by_projection_frame_vs_oracle(O, offset, th, mono, check_ori):
     assert rn > 200
 
 
+@pytest.mark.parametrize("reps,th", [(2, 15.0), (5, 30.0)])
+def test_search_by_projection_frame_contended(O, reps, th):
+    """Every last-frame point repeated `reps` times (same projection, same descriptor, mixed Observations()):
+    consecutive queries compete for the same keypoints, so the walk's order-dependent parts decide the result."""
+    from multi_orb_slam_b200._lib import Camera
+    from multi_orb_slam_b200.matcher import Frame, ORBmatcher
+    s = _rig_scene(O, 5, 700, (0, 0, 0.3))
+    sf = O.extractor("port").scale_tables()[0]
+    n = s["n"]
+    rep = lambda a: np.repeat(a, reps, axis=0)
+    last_k, last_cam, last_valid = rep(s["last_k"]), rep(s["last_cam"]), rep(s["last_valid"])
+    last_xyz, last_desc = rep(s["last_xyz"]), rep(s["last_desc"])
+    last_obs = (s["rng"].random(len(last_k)) < 0.5).astype(s["last_obs"].dtype)
+    fmp0 = np.full(n, -1, np.int32)
+    fobs0 = np.zeros(n, np.int32)
+    args = (CAM, s["Tcw"], s["Tlw"], last_k, last_cam, last_valid, last_xyz, last_desc, last_obs, CALIB, th, False)
+    rn, rfmp = O.search_by_projection_frame(s["cur_k"], s["cur_d"], s["ur"], s["cur_cam"], (0, 640, 0, 480), sf, *args, True,
+                                            fmp0, fobs0)
+    F = Frame(s["cur_k"], s["cur_d"], 640, 480, mvScaleFactors=sf, mvuRight=s["ur"], mvpMapPoints=fmp0.copy(),
+              mvpMapPointsObserved=fobs0)
+    gn = ORBmatcher(0.9, True).SearchByProjectionFrame(F, s["cur_cam"], Camera(*CAM), *args[1:])
+    assert gn == rn and np.array_equal(F.mvpMapPoints, rfmp)
+    assert rn > 100
+
+
 @pytest.mark.parametrize("th,orb_dist,check_ori", [(10.0, 100, True), (3.0, 64, True), (10.0, 100, False)])
 def test_search_by_projection_keyframe_vs_oracle(O, th, orb_dist, check_ori):
     from multi_orb_slam_b200._lib import Camera
