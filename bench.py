@@ -286,6 +286,28 @@ def widened_rows_leg(matcher, device, with_cpu):
             s["cur_k"], s["cur_d"], s["ur"], s["cur_cam"], (0, 640, 0, 480), sf_r, RIG_CAM, s["Tcw"], s["Tlw"], s["last_k"],
             s["last_cam"], s["last_valid"], s["last_xyz"], s["last_desc"], s["last_obs"], RIG_CALIB, 15.0, False, True, fmp0, fobs0), 3)
     out["search_by_projection_frame"] = row
+    # configs[3]'s matcher: SearchByProjection(Frame, vector<MapPoint*>, th) of SearchLocalPoints, KITTI-shaped frame
+    from multi_orb_slam_b200.matcher import MapPoints
+    from multi_orb_slam_b200.synth import projection_case, textured
+    exk = ORBextractor(2000, 1.2, 8, 20, 7, image_size=(1241, 376), max_batch=1, device=device)
+    kk, dk_ = exk(textured(1241, 376, 2))
+    mpk, mpdk, _ = projection_case(kk, dk_, 2, 20000)
+    sf_k = np.asarray(exk.GetScaleFactors(), np.float32)
+    obs_k = np.ones(len(mpk), np.int32)
+    ur_k = np.full(len(kk), -1, np.float32)
+    mpts = MapPoints(mpk, mpdk, obs_k)
+    m08 = type(matcher)(0.8, True, device=device)
+
+    def spp_gpu():
+        fr = Frame(kk, dk_, 1241, 376, mvScaleFactors=sf_k, mvuRight=ur_k)
+        return m08.SearchByProjection(fr, mpts, 3.0)
+
+    row = {"workload": f"SearchByProjection(Frame, MapPoints, th=3), 1241x376, {len(kk)} keypoints x 20000 map points (configs[3])",
+           "gpu_ms": best_ms(spp_gpu)}
+    if with_cpu:
+        row["cpu_ms"] = best_ms(lambda: oracle_lib.search_by_projection_points(kk, dk_, ur_k, (0, 1241, 0, 376), sf_k, mpk, mpdk,
+                                                                               obs_k, 3.0, 0.8), 3)
+    out["search_by_projection_points"] = row
     # Fuse(KeyFrame*, vpMapPoints, Calib, th): 2500 map points of the neighbours into one key frame
     s2 = rig_scene(gpu_extract, 21, 2500, (0, 0, 0))
     r2 = s2["rng"]

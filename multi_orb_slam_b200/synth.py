@@ -302,3 +302,26 @@ def rig_scene(extract, seed, n_last, tlast_offset):
                 last_k=last_k, last_cam=cur_cam[src].copy(), last_valid=(rng.random(n_last) < 0.9).astype(np.int32),
                 last_xyz=Xw.astype(np.float32), last_desc=np.packbits(bits, axis=1),
                 last_obs=(rng.random(n_last) < 0.85).astype(np.int32), rng=rng, n=n)
+
+
+def projection_case(k, d, seed, nmp, width=1241, height=376):
+    """BASELINE configs[3]'s matcher input: `nmp` map points for SearchByProjection(Frame, vector<MapPoint*>), derived
+    from a frame's keypoints `k` / descriptors `d` (most project near the keypoint they come from, with up to 60 flipped
+    descriptor bits; some project anywhere).  Returns (mp records, mp descriptors, rng)."""
+    from ._lib import MP_DTYPE
+    rng = np.random.default_rng(seed + 50)
+    mp = np.zeros(nmp, MP_DTYPE)
+    src = rng.integers(0, len(k), nmp)
+    near = rng.random(nmp) < 0.8
+    mp["proj_x"] = np.where(near, k["x"][src] + rng.normal(0, 3, nmp), rng.uniform(0, width, nmp)).astype(np.float32)
+    mp["proj_y"] = np.where(near, k["y"][src] + rng.normal(0, 3, nmp), rng.uniform(0, height, nmp)).astype(np.float32)
+    mp["proj_xr"] = mp["proj_x"] - 5
+    mp["view_cos"] = rng.uniform(0.5, 1.0, nmp).astype(np.float32)
+    mp["view_cos"][rng.random(nmp) < 0.1] = 0.9995
+    mp["level"] = np.where(near, np.clip(k["octave"][src] + rng.integers(0, 2, nmp), 0, 7), rng.integers(0, 8, nmp))
+    mp["track_in_view"] = rng.random(nmp) < 0.95
+    mp["bad"] = rng.random(nmp) < 0.03
+    bits = np.unpackbits(d[src], axis=1)
+    flips = rng.integers(0, 61, nmp)
+    bits ^= (np.argsort(np.argsort(rng.random((nmp, 256)), axis=1), axis=1) < flips[:, None]).astype(np.uint8)
+    return mp, np.packbits(bits, axis=1), rng

@@ -124,28 +124,12 @@ def test_search_for_initialization_batch(M, O):
         assert nm[p] == rn and np.array_equal(m12[p, : len(a)], rm12) and np.array_equal(newprev[p, : len(a)], rprev)
 
 
-def _projection_case(O, seed, nmp, th_levels=8):
-    from multi_orb_slam_b200._lib import MP_DTYPE
+def _projection_case(O, seed, nmp):
+    from multi_orb_slam_b200.synth import projection_case
     port = O.extractor("port", nfeatures=2000)
-    img = textured(1241, 376, seed)
-    k, d, _ = port.extract(img)
-    rng = np.random.default_rng(seed + 50)
-    mp = np.zeros(nmp, MP_DTYPE)
-    src = rng.integers(0, len(k), nmp)
-    # most points project near the keypoint they were derived from, some anywhere
-    near = rng.random(nmp) < 0.8
-    mp["proj_x"] = np.where(near, k["x"][src] + rng.normal(0, 3, nmp), rng.uniform(0, 1241, nmp)).astype(np.float32)
-    mp["proj_y"] = np.where(near, k["y"][src] + rng.normal(0, 3, nmp), rng.uniform(0, 376, nmp)).astype(np.float32)
-    mp["proj_xr"] = mp["proj_x"] - 5
-    mp["view_cos"] = rng.uniform(0.5, 1.0, nmp).astype(np.float32)
-    mp["view_cos"][rng.random(nmp) < 0.1] = 0.9995
-    mp["level"] = np.where(near, np.clip(k["octave"][src] + rng.integers(0, 2, nmp), 0, 7), rng.integers(0, 8, nmp))
-    mp["track_in_view"] = rng.random(nmp) < 0.95
-    mp["bad"] = rng.random(nmp) < 0.03
-    bits = np.unpackbits(d[src], axis=1)
-    flips = rng.integers(0, 61, nmp)
-    bits ^= (np.argsort(np.argsort(rng.random((nmp, 256)), axis=1), axis=1) < flips[:, None]).astype(np.uint8)
-    return k, d, mp, np.packbits(bits, axis=1), rng
+    k, d, _ = port.extract(textured(1241, 376, seed))
+    mp, mpd, rng = projection_case(k, d, seed, nmp)
+    return k, d, mp, mpd, rng
 
 
 @pytest.mark.parametrize("nmp,th,with_stereo,with_obs", [(3000, 3.0, False, False), (20000, 3.0, False, False),
@@ -172,6 +156,30 @@ def test_search_by_projection_points_vs_oracle(M, O, nmp, th, with_stereo, with_
     gn = m.SearchByProjection(F, MapPoints(mp, mpd, mp_obs), th)
     assert gn == rn and np.array_equal(F.mvpMapPoints, rfmp)
     assert rn > nmp // 20
+
+
+@pytest.mark.parametrize("reps,th", [(2, 3.0), (6, 6.0)])
+def test_search_by_projection_points_contended(M, O, reps, th):
+    """Every map point repeated `reps` times (same projection and descriptor, mixed Observations()): consecutive points
+    compete for the same keypoints and for each other's second-best, so the order-dependent parts decide the result."""
+    from multi_orb_slam_b200.matcher import Frame, MapPoints, ORBmatcher
+    k, d, mp, mpd, rng = _projection_case(O, 4, 1500)
+    mp, mpd = np.repeat(mp, reps), np.repeat(mpd, reps, axis=0)
+    nmp = len(mp)
+    sf = O.extractor("port").scale_tables()[0]
+    n = len(k)
+    ur = np.full(n, -1, np.float32)
+    mp_obs = (rng.random(nmp) < 0.6).astype(np.int32)
+    fmp0 = np.full(n, -1, np.int32)
+    fobs0 = np.zeros(n, np.int32)
+    held = rng.random(n) < 0.1
+    fmp0[held] = rng.integers(0, nmp, held.sum())
+    fobs0[held] = rng.random(held.sum()) < 0.5
+    rn, rfmp = O.search_by_projection_points(k, d, ur, (0, 1241, 0, 376), sf, mp, mpd, mp_obs, th, 0.8, fmp0, fobs0)
+    F = Frame(k, d, 1241, 376, mvScaleFactors=sf, mvuRight=ur, mvpMapPoints=fmp0.copy(), mvpMapPointsObserved=fobs0)
+    gn = ORBmatcher(0.8, True).SearchByProjection(F, MapPoints(mp, mpd, mp_obs), th)
+    assert gn == rn and np.array_equal(F.mvpMapPoints, rfmp)
+    assert rn > 300
 
 
 def test_bruteforce_batch_vs_oracle(O):
