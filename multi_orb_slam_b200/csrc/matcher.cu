@@ -984,46 +984,81 @@ __global__ void __launch_bounds__(256) k_bow_resolve(const BowQuery* __restrict_
   if (tid < HISTO_LENGTH) s_hist[tid] = 0;
   __syncthreads();
   const uint32_t* R = staged ? s_rows : rows_all + r0;  // indexed by row offsets relative to the pair
-  if (tid < 32) {
-    // The walk is one dependent chain, so it touches no HBM on its critical path: offsets and counts
-    // of 32 queries are fetched by the 32 lanes at once and broadcast by shuffle, and the rotation
-    // bins (which need both keypoint angles) are taken afterwards by the whole CTA; during the walk
-    // q_bin[j] only records the matched side-2 index.
-    int nmatches = 0;
-    int l_cnt = 0, l_off = 0;
-    for (int j = 0; j < nq; ++j) {
-      if ((j & 31) == 0) {
-        const int jj = j + lane;
-        if (jj < nq) { l_cnt = q[jj].cnt; l_off = q[jj].off; }
-      }
-      const int cnt = __shfl_sync(0xffffffffu, l_cnt, j & 31);
-      const int off = __shfl_sync(0xffffffffu, l_off, j & 31) - r0;
-      // key = dist << 16 | position in the node's vector: the strict-< scan order (:311-321)
-      uint32_t best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
-      for (int c = lane; c < cnt; c += 32) {
-        const uint32_t e = R[off + c];
-        const uint32_t idx2 = e & 0xFFFFu;
-        if ((e >> 16) == 0xFFFFu || (s_taken[idx2 >> 5] >> (idx2 & 31) & 1u)) continue;
-        const uint32_t key = (e & 0xFFFF0000u) | (uint32_t)c;
-        second = min(second, max(best, key));
-        best = min(best, key);
-      }
-      warp_top2(best, second);
-      int matched = -1;
-      if (best != 0xFFFFFFFFu) {
-        const int bestDist1 = (int)(best >> 16);
-        const int bestDist2 = second == 0xFFFFFFFFu ? 256 : (int)(second >> 16);
-        if (bestDist1 <= max_dist && (float)bestDist1 < __fmul_rn(nnratio, (float)bestDist2)) {
-          const int idx2 = (int)(R[off + (int)(best & 0xFFFFu)] & 0xFFFFu);
-          if (lane == 0) s_taken[idx2 >> 5] |= 1u << (idx2 & 31);
-          matched = idx2;
-          nmatches++;
-          __syncwarp();
+  {
+    // Ordered walk, eight queries per step (a warp per query).  A query's outcome depends only on
+    // the two least keys among its side-2 candidates that are still unmatched, and the matched set
+    // only grows: every pending warp scans its row under the matched bits as they stand, warp 0
+    // commits the longest prefix of the step whose answers are independent (a lane conflicts when a
+    // lower lane of the step is about to match its best or its second), the rest scan again.  The
+    // lowest pending query never conflicts, so matches are made in the reference's order.  During
+    // the walk q_bin[j] records the matched side-2 index; the rotation bins follow below.
+    __shared__ int s_b[8], s_s[8], s_will[8];
+    __shared__ unsigned s_donem, s_leftm;
+    const int w = tid >> 5;
+    int nmatches = 0;  // warp 0's count
+    int cnt_n = w < nq ? q[w].cnt : 0, off_n = w < nq ? q[w].off : 0;
+    for (int j0 = 0; j0 < nq; j0 += 8) {
+      const int j = j0 + w;
+      const int cnt = j < nq ? cnt_n : 0, off = off_n - r0;
+      if (j + 8 < nq) { cnt_n = q[j + 8].cnt; off_n = q[j + 8].off; }  // next step's fields, in flight during this one
+      bool pend = cnt > 0;
+      if (!pend && j < nq && lane == 0) q_bin[j] = -1;
+      for (;;) {
+        int b = -1, sx = -1, will = 0;
+        if (pend) {
+          // key = dist << 16 | position in the node's vector: the strict-< scan order (:311-321)
+          uint32_t best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
+          for (int c = lane; c < cnt; c += 32) {
+            const uint32_t e = R[off + c];
+            const uint32_t idx2 = e & 0xFFFFu;
+            if ((e >> 16) == 0xFFFFu || (s_taken[idx2 >> 5] >> (idx2 & 31) & 1u)) continue;
+            const uint32_t key = (e & 0xFFFF0000u) | (uint32_t)c;
+            second = min(second, max(best, key));
+            best = min(best, key);
+          }
+          warp_top2(best, second);
+          // nothing left, or the least distance above the gate (it can only grow): no match, final
+          if (best == 0xFFFFFFFFu || (int)(best >> 16) > max_dist) {
+            pend = false;
+            if (lane == 0) q_bin[j] = -1;
+          } else {
+            const int bestDist1 = (int)(best >> 16);
+            const int bestDist2 = second == 0xFFFFFFFFu ? 256 : (int)(second >> 16);
+            b = (int)(R[off + (int)(best & 0xFFFFu)] & 0xFFFFu);
+            if (second != 0xFFFFFFFFu) sx = (int)(R[off + (int)(second & 0xFFFFu)] & 0xFFFFu);
+            will = (float)bestDist1 < __fmul_rn(nnratio, (float)bestDist2);
+          }
         }
+        if (lane == 0) { s_b[w] = b; s_s[w] = sx; s_will[w] = will; }
+        __syncthreads();
+        if (w == 0) {
+          const int l8 = lane & 7;
+          const int mb = s_b[l8], ms = s_s[l8], mw = s_will[l8];
+          const bool p = lane < 8 && mb >= 0;
+          bool conflict = false;
+#pragma unroll
+          for (int src = 0; src < 7; ++src) {
+            const int ob = __shfl_sync(0xffffffffu, mw ? mb : -1, src);
+            if (p && src < lane && ob >= 0 && (ob == mb || ob == ms)) conflict = true;
+          }
+          const unsigned cm = __ballot_sync(0xffffffffu, conflict);
+          const int first = cm ? __ffs(cm) - 1 : 32;
+          const bool done = p && lane < first;
+          const bool commit = done && mw;
+          if (commit) atomicOr(&s_taken[mb >> 5], 1u << (mb & 31));
+          if (done) q_bin[j0 + lane] = commit ? mb : -1;
+          nmatches += __popc(__ballot_sync(0xffffffffu, commit));
+          const unsigned dm = __ballot_sync(0xffffffffu, done), pm = __ballot_sync(0xffffffffu, p);
+          if (lane == 0) { s_donem = dm; s_leftm = pm & ~dm; }
+        }
+        __syncthreads();
+        if (s_donem >> w & 1u) pend = false;
+        const unsigned left = s_leftm;
+        __syncthreads();  // s_b / s_donem are rewritten in the next round
+        if (!left) break;
       }
-      if (lane == 0) q_bin[j] = matched;
     }
-    if (lane == 0) s_nmatch = nmatches;
+    if (tid == 0) s_nmatch = nmatches;
   }
   __syncthreads();
   // matches and their rotation bins (:330-341), a thread per query
