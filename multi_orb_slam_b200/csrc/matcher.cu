@@ -1286,7 +1286,7 @@ __global__ void __launch_bounds__(1024) k_scan_exclusive(const int* __restrict__
 // overwritten by later points exactly as in the sequential loop.  (SearchLocalPoints projects several
 // map points onto every keypoint, so a static best per point computed up front is mostly stale by the
 // time the walk reaches it: that single-warp speculative form measured 8.9 ms on configs[3]'s 20 000
-// points, the plain sequential warp 6.8 ms, this form 1.26 ms.)
+// points, the plain sequential warp 6.8 ms, this form 1.2 ms.)
 __global__ void __launch_bounds__(1024) k_proj_resolve_cta(const int* __restrict__ row_cnt, const int* __restrict__ row_off,
                                                            const uint32_t* __restrict__ rows,
                                                            const int32_t* __restrict__ mp_obs, int nmp, int n, float nnratio,
@@ -1301,10 +1301,31 @@ __global__ void __launch_bounds__(1024) k_proj_resolve_cta(const int* __restrict
   for (int i = tid; i < n; i += 1024) held[i] = (frame_mp[i] >= 0 && frame_mp_obs && frame_mp_obs[i] > 0) ? 1 : 0;
   __syncthreads();
   int nmatches = 0;  // warp 0's count
+  // Nothing on the walk's critical path waits for HBM: a warp keeps the first PROJ_SLOTS * 32
+  // candidates of its point in registers (longer rows read the rest in place), the entries of the
+  // next step's point are fetched while this step resolves, and the counts / offsets one step
+  // further ahead.
+  constexpr int PROJ_SLOTS = 4;
+  constexpr uint32_t NO_ENTRY = 0xFFFFFFFFu;  // entries are dist << 20 | level << 16 | index < 2^29
+  auto entry_at = [&](const uint32_t (&ent)[PROJ_SLOTS], const uint32_t* row, int pos) -> uint32_t {
+    if (pos >= PROJ_SLOTS * 32) return row[pos];
+    uint32_t v = ent[0];
+#pragma unroll
+    for (int k = 1; k < PROJ_SLOTS; ++k)
+      if ((pos >> 5) == k) v = ent[k];
+    return __shfl_sync(0xffffffffu, v, pos & 31);
+  };
+  uint32_t ent[PROJ_SLOTS], ent_n[PROJ_SLOTS];
+  int cnt = w < nmp ? row_cnt[w] : 0, off = w < nmp ? row_off[w] : 0;
+  int cnt_n = 32 + w < nmp ? row_cnt[32 + w] : 0, off_n = 32 + w < nmp ? row_off[32 + w] : 0;
+#pragma unroll
+  for (int k = 0; k < PROJ_SLOTS; ++k) ent[k] = k * 32 + lane < cnt ? rows[off + k * 32 + lane] : NO_ENTRY;
   for (int b0 = 0; b0 < nmp; b0 += 32) {
-    const int i = b0 + w;
-    const int cnt = i < nmp ? row_cnt[i] : 0;
-    const uint32_t* row = rows + (i < nmp ? row_off[i] : 0);
+#pragma unroll
+    for (int k = 0; k < PROJ_SLOTS; ++k) ent_n[k] = k * 32 + lane < cnt_n ? rows[off_n + k * 32 + lane] : NO_ENTRY;
+    const int i2 = b0 + 64 + w;
+    const int cnt_nn = i2 < nmp ? row_cnt[i2] : 0, off_nn = i2 < nmp ? row_off[i2] : 0;
+    const uint32_t* row = rows + off;
     bool pend = cnt > 0;
     // warp 0 keeps the per-point constants of the step, lane = point
     const int li = b0 + lane;
@@ -1313,7 +1334,15 @@ __global__ void __launch_bounds__(1024) k_proj_resolve_cta(const int* __restrict
       int bidx = -1, sidx = -1, will = 0;
       if (pend) {
         uint32_t best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
-        for (int c = lane; c < cnt; c += 32) {
+#pragma unroll
+        for (int k = 0; k < PROJ_SLOTS; ++k) {
+          const uint32_t e = ent[k];
+          if (e == NO_ENTRY || held[e & 0xFFFFu]) continue;
+          const uint32_t key = (e >> 20) << 16 | (uint32_t)(k * 32 + lane);
+          second = min(second, max(best, key));
+          best = min(best, key);
+        }
+        for (int c = PROJ_SLOTS * 32 + lane; c < cnt; c += 32) {
           const uint32_t e = row[c];
           if (held[e & 0xFFFFu]) continue;
           const uint32_t key = (e >> 20) << 16 | (uint32_t)c;
@@ -1326,12 +1355,12 @@ __global__ void __launch_bounds__(1024) k_proj_resolve_cta(const int* __restrict
           pend = false;
         } else {
           const int bestDist = (int)(best >> 16);
-          const uint32_t eb = row[best & 0xFFFFu];
+          const uint32_t eb = entry_at(ent, row, (int)(best & 0xFFFFu));
           const int bestLevel = (int)(eb >> 16 & 15u);
           bidx = (int)(eb & 0xFFFFu);
           int bestDist2 = 256, bestLevel2 = -1;
           if (second != 0xFFFFFFFFu) {
-            const uint32_t es = row[second & 0xFFFFu];
+            const uint32_t es = entry_at(ent, row, (int)(second & 0xFFFFu));
             bestDist2 = (int)(second >> 16);
             bestLevel2 = (int)(es >> 16 & 15u);
             sidx = (int)(es & 0xFFFFu);
@@ -1374,6 +1403,10 @@ __global__ void __launch_bounds__(1024) k_proj_resolve_cta(const int* __restrict
       __syncthreads();  // s_bidx / s_done are rewritten in the next round
       if (!left) break;
     }
+    cnt = cnt_n; off = off_n;
+    cnt_n = cnt_nn; off_n = off_nn;
+#pragma unroll
+    for (int k = 0; k < PROJ_SLOTS; ++k) ent[k] = ent_n[k];
   }
   if (tid == 0) *nmatches_out = nmatches;
 }
