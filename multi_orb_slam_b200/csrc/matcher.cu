@@ -1294,8 +1294,10 @@ __global__ void __launch_bounds__(1024) k_proj_resolve_cta(const int* __restrict
                                                            uint8_t* __restrict__ held_global, int held_in_smem,
                                                            int* __restrict__ nmatches_out) {
   extern __shared__ __align__(16) uint8_t s_held[];
-  __shared__ int s_bidx[32], s_sidx[32], s_will[32];
-  __shared__ unsigned s_done, s_left;
+  // per-round exchange, double-buffered by round parity: two barriers per round instead of three
+  __shared__ int s_bidx[2][32], s_sidx[2][32], s_will[2][32];
+  __shared__ unsigned s_done[2], s_left[2];
+  int rp = 0;  // round parity
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   uint8_t* held = held_in_smem ? s_held : held_global;
   for (int i = tid; i < n; i += 1024) held[i] = (frame_mp[i] >= 0 && frame_mp_obs && frame_mp_obs[i] > 0) ? 1 : 0;
@@ -1368,10 +1370,10 @@ __global__ void __launch_bounds__(1024) k_proj_resolve_cta(const int* __restrict
           will = !(bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2));
         }
       }
-      if (lane == 0) { s_bidx[w] = bidx; s_sidx[w] = sidx; s_will[w] = will; }
+      if (lane == 0) { s_bidx[rp][w] = bidx; s_sidx[rp][w] = sidx; s_will[rp][w] = will; }
       __syncthreads();
       if (w == 0) {
-        const int b = s_bidx[lane], sx = s_sidx[lane], wl = s_will[lane];
+        const int b = s_bidx[rp][lane], sx = s_sidx[rp][lane], wl = s_will[rp][lane];
         const bool p = b >= 0;  // pending points have a best keypoint, free under the current occupancy
         const bool wants = p && wl;
         const unsigned peers = __match_any_sync(0xffffffffu, wants ? b : -1 - lane);
@@ -1395,12 +1397,12 @@ __global__ void __launch_bounds__(1024) k_proj_resolve_cta(const int* __restrict
         }
         nmatches += __popc(__ballot_sync(0xffffffffu, commit));
         const unsigned dm = __ballot_sync(0xffffffffu, done), pm = __ballot_sync(0xffffffffu, p);
-        if (lane == 0) { s_done = dm; s_left = pm & ~dm; }
+        if (lane == 0) { s_done[rp] = dm; s_left[rp] = pm & ~dm; }
       }
       __syncthreads();
-      if (s_done >> w & 1u) pend = false;
-      const unsigned left = s_left;
-      __syncthreads();  // s_bidx / s_done are rewritten in the next round
+      if (s_done[rp] >> w & 1u) pend = false;
+      const unsigned left = s_left[rp];
+      rp ^= 1;
       if (!left) break;
     }
     cnt = cnt_n; off = off_n;
@@ -2476,8 +2478,10 @@ __global__ void __launch_bounds__(1024) k_query_resolve_cta(const ProjQuery* __r
                                                             int* __restrict__ nmatches_out) {
   extern __shared__ __align__(16) uint8_t s_held[];
   __shared__ int s_hist[HISTO_LENGTH];
-  __shared__ int s_bidx[32];
-  __shared__ unsigned s_done, s_left;
+  // per-round exchange, double-buffered by round parity: two barriers per round instead of three
+  __shared__ int s_bidx[2][32];
+  __shared__ unsigned s_done[2], s_left[2];
+  int rp = 0;  // round parity
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const unsigned lt = (1u << lane) - 1u;
   uint8_t* held = held_in_smem ? s_held : held_global;
@@ -2522,10 +2526,10 @@ __global__ void __launch_bounds__(1024) k_query_resolve_cta(const ProjQuery* __r
           bidx = __shfl_sync(0xffffffffu, my_idx, __ffs(owner) - 1);
         }
       }
-      if (lane == 0) s_bidx[w] = bidx;
+      if (lane == 0) s_bidx[rp][w] = bidx;
       __syncthreads();
       if (w == 0) {
-        const int b = s_bidx[lane];
+        const int b = s_bidx[rp][lane];
         const bool p = b >= 0;
         const unsigned peers = __match_any_sync(0xffffffffu, p ? b : -1 - lane);
         const bool conflict = p && (peers & lt) != 0;
@@ -2544,12 +2548,12 @@ __global__ void __launch_bounds__(1024) k_query_resolve_cta(const ProjQuery* __r
         }
         nacc += __popc(commits);
         const unsigned pm = __ballot_sync(0xffffffffu, p);
-        if (lane == 0) { s_done = commits; s_left = pm & ~commits; }
+        if (lane == 0) { s_done[rp] = commits; s_left[rp] = pm & ~commits; }
       }
       __syncthreads();
-      if (s_done >> w & 1u) pend = false;
-      const unsigned left = s_left;
-      __syncthreads();  // s_bidx / s_done are rewritten in the next round
+      if (s_done[rp] >> w & 1u) pend = false;
+      const unsigned left = s_left[rp];
+      rp ^= 1;
       if (!left) break;
     }
   }
