@@ -1,5 +1,6 @@
 // C-ABI of the extractor (include/orb_b200.h): handle, geometry, HBM workspace, launches.
 // Replaces class ORBextractor (reference include/ORBextractor.h:45-112, src/ORBextractor.cc).
+#include "device_guard.h"
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -354,10 +355,10 @@ int orbx_create(const orbx_config* cfg, orbx_extractor** out) {
     if (h->err.empty()) h->err = "no CUDA device (this library has no CPU fallback)";
     return fail(ORBX_E_CUDA);
   }
-  if (cfg->device >= 0) {
-    if (!h->check(cudaSetDevice(cfg->device), "cudaSetDevice")) return fail(ORBX_E_CUDA);
-  }
+  if (cfg->device >= ndev) { h->err = "no such CUDA device"; return fail(ORBX_E_CUDA); }
   if (!h->check(cudaGetDevice(&h->device), "cudaGetDevice")) return fail(ORBX_E_CUDA);
+  if (cfg->device >= 0) h->device = cfg->device;
+  OrbDeviceGuard dev_guard(h->device);  // the caller's current device is restored on return
   if (!h->check(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail(ORBX_E_CUDA);
   h->stream = h->own_stream;
   for (auto& set : h->ev)
@@ -385,7 +386,7 @@ int orbx_create(const orbx_config* cfg, orbx_extractor** out) {
        h->check(cudaMemcpy(h->gh.d_cells, cells.data(), cells.size() * sizeof(OrbCell), cudaMemcpyHostToDevice), "copy cells") &&
        h->check(cudaMemcpy(h->gh.d_xtab, xt.data(), xt.size() * sizeof(OrbXTap), cudaMemcpyHostToDevice), "copy xtab") &&
        h->check(cudaMemcpy(h->gh.d_ytab, yt.data(), yt.size() * sizeof(OrbYTap), cudaMemcpyHostToDevice), "copy ytab") &&
-       h->check(orbk::prepare_octree(g), "octree shared-memory opt-in") &&
+       h->check(orbk::prepare_octree(h->gh), "octree shared-memory opt-in") &&
        h->check(orbk::prepare_pyramid(g), "pyramid shared-memory opt-in");
   if (!ok) return fail(ORBX_E_CUDA);
   *out = h;
@@ -437,7 +438,7 @@ int orbx_extract_batch_device(orbx_extractor* h, const uint8_t* d_images, int n_
     h->err = "invalid argument";
     return ORBX_E_INVALID;
   }
-  cudaSetDevice(h->device);
+  OrbDeviceGuard dev_guard(h->device);
   for (int f0 = 0; f0 < n_frames; f0 += h->cfg.max_batch) {
     const int nb = std::min(h->cfg.max_batch, n_frames - f0);
     const int rc = run_batch(h, d_images + (size_t)f0 * frame_stride, nb, frame_stride, row_stride,
@@ -454,7 +455,7 @@ int orbx_extract_batch_host(orbx_extractor* h, const uint8_t* images, int n_fram
     h->err = "invalid argument";
     return ORBX_E_INVALID;
   }
-  cudaSetDevice(h->device);
+  OrbDeviceGuard dev_guard(h->device);
   if (!ensure_staging(h, cap)) return ORBX_E_CUDA;
   const int W = h->cfg.width, H = h->cfg.height;
   int status = ORBX_OK;
@@ -556,7 +557,7 @@ int orbx_get_pyramid_level(orbx_extractor* h, int frame, int level, int with_bor
   if (!dst) return ORBX_OK;
   if (frame < 0 || frame >= h->last_batch) { h->err = "no such frame in the last batch"; return ORBX_E_STATE; }
   if (dst_stride < (size_t)ow) return ORBX_E_INVALID;
-  cudaSetDevice(h->device);
+  OrbDeviceGuard dev_guard(h->device);
   // The levels are stored without the EDGE_THRESHOLD border (level 0 is the caller's frame): copy the
   // interior into place, then mirror it outwards exactly as copyMakeBorder(BORDER_REFLECT_101) does
   // (src/ORBextractor.cc:1124-1130).  This accessor is not on the hot path.
@@ -595,7 +596,7 @@ int orbx_debug_candidates(orbx_extractor* h, int frame, int level, int32_t* x, i
                           int* n) {
   if (!h || level < 0 || level >= h->cfg.nlevels || !n) return ORBX_E_INVALID;
   if (frame < 0 || frame >= h->last_batch) return ORBX_E_STATE;
-  cudaSetDevice(h->device);
+  OrbDeviceGuard dev_guard(h->device);
   const OrbGeom& g = h->gh.g;
   const OrbLevelGeom& L = g.lv[level];
   std::vector<int> cc(L.n_cells);
@@ -619,7 +620,7 @@ int orbx_debug_candidates(orbx_extractor* h, int frame, int level, int32_t* x, i
 int orbx_debug_blurred(orbx_extractor* h, int frame, int level, uint8_t* dst, size_t dst_stride) {
   if (!h || level < 0 || level >= h->cfg.nlevels || !dst) return ORBX_E_INVALID;
   if (frame < 0 || frame >= h->last_batch) return ORBX_E_STATE;
-  cudaSetDevice(h->device);
+  OrbDeviceGuard dev_guard(h->device);
   const OrbLevelGeom& L = h->gh.g.lv[level];
   if (!h->check(cudaStreamSynchronize(h->stream), "sync") ||
       !h->check(cudaMemcpy2D(dst, dst_stride, h->d_blur + (size_t)frame * h->gh.g.blur_frame_bytes + L.blur_off, L.bpitch,

@@ -10,6 +10,7 @@
 // frame) so the small per-frame work fills the 148 SMs.
 #include <cuda_runtime.h>
 #include <cstdlib>
+#include <mutex>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -815,7 +816,9 @@ void launch_fast(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, const uint8_
   ++*launches;
 }
 
-int octree_smem_keys(const OrbGeom& g) {
+// Shared-memory budget of the octree kernel, resolved ONCE per handle (orbx_create) and kept in the
+// handle's OrbGeomHost: the launch and the opt-in must agree, whatever happens to the environment later.
+static int octree_smem_keys(const OrbGeom& g) {
   int m = 0;
   for (int l = 0; l < g.nlevels; ++l) m = max(m, g.lv[l].key_cap);
   int cap_keys = 6144;  // 36 KB of keys + labels keeps ~3 CTAs resident per SM
@@ -823,21 +826,22 @@ int octree_smem_keys(const OrbGeom& g) {
   return min(m, cap_keys);
 }
 
-size_t octree_smem_bytes(const OrbGeom& g) {
-  OtScratch s;
-  return (size_t)ot_layout(s, g.ot_cap, g.ot_scan_cap, 256) + (size_t)octree_smem_keys(g) * 6;
-}
-
 cudaError_t prepare_pyramid(const OrbGeom&) { return cudaSuccess; }  // the pyramid kernels use no shared memory
 
 // The opt-in limit is a property of the FUNCTION (per device), shared by every handle: only ever
 // raise it, so a handle with a smaller nfeatures cannot shrink it under another handle's feet.
-cudaError_t prepare_octree(const OrbGeom& g) {
+// The reference creates one extractor per camera, possibly from several threads: serialised.
+cudaError_t prepare_octree(OrbGeomHost& gh) {
   static int raised[64] = {0};
+  static std::mutex mu;
+  OtScratch s;
+  gh.ot_smem_keys = octree_smem_keys(gh.g);
+  gh.ot_smem_bytes = (size_t)ot_layout(s, gh.g.ot_cap, gh.g.ot_scan_cap, 256) + (size_t)gh.ot_smem_keys * 6;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  const int need = (int)octree_smem_bytes(g);
+  const int need = (int)gh.ot_smem_bytes;
+  std::lock_guard<std::mutex> lock(mu);
   if (dev < 64 && need <= raised[dev]) return cudaSuccess;
   e = cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
   if (e == cudaSuccess && dev < 64) raised[dev] = need;
@@ -847,8 +851,8 @@ cudaError_t prepare_octree(const OrbGeom& g) {
 void launch_octree(const OrbGeomHost& gh, int n_frames, const uint32_t* d_cand, const int* d_cell_count,
                    uint32_t* d_keys, uint16_t* d_knode, uint32_t* d_sel, int* d_sel_count, cudaStream_t st,
                    long long* launches) {
-  k_octree<<<dim3(n_frames, gh.g.nlevels), 256, octree_smem_bytes(gh.g), st>>>(gh.d_geom, d_cand, d_cell_count, d_keys,
-                                                                                d_knode, d_sel, d_sel_count, octree_smem_keys(gh.g));
+  k_octree<<<dim3(n_frames, gh.g.nlevels), 256, gh.ot_smem_bytes, st>>>(gh.d_geom, d_cand, d_cell_count, d_keys, d_knode,
+                                                                         d_sel, d_sel_count, gh.ot_smem_keys);
   ++*launches;
 }
 

@@ -22,14 +22,15 @@ struct OrbGeomHost {
   OrbCell* d_cells;        // [g.n_cells]
   OrbXTap* d_xtab;
   OrbYTap* d_ytab;
+  int ot_smem_keys;        // octree: keys kept in shared memory (prepare_octree)
+  size_t ot_smem_bytes;    // octree: dynamic shared memory per CTA
 };
 
 void launch_pyramid(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, uint8_t* d_pyr, cudaStream_t st,
                     long long* launches);
 void launch_fast(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, const uint8_t* d_pyr, uint32_t* d_cand,
                  int* d_cell_count, cudaStream_t st, long long* launches);
-size_t octree_smem_bytes(const OrbGeom& g);
-cudaError_t prepare_octree(const OrbGeom& g);
+cudaError_t prepare_octree(OrbGeomHost& gh);  // resolves gh.ot_smem_* and raises the kernel's opt-in limit
 cudaError_t prepare_pyramid(const OrbGeom& g);
 void launch_octree(const OrbGeomHost& gh, int n_frames, const uint32_t* d_cand, const int* d_cell_count,
                    uint32_t* d_keys, uint16_t* d_knode, uint32_t* d_sel, int* d_sel_count, cudaStream_t st,

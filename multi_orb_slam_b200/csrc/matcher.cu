@@ -8,6 +8,7 @@
 // integer POPC issue rate (16 lanes/clk/SM), not by HBM: descriptors are tiny and stay on chip.
 // Order-dependent reference loops are split into a parallel phase (grid lookup + distances,
 // candidates kept in the reference's traversal order) and an ordered resolve phase.
+#include "device_guard.h"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -713,8 +714,9 @@ __global__ void __launch_bounds__(256) k_undistort(const orbx_keypoint* __restri
 __global__ void __launch_bounds__(256) k_stereo_rgbd(const orbx_keypoint* __restrict__ kps,
                                                      const orbx_keypoint* __restrict__ kps_un,
                                                      const int32_t* __restrict__ counts, int cap,
-                                                     const float* __restrict__ depth, size_t row_stride, size_t frame_stride,
-                                                     float mbf, float* __restrict__ uright, float* __restrict__ depth_out) {
+                                                     const float* __restrict__ depth, int cols, int rows, size_t row_stride,
+                                                     size_t frame_stride, float mbf, float* __restrict__ uright,
+                                                     float* __restrict__ depth_out) {
   const int frame = blockIdx.y;
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= cap) return;
@@ -722,7 +724,11 @@ __global__ void __launch_bounds__(256) k_stereo_rgbd(const orbx_keypoint* __rest
   float ur = -1.f, dz = -1.f;
   if (i < min(counts[frame], cap)) {
     const orbx_keypoint kp = kps[o];
-    const float d = depth[(size_t)frame * frame_stride + (size_t)(int)kp.y * row_stride + (int)kp.x];
+    // a keypoint outside the depth image (a depth map smaller than the extraction image) has no depth; the
+    // reference's cv::Mat::at would read out of bounds here
+    const int px = (int)kp.x, py = (int)kp.y;
+    const float d = (px >= 0 && px < cols && py >= 0 && py < rows)
+                        ? depth[(size_t)frame * frame_stride + (size_t)py * row_stride + px] : -1.f;
     if (d > 0) {
       dz = d;
       ur = __fsub_rn(kps_un[o].x, __fdiv_rn(mbf, d));
@@ -1205,7 +1211,9 @@ __global__ void __launch_bounds__(256) k_tri_finish(const BowQuery* __restrict__
 // Phase A (warp per map point, whole grid): window query at levels [pred-1, pred], stereo gate
 // (:111-116), distances; candidates kept in traversal order as dist<<20 | octave<<16 | idx.
 // `count_only` pass sizes the ragged rows, then a scan gives row offsets.
-__device__ __forceinline__ float radius_by_viewing_cos(float view_cos) { return view_cos > 0.998f ? 2.5f : 4.0f; }
+// :151-157 compares the float against the DOUBLE literal 0.998; (float)0.998 rounds up to 0.99800003, so
+// view_cos == 0.998f is "greater" there: compare in double
+__device__ __forceinline__ float radius_by_viewing_cos(float view_cos) { return (double)view_cos > 0.998 ? 2.5f : 4.0f; }
 
 __global__ void __launch_bounds__(256) k_proj_candidates(const orbx_keypoint* __restrict__ k, const uint8_t* __restrict__ desc,
                                                          const float* __restrict__ u_right, orbm_bounds b,
@@ -1743,8 +1751,10 @@ int orbm_create(int device, orbm_matcher** out) {
     delete m;
     return ORBX_E_CUDA;
   }
-  if (device >= 0 && !m->check(cudaSetDevice(device), "cudaSetDevice")) { g_mcreate_error = m->err; delete m; return ORBX_E_CUDA; }
+  if (device >= ndev) { g_mcreate_error = "no such CUDA device"; delete m; return ORBX_E_CUDA; }
   cudaGetDevice(&m->device);
+  if (device >= 0) m->device = device;
+  OrbDeviceGuard dev_guard(m->device);  // the caller's current device is restored on return
   if (!m->check(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
     g_mcreate_error = m->err;
     delete m;
@@ -1780,7 +1790,7 @@ int orbm_set_stream(orbm_matcher* m, void* cuda_stream) {
 int orbm_distance_pairs_host(orbm_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* out) {
   if (!m || !a || !b || !out || n < 0) return ORBX_E_INVALID;
   if (n == 0) return ORBX_OK;
-  cudaSetDevice(m->device);
+  OrbDeviceGuard dev_guard(m->device);
   uint8_t* da = m->scratch<uint8_t>(1, (size_t)n * 32);
   uint8_t* db = m->scratch<uint8_t>(2, (size_t)n * 32);
   int32_t* dout = m->scratch<int32_t>(3, n);
@@ -1796,7 +1806,7 @@ int orbm_distance_pairs_host(orbm_matcher* m, const uint8_t* a, const uint8_t* b
 int orbm_bruteforce_device(orbm_matcher* m, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, float ratio,
                            int th_dist, int32_t* d_idx, int32_t* d_d1, int32_t* d_d2) {
   if (!m || nq < 0 || nt < 0 || (nq && (!d_q || !d_idx || !d_d1 || !d_d2)) || (nt && !d_t)) return ORBX_E_INVALID;
-  cudaSetDevice(m->device);
+  OrbDeviceGuard dev_guard(m->device);
   return bf_launch(m, d_q, nq, d_t, nt, ratio, th_dist, d_idx, d_d1, d_d2);
 }
 
@@ -1804,7 +1814,7 @@ int orbm_bruteforce_host(orbm_matcher* m, const uint8_t* q, int nq, const uint8_
                          int32_t* idx, int32_t* d1, int32_t* d2) {
   if (!m || nq < 0 || nt < 0 || (nq && (!q || !idx || !d1 || !d2)) || (nt && !t)) return ORBX_E_INVALID;
   if (nq == 0) return ORBX_OK;
-  cudaSetDevice(m->device);
+  OrbDeviceGuard dev_guard(m->device);
   uint8_t* dq = m->scratch<uint8_t>(1, (size_t)nq * 32);
   uint8_t* dt = m->scratch<uint8_t>(2, (size_t)nt * 32);
   int32_t* dres = m->scratch<int32_t>(3, (size_t)nq * 3);
@@ -1826,7 +1836,7 @@ int orbm_bruteforce_batch_device(orbm_matcher* m, int n_pairs, int cap, const ui
       (q_stride & 15) || (t_stride & 15))
     return ORBX_E_INVALID;
   if (n_pairs == 0) return ORBX_OK;
-  cudaSetDevice(m->device);
+  OrbDeviceGuard dev_guard(m->device);
   const int qblocks = (cap + BF_THREADS * BF_QPT - 1) / (BF_THREADS * BF_QPT);
   for (int p0 = 0; p0 < n_pairs; p0 += 65535) {
     const int np = std::min(65535, n_pairs - p0);
@@ -1845,7 +1855,7 @@ int orbm_search_for_initialization_device(orbm_matcher* m, int n_pairs, int cap,
                                           int32_t* d_matches12, int32_t* d_nmatches) {
   if (!m || n_pairs < 0 || cap < 1 || cap > 65535) return ORBX_E_INVALID;
   if (n_pairs == 0) return ORBX_OK;
-  cudaSetDevice(m->device);
+  OrbDeviceGuard dev_guard(m->device);
   const size_t smem = sizeof(int) * 9 * (size_t)cap + sizeof(uint32_t) * INIT_SMEM_CAND;
   if (smem > 200 * 1024) { m->err = "cap too large for SearchForInitialization"; return ORBX_E_INVALID; }
   // candidate rows are cap x cap per pair: process pairs in groups that keep the scratch <= ~2 GiB
@@ -1880,7 +1890,7 @@ int orbm_search_for_initialization_host(orbm_matcher* m, int n_pairs, int cap, c
                                         int32_t* matches12, int32_t* nmatches) {
   if (!m || n_pairs < 0 || cap < 1) return ORBX_E_INVALID;
   if (n_pairs == 0) return ORBX_OK;
-  cudaSetDevice(m->device);
+  OrbDeviceGuard dev_guard(m->device);
   const size_t nk = (size_t)n_pairs * cap;
   orbx_keypoint* dk = m->scratch<orbx_keypoint>(8, 2 * nk);
   uint8_t* dd = m->scratch<uint8_t>(9, 2 * nk * 32);
@@ -1921,7 +1931,7 @@ int orbm_search_by_projection_points_host(orbm_matcher* m, const orbx_keypoint* 
       m->err = "map point level out of range";
       return ORBX_E_INVALID;
     }
-  cudaSetDevice(m->device);
+  OrbDeviceGuard dev_guard(m->device);
   cudaStream_t st = m->stream;
   // frame side
   const size_t frame_bytes = (size_t)n * (sizeof(orbx_keypoint) + 32 + 4 + 4 + 4 + 1) + 64 * 4;
@@ -2057,7 +2067,7 @@ int orbm_search_by_bow_batch_host(orbm_matcher* m, orbm_bow_pair* pairs, int n_p
       o2 += P.n2;
     }
   }
-  cudaSetDevice(m->device);
+  OrbDeviceGuard dev_guard(m->device);
   cudaStream_t st = m->stream;
   uint8_t* dd = m->scratch<uint8_t>(8, (G1 + G2) * 32 + G2 + 64);
   float* dang = m->scratch<float>(9, G1 + G2);
@@ -2209,7 +2219,7 @@ int orbm_search_for_triangulation_batch_host(orbm_matcher* m, orbm_tri_pair* pai
       o2 += P.n2;
     }
   }
-  cudaSetDevice(m->device);
+  OrbDeviceGuard dev_guard(m->device);
   cudaStream_t st = m->stream;
   uint8_t* sb = m->scratch<uint8_t>(8, G * (32 + sizeof(orbx_keypoint) + 12) + 256);
   int32_t* dints = m->scratch<int32_t>(4, items2.size() + G1 + nq + (size_t)n_pairs * (HISTO_LENGTH + 2) + 8);
@@ -2288,7 +2298,7 @@ int orbm_compute_distinctive_descriptors_host(orbm_matcher* m, const uint8_t* de
     if (big_total > 0x7FFFFFFFu) { m->err = "descriptor sets too large"; return ORBX_E_CAPACITY; }
     n_max = std::max(n_max, std::min(N, DD_SMEM_N));
   }
-  cudaSetDevice(m->device);
+  OrbDeviceGuard dev_guard(m->device);
   cudaStream_t st = m->stream;
   uint8_t* dd = m->scratch<uint8_t>(8, (size_t)std::max(total, 1) * 32);
   int32_t* dints = m->scratch<int32_t>(4, (size_t)3 * n_points + 2);
@@ -2333,7 +2343,7 @@ int orbm_undistort_keypoints_device(orbm_matcher* m, int n_frames, int cap, cons
   if (!m || n_frames < 0 || cap < 1 || !d_kps || !d_counts || !dist5 || !d_kps_un || fx == 0.f || fy == 0.f)
     return ORBX_E_INVALID;
   if (n_frames == 0) return ORBX_OK;
-  cudaSetDevice(m->device);
+  OrbDeviceGuard dev_guard(m->device);
   k_undistort<<<dim3((cap + 255) / 256, n_frames), 256, 0, m->stream>>>(d_kps, d_counts, 0, cap,
                                                                         undistort_params(fx, fy, cx, cy, dist5),
                                                                         dist5[0] == 0.0f, d_kps_un);  // :675-679
@@ -2345,7 +2355,7 @@ int orbm_undistort_keypoints_host(orbm_matcher* m, const orbx_keypoint* k, int n
                                   const float* dist5, orbx_keypoint* k_un) {
   if (!m || n < 0 || (n && (!k || !k_un)) || !dist5 || fx == 0.f || fy == 0.f) return ORBX_E_INVALID;
   if (n == 0) return ORBX_OK;
-  cudaSetDevice(m->device);
+  OrbDeviceGuard dev_guard(m->device);
   cudaStream_t st = m->stream;
   orbx_keypoint* d = m->scratch<orbx_keypoint>(8, 2 * (size_t)n);
   if (!d) return ORBX_E_CUDA;
@@ -2381,11 +2391,12 @@ int orbm_compute_stereo_from_rgbd_device(orbm_matcher* m, int n_frames, int cap,
                                          int cols, int rows, size_t row_stride_floats, size_t frame_stride_floats, float mbf,
                                          float* d_uright, float* d_depth_out) {
   if (!m || n_frames < 0 || cap < 1 || !d_kps || !d_kps_un || !d_counts || !d_depth || !d_uright || !d_depth_out ||
-      cols < 1 || rows < 1 || row_stride_floats < (size_t)cols)
+      cols < 1 || rows < 1 || row_stride_floats < (size_t)cols ||
+      (n_frames > 1 && frame_stride_floats < (size_t)rows * row_stride_floats))
     return ORBX_E_INVALID;
   if (n_frames == 0) return ORBX_OK;
-  cudaSetDevice(m->device);
-  k_stereo_rgbd<<<dim3((cap + 255) / 256, n_frames), 256, 0, m->stream>>>(d_kps, d_kps_un, d_counts, cap, d_depth,
+  OrbDeviceGuard dev_guard(m->device);
+  k_stereo_rgbd<<<dim3((cap + 255) / 256, n_frames), 256, 0, m->stream>>>(d_kps, d_kps_un, d_counts, cap, d_depth, cols, rows,
                                                                           row_stride_floats, frame_stride_floats, mbf,
                                                                           d_uright, d_depth_out);
   m->launches += 1;
@@ -2401,7 +2412,7 @@ int orbm_compute_stereo_matches_device(orbm_matcher* m, const orbx_pyramid_view*
       left->nlevels < 1 || n_frames > left->n_frames || n_frames > right->n_frames)
     return ORBX_E_INVALID;
   if (n_frames == 0) return ORBX_OK;
-  cudaSetDevice(m->device);
+  OrbDeviceGuard dev_guard(m->device);
   int32_t* sad = m->scratch<int32_t>(8, (size_t)n_frames * cap_l);
   if (!sad) return ORBX_E_CUDA;
   // the keypoints and pyramids come from the extractors' streams: order this stream after them
@@ -2428,7 +2439,7 @@ int orbm_assign_features_to_grid_device(orbm_matcher* m, int n_frames, int cap, 
       !(bounds.max_x > bounds.min_x) || !(bounds.max_y > bounds.min_y))
     return ORBX_E_INVALID;
   if (n_frames == 0) return ORBX_OK;
-  cudaSetDevice(m->device);
+  OrbDeviceGuard dev_guard(m->device);
   k_build_grid<<<n_frames, 256, 0, m->stream>>>(d_kps_un, d_counts, 0, cap, bounds, d_cell_start, d_items);
   m->launches += 1;
   return m->check(cudaGetLastError(), "grid launch") ? ORBX_OK : ORBX_E_CUDA;
@@ -2600,7 +2611,7 @@ int run_projected(orbm_matcher* m, const orbx_keypoint* k, const uint8_t* desc, 
   *nmatches = 0;
   const int nq = (int)q.size();
   if (n == 0 || nq == 0) return ORBX_OK;
-  cudaSetDevice(m->device);
+  OrbDeviceGuard dev_guard(m->device);
   cudaStream_t st = m->stream;
   const size_t frame_bytes = (size_t)n * (32 + sizeof(orbx_keypoint) + 4 + 4 + 4 + 4 + 1) + 256;
   uint8_t* fb = m->scratch<uint8_t>(8, frame_bytes);
@@ -2867,7 +2878,7 @@ int fuse_run(orbm_matcher* m, const orbx_keypoint* kf_k, const uint8_t* kf_desc,
              const float* inv_level_sigma2, int nlevels, int gate, int32_t* best_idx, int* n_fused, int th_dist = TH_LOW) {
   const int nq = (int)q.size();
   if (nq == 0) return ORBX_OK;
-  cudaSetDevice(m->device);
+  OrbDeviceGuard dev_guard(m->device);
   cudaStream_t st = m->stream;
   uint8_t* fb = m->scratch<uint8_t>(8, (size_t)n_kf * (32 + sizeof(orbx_keypoint) + 8) + 256);
   uint8_t* qb = m->scratch<uint8_t>(9, (size_t)n_mp * (32 + 8) + (size_t)nq * sizeof(ProjQuery) + 256);
@@ -3202,7 +3213,7 @@ int orbm_set_vocabulary(orbm_matcher* m, const int32_t* child_start, const int32
   for (int c = 0; c < n_children; ++c)
     if (child_ids[c] <= 0 || child_ids[c] >= n_nodes) { m->err = "vocabulary: child id out of range"; return ORBX_E_INVALID; }
   if (child_start[1] == 0) { m->err = "vocabulary: the root has no children"; return ORBX_E_INVALID; }
-  cudaSetDevice(m->device);
+  OrbDeviceGuard dev_guard(m->device);
   cudaStreamSynchronize(m->stream);
   cudaFree(m->voc_child_start); cudaFree(m->voc_child_ids); cudaFree(m->voc_desc);
   m->voc_child_start = m->voc_child_ids = nullptr; m->voc_desc = nullptr; m->voc_nodes = 0;
@@ -3229,7 +3240,7 @@ int orbm_bow_transform_host(orbm_matcher* m, const uint8_t* desc, int n, int lev
   *n_bow = *n_fv = 0;
   fv_start[0] = 0;
   if (n == 0) return ORBX_OK;
-  cudaSetDevice(m->device);
+  OrbDeviceGuard dev_guard(m->device);
   cudaStream_t st = m->stream;
   uint8_t* dd = m->scratch<uint8_t>(8, (size_t)n * 32);
   int32_t* dout = m->scratch<int32_t>(4, 2 * (size_t)n);

@@ -158,6 +158,30 @@ def test_search_by_projection_points_vs_oracle(M, O, nmp, th, with_stereo, with_
     assert rn > nmp // 20
 
 
+def test_search_by_projection_points_view_cos_boundary(M, O):
+    """RadiusByViewingCos (src/ORBmatcher.cc:151-157) compares the float against the double literal 0.998:
+    view_cos == float32(0.998) = 0.99800003 counts as greater (radius 2.5), float32 just below does not (4.0)."""
+    from multi_orb_slam_b200.matcher import Frame, MapPoints, ORBmatcher
+    k, d, mp, mpd, rng = _projection_case(O, 6, 4000)
+    edge = np.float32(0.998)
+    mp["view_cos"][::2] = edge
+    mp["view_cos"][1::4] = np.nextafter(edge, np.float32(0))
+    sf = O.extractor("port").scale_tables()[0]
+    n, nmp = len(k), len(mp)
+    ur = np.full(n, -1, np.float32)
+    obs = np.ones(nmp, np.int32)
+    fmp0, fobs0 = np.full(n, -1, np.int32), np.zeros(n, np.int32)
+    rn, rfmp = O.search_by_projection_points(k, d, ur, (0, 1241, 0, 376), sf, mp, mpd, obs, 3.0, 0.8, fmp0, fobs0)
+    F = Frame(k, d, 1241, 376, mvScaleFactors=sf, mvuRight=ur, mvpMapPoints=fmp0.copy(), mvpMapPointsObserved=fobs0)
+    gn = ORBmatcher(0.8, True).SearchByProjection(F, MapPoints(mp, mpd, obs), 3.0)
+    assert gn == rn and np.array_equal(F.mvpMapPoints, rfmp)
+    # the boundary matters on this case: widening the edge points' window to 4.0 changes the oracle's answer
+    mp2 = mp.copy()
+    mp2["view_cos"][::2] = np.nextafter(edge, np.float32(0))
+    rn2, rfmp2 = O.search_by_projection_points(k, d, ur, (0, 1241, 0, 376), sf, mp2, mpd, obs, 3.0, 0.8, fmp0, fobs0)
+    assert not np.array_equal(rfmp2, rfmp)
+
+
 @pytest.mark.parametrize("reps,th", [(2, 3.0), (6, 6.0)])
 def test_search_by_projection_points_contended(M, O, reps, th):
     """Every map point repeated `reps` times (same projection and descriptor, mixed Observations()): consecutive points
