@@ -168,6 +168,15 @@ int orbm_bruteforce_batch_device(orbm_matcher* m, int n_pairs, int cap, const ui
                                  size_t q_stride, const uint8_t* d_t, const int32_t* d_nt, size_t t_stride, float ratio,
                                  int th_dist, int32_t* d_idx, int32_t* d_d1, int32_t* d_d2);
 
+/* The same scan for pairs whose rows lie anywhere inside ONE device buffer — the all-gathered per-camera blocks
+ * of a multi-GPU rig (orbd_allgather_inplace below): pair p takes its query rows at d_base + d_q_off[p], its
+ * target rows at d_base + d_t_off[p] and its two row counts (int32) at d_base + d_nq_off[p] / d_nt_off[p]; all
+ * offsets in bytes, rows 16-byte aligned.  One launch for all camera pairs and rig-frames of a chunk
+ * (src/ORBmatcher.cc:628,3582 loop over the cameras of mDescriptors_total).  Results at [p*cap + i]. */
+int orbm_bruteforce_indexed_device(orbm_matcher* m, int n_pairs, int cap, const uint8_t* d_base, const int64_t* d_q_off,
+                                   const int64_t* d_t_off, const int64_t* d_nq_off, const int64_t* d_nt_off, float ratio,
+                                   int th_dist, int32_t* d_idx, int32_t* d_d1, int32_t* d_d2);
+
 /* Frame grid bounds mnMinX/mnMaxX/mnMinY/mnMaxY (src/Frame.cc:262-278). */
 typedef struct {
   float min_x, max_x, min_y, max_y;
@@ -453,6 +462,30 @@ typedef struct {
 } orbm_tri_pair;
 int orbm_search_for_triangulation_batch_host(orbm_matcher* m, orbm_tri_pair* pairs, int n_pairs, int nlevels, int only_stereo,
                                              const int32_t* cam_enabled, int check_ori);
+
+/* ---- multi-GPU: the one collective of the path ------------------------------------------------------------
+ * One process per GPU.  Camera streams are dealt over the ranks; every rank extracts its cameras and the
+ * per-camera blocks (counts, keypoints, descriptors of a chunk of rig-frames) of ALL cameras are all-gathered so
+ * that each rank can match its share of rig-frames across cameras: the multi-GPU form of
+ * Frame::mDescriptors_total (src/Frame.cc:170,191-194), which the reference builds by concatenating the cameras'
+ * descriptors on its single device.  The extractor writes straight into the rank's slot of the gather buffer
+ * (orbx_extract_batch_device takes any device pointers), so the exchange is ONE in-place NCCL all-gather per
+ * chunk, asynchronous on the caller's stream.  NCCL is bound at run time (dlopen "libnccl.so.2", or the path in
+ * $ORB_NCCL_LIB); ORBX_E_STATE when it cannot be loaded. */
+#define ORBD_UNIQUE_ID_BYTES 128
+typedef struct orbd_comm orbd_comm;
+/* ncclGetUniqueId: call on one rank, distribute the 128 bytes to the others by the host's own means. */
+int orbd_get_unique_id(uint8_t* id128);
+/* ncclCommInitRank on `device` (-1 = current).  Collective: every rank of the job must call it. */
+int orbd_comm_create(int rank, int world, const uint8_t* id128, int device, orbd_comm** out);
+void orbd_comm_destroy(orbd_comm* c);
+int orbd_rank(const orbd_comm* c);
+int orbd_world(const orbd_comm* c);
+/* d_buf holds world * bytes_per_rank bytes; rank r's block is at d_buf + r*bytes_per_rank and must be complete on
+ * `cuda_stream` order.  After the call (stream order) every rank holds all blocks.  world == 1: no-op. */
+int orbd_allgather_inplace(orbd_comm* c, void* d_buf, size_t bytes_per_rank, void* cuda_stream);
+int orbd_nccl_version(void);
+const char* orbd_last_error(const orbd_comm* c);
 
 #ifdef __cplusplus
 }

@@ -105,6 +105,7 @@ _SIGS = {
     "orbm_bruteforce_device": (_i, [_vp, _vp, _i, _vp, _i, _f, _i, _vp, _vp, _vp]),
     "orbm_bruteforce_host": (_i, [_vp, _vp, _i, _vp, _i, _f, _i, _vp, _vp, _vp]),
     "orbm_bruteforce_batch_device": (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp, _vp, _sz, _f, _i, _vp, _vp, _vp]),
+    "orbm_bruteforce_indexed_device": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp]),
     "orbm_search_for_initialization_device": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, Bounds, _vp, _i, _f, _i,
                                                   _vp, _vp]),
     "orbm_search_for_initialization_host": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, Bounds, _vp, _i, _f, _i,
@@ -140,6 +141,14 @@ _SIGS = {
     "orbm_search_for_triangulation_batch_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
     "orbm_search_for_triangulation_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, FeatVec, _vp, _vp, _vp, _vp, _vp, _i,
                                                FeatVec, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, C.POINTER(_i)]),
+    "orbd_get_unique_id": (_i, [_vp]),
+    "orbd_comm_create": (_i, [_i, _i, _vp, _i, C.POINTER(_vp)]),
+    "orbd_comm_destroy": (None, [_vp]),
+    "orbd_rank": (_i, [_vp]),
+    "orbd_world": (_i, [_vp]),
+    "orbd_allgather_inplace": (_i, [_vp, _vp, _sz, _vp]),
+    "orbd_nccl_version": (_i, []),
+    "orbd_last_error": (C.c_char_p, [_vp]),
 }
 EXPORTS = tuple(_SIGS)
 for _name, (_res, _args) in _SIGS.items():
@@ -155,6 +164,11 @@ def check_x(handle, rc: int) -> None:
 def check_m(handle, rc: int) -> None:
     if rc != OK:
         raise OrbError(rc, (lib.orbm_last_error(handle) or b"").decode())
+
+
+def check_d(handle, rc: int) -> None:
+    if rc != OK:
+        raise OrbError(rc, (lib.orbd_last_error(handle) or b"").decode())
 
 
 def ptr(a) -> int:

@@ -128,17 +128,12 @@ __global__ void k_bf_merge(const uint2* __restrict__ partial, int nq, int nsplit
 // (camera c, camera c') of one rig-frame).  Pair p matches rows q + p*q_stride (nq[p] valid)
 // against rows t + p*t_stride (nt[p] valid); results are strided by `cap`.  One CTA per
 // (256-query tile, pair); all targets of the pair stream through shared memory, so no merge pass.
-__global__ void __launch_bounds__(BF_THREADS) k_bruteforce_batch(const uint8_t* __restrict__ q, const int32_t* __restrict__ nq_arr,
-                                                                 size_t q_stride, const uint8_t* __restrict__ t,
-                                                                 const int32_t* __restrict__ nt_arr, size_t t_stride, int cap,
-                                                                 float ratio, int th_dist, int32_t* __restrict__ out_idx,
-                                                                 int32_t* __restrict__ out_d1, int32_t* __restrict__ out_d2) {
+__device__ __forceinline__ void bf_pair_body(const uint8_t* __restrict__ qp, int nq, const uint8_t* __restrict__ tp, int nt,
+                                             int pair, int cap, float ratio, int th_dist, int32_t* __restrict__ out_idx,
+                                             int32_t* __restrict__ out_d1, int32_t* __restrict__ out_d2) {
   __shared__ uint4 s_t[BF_TILE * 2];
-  const int pair = blockIdx.y, tid = threadIdx.x;
-  const int nq = min(nq_arr[pair], cap), nt = min(nt_arr[pair], cap);
+  const int tid = threadIdx.x;
   if ((int)(blockIdx.x * BF_QPT * BF_THREADS) >= nq) return;
-  const uint8_t* qp = q + (size_t)pair * q_stride;
-  const uint8_t* tp = t + (size_t)pair * t_stride;
   uint4 qa[BF_QPT], qb[BF_QPT];
   uint32_t best[BF_QPT], second[BF_QPT];
 #pragma unroll
@@ -180,6 +175,32 @@ __global__ void __launch_bounds__(BF_THREADS) k_bruteforce_batch(const uint8_t* 
       out_idx[o] = (bi >= 0 && b <= th_dist && (float)b < __fmul_rn((float)sc, ratio)) ? bi : -1;
     }
   }
+}
+
+__global__ void __launch_bounds__(BF_THREADS) k_bruteforce_batch(const uint8_t* __restrict__ q, const int32_t* __restrict__ nq_arr,
+                                                                 size_t q_stride, const uint8_t* __restrict__ t,
+                                                                 const int32_t* __restrict__ nt_arr, size_t t_stride, int cap,
+                                                                 float ratio, int th_dist, int32_t* __restrict__ out_idx,
+                                                                 int32_t* __restrict__ out_d1, int32_t* __restrict__ out_d2) {
+  const int pair = blockIdx.y;
+  bf_pair_body(q + (size_t)pair * q_stride, min(nq_arr[pair], cap), t + (size_t)pair * t_stride, min(nt_arr[pair], cap), pair,
+               cap, ratio, th_dist, out_idx, out_d1, out_d2);
+}
+
+// The same scan for pairs whose rows sit anywhere inside one buffer (the all-gathered per-camera blocks of a rig,
+// multi_orb_slam_b200/dist.py): pair p reads its query / target rows and its two counts at byte offsets from `base`.
+__global__ void __launch_bounds__(BF_THREADS) k_bruteforce_indexed(const uint8_t* __restrict__ base,
+                                                                   const long long* __restrict__ q_off,
+                                                                   const long long* __restrict__ t_off,
+                                                                   const long long* __restrict__ nq_off,
+                                                                   const long long* __restrict__ nt_off, int cap, float ratio,
+                                                                   int th_dist, int32_t* __restrict__ out_idx,
+                                                                   int32_t* __restrict__ out_d1, int32_t* __restrict__ out_d2) {
+  const int pair = blockIdx.y;
+  const int nq = *reinterpret_cast<const int32_t*>(base + nq_off[pair]);
+  const int nt = *reinterpret_cast<const int32_t*>(base + nt_off[pair]);
+  bf_pair_body(base + q_off[pair], min(nq, cap), base + t_off[pair], min(nt, cap), pair, cap, ratio, th_dist, out_idx, out_d1,
+               out_d2);
 }
 
 // ---- frame grid ------------------------------------------------------------------------------
@@ -1846,6 +1867,28 @@ int orbm_bruteforce_batch_device(orbm_matcher* m, int n_pairs, int cap, const ui
     m->launches++;
   }
   return m->check(cudaGetLastError(), "bruteforce batch launch") ? ORBX_OK : ORBX_E_CUDA;
+}
+
+int orbm_bruteforce_indexed_device(orbm_matcher* m, int n_pairs, int cap, const uint8_t* d_base, const int64_t* d_q_off,
+                                   const int64_t* d_t_off, const int64_t* d_nq_off, const int64_t* d_nt_off, float ratio,
+                                   int th_dist, int32_t* d_idx, int32_t* d_d1, int32_t* d_d2) {
+  if (!m || n_pairs < 0 || cap < 1 || cap > 65535 ||
+      (n_pairs && (!d_base || !d_q_off || !d_t_off || !d_nq_off || !d_nt_off || !d_idx || !d_d1 || !d_d2)) ||
+      (reinterpret_cast<uintptr_t>(d_base) & 15))
+    return ORBX_E_INVALID;
+  if (n_pairs == 0) return ORBX_OK;
+  OrbDeviceGuard dev_guard(m->device);
+  const int qblocks = (cap + BF_THREADS * BF_QPT - 1) / (BF_THREADS * BF_QPT);
+  static_assert(sizeof(long long) == sizeof(int64_t), "offset tables are 64-bit");
+  for (int p0 = 0; p0 < n_pairs; p0 += 65535) {
+    const int np = std::min(65535, n_pairs - p0);
+    k_bruteforce_indexed<<<dim3(qblocks, np), BF_THREADS, 0, m->stream>>>(
+        d_base, reinterpret_cast<const long long*>(d_q_off) + p0, reinterpret_cast<const long long*>(d_t_off) + p0,
+        reinterpret_cast<const long long*>(d_nq_off) + p0, reinterpret_cast<const long long*>(d_nt_off) + p0, cap, ratio, th_dist,
+        d_idx + (size_t)p0 * cap, d_d1 + (size_t)p0 * cap, d_d2 + (size_t)p0 * cap);
+    m->launches++;
+  }
+  return m->check(cudaGetLastError(), "bruteforce indexed launch") ? ORBX_OK : ORBX_E_CUDA;
 }
 
 int orbm_search_for_initialization_device(orbm_matcher* m, int n_pairs, int cap, const orbx_keypoint* d_k1,

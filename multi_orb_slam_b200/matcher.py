@@ -125,6 +125,18 @@ class ORBmatcher:
             self._h, P, cap, q.data_ptr(), nq.data_ptr(), q.stride(0), t.data_ptr(), nt.data_ptr(), t.stride(0),
             self.mfNNratio if ratio is None else ratio, th_dist, idx.data_ptr(), d1.data_ptr(), d2.data_ptr()))
 
+    def bruteforce_indexed_device(self, base, tables, idx, d1, d2, cap: int, th_dist: int = TH_LOW,
+                                  ratio: Optional[float] = None):
+        """Pairs addressed by byte offsets inside one device buffer (dist.RigLayout.match_tables): base uint8 CUDA
+        tensor, tables int64 CUDA tensor [4, P] (query rows, target rows, query count, target count), idx/d1/d2
+        [P, cap] i32.  One launch for all pairs.  Asynchronous."""
+        P = tables.shape[1]
+        assert tables.shape[0] == 4 and tables.is_contiguous() and idx.shape[0] >= P and idx.shape[1] == cap
+        check_m(self._h, lib.orbm_bruteforce_indexed_device(
+            self._h, P, cap, base.data_ptr(), tables[0].data_ptr(), tables[1].data_ptr(), tables[2].data_ptr(),
+            tables[3].data_ptr(), self.mfNNratio if ratio is None else ratio, th_dist, idx.data_ptr(), d1.data_ptr(),
+            d2.data_ptr()))
+
     # -- SearchForInitialization (src/ORBmatcher.cc:868-983) --------------------------------------
     def SearchForInitialization(self, F1: Frame, F2: Frame, vbPrevMatched: np.ndarray, windowSize: int = 10):
         """Returns (nmatches, vnMatches12); vbPrevMatched ([N1,2] f32) is updated in place."""

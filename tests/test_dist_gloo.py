@@ -67,3 +67,64 @@ def test_allgather_camera_blocks_world2():
             assert p.exitcode == 0
         assert ret[0][0] and ret[1][0]
         assert (ret[0][1], ret[0][2], ret[1][1], ret[1][2]) == (0, 2, 2, 3)
+
+
+def test_rig_layout_blocks_and_tables():
+    from multi_orb_slam_b200.dist import RigLayout
+    L = RigLayout(8, 4, 5, 7)
+    assert L.per == 2 and L.bytes_per_rank == 2 * L.block_bytes and L.total_bytes == 8 * L.block_bytes
+    # rank r's cameras r, r+4 occupy blocks 2r, 2r+1: its send slot is contiguous
+    assert [L.block_of(c) for c in range(8)] == [0, 2, 4, 6, 1, 3, 5, 7]
+    for off in (L.off_kps, L.off_desc, L.block_bytes):
+        assert off % 256 == 0
+    buf = torch.zeros(L.total_bytes, dtype=torch.uint8)
+    for c in range(8):
+        counts, kps, desc = L.views(buf, c)
+        assert counts.shape == (5,) and kps.shape == (5, 7, 6) and desc.shape == (5, 7, 32)
+        counts[:] = 100 * c + torch.arange(5, dtype=torch.int32)
+        desc[:] = c
+    pairs = cross_camera_pairs(8)
+    t = L.match_tables(pairs, 1, 4)
+    assert t.shape == (4, 8 * 3)
+    raw = buf.numpy()
+    for pi, (a, b) in enumerate(pairs):
+        for f in range(1, 4):
+            p = pi * 3 + (f - 1)
+            assert raw[t[0, p]] == a and raw[t[1, p]] == b                      # descriptor rows of the right cameras
+            assert raw[t[2, p]:t[2, p] + 4].view(np.int32)[0] == 100 * a + f   # counts of the right frame
+            assert raw[t[3, p]:t[3, p] + 4].view(np.int32)[0] == 100 * b + f
+            assert t[0, p] % 16 == 0 and t[1, p] % 16 == 0
+
+
+def _rig_worker(rank, world, port, n_cams, chunk, cap, ret):
+    from multi_orb_slam_b200.dist import RigGather, RigLayout
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = RigLayout(n_cams, world, chunk, cap)
+        g = torch.Generator().manual_seed(1)
+        full = torch.randint(0, 256, (L.total_bytes,), dtype=torch.uint8, generator=g)  # what every rank must end with
+        buf = torch.zeros(L.total_bytes, dtype=torch.uint8)
+        for c in cameras_of(rank, n_cams, world):  # "extraction" fills only the rank's own camera blocks
+            o = L.block_offset(c)
+            buf[o:o + L.block_bytes] = full[o:o + L.block_bytes]
+        RigGather(rank, world, backend="torch").allgather_inplace(buf, L.bytes_per_rank)
+        ret[rank] = bool(torch.equal(buf, full))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rig_gather_inplace_world2():
+    world, n_cams, chunk, cap = 2, 4, 3, 5
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        ret = mgr.dict()
+        procs = [ctx.Process(target=_rig_worker, args=(r, world, port, n_cams, chunk, cap, ret)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+        assert ret[0] and ret[1]

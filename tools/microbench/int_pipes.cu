@@ -1,0 +1,128 @@
+// Integer-pipe throughput microbenchmark for sm_100a (B200): warp-instructions per clock per SM of the
+// instructions the ORB kernels are made of.  SURVEY.md 8(d) asks for the POPC rate that bounds Hamming
+// matching; the others calibrate the per-pixel instruction budgets quoted in DESIGN.md.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench/int_pipes tools/microbench/int_pipes.cu
+//   tools/microbench/int_pipes            (prints one JSON object)
+//
+// Method: every thread runs ITER iterations of 8 independent dependency chains of one instruction
+// (so latency is hidden by ILP x 32 warps/SM-quarter), 148*4 CTAs x 256 threads, timed with CUDA events;
+// the loop overhead (one IADD + one BRA per 8*UNROLL instructions) is < 2 %.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define ITER 2048
+#define UNROLL 8
+
+enum Op { POPC, LOP3, IADD3, IMAD, PRMT, SHF, VABSDIFF4, VIMNMX3, VIMNMX3_16, IDP4A, IDP2A, POPC_LOP, POPC_IMAD, HAMMING8,
+          LDS_U8, LDS_32, N_OPS };
+static const char* kNames[N_OPS] = {"popc", "lop3", "iadd3", "imad", "prmt", "shf_funnel", "vabsdiff4", "vimnmx3_s32",
+                                    "vimnmx3_s16x2", "idp4a", "idp2a", "popc+lop3 (1:1)", "popc+imad (1:1)",
+                                    "hamming256 (8 x xor+popc+add)", "lds_u8 (conflict-free)", "lds_b32 (conflict-free)"};
+
+template <int OP>
+__global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t seed) {
+  __shared__ uint32_t sm[1024];
+  for (int i = threadIdx.x; i < 1024; i += 256) sm[i] = i * 2654435761u;
+  __syncthreads();
+  uint32_t a[8], b = seed ^ threadIdx.x, c = seed * 3u + 1u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = seed + j * 977u + threadIdx.x;
+  for (int it = 0; it < ITER; ++it) {
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (OP == POPC) asm volatile("popc.b32 %0, %0;" : "+r"(a[j]));
+        else if (OP == LOP3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[j]) : "r"(b), "r"(c));
+        else if (OP == IADD3) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[j]) : "r"(b));
+        else if (OP == IMAD) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[j]) : "r"(b), "r"(c));
+        else if (OP == PRMT) asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(a[j]) : "r"(b), "r"(c));
+        else if (OP == SHF) asm volatile("shf.r.wrap.b32 %0, %0, %1, %2;" : "+r"(a[j]) : "r"(b), "r"(c));
+        else if (OP == VABSDIFF4) a[j] = __vabsdiffu4(a[j], b);
+        else if (OP == VIMNMX3) a[j] = (uint32_t)__vimin3_s32((int)a[j], (int)b, (int)c);
+        else if (OP == VIMNMX3_16) a[j] = __vimin3_s16x2(a[j], b, c);
+        else if (OP == IDP4A) a[j] = __dp4a(a[j], b, c);
+        else if (OP == IDP2A) a[j] = __dp2a_lo(a[j], b, c);
+        else if (OP == POPC_LOP) {
+          if (j & 1) asm volatile("popc.b32 %0, %0;" : "+r"(a[j]));
+          else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[j]) : "r"(b), "r"(c));
+        } else if (OP == POPC_IMAD) {
+          if (j & 1) asm volatile("popc.b32 %0, %0;" : "+r"(a[j]));
+          else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[j]) : "r"(b), "r"(c));
+        } else if (OP == HAMMING8) {
+          // one 256-bit pair per 8 (xor, popc, add) triples, the way k_bruteforce's inner loop is built
+          uint32_t x;
+          asm volatile("xor.b32 %0, %1, %2;" : "=r"(x) : "r"(a[j]), "r"(b));
+          asm volatile("popc.b32 %0, %0;" : "+r"(x));
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(a[j]) : "r"(x));
+        } else if (OP == LDS_U8) {
+          a[j] = reinterpret_cast<volatile uint8_t*>(sm)[(a[j] & 0xf80u) + threadIdx.x % 128];
+        } else if (OP == LDS_32) {
+          a[j] = reinterpret_cast<volatile uint32_t*>(sm)[(a[j] & 0x3e0u) + (threadIdx.x & 31)];
+        }
+      }
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += a[j];
+  if (s == 0x12345678u) out[0] = s;  // keeps the chains alive
+}
+
+template <int OP>
+double run(uint32_t* d_out, int sms, double clk_hz) {
+  const dim3 grid(sms * 4), block(256);
+  k<OP><<<grid, block>>>(d_out, 12345u);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int r = 0; r < 5; ++r) {
+    cudaEventRecord(e0);
+    k<OP><<<grid, block>>>(d_out, 12345u + r);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    best = ms < best ? ms : best;
+  }
+  const int per_chain = OP == HAMMING8 ? 3 : 1;
+  const double warp_instr = (double)grid.x * (block.x / 32) * ITER * UNROLL * 8 * per_chain;
+  return warp_instr / (best * 1e-3) / clk_hz / sms;  // warp-instructions per clock per SM
+}
+
+int main() {
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, 0) != cudaSuccess) { fprintf(stderr, "no CUDA device\n"); return 1; }
+  int clk_khz = 0;
+  cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
+  const double clk_hz = clk_khz * 1e3;
+  uint32_t* d_out;
+  cudaMalloc(&d_out, 64);
+  double r[N_OPS];
+  r[POPC] = run<POPC>(d_out, p.multiProcessorCount, clk_hz);
+  r[LOP3] = run<LOP3>(d_out, p.multiProcessorCount, clk_hz);
+  r[IADD3] = run<IADD3>(d_out, p.multiProcessorCount, clk_hz);
+  r[IMAD] = run<IMAD>(d_out, p.multiProcessorCount, clk_hz);
+  r[PRMT] = run<PRMT>(d_out, p.multiProcessorCount, clk_hz);
+  r[SHF] = run<SHF>(d_out, p.multiProcessorCount, clk_hz);
+  r[VABSDIFF4] = run<VABSDIFF4>(d_out, p.multiProcessorCount, clk_hz);
+  r[VIMNMX3] = run<VIMNMX3>(d_out, p.multiProcessorCount, clk_hz);
+  r[VIMNMX3_16] = run<VIMNMX3_16>(d_out, p.multiProcessorCount, clk_hz);
+  r[IDP4A] = run<IDP4A>(d_out, p.multiProcessorCount, clk_hz);
+  r[IDP2A] = run<IDP2A>(d_out, p.multiProcessorCount, clk_hz);
+  r[POPC_LOP] = run<POPC_LOP>(d_out, p.multiProcessorCount, clk_hz);
+  r[POPC_IMAD] = run<POPC_IMAD>(d_out, p.multiProcessorCount, clk_hz);
+  r[HAMMING8] = run<HAMMING8>(d_out, p.multiProcessorCount, clk_hz);
+  r[LDS_U8] = run<LDS_U8>(d_out, p.multiProcessorCount, clk_hz);
+  r[LDS_32] = run<LDS_32>(d_out, p.multiProcessorCount, clk_hz);
+  printf("{\"device\": \"%s\", \"sms\": %d, \"clock_mhz_nominal\": %.0f, \"unit\": \"warp-instructions per clock per SM "
+         "(x32 = lane-ops/clk/SM; clock = cudaDevAttrClockRate)\", \"rates\": {",
+         p.name, p.multiProcessorCount, clk_hz / 1e6);
+  for (int i = 0; i < N_OPS; ++i) printf("%s\"%s\": %.3f", i ? ", " : "", kNames[i], r[i]);
+  printf("}, \"popc_lanes_per_clk_per_sm\": %.2f, \"hamming256_pairs_per_clk_per_sm\": %.3f}\n", r[POPC] * 32,
+         r[HAMMING8] * 32 / 24.0);
+  return 0;
+}
