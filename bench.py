@@ -349,6 +349,253 @@ def widened_rows_leg(matcher, device, with_cpu):
     return out
 
 
+RIG8 = {"n_cams": 8, "w": 1280, "h": 720, "nfeatures": 1000, "bytes_per_frame": 16797777}  # SURVEY.md 8(d), K = 1000
+KITTI = {"w": 1241, "h": 376, "nfeatures": 2000, "bytes_per_frame": 10587233}
+
+
+def rig8_leg(args, world, rank, local_rank, dev, barrier, peak):
+    """BASELINE.json configs[4]: the 8-camera 1280x720 rig, one step = `rig8_frames` rig-frames of all 8 cameras
+    (4096 camera-frames by default) sharded over the ranks: extraction of the rank's cameras written straight into the
+    gather buffer, one in-place NCCL all-gather per chunk (through the C ABI) underneath the next chunk's extraction,
+    cross-camera brute-force matching of the rank's rig-frame share — all inside the timed region.  STRONG scaling:
+    the step is the same 4096 camera-frames at every N."""
+    import torch
+    import torch.distributed as dist
+    from multi_orb_slam_b200.rig import RigFrontEnd
+    from multi_orb_slam_b200.synth import camera_sequence
+    F, chunk, distinct = args.rig8_frames, args.rig8_chunk, args.rig8_distinct
+    fe = RigFrontEnd(RIG8["n_cams"], RIG8["nfeatures"], SCALE, NLEVELS, INI_TH, MIN_TH, image_size=(RIG8["w"], RIG8["h"]),
+                     rig_frames=F, chunk=chunk, rank=rank, world=world, device=local_rank, nnratio=NNRATIO, th_dist=50)
+    images = {}
+    for c in fe.cams:
+        base = torch.from_numpy(camera_sequence(RIG8["w"], RIG8["h"], distinct, 300 + c)).to(dev)
+        full = torch.empty((F, RIG8["h"], RIG8["w"]), dtype=torch.uint8, device=dev)
+        for i in range(0, F, distinct):  # every frame has its own HBM bytes (no L2 reuse across the tiled copies)
+            full[i:i + distinct] = base[: min(distinct, F - i)]
+        images[c] = full
+
+    def timed(steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            res = fe.step(images)
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, res
+
+    steps = max(3, min(args.steps, args.rig8_steps))
+    timed(max(3, args.warmup))
+    l0 = fe.launch_count
+    ms, res = timed(steps)
+    launches = (fe.launch_count - l0) // steps
+    out = {"workload": f"configs[4]: {RIG8['n_cams']} cameras x {F} rig-frames of {RIG8['w']}x{RIG8['h']} "
+                       f"({RIG8['n_cams'] * F} camera-frames per step, tiled from {distinct} distinct frames per camera), "
+                       f"nFeatures {RIG8['nfeatures']}; camera streams dealt over the ranks, chunks of {fe.chunk} rig-frames; "
+                       "cross-camera match = brute force camera c -> (c+1) mod 8, ratio 0.9, TH_LOW 50, rig-frames "
+                       "sharded over the ranks",
+           "scaling": "strong", "n_gpus": world, "steps": steps, "ms_per_step": ms,
+           "value": RIG8["n_cams"] * F / (ms * 1e-3), "unit": UNIT,
+           "cameras_per_rank": len(fe.cams), "chunks_per_step": fe.n_chunks, "gpu_launches_per_step": int(launches),
+           "collective": "one in-place ncclAllGather per chunk via orbd_allgather_inplace (C ABI), own stream"
+                         if world > 1 else "none (single rank)",
+           "inputs": "resident in HBM"}
+    gbs = RIG8["bytes_per_frame"] * RIG8["n_cams"] * F / (ms * 1e-3) / 1e9
+    out["roofline"] = {"bound": "hbm", "algorithmic_bytes_per_frame": RIG8["bytes_per_frame"], "achieved": round(gbs, 1),
+                       "peak": peak * world, "unit": "GB/s", "frac": round(gbs / (peak * world), 4)}
+    matched = sum(int((i >= 0).sum().item()) for i in res.idx)
+    rows = sum(hi - lo for _, lo, hi in res.shards) * len(fe.pairs)
+    out["cross_camera_matches_rank0"] = {"pair_frames": rows, "accepted": matched}
+    if world > 1:
+        # the collective alone (every chunk's all-gather back to back), and the step without it: exposed time
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        with torch.cuda.stream(fe.s_comm):
+            a0.record(fe.s_comm)
+            for _ in range(reps):
+                for k in range(fe.n_chunks):
+                    fe.gather.allgather_inplace(fe.bufs[k % fe.depth], fe.layout.bytes_per_rank, fe.s_comm.cuda_stream)
+            a1.record(fe.s_comm)
+        fe.s_comm.synchronize()
+        ag = torch.tensor([a0.elapsed_time(a1) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(ag, op=dist.ReduceOp.MAX)
+        ag_ms = float(ag.item())
+        # A/B, interleaved so that drift cancels: the step with and without its collective
+        with_g, without_g = [ms], []
+        for _ in range(3):
+            fe.skip_gather = True
+            without_g.append(timed(steps)[0])
+            fe.skip_gather = False
+            with_g.append(timed(steps)[0])
+        ms_nog = float(np.median(without_g))
+        exposed = max(0.0, float(np.median(with_g)) - ms_nog)
+        out["allgather"] = {"ms_per_step_alone": ag_ms, "bytes_per_rank_per_step": fe.layout.bytes_per_rank * fe.n_chunks,
+                            "algbw_GBps": fe.layout.bytes_per_rank * fe.n_chunks * (world - 1) / (ag_ms * 1e-3) / 1e9,
+                            "ms_per_step_without_collective": ms_nog, "exposed_ms": exposed,
+                            "overlap_frac": round(1.0 - min(1.0, exposed / ag_ms), 3) if ag_ms > 0 else None,
+                            "collective_share_of_step": round(exposed / ms, 4)}
+    fe.close()
+    return out
+
+
+def cpu_rig8_run(threads):
+    """CPU reference on a bounded sample of configs[4]: one rig-frame per camera pair of distinct frames (8 cameras x 2
+    rig-frames of 1280x720), extraction on all host cores, then the 16 cross-camera brute-force scans."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from concurrent.futures import ThreadPoolExecutor
+    from multi_orb_slam_b200.synth import camera_sequence
+    oracle_lib.build_oracle()
+    libkind = "ref" if oracle_lib.load("ref") is not None else "port"
+    n_rig = 8
+    seqs = [camera_sequence(RIG8["w"], RIG8["h"], n_rig, 300 + c) for c in range(RIG8["n_cams"])]
+    local = threading.local()
+
+    def extract(job):
+        c, f = job
+        if not hasattr(local, "ex"):
+            local.ex = oracle_lib.extractor(libkind, nfeatures=RIG8["nfeatures"], scale=SCALE, nlevels=NLEVELS, ini_th=INI_TH,
+                                            min_th=MIN_TH)
+        return local.ex.extract(seqs[c][f])[:2]
+
+    jobs = [(c, f) for f in range(n_rig) for c in range(RIG8["n_cams"])]
+    with ThreadPoolExecutor(threads) as pool:
+        list(pool.map(extract, jobs[:threads]))
+        t0 = time.perf_counter()
+        feats = dict(zip(jobs, pool.map(extract, jobs)))
+        list(pool.map(lambda j: oracle_lib.bruteforce(feats[j][1], feats[((j[0] + 1) % RIG8["n_cams"], j[1])][1], NNRATIO, 50), jobs))
+        dt = time.perf_counter() - t0
+    return {"value": len(jobs) / dt, "unit": UNIT, "cores": threads, "kind": "reference" if libkind == "ref" else "port",
+            "sample": f"{n_rig} rig-frames x {RIG8['n_cams']} cameras of 1280x720 + {len(jobs)} cross-camera scans, {dt:.2f} s wall"}
+
+
+def configs_leg(args, matcher, device, with_cpu, peak, sm_max):
+    """The other BASELINE.json configs as measured rows (single GPU): [0] single-frame latency through
+    ORBextractor::operator() (orbx_extract: host image in, host keypoints / descriptors out), [2] the brute-force
+    sweep 1k..64k, [3] KITTI-shape stereo extraction (1241x376, nFeatures 2000, left + right)."""
+    import torch
+    from multi_orb_slam_b200.extractor import ORBextractor
+    from multi_orb_slam_b200.synth import perturbed_descriptors, random_descriptors, stereo_pair, textured
+    dev = torch.device("cuda", device)
+    out = {}
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        oracle_lib.build_oracle()
+        libkind = "ref" if oracle_lib.load("ref") is not None else "port"
+
+    # ---- configs[0]: one 640x480 frame --------------------------------------------------------------
+    img = textured(W, H, 0)
+    ex1 = ORBextractor(NF0, SCALE, NLEVELS, INI_TH, MIN_TH, image_size=(W, H), max_batch=1, device=device)
+    for _ in range(10):
+        k0, _ = ex1(img)
+    ts = []
+    for _ in range(50):
+        t0 = time.perf_counter()
+        ex1(img)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    row = {"workload": "configs[0]: single 640x480 frame through ORBextractor::operator() (C ABI orbx_extract, pageable host "
+                       "image in, host keypoints + descriptors out, one frame per call)",
+           "latency_ms_median": float(np.median(ts)), "latency_ms_min": float(min(ts)), "keypoints": int(len(k0)),
+           "frames_per_s": 1e3 / float(np.median(ts))}
+    if with_cpu:
+        cpu = oracle_lib.extractor(libkind, nfeatures=NF0, scale=SCALE, nlevels=NLEVELS, ini_th=INI_TH, min_th=MIN_TH)
+        cpu.extract(img)
+        tc = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            cpu.extract(img)
+            tc.append((time.perf_counter() - t0) * 1e3)
+        row["cpu_1thread_ms"] = float(min(tc))
+        row["cpu_kind"] = "reference" if libkind == "ref" else "port"
+    out["configs0_single_frame"] = row
+
+    # ---- configs[2]: brute-force sweep --------------------------------------------------------------
+    popc_peak = 148 * 16 * sm_max * 1e6 / 8
+    A = random_descriptors(65536, 7)
+    Bq, _ = perturbed_descriptors(A, 8)
+    dA, dB = torch.from_numpy(A).to(dev), torch.from_numpy(Bq).to(dev)
+    sweep = []
+    torch.cuda.synchronize(dev)
+    st = torch.cuda.Stream(device=dev)  # the library runs on this stream; the events below are recorded on it
+    matcher.set_stream(st.cuda_stream)
+    for n in (1024, 2048, 4096, 8192, 16384, 32768, 65536):
+        idx, d1, d2 = (torch.empty((n,), dtype=torch.int32, device=dev) for _ in range(3))
+        reps = max(3, min(200, int(2e9 / (n * n))))
+        for _ in range(3):
+            matcher.bruteforce_device(dB[:n], dA[:n], idx, d1, d2, th_dist=50, ratio=0.9)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(reps):
+            matcher.bruteforce_device(dB[:n], dA[:n], idx, d1, d2, th_dist=50, ratio=0.9)
+        e1.record(st)
+        st.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        pairs = float(n) * n / (ms * 1e-3)
+        sweep.append({"n": n, "ms": round(ms, 4), "pairs_per_s": pairs, "frac_of_popc_peak": round(pairs / popc_peak, 4),
+                      "accepted": int((idx >= 0).sum().item())})
+    out["configs2_bruteforce_sweep"] = {"workload": "configs[2]: N x N 256-bit descriptors, ratio 0.9, TH_LOW 50, device-resident",
+                                        "popc_peak_pairs_per_s": popc_peak, "rows": sweep}
+
+    # ---- configs[3]: KITTI-shape stereo extraction ---------------------------------------------------
+    n_pairs = args.kitti_pairs
+    base = [stereo_pair(KITTI["w"], KITTI["h"], 900 + i) for i in range(min(n_pairs, 8))]
+    exl, exr = (ORBextractor(KITTI["nfeatures"], SCALE, NLEVELS, INI_TH, MIN_TH, image_size=(KITTI["w"], KITTI["h"]),
+                             max_batch=n_pairs, device=device) for _ in range(2))
+    imgs = []
+    for side in range(2):
+        b = torch.from_numpy(np.stack([p[side] for p in base])).to(dev)
+        full = torch.empty((n_pairs, KITTI["h"], KITTI["w"]), dtype=torch.uint8, device=dev)
+        for i in range(0, n_pairs, len(base)):
+            full[i:i + len(base)] = b[: min(len(base), n_pairs - i)]
+        imgs.append(full)
+    torch.cuda.synchronize(dev)  # the tiled copies above ran on torch's current stream
+    for e in (exl, exr):
+        e.set_stream(st.cuda_stream)
+    outs = [(torch.empty((n_pairs, e.capacity, 6), dtype=torch.float32, device=dev),
+             torch.empty((n_pairs, e.capacity, 32), dtype=torch.uint8, device=dev),
+             torch.empty((n_pairs,), dtype=torch.int32, device=dev)) for e in (exl, exr)]
+
+    def kitti_step():
+        exl.extract_batch_device(imgs[0], *outs[0])
+        exr.extract_batch_device(imgs[1], *outs[1])
+
+    for _ in range(3):
+        kitti_step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record(st)
+    for _ in range(reps):
+        kitti_step()
+    e1.record(st)
+    st.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    fps = 2 * n_pairs / (ms * 1e-3)
+    gbs = KITTI["bytes_per_frame"] * fps / 1e9
+    row = {"workload": f"configs[3]: {n_pairs} stereo pairs of {KITTI['w']}x{KITTI['h']} (left + right), nFeatures "
+                       f"{KITTI['nfeatures']}, device-resident (tiled from {len(base)} distinct pairs); the 20 000-point "
+                       "SearchByProjection of this config is widened_rows.search_by_projection_points",
+           "ms_per_step": ms, "value": fps, "unit": "images/s", "keypoints_per_image": float(outs[0][2].float().mean().item()),
+           "roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": KITTI["bytes_per_frame"], "achieved": round(gbs, 1),
+                        "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4)}}
+    if with_cpu:
+        cpu = oracle_lib.extractor(libkind, nfeatures=KITTI["nfeatures"], scale=SCALE, nlevels=NLEVELS, ini_th=INI_TH, min_th=MIN_TH)
+        cpu.extract(base[0][0])
+        t0 = time.perf_counter()
+        for side in range(2):
+            cpu.extract(base[1 % len(base)][side])
+        row["cpu_1thread_images_per_s"] = 2 / (time.perf_counter() - t0)
+    out["configs3_kitti_stereo"] = row
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -388,12 +635,20 @@ def main():
     ap.add_argument("--ref-rig-frames", type=int, default=64, help="rig-frames per CPU reference step")
     ap.add_argument("--cpu-rig-frames", type=int, default=256, help="rig-frames of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-1t-rig-frames", type=int, default=32, help="rig-frames of the one-thread cpu_baseline sample")
     ap.add_argument("--e2e-depth", type=int, default=3, help="steps in flight in the streaming end-to-end leg")
     ap.add_argument("--e2e-chunks", type=int, default=1, help="chunks per step of the streaming end-to-end leg")
     ap.add_argument("--serial-match", action="store_true",
                     help="run SearchForInitialization after both cameras on the extractor stream (A/B of the side stream)")
     ap.add_argument("--split-profile", action="store_true", help="take the per-stage events on separate steps")
     ap.add_argument("--bf-size", type=int, default=65536, help="N of the N x N brute-force matching leg")
+    ap.add_argument("--rig8-frames", type=int, default=512, help="rig-frames per step of the configs[4] leg (x 8 cameras)")
+    ap.add_argument("--rig8-chunk", type=int, default=64, help="rig-frames per extraction / all-gather chunk (configs[4])")
+    ap.add_argument("--rig8-distinct", type=int, default=8, help="distinct synthetic frames per camera, tiled (configs[4])")
+    ap.add_argument("--rig8-steps", type=int, default=5, help="timed steps of the configs[4] leg (capped by --steps)")
+    ap.add_argument("--no-rig8", action="store_true", help="skip the configs[4] leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[0]/[2]/[3] rows")
+    ap.add_argument("--kitti-pairs", type=int, default=64, help="stereo pairs per step of the configs[3] row")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -562,23 +817,34 @@ def main():
     total_matches = int(nmatch.sum().item())
     n_kp = [int(c.sum().item()) for c in counts]
 
+    # the metric's own setting on every frame: camera 1's extractor (nFeatures 1000) alone, same frames
+    ms_nf1000 = timed(lambda: ex[0].extract_batch_device(d_img[0], kps[0], desc[0], counts[0]), args.steps, False)
+
     # ---- end-to-end leg (pinned host -> device -> pinned host every step) -----------------------
     e2e_run(2)
     e2e_ms_dev, e2e_wall, e2e_res = e2e_run(args.steps)
     if int(e2e_res.nmatches.sum().item()) != total_matches or [int(c.sum().item()) for c in e2e_res.counts] != n_kp:
         raise SystemExit("bench.py: end-to-end results differ from the device-resident leg")
     # the raw H2D copy of one step's frames, for reference (the PCIe floor of the end-to-end leg)
-    barrier()
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        c0.record(stream)
-        for c in range(2):
-            d_img[c].copy_(h_img[c], non_blocking=True)
-        c1.record(stream)
-    stream.synchronize()
-    h2d_ms = c0.elapsed_time(c1)
+    # (all ranks copy at the same time: at N > 1 this IS the platform's concurrent pinned-H2D ceiling)
+    h2d_all = []
+    for rep in range(6):
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            c0.record(stream)
+            for c in range(2):
+                d_img[c].copy_(h_img[c], non_blocking=True)
+            c1.record(stream)
+        stream.synchronize()
+        h2d_all.append(c0.elapsed_time(c1))
+    h2d_t = torch.tensor([float(np.median(h2d_all[1:])), float(min(h2d_all[1:]))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(h2d_t, op=dist.ReduceOp.MAX)
+    h2d_ms, h2d_ms_best = float(h2d_t[0].item()), float(h2d_t[1].item())
     clocks = sampler.stop() if rank == 0 else None  # sampled over the device leg and the end-to-end leg
     h2d, d2h = pipe.h2d_bytes_per_step, pipe.d2h_bytes_per_step
+    e2e_depth, e2e_chunks, pipe_launches_total = pipe.depth, pipe.n_chunks, pipe.launch_count
 
     # ---- Hamming matches/s: brute-force leg (BASELINE.json configs[2] upper end) ----------------
     from multi_orb_slam_b200.synth import perturbed_descriptors, random_descriptors
@@ -629,6 +895,14 @@ def main():
     # single-GPU runs only (like cpu_baseline): small latency-bound calls, nothing to shard
     widened = widened_rows_leg(matcher, local_rank, not args.no_cpu_baseline) if world == 1 else None
 
+    peak, peak_src = load_peaks()
+    torch.cuda.empty_cache()
+    rig8 = None if args.no_rig8 else rig8_leg(args, world, rank, local_rank, dev, barrier, peak)
+    sm_max_cfg = (clocks or {}).get("sm_max_mhz") or 1965.0
+    configs_rows = None
+    if world == 1 and not args.no_configs:
+        configs_rows = configs_leg(args, matcher, local_rank, not args.no_cpu_baseline, peak, sm_max_cfg)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -637,7 +911,6 @@ def main():
     frames_per_step = 2 * F * world
     value = frames_per_step / (ms_step * 1e-3)
     e2e_value = frames_per_step / (e2e_ms_dev * 1e-3)
-    peak, peak_src = load_peaks()
     sb = stage_bytes_per_frame(W, H, NF0)
     names = ["pyramid", "fast", "octree", "blur", "orient_describe"]
     stages = {}
@@ -678,8 +951,11 @@ def main():
                      "frac": round(rate / issue_peak, 3),
                      "source": "instruction count from profiles/r01_traffic.json (ncu smsp__inst_executed.sum), "
                                "148 SM x 4 schedulers x SM clock"}
-    total_alg = sum(sb[n] for n in names) * 2 * F
+    # every pixel term for both cameras; the keypoint term with the keypoints actually produced (camera 2 runs nFeatures 500)
+    total_alg = sum(sb[n] for n in names if n != "orient_describe") * 2 * F + (749 + 512 + 28 + 32) * (n_kp[0] + n_kp[1])
     pipe_gbs = total_alg / (ms_step * 1e-3) / 1e9
+    nf1000_fps = F * world / (ms_nf1000 * 1e-3)
+    nf1000_gbs = (sum(sb[n] for n in names if n != "orient_describe") * F + (749 + 512 + 28 + 32) * n_kp[0]) / (ms_nf1000 * 1e-3) / 1e9
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -693,16 +969,27 @@ def main():
                    "keypoints_per_step_rank0": n_kp, "init_matches_per_step_rank0": total_matches},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms_dev, "wall_ms_per_step": e2e_wall,
-                "api": "multi_orb_slam_b200.pipeline.RigPipeline.submit/result", "chunks_per_step": pipe.n_chunks,
-                "pipeline_depth": pipe.depth, "h2d_copy_alone_ms": h2d_ms,
+                "api": "multi_orb_slam_b200.pipeline.RigPipeline.submit/result", "chunks_per_step": e2e_chunks,
+                "pipeline_depth": e2e_depth, "h2d_copy_alone_ms": h2d_ms, "h2d_copy_alone_ms_best": h2d_ms_best,
+                "h2d_ceiling": {"what": "all ranks copy one step's frames pinned->device at the same time, nothing else running "
+                                        "(median / best of 5, max over ranks)",
+                                "per_rank_GBps": round(h2d / (h2d_ms * 1e-3) / 1e9, 2),
+                                "aggregate_GBps": round(world * h2d / (h2d_ms * 1e-3) / 1e9, 2),
+                                "frames_per_s_at_ceiling": frames_per_step / (h2d_ms * 1e-3)},
+                "frac_of_min_kernel_rate_and_h2d_ceiling": round(e2e_value / min(value, frames_per_step / (h2d_ms * 1e-3)), 4),
                 "pinned_numa_bound_cpus": numa_cpus},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
                      "frac": stages[dom]["frac_of_hbm_peak"], "traffic": traffic,
                      "algorithmic_bytes_per_launch": int(sb[dom] * F), "launches_per_step": 2, "peak_source": peak_src,
-                     "pipeline": {"algorithmic_bytes_per_frame": int(sum(sb[n] for n in names)),
+                     "pipeline": {"algorithmic_bytes_per_frame": int(total_alg / (2 * F)),
+                                  "keypoint_term": "produced keypoints (not the nFeatures quota)",
                                   "achieved": round(pipe_gbs, 1), "frac": round(pipe_gbs / (peak * 1.0), 4)},
+                     "nfeatures1000_only": {"workload": "camera 1's extractor (nFeatures 1000) alone on its frames, "
+                                                        "no matcher: the metric's own setting on every frame",
+                                            "value": nf1000_fps, "unit": UNIT, "ms_per_step": ms_nf1000,
+                                            "achieved": round(nf1000_gbs, 1), "frac": round(nf1000_gbs / peak, 4)},
                      "issue": issue},
         "stages": stages,
     }
@@ -716,7 +1003,11 @@ def main():
     if widened is not None:
         out["widened_rows"] = widened
     if allgather is not None:
-        out["allgather"] = allgather
+        out["allgather_configs1_buffers"] = allgather
+    if rig8 is not None:
+        out["rig8"] = rig8
+    if configs_rows is not None:
+        out["configs"] = configs_rows
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         n_rig = min(args.cpu_rig_frames, F)
@@ -724,6 +1015,14 @@ def main():
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
                                "sample": f"{n_rig} rig-frames ({2 * n_rig} camera-frames) + {n_rig - 1} "
                                          f"SearchForInitialization pairs of the same workload, {dt:.2f} s wall"}
+        # how the reference itself runs the path: both cameras one after the other on the tracking thread
+        # (src/Frame.cc:182-185) — one core
+        n1 = min(args.cpu_1t_rig_frames, F)
+        v1, dt1, _ = cpu_reference_run([c[:n1] for c in cams], n1, 1)
+        out["cpu_baseline"]["one_thread"] = {"value": v1, "unit": UNIT, "cores": 1,
+                                             "sample": f"{n1} rig-frames ({2 * n1} camera-frames) + {n1 - 1} pairs, {dt1:.2f} s wall"}
+        if rig8 is not None:
+            out["rig8"]["cpu_baseline"] = cpu_rig8_run(threads)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

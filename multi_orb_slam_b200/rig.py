@@ -63,7 +63,9 @@ class RigFrontEnd:
         self.layout = RigLayout(self.n_cams, self.world, self.chunk, self.cap)
         self.gather = RigGather(self.rank, self.world, backend=backend, device=device, group=group)
         self.matcher = ORBmatcher(nnratio, True, device=device)
-        self.s_compute, self.s_comm = torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)
+        # the collective and the matcher are small next to the extraction kernels that fill the GPU: high priority, so
+        # their CTAs are placed as soon as SMs drain instead of queueing behind whole extraction grids
+        self.s_compute, self.s_comm = torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev, priority=-1)
         self.s_match = torch.cuda.Stream(device=self.dev, priority=-1)
         self.ex.set_stream(self.s_compute.cuda_stream)
         self.matcher.set_stream(self.s_match.cuda_stream)
@@ -72,6 +74,7 @@ class RigFrontEnd:
         self.buf_free = [None] * self.depth  # event: the matcher has finished reading the buffer
         self._tables: Dict[int, tuple] = {}
         self._out: Dict[Tuple[int, int], tuple] = {}
+        self.skip_gather = False  # measurement only (bench.py): time the step without its collective
         self.allgather_bytes_per_chunk = self.layout.bytes_per_rank * (self.world - 1) if self.world > 1 else 0
 
     @property
@@ -108,7 +111,7 @@ class RigFrontEnd:
                     self.ex.extract_batch_device(images[c][f0:f1], kps[:n], desc[:n], counts[:n])
                 ev_x = torch.cuda.Event()
                 ev_x.record(self.s_compute)
-            if self.world > 1:
+            if self.world > 1 and not self.skip_gather:
                 self.s_comm.wait_event(ev_x)
                 with torch.cuda.stream(self.s_comm):
                     self.gather.allgather_inplace(buf, self.layout.bytes_per_rank, self.s_comm.cuda_stream)

@@ -12,17 +12,20 @@
 #include <stdint.h>
 #include <stdio.h>
 
-#define ITER 2048
+#define ITER 512
 #define UNROLL 8
 
 enum Op { POPC, LOP3, IADD3, IMAD, PRMT, SHF, VABSDIFF4, VIMNMX3, VIMNMX3_16, IDP4A, IDP2A, POPC_LOP, POPC_IMAD, HAMMING8,
-          LDS_U8, LDS_32, N_OPS };
+          LDS_U8, LDS_32, LDS_64, LDS_128, LDS_U8_SCATTER, STS_32, STS_U8, LDG_32, LDG_128, SHFL, REDUX, VOTE, MATCH, N_OPS };
 static const char* kNames[N_OPS] = {"popc", "lop3", "iadd3", "imad", "prmt", "shf_funnel", "vabsdiff4", "vimnmx3_s32",
                                     "vimnmx3_s16x2", "idp4a", "idp2a", "popc+lop3 (1:1)", "popc+imad (1:1)",
-                                    "hamming256 (8 x xor+popc+add)", "lds_u8 (conflict-free)", "lds_b32 (conflict-free)"};
+                                    "hamming256 (8 x xor+popc+add)", "lds_u8 (conflict-free)", "lds_b32 (conflict-free)",
+                                    "lds_b64 (conflict-free)", "lds_b128 (conflict-free)", "lds_u8 (4 rows x 36 B, pitch 48: phase-B pattern)",
+                                    "sts_b32", "sts_u8", "ldg_b32 (L1 hit, coalesced)", "ldg_b128 (L1 hit)", "shfl_idx", "redux_or",
+                                    "vote_ballot", "match_any"};
 
 template <int OP>
-__global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t seed) {
+__global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t seed, const uint32_t* __restrict__ g) {
   __shared__ uint32_t sm[1024];
   for (int i = threadIdx.x; i < 1024; i += 256) sm[i] = i * 2654435761u;
   __syncthreads();
@@ -61,6 +64,39 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t seed) {
           a[j] = reinterpret_cast<volatile uint8_t*>(sm)[(a[j] & 0xf80u) + threadIdx.x % 128];
         } else if (OP == LDS_32) {
           a[j] = reinterpret_cast<volatile uint32_t*>(sm)[(a[j] & 0x3e0u) + (threadIdx.x & 31)];
+        } else if (OP == LDS_64) {
+          uint32_t x, y;
+          const uint32_t addr = (uint32_t)__cvta_generic_to_shared(sm) + 8u * ((a[j] & 0x40u) + (threadIdx.x & 31));
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(addr));
+          a[j] = x + y;
+        } else if (OP == LDS_128) {
+          uint32_t x, y, z, w;
+          const uint32_t addr = (uint32_t)__cvta_generic_to_shared(sm) + 16u * ((a[j] & 0x20u) + (threadIdx.x & 31));
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(addr));
+          a[j] = x + w;
+        } else if (OP == LDS_U8_SCATTER) {
+          // 32 candidates spread over ~4 rows of a 36-byte wide tile with pitch 48
+          const uint32_t lane = threadIdx.x & 31;
+          a[j] = reinterpret_cast<volatile uint8_t*>(sm)[(a[j] & 0xe00u) + (lane >> 3) * 48 + ((lane * 5 + j) % 36)];
+        } else if (OP == STS_32) {
+          reinterpret_cast<volatile uint32_t*>(sm)[(a[j] & 0x3e0u) + (threadIdx.x & 31)] = a[j];
+          a[j] += b;
+        } else if (OP == STS_U8) {
+          reinterpret_cast<volatile uint8_t*>(sm)[(a[j] & 0xf80u) + threadIdx.x % 128] = (uint8_t)a[j];
+          a[j] += b;
+        } else if (OP == LDG_32) {
+          a[j] = __ldg(g + ((a[j] & 0x3e0u) + (threadIdx.x & 31)));
+        } else if (OP == LDG_128) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(g) + ((a[j] & 0xc0u) + (threadIdx.x & 31)));
+          a[j] = v.x + v.w;
+        } else if (OP == SHFL) {
+          a[j] = __shfl_sync(0xffffffffu, a[j], (threadIdx.x + 1 + j) & 31);
+        } else if (OP == REDUX) {
+          a[j] = __reduce_or_sync(0xffffffffu, a[j] + threadIdx.x);
+        } else if (OP == VOTE) {
+          a[j] = __ballot_sync(0xffffffffu, (a[j] + threadIdx.x) & 1) + b;
+        } else if (OP == MATCH) {
+          a[j] = __match_any_sync(0xffffffffu, a[j] & 7u) + threadIdx.x;
         }
       }
     }
@@ -71,17 +107,19 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t seed) {
   if (s == 0x12345678u) out[0] = s;  // keeps the chains alive
 }
 
+static const uint32_t* g_buf = nullptr;
 template <int OP>
-double run(uint32_t* d_out, int sms, double clk_hz) {
+double run(uint32_t* d_out, int sms, double clk_hz, const uint32_t* g = nullptr) {
+  g = g ? g : g_buf;
   const dim3 grid(sms * 4), block(256);
-  k<OP><<<grid, block>>>(d_out, 12345u);
+  k<OP><<<grid, block>>>(d_out, 12345u, g);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   float best = 1e30f;
   for (int r = 0; r < 5; ++r) {
     cudaEventRecord(e0);
-    k<OP><<<grid, block>>>(d_out, 12345u + r);
+    k<OP><<<grid, block>>>(d_out, 12345u + r, g);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms;
@@ -101,6 +139,10 @@ int main() {
   const double clk_hz = clk_khz * 1e3;
   uint32_t* d_out;
   cudaMalloc(&d_out, 64);
+  uint32_t* d_g;
+  cudaMalloc(&d_g, 1 << 16);
+  cudaMemset(d_g, 0, 1 << 16);
+  g_buf = d_g;
   double r[N_OPS];
   r[POPC] = run<POPC>(d_out, p.multiProcessorCount, clk_hz);
   r[LOP3] = run<LOP3>(d_out, p.multiProcessorCount, clk_hz);
@@ -118,6 +160,17 @@ int main() {
   r[HAMMING8] = run<HAMMING8>(d_out, p.multiProcessorCount, clk_hz);
   r[LDS_U8] = run<LDS_U8>(d_out, p.multiProcessorCount, clk_hz);
   r[LDS_32] = run<LDS_32>(d_out, p.multiProcessorCount, clk_hz);
+  r[LDS_64] = run<LDS_64>(d_out, p.multiProcessorCount, clk_hz);
+  r[LDS_128] = run<LDS_128>(d_out, p.multiProcessorCount, clk_hz);
+  r[LDS_U8_SCATTER] = run<LDS_U8_SCATTER>(d_out, p.multiProcessorCount, clk_hz);
+  r[STS_32] = run<STS_32>(d_out, p.multiProcessorCount, clk_hz);
+  r[STS_U8] = run<STS_U8>(d_out, p.multiProcessorCount, clk_hz);
+  r[LDG_32] = run<LDG_32>(d_out, p.multiProcessorCount, clk_hz);
+  r[LDG_128] = run<LDG_128>(d_out, p.multiProcessorCount, clk_hz);
+  r[SHFL] = run<SHFL>(d_out, p.multiProcessorCount, clk_hz);
+  r[REDUX] = run<REDUX>(d_out, p.multiProcessorCount, clk_hz);
+  r[VOTE] = run<VOTE>(d_out, p.multiProcessorCount, clk_hz);
+  r[MATCH] = run<MATCH>(d_out, p.multiProcessorCount, clk_hz);
   printf("{\"device\": \"%s\", \"sms\": %d, \"clock_mhz_nominal\": %.0f, \"unit\": \"warp-instructions per clock per SM "
          "(x32 = lane-ops/clk/SM; clock = cudaDevAttrClockRate)\", \"rates\": {",
          p.name, p.multiProcessorCount, clk_hz / 1e6);
