@@ -41,12 +41,14 @@ cv::Mat fmat(const float* p, int r, int c) {
 void set_bounds(om_bounds b) {
   Frame::mnMinX = b.min_x; Frame::mnMaxX = b.max_x; Frame::mnMinY = b.min_y; Frame::mnMaxY = b.max_y;
 }
+#ifndef OMR_HOT_ONLY
 DBoW2::FeatureVector featvec(const int32_t* node, const int32_t* start, const int32_t* items, int nn) {
   DBoW2::FeatureVector fv;
   for (int a = 0; a < nn; ++a)
     for (int p = start[a]; p < start[a + 1]; ++p) fv.addFeature((DBoW2::NodeId)node[a], (unsigned)items[p]);
   return fv;
 }
+#endif
 // concatenated multi-camera features -> the members a Frame / KeyFrame holds for them
 template <class T>
 void fill_rig(T& f, const oo_keypoint* k, const uint8_t* d, const int32_t* cam, const float* uright, int n, om_bounds b) {
@@ -263,8 +265,12 @@ int omr_search_by_projection_sim3(const oo_keypoint* kf_k, const uint8_t* kf_des
   }
   std::vector<int> cams(n_mp, 0);
   ORBmatcher matcher(0.75f, true);
+#ifdef OMR_HOT_ONLY
+  const int nm = matcher.SearchByProjection(&KF, fmat(Scw, 4, 4), vpPoints, cams, vpMatched, th, fmat(calib, 4, 3));
+#else
   const int nm = g_cam1 ? matcher.SearchByProjection_cam1(&KF, fmat(Scw, 4, 4), vpPoints, vpMatched, th)
                         : matcher.SearchByProjection(&KF, fmat(Scw, 4, 4), vpPoints, cams, vpMatched, th, fmat(calib, 4, 3));
+#endif
   for (int i = 0; i < n_kf; ++i) {
     const int j = index_in(pts, vpMatched[i]);
     if (j >= 0) matched[i] = j;
@@ -273,6 +279,8 @@ int omr_search_by_projection_sim3(const oo_keypoint* kf_k, const uint8_t* kf_des
   return nm;
 }
 
+#ifndef OMR_HOT_ONLY  // the same harness is linked against the product's drop-in translation unit, which defines the hot
+                      // members only (multi_orb_slam_b200/dropin/ORBmatcher_b200.cc, tests/native/Makefile)
 // variant 0: SearchByBoW(KeyFrame*, Frame&, ...) (valid2 ignored: the frame side has no validity test);
 // variant 1: SearchByBoW(KeyFrame*, KeyFrame*, ...)
 int omr_search_by_bow(int variant, const uint8_t* d1, const float* angle1, const int32_t* valid1, int n1, const int32_t* node1,
@@ -488,5 +496,7 @@ int omr_bow_transform(const char* voc_path, const uint8_t* desc, int n, int leve
   *n_fv = a;
   return (int)voc.size();
 }
+
+#endif  // OMR_HOT_ONLY
 
 }  // extern "C"

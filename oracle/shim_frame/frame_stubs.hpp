@@ -12,7 +12,9 @@
 #include "../cvprim.h"
 
 namespace cv {
+#ifndef ORB_REAL_EXTRACTOR  // tests/native/shim_real provides InputArray / OutputArray for the reference's real ORBextractor.h
 typedef const Mat& InputArray;
+#endif
 inline void undistortPoints(const Mat& src, Mat& dst, const Mat& K, const Mat& dist, const Mat&, const Mat&) {
   // Frame.cc calls it in place on an N x 1 two-channel view of an N x 2 CV_32F matrix with R = Mat(), P = K
   const int n = src.rows;
@@ -27,6 +29,7 @@ inline void undistortPoints(const Mat& src, Mat& dst, const Mat& K, const Mat& d
 }  // namespace cv
 
 namespace ORB_SLAM2 {
+#ifndef ORB_REAL_EXTRACTOR  // tests/native/Makefile compiles Frame.cc against the reference's real include/ORBextractor.h
 class ORBextractor {
  public:
   enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
@@ -56,6 +59,7 @@ class ORBextractor {
   std::vector<float> GetScaleSigmaSquares() { return mvLevelSigma2; }
   std::vector<float> GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
 };
+#endif
 
 class Converter {
  public:

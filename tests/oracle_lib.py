@@ -130,7 +130,11 @@ def load(kind: str = "port"):
     if kind in _libs:
         return _libs[kind]
     path = os.path.join(ORACLE_DIR, {"port": "liborb_oracle.so", "ref": "_ref/liborb_ref.so",
-                                     "mref": "_ref/libmatcher_ref.so", "fref": "_ref/libframe_ref.so"}[kind])
+                                     "mref": "_ref/libmatcher_ref.so", "fref": "_ref/libframe_ref.so",
+                                     # NOT an oracle: the PRODUCT's drop-in translation units (multi_orb_slam_b200/dropin/)
+                                     # behind the same C harness as the verbatim reference builds (tests/native/Makefile)
+                                     "dropin": "../tests/native/_build/libmatcher_dropin.so",
+                                     "xdropin": "../tests/native/_build/libextractor_dropin.so"}[kind])
     if kind == "port" and not os.path.exists(path):
         build_oracle()
     lib = C.CDLL(path) if os.path.exists(path) else None
@@ -185,7 +189,7 @@ def features_in_area(kx, ky, koct, bounds, x, y, r, min_level, max_level):
 
 
 def search_for_initialization(k1, d1, k2, d2, bounds2, prev_xy, window=100, nnratio=0.9, check_ori=True, impl="port"):
-    lib = load("port" if impl == "port" else "mref")
+    lib = load({"port": "port", "ref": "mref", "mref": "mref", "dropin": "dropin"}[impl])
     k1 = np.ascontiguousarray(k1, dtype=KP_DTYPE)
     k2 = np.ascontiguousarray(k2, dtype=KP_DTYPE)
     d1 = np.ascontiguousarray(d1, dtype=np.uint8)
@@ -203,7 +207,7 @@ def search_for_initialization(k1, d1, k2, d2, bounds2, prev_xy, window=100, nnra
 
 def search_by_projection_points(k, d, u_right, bounds, scale_factors, mp, mp_desc, mp_obs, th, nnratio,
                                 frame_mp=None, frame_mp_obs=None, impl="port"):
-    lib = load("port" if impl == "port" else "mref")
+    lib = load({"port": "port", "ref": "mref", "mref": "mref", "dropin": "dropin"}[impl])
     k = np.ascontiguousarray(k, dtype=KP_DTYPE)
     d = np.ascontiguousarray(d, dtype=np.uint8)
     n = len(k)
@@ -231,7 +235,7 @@ class Camera(C.Structure):
 
 def search_by_projection_frame(cur_k, cur_desc, cur_uright, cur_cam, bounds, sf, cam, Tcw_cur, Tcw_last, last_k, last_cam,
                                last_valid, last_xyz, last_desc, last_obs, calib, th, mono, check_ori, cur_mp, cur_mp_obs, impl="port"):
-    lib = load("port" if impl == "port" else "mref")
+    lib = load({"port": "port", "ref": "mref", "mref": "mref", "dropin": "dropin"}[impl])
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
     i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
     cur_k, last_k = np.ascontiguousarray(cur_k, dtype=KP_DTYPE), np.ascontiguousarray(last_k, dtype=KP_DTYPE)
@@ -252,7 +256,7 @@ def search_by_projection_frame(cur_k, cur_desc, cur_uright, cur_cam, bounds, sf,
 
 def search_by_projection_keyframe(cur_k, cur_desc, bounds, sf, log_sf, cam, Tcw_cur, kf_valid, kf_xyz, kf_max_dist,
                                   kf_min_dist, kf_max_d, kf_angle, kf_desc, th, orb_dist, check_ori, cur_mp, impl="port"):
-    lib = load("port" if impl == "port" else "mref")
+    lib = load({"port": "port", "ref": "mref", "mref": "mref", "dropin": "dropin"}[impl])
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
     cur_k = np.ascontiguousarray(cur_k, dtype=KP_DTYPE)
     cur_desc, kf_desc = np.ascontiguousarray(cur_desc, dtype=np.uint8), np.ascontiguousarray(kf_desc, dtype=np.uint8)
@@ -271,7 +275,7 @@ def search_by_projection_keyframe(cur_k, cur_desc, bounds, sf, log_sf, cam, Tcw_
 
 def search_by_projection_sim3(kf_k, kf_desc, kf_cam, bounds, sf, log_sf, cam, Scw, calib, mp_valid, mp_xyz, mp_normal,
                               mp_max_dist, mp_min_dist, mp_max_d, mp_desc, th, matched, impl="port"):
-    lib = load("port" if impl == "port" else "mref")
+    lib = load({"port": "port", "ref": "mref", "mref": "mref", "dropin": "dropin"}[impl])
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
     kf_k = np.ascontiguousarray(kf_k, dtype=KP_DTYPE)
     kf_desc, mp_desc = np.ascontiguousarray(kf_desc, dtype=np.uint8), np.ascontiguousarray(mp_desc, dtype=np.uint8)
@@ -329,7 +333,7 @@ def fuse_sim3(kf_k, kf_desc, kf_cam, bounds, sf, log_sf, cam, Scw, calib, mp_val
 
 
 def search_by_sim3(k1, d1, cam1, T1w, k2, d2, cam2, T2w, bounds, sf, log_sf, cam, s12, R12, t12, calib, mp1, mp2, th, impl="port"):
-    lib = load("port" if impl == "port" else "mref")
+    lib = load({"port": "port", "ref": "mref", "mref": "mref", "dropin": "dropin"}[impl])
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
     i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
     k1, k2 = np.ascontiguousarray(k1, dtype=KP_DTYPE), np.ascontiguousarray(k2, dtype=KP_DTYPE)
@@ -671,8 +675,8 @@ def search_for_initialization_frame_ref(k1, d1, k2, d2, cols, rows, fx, fy, cx, 
     return n, m12, prev
 
 
-def distance_ref(a, b):
-    lib = load("mref")
+def distance_ref(a, b, impl="mref"):
+    lib = load(impl)
     a, b = np.ascontiguousarray(a, dtype=np.uint8), np.ascontiguousarray(b, dtype=np.uint8)
     lib.omr_distance.argtypes = [C.c_void_p, C.c_void_p]
     return lib.omr_distance(a.ctypes.data, b.ctypes.data)

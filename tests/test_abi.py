@@ -53,20 +53,3 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_lib" not in src and "liborb_oracle" not in src and "liborb_ref" not in src, f
                 assert not re.search(r'#include\s+"[^"]*oracle/', src), f
-
-
-def _build_dropin():
-    import subprocess
-    out = os.path.join(ROOT, "tests", "native", "dropin_smoke")
-    cmd = ["g++", "-std=c++14", "-O2", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle", "shim"),
-           "-o", out, os.path.join(ROOT, "tests", "native", "dropin_smoke.cc"), os.path.join(ROOT, "oracle", "cvprim.cc"),
-           "-L", os.path.join(ROOT, "multi_orb_slam_b200"), "-l:liborb_b200.so",
-           "-Wl,-rpath," + os.path.join(ROOT, "multi_orb_slam_b200")]
-    subprocess.run(cmd, check=True)
-    return out
-
-
-def test_cpp_dropin_classes_compile_and_link(lib):
-    """include/ORBextractor.h + include/ORBmatcher.h (the reference-shaped C++ classes) compile as
-    C++14 against an OpenCV-style API and link against the C-ABI library."""
-    assert os.path.exists(_build_dropin())

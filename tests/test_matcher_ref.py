@@ -72,8 +72,7 @@ def test_search_by_projection_frame(offset, th, mono, check_ori):
     assert a[0] > 100
 
 
-@pytest.mark.parametrize("th,orb_dist,check_ori", [(10.0, 100, True), (3.0, 64, True), (10.0, 100, False)])
-def test_search_by_projection_keyframe(th, orb_dist, check_ori):
+def _keyframe_case(th, orb_dist, check_ori):
     s = _rig_scene(O, 9, 1200, (0, 0, 0))
     sel = s["cur_cam"] == 0
     cur_k, cur_d = s["cur_k"][sel], s["cur_d"][sel]
@@ -90,16 +89,20 @@ def test_search_by_projection_keyframe(th, orb_dist, check_ori):
     fmp0 = np.full(len(cur_k), -1, np.int32)
     fmp0[rng.random(len(cur_k)) < 0.1] = 5
     log_sf = float(np.log(np.float32(1.2)))
-    args = (cur_k, cur_d, (0, 640, 0, 480), sf, log_sf, CAM, s["Tcw"], valid, xyz, kf_max, kf_min, max_d, ang, desc, th, orb_dist,
+    return (cur_k, cur_d, (0, 640, 0, 480), sf, log_sf, CAM, s["Tcw"], valid, xyz, kf_max, kf_min, max_d, ang, desc, th, orb_dist,
             check_ori, fmp0)
+
+
+@pytest.mark.parametrize("th,orb_dist,check_ori", [(10.0, 100, True), (3.0, 64, True), (10.0, 100, False)])
+def test_search_by_projection_keyframe(th, orb_dist, check_ori):
+    args = _keyframe_case(th, orb_dist, check_ori)
     a = O.search_by_projection_keyframe(*args)
     b = O.search_by_projection_keyframe(*args, impl="ref")
     assert a[0] == b[0] and np.array_equal(a[1], b[1])
     assert a[0] > 100
 
 
-@pytest.mark.parametrize("th,scale", [(10, 1.0), (4, 1.7)])
-def test_search_by_projection_sim3(th, scale):
+def _sim3_case(th, scale):
     s = _rig_scene(O, 13, 1800, (0, 0, 0))
     rng = s["rng"]
     n, nmp = s["n"], len(s["last_xyz"])
@@ -118,8 +121,13 @@ def test_search_by_projection_sim3(th, scale):
     matched0 = np.full(n, -1, np.int32)
     matched0[rng.random(n) < 0.1] = 3
     log_sf = float(np.log(np.float32(1.2)))
-    args = (s["cur_k"], s["cur_d"], s["cur_cam"], (0, 640, 0, 480), sf, log_sf, CAM, Scw, CALIB, valid, xyz, normal, kf_max, kf_min,
+    return (s["cur_k"], s["cur_d"], s["cur_cam"], (0, 640, 0, 480), sf, log_sf, CAM, Scw, CALIB, valid, xyz, normal, kf_max, kf_min,
             max_d, s["last_desc"], th, matched0)
+
+
+@pytest.mark.parametrize("th,scale", [(10, 1.0), (4, 1.7)])
+def test_search_by_projection_sim3(th, scale):
+    args = _sim3_case(th, scale)
     a = O.search_by_projection_sim3(*args)
     b = O.search_by_projection_sim3(*args, impl="ref")
     assert a[0] == b[0] and np.array_equal(a[1], b[1])
