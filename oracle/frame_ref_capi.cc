@@ -75,6 +75,34 @@ std::unique_ptr<Frame> make_frame(Rig& rig, const oo_keypoint* k0, const uint8_t
 
 extern "C" {
 
+// Frame::ComputeStereoMatches — the reference's own text (commented out in the fork, src/Frame.cc:782-956; un-commented
+// at build time into oracle/_ref/ by oracle/gen_stereo_ref.py, never copied into the repository) run on a default-
+// constructed real Frame whose members are set from flat arrays.  pyr_l / pyr_r: mvImagePyramid of the left / right
+// extractor (interior pointers into bordered level buffers, like the reference's ROIs).
+void ofr_compute_stereo_matches(const oo_keypoint* kl, const uint8_t* dl, int nl, const oo_keypoint* kr, const uint8_t* dr, int nr,
+                                const om_image* pyr_l, const om_image* pyr_r, int nlevels, const float* scale_factors,
+                                const float* inv_scale_factors, float mbf, float mb, float* uright, float* depth) {
+  ORBextractor exl(1000, 1.2f, nlevels, 20, 7), exr(1000, 1.2f, nlevels, 20, 7);
+  for (int l = 0; l < nlevels; ++l) {
+    exl.mvImagePyramid.push_back(cv::Mat::wrap(pyr_l[l].h, pyr_l[l].w, CV_8U, (void*)pyr_l[l].data, pyr_l[l].step));
+    exr.mvImagePyramid.push_back(cv::Mat::wrap(pyr_r[l].h, pyr_r[l].w, CV_8U, (void*)pyr_r[l].data, pyr_r[l].step));
+  }
+  Frame F;
+  F.N = nl;
+  F.mvKeys = keys_of(kl, nl);
+  F.mvKeysRight = keys_of(kr, nr);
+  F.mDescriptors = desc_rows(dl, nl);
+  F.mDescriptorsRight = desc_rows(dr, nr);
+  F.mpORBextractorLeft = &exl;
+  F.mpORBextractorRight = &exr;
+  F.mvScaleFactors.assign(scale_factors, scale_factors + nlevels);
+  F.mvInvScaleFactors.assign(inv_scale_factors, inv_scale_factors + nlevels);
+  F.mb = mb;
+  F.mbf = mbf;
+  F.ComputeStereoMatches();
+  for (int i = 0; i < nl; ++i) { uright[i] = F.mvuRight[i]; depth[i] = F.mvDepth[i]; }
+}
+
 // Frame::Frame (two cameras, RGB-D) -> everything the glue computes.  Outputs sized n0 + n1: k_un (mvKeysUn_total),
 // uright / depth (mvuRight_total / mvDepth_total), cam_of (keypoint_to_cam), local_idx (cont_idx_to_local_cam_idx);
 // bounds = mnMinX..; grid_start (2 x (64*48+1)) / grid_items (2 x (n0+n1)): mGrids[cam][ix][iy] as CSR over ix*48+iy.

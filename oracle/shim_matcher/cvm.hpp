@@ -103,6 +103,28 @@ class Mat {
     for (int i = 0; i < rows; ++i) std::memcpy(dst.data + (size_t)i * dst.step, data + (size_t)i * step, (size_t)cols * esz());
   }
   void release() { rows = cols = 0; store.reset(); data = nullptr; }
+  // u8 -> f32 / same-type copy (Frame::ComputeStereoMatches converts 11x11 patches in place, src/Frame.cc:879-880)
+  void convertTo(Mat& dst, int type) const {
+    Mat out(rows, cols, type);
+    for (int i = 0; i < rows; ++i)
+      for (int j = 0; j < cols; ++j) {
+        const float v = type_ == CV_32F ? at<float>(i, j) : (float)at<unsigned char>(i, j);
+        if (type == CV_32F) out.at<float>(i, j) = v; else out.at<unsigned char>(i, j) = (unsigned char)v;
+      }
+    dst = out;
+  }
+  static Mat ones(int r, int c, int type) {
+    Mat m(r, c, type);
+    for (int i = 0; i < r; ++i)
+      for (int j = 0; j < c; ++j) m.at<float>(i, j) = 1.f;
+    return m;
+  }
+  // header over foreign memory (no ownership), e.g. a pyramid level handed in by a test
+  static Mat wrap(int r, int c, int type, void* p, size_t step_bytes) {
+    Mat m;
+    m.rows = r; m.cols = c; m.type_ = type; m.step = step_bytes; m.data = static_cast<unsigned char*>(p);
+    return m;
+  }
   Mat reshape(int) const { return *this; }  // N x 2 one-channel <-> N x 1 two-channel: same memory, channels are not modelled
   MatT t() const;
   Mat inv() const;  // 3x3 CV_32F: closed form in double
@@ -206,6 +228,14 @@ inline Mat operator-(const Mat& c, const GemmT& g) { return gemm_t(GemmT{g.a, g.
 inline Mat operator-(const GemmT& g, const Mat& c) { return gemm_t(g, &c, -1.0); }
 
 inline double norm(const Mat& a) { return std::sqrt(a.dot(a)); }
+enum { NORM_L1 = 2 };
+// cv::norm(a, b, NORM_L1) of two CV_32F matrices: sum of |a - b| accumulated in double (OpenCV normDiffL1_32f)
+inline double norm(const Mat& a, const Mat& b, int) {
+  double s = 0;
+  for (int i = 0; i < a.rows; ++i)
+    for (int j = 0; j < a.cols; ++j) s += std::fabs((double)a.at<float>(i, j) - (double)b.at<float>(i, j));
+  return s;
+}
 
 // cv::FileStorage / cv::FileNode: only so that DBoW2's YAML save/load members (virtual, hence instantiated with the
 // class) compile; they are never called (the vocabulary is read with loadFromTextFile).

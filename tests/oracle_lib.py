@@ -435,9 +435,10 @@ class OmImage(C.Structure):
     _fields_ = [("data", C.c_void_p), ("w", C.c_int32), ("h", C.c_int32), ("step", C.c_size_t)]
 
 
-def compute_stereo_matches(kl, dl, kr, dr, pyr_l, pyr_r, scale, inv_scale, mbf, mb, border=19):
-    """pyr_l / pyr_r: per level the BORDERED level image ((h+2*border) x (w+2*border) u8) of each extractor."""
-    lib = load("port")
+def compute_stereo_matches(kl, dl, kr, dr, pyr_l, pyr_r, scale, inv_scale, mbf, mb, border=19, impl="port"):
+    """pyr_l / pyr_r: per level the BORDERED level image ((h+2*border) x (w+2*border) u8) of each extractor.
+    impl "ref" runs the reference's own (un-commented) Frame::ComputeStereoMatches of oracle/_ref/libframe_ref.so."""
+    lib = load("port" if impl == "port" else "fref")
     kl, kr = np.ascontiguousarray(kl, dtype=KP_DTYPE), np.ascontiguousarray(kr, dtype=KP_DTYPE)
     dl, dr = np.ascontiguousarray(dl, dtype=np.uint8), np.ascontiguousarray(dr, dtype=np.uint8)
     scale, inv_scale = np.ascontiguousarray(scale, dtype=np.float32), np.ascontiguousarray(inv_scale, dtype=np.float32)
@@ -450,7 +451,7 @@ def compute_stereo_matches(kl, dl, kr, dr, pyr_l, pyr_r, scale, inv_scale, mbf, 
                              a.strides[0])
         views.append(arr)
     uright, depth = np.empty(len(kl), np.float32), np.empty(len(kl), np.float32)
-    f = lib.om_compute_stereo_matches
+    f = lib.om_compute_stereo_matches if impl == "port" else lib.ofr_compute_stereo_matches
     f.restype = None
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                   C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]

@@ -82,3 +82,20 @@ def test_search_for_initialization_through_reference_frames(seed, window, check_
     bounds = O.compute_image_bounds(640, 480, *TUM1, TUM1_DIST)
     a = O.search_for_initialization(u1, d1, u2, d2, bounds, prev, window, 0.9, check_ori)
     assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[0] > 20
+
+
+@pytest.mark.parametrize("seed,size,nfeatures,disp,mbf,mb", [
+    (3, (640, 480), 1000, (4, 9, 17, 30), 40.0, 0.08),
+    (5, (400, 300), 300, (6, 13), 35.0, 0.09),
+    (900, (1241, 376), 2000, (5, 12, 26, 44), 386.1448, 386.1448 / 718.856),  # KITTI-shaped (configs[3])
+])
+def test_compute_stereo_matches_vs_the_reference_text(seed, size, nfeatures, disp, mbf, mb):
+    """Frame::ComputeStereoMatches is commented out in the fork (src/Frame.cc:782-956): oracle/gen_stereo_ref.py
+    un-comments the reference's own text at build time into oracle/_ref/ and it runs here, as a member of the reference's
+    real Frame class, against the restatement that checks the CUDA kernel — mvuRight / mvDepth bit for bit."""
+    from test_frame_glue_oracle import _stereo_oracle
+    _, _, ((kl, dl, pl, tl), (kr, dr, pr, _)) = _stereo_oracle(O, seed, nfeatures=nfeatures, W=size[0], H=size[1], disparities=disp)
+    a = O.compute_stereo_matches(kl, dl, kr, dr, pl, pr, tl[0], tl[1], mbf, mb)
+    b = O.compute_stereo_matches(kl, dl, kr, dr, pl, pr, tl[0], tl[1], mbf, mb, impl="ref")
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert (a[0] >= 0).sum() > 0.3 * len(kl)
