@@ -969,7 +969,7 @@ def main():
                    "keypoints_per_step_rank0": n_kp, "init_matches_per_step_rank0": total_matches},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms_dev, "wall_ms_per_step": e2e_wall,
-                "api": "multi_orb_slam_b200.pipeline.RigPipeline.submit/result", "chunks_per_step": e2e_chunks,
+                "api": "C ABI orbp_submit / orbp_wait (include/orb_b200.h) through multi_orb_slam_b200.pipeline.RigPipeline", "chunks_per_step": e2e_chunks,
                 "pipeline_depth": e2e_depth, "h2d_copy_alone_ms": h2d_ms, "h2d_copy_alone_ms_best": h2d_ms_best,
                 "h2d_ceiling": {"what": "all ranks copy one step's frames pinned->device at the same time, nothing else running "
                                         "(median / best of 5, max over ranks)",

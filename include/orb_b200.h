@@ -224,6 +224,11 @@ int orbm_search_by_projection_points_host(orbm_matcher* m, const orbx_keypoint* 
                                           float nnratio, int32_t* frame_mp, const int32_t* frame_mp_obs,
                                           int* nmatches);
 
+/* The single-call projection searches size their candidate-row buffer from the need of earlier calls (first guess:
+ * rows_per_query x queries, default 64) so that no host round trip separates counting from filling; a call whose rows
+ * do not fit is repeated once with the exact size.  Test tap: a budget of 1 forces that path.  Resets the history. */
+int orbm_debug_set_row_budget(orbm_matcher* m, int rows_per_query);
+
 /* Camera intrinsics / stereo fields of Frame read by the pose-based overloads (fx, fy, cx, cy,
  * mb = baseline, mbf). */
 typedef struct {
@@ -462,6 +467,55 @@ typedef struct {
 } orbm_tri_pair;
 int orbm_search_for_triangulation_batch_host(orbm_matcher* m, orbm_tri_pair* pairs, int n_pairs, int nlevels, int only_stereo,
                                              const int32_t* cam_enabled, int check_ori);
+
+/* ---- streaming front end of a multi-camera rig -------------------------------------------------------------
+ * Frame::Frame runs one ORBextractor per camera on every rig-frame (src/Frame.cc:148-346, :182-185) and
+ * MonocularInitialization matches consecutive frames of camera 1 (src/Tracking.cc:870-871).  A pipeline takes the
+ * frames of `rig_frames` rig-frames per step from HOST memory (pinned memory makes the copies asynchronous) and
+ * leaves keypoints / descriptors / counts of every camera and the initialisation matches of camera 0 in pinned host
+ * memory it owns; the copies of step k+1 overlap the kernels of step k (`depth` steps in flight; four CUDA streams:
+ * copy-in, extraction, matching, copy-out).  orbp_submit returns at once; orbp_wait blocks for one step. */
+#define ORBP_MAX_CAMS 8
+typedef struct {
+  int32_t n_cams;
+  int32_t nfeatures[ORBP_MAX_CAMS]; /* per camera (src/Tracking.cc:144-145: the second camera runs with half) */
+  float scale_factor;
+  int32_t nlevels, ini_th_fast, min_th_fast;
+  int32_t width, height;
+  int32_t rig_frames; /* rig-frames per step */
+  int32_t depth;      /* steps in flight, >= 2 (0 = default 3) */
+  int32_t match;      /* != 0: SearchForInitialization(frame t, frame t+1) of camera 0, vbPrevMatched = F1's keypoints */
+  int32_t window;     /* windowSize of that search (100 at src/Tracking.cc:871) */
+  float nnratio;      /* ORBmatcher(nnratio, check_ori) */
+  int32_t check_ori;
+  int32_t device;     /* CUDA device ordinal, -1 = current */
+} orbp_config;
+typedef struct orbp_pipeline orbp_pipeline;
+/* Pinned host memory owned by the pipeline, valid until `depth` further submits.  Camera c: kps[c] / desc[c] hold
+ * rig_frames x cap[c] entries (frame f at f*cap[c]), counts[c][f] valid ones.  matches12: (rig_frames-1) x cap[0]
+ * (vnMatches12 of pair (f, f+1), -1 = none), nmatches[f]; NULL when the pipeline was created with match = 0. */
+typedef struct {
+  const orbx_keypoint* kps[ORBP_MAX_CAMS];
+  const uint8_t* desc[ORBP_MAX_CAMS];
+  const int32_t* counts[ORBP_MAX_CAMS];
+  int32_t cap[ORBP_MAX_CAMS];
+  const int32_t* matches12;
+  const int32_t* nmatches;
+  int32_t rig_frames;
+} orbp_result;
+int orbp_create(const orbp_config* cfg, orbp_pipeline** out);
+void orbp_destroy(orbp_pipeline* p);
+const char* orbp_last_error(const orbp_pipeline* p);
+int orbp_capacity(const orbp_pipeline* p, int cam);
+/* images[c]: rig_frames frames of camera c in host memory, frame f at images[c] + f*frame_stride, `row_stride` bytes
+ * per row.  Returns the step's ticket (>= 0) or an ORBX_E_* code.  The host buffers may be reused once the step's
+ * copy-in has run, i.e. after orbp_wait of this ticket (or orbp_drain). */
+long long orbp_submit(orbp_pipeline* p, const uint8_t* const* images, size_t frame_stride, size_t row_stride);
+int orbp_wait(orbp_pipeline* p, long long ticket, orbp_result* out);
+int orbp_drain(orbp_pipeline* p);
+/* cudaStream_t of the pipeline: 0 copy-in, 1 extraction, 2 matching, 3 copy-out (to time or to order foreign work). */
+void* orbp_stream(orbp_pipeline* p, int which);
+long long orbp_launch_count(const orbp_pipeline* p);
 
 /* ---- multi-GPU: the one collective of the path ------------------------------------------------------------
  * One process per GPU.  Camera streams are dealt over the ranks; every rank extracts its cameras and the

@@ -68,6 +68,20 @@ class PyramidView(C.Structure):
                 ("scale", C.c_float * 16), ("inv_scale", C.c_float * 16), ("stream", C.c_void_p)]
 
 
+class PipelineConfig(C.Structure):
+    """orbp_config (include/orb_b200.h)."""
+    _fields_ = [("n_cams", C.c_int32), ("nfeatures", C.c_int32 * 8), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("rig_frames", C.c_int32), ("depth", C.c_int32), ("match", C.c_int32), ("window", C.c_int32),
+                ("nnratio", C.c_float), ("check_ori", C.c_int32), ("device", C.c_int32)]
+
+
+class PipelineResult(C.Structure):
+    """orbp_result (include/orb_b200.h)."""
+    _fields_ = [("kps", C.c_void_p * 8), ("desc", C.c_void_p * 8), ("counts", C.c_void_p * 8), ("cap", C.c_int32 * 8),
+                ("matches12", C.c_void_p), ("nmatches", C.c_void_p), ("rig_frames", C.c_int32)]
+
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} is missing: build it with `python -m multi_orb_slam_b200.build` "
@@ -110,6 +124,7 @@ _SIGS = {
                                                   _vp, _vp]),
     "orbm_search_for_initialization_host": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, Bounds, _vp, _i, _f, _i,
                                                 _vp, _vp]),
+    "orbm_debug_set_row_budget": (_i, [_vp, _i]),
     "orbm_search_by_projection_points_host": (_i, [_vp, _vp, _vp, _vp, _i, Bounds, _vp, _i, _vp, _vp, _vp, _i, _f, _f,
                                                   _vp, _vp, C.POINTER(_i)]),
     "orbm_search_by_projection_frame_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, Bounds, _vp, _i, Camera, _vp, _vp, _vp, _vp,
@@ -141,6 +156,15 @@ _SIGS = {
     "orbm_search_for_triangulation_batch_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
     "orbm_search_for_triangulation_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, FeatVec, _vp, _vp, _vp, _vp, _vp, _i,
                                                FeatVec, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, C.POINTER(_i)]),
+    "orbp_create": (_i, [C.POINTER(PipelineConfig), C.POINTER(_vp)]),
+    "orbp_destroy": (None, [_vp]),
+    "orbp_last_error": (C.c_char_p, [_vp]),
+    "orbp_capacity": (_i, [_vp, _i]),
+    "orbp_submit": (C.c_longlong, [_vp, _vp, _sz, _sz]),
+    "orbp_wait": (_i, [_vp, C.c_longlong, C.POINTER(PipelineResult)]),
+    "orbp_drain": (_i, [_vp]),
+    "orbp_stream": (_vp, [_vp, _i]),
+    "orbp_launch_count": (C.c_longlong, [_vp]),
     "orbd_get_unique_id": (_i, [_vp]),
     "orbd_comm_create": (_i, [_i, _i, _vp, _i, C.POINTER(_vp)]),
     "orbd_comm_destroy": (None, [_vp]),

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liborb_b200.so")
-SOURCES = ["extract_kernels.cu", "extract_api.cu", "matcher.cu", "dist_api.cu"]
+SOURCES = ["extract_kernels.cu", "extract_api.cu", "matcher.cu", "dist_api.cu", "pipeline_api.cu"]
 HEADERS = ["device_guard.h", "extract_kernels.h", "orb_geom.h", "octree_core.h", "orb_pattern.h", "../../include/orb_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

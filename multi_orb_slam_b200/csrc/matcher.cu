@@ -1244,10 +1244,13 @@ __global__ void __launch_bounds__(256) k_proj_candidates(const orbx_keypoint* __
                                                          const orbm_mappoint* __restrict__ mp,
                                                          const uint8_t* __restrict__ mp_desc, int nmp, float th,
                                                          int count_only, int* __restrict__ row_cnt,
-                                                         const int* __restrict__ row_off, uint32_t* __restrict__ rows) {
+                                                         const int* __restrict__ row_off, uint32_t* __restrict__ rows,
+                                                         long long rows_cap = 0) {
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= nmp) return;
+  // rows_cap > 0: row buffer sized from earlier calls (see k_query_candidates); rows that would not fit are not written
+  if (!count_only && rows_cap > 0 && (long long)row_off[i] + row_cnt[i] > rows_cap) return;
   const orbm_mappoint p = mp[i];
   int cnt = 0;
   if (p.track_in_view && !p.bad) {
@@ -1321,8 +1324,10 @@ __global__ void __launch_bounds__(1024) k_proj_resolve_cta(const int* __restrict
                                                            const int32_t* __restrict__ mp_obs, int nmp, int n, float nnratio,
                                                            int32_t* __restrict__ frame_mp, const int32_t* __restrict__ frame_mp_obs,
                                                            uint8_t* __restrict__ held_global, int held_in_smem,
-                                                           int* __restrict__ nmatches_out) {
+                                                           int* __restrict__ nmatches_out,
+                                                           const int* __restrict__ rows_needed = nullptr, long long rows_cap = 0) {
   extern __shared__ __align__(16) uint8_t s_held[];
+  if (rows_needed && *rows_needed > rows_cap) return;  // the row buffer overflowed: the host repeats the call
   // per-round exchange, double-buffered by round parity: two barriers per round instead of three
   __shared__ int s_bidx[2][32], s_sidx[2][32], s_will[2][32];
   __shared__ unsigned s_done[2], s_left[2];
@@ -1467,7 +1472,8 @@ __global__ void __launch_bounds__(256) k_query_candidates(const orbx_keypoint* _
                                                           const uint16_t* __restrict__ grid_items, int n_frame_kps,
                                                           const ProjQuery* __restrict__ q, const uint8_t* __restrict__ q_desc,
                                                           int nq, int count_only, int* __restrict__ row_cnt,
-                                                          const int* __restrict__ row_off, uint32_t* __restrict__ rows) {
+                                                          const int* __restrict__ row_off, uint32_t* __restrict__ rows,
+                                                          long long rows_cap = 0) {
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= nq) return;
@@ -1481,6 +1487,10 @@ __global__ void __launch_bounds__(256) k_query_candidates(const orbx_keypoint* _
   gv.inv_h = __fdiv_rn((float)GRID_ROWS, __fsub_rn(b.max_y, b.min_y));
   const uint4* qd = reinterpret_cast<const uint4*>(q_desc + (size_t)p.src * 32);
   const uint4 qa = __ldg(qd), qb = __ldg(qd + 1);
+  // count_only 1: count; 0: fill rows + row_off[i].  rows_cap > 0: the row buffer was sized from a previous call's need
+  // instead of this call's exact total (no host round trip between the count and the fill); a query whose rows would
+  // not fit writes nothing and the host repeats the call with the exact size (the scan's total says so).
+  if (!count_only && rows_cap > 0 && (long long)row_off[i] + row_cnt[i] > rows_cap) return;
   uint32_t* row = count_only ? nullptr : rows + row_off[i];
   int cnt = 0;
   grid_query(gv, k, p.u, p.v, p.radius, p.min_level, p.max_level, [&](bool ok, int idx) {
@@ -1574,7 +1584,9 @@ __global__ void __launch_bounds__(32) k_query_resolve_best(const ProjQuery* __re
                                                            int32_t* __restrict__ frame_mp, const int32_t* __restrict__ frame_mp_obs,
                                                            uint8_t* __restrict__ held_global, int held_in_smem,
                                                            int32_t* __restrict__ acc_idx, int32_t* __restrict__ acc_bin,
-                                                           int* __restrict__ nmatches_out) {
+                                                           int* __restrict__ nmatches_out,
+                                                           const int* __restrict__ rows_needed = nullptr, long long rows_cap = 0) {
+  if (rows_needed && *rows_needed > rows_cap) return;  // see k_query_resolve_cta
   extern __shared__ __align__(16) uint8_t s_held[];
   __shared__ uint32_t s_rows[RESOLVE_WIN];
   __shared__ int s_hist[HISTO_LENGTH];
@@ -1722,6 +1734,24 @@ struct orbm_matcher {
     if (e == cudaSuccess) return true;
     err = std::string(what) + ": " + cudaGetErrorString(e);
     return false;
+  }
+  // pinned host staging of the single-call host entry points: every input of a call is packed into ONE block and
+  // goes up in ONE copy, every output comes back in one (pageable cudaMemcpyAsync calls cost ~10 us each)
+  uint8_t* pin[2] = {nullptr, nullptr};
+  size_t pin_bytes[2] = {0, 0};
+  size_t rows_hint = 0;  // candidate-row capacity that was enough for the previous calls (run_projected)
+  int rows_per_query = 64;  // first guess of that capacity (orbm_debug_set_row_budget)
+  uint8_t* pinned(int slot, size_t bytes) {
+    if (bytes > pin_bytes[slot]) {
+      cudaStreamSynchronize(stream);
+      if (pin[slot]) cudaFreeHost(pin[slot]);
+      pin[slot] = nullptr;
+      pin_bytes[slot] = 0;
+      const size_t want = bytes + bytes / 2;
+      if (!check(cudaHostAlloc((void**)&pin[slot], want, cudaHostAllocDefault), "cudaHostAlloc(matcher staging)")) return nullptr;
+      pin_bytes[slot] = want;
+    }
+    return pin[slot];
   }
   template <typename T> T* scratch(int slot, size_t count) {
     const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
@@ -1891,6 +1921,13 @@ int orbm_bruteforce_indexed_device(orbm_matcher* m, int n_pairs, int cap, const 
   return m->check(cudaGetLastError(), "bruteforce indexed launch") ? ORBX_OK : ORBX_E_CUDA;
 }
 
+int orbm_debug_set_row_budget(orbm_matcher* m, int rows_per_query) {
+  if (!m || rows_per_query < 1) return ORBX_E_INVALID;
+  m->rows_per_query = rows_per_query;
+  m->rows_hint = 0;
+  return ORBX_OK;
+}
+
 int orbm_search_for_initialization_device(orbm_matcher* m, int n_pairs, int cap, const orbx_keypoint* d_k1,
                                           const uint8_t* d_d1, const int32_t* d_n1, const orbx_keypoint* d_k2,
                                           const uint8_t* d_d2, const int32_t* d_n2, orbm_bounds bounds2,
@@ -1976,58 +2013,76 @@ int orbm_search_by_projection_points_host(orbm_matcher* m, const orbx_keypoint* 
     }
   OrbDeviceGuard dev_guard(m->device);
   cudaStream_t st = m->stream;
-  // frame side
-  const size_t frame_bytes = (size_t)n * (sizeof(orbx_keypoint) + 32 + 4 + 4 + 4 + 1) + 64 * 4;
-  uint8_t* fb = m->scratch<uint8_t>(8, frame_bytes + 256);
-  // map-point side
-  const size_t mp_bytes = (size_t)nmp * (sizeof(orbm_mappoint) + 32 + 4 + 4 + 4) + 256;
-  uint8_t* mb = m->scratch<uint8_t>(9, mp_bytes);
+  // one device block [uploaded inputs | working arrays], inputs packed in one pinned block: ONE H2D copy (run_projected)
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t o_desc = 0, o_k = up(o_desc + (size_t)n * 32), o_ur = up(o_k + sizeof(orbx_keypoint) * n),
+               o_fmp = up(o_ur + 4 * (size_t)n), o_fobs = up(o_fmp + 4 * (size_t)n), o_sf = up(o_fobs + 4 * (size_t)n),
+               o_md = up(o_sf + 4 * 64), o_mp = up(o_md + (size_t)nmp * 32), o_mobs = up(o_mp + sizeof(orbm_mappoint) * nmp),
+               o_misc = up(o_mobs + 4 * (size_t)nmp), in_bytes = up(o_misc + 8 * sizeof(int));
+  const size_t o_held = in_bytes, o_cnt = up(o_held + n), o_off = up(o_cnt + 4 * (size_t)nmp), total_bytes = up(o_off + 4 * (size_t)nmp);
+  uint8_t* dev = m->scratch<uint8_t>(8, total_bytes);
+  uint8_t* hin = m->pinned(0, in_bytes);
   int* gstart = m->scratch<int>(4, GRID_CELLS + 1);
   uint16_t* gitems = m->scratch<uint16_t>(5, n);
-  int* misc = m->scratch<int>(10, 8);
-  if (!fb || !mb || !gstart || !gitems || !misc) return ORBX_E_CUDA;
-  uint8_t* dd = fb;  // descriptors first: uint4 loads need 16-byte alignment
-  orbx_keypoint* dk = reinterpret_cast<orbx_keypoint*>(dd + (size_t)n * 32);
-  float* dur = reinterpret_cast<float*>(dk + n);
-  int32_t* dfmp = reinterpret_cast<int32_t*>(dur + n);
-  int32_t* dfobs = dfmp + n;
-  float* dsf = reinterpret_cast<float*>(dfobs + n);
-  uint8_t* dheld = reinterpret_cast<uint8_t*>(dsf + 64);
-  uint8_t* dmd = mb;
-  orbm_mappoint* dmp = reinterpret_cast<orbm_mappoint*>(dmd + (size_t)nmp * 32);
-  int32_t* dmobs = reinterpret_cast<int32_t*>(dmp + nmp);
-  int* drow_cnt = dmobs + nmp;
-  int* drow_off = drow_cnt + nmp;
-  cudaMemcpyAsync(dk, k, sizeof(orbx_keypoint) * n, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dd, desc, (size_t)n * 32, cudaMemcpyHostToDevice, st);
-  if (u_right) cudaMemcpyAsync(dur, u_right, sizeof(float) * n, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dfmp, frame_mp, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
-  if (frame_mp_obs) cudaMemcpyAsync(dfobs, frame_mp_obs, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dsf, scale_factors, sizeof(float) * nlevels, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dmp, mp, sizeof(orbm_mappoint) * nmp, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dmd, mp_desc, (size_t)nmp * 32, cudaMemcpyHostToDevice, st);
-  if (mp_obs) cudaMemcpyAsync(dmobs, mp_obs, sizeof(int32_t) * nmp, cudaMemcpyHostToDevice, st);
-  k_build_grid<<<1, 256, 0, st>>>(dk, nullptr, n, n, bounds, gstart, gitems);
-  const int blocks = (nmp + 7) / 8;
-  k_proj_candidates<<<blocks, 256, 0, st>>>(dk, dd, u_right ? dur : nullptr, bounds, gstart, gitems, dsf, dmp, dmd, nmp, th, 1,
-                                            drow_cnt, nullptr, nullptr);
-  k_scan_exclusive<<<1, 1024, 0, st>>>(drow_cnt, drow_off, nmp, misc);
-  m->launches += 3;
-  int total = 0;
-  cudaMemcpyAsync(&total, misc, sizeof(int), cudaMemcpyDeviceToHost, st);
-  if (!m->check(cudaStreamSynchronize(st), "projection candidates (count)")) return ORBX_E_CUDA;
-  uint32_t* rows = m->scratch<uint32_t>(6, (size_t)total);
-  if (!rows) return ORBX_E_CUDA;
-  k_proj_candidates<<<blocks, 256, 0, st>>>(dk, dd, u_right ? dur : nullptr, bounds, gstart, gitems, dsf, dmp, dmd, nmp, th, 0,
-                                            drow_cnt, drow_off, rows);
-  const int held_in_smem = n <= 40960;  // occupancy bytes on chip when they fit
-  k_proj_resolve_cta<<<1, 1024, held_in_smem ? (size_t)((n + 15) & ~15) : 0, st>>>(
-      drow_cnt, drow_off, rows, mp_obs ? dmobs : nullptr, nmp, n, nnratio, dfmp, frame_mp_obs ? dfobs : nullptr, dheld,
-      held_in_smem, misc + 1);
-  m->launches += 2;
-  cudaMemcpyAsync(frame_mp, dfmp, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st);
-  cudaMemcpyAsync(nmatches, misc + 1, sizeof(int), cudaMemcpyDeviceToHost, st);
-  if (!m->check(cudaStreamSynchronize(st), "search_by_projection")) return ORBX_E_CUDA;
+  if (!dev || !hin || !gstart || !gitems) return ORBX_E_CUDA;
+  size_t rows_cap = std::max<size_t>(m->rows_hint, (size_t)nmp * m->rows_per_query);
+  int total = 0, got = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    uint32_t* rows = m->scratch<uint32_t>(6, rows_cap);
+    uint8_t* hout = m->pinned(1, 4 * (size_t)n + 8 * sizeof(int));
+    if (!rows || !hout) return ORBX_E_CUDA;
+    std::memcpy(hin + o_desc, desc, (size_t)n * 32);
+    std::memcpy(hin + o_k, k, sizeof(orbx_keypoint) * n);
+    float* h_ur = reinterpret_cast<float*>(hin + o_ur);
+    if (u_right) std::memcpy(h_ur, u_right, 4 * (size_t)n); else std::fill(h_ur, h_ur + n, -1.f);
+    std::memcpy(hin + o_fmp, frame_mp, 4 * (size_t)n);
+    if (frame_mp_obs) std::memcpy(hin + o_fobs, frame_mp_obs, 4 * (size_t)n); else std::memset(hin + o_fobs, 0, 4 * (size_t)n);
+    std::memcpy(hin + o_sf, scale_factors, sizeof(float) * nlevels);
+    std::memcpy(hin + o_md, mp_desc, (size_t)nmp * 32);
+    std::memcpy(hin + o_mp, mp, sizeof(orbm_mappoint) * nmp);
+    int32_t* h_mobs = reinterpret_cast<int32_t*>(hin + o_mobs);
+    if (mp_obs) std::memcpy(h_mobs, mp_obs, 4 * (size_t)nmp); else std::fill(h_mobs, h_mobs + nmp, 1);
+    std::memset(hin + o_misc, 0, 8 * sizeof(int));  // [0] total candidate rows (scan), [2] nmatches
+    if (!m->check(cudaMemcpyAsync(dev, hin, in_bytes, cudaMemcpyHostToDevice, st), "H2D search_by_projection")) return ORBX_E_CUDA;
+    uint8_t* dd = dev + o_desc;
+    orbx_keypoint* dk = reinterpret_cast<orbx_keypoint*>(dev + o_k);
+    float* dur = reinterpret_cast<float*>(dev + o_ur);
+    int32_t* dfmp = reinterpret_cast<int32_t*>(dev + o_fmp);
+    int32_t* dfobs = reinterpret_cast<int32_t*>(dev + o_fobs);
+    float* dsf = reinterpret_cast<float*>(dev + o_sf);
+    uint8_t* dmd = dev + o_md;
+    orbm_mappoint* dmp = reinterpret_cast<orbm_mappoint*>(dev + o_mp);
+    int32_t* dmobs = reinterpret_cast<int32_t*>(dev + o_mobs);
+    int* misc = reinterpret_cast<int*>(dev + o_misc);
+    uint8_t* dheld = dev + o_held;
+    int* drow_cnt = reinterpret_cast<int*>(dev + o_cnt);
+    int* drow_off = reinterpret_cast<int*>(dev + o_off);
+    k_build_grid<<<1, 256, 0, st>>>(dk, nullptr, n, n, bounds, gstart, gitems);
+    const int blocks = (nmp + 7) / 8;
+    k_proj_candidates<<<blocks, 256, 0, st>>>(dk, dd, dur, bounds, gstart, gitems, dsf, dmp, dmd, nmp, th, 1, drow_cnt, nullptr,
+                                              nullptr);
+    k_scan_exclusive<<<1, 1024, 0, st>>>(drow_cnt, drow_off, nmp, misc);  // misc[0] = total rows needed
+    k_proj_candidates<<<blocks, 256, 0, st>>>(dk, dd, dur, bounds, gstart, gitems, dsf, dmp, dmd, nmp, th, 0, drow_cnt, drow_off,
+                                              rows, (long long)rows_cap);
+    const int held_in_smem = n <= 40960;  // occupancy bytes on chip when they fit
+    k_proj_resolve_cta<<<1, 1024, held_in_smem ? (size_t)((n + 15) & ~15) : 0, st>>>(
+        drow_cnt, drow_off, rows, dmobs, nmp, n, nnratio, dfmp, dfobs, dheld, held_in_smem, misc + 2, misc, (long long)rows_cap);
+    m->launches += 5;
+    cudaMemcpyAsync(hout, dfmp, 4 * (size_t)n, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(hout + 4 * (size_t)n, misc, 8 * sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (!m->check(cudaStreamSynchronize(st), "search_by_projection")) return ORBX_E_CUDA;
+    const int* r = reinterpret_cast<const int*>(hout + 4 * (size_t)n);
+    total = r[0];
+    got = r[2];
+    if ((size_t)total <= rows_cap) {
+      std::memcpy(frame_mp, hout, 4 * (size_t)n);
+      break;
+    }
+    if (attempt == 1) { m->err = "candidate rows overflowed twice"; return ORBX_E_CAPACITY; }
+    rows_cap = (size_t)total + (size_t)total / 4;
+  }
+  m->rows_hint = std::max(m->rows_hint, (size_t)total + (size_t)total / 4);
+  *nmatches = got;
   return m->check(cudaGetLastError(), "search_by_projection launch") ? ORBX_OK : ORBX_E_CUDA;
 }
 
@@ -2529,9 +2584,11 @@ __global__ void __launch_bounds__(1024) k_query_resolve_cta(const ProjQuery* __r
                                                             const int32_t* __restrict__ frame_mp_obs,
                                                             uint8_t* __restrict__ held_global, int held_in_smem,
                                                             int32_t* __restrict__ acc_idx, int32_t* __restrict__ acc_bin,
-                                                            int* __restrict__ nmatches_out) {
+                                                            int* __restrict__ nmatches_out,
+                                                            const int* __restrict__ rows_needed = nullptr, long long rows_cap = 0) {
   extern __shared__ __align__(16) uint8_t s_held[];
   __shared__ int s_hist[HISTO_LENGTH];
+  if (rows_needed && *rows_needed > rows_cap) return;  // the row buffer overflowed: the host repeats the call (run_projected)
   // per-round exchange, double-buffered by round parity: two barriers per round instead of three
   __shared__ int s_bidx[2][32];
   __shared__ unsigned s_done[2], s_left[2];
@@ -2656,72 +2713,97 @@ int run_projected(orbm_matcher* m, const orbx_keypoint* k, const uint8_t* desc, 
   if (n == 0 || nq == 0) return ORBX_OK;
   OrbDeviceGuard dev_guard(m->device);
   cudaStream_t st = m->stream;
-  const size_t frame_bytes = (size_t)n * (32 + sizeof(orbx_keypoint) + 4 + 4 + 4 + 4 + 1) + 256;
-  uint8_t* fb = m->scratch<uint8_t>(8, frame_bytes);
-  const size_t q_bytes = (size_t)n_src * 32 + (size_t)nq * (sizeof(ProjQuery) + 4 + 4 + 4 + 4) + 256;
-  uint8_t* qb = m->scratch<uint8_t>(9, q_bytes);
+  // One device block: [uploaded inputs | working arrays].  The inputs are packed into one pinned host block with the
+  // same layout and go up in ONE copy; the outputs (frame_mp, nmatches, the row cursor) come back in one.
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t o_desc = 0, o_k = up(o_desc + (size_t)n * 32), o_ur = up(o_k + sizeof(orbx_keypoint) * n),
+               o_cam = up(o_ur + 4 * (size_t)n), o_fmp = up(o_cam + 4 * (size_t)n), o_fobs = up(o_fmp + 4 * (size_t)n),
+               o_sd = up(o_fobs + 4 * (size_t)n), o_q = up(o_sd + (size_t)n_src * 32), o_misc = up(o_q + sizeof(ProjQuery) * nq),
+               in_bytes = up(o_misc + 8 * sizeof(int));
+  const size_t o_held = in_bytes, o_cnt = up(o_held + n), o_off = up(o_cnt + 4 * (size_t)nq), o_ai = up(o_off + 4 * (size_t)nq),
+               o_ab = up(o_ai + 4 * (size_t)nq), total_bytes = up(o_ab + 4 * (size_t)nq);
+  uint8_t* dev = m->scratch<uint8_t>(8, total_bytes);
+  uint8_t* hin = m->pinned(0, in_bytes);
   int* gstart = m->scratch<int>(4, (size_t)n_cams * (GRID_CELLS + 1));
   uint16_t* gitems = m->scratch<uint16_t>(5, (size_t)n_cams * n);
-  int* misc = m->scratch<int>(10, 8);
-  if (!fb || !qb || !gstart || !gitems || !misc) return ORBX_E_CUDA;
-  uint8_t* dd = fb;
-  orbx_keypoint* dk = reinterpret_cast<orbx_keypoint*>(dd + (size_t)n * 32);
-  float* dur = reinterpret_cast<float*>(dk + n);
-  int32_t* dcam = reinterpret_cast<int32_t*>(dur + n);
-  int32_t* dfmp = dcam + n;
-  int32_t* dfobs = dfmp + n;
-  uint8_t* dheld = reinterpret_cast<uint8_t*>(dfobs + n);
-  uint8_t* dsd = qb;
-  ProjQuery* dq = reinterpret_cast<ProjQuery*>(dsd + (size_t)n_src * 32);
-  int* drow_cnt = reinterpret_cast<int*>(dq + nq);
-  int* drow_off = drow_cnt + nq;
-  int32_t* dacc_idx = drow_off + nq;
-  int32_t* dacc_bin = dacc_idx + nq;
-  cudaMemcpyAsync(dk, k, sizeof(orbx_keypoint) * n, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dd, desc, (size_t)n * 32, cudaMemcpyHostToDevice, st);
-  if (u_right) cudaMemcpyAsync(dur, u_right, sizeof(float) * n, cudaMemcpyHostToDevice, st);
-  if (cam_of) cudaMemcpyAsync(dcam, cam_of, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dfmp, frame_mp, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
-  if (frame_mp_obs) cudaMemcpyAsync(dfobs, frame_mp_obs, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dsd, src_desc, (size_t)n_src * 32, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dq, q.data(), sizeof(ProjQuery) * nq, cudaMemcpyHostToDevice, st);
-  for (int c = 0; c < n_cams; ++c) {
-    k_build_grid<<<1, 256, 0, st>>>(dk, nullptr, n, n, bounds, gstart + (size_t)c * (GRID_CELLS + 1), gitems + (size_t)c * n,
-                                    cam_of ? dcam : nullptr, c);
-    m->launches++;
+  if (!dev || !hin || !gstart || !gitems) return ORBX_E_CUDA;
+  // candidate rows: a capacity that was enough before (starts at 64 per query); an overflow repeats the call once
+  // (queries whose rows do not fit are skipped by the fill, so nothing is written out of bounds)
+  size_t rows_cap = std::max<size_t>(m->rows_hint, (size_t)nq * m->rows_per_query);
+  int total = 0, got = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    uint32_t* rows = m->scratch<uint32_t>(6, rows_cap);
+    uint8_t* hout = m->pinned(1, 4 * (size_t)n + 8 * sizeof(int));
+    if (!rows || !hout) return ORBX_E_CUDA;
+    std::memcpy(hin + o_desc, desc, (size_t)n * 32);
+    std::memcpy(hin + o_k, k, sizeof(orbx_keypoint) * n);
+    float* h_ur = reinterpret_cast<float*>(hin + o_ur);
+    if (u_right) std::memcpy(h_ur, u_right, 4 * (size_t)n); else std::fill(h_ur, h_ur + n, -1.f);
+    if (cam_of) std::memcpy(hin + o_cam, cam_of, 4 * (size_t)n); else std::memset(hin + o_cam, 0, 4 * (size_t)n);
+    std::memcpy(hin + o_fmp, frame_mp, 4 * (size_t)n);
+    if (frame_mp_obs) std::memcpy(hin + o_fobs, frame_mp_obs, 4 * (size_t)n); else std::memset(hin + o_fobs, 0, 4 * (size_t)n);
+    std::memcpy(hin + o_sd, src_desc, (size_t)n_src * 32);
+    std::memcpy(hin + o_q, q.data(), sizeof(ProjQuery) * nq);
+    int* h_misc = reinterpret_cast<int*>(hin + o_misc);  // [0] total candidate rows (scan), [2] nmatches
+    h_misc[0] = 0; h_misc[1] = 0; h_misc[2] = 0;
+    if (!m->check(cudaMemcpyAsync(dev, hin, in_bytes, cudaMemcpyHostToDevice, st), "H2D projected search")) return ORBX_E_CUDA;
+    uint8_t* dd = dev + o_desc;
+    orbx_keypoint* dk = reinterpret_cast<orbx_keypoint*>(dev + o_k);
+    float* dur = reinterpret_cast<float*>(dev + o_ur);
+    int32_t* dcam = reinterpret_cast<int32_t*>(dev + o_cam);
+    int32_t* dfmp = reinterpret_cast<int32_t*>(dev + o_fmp);
+    int32_t* dfobs = reinterpret_cast<int32_t*>(dev + o_fobs);
+    uint8_t* dsd = dev + o_sd;
+    ProjQuery* dq = reinterpret_cast<ProjQuery*>(dev + o_q);
+    int* misc = reinterpret_cast<int*>(dev + o_misc);
+    uint8_t* dheld = dev + o_held;
+    int* drow_cnt = reinterpret_cast<int*>(dev + o_cnt);
+    int* drow_off = reinterpret_cast<int*>(dev + o_off);
+    int32_t* dacc_idx = reinterpret_cast<int32_t*>(dev + o_ai);
+    int32_t* dacc_bin = reinterpret_cast<int32_t*>(dev + o_ab);
+    for (int c = 0; c < n_cams; ++c) {
+      k_build_grid<<<1, 256, 0, st>>>(dk, nullptr, n, n, bounds, gstart + (size_t)c * (GRID_CELLS + 1), gitems + (size_t)c * n,
+                                      dcam, c);
+      m->launches++;
+    }
+    const int blocks = (nq + 7) / 8;
+    k_query_candidates<<<blocks, 256, 0, st>>>(dk, dd, dur, bounds, gstart, gitems, n, dq, dsd, nq, 1, drow_cnt, nullptr, nullptr);
+    k_scan_exclusive<<<1, 1024, 0, st>>>(drow_cnt, drow_off, nq, misc);  // misc[0] = total rows needed
+    k_query_candidates<<<blocks, 256, 0, st>>>(dk, dd, dur, bounds, gstart, gitems, n, dq, dsd, nq, 0, drow_cnt, drow_off, rows,
+                                               (long long)rows_cap);
+    m->launches += 2;
+    const int held_in_smem = n <= 32768;  // occupancy bytes on chip when they fit beside the 8 KB row window
+    const size_t held_bytes = held_in_smem ? (size_t)((n + 15) & ~15) : 0;
+    bool grouped = false;  // consecutive queries of one source point (Sim3 overload: best over both cameras)
+    for (int i = 1; i < nq && !grouped; ++i) grouped = q[i].src == q[i - 1].src;
+    if (grouped) {
+      k_query_resolve_best<<<1, 32, held_bytes, st>>>(dq, drow_cnt, drow_off, rows, (int)std::min<size_t>(rows_cap, 0x7fffffff), nq,
+                                                      n, dk, th_dist, check_ori, any_point_blocks, dfmp, dfobs, dheld, held_in_smem,
+                                                      dacc_idx, dacc_bin, misc + 2, misc, (long long)rows_cap);
+    } else {
+      k_query_resolve_cta<<<1, 1024, held_bytes, st>>>(dq, drow_cnt, drow_off, rows, nq, n, dk, th_dist, check_ori,
+                                                       any_point_blocks, dfmp, dfobs, dheld, held_in_smem, dacc_idx, dacc_bin,
+                                                       misc + 2, misc, (long long)rows_cap);
+    }
+    m->launches += 2;
+    // the outputs are adjacent on the device only in part: two small copies into one pinned block, one synchronisation
+    cudaMemcpyAsync(hout, dfmp, 4 * (size_t)n, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(hout + 4 * (size_t)n, misc, 8 * sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (!m->check(cudaStreamSynchronize(st), "projected search")) return ORBX_E_CUDA;
+    const int* r = reinterpret_cast<const int*>(hout + 4 * (size_t)n);
+    total = r[0];
+    got = r[2];
+    if ((size_t)total <= rows_cap) {
+      std::memcpy(frame_mp, hout, 4 * (size_t)n);
+      break;
+    }
+    if (attempt == 1) { m->err = "candidate rows overflowed twice"; return ORBX_E_CAPACITY; }
+    rows_cap = (size_t)total + (size_t)total / 4;  // the scan counted every query's rows: this is the exact need
   }
-  const int blocks = (nq + 7) / 8;
-  k_query_candidates<<<blocks, 256, 0, st>>>(dk, dd, u_right ? dur : nullptr, bounds, gstart, gitems, n, dq, dsd, nq, 1,
-                                             drow_cnt, nullptr, nullptr);
-  k_scan_exclusive<<<1, 1024, 0, st>>>(drow_cnt, drow_off, nq, misc);
-  m->launches += 2;
-  int total = 0;
-  cudaMemcpyAsync(&total, misc, sizeof(int), cudaMemcpyDeviceToHost, st);
-  if (!m->check(cudaStreamSynchronize(st), "projected search (count)")) return ORBX_E_CUDA;
-  uint32_t* rows = m->scratch<uint32_t>(6, (size_t)total);
-  if (!rows) return ORBX_E_CUDA;
-  k_query_candidates<<<blocks, 256, 0, st>>>(dk, dd, u_right ? dur : nullptr, bounds, gstart, gitems, n, dq, dsd, nq, 0,
-                                             drow_cnt, drow_off, rows);
-  const int held_in_smem = n <= 32768;  // occupancy bytes on chip when they fit beside the 8 KB row window
-  const size_t held_bytes = held_in_smem ? (size_t)((n + 15) & ~15) : 0;
-  bool grouped = false;  // consecutive queries of one source point (Sim3 overload: best over both cameras)
-  for (int i = 1; i < nq && !grouped; ++i) grouped = q[i].src == q[i - 1].src;
-  if (grouped) {
-    k_query_resolve_best<<<1, 32, held_bytes, st>>>(dq, drow_cnt, drow_off, rows, total, nq, n, dk, th_dist, check_ori,
-                                                    any_point_blocks, dfmp, frame_mp_obs ? dfobs : nullptr, dheld,
-                                                    held_in_smem, dacc_idx, dacc_bin, misc + 1);
-  } else {
-    k_query_resolve_cta<<<1, 1024, held_bytes, st>>>(dq, drow_cnt, drow_off, rows, nq, n, dk, th_dist, check_ori,
-                                                     any_point_blocks, dfmp, frame_mp_obs ? dfobs : nullptr, dheld,
-                                                     held_in_smem, dacc_idx, dacc_bin, misc + 1);
-  }
-  m->launches += 2;
-  cudaMemcpyAsync(frame_mp, dfmp, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st);
-  cudaMemcpyAsync(nmatches, misc + 1, sizeof(int), cudaMemcpyDeviceToHost, st);
-  if (!m->check(cudaStreamSynchronize(st), "projected search")) return ORBX_E_CUDA;
+  m->rows_hint = std::max(m->rows_hint, (size_t)total + (size_t)total / 4);
+  *nmatches = got;
   return m->check(cudaGetLastError(), "projected search launch") ? ORBX_OK : ORBX_E_CUDA;
 }
-
 }  // namespace
 
 extern "C" {

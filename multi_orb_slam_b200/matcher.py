@@ -137,6 +137,11 @@ class ORBmatcher:
             tables[3].data_ptr(), self.mfNNratio if ratio is None else ratio, th_dist, idx.data_ptr(), d1.data_ptr(),
             d2.data_ptr()))
 
+    def debug_set_row_budget(self, rows_per_query: int) -> None:
+        """Test tap (orbm_debug_set_row_budget): first guess of the candidate rows per query of the single-call
+        projection searches; 1 forces the overflow-and-repeat path."""
+        check_m(self._h, lib.orbm_debug_set_row_budget(self._h, int(rows_per_query)))
+
     # -- SearchForInitialization (src/ORBmatcher.cc:868-983) --------------------------------------
     def SearchForInitialization(self, F1: Frame, F2: Frame, vbPrevMatched: np.ndarray, windowSize: int = 10):
         """Returns (nmatches, vnMatches12); vbPrevMatched ([N1,2] f32) is updated in place."""

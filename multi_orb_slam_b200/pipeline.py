@@ -1,40 +1,37 @@
 """Streaming front end of a multi-camera rig: pinned host frames in, pinned host features out.
 
-What Tracking does per rig-frame in the reference (Frame::Frame runs one ORBextractor per camera,
-src/Frame.cc:75-140; MonocularInitialization matches consecutive frames of camera 1 with
-ORBmatcher::SearchForInitialization, src/Tracking.cc:870-871), batched over `rig_frames`
-rig-frames per step and software-pipelined over three CUDA streams:
-
-    copy-in   H2D of the next chunk of frames            (PCIe, DMA engine)
-    compute   extractor of every camera (all extractor kernels on ONE stream: they fill the GPU
-              on their own, running cameras concurrently only thrashes the caches)
-    match     SearchForInitialization of camera 0, on a high-priority side stream as soon as camera
-              0 is extracted: its ordered resolve is a serial chain per pair that leaves the SMs
-              ~90 % idle, so it runs underneath the extraction of the other cameras
-    copy-out  D2H of keypoints / descriptors / matches    (PCIe, the other DMA engine)
-
-Device image buffers and output buffers are `depth` (default 3) steps deep, so the copies of step
-k+1 overlap the kernels of step k even while the consumer still waits for step k-1; `submit` never
-blocks the host, `result` waits for one step.
+Thin Python view of the C-ABI pipeline (`orbp_*`, include/orb_b200.h; multi_orb_slam_b200/csrc/pipeline_api.cu) —
+the same object a C++ Tracking would drive.  What Tracking does per rig-frame in the reference (Frame::Frame runs one
+ORBextractor per camera, src/Frame.cc:148-346; MonocularInitialization matches consecutive frames of camera 1 with
+ORBmatcher::SearchForInitialization, src/Tracking.cc:870-871), batched over `rig_frames` rig-frames per step and
+software-pipelined over four CUDA streams inside the library (copy-in, extraction, matching on a high-priority side
+stream, copy-out; `depth` steps in flight).  `submit` never blocks the host, `result` waits for one step.
 There is no CPU fallback: the extractor and matcher are the CUDA library's."""
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass
-from typing import List, Sequence, Tuple
+from typing import Sequence, Tuple
 
-from ._lib import Bounds
-from .extractor import ORBextractor
-from .matcher import ORBmatcher
+import numpy as np
+
+from . import _lib
+from ._lib import KP_DTYPE, PipelineConfig, PipelineResult, lib
 
 
 @dataclass
 class RigStepResult:
-    """Pinned host tensors of one step (valid until the slot is reused `depth` submits later)."""
-    kps: list        # per camera [F, cap, 6] f32 (orbx_keypoint rows; column 5 = octave bits)
+    """Pinned host arrays of one step, owned by the pipeline (valid until the slot is reused `depth` submits later)."""
+    kps: list        # per camera [F, cap, 6] f32 torch view (orbx_keypoint rows; column 5 = octave bits)
     desc: list       # per camera [F, cap, 32] u8
     counts: list     # per camera [F] i32
-    matches12: object  # [F-1, cap0] i32: SearchForInitialization(frame t, frame t+1) of camera 0
+    matches12: object  # [F-1, cap0] i32: SearchForInitialization(frame t, frame t+1) of camera 0 (None without match)
     nmatches: object   # [F-1] i32
+
+    def keypoints(self, cam: int, frame: int) -> np.ndarray:
+        """KP_DTYPE view of one camera-frame's valid keypoints."""
+        n = int(self.counts[cam][frame])
+        return self.kps[cam][frame, :n].numpy().view(KP_DTYPE).reshape(-1)
 
 
 class RigPipeline:
@@ -44,132 +41,102 @@ class RigPipeline:
                  match: bool = True, device: int = 0):
         import torch
         self.torch = torch
-        self.F, self.depth, self.window, self.match = int(rig_frames), int(depth), int(window), bool(match)
+        if n_chunks != 1:
+            raise ValueError("the C-ABI pipeline submits a step in one piece (n_chunks = 1)")
+        self.n_chunks = 1
+        self.F, self.depth, self.window = int(rig_frames), max(2, int(depth)), int(window)
         self.W, self.H = int(image_size[0]), int(image_size[1])
-        self.n_chunks = max(1, min(int(n_chunks), self.F))
-        self.chunk = (self.F + self.n_chunks - 1) // self.n_chunks
-        self.dev = torch.device("cuda", device)
         self.n_cams = len(nfeatures)
-        self.s_in, self.s_compute, self.s_out = (torch.cuda.Stream(device=self.dev) for _ in range(3))
-        self.s_match = torch.cuda.Stream(device=self.dev, priority=-1)
-        self.ex: List[ORBextractor] = [
-            ORBextractor(nf, scaleFactor, nlevels, iniThFAST, minThFAST, image_size=image_size, max_batch=self.chunk,
-                         device=device) for nf in nfeatures]
-        for e in self.ex:
-            e.set_stream(self.s_compute.cuda_stream)
-        self.matcher = ORBmatcher(nnratio, True, device=device)
-        self.matcher.set_stream(self.s_match.cuda_stream)
-        self.caps = [e.capacity for e in self.ex]
-        self.bounds = Bounds(0.0, float(self.W), 0.0, float(self.H))
-        F, dev = self.F, self.dev
-        # ring of chunk-sized device image buffers, `depth` steps deep: with depth 3 the consumer can still be
-        # reading step k-2 while step k-1 computes and the frames of step k are already on their way
-        self.n_ring = self.depth * self.n_chunks
-        self.img = [[torch.empty((self.chunk, self.H, self.W), dtype=torch.uint8, device=dev) for _ in range(self.n_cams)]
-                    for _ in range(self.n_ring)]
-        self.img_free = [None] * self.n_ring
-
-        def outs(pin):
-            kw = dict(device=dev) if not pin else {}
-            mk = (lambda *a, **k: torch.empty(*a, **k).pin_memory()) if pin else torch.empty
-            return RigStepResult(
-                kps=[mk((F, c, 6), dtype=torch.float32, **kw) for c in self.caps],
-                desc=[mk((F, c, 32), dtype=torch.uint8, **kw) for c in self.caps],
-                counts=[mk((F,), dtype=torch.int32, **kw) for c in self.caps],
-                matches12=mk((max(F - 1, 1), self.caps[0]), dtype=torch.int32, **kw),
-                nmatches=mk((max(F - 1, 1),), dtype=torch.int32, **kw))
-
-        self.d_out = [outs(False) for _ in range(self.depth)]
-        self.h_out = [outs(True) for _ in range(self.depth)]
-        self.done = [None] * self.depth   # last D2H of the step that used the slot
+        self.match = bool(match) and self.F > 1
+        cfg = PipelineConfig()
+        cfg.n_cams = self.n_cams
+        for c, nf in enumerate(nfeatures):
+            cfg.nfeatures[c] = int(nf)
+        cfg.scale_factor, cfg.nlevels, cfg.ini_th_fast, cfg.min_th_fast = float(scaleFactor), int(nlevels), int(iniThFAST), int(minThFAST)
+        cfg.width, cfg.height, cfg.rig_frames, cfg.depth = self.W, self.H, self.F, self.depth
+        cfg.match, cfg.window, cfg.nnratio, cfg.check_ori, cfg.device = int(self.match), self.window, float(nnratio), 1, int(device)
+        h = C.c_void_p()
+        rc = lib.orbp_create(C.byref(cfg), C.byref(h))
+        if rc != _lib.OK:
+            raise _lib.OrbError(rc, (lib.orbp_last_error(None) or b"").decode())
+        self._h = h
+        self.caps = [lib.orbp_capacity(self._h, c) for c in range(self.n_cams)]
+        dev = torch.device("cuda", device)
+        self.dev = dev
+        # the library's streams, for callers that time or order work against the pipeline
+        self.s_in, self.s_compute, self.s_match, self.s_out = (
+            torch.cuda.ExternalStream(lib.orbp_stream(self._h, i), device=dev) for i in range(4))
         self.n_submitted = 0
+        self._keep = {}
+        F = self.F
         self.h2d_bytes_per_step = self.n_cams * F * self.H * self.W
-        self.d2h_bytes_per_step = sum(t.numel() * t.element_size()
-                                      for t in self.h_out[0].kps + self.h_out[0].desc + self.h_out[0].counts) + \
-            (self.h_out[0].matches12.numel() + self.h_out[0].nmatches.numel()) * 4 * int(self.match and F > 1)
+        self.d2h_bytes_per_step = sum(F * c * (24 + 32) + 4 * F for c in self.caps) + \
+            ((F - 1) * self.caps[0] * 4 + (F - 1) * 4) * int(self.match)
+
+    def _check(self, rc: int) -> None:
+        if rc != _lib.OK:
+            raise _lib.OrbError(rc, (lib.orbp_last_error(self._h) or b"").decode())
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib.orbp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     @property
     def launch_count(self) -> int:
-        return sum(e.launch_count for e in self.ex) + self.matcher.launch_count
+        return lib.orbp_launch_count(self._h) if self._h else 0
 
     def submit(self, h_images: Sequence) -> int:
-        """h_images: one pinned uint8 tensor [F, H, W] per camera.  Returns the step's ticket."""
-        torch = self.torch
-        step = self.n_submitted
-        self.n_submitted += 1
-        slot = step % self.depth
-        d, h = self.d_out[slot], self.h_out[slot]
-        if self.done[slot] is not None:
-            # the slot's previous results must have left the device before they are overwritten
-            self.s_compute.wait_event(self.done[slot])
-        ev_match = None
-        for ci in range(self.n_chunks):
-            f0, f1 = ci * self.chunk, min(self.F, (ci + 1) * self.chunk)
-            if f0 >= f1:
-                break
-            n = f1 - f0
-            b = (step * self.n_chunks + ci) % self.n_ring
-            # per-camera events: camera 0 starts computing while camera 1 is still uploading, and its
-            # features leave the device while camera 1 computes
-            ev_in, ev_done = [], []
-            with torch.cuda.stream(self.s_in):
-                if self.img_free[b] is not None:
-                    self.s_in.wait_event(self.img_free[b])
-                for c in range(self.n_cams):
-                    self.img[b][c][:n].copy_(h_images[c][f0:f1], non_blocking=True)
-                    ev_in.append(torch.cuda.Event())
-                    ev_in[c].record(self.s_in)
-            with torch.cuda.stream(self.s_compute):
-                for c in range(self.n_cams):
-                    self.s_compute.wait_event(ev_in[c])
-                    self.ex[c].extract_batch_device(self.img[b][c][:n], d.kps[c][f0:f1], d.desc[c][f0:f1], d.counts[c][f0:f1])
-                    ev_done.append(torch.cuda.Event())
-                    ev_done[c].record(self.s_compute)
-                    if c == 0 and f1 == self.F and self.match and self.F > 1:
-                        ev_match = self._launch_match(d)
-                self.img_free[b] = ev_done[-1]
-            with torch.cuda.stream(self.s_out):
-                for c in range(self.n_cams):
-                    self.s_out.wait_event(ev_done[c])
-                    h.kps[c][f0:f1].copy_(d.kps[c][f0:f1], non_blocking=True)
-                    h.desc[c][f0:f1].copy_(d.desc[c][f0:f1], non_blocking=True)
-                    h.counts[c][f0:f1].copy_(d.counts[c][f0:f1], non_blocking=True)
-        if self.match and self.F > 1:
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(ev_match)
-                h.matches12.copy_(d.matches12, non_blocking=True)
-                h.nmatches.copy_(d.nmatches, non_blocking=True)
-        self.done[slot] = torch.cuda.Event()
-        self.done[slot].record(self.s_out)
-        return step
-
-    def _launch_match(self, d: RigStepResult):
-        """Camera 0 of the whole step is extracted (s_compute): match it on the side stream."""
-        torch = self.torch
-        ev0 = torch.cuda.Event()
-        ev0.record(self.s_compute)
-        with torch.cuda.stream(self.s_match):
-            self.s_match.wait_event(ev0)
-            # pairs (t, t+1) of camera 0: the F2 arrays are the same buffers shifted by one frame
-            self.matcher.search_for_initialization_device(
-                self.F - 1, self.caps[0], d.kps[0], d.desc[0], d.counts[0], d.kps[0][1:], d.desc[0][1:], d.counts[0][1:],
-                self.bounds, None, self.window, d.matches12, d.nmatches)
-            ev = torch.cuda.Event()
-            ev.record(self.s_match)
-        return ev
+        """h_images: one uint8 tensor / array [F, H, W] per camera in host memory (pinned memory makes the copies
+        asynchronous; the same row / frame strides for all cameras).  Returns the step's ticket."""
+        assert len(h_images) == self.n_cams
+        a0 = h_images[0]
+        strides = (a0.stride(0), a0.stride(1)) if hasattr(a0, "stride") else (a0.strides[0], a0.strides[1])
+        ptrs = (C.c_void_p * self.n_cams)()
+        for c, a in enumerate(h_images):
+            assert tuple(a.shape) == (self.F, self.H, self.W)
+            st = (a.stride(0), a.stride(1)) if hasattr(a, "stride") else (a.strides[0], a.strides[1])
+            assert st == strides, "all cameras must share frame / row strides"
+            ptrs[c] = _lib.ptr(a)
+        t = lib.orbp_submit(self._h, ptrs, strides[0], strides[1])
+        if t < 0:
+            self._check(int(t))
+        self._keep[t % self.depth] = h_images  # the host frames must outlive their copy-in
+        self.n_submitted = t + 1
+        return int(t)
 
     def result(self, ticket: int) -> RigStepResult:
         """Blocks until the step's results are in pinned host memory."""
-        if ticket < self.n_submitted - self.depth or ticket >= self.n_submitted:
+        torch = self.torch
+        r = PipelineResult()
+        rc = lib.orbp_wait(self._h, ticket, C.byref(r))
+        if rc == _lib.E_STATE:
             raise ValueError("ticket no longer (or not yet) held by the pipeline")
-        slot = ticket % self.depth
-        self.done[slot].synchronize()
-        return self.h_out[slot]
+        self._check(rc)
+        F = self.F
+
+        def view(ptr, shape, dtype):
+            n = int(np.prod(shape))
+            ct = {np.float32: C.c_float, np.uint8: C.c_uint8, np.int32: C.c_int32}[dtype]
+            arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,)).reshape(shape)
+            return torch.from_numpy(arr)
+
+        kps = [view(r.kps[c], (F, self.caps[c], 6), np.float32) for c in range(self.n_cams)]
+        desc = [view(r.desc[c], (F, self.caps[c], 32), np.uint8) for c in range(self.n_cams)]
+        counts = [view(r.counts[c], (F,), np.int32) for c in range(self.n_cams)]
+        m12 = view(r.matches12, (F - 1, self.caps[0]), np.int32) if self.match else None
+        nm = view(r.nmatches, (F - 1,), np.int32) if self.match else None
+        return RigStepResult(kps, desc, counts, m12, nm)
 
     def run(self, h_images: Sequence) -> RigStepResult:
         """One synchronous step (submit + result)."""
         return self.result(self.submit(h_images))
 
     def drain(self) -> None:
-        for s in (self.s_in, self.s_compute, self.s_match, self.s_out):
-            s.synchronize()
+        self._check(lib.orbp_drain(self._h))

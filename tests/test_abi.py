@@ -20,7 +20,7 @@ def lib():
 def test_header_symbols_are_exported(lib):
     hdr = open(os.path.join(ROOT, "include", "orb_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b(orb[xmd]_[a-z0-9_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(orb[xmdp]_[a-z0-9_]+)\s*\(", hdr))
     assert declared, "no declarations found"
     for name in sorted(declared):
         assert hasattr(lib.lib, name), f"{name} declared in orb_b200.h but not exported"

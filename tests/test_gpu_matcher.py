@@ -182,6 +182,39 @@ def test_search_by_projection_points_view_cos_boundary(M, O):
     assert not np.array_equal(rfmp2, rfmp)
 
 
+def test_projection_searches_repeat_once_when_the_row_budget_overflows(M, O):
+    """The single-call searches size their candidate rows from earlier calls (no host round trip between count and fill);
+    a budget of one row per query overflows on the first call, which must repeat with the exact size and still equal
+    the oracle — for the points overload (a13) and the tracking matcher (a14); later calls reuse the learnt size."""
+    from multi_orb_slam_b200._lib import Camera
+    from multi_orb_slam_b200.matcher import Frame, MapPoints, ORBmatcher
+    k, d, mp, mpd, rng = _projection_case(O, 8, 5000)
+    sf = O.extractor("port").scale_tables()[0]
+    n, nmp = len(k), len(mp)
+    ur, obs = np.full(n, -1, np.float32), np.ones(nmp, np.int32)
+    fmp0, fobs0 = np.full(n, -1, np.int32), np.zeros(n, np.int32)
+    rn, rfmp = O.search_by_projection_points(k, d, ur, (0, 1241, 0, 376), sf, mp, mpd, obs, 3.0, 0.8, fmp0, fobs0)
+    m = ORBmatcher(0.8, True)
+    m.debug_set_row_budget(1)
+    for _ in range(2):  # first call overflows and repeats; the second one fits at once
+        F = Frame(k, d, 1241, 376, mvScaleFactors=sf, mvuRight=ur, mvpMapPoints=fmp0.copy(), mvpMapPointsObserved=fobs0)
+        assert m.SearchByProjection(F, MapPoints(mp, mpd, obs), 3.0) == rn and np.array_equal(F.mvpMapPoints, rfmp)
+    s = _rig_scene(O, 3, 1500, (0, 0, 0.5))
+    n = s["n"]
+    fmp0, fobs0 = np.full(n, -1, np.int32), np.zeros(n, np.int32)
+    rn, rfmp = O.search_by_projection_frame(s["cur_k"], s["cur_d"], s["ur"], s["cur_cam"], (0, 640, 0, 480), sf, CAM, s["Tcw"],
+                                            s["Tlw"], s["last_k"], s["last_cam"], s["last_valid"], s["last_xyz"],
+                                            s["last_desc"], s["last_obs"], CALIB, 15.0, False, True, fmp0, fobs0)
+    m9 = ORBmatcher(0.9, True)
+    m9.debug_set_row_budget(1)
+    for _ in range(2):
+        F = Frame(s["cur_k"], s["cur_d"], 640, 480, mvScaleFactors=sf, mvuRight=s["ur"], mvpMapPoints=fmp0.copy(),
+                  mvpMapPointsObserved=fobs0)
+        gn = m9.SearchByProjectionFrame(F, s["cur_cam"], Camera(*CAM), s["Tcw"], s["Tlw"], s["last_k"], s["last_cam"],
+                                        s["last_valid"], s["last_xyz"], s["last_desc"], s["last_obs"], CALIB, 15.0, False)
+        assert gn == rn and np.array_equal(F.mvpMapPoints, rfmp)
+
+
 @pytest.mark.parametrize("reps,th", [(2, 3.0), (6, 6.0)])
 def test_search_by_projection_points_contended(M, O, reps, th):
     """Every map point repeated `reps` times (same projection and descriptor, mixed Observations()): consecutive points

@@ -16,13 +16,13 @@
 #define UNROLL 8
 
 enum Op { POPC, LOP3, IADD3, IMAD, PRMT, SHF, VABSDIFF4, VIMNMX3, VIMNMX3_16, IDP4A, IDP2A, POPC_LOP, POPC_IMAD, HAMMING8,
-          LDS_U8, LDS_32, LDS_64, LDS_128, LDS_U8_SCATTER, STS_32, STS_U8, LDG_32, LDG_128, SHFL, REDUX, VOTE, MATCH, N_OPS };
+          LDS_U8, LDS_32, LDS_64, LDS_128, LDS_U8_SCATTER, STS_32, STS_U8, LDG_32, LDG_128, SHFL, REDUX, VOTE, MATCH, LDS_U16, STS_U16, STS_64, N_OPS };
 static const char* kNames[N_OPS] = {"popc", "lop3", "iadd3", "imad", "prmt", "shf_funnel", "vabsdiff4", "vimnmx3_s32",
                                     "vimnmx3_s16x2", "idp4a", "idp2a", "popc+lop3 (1:1)", "popc+imad (1:1)",
                                     "hamming256 (8 x xor+popc+add)", "lds_u8 (conflict-free)", "lds_b32 (conflict-free)",
                                     "lds_b64 (conflict-free)", "lds_b128 (conflict-free)", "lds_u8 (4 rows x 36 B, pitch 48: phase-B pattern)",
                                     "sts_b32", "sts_u8", "ldg_b32 (L1 hit, coalesced)", "ldg_b128 (L1 hit)", "shfl_idx", "redux_or",
-                                    "vote_ballot", "match_any"};
+                                    "vote_ballot", "match_any", "lds_u16", "sts_u16", "sts_b64"};
 
 template <int OP>
 __global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t seed, const uint32_t* __restrict__ g) {
@@ -95,6 +95,15 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t seed, const uin
           a[j] = __reduce_or_sync(0xffffffffu, a[j] + threadIdx.x);
         } else if (OP == VOTE) {
           a[j] = __ballot_sync(0xffffffffu, (a[j] + threadIdx.x) & 1) + b;
+        } else if (OP == LDS_U16) {
+          a[j] = reinterpret_cast<volatile uint16_t*>(sm)[(a[j] & 0x7c0u) + threadIdx.x % 64];
+        } else if (OP == STS_U16) {
+          reinterpret_cast<volatile uint16_t*>(sm)[(a[j] & 0x7c0u) + threadIdx.x % 64] = (uint16_t)a[j];
+          a[j] += b;
+        } else if (OP == STS_64) {
+          const uint32_t addr = (uint32_t)__cvta_generic_to_shared(sm) + 8u * ((a[j] & 0x40u) + (threadIdx.x & 31));
+          asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a[j]), "r"(b));
+          a[j] += b;
         } else if (OP == MATCH) {
           a[j] = __match_any_sync(0xffffffffu, a[j] & 7u) + threadIdx.x;
         }
@@ -171,6 +180,9 @@ int main() {
   r[REDUX] = run<REDUX>(d_out, p.multiProcessorCount, clk_hz);
   r[VOTE] = run<VOTE>(d_out, p.multiProcessorCount, clk_hz);
   r[MATCH] = run<MATCH>(d_out, p.multiProcessorCount, clk_hz);
+  r[LDS_U16] = run<LDS_U16>(d_out, p.multiProcessorCount, clk_hz);
+  r[STS_U16] = run<STS_U16>(d_out, p.multiProcessorCount, clk_hz);
+  r[STS_64] = run<STS_64>(d_out, p.multiProcessorCount, clk_hz);
   printf("{\"device\": \"%s\", \"sms\": %d, \"clock_mhz_nominal\": %.0f, \"unit\": \"warp-instructions per clock per SM "
          "(x32 = lane-ops/clk/SM; clock = cudaDevAttrClockRate)\", \"rates\": {",
          p.name, p.multiProcessorCount, clk_hz / 1e6);
