@@ -29,6 +29,7 @@ W, H = 640, 480
 NF0, NF1 = 1000, 500
 SCALE, NLEVELS, INI_TH, MIN_TH = 1.2, 8, 20, 7
 WINDOW, NNRATIO = 100, 0.9
+WARM_S = 0.4  # seconds of load before any timed region (see main)
 METRIC = "ORB camera-frames/sec @640x480 nFeatures=1000 8 lvls; Hamming matches/sec"
 UNIT = "camera-frames/s"
 
@@ -364,6 +365,7 @@ def rig8_leg(args, world, rank, local_rank, dev, barrier, peak):
     from multi_orb_slam_b200.rig import RigFrontEnd
     from multi_orb_slam_b200.synth import camera_sequence
     F, chunk, distinct = args.rig8_frames, args.rig8_chunk, args.rig8_distinct
+    RIG8["n_cams"] = args.rig8_cams
     fe = RigFrontEnd(RIG8["n_cams"], RIG8["nfeatures"], SCALE, NLEVELS, INI_TH, MIN_TH, image_size=(RIG8["w"], RIG8["h"]),
                      rig_frames=F, chunk=chunk, rank=rank, world=world, device=local_rank, nnratio=NNRATIO, th_dist=50)
     images = {}
@@ -374,12 +376,16 @@ def rig8_leg(args, world, rank, local_rank, dev, barrier, peak):
             full[i:i + distinct] = base[: min(distinct, F - i)]
         images[c] = full
 
+    host_ms = [0.0]
+
     def timed(steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for _ in range(steps):
             res = fe.step(images)
+        host_ms[0] = (time.perf_counter() - t0) / steps * 1e3  # host time to enqueue a step (the GPU must not wait for it)
         e1.record()
         torch.cuda.synchronize()
         barrier()
@@ -390,11 +396,19 @@ def rig8_leg(args, world, rank, local_rank, dev, barrier, peak):
             ms = float(t.item())
         return ms, res
 
-    steps = max(3, min(args.steps, args.rig8_steps))
-    timed(max(3, args.warmup))
+    # Warm-up: at least W steps AND at least ~0.5 s of load — the leg starts after seconds of host-side image generation
+    # with the GPU idle, and a B200 needs a few hundred ms of load to return to its full clocks (a 50 ms timed region
+    # started cold measured 8 % slow).  Timed steps: at least 0.25 s worth.
+    ms_probe, _ = timed(max(3, args.warmup))
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < 0.5:
+        timed(max(3, args.warmup))
+    steps = max(3, min(args.steps, args.rig8_steps), int(np.ceil(250.0 / max(ms_probe, 1e-3))))
+    steps = min(steps, 200)
     l0 = fe.launch_count
     ms, res = timed(steps)
     launches = (fe.launch_count - l0) // steps
+    host_enqueue_ms = host_ms[0]
     out = {"workload": f"configs[4]: {RIG8['n_cams']} cameras x {F} rig-frames of {RIG8['w']}x{RIG8['h']} "
                        f"({RIG8['n_cams'] * F} camera-frames per step, tiled from {distinct} distinct frames per camera), "
                        f"nFeatures {RIG8['nfeatures']}; camera streams dealt over the ranks, chunks of {fe.chunk} rig-frames; "
@@ -403,6 +417,7 @@ def rig8_leg(args, world, rank, local_rank, dev, barrier, peak):
            "scaling": "strong", "n_gpus": world, "steps": steps, "ms_per_step": ms,
            "value": RIG8["n_cams"] * F / (ms * 1e-3), "unit": UNIT,
            "cameras_per_rank": len(fe.cams), "chunks_per_step": fe.n_chunks, "gpu_launches_per_step": int(launches),
+           "host_enqueue_ms_per_step_rank0": host_enqueue_ms,
            "collective": "one in-place ncclAllGather per chunk via orbd_allgather_inplace (C ABI), own stream"
                          if world > 1 else "none (single rank)",
            "inputs": "resident in HBM"}
@@ -529,8 +544,11 @@ def configs_leg(args, matcher, device, with_cpu, peak, sm_max):
     for n in (1024, 2048, 4096, 8192, 16384, 32768, 65536):
         idx, d1, d2 = (torch.empty((n,), dtype=torch.int32, device=dev) for _ in range(3))
         reps = max(3, min(200, int(2e9 / (n * n))))
-        for _ in range(3):
-            matcher.bruteforce_device(dB[:n], dA[:n], idx, d1, d2, th_dist=50, ratio=0.9)
+        t_w = time.perf_counter()
+        while time.perf_counter() - t_w < 0.1:
+            for _ in range(3):
+                matcher.bruteforce_device(dB[:n], dA[:n], idx, d1, d2, th_dist=50, ratio=0.9)
+            st.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(st)
         for _ in range(reps):
@@ -567,10 +585,13 @@ def configs_leg(args, matcher, device, with_cpu, peak, sm_max):
         exl.extract_batch_device(imgs[0], *outs[0])
         exr.extract_batch_device(imgs[1], *outs[1])
 
-    for _ in range(3):
-        kitti_step()
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < WARM_S:
+        for _ in range(4):
+            kitti_step()
+        st.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
+    reps = 10
     e0.record(st)
     for _ in range(reps):
         kitti_step()
@@ -647,6 +668,8 @@ def main():
     ap.add_argument("--rig8-distinct", type=int, default=8, help="distinct synthetic frames per camera, tiled (configs[4])")
     ap.add_argument("--rig8-steps", type=int, default=5, help="timed steps of the configs[4] leg (capped by --steps)")
     ap.add_argument("--no-rig8", action="store_true", help="skip the configs[4] leg")
+    ap.add_argument("--rig8-cams", type=int, default=8, help="cameras of the configs[4] leg (development probes only)")
+    ap.add_argument("--rig8-only", action="store_true", help="run only the configs[4] leg and print its block (development)")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[0]/[2]/[3] rows")
     ap.add_argument("--kitti-pairs", type=int, default=64, help="stereo pairs per step of the configs[3] row")
     args = ap.parse_args()
@@ -673,6 +696,17 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.rig8_only:
+        def _barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+        r8 = rig8_leg(args, world, rank, local_rank, dev, _barrier, load_peaks()[0])
+        if rank == 0:
+            print(json.dumps(r8))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     F = args.rig_frames
     cams = make_sequences(F, 2 * rank)  # every rank owns its own rig-frames: independent units, no exchange
     # pinned host copies (e2e leg) and HBM-resident copies (device leg)
@@ -781,10 +815,21 @@ def main():
         return ms
 
     # ---- device-resident leg -------------------------------------------------------------------
-    with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            device_step(d_img)
-    stream.synchronize()
+    # Warm-up: the W requested steps AND at least WARM_S seconds of load.  The legs start after seconds of host-side
+    # set-up with the GPU idle, and a B200 needs a few hundred ms of load to return to its full clocks: a 30-50 ms
+    # timed region started cold reads up to 8 % slow (profiles/r02_notes.md).  The timed region is still exactly K steps.
+    def warm(fn, min_steps):
+        t_w, n = time.perf_counter(), 0
+        while n < min_steps or time.perf_counter() - t_w < WARM_S:
+            with torch.cuda.stream(stream):
+                fn()
+            n += 1
+            if n % 8 == 0:
+                stream.synchronize()
+        stream.synchronize()
+        return n
+
+    warm_steps = warm(lambda: device_step(d_img), args.warmup)
     m_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     step_i = [0]
 
@@ -818,10 +863,14 @@ def main():
     n_kp = [int(c.sum().item()) for c in counts]
 
     # the metric's own setting on every frame: camera 1's extractor (nFeatures 1000) alone, same frames
+    warm(lambda: ex[0].extract_batch_device(d_img[0], kps[0], desc[0], counts[0]), 3)
     ms_nf1000 = timed(lambda: ex[0].extract_batch_device(d_img[0], kps[0], desc[0], counts[0]), args.steps, False)
 
     # ---- end-to-end leg (pinned host -> device -> pinned host every step) -----------------------
-    e2e_run(2)
+    t_w = time.perf_counter()
+    e2e_run(max(2, args.warmup))
+    while time.perf_counter() - t_w < WARM_S:
+        e2e_run(8)
     e2e_ms_dev, e2e_wall, e2e_res = e2e_run(args.steps)
     if int(e2e_res.nmatches.sum().item()) != total_matches or [int(c.sum().item()) for c in e2e_res.counts] != n_kp:
         raise SystemExit("bench.py: end-to-end results differ from the device-resident leg")
@@ -859,8 +908,7 @@ def main():
     def bf_step():
         matcher.bruteforce_device(dB, dA, bf_idx, bf_d1, bf_d2, th_dist=50, ratio=0.9)
 
-    for _ in range(3):
-        bf_step()
+    warm(bf_step, 3)
     bf_ms = timed(bf_step, max(3, args.steps), False)
     bf_pairs = float(nbf) * nbf * world / (bf_ms * 1e-3)
     bf_accepted = int((bf_idx >= 0).sum().item())
@@ -965,6 +1013,8 @@ def main():
                                "ratio 0.9) between consecutive camera-1 frames",
                    "rig_frames_per_gpu": F, "camera_frames_per_step": frames_per_step,
                    "l2_policy": "inputs (157 MB of frames per GPU per step) and workspace exceed the 126 MB L2",
+                   "warmup_policy": f"W = {args.warmup} steps and at least {WARM_S} s of load before every timed region "
+                                    f"({warm_steps} steps here); the timed region is exactly K steps",
                    "parallelism": f"rig-frames sharded over {world} GPU(s), no data-path collective",
                    "keypoints_per_step_rank0": n_kp, "init_matches_per_step_rank0": total_matches},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

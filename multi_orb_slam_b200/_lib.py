@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liborb_b200.so")
+LIB_PATH = os.environ.get("ORB_B200_LIB") or os.path.join(HERE, "liborb_b200.so")  # override: development A/B runs only
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
                      ("response", "<f4"), ("octave", "<i4")])

@@ -11,7 +11,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "liborb_b200.so")
+# development knobs (kernel A/B runs): ORB_B200_LIB = path of the library to build / load instead of the in-tree
+# default, ORB_B200_NVCC_FLAGS = extra nvcc flags (e.g. -DBF_QPT=4)
+LIB = os.environ.get("ORB_B200_LIB") or os.path.join(HERE, "liborb_b200.so")
 SOURCES = ["extract_kernels.cu", "extract_api.cu", "matcher.cu", "dist_api.cu", "pipeline_api.cu"]
 HEADERS = ["device_guard.h", "extract_kernels.h", "orb_geom.h", "octree_core.h", "orb_pattern.h", "../../include/orb_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
@@ -39,7 +41,7 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("ORB_B200_NVCC_FLAGS", "").split() + (["-Xptxas", "-v"] if verbose else []) + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:

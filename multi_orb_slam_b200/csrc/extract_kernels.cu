@@ -65,9 +65,14 @@ __device__ __forceinline__ LevelView level_view(const OrbGeom* __restrict__ g, c
 //   * the rows' vertical taps are fetched once per tile (lane r holds row r) and broadcast by
 //     shuffle.
 #define PYR_ROWS 32
-#define PYR_PREFETCH 4
+#ifndef PYR_PREFETCH
+#define PYR_PREFETCH 4  // source rows in flight per warp (even)
+#endif
+#ifndef PYR_MINB
+#define PYR_MINB 8
+#endif
 
-__global__ void __launch_bounds__(128, 8) k_pyr_resize(int level, int rows_per_tile, const OrbGeom* __restrict__ g,
+__global__ void __launch_bounds__(128, PYR_MINB) k_pyr_resize(int level, int rows_per_tile, const OrbGeom* __restrict__ g,
                                                     OrbLevel0 l0, const OrbXTap* __restrict__ xtab,
                                                     const OrbYTap* __restrict__ ytab, uint8_t* __restrict__ pyr) {
   const OrbLevelGeom& D = g->lv[level];
@@ -183,11 +188,13 @@ __global__ void __launch_bounds__(128, 8) k_pyr_resize(int level, int rows_per_t
   while (s <= s_hi) {
 #pragma unroll
     for (int j = 0; j < PYR_PREFETCH; ++j) load(xb[j]);
-    PYR_ROW(xa[0], hB, hA) PYR_ROW(xa[1], hA, hB) PYR_ROW(xa[2], hB, hA) PYR_ROW(xa[3], hA, hB)
+#pragma unroll
+    for (int j = 0; j < PYR_PREFETCH; j += 2) { PYR_ROW(xa[j], hB, hA) PYR_ROW(xa[j + 1], hA, hB) }
     if (s > s_hi) break;
 #pragma unroll
     for (int j = 0; j < PYR_PREFETCH; ++j) load(xa[j]);
-    PYR_ROW(xb[0], hB, hA) PYR_ROW(xb[1], hA, hB) PYR_ROW(xb[2], hB, hA) PYR_ROW(xb[3], hA, hB)
+#pragma unroll
+    for (int j = 0; j < PYR_PREFETCH; j += 2) { PYR_ROW(xb[j], hB, hA) PYR_ROW(xb[j + 1], hA, hB) }
   }
 #undef PYR_ROW
 }
@@ -213,6 +220,12 @@ __global__ void __launch_bounds__(128, 8) k_pyr_resize(int level, int rows_per_t
 #define FAST_NT 32  // threads per cell CTA: ONE warp per cell.  Measured with more warps per cell (128 frames, ms):
                     // 32 -> 0.42, 64 -> 0.48, 96 -> 0.49, 128 -> 0.50, 160 -> 0.56, 256 -> 0.74: a cell is ~1000 px,
                     // more warps only add barrier and tail idle time
+
+#ifndef FAST_PAIR
+#define FAST_PAIR 0  // 1: phase A handles two adjacent words per lane with 64-bit shared loads (11 LDS per 8 pixels
+                     // instead of 22); the tile then starts one word further right so that the pairs are 8-byte aligned
+#endif
+#define FAST_COL0 (FAST_PAIR ? 5 : 1)  // shared-row byte of sub-image column 0: the tested area starts at byte FAST_COL0 + 3
 
 struct FastSmem {
   // Three regions of shared memory, each reused once its first tenant is dead (6 KB per cell CTA
@@ -259,7 +272,7 @@ template <int PITCH>
 __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int thh, int ch) {
   static_assert(FAST_NT == 32, "one warp per cell");
   constexpr int PW = PITCH / 4;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   // phase A: packed rejection test, four pixels (one word) per lane.  A 9-arc contains one pixel
   // of every opposite pair (k, k+8), so a corner has |p - c| > th for at least one pixel of each
@@ -269,6 +282,51 @@ __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int
   // interact).  The test only has to be a superset of the corners: phase B measures exactly.
   const int T = th >> 1;
   const uint32_t K = 0x01010101u * (uint32_t)(128 - min(T, 127));
+#if FAST_PAIR
+  const int WPR = (tw + 3) >> 2;  // words per tested row
+  const uint32_t last_mask = 0x80808080u >> (8 * (4 * WPR - tw));  // valid pixels of a row's last word
+  const uint32_t* hw = reinterpret_cast<const uint32_t*>(sm.hv);
+  uint16_t* eq = sm.eq;  // word entries: word offset << 4 | pixel nibble
+  int ecount = 0;
+  auto reject = [&](uint32_t c, uint32_t u3, uint32_t d3, uint32_t lw, uint32_t rw, uint32_t ul, uint32_t uc, uint32_t ur,
+                    uint32_t dl, uint32_t dc, uint32_t dq) {
+    const uint32_t f0 = __vabsdiffu4(d3, c) + K, f8 = __vabsdiffu4(u3, c) + K;
+    const uint32_t f4 = __vabsdiffu4(__byte_perm(c, rw, 0x6543), c) + K;
+    const uint32_t f12 = __vabsdiffu4(__byte_perm(lw, c, 0x4321), c) + K;
+    const uint32_t f2 = __vabsdiffu4(__byte_perm(dc, dq, 0x5432), c) + K;
+    const uint32_t f10 = __vabsdiffu4(__byte_perm(ul, uc, 0x5432), c) + K;
+    const uint32_t f6 = __vabsdiffu4(__byte_perm(uc, ur, 0x5432), c) + K;
+    const uint32_t f14 = __vabsdiffu4(__byte_perm(dl, dc, 0x5432), c) + K;
+    return (f0 | f8) & (f4 | f12) & (f2 | f10) & (f6 | f14);
+  };
+  const int PPR = (WPR + 1) >> 1;  // word pairs per tested row
+  const int items = thh * PPR;
+  const int dr = 32 / PPR, dw = 32 - dr * PPR;
+  int row = lane / PPR, w2 = lane - row * PPR;
+  for (int i0 = 0; i0 < items; i0 += 32) {
+    const bool valid = i0 + lane < items;
+    const int woff = ((valid ? row : 0) + 3) * PW + (FAST_COL0 + 3) / 4 + 2 * w2;  // even: 8-byte aligned
+    const uint32_t* p = hw + woff;
+    const uint2 c = *reinterpret_cast<const uint2*>(p);
+    const uint2 u3 = *reinterpret_cast<const uint2*>(p - 3 * PW), d3 = *reinterpret_cast<const uint2*>(p + 3 * PW);
+    const uint2 uc = *reinterpret_cast<const uint2*>(p - 2 * PW), dc = *reinterpret_cast<const uint2*>(p + 2 * PW);
+    const uint32_t lw = p[-1], rw = p[2], ul = p[-2 * PW - 1], ur = p[-2 * PW + 2], dl = p[2 * PW - 1], dq = p[2 * PW + 2];
+    uint32_t pass0 = reject(c.x, u3.x, d3.x, lw, c.y, ul, uc.x, uc.y, dl, dc.x, dc.y);
+    uint32_t pass1 = reject(c.y, u3.y, d3.y, c.x, rw, uc.x, uc.y, ur, dc.x, dc.y, dq);
+    const int wi = 2 * w2;
+    pass0 &= wi == WPR - 1 ? last_mask : 0x80808080u;
+    pass1 &= wi + 1 == WPR - 1 ? last_mask : (wi + 1 < WPR ? 0x80808080u : 0u);
+    if (!valid) pass0 = pass1 = 0;
+    const unsigned b0 = __ballot_sync(0xffffffffu, pass0 != 0), b1 = __ballot_sync(0xffffffffu, pass1 != 0);
+    const int pos = ecount + __popc(b0 & lt) + __popc(b1 & lt);
+    if (pass0) eq[pos] = (uint16_t)(woff << 4 | ((pass0 >> 7) * 0x10204080u) >> 28);
+    if (pass1) eq[pos + (pass0 != 0)] = (uint16_t)((woff + 1) << 4 | ((pass1 >> 7) * 0x10204080u) >> 28);
+    ecount += __popc(b0) + __popc(b1);
+    w2 += dw;
+    row += dr;
+    if (w2 >= PPR) { w2 -= PPR; ++row; }
+  }
+#else
   const int WPR = (tw + 3) >> 2;  // words per tested row
   const int items = thh * WPR;
   const int dr = 32 / WPR, dw = 32 - dr * WPR;
@@ -301,6 +359,7 @@ __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int
     row += dr;
     if (w >= WPR) { w -= WPR; ++row; }
   }
+#endif
   __syncwarp();
   // expand the word entries into one queue entry per surviving pixel
   int nq = 0;
@@ -329,7 +388,7 @@ __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int
   int nc = 0;
   for (int q0 = 0; q0 < nq; q0 += 32) {
     const bool valid = q0 + lane < nq;
-    const int off = valid ? sm.queue[q0 + lane] : 3 * PITCH + 4;  // idle lanes measure the first tested pixel
+    const int off = valid ? sm.queue[q0 + lane] : 3 * PITCH + FAST_COL0 + 3;  // idle lanes measure the first tested pixel
     const int m = fast_arc_measure<PITCH>(sm.img + off);
     const bool corner = valid && m > th;
     if (corner) sm.m[off] = (uint8_t)m;
@@ -364,15 +423,21 @@ __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int
   return nk;
 }
 
+#ifndef FAST_WPC
+#define FAST_WPC 1  // cells (= warps) per CTA; the warps of a CTA never talk to each other
+#endif
 template <int PITCH>
-__global__ void __launch_bounds__(FAST_NT) k_fast_cells(const OrbCell* __restrict__ cells, OrbLevel0 l0,
+__global__ void __launch_bounds__(FAST_NT * FAST_WPC) k_fast_cells(const OrbCell* __restrict__ cells, OrbLevel0 l0,
                                                     const uint8_t* __restrict__ pyr,
                                                     uint32_t* __restrict__ cand, int* __restrict__ cell_count,
                                                     size_t pyr_frame_bytes, size_t cand_frame_u32, int n_cells,
                                                     int ini_th, int min_th, int rows_max, int t_max) {
-  extern __shared__ __align__(16) unsigned char fsm[];
+  extern __shared__ __align__(16) unsigned char fsm_all[];
   FastSmem sm;
   const int r_img = rows_max * PITCH, r_q = max(r_img, (2 * t_max + 31) & ~15);
+  const int cell_idx = blockIdx.x * FAST_WPC + (threadIdx.x >> 5);
+  if (cell_idx >= n_cells) return;  // whole warp; warps only ever synchronise with themselves
+  unsigned char* fsm = fsm_all + (size_t)(threadIdx.x >> 5) * ((2 * r_img + r_q + 16 + 15) & ~15);
   sm.img = fsm;
   sm.kept = reinterpret_cast<uint16_t*>(fsm);
   sm.hv = fsm + r_img;
@@ -381,14 +446,14 @@ __global__ void __launch_bounds__(FAST_NT) k_fast_cells(const OrbCell* __restric
   sm.eq = reinterpret_cast<uint16_t*>(sm.m);
 
   // one 32-byte record tells the CTA everything about its cell
-  const uint4* crec = reinterpret_cast<const uint4*>(cells + blockIdx.x);
+  const uint4* crec = reinterpret_cast<const uint4*>(cells + cell_idx);
   const uint4 c0 = __ldg(crec), c1 = __ldg(crec + 1);
   OrbCell cell;
   reinterpret_cast<uint4*>(&cell)[0] = c0;
   reinterpret_cast<uint4*>(&cell)[1] = c1;
   const int frame = blockIdx.y;
   const int cw = cell.cw, ch = cell.ch, a0 = cell.a0;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x & 31;
   // Word copy of the sub-image rows (16 lanes per row), shifted so that sub-image column 0 lands
   // on byte 1 of the shared row: global word grid -> shared word grid by one byte permute of two
   // adjacent global words.  Level-0 cells read the caller's frame.
@@ -405,7 +470,7 @@ __global__ void __launch_bounds__(FAST_NT) k_fast_cells(const OrbCell* __restric
     for (int wq = tid & 15; wq < nsw; wq += 16) {
       const int i0 = max(wq + o, 0), d1 = min(wq + o + 1, ngw - 1) - i0;
       const uint32_t* gp = reinterpret_cast<const uint32_t*>(base) + (size_t)y_first * pw + i0;
-      uint32_t* sp = reinterpret_cast<uint32_t*>(sm.img) + y_first * (PITCH / 4) + wq;
+      uint32_t* sp = reinterpret_cast<uint32_t*>(sm.img) + y_first * (PITCH / 4) + wq + (FAST_COL0 - 1) / 4;
       for (int y = y_first; y < ch; y += FAST_NT / 16) {
         const uint32_t v = __byte_perm(__ldg(gp), __ldg(gp + d1), sel);
         sp[0] = v;
@@ -417,7 +482,7 @@ __global__ void __launch_bounds__(FAST_NT) k_fast_cells(const OrbCell* __restric
   }
   const int tw = cw - 6, thh = ch - 6;
   int total = 0, th = ini_th;
-  __syncthreads();
+  __syncwarp();
   if (tw > 0 && thh > 0) {
     total = fast_pass<PITCH>(sm, th, tw, thh, ch);
     if (total == 0 && min_th < th) {
@@ -426,7 +491,7 @@ __global__ void __launch_bounds__(FAST_NT) k_fast_cells(const OrbCell* __restric
       // the halved image: rebuild it.
       for (int i = tid; i < ch * (PITCH / 4); i += FAST_NT)
         reinterpret_cast<uint32_t*>(sm.hv)[i] = (reinterpret_cast<const uint32_t*>(sm.img)[i] >> 1) & 0x7f7f7f7fu;
-      __syncthreads();
+      __syncwarp();
       th = min_th;
       total = fast_pass<PITCH>(sm, th, tw, thh, ch);
     }
@@ -437,10 +502,10 @@ __global__ void __launch_bounds__(FAST_NT) k_fast_cells(const OrbCell* __restric
   uint32_t* out = cand + (size_t)frame * cand_frame_u32 + cell.cand_slot_off;
   for (int i = tid; i < total; i += FAST_NT) {
     const int off = sm.kept[i];
-    const int y = off / PITCH, x = off - y * PITCH - 1;
+    const int y = off / PITCH, x = off - y * PITCH - FAST_COL0;
     out[i] = (uint32_t)(x + cell.off_x) | (uint32_t)(y + cell.off_y) << 12 | ((uint32_t)sm.m[off] - 1u) << 24;
   }
-  if (tid == 0) cell_count[(size_t)frame * n_cells + blockIdx.x] = total;
+  if (tid == 0) cell_count[(size_t)frame * n_cells + cell_idx] = total;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -577,7 +642,10 @@ __device__ __forceinline__ void blur_rows(const uint32_t* __restrict__ src, int 
   }
 }
 
-__global__ void __launch_bounds__(128) k_blur(const OrbGeom* __restrict__ g, OrbLevel0 l0, const uint8_t* __restrict__ pyr,
+#ifndef BLUR_MINB
+#define BLUR_MINB 1
+#endif
+__global__ void __launch_bounds__(128, BLUR_MINB) k_blur(const OrbGeom* __restrict__ g, OrbLevel0 l0, const uint8_t* __restrict__ pyr,
                                               uint8_t* __restrict__ blur) {
   const int tile = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (tile >= g->n_blur_tiles) return;
@@ -803,15 +871,16 @@ void launch_fast(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, const uint8_
     cw_max = max(cw_max, gh.g.lv[l].w_cell + 6);
     t_max = max(t_max, gh.g.lv[l].w_cell * gh.g.lv[l].h_cell);
   }
-  const int pitch = cw_max + 3 <= 48 ? 48 : 80;  // + up to 3 bytes of word misalignment
+  const int pitch = cw_max + 3 + (FAST_COL0 - 1) <= 48 ? 48 : 80;  // + up to 3 bytes of word misalignment (+ the pair shift)
   const size_t r_img = (size_t)rows_max * pitch;
-  const size_t smem = 2 * r_img + max(r_img, (size_t)((2 * t_max + 31) & ~15)) + 16;
-  const dim3 grid(gh.g.n_cells, n_frames);
+  const size_t smem_cell = (2 * r_img + max(r_img, (size_t)((2 * t_max + 31) & ~15)) + 16 + 15) & ~(size_t)15;
+  const size_t smem = smem_cell * FAST_WPC;
+  const dim3 grid((gh.g.n_cells + FAST_WPC - 1) / FAST_WPC, n_frames);
   if (pitch == 48)
-    k_fast_cells<48><<<grid, FAST_NT, smem, st>>>(gh.d_cells, l0, d_pyr, d_cand, d_cell_count, gh.g.pyr_frame_bytes,
+    k_fast_cells<48><<<grid, FAST_NT * FAST_WPC, smem, st>>>(gh.d_cells, l0, d_pyr, d_cand, d_cell_count, gh.g.pyr_frame_bytes,
                                                   gh.g.cand_frame_u32, gh.g.n_cells, gh.g.ini_th, gh.g.min_th, rows_max, t_max);
   else
-    k_fast_cells<80><<<grid, FAST_NT, smem, st>>>(gh.d_cells, l0, d_pyr, d_cand, d_cell_count, gh.g.pyr_frame_bytes,
+    k_fast_cells<80><<<grid, FAST_NT * FAST_WPC, smem, st>>>(gh.d_cells, l0, d_pyr, d_cand, d_cell_count, gh.g.pyr_frame_bytes,
                                                   gh.g.cand_frame_u32, gh.g.n_cells, gh.g.ini_th, gh.g.min_th, rows_max, t_max);
   ++*launches;
 }

@@ -55,8 +55,12 @@ __global__ void k_distance_pairs(const uint8_t* __restrict__ a, const uint8_t* _
 // then lowest index, which is exactly the strict-< ascending scan of the reference; the second
 // smallest key carries the second-best distance.  Target chunks (blockIdx.y) are merged by
 // k_bf_merge in ascending chunk order.
+#ifndef BF_THREADS
 #define BF_THREADS 128
+#endif
+#ifndef BF_QPT
 #define BF_QPT 2
+#endif
 #define BF_TILE 256
 
 __global__ void __launch_bounds__(BF_THREADS) k_bruteforce(const uint8_t* __restrict__ q, int nq,
@@ -1774,8 +1778,11 @@ int bf_launch(orbm_matcher* m, const uint8_t* d_q, int nq, const uint8_t* d_t, i
               int32_t* d_idx, int32_t* d_d1, int32_t* d_d2) {
   if (nq == 0) return ORBX_OK;
   const int qblocks = (nq + BF_THREADS * BF_QPT - 1) / (BF_THREADS * BF_QPT);
-  // enough target chunks to put >= ~4 CTAs on each of the 148 SMs; chunk <= 65536 (16-bit local index)
-  int nsplit = std::max(1, std::min((nt + BF_TILE - 1) / BF_TILE, (148 * 4 + qblocks - 1) / qblocks));
+  // Enough target chunks for ~32 CTAs per SM (9 are resident at a time): with the 5.2 CTAs per SM of the first version
+  // the SMs that drew 6 set the pace while the others idled (ncu: XU pipe — where POPC issues — 93 % busy while active
+  // but only 81 % of the elapsed time).  Chunks stay >= 2 tiles so the query prologue amortises; <= 65536 targets
+  // (16-bit local index).
+  int nsplit = std::max(1, std::min((nt + 2 * BF_TILE - 1) / (2 * BF_TILE), (148 * 32 + qblocks - 1) / qblocks));
   nsplit = std::max(nsplit, (nt + 65535) / 65536);
   int chunk = nt > 0 ? (nt + nsplit - 1) / nsplit : 1;
   chunk = (chunk + BF_TILE - 1) / BF_TILE * BF_TILE;

@@ -21,3 +21,16 @@ for _ in range(3):
     m.bruteforce_device(dB, dA, idx, d1, d2, th_dist=50, ratio=0.9)
 m.sync()
 print("accepted", int((idx >= 0).sum().item()))
+# timing (CUDA events on the matcher's stream) when called with a second argument
+if len(sys.argv) > 2:
+    st = torch.cuda.Stream()
+    m.set_stream(st.cuda_stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record(st)
+    for _ in range(reps):
+        m.bruteforce_device(dB, dA, idx, d1, d2, th_dist=50, ratio=0.9)
+    e1.record(st)
+    st.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"{sys.argv[2]}: {ms:.3f} ms, {n * n / ms / 1e9:.1f} G pairs/s, frac of POPC peak {n * n / (ms * 1e-3) / (148 * 16 * 1.965e9 / 8):.3f}")
