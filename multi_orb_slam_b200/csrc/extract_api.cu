@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -264,6 +265,47 @@ bool build_geometry(orbx_extractor* h, std::vector<OrbCell>& cells, std::vector<
   return true;
 }
 
+// Work list of the FAST kernel: every row of cells of every level, cut into chunks of whole cells that fit the
+// ORB_BAND_MAX_PX tested pixels a warp covers per image row (chunks of a row are balanced: 20 cells -> 7 + 7 + 6).
+void build_bands(const OrbGeom& g, const std::vector<OrbCell>& cells, std::vector<OrbBand>& bands) {
+  for (int l = 0; l < g.nlevels; ++l) {
+    const OrbLevelGeom& L = g.lv[l];
+    int p = L.cell_base;
+    const int end = L.cell_base + L.n_cells;
+    while (p < end) {
+      int q = p;
+      while (q < end && cells[q].ini_y == cells[p].ini_y) ++q;  // one row of cells
+      const int n = q - p;
+      const int per = std::max(1, std::min(8, ORB_BAND_MAX_PX / L.w_cell));
+      const int nchunk = (n + per - 1) / per;
+      int c0 = p;
+      for (int k = 0; k < nchunk; ++k) {
+        const int nc = n / nchunk + (k < n % nchunk ? 1 : 0);
+        const OrbCell& first = cells[c0];
+        const OrbCell& last = cells[c0 + nc - 1];
+        OrbBand b;
+        std::memset(&b, 0, sizeof(b));
+        b.level = (short)l;
+        b.n_cells = (short)nc;
+        b.cell_idx0 = c0;
+        b.cand_slot_off = first.cand_slot_off;
+        b.cand_cap = first.cand_cap;
+        b.pitch = (unsigned short)L.pitch;
+        b.y_first = first.ini_y;
+        b.nt = (short)(first.ch - 6);
+        b.x0 = (short)(first.ini_x + 3);
+        b.x1 = (short)(last.ini_x + last.cw - 3);
+        b.xb = (short)((b.x0 - 4) & ~3);
+        b.w_cell = (short)L.w_cell;
+        b.src_off = L.pyr_off + (unsigned)b.y_first * (unsigned)L.pitch + (unsigned)b.xb;
+        bands.push_back(b);
+        c0 += nc;
+      }
+      p = q;
+    }
+  }
+}
+
 template <typename T> bool dev_alloc(orbx_extractor* h, T** p, size_t count, const char* what) {
   return h->check(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)), what);
 }
@@ -350,6 +392,13 @@ int orbx_create(const orbx_config* cfg, orbx_extractor** out) {
   std::vector<OrbXTap> xt;
   std::vector<OrbYTap> yt;
   if (!build_geometry(h, cells, xt, yt)) return fail(ORBX_E_INVALID);
+  std::vector<OrbBand> bands;
+  build_bands(h->gh.g, cells, bands);
+  h->gh.n_bands = (int)bands.size();
+  {
+    const char* e = getenv("ORB_B200_FAST");
+    h->gh.fast_bands = e && std::string(e) == "bands";
+  }
   int ndev = 0;
   if (!h->check(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount") || ndev == 0) {
     if (h->err.empty()) h->err = "no CUDA device (this library has no CPU fallback)";
@@ -369,6 +418,7 @@ int orbx_create(const orbx_config* cfg, orbx_extractor** out) {
   h->img_pitch = (int)align_up(cfg->width, 16);
   bool ok = dev_alloc(h, &h->gh.d_geom, 1, "cudaMalloc(geom)") &&
             dev_alloc(h, &h->gh.d_cells, cells.size(), "cudaMalloc(cells)") &&
+            dev_alloc(h, &h->gh.d_bands, bands.size(), "cudaMalloc(bands)") &&
             dev_alloc(h, &h->gh.d_xtab, xt.size(), "cudaMalloc(xtab)") &&
             dev_alloc(h, &h->gh.d_ytab, yt.size(), "cudaMalloc(ytab)") &&
             dev_alloc(h, &h->d_pyr, B * g.pyr_frame_bytes, "cudaMalloc(pyramid)") &&
@@ -384,6 +434,7 @@ int orbx_create(const orbx_config* cfg, orbx_extractor** out) {
   if (!ok) return fail(ORBX_E_CUDA);
   ok = h->check(cudaMemcpy(h->gh.d_geom, &g, sizeof(g), cudaMemcpyHostToDevice), "copy geom") &&
        h->check(cudaMemcpy(h->gh.d_cells, cells.data(), cells.size() * sizeof(OrbCell), cudaMemcpyHostToDevice), "copy cells") &&
+       h->check(cudaMemcpy(h->gh.d_bands, bands.data(), bands.size() * sizeof(OrbBand), cudaMemcpyHostToDevice), "copy bands") &&
        h->check(cudaMemcpy(h->gh.d_xtab, xt.data(), xt.size() * sizeof(OrbXTap), cudaMemcpyHostToDevice), "copy xtab") &&
        h->check(cudaMemcpy(h->gh.d_ytab, yt.data(), yt.size() * sizeof(OrbYTap), cudaMemcpyHostToDevice), "copy ytab") &&
        h->check(orbk::prepare_octree(h->gh), "octree shared-memory opt-in") &&
@@ -399,7 +450,7 @@ void orbx_destroy(orbx_extractor* h) {
   orbk::dump_octree_marks();
 #endif
   if (h->stream) cudaStreamSynchronize(h->stream);
-  cudaFree(h->gh.d_geom); cudaFree(h->gh.d_cells); cudaFree(h->gh.d_xtab); cudaFree(h->gh.d_ytab);
+  cudaFree(h->gh.d_geom); cudaFree(h->gh.d_cells); cudaFree(h->gh.d_bands); cudaFree(h->gh.d_xtab); cudaFree(h->gh.d_ytab);
   cudaFree(h->d_pyr); cudaFree(h->d_blur); cudaFree(h->d_cand); cudaFree(h->d_cell_count);
   cudaFree(h->d_keys); cudaFree(h->d_knode); cudaFree(h->d_sel); cudaFree(h->d_sel_count);
   cudaFree(h->d_img); cudaFree(h->d_l0); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts);

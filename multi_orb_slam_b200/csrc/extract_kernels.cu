@@ -225,6 +225,11 @@ __global__ void __launch_bounds__(128, PYR_MINB) k_pyr_resize(int level, int row
 #define FAST_PAIR 0  // 1: phase A handles two adjacent words per lane with 64-bit shared loads (11 LDS per 8 pixels
                      // instead of 22); the tile then starts one word further right so that the pairs are 8-byte aligned
 #endif
+#ifndef FAST_HVP
+#define FAST_HVP 0   // bytes per row of the HALVED copy (0: same as the image copy).  Phase A's lanes cover four rows of
+                     // eight words each: with 24 words per row the four row segments fall on disjoint banks (a 12-word
+                     // pitch gives 2-way conflicts on every one of its 11 loads: ncu 169 wavefronts for 86 loads per cell)
+#endif
 #define FAST_COL0 (FAST_PAIR ? 5 : 1)  // shared-row byte of sub-image column 0: the tested area starts at byte FAST_COL0 + 3
 
 struct FastSmem {
@@ -327,22 +332,23 @@ __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int
     if (w2 >= PPR) { w2 -= PPR; ++row; }
   }
 #else
+  constexpr int PWH = (FAST_HVP ? FAST_HVP : PITCH) / 4;  // words per row of the halved copy
   const int WPR = (tw + 3) >> 2;  // words per tested row
   const int items = thh * WPR;
   const int dr = 32 / WPR, dw = 32 - dr * WPR;
   const uint32_t last_mask = 0x80808080u >> (8 * (4 * WPR - tw));  // valid pixels of a row's last word
   int row = lane / WPR, w = lane - row * WPR;
   const uint32_t* hw = reinterpret_cast<const uint32_t*>(sm.hv);
-  uint16_t* eq = sm.eq;  // word entries: word offset << 4 | pixel nibble
+  uint16_t* eq = sm.eq;  // word entries: word offset (image copy) << 4 | pixel nibble
   int ecount = 0;
   for (int i0 = 0; i0 < items; i0 += 32) {
     const bool valid = i0 + lane < items;
     const int woff = ((valid ? row : 0) + 3) * PW + 1 + w;
-    const uint32_t* p = hw + woff;
+    const uint32_t* p = hw + ((valid ? row : 0) + 3) * PWH + 1 + w;
     const uint32_t c = p[0];
-    const uint32_t u3 = p[-3 * PW], d3 = p[3 * PW], lw = p[-1], rw = p[1];
-    const uint32_t ul = p[-2 * PW - 1], uc = p[-2 * PW], ur = p[-2 * PW + 1];
-    const uint32_t dl = p[2 * PW - 1], dc = p[2 * PW], dq = p[2 * PW + 1];
+    const uint32_t u3 = p[-3 * PWH], d3 = p[3 * PWH], lw = p[-1], rw = p[1];
+    const uint32_t ul = p[-2 * PWH - 1], uc = p[-2 * PWH], ur = p[-2 * PWH + 1];
+    const uint32_t dl = p[2 * PWH - 1], dc = p[2 * PWH], dq = p[2 * PWH + 1];
     const uint32_t f0 = __vabsdiffu4(d3, c) + K, f8 = __vabsdiffu4(u3, c) + K;
     const uint32_t f4 = __vabsdiffu4(__byte_perm(c, rw, 0x6543), c) + K;
     const uint32_t f12 = __vabsdiffu4(__byte_perm(lw, c, 0x4321), c) + K;
@@ -434,7 +440,8 @@ __global__ void __launch_bounds__(FAST_NT * FAST_WPC) k_fast_cells(const OrbCell
                                                     int ini_th, int min_th, int rows_max, int t_max) {
   extern __shared__ __align__(16) unsigned char fsm_all[];
   FastSmem sm;
-  const int r_img = rows_max * PITCH, r_q = max(r_img, (2 * t_max + 31) & ~15);
+  constexpr int HVP = FAST_HVP && !FAST_PAIR ? FAST_HVP : PITCH;
+  const int r_img = rows_max * PITCH, r_q = max(rows_max * HVP, (2 * t_max + 31) & ~15);
   const int cell_idx = blockIdx.x * FAST_WPC + (threadIdx.x >> 5);
   if (cell_idx >= n_cells) return;  // whole warp; warps only ever synchronise with themselves
   unsigned char* fsm = fsm_all + (size_t)(threadIdx.x >> 5) * ((2 * r_img + r_q + 16 + 15) & ~15);
@@ -471,12 +478,14 @@ __global__ void __launch_bounds__(FAST_NT * FAST_WPC) k_fast_cells(const OrbCell
       const int i0 = max(wq + o, 0), d1 = min(wq + o + 1, ngw - 1) - i0;
       const uint32_t* gp = reinterpret_cast<const uint32_t*>(base) + (size_t)y_first * pw + i0;
       uint32_t* sp = reinterpret_cast<uint32_t*>(sm.img) + y_first * (PITCH / 4) + wq + (FAST_COL0 - 1) / 4;
+      uint32_t* hp = reinterpret_cast<uint32_t*>(sm.hv) + y_first * (HVP / 4) + wq + (FAST_COL0 - 1) / 4;
       for (int y = y_first; y < ch; y += FAST_NT / 16) {
         const uint32_t v = __byte_perm(__ldg(gp), __ldg(gp + d1), sel);
         sp[0] = v;
-        sp[r_img >> 2] = (v >> 1) & 0x7f7f7f7fu;
+        hp[0] = (v >> 1) & 0x7f7f7f7fu;
         gp += 2 * pw;
         sp += 2 * (PITCH / 4);
+        hp += 2 * (HVP / 4);
       }
     }
   }
@@ -489,8 +498,10 @@ __global__ void __launch_bounds__(FAST_NT * FAST_WPC) k_fast_cells(const OrbCell
       // Every corner of the first pass is a corner at the lower threshold too, so the second pass
       // re-measures it (same value) and its NMS sees the complete map.  The queue has overwritten
       // the halved image: rebuild it.
-      for (int i = tid; i < ch * (PITCH / 4); i += FAST_NT)
-        reinterpret_cast<uint32_t*>(sm.hv)[i] = (reinterpret_cast<const uint32_t*>(sm.img)[i] >> 1) & 0x7f7f7f7fu;
+      for (int i = tid; i < ch * (PITCH / 4); i += FAST_NT) {
+        const int y = i / (PITCH / 4), xw = i - y * (PITCH / 4);
+        reinterpret_cast<uint32_t*>(sm.hv)[y * (HVP / 4) + xw] = (reinterpret_cast<const uint32_t*>(sm.img)[i] >> 1) & 0x7f7f7f7fu;
+      }
       __syncwarp();
       th = min_th;
       total = fast_pass<PITCH>(sm, th, tw, thh, ch);
@@ -506,6 +517,333 @@ __global__ void __launch_bounds__(FAST_NT * FAST_WPC) k_fast_cells(const OrbCell
     out[i] = (uint32_t)(x + cell.off_x) | (uint32_t)(y + cell.off_y) << 12 | ((uint32_t)sm.m[off] - 1u) << 24;
   }
   if (tid == 0) cell_count[(size_t)frame * n_cells + cell_idx] = total;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 (streaming form) per-cell FAST-9/16 with NMS and the iniThFAST -> minThFAST fallback (:790-830), one WARP per
+// band (OrbBand: up to 8 whole cells of one cell row, <= 245 tested pixels wide).  Same three phases as k_fast_cells,
+// but the warp STREAMS down the band's rows instead of staging a cell:
+//   phase A  a lane owns 8 adjacent pixels (two words) of every row and keeps the last seven rows (halved bytes, own
+//            words + the two neighbour words fetched by shuffle) in registers: the packed opposite-pair rejection test
+//            runs entirely on registers - no shared-memory loads.  A lane whose 8 pixels hold a survivor pushes ONE
+//            entry (ring rows, first column, 8-bit survivor mask) behind the entries of the lanes before it (ballot).
+//   phase B  after every block of seven rows the entries are expanded, 32 at a time, into a staging list of
+//            candidates (row-major) that is measured 32 candidates at a time: exact arc measure from a 13-row ring of
+//            the raw rows in shared memory (mirror rows above and below the ring keep the 16 ring offsets compile-time
+//            constants); corners write their measure into a 9-row measure ring and enter a corner FIFO;
+//   phase C  3x3 NMS of the corners whose three measure rows are complete, in FIFO (= row-major) order, neighbours
+//            across a cell boundary counting as 0 (NMS is per cell in the reference); survivors pass through a small
+//            FIFO that a per-cell ordered split (one ballot per cell) empties into the cells' candidate slots.
+// Every buffer is bounded by the row schedule (sized for "every pixel is a candidate / a corner"), the lists stay in
+// cv::FAST's output order, and a band whose cells kept nothing at iniThFAST streams once more at minThFAST with only
+// those cells unmasked (:813-817).
+#define FB_BLOCK 7      // rows per block = the register window's period
+#define FB_RP 264       // raw ring: bytes per row (256 + 8: rows two banks apart)
+#define FB_RSLOTS 13    // block + 6 halo rows; slot s sits at physical row s + 3, rows 0..2 mirror the last three slots,
+#define FB_RROWS 19     // rows 16..18 the first three
+#define FB_MP 272       // measure ring: bytes per row
+#define FB_MSLOTS 9     // block + the pending row and the row above it; slot s at physical row s + 1, row 0 mirrors the
+#define FB_MROWS 11     // last slot, row 10 the first
+#define FB_ENT_CAP 224  // entries of a block (7 rows x 32 lanes)
+#define FB_STG_CAP 320  // staged candidates: < 32 left over + 32 entries x 8
+#define FB_CF_CAP 1024  // corner FIFO (ring)
+#define FB_KF_CAP 64    // NMS survivors waiting for the per-cell split
+#define FB_RAW_BYTES ((FB_RROWS * FB_RP + 15) & ~15)
+#define FB_SMEM (FB_RAW_BYTES + FB_MROWS * FB_MP + 4 * FB_ENT_CAP + 2 * FB_STG_CAP + 2 * FB_CF_CAP + 4 * FB_KF_CAP)
+
+#ifndef FB_MINB
+#define FB_MINB 18  // caps the kernel at 113 registers (it takes 128 uncapped for no gain): 18 warps per SM, the shared-memory limit
+#endif
+__global__ void __launch_bounds__(32, FB_MINB) k_fast_bands(const OrbBand* __restrict__ bands, OrbLevel0 l0,
+                                                   const uint8_t* __restrict__ pyr, uint32_t* __restrict__ cand,
+                                                   int* __restrict__ cell_count, size_t pyr_frame_bytes,
+                                                   size_t cand_frame_u32, int n_cells_frame, int ini_th, int min_th) {
+  __shared__ __align__(16) unsigned char fb[FB_SMEM];
+  uint8_t* const raw = fb;
+  uint8_t* const mr = fb + FB_RAW_BYTES;
+  uint32_t* const ebuf = reinterpret_cast<uint32_t*>(mr + FB_MROWS * FB_MP);
+  uint32_t* const kf = ebuf + FB_ENT_CAP;
+  uint16_t* const stg = reinterpret_cast<uint16_t*>(kf + FB_KF_CAP);
+  uint16_t* const cf = stg + FB_STG_CAP;
+  const int lane = threadIdx.x;
+  const unsigned lt = (1u << lane) - 1u;
+  const unsigned FULL = 0xffffffffu;
+
+  OrbBand band;
+  {
+    const uint4* br = reinterpret_cast<const uint4*>(bands + blockIdx.x);
+    reinterpret_cast<uint4*>(&band)[0] = __ldg(br);
+    reinterpret_cast<uint4*>(&band)[1] = __ldg(br + 1);
+  }
+  const int frame = blockIdx.y;
+  const int ncell = band.n_cells, nt = band.nt, cap = band.cand_cap;
+  int* const cc = cell_count + (size_t)frame * n_cells_frame + band.cell_idx0;
+  if (nt <= 0) {  // cells whose sub-image is too low to hold a tested pixel: cv::FAST finds nothing
+    if (lane < ncell) cc[lane] = 0;
+    return;
+  }
+  uint32_t* const out = cand + (size_t)frame * cand_frame_u32 + band.cand_slot_off;
+  const int xb = band.xb, x0 = band.x0, x1 = band.x1, w_cell = band.w_cell, y_first = band.y_first;
+  const uint32_t inv = (65536u + (uint32_t)w_cell - 1u) / (uint32_t)w_cell;  // (d * inv) >> 16 == d / w_cell for d < 256
+  const int pitch = band.level == 0 ? l0.pitch : band.pitch;
+  const uint8_t* const src = band.level == 0
+                                 ? l0.base + (size_t)frame * l0.frame_stride + (size_t)y_first * l0.pitch + xb
+                                 : pyr + (size_t)frame * pyr_frame_bytes + band.src_off;
+  const int pitch_w = pitch >> 2;
+  const int R_load = nt + 6;
+  const int nbytes = x1 + 3 - xb;  // bytes of a row anybody reads
+  const bool ldA = 8 * lane < nbytes, ldB = 8 * lane + 4 < nbytes;
+
+  int cnt_cell = 0;                       // lane c < ncell: candidates kept in cell c
+  unsigned active = (1u << ncell) - 1u;   // cells tested in this pass
+  for (int pass = 0; pass < 2; ++pass) {
+    const int th = pass ? min_th : ini_th;
+    const uint32_t K = 0x01010101u * (uint32_t)(128 - min(th >> 1, 127));
+    uint32_t maskA = 0, maskB = 0;  // bit 7 of every byte this lane tests
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int x = xb + 8 * lane + k;
+      bool t = x >= x0 && x < x1;
+      if (t) t = (active >> ((uint32_t)((x - x0) * inv) >> 16)) & 1u;
+      if (t) {
+        if (k < 4) maskA |= 0x80u << (8 * k);
+        else maskB |= 0x80u << (8 * (k - 4));
+      }
+    }
+    // the measure ring starts all zero (rows outside the tested area must read 0)
+    for (int i = lane; i < FB_MROWS * FB_MP / 16; i += 32) reinterpret_cast<uint4*>(mr)[i] = make_uint4(0, 0, 0, 0);
+
+    int n_e = 0;                // entries in ebuf
+    int chead = 0, ctail = 0;   // corner FIFO
+    int khead = 0, ktail = 0;   // survivor FIFO
+    int sr = 0;                 // raw ring slot of the next row to store
+    int er_c = 6, em_c = 1;     // physical ring rows (raw, measure) of the next row to test (local row 3 -> slots 3, 0)
+    int t_tested = 2;
+
+    // software pipeline of the global loads: two rows in flight
+    const uint32_t* gp = reinterpret_cast<const uint32_t*>(src) + 2 * lane;
+    int s_issue = 0;
+    uint32_t pA0 = 0, pB0 = 0, pA1 = 0, pB1 = 0;
+    auto issue = [&](uint32_t& a, uint32_t& b) {
+      a = 0;
+      b = 0;
+      if (s_issue < R_load) {
+        if (ldA) a = __ldg(gp);
+        if (ldB) b = __ldg(gp + 1);
+      }
+      gp += pitch_w;
+      ++s_issue;
+    };
+    issue(pA0, pB0);
+    issue(pA1, pB1);
+
+    uint32_t hA[7], hB[7], hL[7], hR[7];  // window: halved bytes of the last seven rows (own two words, neighbour words)
+    auto take_row = [&](int k) {
+      const uint32_t a = pA0, b = pB0;
+      pA0 = pA1;
+      pB0 = pB1;
+      issue(pA1, pB1);
+      hA[k] = (a >> 1) & 0x7f7f7f7fu;
+      hB[k] = (b >> 1) & 0x7f7f7f7fu;
+      hL[k] = __shfl_up_sync(FULL, hB[k], 1);
+      hR[k] = __shfl_down_sync(FULL, hA[k], 1);
+      uint2* dst = reinterpret_cast<uint2*>(raw + (sr + 3) * FB_RP) + lane;
+      *dst = make_uint2(a, b);
+      if (sr >= FB_RSLOTS - 3) dst[-FB_RSLOTS * (FB_RP / 8)] = make_uint2(a, b);
+      if (sr < 3) dst[FB_RSLOTS * (FB_RP / 8)] = make_uint2(a, b);
+      sr = sr == FB_RSLOTS - 1 ? 0 : sr + 1;
+    };
+
+    // ---- phase B / C pieces ------------------------------------------------------------------
+    // rows are recovered from ring slots: a measure-ring row em belongs to the row `age` rows before the last tested
+    auto row_of = [&](int em) {
+      int age = (em_c == 1 ? FB_MSLOTS : em_c - 1) - em;  // em_c - 1 (cyclic) = ring row of the last tested row
+      if (age < 0) age += FB_MSLOTS;
+      return t_tested - age;
+    };
+    auto emit_iter = [&]() {  // per-cell ordered split of up to 32 survivors
+      const int ks = ktail - khead;
+      const bool have = lane < ks;
+      const uint32_t key = kf[(khead + lane) & (FB_KF_CAP - 1)];
+      const int j = have ? (int)(((key & 0xfffu) + 16u - (uint32_t)x0) * inv >> 16) : -1;
+      int rank = 0, add = 0;
+      for (int c = 0; c < ncell; ++c) {
+        const unsigned bm = __ballot_sync(FULL, j == c);
+        if (j == c) rank = __popc(bm & lt);
+        if (lane == c) add = __popc(bm);
+      }
+      const int idx = __shfl_sync(FULL, cnt_cell, j & 31) + rank;
+      if (have && idx < cap) out[j * cap + idx] = key;
+      cnt_cell += add;
+      khead += min(ks, 32);
+    };
+    auto nms_iter = [&](int t_lim) -> int {  // NMS of the FIFO's leading corners with row <= t_lim; returns how many
+      const int csize = ctail - chead;
+      const bool have = lane < csize;
+      const int ent = cf[(chead + (have ? lane : 0)) & (FB_CF_CAP - 1)];
+      const int x = ent & 255, em = (ent >> 8) & 15;
+      const int row = row_of(em);
+      const bool elig = have && row <= t_lim;
+      const int n_take = __popc(__ballot_sync(FULL, elig));  // the FIFO is in row order: the eligible ones lead
+      bool keep = false;
+      int m = 0;
+      const int lx = xb + x;
+      if (elig) {
+        const uint8_t* c = mr + em * FB_MP + x;
+        m = c[0];
+        const int v = max((int)c[-FB_MP], (int)c[FB_MP]);
+        const int l = __vimax3_s32((int)c[-1], (int)c[-FB_MP - 1], (int)c[FB_MP - 1]);
+        const int r = __vimax3_s32((int)c[1], (int)c[-FB_MP + 1], (int)c[FB_MP + 1]);
+        const int cx0 = x0 + (int)((uint32_t)((lx - x0) * inv) >> 16) * w_cell, cx1 = min(cx0 + w_cell, x1);
+        keep = m > v && (lx == cx0 || m > l) && (lx + 1 == cx1 || m > r);
+      }
+      const unsigned kb = __ballot_sync(FULL, keep);
+      if (keep)
+        kf[(ktail + __popc(kb & lt)) & (FB_KF_CAP - 1)] =
+            (uint32_t)(lx - 16) | (uint32_t)(y_first + row - 16) << 12 | ((uint32_t)m - 1u) << 24;
+      ktail += __popc(kb);
+      chead += n_take;
+      __syncwarp();
+      if (ktail - khead >= 32) {
+        emit_iter();
+        __syncwarp();
+      }
+      return n_take;
+    };
+    auto drain = [&]() {  // expand and measure every entry of the block, then NMS every corner above the last tested row
+      __syncwarp();
+      int e0 = 0, s_head = 0, s_tail = 0;
+      while (true) {
+        if (s_tail - s_head < 32 && e0 < n_e) {
+          // the (< 32) staged candidates move to the front, 32 more entries expand behind them
+          const int left = s_tail - s_head;
+          const int keepv = lane < left ? stg[s_head + lane] : 0;
+          const uint32_t e = e0 + lane < n_e ? ebuf[e0 + lane] : 0u;
+          __syncwarp();
+          if (lane < left) stg[lane] = (uint16_t)keepv;
+          const uint32_t nib = e >> 16;
+          const int cnt = __popc(nib);
+          int incl = cnt;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+          }
+          uint16_t* q = stg + left + incl - cnt;
+          const uint32_t base = e & 0xffffu;
+#pragma unroll
+          for (int b = 0; b < 8; ++b)
+            if (nib >> b & 1) *q++ = (uint16_t)(base + b);
+          s_head = 0;
+          s_tail = left + __shfl_sync(FULL, incl, 31);
+          e0 += 32;
+          __syncwarp();
+          continue;
+        }
+        const int navail = s_tail - s_head;
+        if (navail == 0) break;
+        const bool valid = lane < navail;
+        const int ent = stg[s_head + (valid ? lane : 0)];
+        const int x = ent & 255, em = (ent >> 8) & 15, er = ent >> 12;
+        const int m = fast_arc_measure<FB_RP>(raw + er * FB_RP + x);
+        const bool corner = valid && m > th;
+        if (corner) {
+          mr[em * FB_MP + x] = (uint8_t)m;
+          if (em == FB_MSLOTS) mr[x] = (uint8_t)m;
+          if (em == 1) mr[(FB_MROWS - 1) * FB_MP + x] = (uint8_t)m;
+        }
+        const unsigned bm = __ballot_sync(FULL, corner);
+        if (corner) cf[(ctail + __popc(bm & lt)) & (FB_CF_CAP - 1)] = (uint16_t)ent;
+        ctail += __popc(bm);
+        s_head += min(navail, 32);
+        if (ctail - chead > FB_CF_CAP - 64) {
+          // keep the FIFO inside its ring: every row above this iteration's first candidate is completely measured,
+          // so at most two rows (490 corners) + this iteration's are not yet eligible - the rest can go now
+          __syncwarp();
+          const int t_first = row_of((__shfl_sync(FULL, ent, 0) >> 8) & 15);
+          while (ctail - chead > FB_CF_CAP / 2 + 64 && nms_iter(t_first - 2) > 0) {
+          }
+        }
+      }
+      n_e = 0;
+      __syncwarp();
+      while (nms_iter(t_tested - 1) == 32) {
+      }
+      // the next block's measure rows: zero them (their slots held rows that are dead now)
+      for (int i = lane; i < FB_BLOCK * (FB_MP / 16); i += 32) {
+        const int r = i / (FB_MP / 16), c = i - r * (FB_MP / 16);
+        int sl = em_c - 1 + r;
+        if (sl >= FB_MSLOTS) sl -= FB_MSLOTS;
+        reinterpret_cast<uint4*>(mr + (sl + 1) * FB_MP)[c] = make_uint4(0, 0, 0, 0);
+        if (sl == FB_MSLOTS - 1) reinterpret_cast<uint4*>(mr)[c] = make_uint4(0, 0, 0, 0);
+        if (sl == 0) reinterpret_cast<uint4*>(mr + (FB_MROWS - 1) * FB_MP)[c] = make_uint4(0, 0, 0, 0);
+      }
+      __syncwarp();
+    };
+
+    // ---- the stream --------------------------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < 6; ++k) take_row(k);
+    for (int s0 = 6; s0 < R_load; s0 += 7) {
+#pragma unroll
+      for (int u = 0; u < 7; ++u) {
+        if (s0 + u < R_load) {
+          const int k = (6 + u) % 7;  // window slot of the new row; the tested row sits three slots back
+          take_row(k);
+          const int c = (k + 4) % 7, p2 = (k + 6) % 7, m2 = (k + 2) % 7, m3 = (k + 1) % 7;
+          // Packed rejection test (see k_fast_cells): a corner has |p - c| > th for one pixel of every opposite
+          // pair of the eight even ring positions.
+          const uint32_t cA = hA[c], cB = hB[c];
+          const uint32_t c_ab3 = __byte_perm(cA, cB, 0x6543), c_ab1 = __byte_perm(cA, cB, 0x4321);
+          const uint32_t p_ab = __byte_perm(hA[p2], hB[p2], 0x5432), m_ab = __byte_perm(hA[m2], hB[m2], 0x5432);
+          uint32_t passA, passB;
+          {
+            const uint32_t f0 = __vabsdiffu4(hA[k], cA) + K, f8 = __vabsdiffu4(hA[m3], cA) + K;
+            const uint32_t f4 = __vabsdiffu4(c_ab3, cA) + K;
+            const uint32_t f12 = __vabsdiffu4(__byte_perm(hL[c], cA, 0x4321), cA) + K;
+            const uint32_t f2 = __vabsdiffu4(p_ab, cA) + K;
+            const uint32_t f14 = __vabsdiffu4(__byte_perm(hL[p2], hA[p2], 0x5432), cA) + K;
+            const uint32_t f6 = __vabsdiffu4(m_ab, cA) + K;
+            const uint32_t f10 = __vabsdiffu4(__byte_perm(hL[m2], hA[m2], 0x5432), cA) + K;
+            passA = (f0 | f8) & (f4 | f12) & (f2 | f10) & (f6 | f14) & maskA;
+          }
+          {
+            const uint32_t f0 = __vabsdiffu4(hB[k], cB) + K, f8 = __vabsdiffu4(hB[m3], cB) + K;
+            const uint32_t f4 = __vabsdiffu4(__byte_perm(cB, hR[c], 0x6543), cB) + K;
+            const uint32_t f12 = __vabsdiffu4(c_ab1, cB) + K;
+            const uint32_t f2 = __vabsdiffu4(__byte_perm(hB[p2], hR[p2], 0x5432), cB) + K;
+            const uint32_t f14 = __vabsdiffu4(p_ab, cB) + K;
+            const uint32_t f6 = __vabsdiffu4(__byte_perm(hB[m2], hR[m2], 0x5432), cB) + K;
+            const uint32_t f10 = __vabsdiffu4(m_ab, cB) + K;
+            passB = (f0 | f8) & (f4 | f12) & (f2 | f10) & (f6 | f14) & maskB;
+          }
+          // one entry per lane with a survivor: ring rows, first column, 8-bit mask (column order)
+          const unsigned eb = __ballot_sync(FULL, (passA | passB) != 0);
+          if (passA | passB) {
+            const uint32_t nib = (((passA >> 7) * 0x10204080u) >> 28) | ((((passB >> 7) * 0x10204080u) >> 28) << 4);
+            ebuf[n_e + __popc(eb & lt)] = nib << 16 | (uint32_t)(er_c << 12 | em_c << 8 | 8 * lane);
+          }
+          n_e += __popc(eb);
+          er_c = er_c == FB_RSLOTS + 2 ? 3 : er_c + 1;
+          em_c = em_c == FB_MSLOTS ? 1 : em_c + 1;
+          ++t_tested;
+        }
+      }
+      drain();
+    }
+    // the last tested row: the row below it is all zero in the measure ring
+    while (nms_iter(t_tested) == 32) {
+    }
+    if (ktail - khead > 0) emit_iter();
+    __syncwarp();
+
+    if (pass == 0) {
+      const unsigned empty = __ballot_sync(FULL, lane < ncell && cnt_cell == 0);
+      if (empty == 0 || min_th >= ini_th) break;
+      active = empty;
+    }
+  }
+  if (lane < ncell) cc[lane] = min(cnt_cell, cap);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -863,6 +1201,12 @@ void launch_pyramid(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, uint8_t* 
 
 void launch_fast(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, const uint8_t* d_pyr, uint32_t* d_cand,
                  int* d_cell_count, cudaStream_t st, long long* launches) {
+  if (gh.fast_bands) {
+    k_fast_bands<<<dim3(gh.n_bands, n_frames), 32, 0, st>>>(gh.d_bands, l0, d_pyr, d_cand, d_cell_count, gh.g.pyr_frame_bytes,
+                                                            gh.g.cand_frame_u32, gh.g.n_cells, gh.g.ini_th, gh.g.min_th);
+    ++*launches;
+    return;
+  }
   // shared memory sized for this geometry's largest cell (rows x pitch image + measure map,
   // survivor queue, kept list, overlaid): ~6 KB at 640x480, so 32 cell CTAs stay resident per SM
   int rows_max = 0, t_max = 1, cw_max = 0;
@@ -873,7 +1217,8 @@ void launch_fast(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, const uint8_
   }
   const int pitch = cw_max + 3 + (FAST_COL0 - 1) <= 48 ? 48 : 80;  // + up to 3 bytes of word misalignment (+ the pair shift)
   const size_t r_img = (size_t)rows_max * pitch;
-  const size_t smem_cell = (2 * r_img + max(r_img, (size_t)((2 * t_max + 31) & ~15)) + 16 + 15) & ~(size_t)15;
+  const size_t r_hv = (size_t)rows_max * (FAST_HVP && !FAST_PAIR ? FAST_HVP : pitch);
+  const size_t smem_cell = (2 * r_img + max(r_hv, (size_t)((2 * t_max + 31) & ~15)) + 16 + 15) & ~(size_t)15;
   const size_t smem = smem_cell * FAST_WPC;
   const dim3 grid((gh.g.n_cells + FAST_WPC - 1) / FAST_WPC, n_frames);
   if (pitch == 48)

@@ -20,10 +20,14 @@ struct OrbGeomHost {
   OrbGeom g;               // host copy
   OrbGeom* d_geom;         // device copy
   OrbCell* d_cells;        // [g.n_cells]
+  OrbBand* d_bands;        // [n_bands] work list of the FAST kernel
+  int n_bands;
   OrbXTap* d_xtab;
   OrbYTap* d_ytab;
   int ot_smem_keys;        // octree: keys kept in shared memory (prepare_octree)
   size_t ot_smem_bytes;    // octree: dynamic shared memory per CTA
+  int fast_bands;          // FAST kernel of this handle: 0 = one warp per cell (k_fast_cells), 1 = one warp per band
+                           // (k_fast_bands); resolved once in orbx_create (ORB_B200_FAST=cells|bands, default cells)
 };
 
 void launch_pyramid(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, uint8_t* d_pyr, cudaStream_t st,

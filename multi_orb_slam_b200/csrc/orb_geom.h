@@ -52,6 +52,25 @@ struct __align__(16) OrbCell {  // one live FAST cell (:790-830); self-contained
   short pad;
 };
 
+// One unit of work of the FAST kernel: a horizontal band = one row of FAST cells of one level, cut into chunks of
+// whole cells no wider than the 30 lanes x 8 px a warp tests per image row.  The tested areas of the reference's
+// cells (:790-830: sub-image minus its 3-px border) tile [19, w-19) x [19, h-19) of the level, so a band's tested
+// area is the rectangle [x0, x1) x [y_first + 3, y_first + 3 + nt).
+struct __align__(16) OrbBand {
+  unsigned src_off;         // levels >= 1: byte offset, inside a frame's pyramid block, of (row y_first, column xb)
+  unsigned cand_slot_off;   // u32 offset, inside a frame's candidate block, of the first cell's slots
+  int cell_idx0;            // index of the first cell in the frame's cell list
+  unsigned short pitch;     // bytes per row of the level (levels >= 1)
+  unsigned short cand_cap;  // candidate slots per cell
+  short level, n_cells;     // n_cells <= 8
+  short y_first;            // level row of the first row the band loads (first tested row - 3)
+  short nt;                 // tested rows (<= 0: the cells exist but their tested area is empty)
+  short xb;                 // level column of byte 0 of lane 0 (multiple of 4); lanes 1..30 hold the tested pixels
+  short x0, x1;             // tested columns [x0, x1); cell c of the band tests [x0 + c*w_cell, min(x0 + (c+1)*w_cell, x1))
+  short w_cell;
+};
+#define ORB_BAND_MAX_PX 245  // tested pixels per band row: 256 bytes - (up to 7 bytes of alignment) - one word of halo
+
 struct OrbGeom {
   int nlevels;
   int width, height;

@@ -157,33 +157,36 @@ def test_two_handles_with_different_nfeatures(O):
         _assert_same_features(k, d, k_ref, d_ref, f"nf={nf}")
 
 
-def test_cpp_dropin_classes_run(O, tmp_path):
-    """The reference-shaped C++ classes over the C-ABI: same keypoints/descriptors as the oracle."""
-    import struct
-    import subprocess
-    from test_abi import _build_dropin
-    from multi_orb_slam_b200._lib import KP_DTYPE
-    exe = _build_dropin()
-    img = textured(640, 480, 6)
-    src, dst = tmp_path / "img.bin", tmp_path / "out.bin"
-    src.write_bytes(struct.pack("<2i", 640, 480) + img.tobytes())
-    subprocess.run([exe, str(src), str(dst)], check=True)
-    raw = dst.read_bytes()
-    n = struct.unpack_from("<i", raw, 0)[0]
-    k = np.frombuffer(raw, dtype=KP_DTYPE, count=n, offset=4)
-    d = np.frombuffer(raw, dtype=np.uint8, count=n * 32, offset=4 + 24 * n).reshape(n, 32)
-    nm, d01, self_m, pw, ph, nbow, bow_self = struct.unpack_from("<7i", raw, 4 + 56 * n)
-    k_ref, d_ref, _ = O.extractor("port").extract(img)
-    _assert_same_features(k, d, k_ref, d_ref, "C++ drop-in")
-    prev = np.stack([k_ref["x"], k_ref["y"]], axis=1).astype(np.float32)
-    rn, rm12, _ = O.search_for_initialization(k_ref, d_ref, k_ref, d_ref, (0, 640, 0, 480), prev, 100, 0.9, True)
-    assert nm == rn and self_m == int((rm12 == np.arange(len(rm12))).sum())
-    assert d01 == O.distance(d_ref[0], d_ref[1]) and (pw, ph) == (370, 278)
-    # SearchByBoW_cam1 of the frame against itself, vocabulary node = octave
-    from multi_orb_slam_b200.synth import feature_vector
-    fv = feature_vector(k_ref["octave"])
-    bn, bm12, bm21 = O.search_by_bow(d_ref, k_ref["angle"], None, fv, d_ref, k_ref["angle"], None, fv, 0.7, True, 50)
-    assert nbow == bn and bow_self == int((bm21 == np.arange(len(bm21))).sum())
+@pytest.mark.parametrize("case", ["textured", "kitti", "hd", "small", "low_texture", "noise", "constant"])
+def test_band_fast_kernel_matches_the_oracle(O, monkeypatch, case):
+    """The streaming band form of the FAST stage (k_fast_bands, chosen per handle with ORB_B200_FAST=bands; the default
+    is the per-cell kernel): candidate lists per level incl. their order, and the final features, equal to the oracle
+    — on textured frames of several geometries (whole and clipped cells, 3..8 cells per band), on a low-texture frame
+    (most cells rerun at minThFAST), on uniform noise (dense candidates: the bounded buffers fill) and on a constant
+    frame (cells that keep nothing in either pass)."""
+    monkeypatch.setenv("ORB_B200_FAST", "bands")
+    size, nf = {"kitti": ((1241, 376), 2000), "hd": ((1280, 720), 1000), "small": ((320, 240), 300)}.get(case, ((640, 480), 1000))
+    w, h = size
+    if case == "low_texture":
+        rng = np.random.default_rng(3)
+        img = (128 + rng.integers(-6, 7, size=(h, w))).astype(np.uint8)
+        img[200:280, 300:380] += 40
+    elif case == "noise":
+        img = np.random.default_rng(5).integers(0, 256, size=(h, w), dtype=np.uint8)
+    elif case == "constant":
+        img = np.full((h, w), 77, dtype=np.uint8)
+    else:
+        img = textured(w, h, 21)
+    port = O.extractor("port", nfeatures=nf)
+    k_ref, d_ref, _ = port.extract(img)
+    ex = _gpu(nf, size)
+    k, d = ex(img)
+    for l in range(8):
+        gx, gy, gs = ex.debug_candidates(l)
+        rx, ry, rs = port.candidates(l)
+        assert len(gx) == len(rx), f"level {l}: {len(gx)} candidates vs {len(rx)}"
+        assert np.array_equal(gx, rx) and np.array_equal(gy, ry) and np.array_equal(gs, rs), f"candidates level {l}"
+    _assert_same_features(k, d, k_ref, d_ref, case)
 
 
 def test_full_size_batch_is_frame_independent(O):
