@@ -369,14 +369,14 @@ def rig8_leg(args, world, rank, local_rank, dev, barrier, peak):
     fe = RigFrontEnd(RIG8["n_cams"], RIG8["nfeatures"], SCALE, NLEVELS, INI_TH, MIN_TH, image_size=(RIG8["w"], RIG8["h"]),
                      rig_frames=F, chunk=chunk, rank=rank, world=world, device=local_rank, nnratio=NNRATIO, th_dist=50)
     images = {}
-    for c in fe.cams:
+    for c in fe.input_cams:
         base = torch.from_numpy(camera_sequence(RIG8["w"], RIG8["h"], distinct, 300 + c)).to(dev)
         full = torch.empty((F, RIG8["h"], RIG8["w"]), dtype=torch.uint8, device=dev)
         for i in range(0, F, distinct):  # every frame has its own HBM bytes (no L2 reuse across the tiled copies)
             full[i:i + distinct] = base[: min(distinct, F - i)]
         images[c] = full
 
-    host_ms = [0.0]
+    host_ms, per_rank = [0.0], [0.0]
 
     def timed(steps):
         barrier()
@@ -390,34 +390,44 @@ def rig8_leg(args, world, rank, local_rank, dev, barrier, peak):
         torch.cuda.synchronize()
         barrier()
         ms = e0.elapsed_time(e1) / steps
+        per_rank[:] = [ms]
         if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            t = torch.zeros(world, dtype=torch.float64, device=dev)
+            t[rank] = ms
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            per_rank[:] = [float(x) for x in t.tolist()]
+            ms = max(per_rank)
         return ms, res
 
     # Warm-up: at least W steps AND at least ~0.5 s of load — the leg starts after seconds of host-side image generation
     # with the GPU idle, and a B200 needs a few hundred ms of load to return to its full clocks (a 50 ms timed region
     # started cold measured 8 % slow).  Timed steps: at least 0.25 s worth.
-    ms_probe, _ = timed(max(3, args.warmup))
+    timed(max(3, args.warmup))  # first call: lazy allocations, NCCL connection set-up
     t_w = time.perf_counter()
     while time.perf_counter() - t_w < 0.5:
-        timed(max(3, args.warmup))
+        ms_probe, _ = timed(max(3, args.warmup))
     steps = max(3, min(args.steps, args.rig8_steps), int(np.ceil(250.0 / max(ms_probe, 1e-3))))
     steps = min(steps, 200)
     l0 = fe.launch_count
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     ms, res = timed(steps)
+    clocks = sampler.stop() if sampler else None
+    ms_per_rank = list(per_rank)
     launches = (fe.launch_count - l0) // steps
     host_enqueue_ms = host_ms[0]
     out = {"workload": f"configs[4]: {RIG8['n_cams']} cameras x {F} rig-frames of {RIG8['w']}x{RIG8['h']} "
                        f"({RIG8['n_cams'] * F} camera-frames per step, tiled from {distinct} distinct frames per camera), "
-                       f"nFeatures {RIG8['nfeatures']}; camera streams dealt over the ranks, chunks of {fe.chunk} rig-frames; "
+                       f"nFeatures {RIG8['nfeatures']}; camera streams dealt over the ranks (the deal rotates by one camera "
+                       f"per chunk), chunks of {fe.chunk} rig-frames; "
                        "cross-camera match = brute force camera c -> (c+1) mod 8, ratio 0.9, TH_LOW 50, rig-frames "
                        "sharded over the ranks",
            "scaling": "strong", "n_gpus": world, "steps": steps, "ms_per_step": ms,
            "value": RIG8["n_cams"] * F / (ms * 1e-3), "unit": UNIT,
            "cameras_per_rank": len(fe.cams), "chunks_per_step": fe.n_chunks, "gpu_launches_per_step": int(launches),
            "host_enqueue_ms_per_step_rank0": host_enqueue_ms,
+           "ms_per_step_by_rank": [round(x, 3) for x in ms_per_rank], "clocks_rank0": clocks,
            "collective": "one in-place ncclAllGather per chunk via orbd_allgather_inplace (C ABI), own stream"
                          if world > 1 else "none (single rank)",
            "inputs": "resident in HBM"}
@@ -443,17 +453,19 @@ def rig8_leg(args, world, rank, local_rank, dev, barrier, peak):
         dist.all_reduce(ag, op=dist.ReduceOp.MAX)
         ag_ms = float(ag.item())
         # A/B, interleaved so that drift cancels: the step with and without its collective
-        with_g, without_g = [ms], []
+        with_g, without_g, nog_by_rank = [ms], [], None
         for _ in range(3):
             fe.skip_gather = True
             without_g.append(timed(steps)[0])
+            nog_by_rank = [round(x, 3) for x in per_rank]
             fe.skip_gather = False
             with_g.append(timed(steps)[0])
         ms_nog = float(np.median(without_g))
         exposed = max(0.0, float(np.median(with_g)) - ms_nog)
         out["allgather"] = {"ms_per_step_alone": ag_ms, "bytes_per_rank_per_step": fe.layout.bytes_per_rank * fe.n_chunks,
                             "algbw_GBps": fe.layout.bytes_per_rank * fe.n_chunks * (world - 1) / (ag_ms * 1e-3) / 1e9,
-                            "ms_per_step_without_collective": ms_nog, "exposed_ms": exposed,
+                            "ms_per_step_without_collective": ms_nog, "ms_without_collective_by_rank": nog_by_rank,
+                            "exposed_ms": exposed,
                             "overlap_frac": round(1.0 - min(1.0, exposed / ag_ms), 3) if ag_ms > 0 else None,
                             "collective_share_of_step": round(exposed / ms, 4)}
     fe.close()
@@ -664,7 +676,11 @@ def main():
     ap.add_argument("--split-profile", action="store_true", help="take the per-stage events on separate steps")
     ap.add_argument("--bf-size", type=int, default=65536, help="N of the N x N brute-force matching leg")
     ap.add_argument("--rig8-frames", type=int, default=512, help="rig-frames per step of the configs[4] leg (x 8 cameras)")
-    ap.add_argument("--rig8-chunk", type=int, default=64, help="rig-frames per extraction / all-gather chunk (configs[4])")
+    ap.add_argument("--rig8-chunk", type=int, default=256,
+                    help="rig-frames per extraction / all-gather chunk (configs[4]).  A rank extracts one camera's chunk per launch "
+                         "group: 64-frame groups are latency-bound (single-wave octree, tiny top pyramid levels): measured on 8 "
+                         "GPUs 10.77 / 9.46 / 8.98 ms per step at 64 / 128 / 256, scaling efficiency 0.90 / 0.935 / 0.96 "
+                         "(profiles/r02_rig8_scaling.md)")
     ap.add_argument("--rig8-distinct", type=int, default=8, help="distinct synthetic frames per camera, tiled (configs[4])")
     ap.add_argument("--rig8-steps", type=int, default=5, help="timed steps of the configs[4] leg (capped by --steps)")
     ap.add_argument("--no-rig8", action="store_true", help="skip the configs[4] leg")

@@ -25,13 +25,15 @@ def shard_range(n_units: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
-def camera_owner(cam: int, world: int) -> int:
-    """Config 5: camera streams are dealt round-robin, so 8 GPUs take one camera each."""
-    return cam % world
+def camera_owner(cam: int, world: int, rot: int = 0) -> int:
+    """Config 5: camera streams are dealt round-robin, so 8 GPUs take one camera each.  `rot` rotates the deal
+    (RigFrontEnd advances it by one per chunk of rig-frames: the cameras differ in texture, hence in cost, and a rank
+    that kept the busiest camera for the whole batch would set the pace for all the others)."""
+    return (cam + rot) % world
 
 
-def cameras_of(rank: int, n_cams: int, world: int) -> List[int]:
-    return [c for c in range(n_cams) if camera_owner(c, world) == rank]
+def cameras_of(rank: int, n_cams: int, world: int, rot: int = 0) -> List[int]:
+    return [c for c in range(n_cams) if camera_owner(c, world, rot) == rank]
 
 
 def cross_camera_pairs(n_cams: int) -> List[Tuple[int, int]]:
@@ -46,8 +48,9 @@ def _align(n: int, a: int = 256) -> int:
 class RigLayout:
     """Byte layout of the gather buffer of one chunk of `chunk` rig-frames.
 
-    world * per camera blocks, rank-major: block r*per + j belongs to camera r + j*world (the round-robin deal of
-    camera_owner), so rank r's `per` blocks are contiguous = its send slot of the in-place all-gather.  A block:
+    world * per camera blocks, rank-major: block r*per + j belongs to the j-th camera of rank r under the round-robin
+    deal of camera_owner (rotated by `rot`), so rank r's `per` blocks are contiguous = its send slot of the in-place
+    all-gather.  A block:
     counts [chunk] i32 | keypoints [chunk, cap, 6] f32 (orbx_keypoint rows) | descriptors [chunk, cap, 32] u8,
     sections 256-byte aligned."""
 
@@ -63,23 +66,23 @@ class RigLayout:
         self.bytes_per_rank = self.per * self.block_bytes
         self.total_bytes = self.world * self.bytes_per_rank
 
-    def block_of(self, cam: int) -> int:
-        return camera_owner(cam, self.world) * self.per + cam // self.world
+    def block_of(self, cam: int, rot: int = 0) -> int:
+        return camera_owner(cam, self.world, rot) * self.per + cam // self.world
 
-    def block_offset(self, cam: int) -> int:
-        return self.block_of(cam) * self.block_bytes
+    def block_offset(self, cam: int, rot: int = 0) -> int:
+        return self.block_of(cam, rot) * self.block_bytes
 
-    def views(self, buf, cam: int):
+    def views(self, buf, cam: int, rot: int = 0):
         """(counts [chunk] i32, kps [chunk, cap, 6] f32, desc [chunk, cap, 32] u8) views of camera `cam`'s block
         inside the flat uint8 torch tensor `buf`."""
         import torch
-        o = self.block_offset(cam)
+        o = self.block_offset(cam, rot)
         counts = buf[o + self.off_counts: o + self.off_counts + 4 * self.chunk].view(torch.int32)
         kps = buf[o + self.off_kps: o + self.off_kps + 24 * self.chunk * self.cap].view(torch.float32).view(self.chunk, self.cap, 6)
         desc = buf[o + self.off_desc: o + self.off_desc + 32 * self.chunk * self.cap].view(self.chunk, self.cap, 32)
         return counts, kps, desc
 
-    def match_tables(self, pairs: Sequence[Tuple[int, int]], lo: int, hi: int) -> np.ndarray:
+    def match_tables(self, pairs: Sequence[Tuple[int, int]], lo: int, hi: int, rot: int = 0) -> np.ndarray:
         """Offset tables of orbm_bruteforce_indexed_device for rig-frames [lo, hi) of the chunk and the camera pairs
         `pairs`: int64 [4, n] (query rows, target rows, query count, target count), pair index = pi*(hi-lo) + (f-lo)."""
         n = len(pairs) * (hi - lo)
@@ -87,7 +90,7 @@ class RigLayout:
         f = np.arange(lo, hi, dtype=np.int64)
         for pi, (a, b) in enumerate(pairs):
             s = slice(pi * (hi - lo), (pi + 1) * (hi - lo))
-            oa, ob = self.block_offset(a), self.block_offset(b)
+            oa, ob = self.block_offset(a, rot), self.block_offset(b, rot)
             t[0, s] = oa + self.off_desc + f * (32 * self.cap)
             t[1, s] = ob + self.off_desc + f * (32 * self.cap)
             t[2, s] = oa + self.off_counts + 4 * f

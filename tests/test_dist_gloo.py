@@ -29,6 +29,29 @@ def test_camera_dealing():
     assert cross_camera_pairs(3) == [(0, 1), (1, 2), (2, 0)]
 
 
+def test_rotated_camera_deal():
+    """The deal rotates by one camera per chunk: at every rotation the ranks still partition the cameras, every rank's
+    blocks stay contiguous (its all-gather send slot), and over `world` chunks every rank has held every camera."""
+    from multi_orb_slam_b200.dist import RigLayout
+    n_cams, world = 8, 4
+    L = RigLayout(n_cams, world, 5, 7)
+    seen = {r: set() for r in range(world)}
+    for rot in range(world):
+        owned = [cameras_of(r, n_cams, world, rot) for r in range(world)]
+        assert sorted(c for o in owned for c in o) == list(range(n_cams))
+        for r in range(world):
+            assert all(camera_owner(c, world, rot) == r for c in owned[r])
+            assert sorted(L.block_of(c, rot) for c in owned[r]) == [r * L.per + j for j in range(L.per)]
+            seen[r].update(owned[r])
+        assert sorted(L.block_of(c, rot) for c in range(n_cams)) == list(range(n_cams))
+        buf = torch.zeros(L.total_bytes, dtype=torch.uint8)
+        for c in range(n_cams):
+            L.views(buf, c, rot)[2][:] = c + 1
+        t = L.match_tables([(1, 6)], 0, 2, rot)
+        assert buf.numpy()[t[0, 0]] == 2 and buf.numpy()[t[1, 1]] == 7
+    assert all(seen[r] == set(range(n_cams)) for r in range(world))
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

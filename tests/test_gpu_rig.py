@@ -29,7 +29,7 @@ def _check_rank(rank, world, n_cams, F, chunk, backend="orbd"):
     seqs = {c: camera_sequence(W, H, F, 70 + c) for c in range(n_cams)}  # every rank can rebuild any stream
     fe = RigFrontEnd(n_cams, NF, 1.2, 8, 20, 7, image_size=(W, H), rig_frames=F, chunk=chunk, rank=rank, world=world,
                      device=rank, backend=backend)
-    images = {c: torch.from_numpy(seqs[c]).to(f"cuda:{rank}") for c in fe.cams}
+    images = {c: torch.from_numpy(seqs[c]).to(f"cuda:{rank}") for c in fe.input_cams}
     res = fe.step(images, collect=True)
     fe.sync()
     bad = []
@@ -44,7 +44,7 @@ def _check_rank(rank, world, n_cams, F, chunk, backend="orbd"):
         buf = res.collected[k]
         # after the gather every rank holds every camera's block of the chunk
         for c in range(n_cams):
-            counts, kps, desc = (t.cpu().numpy() for t in L.views(buf, c))
+            counts, kps, desc = (t.cpu().numpy() for t in L.views(buf, c, res.rots[k]))
             for j in range(n):
                 rk, rd = ref[(c, f0 + j)]
                 m = int(counts[j])
