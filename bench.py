@@ -659,6 +659,7 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------
 def main():
+    global WARM_S
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -687,8 +688,12 @@ def main():
     ap.add_argument("--rig8-cams", type=int, default=8, help="cameras of the configs[4] leg (development probes only)")
     ap.add_argument("--rig8-only", action="store_true", help="run only the configs[4] leg and print its block (development)")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[0]/[2]/[3] rows")
+    ap.add_argument("--warm-seconds", type=float, default=WARM_S,
+                    help="seconds of load before every timed region, on top of the W warm-up steps (0 for ncu runs: a "
+                         "launch list should not carry hundreds of warm-up steps)")
     ap.add_argument("--kitti-pairs", type=int, default=64, help="stereo pairs per step of the configs[3] row")
     args = ap.parse_args()
+    WARM_S = args.warm_seconds
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference_arm(args)

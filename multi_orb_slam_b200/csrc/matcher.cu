@@ -431,9 +431,18 @@ __global__ void __launch_bounds__(256) k_init_candidates(int cap, const orbx_key
 }
 
 #define INIT_SMEM_CAND 12288  // candidate entries staged in shared memory per pair (48 KB)
-#define INIT_NT 512           // threads of the resolve CTA: the staging of the candidate rows is a chain of
-                              // global-load latencies per warp (a row per iteration), so it wants many warps;
-                              // the ordered walk itself runs on warp 0
+#define INIT_NT 1024          // threads of the resolve CTA: 32 warps stage the candidate rows (a chain of global-load
+                              // latencies per warp, a row per iteration) and then walk the queries 32 at a time
+
+// Ordered walk of k_init_resolve, 32 queries per step (the scheme of k_proj_resolve_cta).  A query's outcome - accepted
+// or not, and with which keypoint of F2 - is a function of its two least keys among the candidates that pass the
+// vMatchedDistance filter (:907), and that filter only ever removes candidates as the walk proceeds (matched distances
+// only shrink).  So every pending warp scans its query's row under the distances as they stand; warp 0 commits the
+// longest prefix of the step whose answers cannot depend on each other: a query is in conflict when a LOWER query of
+// the step that accepts a match takes the keypoint of its best or of its second candidate (claim bytes, lowest lane per
+// keypoint); the lowest pending query never conflicts, so every round commits at least one, in order, and the rest scan
+// again.  Stealing a keypoint from an earlier query (:926-933) touches only that earlier query, which is never one of
+// the same prefix (two queries of a prefix never share a keypoint).
 
 __global__ void __launch_bounds__(INIT_NT) k_init_resolve(int cap, const orbx_keypoint* __restrict__ k1_all,
                                                       const int32_t* __restrict__ n1_arr,
@@ -443,12 +452,14 @@ __global__ void __launch_bounds__(INIT_NT) k_init_resolve(int cap, const orbx_ke
                                                       const int* __restrict__ cand_cnt_all,
                                                       int32_t* __restrict__ matches12_all, int32_t* __restrict__ nmatches_out) {
   // matchedDist, matches21, bin_of, cand count, cand offset, query list, matches12: [cap] ints each;
-  // angle1, angle2: [cap] floats; then INIT_SMEM_CAND staged candidate entries
+  // angle1, angle2: [cap] floats; then INIT_SMEM_CAND staged candidate entries and [cap] claim bytes
   extern __shared__ int s_dyn[];
   __shared__ int s_hist[HISTO_LENGTH];
   __shared__ int s_keep[HISTO_LENGTH];
-  __shared__ int s_nmatch, s_total;
+  __shared__ int s_nmatch, s_total, s_nlist;
   __shared__ int s_wsum[INIT_NT / 32];
+  __shared__ int s_xb[2][32], s_xs[2][32], s_xw[2][32], s_xd[2][32];  // per-round exchange, double-buffered by round parity
+  __shared__ unsigned s_xdone[2], s_xleft[2];
   const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n1 = min(n1_arr[pair], cap), n2 = min(n2_arr[pair], cap);
   const orbx_keypoint* k1 = k1_all + (size_t)pair * cap;
@@ -467,6 +478,7 @@ __global__ void __launch_bounds__(INIT_NT) k_init_resolve(int cap, const orbx_ke
   float* s_ang1 = reinterpret_cast<float*>(s_dyn + 7 * cap);
   float* s_ang2 = reinterpret_cast<float*>(s_dyn + 8 * cap);
   uint32_t* s_cand = reinterpret_cast<uint32_t*>(s_dyn + 9 * cap);
+  uint8_t* s_claim = reinterpret_cast<uint8_t*>(s_cand + INIT_SMEM_CAND);  // [cap] claim bytes of a round (0xFF = free)
   for (int i = tid; i < cap; i += INIT_NT) {
     s_mdist[i] = 0x7FFFFFFF;
     s_m21[i] = -1;
@@ -517,56 +529,98 @@ __global__ void __launch_bounds__(INIT_NT) k_init_resolve(int cap, const orbx_ke
       if (has) s_list[nlist + __popc(bm & ((1u << lane) - 1u))] = i;
       nlist += __popc(bm);
     }
-    __syncwarp();
-    int nmatches = 0;
-    for (int j = 0; j < nlist; ++j) {
-      const int i1 = s_list[j];
-      const int cnt = s_cnt[i1];
-      const uint32_t* row = staged ? s_cand + s_off[i1] : cand + (size_t)i1 * cap;
-      // key = dist << 16 | traversal position: strict-< scan order (:910-919); the lane that
-      // owns the best key also remembers its i2
-      uint32_t best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
-      int my_i2 = -1;
-      for (int c = lane; c < cnt; c += 32) {
-        const uint32_t e = row[c];
-        const int dist = (int)(e >> 16), i2 = (int)(e & 0xFFFFu);
-        if (s_mdist[i2] <= dist) continue;  // :907
-        const uint32_t key = (uint32_t)dist << 16 | (uint32_t)c;
-        second = min(second, max(best, key));
-        if (key < best) { best = key; my_i2 = i2; }
+    if (lane == 0) s_nlist = nlist;
+  }
+  for (int i = tid; i < cap; i += INIT_NT) s_claim[i] = 0xFF;
+  __syncthreads();
+  const int nlist = s_nlist;
+  int nmatches = 0;  // warp 0's count
+  int rp = 0;        // round parity of the exchange buffers
+  for (int b0 = 0; b0 < nlist; b0 += 32) {
+    const int i1 = b0 + warp < nlist ? s_list[b0 + warp] : -1;
+    const int cnt = i1 >= 0 ? s_cnt[i1] : 0;
+    const uint32_t* row = i1 >= 0 ? (staged ? s_cand + s_off[i1] : cand + (size_t)i1 * cap) : nullptr;
+    bool pend = i1 >= 0;
+    for (;;) {
+      int bidx = -1, sidx = -1, will = 0, bdist = 0;
+      if (pend) {
+        // key = dist << 16 | traversal position: strict-< scan order (:910-919); every lane remembers the keypoints
+        // of its own two least keys
+        uint32_t best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
+        int best_i2 = -1, second_i2 = -1;
+        for (int c = lane; c < cnt; c += 32) {
+          const uint32_t e = row[c];
+          const int dist = (int)(e >> 16), i2 = (int)(e & 0xFFFFu);
+          if (s_mdist[i2] <= dist) continue;  // :907
+          const uint32_t key = (uint32_t)dist << 16 | (uint32_t)c;
+          if (key < best) { second = best; second_i2 = best_i2; best = key; best_i2 = i2; }
+          else if (key < second) { second = key; second_i2 = i2; }
+        }
+        const uint32_t my_best = best, my_second = second;
+        warp_top2(best, second);
+        if (best == 0xFFFFFFFFu) {
+          pend = false;  // nothing passes the filter any more: the query is finished without a match
+        } else {
+          bdist = (int)(best >> 16);
+          bidx = __shfl_sync(0xffffffffu, best_i2, __ffs(__ballot_sync(0xffffffffu, my_best == best)) - 1);
+          if (second != 0xFFFFFFFFu) {
+            const int mine = my_best == second ? best_i2 : (my_second == second ? second_i2 : -1);
+            sidx = __shfl_sync(0xffffffffu, mine, __ffs(__ballot_sync(0xffffffffu, mine >= 0)) - 1);
+          }
+          // bestDist2 stays INT_MAX when there is no second candidate (:896-897)
+          const float second_f = second == 0xFFFFFFFFu ? (float)0x7FFFFFFF : (float)(int)(second >> 16);
+          will = bdist <= TH_LOW && (float)bdist < __fmul_rn(second_f, nnratio);
+        }
       }
-      const uint32_t mine = best;
-      warp_top2(best, second);
-      if (best == 0xFFFFFFFFu) continue;
-      const int bestDist = (int)(best >> 16);
-      const unsigned owner = __ballot_sync(0xffffffffu, mine == best);
-      const int bestIdx2 = __shfl_sync(0xffffffffu, my_i2, __ffs(owner) - 1);
-      // bestDist2 stays INT_MAX when there is no second candidate (:896-897)
-      const float second_f = second == 0xFFFFFFFFu ? (float)0x7FFFFFFF : (float)(int)(second >> 16);
-      if (bestDist <= TH_LOW && (float)bestDist < __fmul_rn(second_f, nnratio)) {
-        if (lane == 0) {
-          const int old = s_m21[bestIdx2];
-          if (old >= 0) { s_m12[old] = -1; nmatches--; }
-          s_m12[i1] = bestIdx2;
-          s_m21[bestIdx2] = i1;
-          s_mdist[bestIdx2] = bestDist;
-          nmatches++;
+      if (lane == 0) { s_xb[rp][warp] = bidx; s_xs[rp][warp] = sidx; s_xw[rp][warp] = will; s_xd[rp][warp] = bdist; }
+      __syncthreads();
+      if (warp == 0) {
+        const int b = s_xb[rp][lane], sx = s_xs[rp][lane], wl = s_xw[rp][lane], bd = s_xd[rp][lane];
+        const bool p = b >= 0;
+        const bool wants = p && wl;
+        const unsigned peers = __match_any_sync(0xffffffffu, wants ? b : -1 - lane);
+        const bool claims = wants && (__ffs(peers) - 1 == lane);
+        if (claims) s_claim[b] = (uint8_t)lane;
+        __syncwarp();
+        bool conflict = false;
+        if (p) conflict = s_claim[b] < lane || (sx >= 0 && s_claim[sx] < lane);
+        const unsigned cm = __ballot_sync(0xffffffffu, conflict);
+        const int first = cm ? __ffs(cm) - 1 : 32;
+        __syncwarp();
+        if (claims) s_claim[b] = 0xFF;
+        const bool done = p && lane < first;
+        const bool commit = done && wl;
+        bool stole = false;
+        if (commit) {
+          const int q1 = s_list[b0 + lane];
+          const int old = s_m21[b];
+          if (old >= 0) { s_m12[old] = -1; stole = true; }  // :926-933
+          s_m12[q1] = b;
+          s_m21[b] = q1;
+          s_mdist[b] = bd;
           if (check_ori) {
-            float rot = __fsub_rn(s_ang1[i1], s_ang2[bestIdx2]);
+            float rot = __fsub_rn(s_ang1[q1], s_ang2[b]);
             if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
             int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
             if (bin == HISTO_LENGTH) bin = 0;
-            s_bin[i1] = bin;
-            s_hist[bin]++;
+            s_bin[q1] = bin;
+            atomicAdd(&s_hist[bin], 1);
           }
         }
-        __syncwarp();
+        nmatches += __popc(__ballot_sync(0xffffffffu, commit)) - __popc(__ballot_sync(0xffffffffu, stole));
+        const unsigned dm = __ballot_sync(0xffffffffu, done), pm = __ballot_sync(0xffffffffu, p);
+        if (lane == 0) { s_xdone[rp] = dm; s_xleft[rp] = pm & ~dm; }
       }
+      __syncthreads();
+      if (s_xdone[rp] >> warp & 1u) pend = false;
+      const unsigned left = s_xleft[rp];
+      rp ^= 1;
+      if (!left) break;
     }
-    if (lane == 0) {
-      s_nmatch = nmatches;
-      if (check_ori) three_maxima_keep(s_hist, s_keep);  // ComputeThreeMaxima (:3948-3989)
-    }
+  }
+  if (tid == 0) {
+    s_nmatch = nmatches;
+    if (check_ori) three_maxima_keep(s_hist, s_keep);  // ComputeThreeMaxima (:3948-3989)
   }
   __syncthreads();
   for (int i1 = tid; i1 < n1; i1 += INIT_NT) {
@@ -1943,7 +1997,7 @@ int orbm_search_for_initialization_device(orbm_matcher* m, int n_pairs, int cap,
   if (!m || n_pairs < 0 || cap < 1 || cap > 65535) return ORBX_E_INVALID;
   if (n_pairs == 0) return ORBX_OK;
   OrbDeviceGuard dev_guard(m->device);
-  const size_t smem = sizeof(int) * 9 * (size_t)cap + sizeof(uint32_t) * INIT_SMEM_CAND;
+  const size_t smem = sizeof(int) * 9 * (size_t)cap + sizeof(uint32_t) * INIT_SMEM_CAND + (((size_t)cap + 15) & ~(size_t)15);
   if (smem > 200 * 1024) { m->err = "cap too large for SearchForInitialization"; return ORBX_E_INVALID; }
   // candidate rows are cap x cap per pair: process pairs in groups that keep the scratch <= ~2 GiB
   const size_t per_pair = (size_t)cap * cap * sizeof(uint32_t);

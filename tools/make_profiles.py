@@ -5,9 +5,9 @@ The GPU-side commands (run from the repo root on the box, see DESIGN.md "Measure
 
     python bench.py > gpurun_out/bench_TAG.json
     ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_TAG.csv \
-        python bench.py --steps 2 --warmup 3 --no-cpu-baseline --bf-size 4096
+        python bench.py --steps 2 --warmup 3 --no-cpu-baseline --bf-size 4096 --no-rig8 --no-configs --warm-seconds 0
     ncu --set full --clock-control none --import-source on --launch-skip 75 -c 25 -f -o gpurun_out/prof_TAG \
-        python bench.py --steps 1 --warmup 3 --no-cpu-baseline --bf-size 4096
+        python bench.py --steps 1 --warmup 3 --no-cpu-baseline --bf-size 4096 --no-rig8 --no-configs --warm-seconds 0
 
 usage: tools/make_profiles.py TAG   (reads gpurun_out/*_TAG.*, writes profiles/TAG_*)"""
 import csv
@@ -50,7 +50,7 @@ for r in rows:
     a[1] += float(r["Metric Value"]) / 1e3
 tot = sum(v[1] for v in agg.values())
 with open(os.path.join(pr, f"{tag}_launches.md"), "w") as f:
-    f.write(f"# {tag} — ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --bf-size 4096`\n\n"
+    f.write(f"# {tag} — ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --bf-size 4096 --no-rig8 --no-configs --warm-seconds 0`\n\n"
             "`ncu --metrics gpu__time_duration.sum --clock-control none` — per-launch times are cold-cache and "
             "serialised: compare SHARES with bench.py's `stages`, not absolutes.  Extractor and "
             "SearchForInitialization kernels of all steps (device-resident leg and streaming leg).  In bench.py the "
