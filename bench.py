@@ -994,7 +994,9 @@ def main():
     dom = max(names, key=lambda n: stages[n]["ms"])
     # DRAM traffic of the dominant kernel from the committed ncu capture (per launch = per handle call)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tfiles = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))
+    tpath = os.path.join(ROOT, "profiles", tfiles[-1]) if tfiles else ""  # the latest round's committed capture
+    tname = "profiles/" + tfiles[-1] if tfiles else "none"
     if os.path.exists(tpath):
         per_frame = json.load(open(tpath))["dram_bytes_per_camera_frame"].get(dom)
         if per_frame:
@@ -1018,7 +1020,7 @@ def main():
             rate = wi[dom] * 2 * F / (stages[dom]["ms"] * 1e-3)
             issue = {"achieved": round(rate / 1e9, 1), "peak": round(issue_peak / 1e9, 1), "unit": "G warp-instr/s",
                      "frac": round(rate / issue_peak, 3),
-                     "source": "instruction count from profiles/r01_traffic.json (ncu smsp__inst_executed.sum), "
+                     "source": f"instruction count from {tname} (ncu smsp__inst_executed.sum), "
                                "148 SM x 4 schedulers x SM clock"}
     # every pixel term for both cameras; the keypoint term with the keypoints actually produced (camera 2 runs nFeatures 500)
     total_alg = sum(sb[n] for n in names if n != "orient_describe") * 2 * F + (749 + 512 + 28 + 32) * (n_kp[0] + n_kp[1])

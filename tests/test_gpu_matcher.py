@@ -38,7 +38,8 @@ def test_distance_pairs_vs_oracle(M, O):
     assert np.array_equal(got, np.unpackbits(a ^ b, axis=1).sum(axis=1))
 
 
-@pytest.mark.parametrize("nq,nt", [(1, 1), (1000, 1000), (777, 3001), (4096, 4096), (3, 70000), (257, 255)])
+@pytest.mark.parametrize("nq,nt", [(1, 1), (1000, 1000), (777, 3001), (4096, 4096), (3, 70000), (257, 255),
+                                   (8192, 8192), (16384, 16384), (32768, 32768)])  # the middle of configs[2]'s sweep
 def test_bruteforce_vs_oracle(M, O, nq, nt):
     A = random_descriptors(max(nq, nt), 7)
     B, _ = perturbed_descriptors(A, 8)
