@@ -912,8 +912,34 @@ def main():
     if world > 1:
         dist.all_reduce(h2d_t, op=dist.ReduceOp.MAX)
     h2d_ms, h2d_ms_best = float(h2d_t[0].item()), float(h2d_t[1].item())
-    clocks = sampler.stop() if rank == 0 else None  # sampled over the device leg and the end-to-end leg
     h2d, d2h = pipe.h2d_bytes_per_step, pipe.d2h_bytes_per_step
+    # the same copy with the step's results travelling the other way at the same time (what a pipelined step really
+    # moves): the two directions share the host's memory system, so this, not the one-way copy, is the floor of a step
+    with numa_local(local_rank):
+        h_back = torch.empty(int(d2h), dtype=torch.uint8).pin_memory()
+    d_back = torch.zeros(int(d2h), dtype=torch.uint8, device=dev)
+    s_back = torch.cuda.Stream(device=dev)
+    dup_all = []
+    for rep in range(6):
+        barrier()
+        c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        c0.record(stream)
+        s_back.wait_event(c0)
+        with torch.cuda.stream(stream):
+            for c in range(2):
+                d_img[c].copy_(h_img[c], non_blocking=True)
+            c1.record(stream)
+        with torch.cuda.stream(s_back):
+            h_back.copy_(d_back, non_blocking=True)
+            c2.record(s_back)
+        stream.synchronize()
+        s_back.synchronize()
+        dup_all.append(max(c0.elapsed_time(c1), c0.elapsed_time(c2)))
+    dup_t = torch.tensor([float(np.median(dup_all[1:]))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dup_t, op=dist.ReduceOp.MAX)
+    duplex_ms = float(dup_t[0].item())
+    clocks = sampler.stop() if rank == 0 else None  # sampled over the device leg and the end-to-end leg
     e2e_depth, e2e_chunks, pipe_launches_total = pipe.depth, pipe.n_chunks, pipe.launch_count
 
     # ---- Hamming matches/s: brute-force leg (BASELINE.json configs[2] upper end) ----------------
@@ -1050,6 +1076,11 @@ def main():
                                 "aggregate_GBps": round(world * h2d / (h2d_ms * 1e-3) / 1e9, 2),
                                 "frames_per_s_at_ceiling": frames_per_step / (h2d_ms * 1e-3)},
                 "frac_of_min_kernel_rate_and_h2d_ceiling": round(e2e_value / min(value, frames_per_step / (h2d_ms * 1e-3)), 4),
+                "duplex_ceiling": {"what": "the same upload with one step's results (d2h_bytes_per_step) downloaded into pinned "
+                                           "memory at the same time on a second stream, all ranks at once (median of 5, max "
+                                           "over ranks): what a pipelined step moves",
+                                   "ms": duplex_ms, "frames_per_s_at_ceiling": frames_per_step / (duplex_ms * 1e-3)},
+                "frac_of_min_kernel_rate_and_duplex_ceiling": round(e2e_value / min(value, frames_per_step / (duplex_ms * 1e-3)), 4),
                 "pinned_numa_bound_cpus": numa_cpus},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,

@@ -58,6 +58,9 @@ typedef struct orbx_extractor orbx_extractor;
 
 /* ---- extractor: replaces class ORBextractor (include/ORBextractor.h:45-112) ---------------- */
 
+/* Environment read once, when the handle is created (tuning / A-B runs; results are identical either way):
+ *   ORB_B200_FAST=bands   run the FAST stage with the streaming band kernel instead of the per-cell kernel
+ *   ORB_OT_SMEM_KEYS=n    octree keys kept in shared memory per CTA */
 int orbx_create(const orbx_config* cfg, orbx_extractor** out);
 void orbx_destroy(orbx_extractor* h);
 /* Last error text of this handle (or of the failed create when h == NULL). */
