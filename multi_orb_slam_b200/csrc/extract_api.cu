@@ -267,7 +267,10 @@ bool build_geometry(orbx_extractor* h, std::vector<OrbCell>& cells, std::vector<
 
 // Work list of the FAST kernel: every row of cells of every level, cut into chunks of whole cells that fit the
 // ORB_BAND_MAX_PX tested pixels a warp covers per image row (chunks of a row are balanced: 20 cells -> 7 + 7 + 6).
-void build_bands(const OrbGeom& g, const std::vector<OrbCell>& cells, std::vector<OrbBand>& bands) {
+void build_bands(const OrbGeom& g, const std::vector<OrbCell>& cells, std::vector<OrbBand>& bands,
+                 std::vector<unsigned>& band_bm, std::vector<uint2>& cell_bm, unsigned* bm_rows_frame) {
+  unsigned bm_rows = 0;
+  cell_bm.assign(cells.size(), make_uint2(0u, 0u));
   for (int l = 0; l < g.nlevels; ++l) {
     const OrbLevelGeom& L = g.lv[l];
     int p = L.cell_base;
@@ -299,11 +302,15 @@ void build_bands(const OrbGeom& g, const std::vector<OrbCell>& cells, std::vecto
         b.w_cell = (short)L.w_cell;
         b.src_off = L.pyr_off + (unsigned)b.y_first * (unsigned)L.pitch + (unsigned)b.xb;
         bands.push_back(b);
+        band_bm.push_back(bm_rows);
+        for (int ci = c0; ci < c0 + nc; ++ci) cell_bm[ci] = make_uint2(bm_rows, (unsigned)(cells[ci].ini_x + 3 - b.xb));
+        bm_rows += (unsigned)std::max(0, (int)b.nt);
         c0 += nc;
       }
       p = q;
     }
   }
+  *bm_rows_frame = bm_rows;
 }
 
 template <typename T> bool dev_alloc(orbx_extractor* h, T** p, size_t count, const char* what) {
@@ -393,11 +400,14 @@ int orbx_create(const orbx_config* cfg, orbx_extractor** out) {
   std::vector<OrbYTap> yt;
   if (!build_geometry(h, cells, xt, yt)) return fail(ORBX_E_INVALID);
   std::vector<OrbBand> bands;
-  build_bands(h->gh.g, cells, bands);
+  std::vector<unsigned> band_bm;
+  std::vector<uint2> cell_bm;
+  build_bands(h->gh.g, cells, bands, band_bm, cell_bm, &h->gh.bm_rows_frame);
   h->gh.n_bands = (int)bands.size();
   {
     const char* e = getenv("ORB_B200_FAST");
-    h->gh.fast_bands = e && std::string(e) == "bands";
+    const std::string mode = e ? e : "";
+    h->gh.fast_mode = mode == "bands" ? 1 : (mode == "split" ? 2 : 0);
   }
   int ndev = 0;
   if (!h->check(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount") || ndev == 0) {
@@ -419,6 +429,9 @@ int orbx_create(const orbx_config* cfg, orbx_extractor** out) {
   bool ok = dev_alloc(h, &h->gh.d_geom, 1, "cudaMalloc(geom)") &&
             dev_alloc(h, &h->gh.d_cells, cells.size(), "cudaMalloc(cells)") &&
             dev_alloc(h, &h->gh.d_bands, bands.size(), "cudaMalloc(bands)") &&
+            dev_alloc(h, &h->gh.d_band_bm, band_bm.size(), "cudaMalloc(band bitmap rows)") &&
+            dev_alloc(h, &h->gh.d_cell_bm, cell_bm.size(), "cudaMalloc(cell bitmap rows)") &&
+            dev_alloc(h, &h->gh.d_bitmap, h->gh.fast_mode == 2 ? B * h->gh.bm_rows_frame * 32 : 1, "cudaMalloc(FAST bitmap)") &&
             dev_alloc(h, &h->gh.d_xtab, xt.size(), "cudaMalloc(xtab)") &&
             dev_alloc(h, &h->gh.d_ytab, yt.size(), "cudaMalloc(ytab)") &&
             dev_alloc(h, &h->d_pyr, B * g.pyr_frame_bytes, "cudaMalloc(pyramid)") &&
@@ -435,6 +448,8 @@ int orbx_create(const orbx_config* cfg, orbx_extractor** out) {
   ok = h->check(cudaMemcpy(h->gh.d_geom, &g, sizeof(g), cudaMemcpyHostToDevice), "copy geom") &&
        h->check(cudaMemcpy(h->gh.d_cells, cells.data(), cells.size() * sizeof(OrbCell), cudaMemcpyHostToDevice), "copy cells") &&
        h->check(cudaMemcpy(h->gh.d_bands, bands.data(), bands.size() * sizeof(OrbBand), cudaMemcpyHostToDevice), "copy bands") &&
+       h->check(cudaMemcpy(h->gh.d_band_bm, band_bm.data(), band_bm.size() * sizeof(unsigned), cudaMemcpyHostToDevice), "copy band rows") &&
+       h->check(cudaMemcpy(h->gh.d_cell_bm, cell_bm.data(), cell_bm.size() * sizeof(uint2), cudaMemcpyHostToDevice), "copy cell rows") &&
        h->check(cudaMemcpy(h->gh.d_xtab, xt.data(), xt.size() * sizeof(OrbXTap), cudaMemcpyHostToDevice), "copy xtab") &&
        h->check(cudaMemcpy(h->gh.d_ytab, yt.data(), yt.size() * sizeof(OrbYTap), cudaMemcpyHostToDevice), "copy ytab") &&
        h->check(orbk::prepare_octree(h->gh), "octree shared-memory opt-in") &&
@@ -450,7 +465,7 @@ void orbx_destroy(orbx_extractor* h) {
   orbk::dump_octree_marks();
 #endif
   if (h->stream) cudaStreamSynchronize(h->stream);
-  cudaFree(h->gh.d_geom); cudaFree(h->gh.d_cells); cudaFree(h->gh.d_bands); cudaFree(h->gh.d_xtab); cudaFree(h->gh.d_ytab);
+  cudaFree(h->gh.d_geom); cudaFree(h->gh.d_cells); cudaFree(h->gh.d_bands); cudaFree(h->gh.d_band_bm); cudaFree(h->gh.d_cell_bm); cudaFree(h->gh.d_bitmap); cudaFree(h->gh.d_xtab); cudaFree(h->gh.d_ytab);
   cudaFree(h->d_pyr); cudaFree(h->d_blur); cudaFree(h->d_cand); cudaFree(h->d_cell_count);
   cudaFree(h->d_keys); cudaFree(h->d_knode); cudaFree(h->d_sel); cudaFree(h->d_sel_count);
   cudaFree(h->d_img); cudaFree(h->d_l0); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts);

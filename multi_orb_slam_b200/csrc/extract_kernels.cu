@@ -273,12 +273,50 @@ __device__ __forceinline__ int fast_arc_measure(const uint8_t* p) {
 
 // One threshold pass over the tested area (tw x thh pixels starting at sub-image (3,3)).
 // Returns the number of NMS survivors, left (unordered) in sm.kept.
+// `bm_rows` != nullptr: the survivors of the rejection test come from the pass-bit bitmap k_fast_prefilter wrote (one
+// 32-byte row per tested row of the cell's band, bit = column - band origin; `bm_bit0` = bit of the cell's first tested
+// column) instead of phase A: a lane takes a row, counts its bits, and expands them behind the rows above it.
 template <int PITCH>
-__device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int thh, int ch) {
+__device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int thh, int ch,
+                                         const uint32_t* __restrict__ bm_rows = nullptr, int bm_bit0 = 0) {
   static_assert(FAST_NT == 32, "one warp per cell");
   constexpr int PW = PITCH / 4;
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
+  int nq = 0;
+  if (bm_rows) {
+    const int k = bm_bit0 >> 5, sh = bm_bit0 & 31;
+    const uint32_t keep0 = tw >= 32 ? 0xFFFFFFFFu : (1u << tw) - 1u;
+    const uint32_t keep1 = tw > 32 ? (tw >= 64 ? 0xFFFFFFFFu : (1u << (tw - 32)) - 1u) : 0u;
+    for (int r0 = 0; r0 < thh; r0 += 32) {
+      const int r = r0 + lane;
+      uint32_t m0 = 0, m1 = 0;
+      if (r < thh) {
+        const uint32_t* row = bm_rows + 8 * r;
+        const uint32_t w0 = __ldg(row + k), w1 = k + 1 < 8 ? __ldg(row + k + 1) : 0u, w2 = k + 2 < 8 ? __ldg(row + k + 2) : 0u;
+        m0 = __funnelshift_r(w0, w1, sh) & keep0;
+        m1 = __funnelshift_r(w1, w2, sh) & keep1;
+      }
+      const int cnt = __popc(m0) + __popc(m1);
+      int incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      uint16_t* q = sm.queue + nq + incl - cnt;
+      const int off0 = (r + 3) * PITCH + FAST_COL0 + 3;
+      while (m0) {
+        *q++ = (uint16_t)(off0 + __ffs(m0) - 1);
+        m0 &= m0 - 1;
+      }
+      while (m1) {
+        *q++ = (uint16_t)(off0 + 32 + __ffs(m1) - 1);
+        m1 &= m1 - 1;
+      }
+      nq += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  } else {
   // phase A: packed rejection test, four pixels (one word) per lane.  A 9-arc contains one pixel
   // of every opposite pair (k, k+8), so a corner has |p - c| > th for at least one pixel of each
   // of the pairs 0/8, 4/12, 2/10, 6/14.  On the halved bytes (a' = a >> 1) |a - c| > th implies
@@ -368,7 +406,6 @@ __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int
 #endif
   __syncwarp();
   // expand the word entries into one queue entry per surviving pixel
-  int nq = 0;
   for (int e0 = 0; e0 < ecount; e0 += 32) {
     const int e = e0 + lane < ecount ? eq[e0 + lane] : 0;
     const int nib = e & 15, cnt = __popc(nib);
@@ -385,6 +422,7 @@ __device__ __forceinline__ int fast_pass(const FastSmem& sm, int th, int tw, int
       if (nib >> k & 1) sm.queue[pos++] = (uint16_t)(boff + k);
     nq += __shfl_sync(0xffffffffu, incl, 31);
   }
+  }  // phase A in this kernel
   __syncwarp();
   // the entries are consumed: their region becomes the (zeroed) measure map
   for (int i = lane; i < ch * (PITCH / 16); i += 32) reinterpret_cast<uint4*>(sm.m)[i] = make_uint4(0, 0, 0, 0);
@@ -437,7 +475,9 @@ __global__ void __launch_bounds__(FAST_NT * FAST_WPC) k_fast_cells(const OrbCell
                                                     const uint8_t* __restrict__ pyr,
                                                     uint32_t* __restrict__ cand, int* __restrict__ cell_count,
                                                     size_t pyr_frame_bytes, size_t cand_frame_u32, int n_cells,
-                                                    int ini_th, int min_th, int rows_max, int t_max) {
+                                                    int ini_th, int min_th, int rows_max, int t_max,
+                                                    const uint8_t* __restrict__ bitmap = nullptr,
+                                                    const uint2* __restrict__ cell_bm = nullptr, size_t bm_frame_bytes = 0) {
   extern __shared__ __align__(16) unsigned char fsm_all[];
   FastSmem sm;
   constexpr int HVP = FAST_HVP && !FAST_PAIR ? FAST_HVP : PITCH;
@@ -482,7 +522,7 @@ __global__ void __launch_bounds__(FAST_NT * FAST_WPC) k_fast_cells(const OrbCell
       for (int y = y_first; y < ch; y += FAST_NT / 16) {
         const uint32_t v = __byte_perm(__ldg(gp), __ldg(gp + d1), sel);
         sp[0] = v;
-        hp[0] = (v >> 1) & 0x7f7f7f7fu;
+        if (!bitmap) hp[0] = (v >> 1) & 0x7f7f7f7fu;  // the halved copy feeds phase A only
         gp += 2 * pw;
         sp += 2 * (PITCH / 4);
         hp += 2 * (HVP / 4);
@@ -493,7 +533,13 @@ __global__ void __launch_bounds__(FAST_NT * FAST_WPC) k_fast_cells(const OrbCell
   int total = 0, th = ini_th;
   __syncwarp();
   if (tw > 0 && thh > 0) {
-    total = fast_pass<PITCH>(sm, th, tw, thh, ch);
+    if (bitmap) {
+      const uint2 bm = __ldg(cell_bm + cell_idx);
+      total = fast_pass<PITCH>(sm, th, tw, thh, ch,
+                               reinterpret_cast<const uint32_t*>(bitmap + (size_t)frame * bm_frame_bytes) + (size_t)bm.x * 8, (int)bm.y);
+    } else {
+      total = fast_pass<PITCH>(sm, th, tw, thh, ch);
+    }
     if (total == 0 && min_th < th) {
       // Every corner of the first pass is a corner at the lower threshold too, so the second pass
       // re-measures it (same value) and its NMS sees the complete map.  The queue has overwritten
@@ -517,6 +563,117 @@ __global__ void __launch_bounds__(FAST_NT * FAST_WPC) k_fast_cells(const OrbCell
     out[i] = (uint32_t)(x + cell.off_x) | (uint32_t)(y + cell.off_y) << 12 | ((uint32_t)sm.m[off] - 1u) << 24;
   }
   if (tid == 0) cell_count[(size_t)frame * n_cells + cell_idx] = total;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3a (split form) the rejection test of the FAST stage on its own, one WARP per band (OrbBand), no shared memory: the
+// phase A of k_fast_bands - a lane owns 8 adjacent pixels of every row and keeps the last seven rows (halved bytes, own
+// words + neighbour words by shuffle) in registers - writing one byte of pass bits per lane and tested row into a bitmap
+// (32 bytes per band row, coalesced).  k_fast_cells, launched behind it with the bitmap, then skips its own phase A (11
+// shared loads per four pixels, the halved tile copy, the entry expansion) and starts at the arc measure.  Threshold
+// iniThFAST only: a cell that keeps nothing reruns at minThFAST inside k_fast_cells with its own phase A (:813-817).
+__global__ void __launch_bounds__(128) k_fast_prefilter(const OrbBand* __restrict__ bands, const unsigned* __restrict__ band_bm,
+                                                        int n_bands, OrbLevel0 l0, const uint8_t* __restrict__ pyr,
+                                                        uint8_t* __restrict__ bitmap, size_t pyr_frame_bytes,
+                                                        size_t bm_frame_bytes, int ini_th) {
+  const int lane = threadIdx.x & 31;
+  const int bi = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (bi >= n_bands) return;  // whole warp
+  const unsigned FULL = 0xffffffffu;
+  OrbBand band;
+  {
+    const uint4* br = reinterpret_cast<const uint4*>(bands + bi);
+    reinterpret_cast<uint4*>(&band)[0] = __ldg(br);
+    reinterpret_cast<uint4*>(&band)[1] = __ldg(br + 1);
+  }
+  const int nt = band.nt;
+  if (nt <= 0) return;
+  const int frame = blockIdx.y;
+  const int xb = band.xb, x0 = band.x0, x1 = band.x1, y_first = band.y_first;
+  const int pitch = band.level == 0 ? l0.pitch : band.pitch;
+  const uint8_t* const src = band.level == 0
+                                 ? l0.base + (size_t)frame * l0.frame_stride + (size_t)y_first * l0.pitch + xb
+                                 : pyr + (size_t)frame * pyr_frame_bytes + band.src_off;
+  const int pitch_w = pitch >> 2;
+  const int R_load = nt + 6;
+  const int nbytes = x1 + 3 - xb;
+  const bool ldA = 8 * lane < nbytes, ldB = 8 * lane + 4 < nbytes;
+  const uint32_t K = 0x01010101u * (uint32_t)(128 - min(ini_th >> 1, 127));
+  uint32_t maskA = 0, maskB = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int x = xb + 8 * lane + k;
+    if (x >= x0 && x < x1) {
+      if (k < 4) maskA |= 0x80u << (8 * k);
+      else maskB |= 0x80u << (8 * (k - 4));
+    }
+  }
+  uint8_t* out = bitmap + (size_t)frame * bm_frame_bytes + (size_t)__ldg(band_bm + bi) * 32 + lane;
+
+  const uint32_t* gp = reinterpret_cast<const uint32_t*>(src) + 2 * lane;
+  int s_issue = 0;
+  uint32_t pA0 = 0, pB0 = 0, pA1 = 0, pB1 = 0;
+  auto issue = [&](uint32_t& a, uint32_t& b) {
+    a = 0;
+    b = 0;
+    if (s_issue < R_load) {
+      if (ldA) a = __ldg(gp);
+      if (ldB) b = __ldg(gp + 1);
+    }
+    gp += pitch_w;
+    ++s_issue;
+  };
+  issue(pA0, pB0);
+  issue(pA1, pB1);
+  uint32_t hA[7], hB[7], hL[7], hR[7];
+  auto take_row = [&](int k) {
+    const uint32_t a = pA0, b = pB0;
+    pA0 = pA1;
+    pB0 = pB1;
+    issue(pA1, pB1);
+    hA[k] = (a >> 1) & 0x7f7f7f7fu;
+    hB[k] = (b >> 1) & 0x7f7f7f7fu;
+    hL[k] = __shfl_up_sync(FULL, hB[k], 1);
+    hR[k] = __shfl_down_sync(FULL, hA[k], 1);
+  };
+#pragma unroll
+  for (int k = 0; k < 6; ++k) take_row(k);
+  for (int s0 = 6; s0 < R_load; s0 += 7) {
+#pragma unroll
+    for (int u = 0; u < 7; ++u) {
+      if (s0 + u < R_load) {
+        const int k = (6 + u) % 7;
+        take_row(k);
+        const int c = (k + 4) % 7, p2 = (k + 6) % 7, m2 = (k + 2) % 7, m3 = (k + 1) % 7;
+        const uint32_t cA = hA[c], cB = hB[c];
+        const uint32_t c_ab3 = __byte_perm(cA, cB, 0x6543), c_ab1 = __byte_perm(cA, cB, 0x4321);
+        const uint32_t p_ab = __byte_perm(hA[p2], hB[p2], 0x5432), m_ab = __byte_perm(hA[m2], hB[m2], 0x5432);
+        uint32_t passA, passB;
+        {
+          const uint32_t f0 = __vabsdiffu4(hA[k], cA) + K, f8 = __vabsdiffu4(hA[m3], cA) + K;
+          const uint32_t f4 = __vabsdiffu4(c_ab3, cA) + K;
+          const uint32_t f12 = __vabsdiffu4(__byte_perm(hL[c], cA, 0x4321), cA) + K;
+          const uint32_t f2 = __vabsdiffu4(p_ab, cA) + K;
+          const uint32_t f14 = __vabsdiffu4(__byte_perm(hL[p2], hA[p2], 0x5432), cA) + K;
+          const uint32_t f6 = __vabsdiffu4(m_ab, cA) + K;
+          const uint32_t f10 = __vabsdiffu4(__byte_perm(hL[m2], hA[m2], 0x5432), cA) + K;
+          passA = (f0 | f8) & (f4 | f12) & (f2 | f10) & (f6 | f14) & maskA;
+        }
+        {
+          const uint32_t f0 = __vabsdiffu4(hB[k], cB) + K, f8 = __vabsdiffu4(hB[m3], cB) + K;
+          const uint32_t f4 = __vabsdiffu4(__byte_perm(cB, hR[c], 0x6543), cB) + K;
+          const uint32_t f12 = __vabsdiffu4(c_ab1, cB) + K;
+          const uint32_t f2 = __vabsdiffu4(__byte_perm(hB[p2], hR[p2], 0x5432), cB) + K;
+          const uint32_t f14 = __vabsdiffu4(p_ab, cB) + K;
+          const uint32_t f6 = __vabsdiffu4(__byte_perm(hB[m2], hR[m2], 0x5432), cB) + K;
+          const uint32_t f10 = __vabsdiffu4(m_ab, cB) + K;
+          passB = (f0 | f8) & (f4 | f12) & (f2 | f10) & (f6 | f14) & maskB;
+        }
+        *out = (uint8_t)((((passA >> 7) * 0x10204080u) >> 28) | ((((passB >> 7) * 0x10204080u) >> 28) << 4));
+        out += 32;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1201,11 +1358,19 @@ void launch_pyramid(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, uint8_t* 
 
 void launch_fast(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, const uint8_t* d_pyr, uint32_t* d_cand,
                  int* d_cell_count, cudaStream_t st, long long* launches) {
-  if (gh.fast_bands) {
+  if (gh.fast_mode == 1) {
     k_fast_bands<<<dim3(gh.n_bands, n_frames), 32, 0, st>>>(gh.d_bands, l0, d_pyr, d_cand, d_cell_count, gh.g.pyr_frame_bytes,
                                                             gh.g.cand_frame_u32, gh.g.n_cells, gh.g.ini_th, gh.g.min_th);
     ++*launches;
     return;
+  }
+  const bool split = gh.fast_mode == 2;
+  const size_t bm_frame_bytes = (size_t)gh.bm_rows_frame * 32;
+  if (split) {
+    k_fast_prefilter<<<dim3((gh.n_bands + 3) / 4, n_frames), 128, 0, st>>>(gh.d_bands, gh.d_band_bm, gh.n_bands, l0, d_pyr,
+                                                                          gh.d_bitmap, gh.g.pyr_frame_bytes, bm_frame_bytes,
+                                                                          gh.g.ini_th);
+    ++*launches;
   }
   // shared memory sized for this geometry's largest cell (rows x pitch image + measure map,
   // survivor queue, kept list, overlaid): ~6 KB at 640x480, so 32 cell CTAs stay resident per SM
@@ -1223,10 +1388,12 @@ void launch_fast(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, const uint8_
   const dim3 grid((gh.g.n_cells + FAST_WPC - 1) / FAST_WPC, n_frames);
   if (pitch == 48)
     k_fast_cells<48><<<grid, FAST_NT * FAST_WPC, smem, st>>>(gh.d_cells, l0, d_pyr, d_cand, d_cell_count, gh.g.pyr_frame_bytes,
-                                                  gh.g.cand_frame_u32, gh.g.n_cells, gh.g.ini_th, gh.g.min_th, rows_max, t_max);
+                                                  gh.g.cand_frame_u32, gh.g.n_cells, gh.g.ini_th, gh.g.min_th, rows_max, t_max,
+                                                  split ? gh.d_bitmap : nullptr, gh.d_cell_bm, bm_frame_bytes);
   else
     k_fast_cells<80><<<grid, FAST_NT * FAST_WPC, smem, st>>>(gh.d_cells, l0, d_pyr, d_cand, d_cell_count, gh.g.pyr_frame_bytes,
-                                                  gh.g.cand_frame_u32, gh.g.n_cells, gh.g.ini_th, gh.g.min_th, rows_max, t_max);
+                                                  gh.g.cand_frame_u32, gh.g.n_cells, gh.g.ini_th, gh.g.min_th, rows_max, t_max,
+                                                  split ? gh.d_bitmap : nullptr, gh.d_cell_bm, bm_frame_bytes);
   ++*launches;
 }
 

@@ -26,8 +26,13 @@ struct OrbGeomHost {
   OrbYTap* d_ytab;
   int ot_smem_keys;        // octree: keys kept in shared memory (prepare_octree)
   size_t ot_smem_bytes;    // octree: dynamic shared memory per CTA
-  int fast_bands;          // FAST kernel of this handle: 0 = one warp per cell (k_fast_cells), 1 = one warp per band
-                           // (k_fast_bands); resolved once in orbx_create (ORB_B200_FAST=cells|bands, default cells)
+  int fast_mode;           // FAST stage of this handle, resolved once in orbx_create (ORB_B200_FAST=cells|bands|split):
+                           // 0 = one warp per cell (k_fast_cells), 1 = one warp per band (k_fast_bands), 2 = split:
+                           // k_fast_prefilter (band rejection test on registers -> pass-bit bitmap) + k_fast_cells fed by it
+  unsigned* d_band_bm;     // [n_bands] first bitmap row of every band (split mode)
+  uint2* d_cell_bm;        // [g.n_cells] (first bitmap row of the cell's band, bit of the cell's first tested column)
+  uint8_t* d_bitmap;       // [max_batch][bm_rows_frame][32] pass bits of the rejection test, one row per tested band row
+  unsigned bm_rows_frame;
 };
 
 void launch_pyramid(const OrbGeomHost& gh, OrbLevel0 l0, int n_frames, uint8_t* d_pyr, cudaStream_t st,

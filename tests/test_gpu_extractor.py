@@ -157,14 +157,16 @@ def test_two_handles_with_different_nfeatures(O):
         _assert_same_features(k, d, k_ref, d_ref, f"nf={nf}")
 
 
+@pytest.mark.parametrize("mode", ["bands", "split"])
 @pytest.mark.parametrize("case", ["textured", "kitti", "hd", "small", "low_texture", "noise", "constant"])
-def test_band_fast_kernel_matches_the_oracle(O, monkeypatch, case):
-    """The streaming band form of the FAST stage (k_fast_bands, chosen per handle with ORB_B200_FAST=bands; the default
-    is the per-cell kernel): candidate lists per level incl. their order, and the final features, equal to the oracle
+def test_band_fast_kernel_matches_the_oracle(O, monkeypatch, case, mode):
+    """The other two forms of the FAST stage, chosen per handle with ORB_B200_FAST: `bands` (k_fast_bands, the whole stage
+    streamed per band) and `split` (k_fast_prefilter writes the rejection test's pass bits, k_fast_cells starts at the arc
+    measure).  Candidate lists per level incl. their order, and the final features, equal to the oracle
     — on textured frames of several geometries (whole and clipped cells, 3..8 cells per band), on a low-texture frame
     (most cells rerun at minThFAST), on uniform noise (dense candidates: the bounded buffers fill) and on a constant
     frame (cells that keep nothing in either pass)."""
-    monkeypatch.setenv("ORB_B200_FAST", "bands")
+    monkeypatch.setenv("ORB_B200_FAST", mode)
     size, nf = {"kitti": ((1241, 376), 2000), "hd": ((1280, 720), 1000), "small": ((320, 240), 300)}.get(case, ((640, 480), 1000))
     w, h = size
     if case == "low_texture":
