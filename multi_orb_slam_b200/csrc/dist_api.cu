@@ -45,13 +45,15 @@ bool load_nccl() {
   if (g_nccl.so) return true;
   const char* names[] = {getenv("ORB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
   void* so = nullptr;
+  std::string why = "not found";
   for (const char* n : names) {
     if (!n || !*n) continue;
     so = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
     if (so) break;
+    if (const char* e = dlerror()) why = e;  // dlerror() clears itself: read it once
   }
   if (!so) {
-    g_err = std::string("cannot load NCCL (set ORB_NCCL_LIB): ") + (dlerror() ? dlerror() : "not found");
+    g_err = "cannot load NCCL (set ORB_NCCL_LIB): " + why;
     return false;
   }
   NcclApi a;
