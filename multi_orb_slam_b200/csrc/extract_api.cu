@@ -51,8 +51,19 @@ struct orbx_extractor {
   uint8_t* d_img = nullptr;
   orbx_keypoint* d_kps = nullptr;
   uint8_t* d_desc = nullptr;
-  int* d_counts = nullptr;
   int stage_cap = 0;
+  // Small host calls (the per-image call of the drop-in: one frame at a time) are latency, not throughput: the 11 launches
+  // of a batch are replayed from a CUDA graph (one per batch size, captured on first use), and when the whole staging
+  // block is small its three result arrays come back in ONE copy through pinned memory.
+  struct BatchGraph { int nb, cap; cudaGraphExec_t exec; long long launches; };
+  std::vector<BatchGraph> graphs;
+  bool fork_blur = false;       // set while a small batch is captured: the blur (it needs the pyramid only) runs on a side
+  cudaStream_t side = nullptr;  // branch of the graph next to FAST + octree - at one frame every kernel is a latency chain
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  uint8_t* d_stage = nullptr;   // [kps | desc | counts] in one allocation (d_kps, d_desc, d_stage_counts point into it)
+  int* d_stage_counts = nullptr;
+  uint8_t* h_stage = nullptr;   // pinned mirror of d_stage when it is small
+  size_t stage_bytes = 0;
   int last_batch = 0;  // frames resident in the workspace (for taps)
   orbk::OrbLevel0 last_l0 = {nullptr, 0, 0};  // level-0 view of the last batch
   uint8_t* d_l0 = nullptr;  // aligned copy of the frames, only when the caller's buffer is not 4-byte aligned
@@ -317,15 +328,33 @@ template <typename T> bool dev_alloc(orbx_extractor* h, T** p, size_t count, con
   return h->check(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)), what);
 }
 
+void drop_graphs(orbx_extractor* h) {
+  for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+}
+
+constexpr int kGraphMaxFrames = 8;             // batches up to this size replay a captured graph
+constexpr size_t kSmallStageBytes = 512 << 10;  // staging blocks up to this size come back in one pinned copy
+
 bool ensure_staging(orbx_extractor* h, int cap) {
-  if (h->d_kps && cap <= h->stage_cap) return true;
-  cudaFree(h->d_kps);
-  cudaFree(h->d_desc);
+  if (h->d_stage && cap <= h->stage_cap) return true;
+  drop_graphs(h);  // they hold the old staging pointers
+  cudaFree(h->d_stage);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  h->d_stage = nullptr;
+  h->h_stage = nullptr;
   h->d_kps = nullptr;
   h->d_desc = nullptr;
   const size_t n = (size_t)h->cfg.max_batch * cap;
-  if (!dev_alloc(h, &h->d_kps, n, "cudaMalloc(kps staging)")) return false;
-  if (!dev_alloc(h, &h->d_desc, n * 32, "cudaMalloc(desc staging)")) return false;
+  const size_t off_desc = align_up(n * sizeof(orbx_keypoint), 256), off_counts = off_desc + align_up(n * 32, 256);
+  h->stage_bytes = off_counts + align_up(sizeof(int32_t) * (size_t)h->cfg.max_batch, 256);
+  if (!dev_alloc(h, &h->d_stage, h->stage_bytes, "cudaMalloc(result staging)")) return false;
+  h->d_kps = reinterpret_cast<orbx_keypoint*>(h->d_stage);
+  h->d_desc = h->d_stage + off_desc;
+  h->d_stage_counts = reinterpret_cast<int*>(h->d_stage + off_counts);
+  if (h->stage_bytes <= kSmallStageBytes &&
+      !h->check(cudaHostAlloc((void**)&h->h_stage, h->stage_bytes, cudaHostAllocDefault), "cudaHostAlloc(result staging)"))
+    return false;
   h->stage_cap = cap;
   return true;
 }
@@ -354,12 +383,20 @@ int run_batch(orbx_extractor* h, const uint8_t* d_images, int n_frames, size_t f
   }
   orbk::launch_pyramid(h->gh, l0, n_frames, h->d_pyr, st, &h->launches);
   if (prof) cudaEventRecord(ev[1], st);
+  const bool fork = h->fork_blur && !prof && h->side;
+  if (fork) {
+    cudaEventRecord(h->ev_fork, st);
+    cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+    orbk::launch_blur(h->gh, l0, n_frames, h->d_pyr, h->d_blur, h->side, &h->launches);
+    cudaEventRecord(h->ev_join, h->side);
+  }
   orbk::launch_fast(h->gh, l0, n_frames, h->d_pyr, h->d_cand, h->d_cell_count, st, &h->launches);
   if (prof) cudaEventRecord(ev[2], st);
   orbk::launch_octree(h->gh, n_frames, h->d_cand, h->d_cell_count, h->d_keys, h->d_knode, h->d_sel, h->d_sel_count, st,
                       &h->launches);
   if (prof) cudaEventRecord(ev[3], st);
-  orbk::launch_blur(h->gh, l0, n_frames, h->d_pyr, h->d_blur, st, &h->launches);
+  if (fork) cudaStreamWaitEvent(st, h->ev_join, 0);
+  else orbk::launch_blur(h->gh, l0, n_frames, h->d_pyr, h->d_blur, st, &h->launches);
   if (prof) cudaEventRecord(ev[4], st);
   orbk::launch_orient_describe(h->gh, l0, n_frames, h->d_pyr, h->d_blur, h->d_sel, h->d_sel_count, d_kps, d_desc, d_counts,
                                cap, st, &h->launches);
@@ -418,7 +455,11 @@ int orbx_create(const orbx_config* cfg, orbx_extractor** out) {
   if (!h->check(cudaGetDevice(&h->device), "cudaGetDevice")) return fail(ORBX_E_CUDA);
   if (cfg->device >= 0) h->device = cfg->device;
   OrbDeviceGuard dev_guard(h->device);  // the caller's current device is restored on return
-  if (!h->check(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail(ORBX_E_CUDA);
+  if (!h->check(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
+      !h->check(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking), "cudaStreamCreate") ||
+      !h->check(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming), "cudaEventCreate") ||
+      !h->check(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming), "cudaEventCreate"))
+    return fail(ORBX_E_CUDA);
   h->stream = h->own_stream;
   for (auto& set : h->ev)
     for (auto& e : set)
@@ -442,8 +483,7 @@ int orbx_create(const orbx_config* cfg, orbx_extractor** out) {
             dev_alloc(h, &h->d_knode, B * g.key_frame_u32, "cudaMalloc(key nodes)") &&
             dev_alloc(h, &h->d_sel, B * g.kp_cap_frame, "cudaMalloc(selection)") &&
             dev_alloc(h, &h->d_sel_count, B * g.nlevels, "cudaMalloc(selection counts)") &&
-            dev_alloc(h, &h->d_img, B * (size_t)h->img_pitch * cfg->height, "cudaMalloc(image staging)") &&
-            dev_alloc(h, &h->d_counts, B, "cudaMalloc(counts)");
+            dev_alloc(h, &h->d_img, B * (size_t)h->img_pitch * cfg->height, "cudaMalloc(image staging)");
   if (!ok) return fail(ORBX_E_CUDA);
   ok = h->check(cudaMemcpy(h->gh.d_geom, &g, sizeof(g), cudaMemcpyHostToDevice), "copy geom") &&
        h->check(cudaMemcpy(h->gh.d_cells, cells.data(), cells.size() * sizeof(OrbCell), cudaMemcpyHostToDevice), "copy cells") &&
@@ -465,14 +505,20 @@ void orbx_destroy(orbx_extractor* h) {
   orbk::dump_octree_marks();
 #endif
   if (h->stream) cudaStreamSynchronize(h->stream);
+  drop_graphs(h);
+  cudaFree(h->d_stage);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
   cudaFree(h->gh.d_geom); cudaFree(h->gh.d_cells); cudaFree(h->gh.d_bands); cudaFree(h->gh.d_band_bm); cudaFree(h->gh.d_cell_bm); cudaFree(h->gh.d_bitmap); cudaFree(h->gh.d_xtab); cudaFree(h->gh.d_ytab);
   cudaFree(h->d_pyr); cudaFree(h->d_blur); cudaFree(h->d_cand); cudaFree(h->d_cell_count);
   cudaFree(h->d_keys); cudaFree(h->d_knode); cudaFree(h->d_sel); cudaFree(h->d_sel_count);
-  cudaFree(h->d_img); cudaFree(h->d_l0); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts);
+  cudaFree(h->d_img); cudaFree(h->d_l0);
   for (auto& set : h->ev)
     for (auto& e : set)
       if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
 }
 
@@ -541,12 +587,53 @@ int orbx_extract_batch_host(orbx_extractor* h, const uint8_t* images, int n_fram
                                         cudaMemcpyHostToDevice, h->stream), "H2D image"))
           return ORBX_E_CUDA;
     }
-    const int rc = run_batch(h, h->d_img, nb, (size_t)P * H, P, h->d_kps, h->d_desc, h->d_counts, cap);
+    int rc;
+    if (nb <= kGraphMaxFrames && !h->profiling) {
+      orbx_extractor::BatchGraph* bg = nullptr;
+      for (auto& g : h->graphs)
+        if (g.nb == nb && g.cap == cap) bg = &g;
+      if (!bg) {
+        const long long before = h->launches;
+        if (!h->check(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed), "graph capture")) return ORBX_E_CUDA;
+        h->fork_blur = true;
+        rc = run_batch(h, h->d_img, nb, (size_t)P * H, P, h->d_kps, h->d_desc, h->d_stage_counts, cap);
+        h->fork_blur = false;
+        cudaGraph_t graph = nullptr;
+        const bool ended = h->check(cudaStreamEndCapture(h->stream, &graph), "graph capture end");
+        if (rc != ORBX_OK || !ended) {
+          if (graph) cudaGraphDestroy(graph);
+          return rc != ORBX_OK ? rc : ORBX_E_CUDA;
+        }
+        orbx_extractor::BatchGraph g = {nb, cap, nullptr, h->launches - before};
+        const bool inst = h->check(cudaGraphInstantiate(&g.exec, graph, 0), "graph instantiate");
+        cudaGraphDestroy(graph);
+        if (!inst) return ORBX_E_CUDA;
+        h->launches = before;
+        h->graphs.push_back(g);
+        bg = &h->graphs.back();
+      }
+      if (!h->check(cudaGraphLaunch(bg->exec, h->stream), "graph launch")) return ORBX_E_CUDA;
+      h->launches += bg->launches;
+      h->last_batch = nb;
+      h->last_l0 = {h->d_img, (size_t)P * H, P};
+      rc = ORBX_OK;
+    } else {
+      rc = run_batch(h, h->d_img, nb, (size_t)P * H, P, h->d_kps, h->d_desc, h->d_stage_counts, cap);
+    }
     if (rc != ORBX_OK) return rc;
-    if (!h->check(cudaMemcpyAsync(counts + f0, h->d_counts, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, h->stream), "D2H counts") ||
-        !h->check(cudaMemcpyAsync(kps + (size_t)f0 * cap, h->d_kps, sizeof(orbx_keypoint) * (size_t)nb * cap, cudaMemcpyDeviceToHost, h->stream), "D2H keypoints") ||
-        !h->check(cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, h->d_desc, (size_t)nb * cap * 32, cudaMemcpyDeviceToHost, h->stream), "D2H descriptors") ||
-        !h->check(cudaStreamSynchronize(h->stream), "extract batch"))
+    if (h->h_stage && nb == h->cfg.max_batch && cap == h->stage_cap) {
+      // the whole staging block in one pinned copy, then out of the mirror
+      if (!h->check(cudaMemcpyAsync(h->h_stage, h->d_stage, h->stage_bytes, cudaMemcpyDeviceToHost, h->stream), "D2H results") ||
+          !h->check(cudaStreamSynchronize(h->stream), "extract batch"))
+        return ORBX_E_CUDA;
+      const size_t n = (size_t)nb * cap;
+      std::memcpy(counts + f0, h->h_stage + ((uint8_t*)h->d_stage_counts - h->d_stage), sizeof(int32_t) * nb);
+      std::memcpy(kps + (size_t)f0 * cap, h->h_stage, sizeof(orbx_keypoint) * n);
+      std::memcpy(desc + (size_t)f0 * cap * 32, h->h_stage + (h->d_desc - h->d_stage), n * 32);
+    } else if (!h->check(cudaMemcpyAsync(counts + f0, h->d_stage_counts, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, h->stream), "D2H counts") ||
+               !h->check(cudaMemcpyAsync(kps + (size_t)f0 * cap, h->d_kps, sizeof(orbx_keypoint) * (size_t)nb * cap, cudaMemcpyDeviceToHost, h->stream), "D2H keypoints") ||
+               !h->check(cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, h->d_desc, (size_t)nb * cap * 32, cudaMemcpyDeviceToHost, h->stream), "D2H descriptors") ||
+               !h->check(cudaStreamSynchronize(h->stream), "extract batch"))
       return ORBX_E_CUDA;
     for (int f = 0; f < nb; ++f)
       if (counts[f0 + f] > cap) {
