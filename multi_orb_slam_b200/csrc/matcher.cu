@@ -226,41 +226,53 @@ __device__ __forceinline__ int grid_cell_of(float x, float y, float min_x, float
 }
 
 // One CTA per frame: counting sort of keypoints into grid cells, stable in keypoint index.
+#define GRID_CELL_CACHE 4096  // keypoints whose grid cell is kept in shared memory between the count and the placement
 __global__ void __launch_bounds__(256) k_build_grid(const orbx_keypoint* __restrict__ kps, const int32_t* __restrict__ n_arr,
                                                     int n_fixed, int cap, orbm_bounds b, int* __restrict__ start_out,
                                                     uint16_t* __restrict__ items_out,
-                                                    const int32_t* __restrict__ cam_of = nullptr, int cam = 0) {
+                                                    const int32_t* __restrict__ cam_of = nullptr, int cam = 0,
+                                                    int grid_per_camera = 0) {
+  // grid_per_camera: one CTA per camera of ONE keypoint set (blockIdx.x = camera, outputs `cap` / GRID_CELLS + 1 apart);
+  // otherwise one CTA per frame of a batch (keypoints `cap` apart)
   __shared__ int s_cnt[GRID_CELLS + 1];
-  __shared__ int s_part[257];
-  const int frame = blockIdx.x, tid = threadIdx.x;
+  __shared__ int s_warp[8];
+  __shared__ uint16_t s_cell[GRID_CELL_CACHE];
+  const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (grid_per_camera) cam = frame;
   const int n = n_arr ? min(n_arr[frame], cap) : n_fixed;
-  const orbx_keypoint* k = kps + (size_t)frame * cap;
+  const orbx_keypoint* k = grid_per_camera ? kps : kps + (size_t)frame * cap;
   const float inv_w = __fdiv_rn((float)GRID_COLS, __fsub_rn(b.max_x, b.min_x));
   const float inv_h = __fdiv_rn((float)GRID_ROWS, __fsub_rn(b.max_y, b.min_y));
+  auto cell_of = [&](int i) {
+    int c = grid_cell_of(k[i].x, k[i].y, b.min_x, b.min_y, inv_w, inv_h);
+    if (cam_of && cam_of[i] != cam) c = -1;  // mGrids[cam] holds that camera's keypoints only (src/Frame.cc:384-393)
+    return c;
+  };
   for (int i = tid; i <= GRID_CELLS; i += 256) s_cnt[i] = 0;
   __syncthreads();
   for (int i = tid; i < n; i += 256) {
-    int c = grid_cell_of(k[i].x, k[i].y, b.min_x, b.min_y, inv_w, inv_h);
-    if (cam_of && cam_of[i] != cam) c = -1;  // mGrids[cam] holds that camera's keypoints only (src/Frame.cc:384-393)
+    const int c = cell_of(i);
+    if (i < GRID_CELL_CACHE) s_cell[i] = (uint16_t)c;  // -1 -> 0xFFFF (GRID_CELLS < 0xFFFF)
     if (c >= 0) atomicAdd(&s_cnt[c], 1);
   }
   __syncthreads();
-  // exclusive scan of GRID_CELLS counts: 12 per thread
+  // exclusive scan of GRID_CELLS counts: 12 per thread, warp scans, a scan of the 8 warp sums
   {
     const int lo = tid * 12;
     int s = 0;
     for (int i = lo; i < lo + 12; ++i) s += s_cnt[i];
-    s_part[tid] = s;
-    __syncthreads();
-    if (tid == 0) {
-      int run = 0;
-      for (int i = 0; i < 256; ++i) { const int v = s_part[i]; s_part[i] = run; run += v; }
-      s_part[256] = run;
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
     }
+    if (lane == 31) s_warp[w] = incl;
     __syncthreads();
-    int run = s_part[tid];
+    int run = incl - s;
+    for (int ww = 0; ww < w; ++ww) run += s_warp[ww];
     for (int i = lo; i < lo + 12; ++i) { const int v = s_cnt[i]; s_cnt[i] = run; run += v; }
-    if (tid == 0) s_cnt[GRID_CELLS] = s_part[256];
+    if (tid == 255) s_cnt[GRID_CELLS] = run;
   }
   __syncthreads();
   int* start = start_out + (size_t)frame * (GRID_CELLS + 1);
@@ -272,8 +284,10 @@ __global__ void __launch_bounds__(256) k_build_grid(const orbx_keypoint* __restr
     for (int base = 0; base < n; base += 32) {
       const int i = base + tid;
       int c = -1;
-      if (i < n) c = grid_cell_of(k[i].x, k[i].y, b.min_x, b.min_y, inv_w, inv_h);
-      if (i < n && cam_of && cam_of[i] != cam) c = -1;
+      if (i < n) {
+        if (i < GRID_CELL_CACHE) { const int cc = s_cell[i]; c = cc == 0xFFFF ? -1 : cc; }
+        else c = cell_of(i);
+      }
       const unsigned peers = __match_any_sync(0xffffffffu, c);
       if (c >= 0) {
         const int rank = __popc(peers & ((1u << tid) - 1u));
@@ -1345,21 +1359,34 @@ __global__ void __launch_bounds__(256) k_proj_candidates(const orbx_keypoint* __
 // single-CTA exclusive scan (n up to a few hundred thousand)
 __global__ void __launch_bounds__(1024) k_scan_exclusive(const int* __restrict__ in, int* __restrict__ out, int n,
                                                          int* __restrict__ total) {
-  __shared__ int s_part[1025];
-  const int tid = threadIdx.x;
+  // one CTA: a contiguous chunk per thread, warp scans of the chunk sums, a scan of the 32 warp sums by warp 0
+  __shared__ int s_warp[32];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int chunk = (n + 1023) / 1024;
-  const int lo = tid * chunk, hi = min(n, lo + chunk);
+  const int lo = min(n, tid * chunk), hi = min(n, lo + chunk);
   int s = 0;
   for (int i = lo; i < hi; ++i) s += in[i];
-  s_part[tid] = s;
+  int incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[w] = incl;
   __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int i = 0; i < 1024; ++i) { const int v = s_part[i]; s_part[i] = run; run += v; }
-    *total = run;
+  if (w == 0) {
+    const int ws = s_warp[lane];
+    int wi = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += v;
+    }
+    s_warp[lane] = wi - ws;
+    if (lane == 31) *total = wi;
   }
   __syncthreads();
-  int run = s_part[tid];
+  int run = s_warp[w] + incl - s;
   for (int i = lo; i < hi; ++i) { const int v = in[i]; out[i] = run; run += v; }
 }
 
@@ -2662,10 +2689,22 @@ __global__ void __launch_bounds__(1024) k_query_resolve_cta(const ProjQuery* __r
   if (tid < HISTO_LENGTH) s_hist[tid] = 0;
   __syncthreads();
   int nacc = 0;  // warp 0's count
+  // Nothing on the walk's critical path waits for HBM (the scheme of k_proj_resolve_cta): a warp keeps the first
+  // QR_SLOTS * 32 candidates of its query in registers (longer rows read the rest in place), the entries of the next
+  // step's query are fetched while this step resolves, and the counts / offsets one step further ahead.
+  constexpr int QR_SLOTS = 2;
+  constexpr uint32_t QR_NONE = 0xFFFFFFFFu;  // entries are dist << 16 | index with dist <= 256
+  uint32_t ent[QR_SLOTS], ent_n[QR_SLOTS];
+  int cnt = w < nq ? row_cnt[w] : 0, off = w < nq ? row_off[w] : 0;
+  int cnt_n = 32 + w < nq ? row_cnt[32 + w] : 0, off_n = 32 + w < nq ? row_off[32 + w] : 0;
+#pragma unroll
+  for (int kk = 0; kk < QR_SLOTS; ++kk) ent[kk] = kk * 32 + lane < cnt ? rows[off + kk * 32 + lane] : QR_NONE;
   for (int b0 = 0; b0 < nq; b0 += 32) {
-    const int j = b0 + w;
-    const int cnt = j < nq ? row_cnt[j] : 0;
-    const uint32_t* row = rows + (j < nq ? row_off[j] : 0);
+#pragma unroll
+    for (int kk = 0; kk < QR_SLOTS; ++kk) ent_n[kk] = kk * 32 + lane < cnt_n ? rows[off_n + kk * 32 + lane] : QR_NONE;
+    const int j2 = b0 + 64 + w;
+    const int cnt_nn = j2 < nq ? row_cnt[j2] : 0, off_nn = j2 < nq ? row_off[j2] : 0;
+    const uint32_t* row = rows + off;
     bool pend = cnt > 0;
     // warp 0 keeps the per-query fields of the step, lane = query
     const int lj = b0 + lane;
@@ -2682,10 +2721,17 @@ __global__ void __launch_bounds__(1024) k_query_resolve_cta(const ProjQuery* __r
       if (pend) {
         uint32_t best = 0xFFFFFFFFu;
         int my_idx = -1;
-        for (int c = lane; c < cnt; c += 32) {
+#pragma unroll
+        for (int kk = 0; kk < QR_SLOTS; ++kk) {
+          const uint32_t e = ent[kk];
+          if (e == QR_NONE || held[e & 0xFFFFu]) continue;
+          const uint32_t key = (e >> 16) << 16 | (uint32_t)(kk * 32 + lane);  // dist, then traversal position (strict <)
+          if (key < best) { best = key; my_idx = (int)(e & 0xFFFFu); }
+        }
+        for (int c = QR_SLOTS * 32 + lane; c < cnt; c += 32) {
           const uint32_t e = row[c];
           if (held[e & 0xFFFFu]) continue;
-          const uint32_t key = (e >> 16) << 16 | (uint32_t)c;  // dist, then traversal position (strict <)
+          const uint32_t key = (e >> 16) << 16 | (uint32_t)c;
           if (key < best) { best = key; my_idx = (int)(e & 0xFFFFu); }
         }
         const uint32_t mine = best;
@@ -2728,6 +2774,10 @@ __global__ void __launch_bounds__(1024) k_query_resolve_cta(const ProjQuery* __r
       rp ^= 1;
       if (!left) break;
     }
+    cnt = cnt_n; off = off_n;
+    cnt_n = cnt_nn; off_n = off_nn;
+#pragma unroll
+    for (int kk = 0; kk < QR_SLOTS; ++kk) ent[kk] = ent_n[kk];
   }
   if (w != 0) return;
   int nmatches = nacc;
@@ -2822,11 +2872,8 @@ int run_projected(orbm_matcher* m, const orbx_keypoint* k, const uint8_t* desc, 
     int* drow_off = reinterpret_cast<int*>(dev + o_off);
     int32_t* dacc_idx = reinterpret_cast<int32_t*>(dev + o_ai);
     int32_t* dacc_bin = reinterpret_cast<int32_t*>(dev + o_ab);
-    for (int c = 0; c < n_cams; ++c) {
-      k_build_grid<<<1, 256, 0, st>>>(dk, nullptr, n, n, bounds, gstart + (size_t)c * (GRID_CELLS + 1), gitems + (size_t)c * n,
-                                      dcam, c);
-      m->launches++;
-    }
+    k_build_grid<<<n_cams, 256, 0, st>>>(dk, nullptr, n, n, bounds, gstart, gitems, dcam, 0, 1);  // one CTA per camera
+    m->launches++;
     const int blocks = (nq + 7) / 8;
     k_query_candidates<<<blocks, 256, 0, st>>>(dk, dd, dur, bounds, gstart, gitems, n, dq, dsd, nq, 1, drow_cnt, nullptr, nullptr);
     k_scan_exclusive<<<1, 1024, 0, st>>>(drow_cnt, drow_off, nq, misc);  // misc[0] = total rows needed
@@ -3085,10 +3132,15 @@ int fuse_run(orbm_matcher* m, const orbx_keypoint* kf_k, const uint8_t* kf_desc,
   cudaMemcpyAsync(dmd, mp_desc, (size_t)n_mp * 32, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(dq, q.data(), sizeof(ProjQuery) * nq, cudaMemcpyHostToDevice, st);
   cudaMemsetAsync(dbest, 0xFF, sizeof(int32_t) * 2 * (size_t)n_mp, st);
-  for (int c = 0; c < 2; ++c) {
-    k_build_grid<<<1, 256, 0, st>>>(dk, nullptr, n_kf, n_kf, b, gstart + (size_t)c * (GRID_CELLS + 1), gitems + (size_t)c * n_kf,
-                                    kf_cam ? dcam : nullptr, c);
+  if (kf_cam) {
+    k_build_grid<<<2, 256, 0, st>>>(dk, nullptr, n_kf, n_kf, b, gstart, gitems, dcam, 0, 1);  // one CTA per camera
     m->launches++;
+  } else {
+    for (int c = 0; c < 2; ++c) {
+      k_build_grid<<<1, 256, 0, st>>>(dk, nullptr, n_kf, n_kf, b, gstart + (size_t)c * (GRID_CELLS + 1), gitems + (size_t)c * n_kf,
+                                      nullptr, c);
+      m->launches++;
+    }
   }
   LevelTable lt;
   for (int i = 0; i < ORBX_MAX_LEVELS; ++i) lt.v[i] = (inv_level_sigma2 && i < nlevels) ? inv_level_sigma2[i] : 0.f;
