@@ -1055,113 +1055,106 @@ __global__ void __launch_bounds__(256) k_bow_candidates(const BowQuery* __restri
   }
 }
 
-#define BOW_SMEM_ROWS 55000  // candidate entries staged in shared memory (215 KB of the SM's 227 KB; one CTA per pair)
+#define BOW_SMEM_ROWS 52000  // candidate entries staged in shared memory (203 KB of the SM's 227 KB; one CTA per pair)
 
 // One CTA per pair of the batch.  pair_info[p] = {first query, query count, first row, row count, o1, o2, n2, 0}.
-__global__ void __launch_bounds__(256) k_bow_resolve(const BowQuery* __restrict__ q_all, const int32_t* __restrict__ pair_info,
+#define BOW_NT 1024
+__global__ void __launch_bounds__(BOW_NT) k_bow_resolve(const BowQuery* __restrict__ q_all, const int32_t* __restrict__ pair_info,
                                                      const uint32_t* __restrict__ rows_all, const float* __restrict__ angle1,
                                                      const float* __restrict__ angle2, float nnratio, int check_ori,
-                                                     int max_dist, int32_t* __restrict__ matches12,
+                                                     int max_dist, int max_nodes, int32_t* __restrict__ matches12,
                                                      int32_t* __restrict__ matches21, int32_t* __restrict__ q_bin_all,
                                                      int* __restrict__ nmatches_out) {
-  extern __shared__ uint32_t s_bow[];  // [n2 / 32 + 1] matched bits of side 2, then the staged rows
+  // [max_nodes + 1] first query of every vocabulary node, [n2 / 32 + 1] matched bits of side 2, then the staged rows
+  extern __shared__ uint32_t s_bow[];
   __shared__ int s_hist[HISTO_LENGTH];
   __shared__ int s_keep[HISTO_LENGTH];
-  __shared__ int s_nmatch;
-  const int tid = threadIdx.x, lane = tid & 31;
+  __shared__ int s_nmatch, s_nn;
+  __shared__ int s_wcount[BOW_NT / 32];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int32_t* info = pair_info + 8 * blockIdx.x;
   const int q0 = info[0], nq = info[1], r0 = info[2], total_rows = info[3], o2 = info[5], n2 = info[6];
   const BowQuery* q = q_all + q0;
   int32_t* q_bin = q_bin_all + q0;
   const int nwords = n2 / 32 + 1;
-  uint32_t* s_taken = s_bow;
-  uint32_t* s_rows = s_bow + nwords;
+  int* s_nodes = reinterpret_cast<int*>(s_bow);
+  uint32_t* s_taken = s_bow + max_nodes + 1;
+  uint32_t* s_rows = s_taken + nwords;
   const bool staged = total_rows <= BOW_SMEM_ROWS;
-  for (int i = tid; i < nwords; i += 256) s_taken[i] = 0;
+  for (int i = tid; i < nwords; i += BOW_NT) s_taken[i] = 0;
   if (staged)
-    for (int i = tid; i < total_rows; i += 256) s_rows[i] = rows_all[r0 + i];
+    for (int i = tid; i < total_rows; i += BOW_NT) s_rows[i] = rows_all[r0 + i];
   if (tid < HISTO_LENGTH) s_hist[tid] = 0;
+  if (tid == 0) { s_nmatch = 0; s_nn = 0; }
   __syncthreads();
   const uint32_t* R = staged ? s_rows : rows_all + r0;  // indexed by row offsets relative to the pair
+  // The queries arrive in node order (the host walks the two feature vectors) and a query's candidates are the side-2
+  // features of ITS node.  The walk's only state is the matched bit of each side-2 feature (:270-271, :311), and a
+  // feature belongs to exactly one node of the feature vector: queries of different nodes never see each other's
+  // effects.  So the ordered walk decomposes into independent per-node walks - a warp takes a node and walks its
+  // queries in order, 32 nodes at a time - with the same matches as the sequential loop over all nodes.
+  for (int base = 0; base < nq; base += BOW_NT) {  // ordered list of the nodes' first queries (t0 = first side-2 item)
+    const int j = base + tid;
+    const bool first = j < nq && (j == 0 || q[j].t0 != q[j - 1].t0);
+    const unsigned bal = __ballot_sync(0xffffffffu, first);
+    if (lane == 0) s_wcount[w] = __popc(bal);
+    __syncthreads();
+    int pos = s_nn + __popc(bal & ((1u << lane) - 1u));
+    for (int ww = 0; ww < w; ++ww) pos += s_wcount[ww];
+    if (first) s_nodes[pos] = j;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int ww = 0; ww < BOW_NT / 32; ++ww) t += s_wcount[ww];
+      s_nn += t;
+    }
+    __syncthreads();
+  }
+  const int n_nodes = s_nn;
+  if (tid == 0) s_nodes[n_nodes] = nq;
+  __syncthreads();
   {
-    // Ordered walk, eight queries per step (a warp per query).  A query's outcome depends only on
-    // the two least keys among its side-2 candidates that are still unmatched, and the matched set
-    // only grows: every pending warp scans its row under the matched bits as they stand, warp 0
-    // commits the longest prefix of the step whose answers are independent (a lane conflicts when a
-    // lower lane of the step is about to match its best or its second), the rest scan again.  The
-    // lowest pending query never conflicts, so matches are made in the reference's order.  During
-    // the walk q_bin[j] records the matched side-2 index; the rotation bins follow below.
-    __shared__ int s_b[8], s_s[8], s_will[8];
-    __shared__ unsigned s_donem, s_leftm;
-    const int w = tid >> 5;
-    int nmatches = 0;  // warp 0's count
-    int cnt_n = w < nq ? q[w].cnt : 0, off_n = w < nq ? q[w].off : 0;
-    for (int j0 = 0; j0 < nq; j0 += 8) {
-      const int j = j0 + w;
-      const int cnt = j < nq ? cnt_n : 0, off = off_n - r0;
-      if (j + 8 < nq) { cnt_n = q[j + 8].cnt; off_n = q[j + 8].off; }  // next step's fields, in flight during this one
-      bool pend = cnt > 0;
-      if (!pend && j < nq && lane == 0) q_bin[j] = -1;
-      for (;;) {
-        int b = -1, sx = -1, will = 0;
-        if (pend) {
-          // key = dist << 16 | position in the node's vector: the strict-< scan order (:311-321)
-          uint32_t best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
-          for (int c = lane; c < cnt; c += 32) {
-            const uint32_t e = R[off + c];
-            const uint32_t idx2 = e & 0xFFFFu;
-            if ((e >> 16) == 0xFFFFu || (s_taken[idx2 >> 5] >> (idx2 & 31) & 1u)) continue;
-            const uint32_t key = (e & 0xFFFF0000u) | (uint32_t)c;
-            second = min(second, max(best, key));
-            best = min(best, key);
-          }
-          warp_top2(best, second);
-          // nothing left, or the least distance above the gate (it can only grow): no match, final
-          if (best == 0xFFFFFFFFu || (int)(best >> 16) > max_dist) {
-            pend = false;
-            if (lane == 0) q_bin[j] = -1;
-          } else {
-            const int bestDist1 = (int)(best >> 16);
-            const int bestDist2 = second == 0xFFFFFFFFu ? 256 : (int)(second >> 16);
-            b = (int)(R[off + (int)(best & 0xFFFFu)] & 0xFFFFu);
-            if (second != 0xFFFFFFFFu) sx = (int)(R[off + (int)(second & 0xFFFFu)] & 0xFFFFu);
-            will = (float)bestDist1 < __fmul_rn(nnratio, (float)bestDist2);
+    int nm = 0;
+    for (int node = w; node < n_nodes; node += BOW_NT / 32) {
+      const int j_end = s_nodes[node + 1];
+      int j = s_nodes[node];
+      int cnt = q[j].cnt, off = q[j].off - r0;
+      for (; j < j_end; ++j) {
+        int cnt_n = 0, off_n = 0;
+        if (j + 1 < j_end) { cnt_n = q[j + 1].cnt; off_n = q[j + 1].off - r0; }  // in flight during this query
+        // key = dist << 16 | position in the node's vector: the strict-< scan order (:311-321)
+        uint32_t best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
+        for (int c = lane; c < cnt; c += 32) {
+          const uint32_t e = R[off + c];
+          const uint32_t idx2 = e & 0xFFFFu;
+          if ((e >> 16) == 0xFFFFu || (s_taken[idx2 >> 5] >> (idx2 & 31) & 1u)) continue;
+          const uint32_t key = (e & 0xFFFF0000u) | (uint32_t)c;
+          second = min(second, max(best, key));
+          best = min(best, key);
+        }
+        warp_top2(best, second);
+        int res = -1;
+        // nothing left, or the least distance above the gate: no match
+        if (best != 0xFFFFFFFFu && (int)(best >> 16) <= max_dist) {
+          const int bestDist1 = (int)(best >> 16);
+          const int bestDist2 = second == 0xFFFFFFFFu ? 256 : (int)(second >> 16);
+          if ((float)bestDist1 < __fmul_rn(nnratio, (float)bestDist2)) {
+            res = (int)(R[off + (int)(best & 0xFFFFu)] & 0xFFFFu);
+            if (lane == 0) atomicOr(&s_taken[res >> 5], 1u << (res & 31));  // other nodes' bits share the word
+            ++nm;
           }
         }
-        if (lane == 0) { s_b[w] = b; s_s[w] = sx; s_will[w] = will; }
-        __syncthreads();
-        if (w == 0) {
-          const int l8 = lane & 7;
-          const int mb = s_b[l8], ms = s_s[l8], mw = s_will[l8];
-          const bool p = lane < 8 && mb >= 0;
-          bool conflict = false;
-#pragma unroll
-          for (int src = 0; src < 7; ++src) {
-            const int ob = __shfl_sync(0xffffffffu, mw ? mb : -1, src);
-            if (p && src < lane && ob >= 0 && (ob == mb || ob == ms)) conflict = true;
-          }
-          const unsigned cm = __ballot_sync(0xffffffffu, conflict);
-          const int first = cm ? __ffs(cm) - 1 : 32;
-          const bool done = p && lane < first;
-          const bool commit = done && mw;
-          if (commit) atomicOr(&s_taken[mb >> 5], 1u << (mb & 31));
-          if (done) q_bin[j0 + lane] = commit ? mb : -1;
-          nmatches += __popc(__ballot_sync(0xffffffffu, commit));
-          const unsigned dm = __ballot_sync(0xffffffffu, done), pm = __ballot_sync(0xffffffffu, p);
-          if (lane == 0) { s_donem = dm; s_leftm = pm & ~dm; }
-        }
-        __syncthreads();
-        if (s_donem >> w & 1u) pend = false;
-        const unsigned left = s_leftm;
-        __syncthreads();  // s_b / s_donem are rewritten in the next round
-        if (!left) break;
+        if (lane == 0) q_bin[j] = res;  // the matched side-2 index for now; the rotation bins follow below
+        __syncwarp();
+        cnt = cnt_n;
+        off = off_n;
       }
     }
-    if (tid == 0) s_nmatch = nmatches;
+    if (lane == 0 && nm) atomicAdd(&s_nmatch, nm);
   }
   __syncthreads();
   // matches and their rotation bins (:330-341), a thread per query
-  for (int j = tid; j < nq; j += 256) {
+  for (int j = tid; j < nq; j += BOW_NT) {
     const int idx2 = q_bin[j];
     if (idx2 < 0) continue;
     const int idx1 = q[j].idx1;
@@ -1181,7 +1174,7 @@ __global__ void __launch_bounds__(256) k_bow_resolve(const BowQuery* __restrict_
   __syncthreads();
   // removal pass (:365-383) and the side-2 view of the matches
   const int o1 = info[4];
-  for (int j = tid; j < nq; j += 256) {
+  for (int j = tid; j < nq; j += BOW_NT) {
     const int bin = q_bin[j];
     if (bin < 0) continue;
     const int idx1 = q[j].idx1;
@@ -2277,12 +2270,19 @@ int orbm_search_by_bow_batch_host(orbm_matcher* m, orbm_bow_pair* pairs, int n_p
   cudaMemcpyAsync(dinfo, info.data(), sizeof(int32_t) * info.size(), cudaMemcpyHostToDevice, st);
   cudaMemsetAsync(dm12, 0xFF, sizeof(int32_t) * (G1 + G2), st);  // matches12 and matches21 = -1
   cudaMemsetAsync(dnm, 0, sizeof(int) * n_pairs, st);
-  const size_t smem = sizeof(uint32_t) * ((size_t)(max_n2 / 32 + 1) + max_rows);
+  int max_nodes = 0;  // vocabulary nodes with queries, per pair (queries of a node are consecutive and share t0)
+  for (int p = 0; p < n_pairs; ++p) {
+    const int qa = info[8 * p], qn = info[8 * p + 1];
+    int nn = 0;
+    for (int j = qa; j < qa + qn; ++j) nn += j == qa || queries[j].t0 != queries[j - 1].t0;
+    max_nodes = std::max(max_nodes, nn);
+  }
+  const size_t smem = sizeof(uint32_t) * ((size_t)(max_nodes + 1) + (size_t)(max_n2 / 32 + 1) + max_rows);
   if (smem > 48 * 1024 &&
       !m->check(cudaFuncSetAttribute(k_bow_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in"))
     return ORBX_E_CUDA;
   k_bow_candidates<<<(nq + 7) / 8, 256, 0, st>>>(dq, nq, dd1, dd2, dvalid2, ditems2, rows);
-  k_bow_resolve<<<n_pairs, 256, smem, st>>>(dq, dinfo, rows, da1, da2, nnratio, check_ori, max_dist, dm12, dm21, dbin, dnm);
+  k_bow_resolve<<<n_pairs, BOW_NT, smem, st>>>(dq, dinfo, rows, da1, da2, nnratio, check_ori, max_dist, max_nodes, dm12, dm21, dbin, dnm);
   m->launches += 2;
   std::vector<int32_t> hm(G1 + G2), hnm(n_pairs);
   cudaMemcpyAsync(hm.data(), dm12, sizeof(int32_t) * (G1 + G2), cudaMemcpyDeviceToHost, st);
