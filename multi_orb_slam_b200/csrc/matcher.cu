@@ -2228,46 +2228,52 @@ int orbm_search_by_bow_batch_host(orbm_matcher* m, orbm_bow_pair* pairs, int n_p
   }
   const int nq = (int)queries.size();
   if (nq == 0) return ORBX_OK;
-  // pack the per-pair arrays into batch-global ones
-  std::vector<uint8_t> hd((G1 + G2) * 32), hvalid2(G2, 1);
-  std::vector<float> hang(G1 + G2);
+  // One device block [uploaded inputs | working arrays]; the inputs are packed straight into ONE pinned host block and go
+  // up in ONE copy, the outputs come back through a second pinned block (pageable cudaMemcpyAsync calls cost ~10 us each
+  // and a batch of 32 pairs is 4 MB of descriptors).
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t o_desc = 0, o_valid = al((G1 + G2) * 32), o_ang = o_valid + al(G2), o_items = o_ang + al(4 * (G1 + G2)),
+               o_q = o_items + al(4 * items2.size()), o_info = o_q + al(sizeof(BowQuery) * (size_t)nq),
+               in_bytes = o_info + al(4 * info.size());
+  const size_t o_m = in_bytes, o_bin = o_m + al(4 * (G1 + G2)), o_nm = o_bin + al(4 * (size_t)nq),
+               dev_bytes = o_nm + al(4 * (size_t)n_pairs);
+  OrbDeviceGuard dev_guard(m->device);
+  cudaStream_t st = m->stream;
+  uint8_t* hin = m->pinned(0, in_bytes);
+  uint8_t* hout = m->pinned(1, 4 * (G1 + G2) + 4 * (size_t)n_pairs);
+  uint8_t* dev = m->scratch<uint8_t>(8, dev_bytes);
+  uint32_t* rows = m->scratch<uint32_t>(6, (size_t)total);
+  if (!hin || !hout || !dev || !rows) return ORBX_E_CUDA;
   {
+    uint8_t* hd = hin + o_desc;
+    uint8_t* hvalid2 = hin + o_valid;
+    float* hang = reinterpret_cast<float*>(hin + o_ang);
     size_t o1 = 0, o2 = 0;
     for (int p = 0; p < n_pairs; ++p) {
       const orbm_bow_pair& P = pairs[p];
-      if (P.n1) { std::memcpy(&hd[o1 * 32], P.desc1, (size_t)P.n1 * 32); std::memcpy(&hang[o1], P.angle1, sizeof(float) * P.n1); }
+      if (P.n1) { std::memcpy(hd + o1 * 32, P.desc1, (size_t)P.n1 * 32); std::memcpy(hang + o1, P.angle1, sizeof(float) * P.n1); }
       if (P.n2) {
-        std::memcpy(&hd[(G1 + o2) * 32], P.desc2, (size_t)P.n2 * 32);
-        std::memcpy(&hang[G1 + o2], P.angle2, sizeof(float) * P.n2);
-        if (P.valid2)
-          for (int i = 0; i < P.n2; ++i) hvalid2[o2 + i] = P.valid2[i] ? 1 : 0;
+        std::memcpy(hd + (G1 + o2) * 32, P.desc2, (size_t)P.n2 * 32);
+        std::memcpy(hang + G1 + o2, P.angle2, sizeof(float) * P.n2);
+        for (int i = 0; i < P.n2; ++i) hvalid2[o2 + i] = P.valid2 ? (P.valid2[i] ? 1 : 0) : 1;
       }
       o1 += P.n1;
       o2 += P.n2;
     }
+    std::memcpy(hin + o_items, items2.data(), 4 * items2.size());
+    std::memcpy(hin + o_q, queries.data(), sizeof(BowQuery) * (size_t)nq);
+    std::memcpy(hin + o_info, info.data(), 4 * info.size());
   }
-  OrbDeviceGuard dev_guard(m->device);
-  cudaStream_t st = m->stream;
-  uint8_t* dd = m->scratch<uint8_t>(8, (G1 + G2) * 32 + G2 + 64);
-  float* dang = m->scratch<float>(9, G1 + G2);
-  int32_t* dints = m->scratch<int32_t>(4, items2.size() + G1 + G2 + nq + (size_t)n_pairs * 9 + 8);
-  BowQuery* dq = m->scratch<BowQuery>(5, nq);
-  uint32_t* rows = m->scratch<uint32_t>(6, (size_t)total);
-  if (!dd || !dang || !dints || !dq || !rows) return ORBX_E_CUDA;
-  uint8_t *dd1 = dd, *dd2 = dd + G1 * 32, *dvalid2 = dd + (G1 + G2) * 32;
-  float *da1 = dang, *da2 = dang + G1;
-  int32_t* ditems2 = dints;
-  int32_t* dm12 = ditems2 + items2.size();
+  uint8_t *dd1 = dev + o_desc, *dd2 = dd1 + G1 * 32, *dvalid2 = dev + o_valid;
+  float *da1 = reinterpret_cast<float*>(dev + o_ang), *da2 = da1 + G1;
+  int32_t* ditems2 = reinterpret_cast<int32_t*>(dev + o_items);
+  BowQuery* dq = reinterpret_cast<BowQuery*>(dev + o_q);
+  int32_t* dinfo = reinterpret_cast<int32_t*>(dev + o_info);
+  int32_t* dm12 = reinterpret_cast<int32_t*>(dev + o_m);
   int32_t* dm21 = dm12 + G1;
-  int32_t* dbin = dm21 + G2;
-  int32_t* dinfo = dbin + nq;
-  int* dnm = dinfo + (size_t)n_pairs * 8;
-  cudaMemcpyAsync(dd, hd.data(), hd.size(), cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dvalid2, hvalid2.data(), G2, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dang, hang.data(), sizeof(float) * hang.size(), cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(ditems2, items2.data(), sizeof(int32_t) * items2.size(), cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dq, queries.data(), sizeof(BowQuery) * nq, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dinfo, info.data(), sizeof(int32_t) * info.size(), cudaMemcpyHostToDevice, st);
+  int32_t* dbin = reinterpret_cast<int32_t*>(dev + o_bin);
+  int* dnm = reinterpret_cast<int*>(dev + o_nm);
+  cudaMemcpyAsync(dev, hin, in_bytes, cudaMemcpyHostToDevice, st);
   cudaMemsetAsync(dm12, 0xFF, sizeof(int32_t) * (G1 + G2), st);  // matches12 and matches21 = -1
   cudaMemsetAsync(dnm, 0, sizeof(int) * n_pairs, st);
   int max_nodes = 0;  // vocabulary nodes with queries, per pair (queries of a node are consecutive and share t0)
@@ -2284,16 +2290,17 @@ int orbm_search_by_bow_batch_host(orbm_matcher* m, orbm_bow_pair* pairs, int n_p
   k_bow_candidates<<<(nq + 7) / 8, 256, 0, st>>>(dq, nq, dd1, dd2, dvalid2, ditems2, rows);
   k_bow_resolve<<<n_pairs, BOW_NT, smem, st>>>(dq, dinfo, rows, da1, da2, nnratio, check_ori, max_dist, max_nodes, dm12, dm21, dbin, dnm);
   m->launches += 2;
-  std::vector<int32_t> hm(G1 + G2), hnm(n_pairs);
-  cudaMemcpyAsync(hm.data(), dm12, sizeof(int32_t) * (G1 + G2), cudaMemcpyDeviceToHost, st);
-  cudaMemcpyAsync(hnm.data(), dnm, sizeof(int) * n_pairs, cudaMemcpyDeviceToHost, st);
+  int32_t* hm = reinterpret_cast<int32_t*>(hout);
+  int32_t* hnm = hm + (G1 + G2);
+  cudaMemcpyAsync(hm, dm12, sizeof(int32_t) * (G1 + G2), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(hnm, dnm, sizeof(int) * n_pairs, cudaMemcpyDeviceToHost, st);
   if (!m->check(cudaStreamSynchronize(st), "search_by_bow")) return ORBX_E_CUDA;
   {
     size_t o1 = 0, o2 = 0;
     for (int p = 0; p < n_pairs; ++p) {
       orbm_bow_pair& P = pairs[p];
-      std::copy(hm.begin() + o1, hm.begin() + o1 + P.n1, P.matches12);
-      if (P.matches21) std::copy(hm.begin() + G1 + o2, hm.begin() + G1 + o2 + P.n2, P.matches21);
+      std::copy(hm + o1, hm + o1 + P.n1, P.matches12);
+      if (P.matches21) std::copy(hm + G1 + o2, hm + G1 + o2 + P.n2, P.matches21);
       P.nmatches = hnm[p];
       o1 += P.n1;
       o2 += P.n2;
