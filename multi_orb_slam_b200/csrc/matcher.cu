@@ -2053,6 +2053,45 @@ int orbm_search_for_initialization_host(orbm_matcher* m, int n_pairs, int cap, c
   if (n_pairs == 0) return ORBX_OK;
   OrbDeviceGuard dev_guard(m->device);
   const size_t nk = (size_t)n_pairs * cap;
+  // A few pairs (the per-frame call of Tracking::MonocularInitialization is ONE): ten pageable copies would cost more
+  // than the kernels, so the inputs go up in one pinned block and the outputs come back in one.
+  const size_t in_small = nk * (2 * sizeof(orbx_keypoint) + 64 + 8) + 8 * (size_t)n_pairs;
+  if (in_small <= (1u << 20)) {
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    // [k1 k2 | d1 d2 | n1 n2 | prev || nmatches | matches12]: the upload ends after prev (read AND updated), the download
+    // starts at prev
+    const size_t o_k = 0, o_d = al(2 * nk * sizeof(orbx_keypoint)), o_n = o_d + al(2 * nk * 32),
+                 o_prev = o_n + al(8 * (size_t)n_pairs), o_nm = o_prev + al(8 * nk), o_m12 = o_nm + al(4 * (size_t)n_pairs),
+                 dev_bytes = o_m12 + al(4 * nk), in_bytes = o_nm, o_out = o_prev, out_bytes = dev_bytes - o_out;
+    uint8_t* hin = m->pinned(0, in_bytes);
+    uint8_t* hout = m->pinned(1, out_bytes);
+    uint8_t* dev = m->scratch<uint8_t>(8, dev_bytes);
+    if (!hin || !hout || !dev) return ORBX_E_CUDA;
+    cudaStream_t st = m->stream;
+    std::memcpy(hin + o_k, k1, nk * sizeof(orbx_keypoint));
+    std::memcpy(hin + o_k + nk * sizeof(orbx_keypoint), k2, nk * sizeof(orbx_keypoint));
+    std::memcpy(hin + o_d, d1, nk * 32);
+    std::memcpy(hin + o_d + nk * 32, d2, nk * 32);
+    std::memcpy(hin + o_n, n1, 4 * (size_t)n_pairs);
+    std::memcpy(hin + o_n + 4 * (size_t)n_pairs, n2, 4 * (size_t)n_pairs);
+    std::memcpy(hin + o_prev, prev_xy, 8 * nk);
+    cudaMemcpyAsync(dev, hin, in_bytes, cudaMemcpyHostToDevice, st);
+    orbx_keypoint* dk = reinterpret_cast<orbx_keypoint*>(dev + o_k);
+    uint8_t* dd = dev + o_d;
+    int32_t* dn = reinterpret_cast<int32_t*>(dev + o_n);
+    int32_t* dnm = reinterpret_cast<int32_t*>(dev + o_nm);
+    int32_t* dm12 = reinterpret_cast<int32_t*>(dev + o_m12);
+    float* dprev = reinterpret_cast<float*>(dev + o_prev);
+    const int rc = orbm_search_for_initialization_device(m, n_pairs, cap, dk, dd, dn, dk + nk, dd + nk * 32, dn + n_pairs,
+                                                         bounds2, dprev, window, nnratio, check_ori, dm12, dnm);
+    if (rc != ORBX_OK) return rc;
+    cudaMemcpyAsync(hout, dev + o_out, out_bytes, cudaMemcpyDeviceToHost, st);
+    if (!m->check(cudaStreamSynchronize(st), "search_for_initialization")) return ORBX_E_CUDA;
+    std::memcpy(nmatches, hout + (o_nm - o_out), 4 * (size_t)n_pairs);
+    std::memcpy(matches12, hout + (o_m12 - o_out), 4 * nk);
+    std::memcpy(prev_xy, hout + (o_prev - o_out), 8 * nk);
+    return ORBX_OK;
+  }
   orbx_keypoint* dk = m->scratch<orbx_keypoint>(8, 2 * nk);
   uint8_t* dd = m->scratch<uint8_t>(9, 2 * nk * 32);
   int32_t* dn = m->scratch<int32_t>(10, 3 * (size_t)n_pairs + nk);
@@ -2384,75 +2423,83 @@ int orbm_search_for_triangulation_batch_host(orbm_matcher* m, orbm_tri_pair* pai
   // key-frame-2 features follow all key-frame-1 features in the packed arrays
   for (int32_t& v : items2) v += (int32_t)G1;
   for (BowQuery& bq : queries) bq.o2 += (int32_t)G1;
-  // pack both sides into batch-global arrays: descriptors, keypoints, has_mp, cam, uright
+  // One device block [uploaded inputs | working arrays]; both sides are packed into batch-global arrays (descriptors,
+  // keypoints, has_mp, cam, uright) straight inside ONE pinned host block that goes up in ONE copy; the results come back
+  // through a second pinned block.
   const size_t G = G1 + G2;
-  std::vector<uint8_t> hd(G * 32);
-  std::vector<orbx_keypoint> hk(G);
-  std::vector<int32_t> hmp(G), hcam(G);
-  std::vector<float> hur(G);
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t o_d = 0, o_k = al(G * 32), o_mp = o_k + al(sizeof(orbx_keypoint) * G), o_cam = o_mp + al(4 * G),
+               o_ur = o_cam + al(4 * G), o_const = o_ur + al(4 * G), o_items = o_const + al(4 * hconst.size()),
+               o_q = o_items + al(4 * items2.size()), o_pq = o_q + al(sizeof(BowQuery) * (size_t)nq),
+               in_bytes = o_pq + al(4 * (size_t)(n_pairs + 1));
+  const size_t o_m12 = in_bytes, o_bin = o_m12 + al(4 * G1), o_hist = o_bin + al(4 * (size_t)nq),
+               dev_bytes = o_hist + al(4 * ((size_t)n_pairs * (HISTO_LENGTH + 1)));
+  OrbDeviceGuard dev_guard(m->device);
+  cudaStream_t st = m->stream;
+  uint8_t* hin = m->pinned(0, in_bytes);
+  uint8_t* hout = m->pinned(1, 4 * G1 + 4 * (size_t)n_pairs);
+  uint8_t* dev = m->scratch<uint8_t>(8, dev_bytes);
+  if (!hin || !hout || !dev) return ORBX_E_CUDA;
   {
+    uint8_t* hd = hin + o_d;
+    orbx_keypoint* hk = reinterpret_cast<orbx_keypoint*>(hin + o_k);
+    int32_t* hmp = reinterpret_cast<int32_t*>(hin + o_mp);
+    int32_t* hcam = reinterpret_cast<int32_t*>(hin + o_cam);
+    float* hur = reinterpret_cast<float*>(hin + o_ur);
     size_t o1 = 0, o2 = G1;
     for (int p = 0; p < n_pairs; ++p) {
       const orbm_tri_pair& P = pairs[p];
       if (P.n1) {
-        std::memcpy(&hd[o1 * 32], P.desc1, (size_t)P.n1 * 32);
-        std::copy(P.k1, P.k1 + P.n1, hk.begin() + o1);
-        std::copy(P.has_mp1, P.has_mp1 + P.n1, hmp.begin() + o1);
-        std::copy(P.cam1, P.cam1 + P.n1, hcam.begin() + o1);
-        std::copy(P.uright1, P.uright1 + P.n1, hur.begin() + o1);
+        std::memcpy(hd + o1 * 32, P.desc1, (size_t)P.n1 * 32);
+        std::copy(P.k1, P.k1 + P.n1, hk + o1);
+        std::copy(P.has_mp1, P.has_mp1 + P.n1, hmp + o1);
+        std::copy(P.cam1, P.cam1 + P.n1, hcam + o1);
+        std::copy(P.uright1, P.uright1 + P.n1, hur + o1);
       }
       if (P.n2) {
-        std::memcpy(&hd[o2 * 32], P.desc2, (size_t)P.n2 * 32);
-        std::copy(P.k2, P.k2 + P.n2, hk.begin() + o2);
-        std::copy(P.has_mp2, P.has_mp2 + P.n2, hmp.begin() + o2);
-        std::copy(P.cam2, P.cam2 + P.n2, hcam.begin() + o2);
-        std::copy(P.uright2, P.uright2 + P.n2, hur.begin() + o2);
+        std::memcpy(hd + o2 * 32, P.desc2, (size_t)P.n2 * 32);
+        std::copy(P.k2, P.k2 + P.n2, hk + o2);
+        std::copy(P.has_mp2, P.has_mp2 + P.n2, hmp + o2);
+        std::copy(P.cam2, P.cam2 + P.n2, hcam + o2);
+        std::copy(P.uright2, P.uright2 + P.n2, hur + o2);
       }
       o1 += P.n1;
       o2 += P.n2;
     }
+    std::memcpy(hin + o_const, hconst.data(), 4 * hconst.size());
+    std::memcpy(hin + o_items, items2.data(), 4 * items2.size());
+    std::memcpy(hin + o_q, queries.data(), sizeof(BowQuery) * (size_t)nq);
+    std::memcpy(hin + o_pq, pair_q.data(), 4 * (size_t)(n_pairs + 1));
   }
-  OrbDeviceGuard dev_guard(m->device);
-  cudaStream_t st = m->stream;
-  uint8_t* sb = m->scratch<uint8_t>(8, G * (32 + sizeof(orbx_keypoint) + 12) + 256);
-  int32_t* dints = m->scratch<int32_t>(4, items2.size() + G1 + nq + (size_t)n_pairs * (HISTO_LENGTH + 2) + 8);
-  BowQuery* dq = m->scratch<BowQuery>(5, nq);
-  float* dconst = m->scratch<float>(9, hconst.size());
-  if (!sb || !dints || !dq || !dconst) return ORBX_E_CUDA;
-  uint8_t* dd = sb;  // descriptors first: uint4 loads need 16-byte alignment
-  orbx_keypoint* dk = reinterpret_cast<orbx_keypoint*>(dd + G * 32);
-  int32_t* dmp = reinterpret_cast<int32_t*>(dk + G);
-  int32_t* dcam = dmp + G;
-  float* dur = reinterpret_cast<float*>(dcam + G);
-  cudaMemcpyAsync(dd, hd.data(), hd.size(), cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dk, hk.data(), sizeof(orbx_keypoint) * G, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dmp, hmp.data(), sizeof(int32_t) * G, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dcam, hcam.data(), sizeof(int32_t) * G, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dur, hur.data(), sizeof(float) * G, cudaMemcpyHostToDevice, st);
-  const TriSide s1 = {dk, dd, dmp, dcam, dur};  // both sides share the arrays (batch-global indices)
-  int32_t* ditems2 = dints;
-  int32_t* dm12 = ditems2 + items2.size();
-  int32_t* dbin = dm12 + G1;
-  int32_t* dpq = dbin + nq;
-  int* dhist = dpq + n_pairs + 1;
+  uint8_t* dd = dev + o_d;  // descriptors first: uint4 loads need 16-byte alignment
+  orbx_keypoint* dk = reinterpret_cast<orbx_keypoint*>(dev + o_k);
+  int32_t* dmp = reinterpret_cast<int32_t*>(dev + o_mp);
+  int32_t* dcam = reinterpret_cast<int32_t*>(dev + o_cam);
+  float* dur = reinterpret_cast<float*>(dev + o_ur);
+  float* dconst = reinterpret_cast<float*>(dev + o_const);
+  int32_t* ditems2 = reinterpret_cast<int32_t*>(dev + o_items);
+  BowQuery* dq = reinterpret_cast<BowQuery*>(dev + o_q);
+  int32_t* dpq = reinterpret_cast<int32_t*>(dev + o_pq);
+  int32_t* dm12 = reinterpret_cast<int32_t*>(dev + o_m12);
+  int32_t* dbin = reinterpret_cast<int32_t*>(dev + o_bin);
+  int* dhist = reinterpret_cast<int*>(dev + o_hist);
   int* dnm = dhist + (size_t)n_pairs * HISTO_LENGTH;
-  cudaMemcpyAsync(dconst, hconst.data(), sizeof(float) * hconst.size(), cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(ditems2, items2.data(), sizeof(int32_t) * items2.size(), cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dq, queries.data(), sizeof(BowQuery) * nq, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dpq, pair_q.data(), sizeof(int32_t) * (n_pairs + 1), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dev, hin, in_bytes, cudaMemcpyHostToDevice, st);
+  const TriSide s1 = {dk, dd, dmp, dcam, dur};  // both sides share the arrays (batch-global indices)
   cudaMemsetAsync(dm12, 0xFF, sizeof(int32_t) * G1, st);
   cudaMemsetAsync(dhist, 0, sizeof(int) * ((size_t)n_pairs * (HISTO_LENGTH + 1)), st);
   k_tri_match<<<(nq + 7) / 8, 256, 0, st>>>(dq, nq, s1, s1, ditems2, dconst, only_stereo, check_ori, dm12, dbin, dhist);
   k_tri_finish<<<n_pairs, 256, 0, st>>>(dq, dpq, check_ori, dbin, dhist, dm12, dnm);
   m->launches += 2;
-  std::vector<int32_t> hm(G1), hnm(n_pairs);
-  cudaMemcpyAsync(hm.data(), dm12, sizeof(int32_t) * G1, cudaMemcpyDeviceToHost, st);
-  cudaMemcpyAsync(hnm.data(), dnm, sizeof(int) * n_pairs, cudaMemcpyDeviceToHost, st);
+  int32_t* hm = reinterpret_cast<int32_t*>(hout);
+  int32_t* hnm = hm + G1;
+  cudaMemcpyAsync(hm, dm12, sizeof(int32_t) * G1, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(hnm, dnm, sizeof(int) * n_pairs, cudaMemcpyDeviceToHost, st);
   if (!m->check(cudaStreamSynchronize(st), "search_for_triangulation")) return ORBX_E_CUDA;
   {
     size_t o1 = 0;
     for (int p = 0; p < n_pairs; ++p) {
-      std::copy(hm.begin() + o1, hm.begin() + o1 + pairs[p].n1, pairs[p].matches12);
+      std::copy(hm + o1, hm + o1 + pairs[p].n1, pairs[p].matches12);
       pairs[p].nmatches = hnm[p];
       o1 += pairs[p].n1;
     }
