@@ -282,6 +282,34 @@ def widened_rows_leg(matcher, device, with_cpu):
 
     row = {"workload": f"SearchByProjection(CurrentFrame, LastFrame) of TrackWithMotionModel, two cameras, {n_cur} keypoints x "
                        "1500 last-frame map points", "gpu_ms": best_ms(spf_gpu)}
+    # the same call with its arguments marshalled ONCE: what a C++ caller of orbm_search_by_projection_frame_host pays
+    # (gpu_ms above also carries the Python mirror's per-call Frame object and ~20 numpy -> pointer conversions)
+    import ctypes as C
+    from multi_orb_slam_b200._lib import KP_DTYPE as _KP, Bounds, lib as _lib
+    _f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    _i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    a_k, a_d = np.ascontiguousarray(s["cur_k"], dtype=_KP), np.ascontiguousarray(s["cur_d"], dtype=np.uint8)
+    a_ur, a_cc, a_sf = _f32(s["ur"]), _i32(s["cur_cam"]), _f32(sf_r)
+    a_tc, a_tl, a_cal = _f32(s["Tcw"]), _f32(s["Tlw"]), _f32(RIG_CALIB)
+    a_lk, a_lc, a_lv = np.ascontiguousarray(s["last_k"], dtype=_KP), _i32(s["last_cam"]), _i32(s["last_valid"])
+    a_lx, a_ld, a_lo = _f32(s["last_xyz"]), np.ascontiguousarray(s["last_desc"], dtype=np.uint8), _i32(s["last_obs"])
+    a_fmp, a_fobs, a_nm = fmp0.copy(), _i32(fobs0), C.c_int(0)
+    cam_c, bnd = Camera(*RIG_CAM), Bounds(0.0, 640.0, 0.0, 480.0)
+    ptr = [a.ctypes.data for a in (a_k, a_d, a_ur, a_cc, a_sf, a_tc, a_tl, a_lk, a_lc, a_lv, a_lx, a_ld, a_lo, a_cal, a_fmp, a_fobs)]
+
+    def spf_c():
+        np.copyto(a_fmp, fmp0)
+        rc = _lib.orbm_search_by_projection_frame_host(matcher._h, ptr[0], ptr[1], ptr[2], ptr[3], n_cur, bnd, ptr[4], len(a_sf),
+                                                       cam_c, ptr[5], ptr[6], ptr[7], ptr[8], ptr[9], ptr[10], ptr[11], ptr[12],
+                                                       len(a_lk), ptr[13], 15.0, 0, 1, ptr[14], ptr[15], C.byref(a_nm))
+        if rc != 0:
+            raise SystemExit("bench.py: orbm_search_by_projection_frame_host failed")
+        return a_nm.value
+
+    n_wrapped = spf_gpu()
+    if spf_c() != n_wrapped:
+        raise SystemExit("bench.py: the pre-marshalled tracking-matcher call differs from the wrapped one")
+    row["c_abi_ms"] = best_ms(spf_c, 10)
     if with_cpu:
         row["cpu_ms"] = best_ms(lambda: oracle_lib.search_by_projection_frame(
             s["cur_k"], s["cur_d"], s["ur"], s["cur_cam"], (0, 640, 0, 480), sf_r, RIG_CAM, s["Tcw"], s["Tlw"], s["last_k"],

@@ -2719,15 +2719,23 @@ inline void mat3t_mul_vec(const float* R, int rs, const float* x, float alpha, f
 // overwrites of keypoints that stay free (Observations()==0, :3565-3567) and the accepted list are
 // those of the sequential loop.  (Tracking matcher, 1500 points: sequential warp 1.5 ms per call,
 // single-warp speculation on a precomputed static best 0.49 ms, this form 0.34 ms.)
+// Segments: queries interact only through the occupancy of the keypoints they can reach, and a query reaches the keypoints
+// of ONE camera (its grid), so the queries of different cameras never see each other's effects: the host orders the queries
+// by camera (stable) and every camera's segment is walked by its own CTA, in the reference's order within the camera.
+// Only the rotation histogram is shared by the whole call: with more than one segment the CTAs add their bins to a global
+// histogram and k_query_finish applies the three-maxima filter.
+struct QuerySegs { int n; int start[9]; };
 __global__ void __launch_bounds__(1024) k_query_resolve_cta(const ProjQuery* __restrict__ q, const int* __restrict__ row_cnt,
                                                             const int* __restrict__ row_off, const uint32_t* __restrict__ rows,
-                                                            int nq, int n, const orbx_keypoint* __restrict__ k, int th_dist,
+                                                            QuerySegs segs, int n, const orbx_keypoint* __restrict__ k, int th_dist,
                                                             int check_ori, int any_point_blocks, int32_t* __restrict__ frame_mp,
                                                             const int32_t* __restrict__ frame_mp_obs,
                                                             uint8_t* __restrict__ held_global, int held_in_smem,
                                                             int32_t* __restrict__ acc_idx, int32_t* __restrict__ acc_bin,
-                                                            int* __restrict__ nmatches_out,
+                                                            int* __restrict__ nmatches_out, int* __restrict__ ghist,
+                                                            int* __restrict__ seg_nacc,
                                                             const int* __restrict__ rows_needed = nullptr, long long rows_cap = 0) {
+
   extern __shared__ __align__(16) uint8_t s_held[];
   __shared__ int s_hist[HISTO_LENGTH];
   if (rows_needed && *rows_needed > rows_cap) return;  // the row buffer overflowed: the host repeats the call (run_projected)
@@ -2742,6 +2750,9 @@ __global__ void __launch_bounds__(1024) k_query_resolve_cta(const ProjQuery* __r
     held[i] = frame_mp[i] >= 0 && (any_point_blocks || (frame_mp_obs && frame_mp_obs[i] > 0)) ? 1 : 0;
   if (tid < HISTO_LENGTH) s_hist[tid] = 0;
   __syncthreads();
+  const int qa = segs.start[blockIdx.x], nq = segs.start[blockIdx.x + 1];  // this CTA's queries [qa, nq)
+  acc_idx += qa;  // the accepted matches of a segment are listed from its first query on
+  acc_bin += qa;
   int nacc = 0;  // warp 0's count
   // Nothing on the walk's critical path waits for HBM (the scheme of k_proj_resolve_cta): a warp keeps the first
   // QR_SLOTS * 32 candidates of its query in registers (longer rows read the rest in place), the entries of the next
@@ -2749,11 +2760,11 @@ __global__ void __launch_bounds__(1024) k_query_resolve_cta(const ProjQuery* __r
   constexpr int QR_SLOTS = 2;
   constexpr uint32_t QR_NONE = 0xFFFFFFFFu;  // entries are dist << 16 | index with dist <= 256
   uint32_t ent[QR_SLOTS], ent_n[QR_SLOTS];
-  int cnt = w < nq ? row_cnt[w] : 0, off = w < nq ? row_off[w] : 0;
-  int cnt_n = 32 + w < nq ? row_cnt[32 + w] : 0, off_n = 32 + w < nq ? row_off[32 + w] : 0;
+  int cnt = qa + w < nq ? row_cnt[qa + w] : 0, off = qa + w < nq ? row_off[qa + w] : 0;
+  int cnt_n = qa + 32 + w < nq ? row_cnt[qa + 32 + w] : 0, off_n = qa + 32 + w < nq ? row_off[qa + 32 + w] : 0;
 #pragma unroll
   for (int kk = 0; kk < QR_SLOTS; ++kk) ent[kk] = kk * 32 + lane < cnt ? rows[off + kk * 32 + lane] : QR_NONE;
-  for (int b0 = 0; b0 < nq; b0 += 32) {
+  for (int b0 = qa; b0 < nq; b0 += 32) {
 #pragma unroll
     for (int kk = 0; kk < QR_SLOTS; ++kk) ent_n[kk] = kk * 32 + lane < cnt_n ? rows[off_n + kk * 32 + lane] : QR_NONE;
     const int j2 = b0 + 64 + w;
@@ -2835,6 +2846,22 @@ __global__ void __launch_bounds__(1024) k_query_resolve_cta(const ProjQuery* __r
   }
   if (w != 0) return;
   int nmatches = nacc;
+  if (gridDim.x > 1) {
+    // one of several segments: the bins go to the call's histogram, k_query_finish filters
+    if (check_ori) {
+      __syncwarp();
+      for (int e = lane; e < nacc; e += 32) {
+        float rot = __fsub_rn(__int_as_float(acc_bin[e]), k[acc_idx[e]].angle);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
+        if (bin == HISTO_LENGTH) bin = 0;
+        acc_bin[e] = bin;
+        atomicAdd(&ghist[bin], 1);
+      }
+    }
+    if (lane == 0) seg_nacc[blockIdx.x] = nacc;
+    return;
+  }
   if (check_ori) {
     __syncwarp();
     // rotation bins of the accepted matches (:3604-3615), lanes over the matches
@@ -2868,14 +2895,73 @@ __global__ void __launch_bounds__(1024) k_query_resolve_cta(const ProjQuery* __r
   if (lane == 0) *nmatches_out = nmatches;
 }
 
+// Rotation-consistency filter of a call whose queries were walked as several segments (:3617-3636): one warp.
+__global__ void __launch_bounds__(32) k_query_finish(QuerySegs segs, int check_ori, const int32_t* __restrict__ acc_idx,
+                                                     const int32_t* __restrict__ acc_bin, const int* __restrict__ ghist,
+                                                     const int* __restrict__ seg_nacc, int32_t* __restrict__ frame_mp,
+                                                     int* __restrict__ nmatches_out) {
+  const int lane = threadIdx.x;
+  __shared__ int s_h[HISTO_LENGTH], s_na[8];
+  if (lane < HISTO_LENGTH) s_h[lane] = ghist[lane];  // one round trip to HBM for everything the serial part reads
+  if (lane < segs.n) s_na[lane] = seg_nacc[lane];
+  __syncwarp();
+  int nmatches = 0;
+  for (int sg = 0; sg < segs.n; ++sg) nmatches += s_na[sg];
+  if (check_ori) {
+    int max1 = 0, max2 = 0, max3 = 0, i1_ = -1, i2_ = -1, i3_ = -1;  // every lane computes the same maxima
+    for (int i = 0; i < HISTO_LENGTH; ++i) {
+      const int sv = s_h[i];
+      if (sv > max1) { max3 = max2; max2 = max1; max1 = sv; i3_ = i2_; i2_ = i1_; i1_ = i; }
+      else if (sv > max2) { max3 = max2; max2 = sv; i3_ = i2_; i2_ = i; }
+      else if (sv > max3) { max3 = sv; i3_ = i; }
+    }
+    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2_ = -1; i3_ = -1; }
+    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { i3_ = -1; }
+    int removed = 0;
+    for (int sg = 0; sg < segs.n; ++sg) {
+      const int base = segs.start[sg], na = s_na[sg];
+      for (int e = lane; e < na; e += 32) {
+        const int bin = acc_bin[base + e];
+        if (bin != i1_ && bin != i2_ && bin != i3_) { frame_mp[acc_idx[base + e]] = -1; ++removed; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+    nmatches -= removed;
+  }
+  if (lane == 0) *nmatches_out = nmatches;
+}
+
 // Device side shared by the overloads: per-camera grids, candidates, ordered resolve.
 int run_projected(orbm_matcher* m, const orbx_keypoint* k, const uint8_t* desc, const float* u_right, const int32_t* cam_of,
-                  int n_cams, int n, orbm_bounds bounds, const std::vector<ProjQuery>& q, const uint8_t* src_desc, int n_src,
+                  int n_cams, int n, orbm_bounds bounds, const std::vector<ProjQuery>& q_in, const uint8_t* src_desc, int n_src,
                   int th_dist, int check_ori, int any_point_blocks, int32_t* frame_mp, const int32_t* frame_mp_obs,
                   int* nmatches) {
   *nmatches = 0;
-  const int nq = (int)q.size();
+  const int nq = (int)q_in.size();
   if (n == 0 || nq == 0) return ORBX_OK;
+  bool grouped = false;  // consecutive queries of one source point (Sim3 overload: best over both cameras)
+  for (int i = 1; i < nq && !grouped; ++i) grouped = q_in[i].src == q_in[i - 1].src;
+  // Queries of different cameras are independent (k_query_resolve_cta): ordered by camera, stable, one segment each.
+  const bool held_fits = n <= 32768;
+  const bool split = !grouped && n_cams > 1 && n_cams <= 8 && held_fits;
+  std::vector<ProjQuery> q_sorted;
+  QuerySegs segs;
+  segs.n = 1;
+  segs.start[0] = 0;
+  segs.start[1] = nq;
+  if (split) {
+    q_sorted.reserve(nq);
+    segs.n = n_cams;
+    for (int c = 0; c < n_cams; ++c) {
+      segs.start[c] = (int)q_sorted.size();
+      for (const ProjQuery& e : q_in)
+        if (e.cam == c) q_sorted.push_back(e);
+    }
+    segs.start[n_cams] = (int)q_sorted.size();
+    if ((int)q_sorted.size() != nq) { m->err = "query with a camera index out of range"; return ORBX_E_INVALID; }
+  }
+  const std::vector<ProjQuery>& q = split ? q_sorted : q_in;
   OrbDeviceGuard dev_guard(m->device);
   cudaStream_t st = m->stream;
   // One device block: [uploaded inputs | working arrays].  The inputs are packed into one pinned host block with the
@@ -2884,7 +2970,7 @@ int run_projected(orbm_matcher* m, const orbx_keypoint* k, const uint8_t* desc, 
   const size_t o_desc = 0, o_k = up(o_desc + (size_t)n * 32), o_ur = up(o_k + sizeof(orbx_keypoint) * n),
                o_cam = up(o_ur + 4 * (size_t)n), o_fmp = up(o_cam + 4 * (size_t)n), o_fobs = up(o_fmp + 4 * (size_t)n),
                o_sd = up(o_fobs + 4 * (size_t)n), o_q = up(o_sd + (size_t)n_src * 32), o_misc = up(o_q + sizeof(ProjQuery) * nq),
-               in_bytes = up(o_misc + 8 * sizeof(int));
+               in_bytes = up(o_misc + 64 * sizeof(int));  // misc: [0] rows needed, [2] nmatches, [8..38) histogram, [40..48) per segment
   const size_t o_held = in_bytes, o_cnt = up(o_held + n), o_off = up(o_cnt + 4 * (size_t)nq), o_ai = up(o_off + 4 * (size_t)nq),
                o_ab = up(o_ai + 4 * (size_t)nq), total_bytes = up(o_ab + 4 * (size_t)nq);
   uint8_t* dev = m->scratch<uint8_t>(8, total_bytes);
@@ -2910,7 +2996,7 @@ int run_projected(orbm_matcher* m, const orbx_keypoint* k, const uint8_t* desc, 
     std::memcpy(hin + o_sd, src_desc, (size_t)n_src * 32);
     std::memcpy(hin + o_q, q.data(), sizeof(ProjQuery) * nq);
     int* h_misc = reinterpret_cast<int*>(hin + o_misc);  // [0] total candidate rows (scan), [2] nmatches
-    h_misc[0] = 0; h_misc[1] = 0; h_misc[2] = 0;
+    std::memset(h_misc, 0, 64 * sizeof(int));
     if (!m->check(cudaMemcpyAsync(dev, hin, in_bytes, cudaMemcpyHostToDevice, st), "H2D projected search")) return ORBX_E_CUDA;
     uint8_t* dd = dev + o_desc;
     orbx_keypoint* dk = reinterpret_cast<orbx_keypoint*>(dev + o_k);
@@ -2934,18 +3020,20 @@ int run_projected(orbm_matcher* m, const orbx_keypoint* k, const uint8_t* desc, 
     k_query_candidates<<<blocks, 256, 0, st>>>(dk, dd, dur, bounds, gstart, gitems, n, dq, dsd, nq, 0, drow_cnt, drow_off, rows,
                                                (long long)rows_cap);
     m->launches += 2;
-    const int held_in_smem = n <= 32768;  // occupancy bytes on chip when they fit beside the 8 KB row window
+    const int held_in_smem = held_fits;  // occupancy bytes on chip when they fit beside the 8 KB row window
     const size_t held_bytes = held_in_smem ? (size_t)((n + 15) & ~15) : 0;
-    bool grouped = false;  // consecutive queries of one source point (Sim3 overload: best over both cameras)
-    for (int i = 1; i < nq && !grouped; ++i) grouped = q[i].src == q[i - 1].src;
     if (grouped) {
       k_query_resolve_best<<<1, 32, held_bytes, st>>>(dq, drow_cnt, drow_off, rows, (int)std::min<size_t>(rows_cap, 0x7fffffff), nq,
                                                       n, dk, th_dist, check_ori, any_point_blocks, dfmp, dfobs, dheld, held_in_smem,
                                                       dacc_idx, dacc_bin, misc + 2, misc, (long long)rows_cap);
     } else {
-      k_query_resolve_cta<<<1, 1024, held_bytes, st>>>(dq, drow_cnt, drow_off, rows, nq, n, dk, th_dist, check_ori,
-                                                       any_point_blocks, dfmp, dfobs, dheld, held_in_smem, dacc_idx, dacc_bin,
-                                                       misc + 2, misc, (long long)rows_cap);
+      k_query_resolve_cta<<<segs.n, 1024, held_bytes, st>>>(dq, drow_cnt, drow_off, rows, segs, n, dk, th_dist, check_ori,
+                                                            any_point_blocks, dfmp, dfobs, dheld, held_in_smem, dacc_idx,
+                                                            dacc_bin, misc + 2, misc + 8, misc + 40, misc, (long long)rows_cap);
+      if (segs.n > 1) {
+        k_query_finish<<<1, 32, 0, st>>>(segs, check_ori, dacc_idx, dacc_bin, misc + 8, misc + 40, dfmp, misc + 2);
+        m->launches++;
+      }
     }
     m->launches += 2;
     // the outputs are adjacent on the device only in part: two small copies into one pinned block, one synchronisation
