@@ -236,7 +236,10 @@ OT_DEV void ot_key_pass(const uint32_t* keys, uint16_t* knode, int M, const OtSc
 #pragma unroll
     for (int u = 0; u < 4; ++u) v[u] = (k0 + u * T < M) ? knode[k0 + u * T] : 0u;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) slot[u] = mv[4 * (int)(v[u] & OT_POS_MASK) + (int)(v[u] >> 14)];
+    // (lanes past the last key must not follow the table: their label 0 may name a root that holds no key, whose entry
+    // was never written - an arbitrary slot would index the node array out of bounds)
+    for (int u = 0; u < 4; ++u)
+      slot[u] = (k0 + u * T < M) ? mv[4 * (int)(v[u] & OT_POS_MASK) + (int)(v[u] >> 14)] : 0;
     if (count_next) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {

@@ -71,6 +71,23 @@ def test_low_texture_uses_min_threshold(O):
     _assert_same_features(k, d, k_ref, d_ref, "low texture")
 
 
+def test_keypoints_only_in_the_right_half(O):
+    """Regression (found by tools/dev/fuzz_parity.py under compute-sanitizer): when the LEFT octree roots of a level hold no
+    key, lanes past the last key of k_octree's key pass followed label 0 into a move-table entry nobody had written and
+    indexed the node array with whatever shared memory held.  Texture in the right third only, on a wide frame (four roots)."""
+    w, h = 1241, 376
+    rng = np.random.default_rng(17)
+    img = (128 + rng.integers(-5, 6, size=(h, w))).astype(np.uint8)
+    img[:, 2 * w // 3:] = textured(w, h, 4)[:, 2 * w // 3:]
+    ref = O.extractor("port", nfeatures=1733)
+    k_ref, d_ref, _ = ref.extract(img)
+    ex = _gpu(1733, (w, h), max_batch=3)
+    for _ in range(3):  # shared memory of earlier launches is what the stray index used to come from
+        k, d = ex(img)
+        _assert_same_features(k, d, k_ref, d_ref, "right half only")
+    assert len(k_ref) > 100
+
+
 def test_constant_image_gives_no_keypoints():
     k, d = _gpu()(np.full((480, 640), 77, dtype=np.uint8))
     assert len(k) == 0 and d.shape == (0, 32)
